@@ -1,0 +1,186 @@
+/* ofdft_b200.h -- C ABI of the B200-native (sm_100a) Monte-Carlo energy-estimator hot path.
+ *
+ * The reference (ChemAI-Lab/ofdft_nflows) is pure Python/JAX and has no FFI; the "interface" each
+ * entry point replaces is therefore a Python call signature, cited per function below
+ * (paths relative to the reference checkout).  A JAX host binds these through jax.ffi custom calls
+ * wrapped in jax.custom_vjp; the in-repo host mirror binds them with ctypes.
+ *
+ * Conventions (all entry points):
+ *   - plain C: device pointers + PODs only; `stream` is a cudaStream_t passed as void*;
+ *   - asynchronous on `stream`; never allocates, never synchronises, never owns memory;
+ *     scratch is caller-provided and sized by the companion *_scratch_bytes();
+ *   - returns 0 on success, a positive cudaError_t from the launch, or a negative OFDFT_E* code;
+ *   - re-entrant / thread-safe (no mutable global state);
+ *   - all floating-point buffers are float32 unless stated; energy sums are float64.
+ *
+ * Flat parameter vector `theta` (key-sorted ravel_pytree order of the Flax pytree):
+ *   [last_layer.bias(n_out) | last_layer.kernel(H_L*n_out) | layers_0.bias(H) | layers_0.kernel(I*H) |
+ *    layers_1.bias(H) | layers_1.kernel(H*H) | ...],  kernels (in,out) row-major.
+ *   GNN field: I = 2 + n_types, input order [t, r, onehot]  (ofdft_normflows/equiv_flows.py:51)
+ *   MLP field: I = 1 + d,       input order [t, x]          (ofdft_normflows/cn_flows.py:133-134)
+ *
+ * State rows ("trajectories"), row-major: 3-D [x0 x1 x2 | logp | s0 s1 s2], 1-D [x | logp | s]
+ *   (ofdft_normflows/utils.py:98-99,133-134).
+ */
+#ifndef OFDFT_B200_H_
+#define OFDFT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OFDFT_B200_ABI_VERSION 1
+
+/* error codes (negative) */
+#define OFDFT_EINVAL      (-1)   /* bad argument (null pointer, size <= 0, ...)           */
+#define OFDFT_EUNSUPPORTED (-2)  /* shape outside what the kernels are instantiated for   */
+#define OFDFT_ESCRATCH    (-3)   /* scratch buffer too small                               */
+
+/* jets carried per trajectory */
+#define OFDFT_JETS_X      1      /* x only                  (second-half rows: only xp is used, H20_...py:154-156) */
+#define OFDFT_JETS_XLOGP  2      /* x, logp                 (neural_ode, jax_ode.py:9-49)                           */
+#define OFDFT_JETS_FULL   3      /* x, logp, score          (neural_ode_score, jax_ode.py:51-110)                   */
+
+/* functional selectors (lower-cased string keys of functionals.py factories) */
+enum {
+  OFDFT_KIN_NONE = 0, OFDFT_KIN_TF = 1, OFDFT_KIN_W = 2, OFDFT_KIN_TF_W = 3,   /* functionals.py:21-43   */
+  OFDFT_KIN_TF1D = 4, OFDFT_KIN_TFW_1D = 5
+};
+enum {
+  OFDFT_HART_NONE = 0, OFDFT_HART_COULOMB = 1,      /* 'hartree'    functionals.py:463-486 (eps per component) */
+  OFDFT_HART_SOFTC = 2,                             /* 'softc'      functionals.py:439-461 (1-D, no 1/2)        */
+  OFDFT_HART_MT = 3                                 /* 'hartree_mt' functionals.py:489-496                      */
+};
+enum {
+  OFDFT_NUC_NONE = 0, OFDFT_NUC_POINT = 1,          /* 'nuclei_potential' functionals.py:556-587 (eps on r)    */
+  OFDFT_NUC_HGH = 2,                                /* 'hgh' functionals.py:617-655 (H parameters for all)     */
+  OFDFT_NUC_ATTRACTION = 3,                         /* 'attraction' functionals.py:523-549 (1-D)               */
+  OFDFT_NUC_HGH_SPECIES = 4                         /* NON-reference: H/O tables by Z (hgh_pseudopotentials.py:8-11) */
+};
+enum {
+  OFDFT_X_NONE = 0, OFDFT_X_LDA = 1                 /* 'lda' functionals.py:391-417 ((3/pi)**1/3 as coded)     */
+};
+
+/* energy-term slots of the float64 sums written by ofdft_functionals_fwd_bwd (F_values, H20_...py:43-49) */
+#define OFDFT_TERM_KIN  0
+#define OFDFT_TERM_NUC  1
+#define OFDFT_TERM_HART 2
+#define OFDFT_TERM_X    3
+#define OFDFT_TERM_C    4
+#define OFDFT_N_TERMS   8
+
+typedef struct {
+  int32_t d;             /* 3 or 1                                                           */
+  int32_t kin, hart, nuc, x;
+  int32_t n_nuclei;      /* 3-D: rows of coords/z                                            */
+  float   Ne;
+  float   R, Z_alpha, Z_beta;     /* 1-D attraction (LiH.py:218-223)                         */
+} ofdft_energy_spec;
+
+/* ---- library ---------------------------------------------------------------------------------- */
+int ofdft_b200_abi_version(void);
+/* 0 if a device of compute capability 10.x is current, negative otherwise */
+int ofdft_b200_check_device(void);
+const char* ofdft_b200_strerror(int code);
+
+/* ---- 3-D equivariant GNN flow: fused fixed-step (RK4) integrator -------------------------------
+ * Replaces neural_ode / neural_ode_score (ofdft_normflows/jax_ode.py:9-49, 51-110) evaluated on
+ * Gen_EqvFlow (ofdft_normflows/equiv_flows.py:108-127) with features = (64, 64).
+ *   theta   : 4289 + 64*(2+n_types) floats          nuclei : (Na,3)     onehot : (Na,n_types)
+ *   y_in    : (B, in_stride)  rows [x | logp | s]; columns beyond what the row's jets need are ignored
+ *   y_out   : (B, out_stride) same layout at t1 (only the carried columns are written)
+ *   rows [0, n_a) carry jets_a, rows [n_a, B) carry jets_b (one launch, heavy tiles first)
+ *   ckpt    : NULL, or ofdft_cnf_gnn_ckpt_bytes(B, n_steps) bytes receiving every RK4 stage state
+ *             (x, s) for the backward pass
+ *   y0sign  : +1 (bool_neg=False) or -1 (bool_neg=True): t' = y0*t, output scaled by y0
+ *   scratch : ofdft_cnf_gnn_fwd_scratch_bytes() bytes
+ */
+size_t ofdft_cnf_gnn_ckpt_bytes(int64_t B, int32_t n_steps);
+size_t ofdft_cnf_gnn_fwd_scratch_bytes(void);
+int ofdft_cnf_gnn_fwd(void* stream, const float* theta, const float* nuclei, const float* onehot,
+                      const float* y_in, float* y_out, float* ckpt, void* scratch, size_t scratch_bytes,
+                      int64_t B, int64_t n_a, int32_t jets_a, int32_t jets_b,
+                      int32_t in_stride, int32_t out_stride,
+                      int32_t Na, int32_t n_types, int32_t n_steps, float t0, float t1, float y0sign);
+
+/* Discrete adjoint of ofdft_cnf_gnn_fwd (replaces the odeint custom_vjp the reference reaches through
+ * jax.value_and_grad, H20_mol_ofdft_min_equiv_flows.py:177-178).
+ *   ybar1     : (B, bar_stride) cotangent of y(t1), rows [xbar | logpbar | sbar]
+ *   theta_bar : n_theta floats, OVERWRITTEN with d<ybar1, y(t1)>/d theta
+ *   ybar0     : NULL or (B, bar_stride) cotangent of y(t0)
+ *   scratch   : ofdft_cnf_gnn_bwd_scratch_bytes(n_types) bytes
+ */
+size_t ofdft_cnf_gnn_bwd_scratch_bytes(int32_t n_types);
+int ofdft_cnf_gnn_bwd(void* stream, const float* theta, const float* nuclei, const float* onehot,
+                      const float* ckpt, const float* ybar1, float* theta_bar, float* ybar0,
+                      void* scratch, size_t scratch_bytes,
+                      int64_t B, int64_t n_a, int32_t jets_a, int32_t jets_b, int32_t bar_stride,
+                      int32_t Na, int32_t n_types, int32_t n_steps, float t0, float t1, float y0sign);
+
+/* One evaluation of the vector field, f.apply(params, t, states) (equiv_flows.py:124-127) or the
+ * score-augmented right-hand side _evol_fn_i (jax_ode.py:80-94):  dy (B, stride) <- d/dt y. */
+int ofdft_cnf_gnn_rhs(void* stream, const float* theta, const float* nuclei, const float* onehot,
+                      const float* y, float* dy, void* scratch, size_t scratch_bytes,
+                      int64_t B, int32_t jets, int32_t stride, int32_t Na, int32_t n_types, float t, float y0sign);
+
+/* ---- 1-D tanh-MLP flow (Gen_CNFSimpleMLP, cn_flows.py:166-182; LiH.py:64-65 uses (512,512,512)) --
+ * Same contract as the GNN entry points with d = 1: rows [x | logp | s]; theta per the layout above
+ * with I = 2.  Supported: n_layers in [2,4], hidden width H multiple of 64 up to 512.
+ */
+size_t ofdft_cnf_mlp1d_ckpt_bytes(int64_t B, int32_t n_steps);
+size_t ofdft_cnf_mlp1d_scratch_bytes(int64_t B, int32_t H, int32_t n_layers);
+int ofdft_cnf_mlp1d_fwd(void* stream, const float* theta, const float* y_in, float* y_out, float* ckpt,
+                        void* scratch, size_t scratch_bytes, int64_t B, int32_t jets, int32_t stride,
+                        int32_t H, int32_t n_layers, int32_t n_steps, float t0, float t1, float y0sign);
+int ofdft_cnf_mlp1d_bwd(void* stream, const float* theta, const float* ckpt, const float* ybar1,
+                        float* theta_bar, float* ybar0, void* scratch, size_t scratch_bytes,
+                        int64_t B, int32_t jets, int32_t stride, int32_t H, int32_t n_layers,
+                        int32_t n_steps, float t0, float t1, float y0sign);
+
+/* ---- functionals: fused per-term reductions + cotangents ----------------------------------------
+ * Replaces the functional calls + jnp.mean of `loss` (H20_mol_ofdft_min_equiv_flows.py:150-173,
+ * LiH.py:118-138) and their VJP.
+ *   y1     : (2*bs, stride) state at t1; rows [0,bs) = x/logp/score, rows [bs,2bs) supply xp
+ *   coords : (n_nuclei,3), z : (n_nuclei)  (mol_info, H20_...py:76); HOST pointers (static molecule
+ *            tables -- XLA attributes under jax.ffi -- copied into the launch arguments; n_nuclei <= 64);
+ *            ignored when d == 1
+ *   sums   : OFDFT_N_TERMS float64: per-term MEANS [kin, vnuc, hart, x, c, total, 0, 0]
+ *   ybar1  : NULL or (2*bs, stride): d(total mean)/d y1 (all columns written)
+ *   scratch: ofdft_functionals_scratch_bytes(bs)
+ */
+size_t ofdft_functionals_scratch_bytes(int64_t bs);
+int ofdft_functionals_fwd_bwd(void* stream, const ofdft_energy_spec* spec, const float* coords, const float* z,
+                              const float* y1, int32_t stride, int64_t bs, double* sums, float* ybar1,
+                              void* scratch, size_t scratch_bytes);
+
+/* Per-sample integrands (bs,1) of the string-keyed factories _kinetic/_hartree/_nuclear/
+ * _exchange_correlation (functionals.py:21-43,164-183,425-436,504-521):
+ *   e[term*bs + i] for term in {KIN, NUC, HART, X}; inputs as ofdft_functionals_fwd_bwd. */
+int ofdft_functionals_integrands(void* stream, const ofdft_energy_spec* spec, const float* coords, const float* z,
+                                 const float* y1, int32_t stride, int64_t bs, float* e);
+
+/* ---- all-pairs Hartree (north-star generalisation of the paired estimator) ----------------------
+ * sum_{i<n, j<m} w / sqrt(|x_i - xp_j|^2 + d*eps)   (kind COULOMB, d = 3, w = 0.5 Ne^2)
+ * sum_{i,j}      w / sqrt(1 + (x_i - xp_j)^2)       (kind SOFTC,   d = 1, w = Ne^2)
+ *   x (n, x_stride), xp (m, x_stride): first d columns are coordinates
+ *   esum   : 1 float64, the pair MEAN  (1/(n*m)) * sum
+ *   xbar   : NULL or (n, d) d(esum)/dx ;  xpbar : NULL or (m, d)
+ *   scratch: ofdft_hartree_allpairs_scratch_bytes(n, m)
+ */
+size_t ofdft_hartree_allpairs_scratch_bytes(int64_t n, int64_t m);
+int ofdft_hartree_allpairs(void* stream, int32_t kind, int32_t d, float Ne, const float* x, const float* xp,
+                           int32_t x_stride, int64_t n, int64_t m, double* esum, float* xbar, float* xpbar,
+                           void* scratch, size_t scratch_bytes);
+
+/* FP32 FFMA / SFU peak microbenchmarks (roofline denominators; bench.py).  Run `iters` dependent
+ * rounds on every SM; return via *out the number of FFMA (or MUFU.RSQ) lane-operations issued. */
+int ofdft_microbench_ffma(void* stream, float* sink, int32_t iters, double* ops_out);
+int ofdft_microbench_sfu(void* stream, float* sink, int32_t iters, double* ops_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OFDFT_B200_H_ */

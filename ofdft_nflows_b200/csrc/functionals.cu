@@ -1,0 +1,460 @@
+// functionals.cu -- fused OF-DFT functional reductions + cotangents, per-sample integrands, and the tiled
+// all-pairs Hartree kernel.  Reference: ofdft_normflows/functionals.py (per-function lines cited below) and the
+// `loss` closures H20_mol_ofdft_min_equiv_flows.py:150-173 / LiH.py:118-138.
+// The local reductions are HBM-bound (read x, xp, logp, s; write cotangents); the all-pairs kernel is bound by the
+// FP32/SFU pipes (12 B per point amortised over a 256-point shared-memory tile).
+#include "common.cuh"
+
+namespace ofdft {
+
+constexpr int kFnThreads = 256;
+constexpr int kFnMaxNuc = 64;
+
+struct FnArgs {
+  ofdft_energy_spec spec;
+  float coords[kFnMaxNuc * 3];
+  float z[kFnMaxNuc];
+  const float* y1; int stride; long long bs;
+  double* partial;    // [grid][5]
+  float* ybar1;       // (2bs, stride) or null
+  float* integrands;  // (4, bs) or null
+};
+
+// HGH local pseudopotential parameters (ofdft_normflows/hgh_pseudopotentials.py:8-11)
+struct Hgh { float zion, rloc, c1, c2, c3, c4; };
+__device__ __forceinline__ Hgh hgh_H() { return {1.f, 0.2f, -4.180237f, 0.725075f, 0.f, 0.f}; }
+__device__ __forceinline__ Hgh hgh_O() { return {6.f, 0.247621f, -16.580318f, 2.395701f, 0.f, 0.f}; }
+
+struct Terms { float kin, nuc, hart, x; float gx[3], gxp[3], gl, gs[3]; };
+
+// one first-half row i with its partner row bs+i: integrands and their derivatives (un-normalised)
+__device__ __forceinline__ Terms eval_row(const FnArgs& a, long long i) {
+  const ofdft_energy_spec& sp = a.spec;
+  const int d = sp.d;
+  const float Ne = sp.Ne;
+  const float* row = a.y1 + i * a.stride;
+  const float* rowp = a.y1 + (a.bs + i) * a.stride;
+  Terms t;
+  t.kin = t.nuc = t.hart = t.x = 0.f; t.gl = 0.f;
+  float x[3] = {0, 0, 0}, xp[3] = {0, 0, 0}, s[3] = {0, 0, 0};
+  for (int c = 0; c < d; ++c) { x[c] = row[c]; xp[c] = rowp[c]; s[c] = row[d + 1 + c]; }
+  const float logp = row[d];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) { t.gx[c] = 0.f; t.gxp[c] = 0.f; t.gs[c] = 0.f; }
+  // ---- kinetic (functionals.py:70-158) ----
+  const int kin = sp.kin;
+  if (kin == OFDFT_KIN_TF || kin == OFDFT_KIN_TF_W) {
+    const float cTF = 2.871234000188191f;                         // (3/10)(3 pi^2)^(2/3)
+    const float e = cTF * powf(Ne, 5.0f / 3.0f) * expf((2.0f / 3.0f) * logp);   // c Ne^{5/3} den^{2/3}
+    t.kin += e; t.gl += (2.0f / 3.0f) * e;
+  }
+  if (kin == OFDFT_KIN_TF1D || kin == OFDFT_KIN_TFW_1D) {
+    const float e = 0.41123351671205655f * Ne * Ne * Ne * expf(2.0f * logp);    // (pi^2/24) Ne^3 den^2
+    t.kin += e; t.gl += 2.0f * e;
+  }
+  if (kin == OFDFT_KIN_W || kin == OFDFT_KIN_TF_W || kin == OFDFT_KIN_TFW_1D) {
+    const float cw = 0.2f * Ne * 0.125f;                          // lambda0 Ne / 8
+    t.kin += cw * (s[0] * s[0] + s[1] * s[1] + s[2] * s[2]);
+    for (int c = 0; c < d; ++c) t.gs[c] = 2.0f * cw * s[c];
+  }
+  // ---- exchange: lda (functionals.py:391-417; (3/pi)**1/3 == 1/pi as coded) ----
+  if (sp.x == OFDFT_X_LDA) {
+    const float l = -0.75f * powf(Ne, 4.0f / 3.0f) * 0.3183098861837907f;
+    const float e = l * expf((1.0f / 3.0f) * logp);
+    t.x = e; t.gl += (1.0f / 3.0f) * e;
+  }
+  // ---- Hartree, row-paired (functionals.py:439-496) ----
+  if (sp.hart != OFDFT_HART_NONE) {
+    float df[3] = {x[0] - xp[0], x[1] - xp[1], x[2] - xp[2]};
+    float zz, w;
+    if (sp.hart == OFDFT_HART_SOFTC) { zz = 1.0f + df[0] * df[0]; w = Ne * Ne; }
+    else {
+      const float eps = sp.hart == OFDFT_HART_COULOMB ? 1e-5f : 0.f;   // eps per component inside the sum
+      zz = 0.f;
+      for (int c = 0; c < d; ++c) zz += df[c] * df[c] + eps;
+      w = 0.5f * Ne * Ne;
+    }
+    const float rs = 1.0f / sqrtf(zz);
+    t.hart = w * rs;
+    const float g = -w * rs / zz;
+    for (int c = 0; c < d; ++c) { t.gx[c] += g * df[c]; t.gxp[c] -= g * df[c]; }
+  }
+  // ---- nuclear attraction (functionals.py:523-655) ----
+  if (sp.nuc == OFDFT_NUC_ATTRACTION) {
+    const float A = x[0] + 0.5f * sp.R, B = x[0] - 0.5f * sp.R;
+    const float ia = 1.0f / sqrtf(1.0f + A * A), ib = 1.0f / sqrtf(1.0f + B * B);
+    t.nuc = Ne * (-sp.Z_alpha * ia - sp.Z_beta * ib);
+    t.gx[0] += Ne * (sp.Z_alpha * A * ia * ia * ia + sp.Z_beta * B * ib * ib * ib);
+  } else if (sp.nuc != OFDFT_NUC_NONE) {
+    float e = 0.f;
+    for (int n = 0; n < sp.n_nuclei; ++n) {
+      const float d0 = x[0] - a.coords[3 * n], d1 = x[1] - a.coords[3 * n + 1], d2 = x[2] - a.coords[3 * n + 2];
+      const float r = sqrtf(d0 * d0 + d1 * d1 + d2 * d2);
+      float dvdr;
+      if (sp.nuc == OFDFT_NUC_POINT) {
+        const float re = r + 1e-4f;                               // eps on r, not r^2
+        e -= a.z[n] / re;
+        dvdr = a.z[n] / (re * re);
+      } else {
+        const Hgh p = (sp.nuc == OFDFT_NUC_HGH_SPECIES && a.z[n] == 8.0f) ? hgh_O() : hgh_H();
+        const float rr = r / p.rloc, rr2 = rr * rr;
+        const float ex = expf(-0.5f * rr2);
+        const float er = erff(rr * 0.7071067811865476f);
+        const float poly = p.c1 + rr2 * (p.c2 + rr2 * (p.c3 + rr2 * p.c4));
+        e += (-p.zion / r) * er + ex * poly;
+        const float dpoly = rr * (2.0f * p.c2 + rr2 * (4.0f * p.c3 + rr2 * 6.0f * p.c4)) / p.rloc;
+        dvdr = p.zion / (r * r) * er - (p.zion / r) * (0.7978845608028654f / p.rloc) * ex
+               + ex * (dpoly - rr / p.rloc * poly);
+      }
+      const float g = Ne * dvdr / r;
+      t.gx[0] += g * d0; t.gx[1] += g * d1; t.gx[2] += g * d2;
+    }
+    t.nuc = Ne * e;
+  }
+  return t;
+}
+
+__global__ void __launch_bounds__(kFnThreads) functionals_kernel(const FnArgs a) {
+  const long long i = (long long)blockIdx.x * kFnThreads + threadIdx.x;
+  double acc[4] = {0, 0, 0, 0};
+  if (i < a.bs) {
+    const Terms t = eval_row(a, i);
+    acc[0] = t.kin; acc[1] = t.nuc; acc[2] = t.hart; acc[3] = t.x;
+    const int d = a.spec.d;
+    if (a.integrands) {
+      a.integrands[0 * a.bs + i] = t.kin; a.integrands[1 * a.bs + i] = t.nuc;
+      a.integrands[2 * a.bs + i] = t.hart; a.integrands[3 * a.bs + i] = t.x;
+    }
+    if (a.ybar1) {
+      const float inv = 1.0f / (float)a.bs;
+      float* o = a.ybar1 + i * a.stride;
+      float* op = a.ybar1 + (a.bs + i) * a.stride;
+      for (int c = 0; c < a.stride; ++c) { o[c] = 0.f; op[c] = 0.f; }
+      for (int c = 0; c < d; ++c) { o[c] = t.gx[c] * inv; op[c] = t.gxp[c] * inv; o[d + 1 + c] = t.gs[c] * inv; }
+      o[d] = t.gl * inv;
+    }
+  }
+  if (a.partial == nullptr) return;
+  __shared__ double red[4][kFnThreads / 32];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    double v = acc[k];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) red[k][threadIdx.x >> 5] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double v = 0.0;
+    for (int w = 0; w < kFnThreads / 32; ++w) v += red[threadIdx.x][w];
+    a.partial[(size_t)blockIdx.x * 4 + threadIdx.x] = v;
+  }
+}
+
+__global__ void functionals_final_kernel(const double* __restrict__ partial, int nblk, long long bs, double* sums) {
+  __shared__ double red[4][8];
+  const int k = threadIdx.x >> 6, l = threadIdx.x & 63;   // 256 threads: 4 terms x 64 lanes
+  double v = 0.0;
+  for (int b = l; b < nblk; b += 64) v += partial[(size_t)b * 4 + k];
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((l & 31) == 0) red[k][l >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int t = 0; t < 4; ++t) { const double m = (red[t][0] + red[t][1]) / (double)bs; sums[t] = m; tot += m; }
+    sums[OFDFT_TERM_C] = 0.0; sums[5] = tot; sums[6] = 0.0; sums[7] = 0.0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// all-pairs Hartree: E = (w/(n m)) sum_ij 1/sqrt(|x_i - xp_j|^2 + c), force on x_i
+// ------------------------------------------------------------------------------------------------
+constexpr int kHpThreads = 256;
+constexpr int kHpPts = 2;                 // i-points per thread
+constexpr int kHpTile = 256;              // j-points per shared-memory tile
+
+template <int D>
+__global__ void __launch_bounds__(kHpThreads) hartree_pairs_kernel(const float* __restrict__ x, const float* __restrict__ xp,
+                                                                  int stride, long long n, long long m, float cst,
+                                                                  int splits, double* __restrict__ epart,
+                                                                  float* __restrict__ fpart) {
+  __shared__ float4 tile[kHpTile];
+  const long long i0 = ((long long)blockIdx.x * kHpThreads + threadIdx.x) * kHpPts;
+  float xi[kHpPts][3], f[kHpPts][3], e[kHpPts];
+#pragma unroll
+  for (int p = 0; p < kHpPts; ++p) {
+    const long long i = i0 + p < n ? i0 + p : n - 1;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { xi[p][c] = c < D ? x[i * stride + c] : 0.f; f[p][c] = 0.f; }
+    e[p] = 0.f;
+  }
+  const long long per = (m + splits - 1) / splits;
+  const long long j_begin = (long long)blockIdx.y * per;
+  const long long j_end = j_begin + per < m ? j_begin + per : m;
+  double esum = 0.0;
+  for (long long jt = j_begin; jt < j_end; jt += kHpTile) {
+    __syncthreads();
+    {
+      const long long j = jt + threadIdx.x;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (j < j_end) {
+        v.x = xp[j * stride];
+        if (D == 3) { v.y = xp[j * stride + 1]; v.z = xp[j * stride + 2]; }
+        v.w = 1.0f;                           // w = 0 masks padded points
+      }
+      tile[threadIdx.x] = v;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int jj = 0; jj < kHpTile; ++jj) {
+      const float4 q = tile[jj];
+#pragma unroll
+      for (int p = 0; p < kHpPts; ++p) {
+        const float d0 = xi[p][0] - q.x;
+        float zz = fmaf(d0, d0, cst);
+        float d1 = 0.f, d2 = 0.f;
+        if (D == 3) { d1 = xi[p][1] - q.y; d2 = xi[p][2] - q.z; zz = fmaf(d1, d1, zz); zz = fmaf(d2, d2, zz); }
+        const float rs = rsqrtf(zz) * q.w;
+        e[p] += rs;
+        const float g = rs * rs * rs;         // q.w in {0,1}
+        f[p][0] = fmaf(g, d0, f[p][0]);
+        if (D == 3) { f[p][1] = fmaf(g, d1, f[p][1]); f[p][2] = fmaf(g, d2, f[p][2]); }
+      }
+    }
+    // flush the fp32 tile sums into the float64 accumulator every tile
+#pragma unroll
+    for (int p = 0; p < kHpPts; ++p) { if (i0 + p < n) esum += (double)e[p]; e[p] = 0.f; }
+  }
+#pragma unroll
+  for (int p = 0; p < kHpPts; ++p)
+    if (i0 + p < n && fpart != nullptr)
+      for (int c = 0; c < D; ++c) fpart[((size_t)blockIdx.y * n + (i0 + p)) * D + c] = f[p][c];
+  __shared__ double red[kHpThreads / 32];
+  for (int o = 16; o > 0; o >>= 1) esum += __shfl_xor_sync(0xffffffffu, esum, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = esum;
+  __syncthreads();
+  if (threadIdx.x == 0 && epart != nullptr) {
+    double v = 0.0;
+    for (int w = 0; w < kHpThreads / 32; ++w) v += red[w];
+    epart[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = v;
+  }
+}
+
+__global__ void hartree_force_reduce_kernel(const float* __restrict__ fpart, float* __restrict__ out, long long n_el,
+                                            int splits, float scale) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_el) return;
+  float s = 0.f;
+  for (int k = 0; k < splits; ++k) s += fpart[(size_t)k * n_el + i];
+  out[i] = -scale * s;     // d/dx_i of 1/sqrt(z) = -(x_i - x_j)/z^{3/2}
+}
+
+__global__ void hartree_energy_reduce_kernel(const double* __restrict__ epart, int nblk, double scale, double* out) {
+  __shared__ double red[8];
+  double v = 0.0;
+  for (int b = threadIdx.x; b < nblk; b += 256) v += epart[b];
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) { double s = 0.0; for (int w = 0; w < 8; ++w) s += red[w]; *out = s * scale; }
+}
+
+static int hp_splits(long long n, long long m) {
+  const long long blocks_i = (n + kHpThreads * kHpPts - 1) / (kHpThreads * kHpPts);
+  long long s = (592 + blocks_i - 1) / blocks_i;
+  const long long max_s = (m + kHpTile - 1) / kHpTile;
+  if (s > max_s) s = max_s;
+  if (s > 64) s = 64;
+  if (s < 1) s = 1;
+  return (int)s;
+}
+static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+// ------------------------------------------------------------------------------------------------
+// peak microbenchmarks (roofline denominators)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) microbench_ffma_kernel(float* sink, int iters) {
+  float a[16];
+  const float b = 1.0f + 1e-7f * threadIdx.x, c = 1e-9f * blockIdx.x;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = (float)i * 0.25f;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int u = 0; u < 16; ++u)
+#pragma unroll
+      for (int i = 0; i < 16; ++i) a[i] = fmaf(a[i], b, c);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += a[i];
+  if (s == 123.456f) sink[0] = s;
+}
+
+__global__ void __launch_bounds__(256) microbench_sfu_kernel(float* sink, int iters) {
+  float a[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a[i] = 1.0f + (float)i + 1e-3f * threadIdx.x;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = rsqrtf(a[i]);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += a[i];
+  if (s == 123.456f) sink[0] = s;
+}
+
+}  // namespace ofdft
+
+using namespace ofdft;
+
+extern "C" size_t ofdft_functionals_scratch_bytes(int64_t bs) {
+  const size_t nblk = (size_t)((bs + kFnThreads - 1) / kFnThreads);
+  return align256(nblk * 4 * sizeof(double));
+}
+
+static int fill_fn_args(FnArgs& a, const ofdft_energy_spec* spec, const float* coords_dev_or_host, const float* z) {
+  (void)coords_dev_or_host; (void)z;
+  if (!spec) return OFDFT_EINVAL;
+  if (spec->d != 1 && spec->d != 3) return OFDFT_EUNSUPPORTED;
+  a.spec = *spec;
+  return 0;
+}
+
+// coords / z are HOST pointers (tiny molecule tables, copied into the kernel argument block)
+static int launch_functionals(void* stream, const ofdft_energy_spec* spec, const float* coords, const float* z,
+                              const float* y1, int32_t stride, int64_t bs, double* sums, float* ybar1, float* integrands,
+                              void* scratch, size_t scratch_bytes) {
+  FnArgs a;
+  int rc = fill_fn_args(a, spec, coords, z);
+  if (rc) return rc;
+  if (!y1 || bs <= 0 || stride < 2 * spec->d + 1) return OFDFT_EINVAL;
+  const bool needs_mol = spec->d == 3 && spec->nuc != OFDFT_NUC_NONE;
+  if (needs_mol) {
+    if (!coords || !z || spec->n_nuclei < 1) return OFDFT_EINVAL;
+    if (spec->n_nuclei > kFnMaxNuc) return OFDFT_EUNSUPPORTED;
+    for (int i = 0; i < spec->n_nuclei * 3; ++i) a.coords[i] = coords[i];
+    for (int i = 0; i < spec->n_nuclei; ++i) a.z[i] = z[i];
+  }
+  a.y1 = y1; a.stride = stride; a.bs = bs; a.ybar1 = ybar1; a.integrands = integrands;
+  const int nblk = (int)((bs + kFnThreads - 1) / kFnThreads);
+  a.partial = nullptr;
+  if (sums) {
+    if (!scratch) return OFDFT_EINVAL;
+    if (scratch_bytes < ofdft_functionals_scratch_bytes(bs)) return OFDFT_ESCRATCH;
+    a.partial = (double*)scratch;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  functionals_kernel<<<nblk, kFnThreads, 0, st>>>(a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return (int)e;
+  if (sums) {
+    functionals_final_kernel<<<1, 256, 0, st>>>(a.partial, nblk, bs, sums);
+    e = cudaGetLastError();
+  }
+  return (int)e;
+}
+
+extern "C" int ofdft_functionals_fwd_bwd(void* stream, const ofdft_energy_spec* spec, const float* coords, const float* z,
+                                         const float* y1, int32_t stride, int64_t bs, double* sums, float* ybar1,
+                                         void* scratch, size_t scratch_bytes) {
+  if (!sums) return OFDFT_EINVAL;
+  return launch_functionals(stream, spec, coords, z, y1, stride, bs, sums, ybar1, nullptr, scratch, scratch_bytes);
+}
+
+extern "C" int ofdft_functionals_integrands(void* stream, const ofdft_energy_spec* spec, const float* coords, const float* z,
+                                            const float* y1, int32_t stride, int64_t bs, float* e) {
+  if (!e) return OFDFT_EINVAL;
+  return launch_functionals(stream, spec, coords, z, y1, stride, bs, nullptr, nullptr, e, nullptr, 0);
+}
+
+extern "C" size_t ofdft_hartree_allpairs_scratch_bytes(int64_t n, int64_t m) {
+  if (n <= 0 || m <= 0) return 256;
+  const size_t s1 = (size_t)hp_splits(n, m), s2 = (size_t)hp_splits(m, n);
+  const size_t blocks1 = (size_t)((n + kHpThreads * kHpPts - 1) / (kHpThreads * kHpPts));
+  const size_t f1 = s1 * (size_t)n * 3 * sizeof(float), f2 = s2 * (size_t)m * 3 * sizeof(float);
+  return align256(s1 * blocks1 * sizeof(double)) + align256(f1 > f2 ? f1 : f2);
+}
+
+extern "C" int ofdft_hartree_allpairs(void* stream, int32_t kind, int32_t d, float Ne, const float* x, const float* xp,
+                                      int32_t x_stride, int64_t n, int64_t m, double* esum, float* xbar, float* xpbar,
+                                      void* scratch, size_t scratch_bytes) {
+  if (!x || !xp || !esum || !scratch || n <= 0 || m <= 0 || x_stride < d) return OFDFT_EINVAL;
+  float cst, w;
+  if (kind == OFDFT_HART_COULOMB && d == 3) { cst = 3e-5f; w = 0.5f * Ne * Ne; }
+  else if (kind == OFDFT_HART_SOFTC && d == 1) { cst = 1.0f; w = Ne * Ne; }
+  else return OFDFT_EUNSUPPORTED;
+  if (scratch_bytes < ofdft_hartree_allpairs_scratch_bytes(n, m)) return OFDFT_ESCRATCH;
+  cudaStream_t st = (cudaStream_t)stream;
+  const double scale = (double)w / ((double)n * (double)m);
+  for (int pass = 0; pass < 2; ++pass) {
+    const float* a = pass == 0 ? x : xp;
+    const float* b = pass == 0 ? xp : x;
+    const long long na = pass == 0 ? n : m, nb = pass == 0 ? m : n;
+    float* out = pass == 0 ? xbar : xpbar;
+    if (pass == 1 && out == nullptr) break;
+    const int splits = hp_splits(na, nb);
+    const unsigned blocks = (unsigned)((na + kHpThreads * kHpPts - 1) / (kHpThreads * kHpPts));
+    double* epart = (double*)scratch;
+    float* fpart = (float*)((char*)scratch + align256((size_t)hp_splits(n, m) *
+                            (size_t)((n + kHpThreads * kHpPts - 1) / (kHpThreads * kHpPts)) * sizeof(double)));
+    dim3 grid(blocks, (unsigned)splits);
+    double* ep = pass == 0 ? epart : nullptr;
+    float* fp = out ? fpart : nullptr;
+    if (d == 3) hartree_pairs_kernel<3><<<grid, kHpThreads, 0, st>>>(a, b, x_stride, na, nb, cst, splits, ep, fp);
+    else hartree_pairs_kernel<1><<<grid, kHpThreads, 0, st>>>(a, b, x_stride, na, nb, cst, splits, ep, fp);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    if (pass == 0) {
+      hartree_energy_reduce_kernel<<<1, 256, 0, st>>>(epart, (int)(blocks * splits), scale, esum);
+      e = cudaGetLastError();
+      if (e != cudaSuccess) return (int)e;
+    }
+    if (out) {
+      const long long n_el = na * d;
+      hartree_force_reduce_kernel<<<(unsigned)((n_el + 255) / 256), 256, 0, st>>>(fpart, out, n_el, splits, (float)scale);
+      e = cudaGetLastError();
+      if (e != cudaSuccess) return (int)e;
+    }
+  }
+  return 0;
+}
+
+extern "C" int ofdft_microbench_ffma(void* stream, float* sink, int32_t iters, double* ops_out) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = sms * 8;
+  microbench_ffma_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(sink, iters);
+  if (ops_out) *ops_out = (double)grid * 256.0 * (double)iters * 256.0;
+  return (int)cudaGetLastError();
+}
+
+extern "C" int ofdft_microbench_sfu(void* stream, float* sink, int32_t iters, double* ops_out) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = sms * 8;
+  microbench_sfu_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(sink, iters);
+  if (ops_out) *ops_out = (double)grid * 256.0 * (double)iters * 64.0;
+  return (int)cudaGetLastError();
+}
+
+extern "C" int ofdft_b200_abi_version(void) { return OFDFT_B200_ABI_VERSION; }
+
+extern "C" int ofdft_b200_check_device(void) {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return OFDFT_EUNSUPPORTED;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return OFDFT_EUNSUPPORTED;
+  return major == 10 ? 0 : OFDFT_EUNSUPPORTED;
+}
+
+extern "C" const char* ofdft_b200_strerror(int code) {
+  if (code == 0) return "ok";
+  if (code == OFDFT_EINVAL) return "ofdft_b200: invalid argument";
+  if (code == OFDFT_EUNSUPPORTED) return "ofdft_b200: unsupported shape/configuration";
+  if (code == OFDFT_ESCRATCH) return "ofdft_b200: scratch buffer too small";
+  if (code > 0) return cudaGetErrorString((cudaError_t)code);
+  return "ofdft_b200: unknown error";
+}

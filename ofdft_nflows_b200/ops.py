@@ -1,0 +1,202 @@
+"""Device-level operators: thin wrappers that pass torch CUDA buffers and the current stream to the C ABI.
+
+torch is used for device memory, streams and (elsewhere) torch.distributed only; every arithmetic
+operation of the hot path happens inside libofdft_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import EnergySpecC
+
+JETS_X, JETS_XLOGP, JETS_FULL = 1, 2, 3
+
+KIN = {"": 0, "none": 0, "tf": 1, "thomas_fermi": 1, "w": 2, "weizsacker": 2, "w1d": 2, "weizsacker1d": 2,
+       "tf-w": 3, "thomas_fermi_weizsacker": 3, "tf1d": 4, "thomas_fermi_1d": 4,
+       "tfw_1d": 5, "thomas_fermi_weizsacker_1d": 5}
+HART = {"": 0, "none": 0, "hartree": 1, "hartree_potential": 1, "softc": 2, "soft_coulomb": 2, "hartree_mt": 3}
+NUC = {"": 0, "none": 0, "nuclei_potential": 1, "nuclei": 1, "hgh": 2, "nuclei_potential_hgh": 2,
+       "attraction": 3, "attr": 3, "hgh_species": 4}
+XC_X = {"": 0, "none": 0, "lda": 1, "local_density_approximation": 1}
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError("ofdft_nflows_b200: tensors must live on a CUDA device (no CPU fallback)")
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        t = t.to(torch.float32).contiguous()
+    return t
+
+
+def _cols(jets: int, d: int = 3) -> int:
+    return {1: d, 2: d + 1, 3: 2 * d + 1}[jets]
+
+
+def gnn_theta_size(n_types: int) -> int:
+    return 4289 + 64 * (2 + n_types)
+
+
+def gnn_fwd(theta, nuclei, onehot, y_in, n_a: int, jets_a: int, jets_b: int, n_steps: int,
+            t0: float, t1: float, y0sign: float, want_ckpt: bool = False, out: Optional[torch.Tensor] = None
+            ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """ofdft_cnf_gnn_fwd: integrate rows [0,n_a) with jets_a and rows [n_a,B) with jets_b."""
+    lib = _lib.load()
+    theta, nuclei, onehot, y_in = _f32c(theta), _f32c(nuclei), _f32c(onehot), _f32c(y_in)
+    B, stride = y_in.shape
+    Na, n_types = onehot.shape
+    if theta.numel() != gnn_theta_size(n_types):
+        raise ValueError(f"theta has {theta.numel()} entries, expected {gnn_theta_size(n_types)} (features must be (64, 64))")
+    y_out = out if out is not None else torch.zeros_like(y_in)
+    ckpt = None
+    if want_ckpt:
+        ckpt = torch.empty(lib.ofdft_cnf_gnn_ckpt_bytes(B, n_steps) // 4, dtype=torch.float32, device=y_in.device)
+    sb = lib.ofdft_cnf_gnn_fwd_scratch_bytes()
+    scratch = torch.empty(sb, dtype=torch.uint8, device=y_in.device)
+    _lib.check(lib.ofdft_cnf_gnn_fwd(_stream(), _ptr(theta), _ptr(nuclei), _ptr(onehot), _ptr(y_in), _ptr(y_out),
+                                     _ptr(ckpt), _ptr(scratch), sb, B, n_a, jets_a, jets_b, stride, y_out.shape[1],
+                                     Na, n_types, n_steps, t0, t1, y0sign), "ofdft_cnf_gnn_fwd")
+    return y_out, ckpt
+
+
+def gnn_bwd(theta, nuclei, onehot, ckpt, ybar1, n_a: int, jets_a: int, jets_b: int, n_steps: int,
+            t0: float, t1: float, y0sign: float, want_ybar0: bool = False):
+    """ofdft_cnf_gnn_bwd: discrete adjoint; returns (theta_bar, ybar0 or None)."""
+    lib = _lib.load()
+    theta, nuclei, onehot, ybar1 = _f32c(theta), _f32c(nuclei), _f32c(onehot), _f32c(ybar1)
+    B, stride = ybar1.shape
+    Na, n_types = onehot.shape
+    theta_bar = torch.empty_like(theta)
+    ybar0 = torch.zeros_like(ybar1) if want_ybar0 else None
+    sb = lib.ofdft_cnf_gnn_bwd_scratch_bytes(n_types)
+    scratch = torch.empty(sb, dtype=torch.uint8, device=ybar1.device)
+    _lib.check(lib.ofdft_cnf_gnn_bwd(_stream(), _ptr(theta), _ptr(nuclei), _ptr(onehot), _ptr(ckpt), _ptr(ybar1),
+                                     _ptr(theta_bar), _ptr(ybar0), _ptr(scratch), sb, B, n_a, jets_a, jets_b, stride,
+                                     Na, n_types, n_steps, t0, t1, y0sign), "ofdft_cnf_gnn_bwd")
+    return theta_bar, ybar0
+
+
+def gnn_rhs(theta, nuclei, onehot, y, jets: int, t: float, y0sign: float) -> torch.Tensor:
+    """ofdft_cnf_gnn_rhs: one evaluation of d/dt [x, logp, (score)]."""
+    lib = _lib.load()
+    theta, nuclei, onehot, y = _f32c(theta), _f32c(nuclei), _f32c(onehot), _f32c(y)
+    B, stride = y.shape
+    Na, n_types = onehot.shape
+    dy = torch.zeros_like(y)
+    sb = lib.ofdft_cnf_gnn_fwd_scratch_bytes()
+    scratch = torch.empty(sb, dtype=torch.uint8, device=y.device)
+    _lib.check(lib.ofdft_cnf_gnn_rhs(_stream(), _ptr(theta), _ptr(nuclei), _ptr(onehot), _ptr(y), _ptr(dy),
+                                     _ptr(scratch), sb, B, jets, stride, Na, n_types, t, y0sign), "ofdft_cnf_gnn_rhs")
+    return dy
+
+
+@dataclass
+class EnergySpec:
+    """Functional selection of one driver run (argparse names of the reference drivers,
+    H20_mol_ofdft_min_equiv_flows.py:225-249, LiH.py:211-223)."""
+    Ne: float
+    d: int = 3
+    kin: str = "tf-w"
+    hart: str = "hartree"
+    nuc: str = "nuclei_potential"
+    x: str = "lda"
+    coords: Optional[object] = None   # (Na,3) host array (bohr)
+    z: Optional[object] = None        # (Na,)
+    R: float = 0.0
+    Z_alpha: float = 0.0
+    Z_beta: float = 0.0
+
+    def to_c(self):
+        import numpy as np
+        try:
+            kin, hart, nuc, x = KIN[self.kin.lower()], HART[self.hart.lower()], NUC[self.nuc.lower()], XC_X[self.x.lower()]
+        except KeyError as e:
+            raise NotImplementedError(f"functional {e} is not implemented by the CUDA path") from None
+        n = 0
+        coords = z = None
+        if self.d == 3 and nuc != 0:
+            coords = np.ascontiguousarray(np.asarray(self.coords, dtype=np.float32).reshape(-1, 3))
+            z = np.ascontiguousarray(np.asarray(self.z, dtype=np.float32).reshape(-1))
+            n = coords.shape[0]
+        spec = EnergySpecC(self.d, kin, hart, nuc, x, n, float(self.Ne), float(self.R), float(self.Z_alpha), float(self.Z_beta))
+        return spec, coords, z
+
+
+def _host_ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+def functionals_fwd_bwd(spec: EnergySpec, y1: torch.Tensor, want_bar: bool = True):
+    """ofdft_functionals_fwd_bwd: returns (sums float64[8] on device: means kin, vnuc, hart, x, c, total; ybar1)."""
+    lib = _lib.load()
+    y1 = _f32c(y1)
+    B, stride = y1.shape
+    bs = B // 2
+    cs, coords, z = spec.to_c()
+    sums = torch.empty(8, dtype=torch.float64, device=y1.device)
+    ybar1 = torch.empty_like(y1) if want_bar else None
+    sb = lib.ofdft_functionals_scratch_bytes(bs)
+    scratch = torch.empty(sb, dtype=torch.uint8, device=y1.device)
+    _lib.check(lib.ofdft_functionals_fwd_bwd(_stream(), C.byref(cs), _host_ptr(coords), _host_ptr(z), _ptr(y1), stride,
+                                             bs, _ptr(sums), _ptr(ybar1), _ptr(scratch), sb), "ofdft_functionals_fwd_bwd")
+    return sums, ybar1
+
+
+def functionals_integrands(spec: EnergySpec, y1: torch.Tensor) -> torch.Tensor:
+    """ofdft_functionals_integrands: (4, bs) per-sample integrands [kin, vnuc, hart, x]."""
+    lib = _lib.load()
+    y1 = _f32c(y1)
+    B, stride = y1.shape
+    bs = B // 2
+    cs, coords, z = spec.to_c()
+    e = torch.empty((4, bs), dtype=torch.float32, device=y1.device)
+    _lib.check(lib.ofdft_functionals_integrands(_stream(), C.byref(cs), _host_ptr(coords), _host_ptr(z), _ptr(y1), stride,
+                                                bs, _ptr(e)), "ofdft_functionals_integrands")
+    return e
+
+
+def hartree_allpairs(x: torch.Tensor, xp: torch.Tensor, Ne: float, kind: str = "hartree", want_grad: bool = True):
+    """ofdft_hartree_allpairs: cross-set pair mean + gradients.  x (n, >=d), xp (m, >=d)."""
+    lib = _lib.load()
+    x, xp = _f32c(x), _f32c(xp)
+    d = 3 if HART[kind] == 1 else 1
+    if x.shape[1] != xp.shape[1]:
+        raise ValueError("x and xp must share the row stride")
+    n, m = x.shape[0], xp.shape[0]
+    esum = torch.empty(1, dtype=torch.float64, device=x.device)
+    xbar = torch.empty((n, d), dtype=torch.float32, device=x.device) if want_grad else None
+    xpbar = torch.empty((m, d), dtype=torch.float32, device=x.device) if want_grad else None
+    sb = lib.ofdft_hartree_allpairs_scratch_bytes(n, m)
+    scratch = torch.empty(sb, dtype=torch.uint8, device=x.device)
+    _lib.check(lib.ofdft_hartree_allpairs(_stream(), HART[kind], d, float(Ne), _ptr(x), _ptr(xp), x.shape[1], n, m,
+                                          _ptr(esum), _ptr(xbar), _ptr(xpbar), _ptr(scratch), sb), "ofdft_hartree_allpairs")
+    return esum, xbar, xpbar
+
+
+def microbench(kind: str, iters: int = 2000, repeat: int = 5) -> float:
+    """Measured FP32-FFMA (flop/s, 2 per FFMA) or SFU (rsqrt/s) peak of the current device."""
+    lib = _lib.load()
+    sink = torch.zeros(4, dtype=torch.float32, device="cuda")
+    ops = C.c_double(0.0)
+    fn = lib.ofdft_microbench_ffma if kind == "ffma" else lib.ofdft_microbench_sfu
+    best = float("inf")
+    for _ in range(repeat + 1):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        _lib.check(fn(_stream(), _ptr(sink), iters, C.byref(ops)), "microbench")
+        b.record()
+        b.synchronize()
+        best = min(best, a.elapsed_time(b) * 1e-3)
+    return ops.value * (2.0 if kind == "ffma" else 1.0) / best
