@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""bench.py -- training-step trajectories/s of the Monte-Carlo energy estimator (CNF fwd + energy + grad).
+
+    python bench.py --gpus 1 --steps 20 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # restated reference (JAX unavailable) on the host cores
+
+One "step" = one pass of the hot path over one synthetic batch: integrate 2*bs base samples through the CNF
+(x, log rho, score for the first half; x for the second half), evaluate the OF-DFT functionals, back-propagate
+to the flow parameters.  Unit: trajectories/s (one trajectory = one row of the ODE state).
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H = 64
+WORKLOADS = {
+    # name: (molecule, per-GPU bs, nuclear functional)       BASELINE.json configs[2] / [1] / [3] / [4]
+    "h2o": ("H2O", 65536, "hgh"),
+    "h2": ("H2", 4096, "nuclei_potential"),
+    "lih": ("LiH", 131072, "nuclei_potential"),
+    "c6h6": ("C6H6", 16384, "nuclei_potential"),
+}
+
+
+def algorithmic_flops_per_traj_eval(na: int, jets: int) -> float:
+    """Mat-mul-only 2-jet count per (trajectory, RHS evaluation): Na * [2*J*H^2 + 2*J*H + 2*H]
+    (J = jets carried: 3 = x/logp/score, 1 = x only)."""
+    return na * (2.0 * jets * H * H + 2.0 * jets * H + 2.0 * H)
+
+
+def make_problem(workload: str, bs: int, seed_offset: int = 0):
+    """Synthetic inputs of the named config: promolecular base samples + prior logp/score, LeCun-normal hidden
+    layers (zero biases) and a non-zero last layer 0.5*N(0,1/64) (the reference's zero-init
+    last layer would make the field trivial).  Uses only the package's own host-side input producers."""
+    from ofdft_nflows_b200 import utils as U
+    molname, _, nuc = WORKLOADS[workload]
+    Ne, atoms, z, coords = U.coordinates(molname)
+    onehot = U.one_hot_encode(z) if molname == "C6H6" else U.jax_one_hot(z)     # OFDFT_NF.py:73 vs H20_...py:83-84
+    mol = {"coords": coords, "z": z, "Ne": Ne, "onehot": onehot}
+    nt = onehot.shape[1]
+    rng = np.random.default_rng(4321)
+    I = 2 + nt
+    w1 = rng.standard_normal((I, H)) / math.sqrt(I)
+    w2 = rng.standard_normal((H, H)) / math.sqrt(H)
+    # keep the summed field benign for many-nucleus molecules (the displacement scales with Na)
+    w3 = 0.5 * min(1.0, 3.0 / len(z)) * rng.standard_normal((H, 1)) / math.sqrt(H)
+    # flat theta, ravel_pytree key order: last_layer.{bias,kernel}, layers_0.{bias,kernel}, layers_1.{bias,kernel}
+    theta = np.concatenate([np.zeros(1), w3.ravel(), np.zeros(H), w1.ravel(), np.zeros(H), w2.ravel()]).astype(np.float32)
+    batch = next(U.batch_generator(1234 + seed_offset, bs, U.ProMolecularDensity(z, coords)))
+    return mol, nuc, theta, batch
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU while the timed region runs."""
+
+    def __init__(self, index: int, period: float = 0.05):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
+                     "hw_power_brake_slowdown": 0x80}
+            while not self._stop_evt.is_set():
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+                time.sleep(self.period)
+        except Exception as e:   # never fail the benchmark because of the sampler
+            self.reasons.add(f"sampler_error:{type(e).__name__}")
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2.0)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def cpu_reference_step(workload: str, bs: int, threads: int):
+    """One fwd+grad step of the restated reference on the host: float64, generic nested autodiff RHS
+    (vmap(jacrev) + value_and_grad + vjp), adaptive Dopri5 rtol=atol=1e-7, reverse-mode gradient.
+    Returns (seconds, trajectories)."""
+    import torch
+    from oracle import ofdft_oracle as O, ref_torch as R
+    torch.set_num_threads(threads)
+    mol, nuc, theta, batch = make_problem(workload, bs)
+    nt = mol["onehot"].shape[1]
+    spec = O.EnergySpec(Ne=mol["Ne"], kin="tf-w", hart="hartree", nuc=nuc, x="lda", coords=mol["coords"], z=mol["z"])
+    model = R.GenEqvFlow((H, H), mol["coords"], mol["onehot"], bool_neg=True)
+    t0 = time.perf_counter()
+    R.value_and_grad_loss(model, theta.astype(np.float64), 2 + nt, (H, H), batch.astype(np.float64), spec, method="dopri5")
+    return time.perf_counter() - t0, 2 * bs
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path.  JAX/Flax are not installable in
+    this image (no wheels, no network), so this times the reference-faithful restatement oracle/ref_torch.py
+    on all host cores, on a bounded sample of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    wl = args.workload
+    # size the sample so that (steps + warmup) steps take about two minutes
+    cpu_reference_step(wl, 64, cores)                       # warm the thread pool / autograd caches
+    t_probe, n_probe = cpu_reference_step(wl, 1024, cores)
+    per_traj = t_probe / n_probe
+    budget = 120.0 / max(1, args.steps + args.warmup)
+    bs = int(max(256, min(8192, budget / per_traj / 2)))
+    for _ in range(args.warmup):
+        cpu_reference_step(wl, bs, cores)
+    times = []
+    for _ in range(args.steps):
+        t, n = cpu_reference_step(wl, bs, cores)
+        times.append(t)
+    total = sum(times)
+    value = n * args.steps / total
+    molname, full_bs, nuc = WORKLOADS[wl]
+    sample = (f"bs={bs} ({n} trajectories) of the {molname} bs={full_bs} workload per step; float64, nested-autodiff RHS, "
+              f"adaptive Dopri5 rtol=atol=1e-7, reverse-mode gradient (oracle/ref_torch.py; JAX not installable here)")
+    line = {
+        "impl": "reference", "metric": "training-step trajectories/s (CNF fwd+grad+energy)", "value": value,
+        "unit": "trajectories/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{molname} 3-D equivariant flow, TF+W / {nuc} / Hartree / LDA, bs={full_bs} per GPU "
+                               f"(CPU arm: bounded sample bs={bs})"},
+        "cpu_baseline": {"value": value, "unit": "trajectories/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "trajectories/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="h2o", choices=sorted(WORKLOADS))
+    ap.add_argument("--bs", type=int, default=0, help="per-GPU batch size (default: the workload's)")
+    ap.add_argument("--n-steps", type=int, default=16, help="RK4 steps of the fixed-step integrator")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--full-jets", action="store_true", help="carry logp/score on the second half too (reference dataflow)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from ofdft_nflows_b200 import ops
+    from ofdft_nflows_b200.equiv_flows import Gen_EqvFlow
+    from ofdft_nflows_b200.estimator import EnergyEstimator
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    n_gpus = world
+
+    molname, bs_default, nuc = WORKLOADS[args.workload]
+    bs = args.bs or bs_default
+    mol, nuc, theta_np, batch_np = make_problem(args.workload, bs, seed_offset=rank)
+    B = 2 * bs
+    na = mol["coords"].shape[0]
+    model = Gen_EqvFlow(3, (H, H), mol["coords"], mol["onehot"], bool_neg=True, device=dev)
+    spec = ops.EnergySpec(Ne=mol["Ne"], d=3, kin="tf-w", hart="hartree", nuc=nuc, x="lda", coords=mol["coords"], z=mol["z"])
+    est = EnergyEstimator(model, spec, n_steps=args.n_steps, skip_unused_jets=not args.full_jets)
+    theta = torch.as_tensor(theta_np, device=dev)
+    params = model.unravel(theta)
+    batch = torch.as_tensor(batch_np, device=dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- roofline denominator: measured FP32 FFMA peak of this device (MEASURED_PEAKS.json has no FP32 figure) ----
+    ffma_peak = ops.microbench("ffma")
+
+    # ---- device-resident timed region ----
+    for _ in range(args.warmup):
+        est.step_flat(theta, batch)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    step_ev, kern_ev = [], []
+    for _ in range(args.steps):
+        flush.fill_(1)                                           # flush L2 between timed iterations
+        timers = []
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        sums, tbar, _ = est.step_flat(theta, batch, timers=timers)
+        e.record()
+        step_ev.append((s, e)); kern_ev.append(timers)
+    barrier()
+    clocks = sampler.stop()
+    step_ms = [s.elapsed_time(e) for s, e in step_ev]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_s = total_ms.item() * 1e-3
+    value = n_gpus * B * args.steps / total_s
+    kern_ms = {}
+    for timers in kern_ev:
+        for name, s, e in timers:
+            kern_ms.setdefault(name, []).append(s.elapsed_time(e))
+    kern_avg = {k: sum(v) / len(v) for k, v in kern_ms.items()}
+
+    # ---- end to end through the public API with HOST buffers ----
+    host_batch = torch.as_tensor(batch_np).pin_memory()
+    host_sums = torch.empty(8, dtype=torch.float64).pin_memory()
+    host_grad = torch.empty(theta.numel(), dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        b = host_batch.to(dev, non_blocking=True)
+        (energy, fv), grads = est.value_and_grad(params, b)
+        host_sums.copy_(est.last_sums, non_blocking=True)
+        host_grad.copy_(model.flat_theta(grads), non_blocking=True)
+
+    for _ in range(args.warmup):
+        e2e_step()
+    barrier()
+    e2e_ev = []
+    for _ in range(args.steps):
+        flush.fill_(1)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(); e2e_step(); e.record()
+        e2e_ev.append((s, e))
+    barrier()
+    e2e_ms = torch.tensor([sum(s.elapsed_time(e) for s, e in e2e_ev)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_value = n_gpus * B * args.steps / (e2e_ms.item() * 1e-3)
+
+    # ---- roofline of the dominant kernel (the discrete-adjoint backward) ----
+    jets_b = 3 if args.full_jets else 1
+    evals = 4 * args.n_steps
+    fwd_flops = bs * evals * (algorithmic_flops_per_traj_eval(na, 3) + algorithmic_flops_per_traj_eval(na, jets_b))
+    bwd_flops = 2.0 * fwd_flops
+    bwd_s = kern_avg["gnn_bwd"] * 1e-3
+    achieved = bwd_flops / bwd_s / 1e12
+    roofline = {
+        "bound": "fp32", "kernel": "gnn_bwd_kernel", "achieved": achieved, "peak": ffma_peak / 1e12, "unit": "TFLOP/s",
+        "frac": achieved / (ffma_peak / 1e12), "traffic": None,
+        "peak_source": "ofdft_microbench_ffma measured in this run (FP32 FFMA pipe; MEASURED_PEAKS.json holds HBM/bf16 only)",
+        "algorithmic_flops_per_launch": bwd_flops, "executed_over_algorithmic": 1.5,
+        "kernel_ms": kern_avg,
+        "fwd": {"kernel": "gnn_fwd_kernel", "achieved": fwd_flops / (kern_avg["gnn_fwd"] * 1e-3) / 1e12,
+                "frac": fwd_flops / (kern_avg["gnn_fwd"] * 1e-3) / ffma_peak},
+        "step": {"algorithmic_flops": 3.0 * fwd_flops, "frac": 3.0 * fwd_flops / (total_s / args.steps) / ffma_peak},
+    }
+
+    line = None
+    if rank == 0:
+        line = {
+            "metric": "training-step trajectories/s (CNF fwd+grad+energy)", "value": value, "unit": "trajectories/s",
+            "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_s / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{molname} 3-D equivariant flow (64,64), TF+W / {nuc} / paired Hartree / LDA, "
+                                   f"bs={bs} per GPU ({B} trajectories), RK4 x{args.n_steps}",
+                       "second_half_jets": "x only (denp/scorep are unused by the reference loss)" if not args.full_jets
+                       else "full (reference dataflow)",
+                       "l2": "flushed between timed iterations (256 MiB write)", "parallelism": f"batch-sharded x{n_gpus}"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "trajectories/s", "h2d_bytes_per_step": int(host_batch.numel() * 4),
+                    "d2h_bytes_per_step": int(host_sums.numel() * 8 + host_grad.numel() * 4)},
+            "gpu_launches": 5 * args.steps,
+            "roofline": roofline,
+            "energy_terms_last_step": [float(v) for v in sums.cpu().numpy()[:6]],
+        }
+        if n_gpus == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            cbs = 2048
+            cpu_reference_step(args.workload, 64, cores)    # warm-up (thread pool, autograd caches)
+            t, n = cpu_reference_step(args.workload, cbs, cores)
+            line["cpu_baseline"] = {
+                "value": n / t, "unit": "trajectories/s", "cores": cores, "kind": "port",
+                "sample": f"bs={cbs} ({n} trajectories) of the same workload, one step; float64 nested-autodiff RHS + adaptive "
+                          f"Dopri5 1e-7 + reverse-mode gradient (oracle/ref_torch.py, torch CPU; JAX not installable here)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

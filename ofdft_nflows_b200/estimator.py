@@ -1,0 +1,111 @@
+"""Fused Monte-Carlo energy estimator: one training step's work (the path bench.py measures).
+
+``EnergyEstimator.value_and_grad(params, batch)`` is the B200 counterpart of
+``jax.value_and_grad(loss, has_aux=True)(params, batch)`` in the reference drivers
+(H20_mol_ofdft_min_equiv_flows.py:150-178, LiH.py:118-146):
+
+    forward integrator (rows [0,bs): x, logp, score + stage checkpoints; rows [bs,2bs): x only -- the reference
+    never uses denp/scorep, H20_...py:154-156)  ->  fused functional reductions + cotangents  ->  discrete adjoint.
+
+Three kernel launches + two tiny reductions on one stream; the result stays on the device until the caller reads it.
+With ``torch.distributed`` initialised, every rank integrates its shard of the batch (both halves sharded
+identically, so the paired Hartree estimator needs no coordinate exchange) and the per-term sums and the
+parameter gradient are all-reduced once.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Any, Dict, Optional, Tuple
+
+import torch
+
+from . import ops
+from .jax_ode import DEFAULT_N_STEPS
+
+
+@dataclass
+class F_values:
+    """Per-term means (reference chex dataclass, H20_mol_ofdft_min_equiv_flows.py:43-49)."""
+    energy: torch.Tensor
+    kin: torch.Tensor
+    vnuc: torch.Tensor
+    hart: torch.Tensor
+    xc: torch.Tensor
+
+
+def shard_batch(batch, rank: int, world: int):
+    """Rows of rank ``rank``: the same slice of BOTH halves, so that trajectory i and its Hartree partner i+bs land
+    on the same GPU and the paired estimator needs no coordinate exchange.
+    ``batch`` is (2*bs, w) with bs divisible by ``world``; returns (2*bs/world, w)."""
+    bs = batch.shape[0] // 2
+    if bs % world:
+        raise ValueError(f"batch size {bs} is not divisible by the world size {world}")
+    per = bs // world
+    lo, hi = rank * per, (rank + 1) * per
+    cat = torch.cat if isinstance(batch, torch.Tensor) else __import__("numpy").concatenate
+    return cat([batch[lo:hi], batch[bs + lo:bs + hi]], 0)
+
+
+class EnergyEstimator:
+    def __init__(self, model: Any, spec: ops.EnergySpec, n_steps: int = DEFAULT_N_STEPS, t0: float = 0.0, t1: float = 1.0,
+                 skip_unused_jets: bool = True, group: Optional[Any] = None):
+        self.model, self.spec, self.n_steps, self.t0, self.t1 = model, spec, int(n_steps), float(t0), float(t1)
+        # rows of the second half only supply xp: integrate them without the logp/score channels
+        self.jets_b = ops.JETS_X if skip_unused_jets else ops.JETS_FULL
+        self.group = group
+        self._is_gnn = hasattr(model, "xyz_nuclei")
+
+    def _dist(self) -> bool:
+        import torch.distributed as dist
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
+
+    def step_flat(self, theta: torch.Tensor, batch: torch.Tensor, timers: Optional[list] = None
+                  ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """(sums float64[8] = means [kin, vnuc, hart, x, c, total, 0, 0], theta_bar, y1) for the local shard,
+        all-reduced (mean over ranks) when running distributed.  ``timers``: optional list that receives
+        (kernel name, start event, end event) triples recorded on the current stream (bench.py roofline)."""
+        m = self.model
+        B = batch.shape[0]
+        bs = B // 2
+
+        def mark():
+            if timers is None:
+                return None
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            return ev
+
+        if self._is_gnn:
+            e0 = mark()
+            y1, ckpt = ops.gnn_fwd(theta, m.xyz_nuclei, m.z_one_hot, batch, bs, ops.JETS_FULL, self.jets_b, self.n_steps,
+                                   self.t0, self.t1, m.y0, want_ckpt=True)
+            e1 = mark()
+            sums, ybar1 = ops.functionals_fwd_bwd(self.spec, y1)
+            e2 = mark()
+            tbar, _ = ops.gnn_bwd(theta, m.xyz_nuclei, m.z_one_hot, ckpt, ybar1, bs, ops.JETS_FULL, self.jets_b,
+                                  self.n_steps, self.t0, self.t1, m.y0)
+            e3 = mark()
+            if timers is not None:
+                timers += [("gnn_fwd", e0, e1), ("functionals", e1, e2), ("gnn_bwd", e2, e3)]
+        else:
+            from .cn_flows import mlp_fwd, mlp_bwd
+            y1, ckpt = mlp_fwd(theta, batch, m, self.t0, self.t1, ops.JETS_FULL, self.n_steps, want_ckpt=True)
+            sums, ybar1 = ops.functionals_fwd_bwd(self.spec, y1)
+            tbar, _ = mlp_bwd(theta, ckpt, ybar1, m, self.t0, self.t1, ops.JETS_FULL, self.n_steps)
+        if self._dist():
+            import torch.distributed as dist
+            ws = dist.get_world_size(self.group)
+            # one latency-bound collective each: 8 doubles and n_theta floats (mean of equally sized shards)
+            dist.all_reduce(sums, group=self.group)
+            dist.all_reduce(tbar, group=self.group)
+            sums /= ws
+            tbar /= ws
+        return sums, tbar, y1
+
+    def value_and_grad(self, params: Dict[str, Any], batch: torch.Tensor):
+        """-> ((energy, F_values), grads) with ``grads`` shaped like ``params``."""
+        theta = self.model.flat_theta(params).detach()
+        sums, tbar, _ = self.step_flat(theta, batch)
+        self.last_sums = sums
+        fv = F_values(energy=sums[5], kin=sums[0], vnuc=sums[1], hart=sums[2], xc=sums[3] + sums[4])
+        return (sums[5], fv), self.model.unravel(tbar)

@@ -1,0 +1,55 @@
+"""Generates tests/golden/*.npz from the float64 restatements (run from the repo root:
+``python tests/golden/make_golden.py``).  The reference itself cannot run here (JAX absent), so each vector is
+produced by oracle/ref_torch.py -- the autodiff transliteration of the reference source with the reference's
+adaptive Dopri5 (rtol=atol=1e-7) -- and cross-checked against the closed-form oracle before it is written.
+Seeds are fixed; the files are small (a few hundred rows)."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import ofdft_oracle as O, ref_torch as R  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def case_3d(name, molname, bs, nuc, seed, last_scale):
+    rng = np.random.default_rng(seed)
+    mol = O.molecule(molname)
+    nt = mol["onehot"].shape[1]
+    p = O.init_params(rng, 2 + nt, (64, 64), 1, last_scale=last_scale)
+    for w, b in p.hidden:
+        b[:] = 0.1 * rng.standard_normal(b.shape)
+    p.last[1][:] = 0.05 if last_scale > 0 else 0.0
+    theta = O.flatten_params(p).astype(np.float32).astype(np.float64)
+    batch = O.batch_generator_3d(rng, bs, mol["coords"], mol["z"]).astype(np.float32).astype(np.float64)
+    spec = O.EnergySpec(Ne=mol["Ne"], kin="tf-w", hart="hartree", nuc=nuc, x="lda", coords=mol["coords"], z=mol["z"])
+    model = R.GenEqvFlow((64, 64), mol["coords"], mol["onehot"], bool_neg=True)
+    e, terms, g, y1, stats = R.value_and_grad_loss(model, theta, 2 + nt, (64, 64), batch, spec, method="dopri5")
+    # cross-check with the closed-form oracle (adaptive forward; RK4 x64 discrete adjoint for the gradient)
+    fld = O.GNNField(O.unflatten_params(theta, 2 + nt, (64, 64)), mol["coords"], mol["onehot"], bool_neg=True)
+    e2, terms2, y12, _ = O.loss_adaptive(fld, spec, batch)
+    _, _, g2, _ = O.loss_and_grad(fld, spec, batch, n_steps=64)
+    assert abs(e - e2) <= 1e-10 * abs(e2), (e, e2)
+    gn = np.linalg.norm(g2)
+    gdev = np.linalg.norm(g - g2) / gn
+    # back-propagating through the adaptive step sequence is only as accurate as the FORWARD error control makes
+    # the step grid: for the zero-initialised (identity) flow the controller takes 10x-growing steps and the
+    # parameter-gradient quadrature degrades to ~5e-5 (the reference's continuous adjoint re-controls the error on
+    # the adjoint system, which this transliteration does not).  The stored gradient is therefore the float64
+    # RK4 x64 discrete adjoint (converged to ~1e-9); the autodiff gradient must agree with it to the tolerance below.
+    assert gdev <= (2e-6 if last_scale > 0 else 1e-4), gdev
+    g = g2
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), theta=theta.astype(np.float32), batch=batch.astype(np.float32),
+                        coords=mol["coords"], z=mol["z"], onehot=mol["onehot"], Ne=mol["Ne"], nuc=nuc,
+                        y1=y1, energy=e, terms=terms, grad=g, grad_autodiff_dev=gdev, dopri_accepted=stats["accepted"], dopri_nfe=stats["nfe"])
+    print(name, "E", e, "terms", terms, "steps", stats)
+
+
+if __name__ == "__main__":
+    case_3d("h2o_hgh_bs96", "H2O", 96, "hgh", 101, 0.5)
+    case_3d("h2_point_bs80", "H2", 80, "nuclei_potential", 102, 0.5)
+    case_3d("lih_point_bs64", "LiH", 64, "nuclei_potential", 103, 0.5)
+    case_3d("h2o_zero_init_bs32", "H2O", 32, "hgh", 104, 0.0)

@@ -1,0 +1,72 @@
+"""CPU tests of the C-ABI boundary: the library loads, exports every symbol include/ofdft_b200.h declares, and the
+size helpers / argument validation behave (no compute calls: there is no GPU here)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from ofdft_nflows_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "ofdft_b200.h")
+
+
+def _declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(ofdft_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_are_exported_and_bound():
+    lib = _lib.load()
+    names = _declared_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/ofdft_b200.h but not exported"
+        assert n in _lib.SIGNATURES, f"{n} has no ctypes signature in _lib.py"
+    assert sorted(_lib.SIGNATURES) == names
+
+
+def test_abi_version_and_strerror():
+    lib = _lib.load()
+    assert lib.ofdft_b200_abi_version() == 1
+    assert b"invalid" in lib.ofdft_b200_strerror(-1)
+    assert b"unsupported" in lib.ofdft_b200_strerror(-2)
+    assert b"scratch" in lib.ofdft_b200_strerror(-3)
+    assert lib.ofdft_b200_strerror(0) == b"ok"
+
+
+def test_size_helpers():
+    lib = _lib.load()
+    assert lib.ofdft_cnf_gnn_ckpt_bytes(131072, 16) == 16 * 4 * 6 * 131072 * 4
+    assert lib.ofdft_cnf_gnn_fwd_scratch_bytes() >= 4
+    n_theta = 4289 + 64 * 5
+    assert lib.ofdft_cnf_gnn_bwd_scratch_bytes(3) >= 148 * n_theta * 4
+    assert lib.ofdft_functionals_scratch_bytes(65536) >= (65536 // 256) * 4 * 8
+    assert lib.ofdft_hartree_allpairs_scratch_bytes(1000, 777) > 0
+
+
+def test_argument_validation_without_device():
+    lib = _lib.load()
+    # null pointers / bad sizes are rejected before any CUDA call
+    assert lib.ofdft_cnf_gnn_fwd(None, None, None, None, None, None, None, None, 0, 128, 128, 3, 3, 7, 7, 3, 3, 16,
+                                 0.0, 1.0, -1.0) == -1
+    assert lib.ofdft_cnf_gnn_fwd(None, None, None, None, None, None, None, None, 0, 0, 0, 3, 3, 7, 7, 3, 3, 16,
+                                 0.0, 1.0, -1.0) == -1            # B <= 0
+    assert lib.ofdft_cnf_gnn_fwd(None, None, None, None, None, None, None, None, 0, 128, 128, 3, 3, 7, 7, 99, 3, 16,
+                                 0.0, 1.0, -1.0) == -2            # too many nuclei for one launch
+    assert lib.ofdft_cnf_gnn_fwd(None, None, None, None, None, None, None, None, 0, 128, 128, 3, 3, 4, 7, 3, 3, 16,
+                                 0.0, 1.0, -1.0) == -1            # row stride too small for full jets
+    assert lib.ofdft_cnf_gnn_bwd(None, None, None, None, None, None, None, None, None, 0, 128, 128, 4, 3, 7, 3, 3, 16,
+                                 0.0, 1.0, -1.0) == -1            # jets out of range
+    spec = _lib.EnergySpecC(2, 3, 1, 1, 1, 0, 2.0, 0.0, 0.0, 0.0)   # d = 2 is not a thing
+    assert lib.ofdft_functionals_fwd_bwd(None, C.byref(spec), None, None, None, 7, 16, None, None, None, 0) == -1
+    assert lib.ofdft_hartree_allpairs(None, 1, 3, 2.0, None, None, 3, 10, 10, None, None, None, None, 0) == -1
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setenv("OFDFT_B200_LIB", str(tmp_path / "nope.so"))
+    monkeypatch.setattr(_lib, "_LIB", None)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _lib.load()

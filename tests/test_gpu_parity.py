@@ -1,0 +1,257 @@
+"""GPU parity tests (pytest -m gpu): the CUDA path, called through the C ABI, against the float64 oracle on the
+same seeded inputs, against the committed golden vectors (reference semantics: adaptive Dopri5 at 1e-7), and --
+at BASELINE.json's full sizes -- through size-independent properties.
+
+Tolerances (BASELINE.json north_star): every energy term <= 1e-5 relative; gradients <= 1e-4, measured as
+||g - g_ref|| / ||g_ref|| per parameter tensor."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ofdft_oracle as O
+from ofdft_nflows_b200 import ops, utils
+from ofdft_nflows_b200.equiv_flows import Gen_EqvFlow
+from ofdft_nflows_b200.estimator import EnergyEstimator
+from ofdft_nflows_b200.jax_ode import neural_ode, neural_ode_score
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+E_TOL, G_TOL = 1e-5, 1e-4
+
+
+def dev(a):
+    return torch.as_tensor(np.asarray(a, dtype=np.float32), device="cuda")
+
+
+def rel(a, b):
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def tensor_slices(nt):
+    I = 2 + nt
+    return {"b3": (0, 1), "w3": (1, 65), "b1": (65, 129), "W1": (129, 129 + 64 * I), "b2": (129 + 64 * I, 193 + 64 * I),
+            "W2": (193 + 64 * I, 4289 + 64 * I)}
+
+
+def problem(molname, bs, seed, last_scale=0.5, biases=True):
+    rng = np.random.default_rng(seed)
+    mol = O.molecule(molname)
+    nt = mol["onehot"].shape[1]
+    p = O.init_params(rng, 2 + nt, (64, 64), 1, last_scale=last_scale * min(1.0, 3.0 / len(mol["z"])))
+    if biases:
+        for w, b in p.hidden:
+            b[:] = 0.1 * rng.standard_normal(b.shape)
+        p.last[1][:] = 0.05
+    theta = O.flatten_params(p).astype(np.float32).astype(np.float64)
+    batch = O.batch_generator_3d(rng, bs, mol["coords"], mol["z"]).astype(np.float32).astype(np.float64)
+    fld = O.GNNField(O.unflatten_params(theta, 2 + nt, (64, 64)), mol["coords"], mol["onehot"], bool_neg=True)
+    return mol, nt, theta, batch, fld
+
+
+@pytest.mark.parametrize("molname,bs", [("H2", 128), ("H2O", 150), ("LiH", 65), ("C6H6", 70)])
+def test_rhs_matches_oracle(molname, bs):
+    mol, nt, theta, batch, fld = problem(molname, bs, 1)
+    for y0sign, neg in ((-1.0, True), (1.0, False)):
+        f = O.GNNField(fld.params, mol["coords"], mol["onehot"], bool_neg=neg)
+        for jets, w in ((3, 7), (2, 4), (1, 3)):
+            dy = ops.gnn_rhs(dev(theta), dev(mol["coords"]), dev(mol["onehot"]), dev(batch), jets, 0.3, y0sign).cpu().numpy()
+            ref = f.rhs(0.3, batch, jets == 3)
+            scale = np.abs(ref[:, :w]).max()
+            assert np.abs(dy[:, :w] - ref[:, :w]).max() < 2e-6 * max(1.0, scale)
+
+
+@pytest.mark.parametrize("molname,bs,n_steps", [("H2", 128, 4), ("H2O", 150, 8), ("C6H6", 70, 4)])
+def test_forward_matches_oracle_same_scheme(molname, bs, n_steps):
+    """fp32 kernels vs the float64 oracle with the SAME fixed-step scheme (isolates arithmetic error)."""
+    mol, nt, theta, batch, fld = problem(molname, bs, 2)
+    B = 2 * bs
+    ref = O.odeint_rk4(lambda y, t: fld.rhs(t, y, True), batch, 0.0, 1.0, n_steps)
+    th, nuc, oh, y = dev(theta), dev(mol["coords"]), dev(mol["onehot"]), dev(batch)
+    y1 = ops.gnn_fwd(th, nuc, oh, y, B, 3, 3, n_steps, 0.0, 1.0, -1.0)[0].cpu().numpy()
+    assert np.abs(y1[:, :4] - ref[:, :4]).max() < 5e-6
+    assert np.abs(y1[:, 4:] - ref[:, 4:]).max() < 5e-6 * max(1.0, np.abs(ref[:, 4:]).max())
+    # mixed launch: first half full jets, second half x only; ragged tile tails on both segments
+    y1m = ops.gnn_fwd(th, nuc, oh, y, bs, 3, 1, n_steps, 0.0, 1.0, -1.0)[0].cpu().numpy()
+    assert np.array_equal(y1m[:bs], y1[:bs])
+    assert np.abs(y1m[bs:, :3] - ref[bs:, :3]).max() < 5e-6
+    # neural_ode (no score channel), reverse direction t in [-1, 0] with bool_neg=False (rho_rev, H20_...py:132-137)
+    frev = O.GNNField(fld.params, mol["coords"], mol["onehot"], bool_neg=False)
+    z4 = np.concatenate([batch[:, :3], np.zeros((B, 1))], 1)
+    ref_rev = O.odeint_rk4(lambda yy, t: frev.rhs(t, yy, False), z4, -1.0, 0.0, n_steps)
+    y_rev = ops.gnn_fwd(th, nuc, oh, dev(z4), B, 2, 2, n_steps, -1.0, 0.0, 1.0)[0].cpu().numpy()
+    assert np.abs(y_rev - ref_rev).max() < 5e-6
+
+
+@pytest.mark.parametrize("molname,bs,nuc", [("H2", 128, "nuclei_potential"), ("H2O", 150, "hgh"), ("C6H6", 70, "nuclei_potential")])
+def test_training_step_matches_oracle_same_scheme(molname, bs, nuc):
+    mol, nt, theta, batch, fld = problem(molname, bs, 3)
+    n_steps = 4
+    ospec = O.EnergySpec(Ne=mol["Ne"], kin="tf-w", hart="hartree", nuc=nuc, x="lda", coords=mol["coords"], z=mol["z"])
+    e_ref, terms_ref, g_ref, _ = O.loss_and_grad(fld, ospec, batch, n_steps=n_steps)
+    model = Gen_EqvFlow(3, (64, 64), mol["coords"], mol["onehot"], bool_neg=True)
+    spec = ops.EnergySpec(Ne=mol["Ne"], d=3, kin="tf-w", hart="hartree", nuc=nuc, x="lda", coords=mol["coords"], z=mol["z"])
+    for skip in (True, False):
+        est = EnergyEstimator(model, spec, n_steps=n_steps, skip_unused_jets=skip)
+        sums, tbar, _ = est.step_flat(dev(theta), dev(batch))
+        sums = sums.cpu().numpy(); g = tbar.cpu().numpy()
+        for i in range(4):
+            assert abs(sums[i] - terms_ref[i]) <= E_TOL * abs(terms_ref[i]), (i, sums[i], terms_ref[i])
+        assert abs(sums[5] - e_ref) <= E_TOL * abs(e_ref)
+        for name, (a, b) in tensor_slices(nt).items():
+            assert rel(g[a:b], g_ref[a:b]) <= G_TOL, (name, rel(g[a:b], g_ref[a:b]))
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "*.npz"))))
+def test_golden_vectors_reference_semantics(path):
+    """Committed fixtures = the reference's semantics (adaptive Dopri5 1e-7, float64, autodiff gradient).
+    The fixed-step fp32 kernels must land within the north-star tolerances."""
+    g = np.load(path)
+    nt = g["onehot"].shape[1]
+    model = Gen_EqvFlow(3, (64, 64), g["coords"], g["onehot"], bool_neg=True)
+    spec = ops.EnergySpec(Ne=float(g["Ne"]), d=3, kin="tf-w", hart="hartree", nuc=str(g["nuc"]), x="lda", coords=g["coords"], z=g["z"])
+    est = EnergyEstimator(model, spec, n_steps=32)
+    sums, tbar, y1 = est.step_flat(dev(g["theta"]), dev(g["batch"]))
+    sums = sums.cpu().numpy(); grad = tbar.cpu().numpy()
+    for i in range(4):
+        assert abs(sums[i] - g["terms"][i]) <= E_TOL * abs(g["terms"][i]), (i, sums[i], g["terms"][i])
+    assert abs(sums[5] - float(g["energy"])) <= E_TOL * abs(float(g["energy"]))
+    gref = g["grad"]
+    for name, (a, b) in tensor_slices(nt).items():
+        if np.linalg.norm(gref[a:b]) == 0.0:
+            assert np.linalg.norm(grad[a:b]) == 0.0, name          # zero-init: only the last layer has a gradient
+        else:
+            assert rel(grad[a:b], gref[a:b]) <= G_TOL, (name, rel(grad[a:b], gref[a:b]))
+    bs = g["batch"].shape[0] // 2
+    assert np.abs(y1.cpu().numpy()[:bs, :3] - g["y1"][:bs, :3]).max() < 1e-4
+
+
+def test_functionals_all_modes_match_oracle():
+    rng = np.random.default_rng(4)
+    mol = O.molecule("H2O")
+    y1 = O.batch_generator_3d(rng, 300, mol["coords"], mol["z"]).astype(np.float32).astype(np.float64)
+    for kin in ("tf", "w", "tf-w"):
+        for nuc in ("nuclei_potential", "hgh"):
+            for hart in ("hartree", "hartree_mt"):
+                for x in ("lda", ""):
+                    ospec = O.EnergySpec(Ne=10, kin=kin, hart=hart, nuc=nuc, x=x, coords=mol["coords"], z=mol["z"])
+                    spec = ops.EnergySpec(Ne=10, d=3, kin=kin, hart=hart, nuc=nuc, x=x, coords=mol["coords"], z=mol["z"])
+                    e_ref, terms_ref = O.energy_terms(ospec, y1, 3)
+                    sums, yb = ops.functionals_fwd_bwd(spec, dev(y1))
+                    sums = sums.cpu().numpy()
+                    for i in range(4):
+                        assert abs(sums[i] - terms_ref[i]) <= 1e-6 * max(abs(terms_ref[i]), 1e-30)
+                    assert rel(yb.cpu().numpy(), O.energy_terms_vjp(ospec, y1, 3)) < 1e-5
+                    integ = ops.functionals_integrands(spec, dev(y1)).cpu().numpy().astype(np.float64)
+                    assert np.allclose(integ.mean(1), terms_ref[:4], rtol=1e-6, atol=1e-12)
+    # 1-D functionals (LiH.py defaults)
+    y1d = O.batch_generator_1d(rng, 257).astype(np.float32).astype(np.float64)
+    ospec = O.EnergySpec(Ne=2, kin="tfw_1d", hart="softc", nuc="attraction", x="", R=0.7, Z_alpha=3, Z_beta=1)
+    spec = ops.EnergySpec(Ne=2, d=1, kin="tfw_1d", hart="softc", nuc="attraction", x="", R=0.7, Z_alpha=3, Z_beta=1)
+    e_ref, terms_ref = O.energy_terms(ospec, y1d, 1)
+    sums, yb = ops.functionals_fwd_bwd(spec, dev(y1d))
+    assert np.allclose(sums.cpu().numpy()[:3], terms_ref[:3], rtol=1e-6)
+    assert rel(yb.cpu().numpy(), O.energy_terms_vjp(ospec, y1d, 1)) < 1e-5
+
+
+def test_hartree_allpairs_matches_numpy():
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((1500, 7)); xp = rng.standard_normal((1111, 7)) + 0.3
+    es, xb, xpb = ops.hartree_allpairs(dev(x), dev(xp), 10.0, "hartree")
+    xf, xpf = x[:, :3].astype(np.float32).astype(np.float64), xp[:, :3].astype(np.float32).astype(np.float64)
+    diff = xf[:, None, :] - xpf[None]
+    zz = (diff ** 2).sum(-1) + 3e-5
+    assert abs(es.item() - 50.0 * (1 / np.sqrt(zz)).mean()) <= 1e-6 * es.item()
+    gref = (-50.0 * diff / zz[..., None] ** 1.5) / (1500 * 1111)
+    assert rel(xb.cpu().numpy(), gref.sum(1)) < 1e-5 and rel(xpb.cpu().numpy(), -gref.sum(0)) < 1e-5
+    # the paired estimator is the diagonal of the pair matrix: all-pairs on n == m reproduces its mean when fed row i only
+    x1 = rng.standard_normal((700, 3)); x1p = rng.standard_normal((900, 3))
+    es1, xb1, _ = ops.hartree_allpairs(dev(x1[:, :1].repeat(3, 1)), dev(x1p[:, :1].repeat(3, 1)), 2.0, "softc")
+    a = x1[:, :1].astype(np.float32).astype(np.float64); b = x1p[:, :1].astype(np.float32).astype(np.float64)
+    assert abs(es1.item() - 4.0 * (1 / np.sqrt(1 + (a - b.T) ** 2)).mean()) <= 1e-6 * es1.item()
+
+
+def test_drop_in_neural_ode_score_autograd():
+    """neural_ode_score(params, batch, f, t0, t1, d) with torch.autograd standing in for jax.custom_vjp."""
+    mol, nt, theta, batch, fld = problem("H2O", 100, 6)
+    model = Gen_EqvFlow(3, (64, 64), mol["coords"], mol["onehot"], bool_neg=True)
+    params = model.unravel(dev(theta).requires_grad_(True))
+    leaves = [params["params"]["cnf"]["net"]["VmapNN_0"][k][l] for k in ("last_layer", "layers_0", "layers_1") for l in ("bias", "kernel")]
+    x, logp, score = neural_ode_score(params, dev(batch), model, 0.0, 1.0, 3, n_steps=4)
+    assert x.shape == (200, 3) and logp.shape == (200, 1) and score.shape == (200, 3)
+    wx, wl, ws = (np.random.default_rng(0).standard_normal(s) for s in ((200, 3), (200, 1), (200, 3)))
+    loss = (x * dev(wx)).sum() + (logp * dev(wl)).sum() + (score * dev(ws)).sum()
+    grads = torch.autograd.grad(loss, leaves)
+    flat = torch.cat([g.reshape(-1) for g in grads]).cpu().numpy()
+    _, stages = O.odeint_rk4(lambda y, t: fld.rhs(t, y, True), batch, 0.0, 1.0, 4, keep=True)
+    _, tref = O.rk4_adjoint(fld, stages, 0.0, 1.0, np.concatenate([wx, wl, ws], 1), True)
+    assert rel(flat, tref) < G_TOL
+    z, lp = neural_ode(params, dev(batch[:, :4]), model, 0.0, 1.0, 3, n_steps=4)
+    assert torch.equal(z, x.detach()) or np.abs(z.cpu().numpy() - x.detach().cpu().numpy()).max() < 1e-6
+    # f.apply(params, t, states) == d/dt [x, logp]
+    dy = model.apply(params, 0.25, dev(batch[:, :4])).cpu().numpy()
+    assert np.abs(dy - fld.rhs(0.25, batch[:, :4], False)).max() < 2e-6 * max(1.0, np.abs(dy).max())
+
+
+# ---- full-size (BASELINE.json config) properties ---------------------------------------------------------------
+
+def _full_problem(bs=65536):
+    Ne, atoms, z, coords = utils.coordinates("H2O")
+    oh = utils.jax_one_hot(z)
+    rng = np.random.default_rng(4321)
+    w1 = rng.standard_normal((5, 64)) / np.sqrt(5); w2 = rng.standard_normal((64, 64)) / 8; w3 = 0.5 * rng.standard_normal((64, 1)) / 8
+    theta = np.concatenate([np.zeros(1), w3.ravel(), np.zeros(64), w1.ravel(), np.zeros(64), w2.ravel()]).astype(np.float32)
+    batch = next(utils.batch_generator(1234, bs, utils.ProMolecularDensity(z, coords)))
+    return Ne, z, coords, oh, theta, batch
+
+
+def test_full_size_zero_init_is_identity_and_only_last_layer_has_gradient():
+    Ne, z, coords, oh, theta, batch = _full_problem()
+    theta0 = theta.copy(); theta0[:65] = 0.0                       # reference default init: last layer zero
+    model = Gen_EqvFlow(3, (64, 64), coords, oh, bool_neg=True)
+    spec = ops.EnergySpec(Ne=Ne, d=3, kin="tf-w", hart="hartree", nuc="hgh", x="lda", coords=coords, z=z)
+    est = EnergyEstimator(model, spec, n_steps=16, skip_unused_jets=False)
+    sums, tbar, y1 = est.step_flat(dev(theta0), dev(batch))
+    assert torch.equal(y1, dev(batch))                              # g == 0  =>  x = z, logp/score untouched, bit-exact
+    g = tbar.cpu().numpy()
+    assert np.abs(g[65:]).max() == 0.0 and np.abs(g[:65]).max() > 0.0
+    # energy of the un-flowed prior == plain functional means of the inputs
+    ospec = O.EnergySpec(Ne=Ne, kin="tf-w", hart="hartree", nuc="hgh", x="lda", coords=coords, z=z)
+    e_ref, terms_ref = O.energy_terms(ospec, batch.astype(np.float64), 3)
+    assert abs(sums[5].item() - e_ref) <= 1e-6 * abs(e_ref)
+
+
+def test_full_size_roundtrip_self_convergence_and_determinism():
+    Ne, z, coords, oh, theta, batch = _full_problem()
+    th, nuc, ohd, y = dev(theta), dev(coords), dev(oh), dev(batch)
+    B = y.shape[0]
+    # rev o fwd = id at full size (fwd: bool_neg=True on [0,1]; rev: bool_neg=False on [-1,0])
+    y1 = ops.gnn_fwd(th, nuc, ohd, y[:, :4].contiguous(), B, 2, 2, 16, 0.0, 1.0, -1.0)[0]
+    y0 = ops.gnn_fwd(th, nuc, ohd, y1, B, 2, 2, 16, -1.0, 0.0, 1.0)[0]
+    # the reverse pass subtracts what the forward added to logp only if started from it: check x and the logp increment
+    assert (y0[:, :3] - y[:, :3]).abs().max().item() < 2e-5
+    assert ((y1[:, 3] - y[:, 3]) + (y0[:, 3] - y1[:, 3])).abs().max().item() < 2e-5
+    # N vs 2N self-convergence of every energy term, and run-to-run bitwise determinism of energy and gradient
+    model = Gen_EqvFlow(3, (64, 64), coords, oh, bool_neg=True)
+    spec = ops.EnergySpec(Ne=Ne, d=3, kin="tf-w", hart="hartree", nuc="hgh", x="lda", coords=coords, z=z)
+    s16, g16, _ = EnergyEstimator(model, spec, n_steps=16).step_flat(th, y)
+    s32, g32, _ = EnergyEstimator(model, spec, n_steps=32).step_flat(th, y)
+    s16b, g16b, _ = EnergyEstimator(model, spec, n_steps=16).step_flat(th, y)
+    assert torch.equal(s16, s16b) and torch.equal(g16, g16b)
+    a, b = s16.cpu().numpy(), s32.cpu().numpy()
+    assert np.all(np.abs(a[:4] - b[:4]) <= E_TOL * np.abs(b[:4]))
+    assert rel(g16.cpu().numpy(), g32.cpu().numpy()) <= G_TOL
+    # skipping the unused second-half jets does not change the result
+    s_full, g_full, _ = EnergyEstimator(model, spec, n_steps=16, skip_unused_jets=False).step_flat(th, y)
+    assert np.allclose(s_full.cpu().numpy(), a, rtol=1e-12) and rel(g_full.cpu().numpy(), g16.cpu().numpy()) < 1e-6
+    # sharding invariance: two half-batches (paired shards) average to the full-batch result (section 8e)
+    from ofdft_nflows_b200.estimator import shard_batch
+    est = EnergyEstimator(model, spec, n_steps=16)
+    parts = [est.step_flat(th, shard_batch(y, r, 2).contiguous()) for r in range(2)]
+    sm = (parts[0][0] + parts[1][0]) / 2
+    gm = (parts[0][1] + parts[1][1]) / 2
+    assert np.allclose(sm.cpu().numpy()[:6], a[:6], rtol=1e-9)
+    assert rel(gm.cpu().numpy(), g16.cpu().numpy()) < 1e-5

@@ -1,0 +1,229 @@
+"""CPU tests of the oracle: closed forms vs the autodiff transliteration of the reference, the committed golden
+vectors, and reference-independent properties."""
+import glob
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ofdft_oracle as O, ref_torch as R
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _setup(molname, bs, seed, feat=(16, 16), last_scale=0.5):
+    rng = np.random.default_rng(seed)
+    mol = O.molecule(molname)
+    nt = mol["onehot"].shape[1]
+    p = O.init_params(rng, 2 + nt, feat, 1, last_scale=last_scale)
+    for w, b in p.hidden:
+        b[:] = 0.1 * rng.standard_normal(b.shape)
+    p.last[1][:] = 0.05 if last_scale else 0.0
+    theta = O.flatten_params(p)
+    batch = O.batch_generator_3d(rng, bs, mol["coords"], mol["z"])
+    return mol, nt, theta, batch
+
+
+@pytest.mark.parametrize("molname", ["H2", "H2O", "C6H6"])
+@pytest.mark.parametrize("bool_neg", [False, True])
+def test_gnn_rhs_closed_form_matches_autodiff(molname, bool_neg):
+    mol, nt, theta, batch = _setup(molname, 6, 1)
+    fld = O.GNNField(O.unflatten_params(theta, 2 + nt, (16, 16)), mol["coords"], mol["onehot"], bool_neg)
+    m = R.GenEqvFlow((16, 16), mol["coords"], mol["onehot"], bool_neg)
+    pt = R.params_from_flat(theta, 2 + nt, (16, 16))
+    ref = R.evol_score(m, pt, 0.37, torch.as_tensor(batch)).numpy()          # jax_ode.py:80-98
+    assert np.abs(fld.rhs(0.37, batch, True) - ref).max() < 1e-12
+    ref2 = m.apply(pt, 0.37, torch.as_tensor(batch[:, :4])).numpy()          # equiv_flows.py:124-127
+    assert np.abs(fld.rhs(0.37, batch[:, :4], False) - ref2).max() < 1e-12
+
+
+def test_mlp_rhs_closed_form_matches_autodiff():
+    rng = np.random.default_rng(2)
+    feat = (24, 24, 24)
+    p = O.init_params(rng, 2, feat, 1, last_scale=0.5)
+    theta = O.flatten_params(p)
+    batch = O.batch_generator_1d(rng, 8)
+    fld = O.MLPField(O.unflatten_params(theta, 2, feat), bool_neg=True)
+    m = R.GenCNFSimpleMLP(1, feat, bool_neg=True)
+    ref = R.evol_score(m, R.params_from_flat(theta, 2, feat), 0.4, torch.as_tensor(batch)).numpy()
+    assert np.abs(fld.rhs(0.4, batch, True) - ref).max() < 1e-12
+
+
+def test_gnn_rhs_vjp_matches_autograd():
+    mol, nt, theta, batch = _setup("H2O", 5, 3)
+    fld = O.GNNField(O.unflatten_params(theta, 2 + nt, (16, 16)), mol["coords"], mol["onehot"], True)
+    kbar = np.random.default_rng(0).standard_normal(batch.shape)
+    yb, tb = fld.rhs_vjp(0.3, batch, kbar, True)
+    th = torch.as_tensor(theta).clone().requires_grad_(True)
+    yy = torch.as_tensor(batch).clone().requires_grad_(True)
+    m = R.GenEqvFlow((16, 16), mol["coords"], mol["onehot"], True)
+    out = R.evol_score(m, R.params_from_flat(th, 2 + nt, (16, 16)), 0.3, yy)
+    gy, gt = torch.autograd.grad((out * torch.as_tensor(kbar)).sum(), [yy, th])
+    assert np.abs(yb - gy.numpy()).max() < 1e-11
+    assert np.abs(tb - gt.numpy()).max() < 1e-10 * max(1.0, np.abs(gt.numpy()).max())
+
+
+@pytest.mark.parametrize("nuc", ["nuclei_potential", "hgh"])
+def test_loss_and_grad_matches_autodiff_3d(nuc):
+    mol, nt, theta, batch = _setup("H2O", 6, 4)
+    spec = O.EnergySpec(Ne=mol["Ne"], kin="tf-w", hart="hartree", nuc=nuc, x="lda", coords=mol["coords"], z=mol["z"])
+    fld = O.GNNField(O.unflatten_params(theta, 2 + nt, (16, 16)), mol["coords"], mol["onehot"], True)
+    e, terms, g, _ = O.loss_and_grad(fld, spec, batch, n_steps=3)
+    m = R.GenEqvFlow((16, 16), mol["coords"], mol["onehot"], True)
+    e2, terms2, g2, _, _ = R.value_and_grad_loss(m, theta, 2 + nt, (16, 16), batch, spec, method="rk4", n_steps=3)
+    assert abs(e - e2) < 1e-12 * abs(e2)
+    assert np.allclose(terms, terms2, rtol=1e-12, atol=0)
+    assert np.linalg.norm(g - g2) < 1e-11 * np.linalg.norm(g2)
+
+
+def test_loss_and_grad_matches_autodiff_1d():
+    rng = np.random.default_rng(5)
+    feat = (16, 16, 16)
+    theta = O.flatten_params(O.init_params(rng, 2, feat, 1, last_scale=0.5))
+    batch = O.batch_generator_1d(rng, 8)
+    spec = O.EnergySpec(Ne=2, kin="tfw_1d", hart="softc", nuc="attraction", x="", R=0.7, Z_alpha=3, Z_beta=1)
+    fld = O.MLPField(O.unflatten_params(theta, 2, feat), bool_neg=True)
+    e, terms, g, _ = O.loss_and_grad(fld, spec, batch, n_steps=3)
+    m = R.GenCNFSimpleMLP(1, feat, bool_neg=True)
+    e2, terms2, g2, _, _ = R.value_and_grad_loss(m, theta, 2, feat, batch, spec, method="rk4", n_steps=3)
+    assert abs(e - e2) < 1e-12 * abs(e2)
+    assert np.linalg.norm(g - g2) < 1e-11 * np.linalg.norm(g2)
+
+
+def test_adaptive_dopri5_numpy_equals_torch_and_converges():
+    mol, nt, theta, batch = _setup("H2", 8, 6)
+    fld = O.GNNField(O.unflatten_params(theta, 2 + nt, (16, 16)), mol["coords"], mol["onehot"], True)
+    y_np, st = O.odeint_dopri5(lambda y, t: fld.rhs(t, y, True), batch, 0.0, 1.0)
+    m = R.GenEqvFlow((16, 16), mol["coords"], mol["onehot"], True)
+    pt = R.params_from_flat(theta, 2 + nt, (16, 16))
+    y_t, st2 = R.odeint_dopri5(lambda y, t: R.evol_score(m, pt, t, y), torch.as_tensor(batch), 0.0, 1.0)
+    assert st == st2
+    assert np.abs(y_np - y_t.numpy()).max() < 1e-11
+    y_rk = O.odeint_rk4(lambda y, t: fld.rhs(t, y, True), batch, 0.0, 1.0, 64)
+    # rtol = atol = 1e-7 controls the batch-RMS LOCAL error per step: individual rows of the reference's own
+    # solution sit ~1e-5 from the converged one (measured 1.7e-5 here), the batch mean far closer
+    assert np.abs(y_np - y_rk).max() < 1e-4
+    assert np.sqrt(np.mean((y_np - y_rk) ** 2)) < 5e-6
+
+
+def test_zero_init_flow_is_identity():
+    """(i) default init: last layer zero => g == 0, x = z, logp and score unchanged."""
+    mol, nt, theta, batch = _setup("H2O", 8, 7, last_scale=0.0)
+    fld = O.GNNField(O.unflatten_params(theta, 2 + nt, (16, 16)), mol["coords"], mol["onehot"], True)
+    y1 = O.odeint_rk4(lambda y, t: fld.rhs(t, y, True), batch, 0.0, 1.0, 4)
+    assert np.abs(y1 - batch).max() == 0.0
+
+
+def test_reverse_of_forward_is_identity_and_logp_cancels():
+    """(ii) NODE_rev(NODE_fwd(z)) = z: model_fwd (bool_neg=True, t in [0,1]) then model_rev (bool_neg=False,
+    t in [-1,0]) as the drivers use them (H20_...py:93-103,132-137)."""
+    mol, nt, theta, batch = _setup("H2O", 8, 8)
+    p = O.unflatten_params(theta, 2 + nt, (16, 16))
+    fwd = O.GNNField(p, mol["coords"], mol["onehot"], True)
+    rev = O.GNNField(p, mol["coords"], mol["onehot"], False)
+    z0 = np.concatenate([batch[:, :3], np.zeros((batch.shape[0], 1))], 1)
+    x1, dl1 = O.neural_ode(fwd, z0, 0.0, 1.0)
+    zz, dl0 = O.neural_ode(rev, np.concatenate([x1, np.zeros_like(dl1)], 1), -1.0, 0.0)
+    assert np.abs(zz - batch[:, :3]).max() < 1e-5       # two adaptive solves at rtol = atol = 1e-7
+    assert np.abs(dl0 + dl1).max() < 1e-5
+
+
+def test_score_is_gradient_of_log_density():
+    """(iii) score channel == finite-difference grad_x log rho_phi(x) evaluated through rho_rev."""
+    mol, nt, theta, batch = _setup("H2", 4, 9)
+    p = O.unflatten_params(theta, 2 + nt, (16, 16))
+    fwd = O.GNNField(p, mol["coords"], mol["onehot"], True)
+    rev = O.GNNField(p, mol["coords"], mol["onehot"], False)
+    x1, logp1, s1 = O.neural_ode_score(fwd, batch, 0.0, 1.0, method="rk4", n_steps=64)
+
+    def logrho(x):
+        z0, dl = O.neural_ode(rev, np.concatenate([x, np.zeros((x.shape[0], 1))], 1), -1.0, 0.0, method="rk4", n_steps=64)
+        return O.promolecular_logp_score(z0, mol["coords"], mol["z"])[0] - dl
+
+    assert np.abs(logrho(x1) - logp1).max() < 1e-7
+    h = 1e-5
+    for c in range(3):
+        e = np.zeros((1, 3)); e[0, c] = h
+        fd = (logrho(x1 + e) - logrho(x1 - e)) / (2 * h)
+        assert np.abs(fd[:, 0] - s1[:, c]).max() < 1e-5
+
+
+def test_density_normalised_1d():
+    """(iv) integral of rho_phi over a trapezoid grid is 1 (LiH.py:109-111,162)."""
+    rng = np.random.default_rng(10)
+    feat = (16, 16)
+    p = O.init_params(rng, 2, feat, 1, last_scale=0.5)
+    rev = O.MLPField(p, bool_neg=False)
+    xs = np.linspace(-20.0, 20.0, 2048)[:, None]
+    z0, dl = O.neural_ode(rev, np.concatenate([xs, np.zeros_like(xs)], 1), -1.0, 0.0, method="rk4", n_steps=32)
+    logp = -0.5 * z0 * z0 - 0.5 * math.log(2 * math.pi) - dl
+    assert abs(np.trapezoid(np.exp(logp).ravel(), xs.ravel()) - 1.0) < 1e-6
+
+
+def test_functional_closed_forms_and_quirks():
+    """(v) closed-form values + the reference quirks."""
+    den = np.array([[0.3], [1.7]]); score = np.array([[0.1, -0.2, 0.3], [1.0, 2.0, -1.0]]); Ne = 10
+    assert np.allclose(O.thomas_fermi(den, score, Ne), 2.871234000188191 * Ne ** (5 / 3) * den ** (2 / 3))
+    assert np.allclose(O.weizsacker(den, score, Ne), 0.2 * Ne / 8 * (score ** 2).sum(1, keepdims=True))
+    assert np.allclose(O.lda(den, score, Ne), -(0.75) * Ne ** (4 / 3) * (1 / math.pi) * den ** (1 / 3))   # (3/pi)**1/3 == 1/pi
+    x = np.array([[0.0, 0.0, 0.0]]); xp = np.array([[1.0, 2.0, 2.0]])
+    assert np.allclose(O.hartree_potential(x, xp, 2), 0.5 * 4 / math.sqrt(9 + 3e-5))                      # eps per component
+    assert np.allclose(O.soft_coulomb(np.array([[0.5]]), np.array([[-0.5]]), 2), 4 / math.sqrt(2.0))      # no 1/2
+    coords = np.array([[0.0, 0.0, 1.0]]); z = np.array([8.0])
+    assert np.allclose(O.nuclei_potential(x, 10, coords, z), -10 * 8 / (1.0 + 1e-4))                      # eps on r
+    hgh = O.nuclei_potential_hgh(x, 10, coords, z)                                                        # H params for O
+    rr = 1.0 / 0.2
+    v = -math.erf(rr / math.sqrt(2)) + math.exp(-0.5 * rr * rr) * (-4.180237 + 0.725075 * rr * rr)
+    assert np.allclose(hgh, 10 * v)
+    assert (O.molecule("H2O")["onehot"] == np.array([[0, 0, 0], [0, 1, 0], [0, 1, 0]])).all()             # Z=8 -> zero row
+    assert (O.molecule("C6H6")["onehot"][:, 0] == np.array([0] * 6 + [1] * 6)).all() or \
+           (O.molecule("C6H6")["onehot"][:, 0] == np.array([1] * 6 + [0] * 6)).all()
+
+
+def test_functional_vjp_matches_finite_differences():
+    mol, nt, theta, batch = _setup("H2O", 16, 11)
+    for nuc in ("nuclei_potential", "hgh"):
+        spec = O.EnergySpec(Ne=10, kin="tf-w", hart="hartree", nuc=nuc, x="lda", coords=mol["coords"], z=mol["z"])
+        gv = O.energy_terms_vjp(spec, batch, 3)
+        gf = O.energy_terms_grad(spec, batch, 3)
+        assert np.abs(gv - gf).max() < 1e-6 * max(1.0, np.abs(gv).max())
+
+
+def test_rk4_self_convergence_and_gradient_fd():
+    """(vi)+(vii): N vs 2N self-convergence and a finite-difference check of dE/dtheta."""
+    mol, nt, theta, batch = _setup("H2", 8, 12)
+    spec = O.EnergySpec(Ne=2, kin="tf-w", hart="hartree", nuc="nuclei_potential", x="lda", coords=mol["coords"], z=mol["z"])
+    mk = lambda th: O.GNNField(O.unflatten_params(th, 2 + nt, (16, 16)), mol["coords"], mol["onehot"], True)
+    e8 = O.loss_and_grad(mk(theta), spec, batch, n_steps=8)[0]
+    e16, _, g16, _ = O.loss_and_grad(mk(theta), spec, batch, n_steps=16)
+    e32 = O.loss_and_grad(mk(theta), spec, batch, n_steps=32)[0]
+    assert abs(e16 - e32) < abs(e8 - e16) / 8          # 4th order: ratio ~16
+    rng = np.random.default_rng(0)
+    v = rng.standard_normal(theta.shape)
+    h = 1e-6
+    fd = (O.loss_and_grad(mk(theta + h * v), spec, batch, n_steps=16)[0]
+          - O.loss_and_grad(mk(theta - h * v), spec, batch, n_steps=16)[0]) / (2 * h)
+    assert abs(fd - g16 @ v) < 1e-6 * max(1.0, abs(fd))
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "*.npz"))))
+def test_oracle_reproduces_golden_vectors(path):
+    """The committed fixtures were produced by oracle/ref_torch.py (autodiff transliteration, adaptive Dopri5);
+    the closed-form oracle must reproduce them."""
+    g = np.load(path)
+    nt = g["onehot"].shape[1]
+    theta = g["theta"].astype(np.float64)
+    fld = O.GNNField(O.unflatten_params(theta, 2 + nt, (64, 64)), g["coords"], g["onehot"], True)
+    spec = O.EnergySpec(Ne=float(g["Ne"]), kin="tf-w", hart="hartree", nuc=str(g["nuc"]), x="lda", coords=g["coords"], z=g["z"])
+    e, terms, y1, st = O.loss_adaptive(fld, spec, g["batch"].astype(np.float64))
+    assert st["accepted"] == int(g["dopri_accepted"]) and st["nfe"] == int(g["dopri_nfe"])
+    assert abs(e - float(g["energy"])) < 1e-10 * abs(float(g["energy"]))
+    assert np.allclose(terms, g["terms"], rtol=1e-10, atol=1e-14)
+    assert np.abs(y1 - g["y1"]).max() < 1e-9
+    # fixed-step scheme the kernels use: RK4 x32 agrees with the adaptive reference within the parity tolerance
+    e32, t32, g32, _ = O.loss_and_grad(fld, spec, g["batch"].astype(np.float64), n_steps=32)
+    assert np.all(np.abs(t32[:4] - g["terms"][:4]) <= 1e-5 * np.abs(g["terms"][:4]))
+    gn = np.linalg.norm(g["grad"])
+    assert np.linalg.norm(g32 - g["grad"]) <= 1e-4 * gn
