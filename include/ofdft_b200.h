@@ -95,27 +95,34 @@ const char* ofdft_b200_strerror(int code);
  *   rows [0, n_a) carry jets_a, rows [n_a, B) carry jets_b (one launch, heavy tiles first)
  *   ckpt    : NULL, or ofdft_cnf_gnn_ckpt_bytes(B, n_steps) bytes receiving every RK4 stage state
  *             (x, s) for the backward pass
+ *   act_ckpt: NULL, or ofdft_cnf_gnn_act_ckpt_bytes(...) bytes receiving the layer-2 activation jets of every
+ *             RHS evaluation (spends HBM capacity -- ~100 KB per full-jet trajectory at Na=3, RK4x16 -- to
+ *             remove the recompute GEMM from the backward pass; NULL selects recomputation)
  *   y0sign  : +1 (bool_neg=False) or -1 (bool_neg=True): t' = y0*t, output scaled by y0
  *   scratch : ofdft_cnf_gnn_fwd_scratch_bytes() bytes
  */
 size_t ofdft_cnf_gnn_ckpt_bytes(int64_t B, int32_t n_steps);
+size_t ofdft_cnf_gnn_act_ckpt_bytes(int64_t B, int64_t n_a, int32_t jets_a, int32_t jets_b, int32_t Na, int32_t n_steps);
 size_t ofdft_cnf_gnn_fwd_scratch_bytes(void);
 int ofdft_cnf_gnn_fwd(void* stream, const float* theta, const float* nuclei, const float* onehot,
-                      const float* y_in, float* y_out, float* ckpt, void* scratch, size_t scratch_bytes,
+                      const float* y_in, float* y_out, float* ckpt, float* act_ckpt,
+                      void* scratch, size_t scratch_bytes,
                       int64_t B, int64_t n_a, int32_t jets_a, int32_t jets_b,
                       int32_t in_stride, int32_t out_stride,
                       int32_t Na, int32_t n_types, int32_t n_steps, float t0, float t1, float y0sign);
 
 /* Discrete adjoint of ofdft_cnf_gnn_fwd (replaces the odeint custom_vjp the reference reaches through
  * jax.value_and_grad, H20_mol_ofdft_min_equiv_flows.py:177-178).
+ *   act_ckpt  : the buffer the forward pass filled, or NULL (recompute)
  *   ybar1     : (B, bar_stride) cotangent of y(t1), rows [xbar | logpbar | sbar]
  *   theta_bar : n_theta floats, OVERWRITTEN with d<ybar1, y(t1)>/d theta
  *   ybar0     : NULL or (B, bar_stride) cotangent of y(t0)
- *   scratch   : ofdft_cnf_gnn_bwd_scratch_bytes(n_types) bytes
+ *   scratch   : ofdft_cnf_gnn_bwd_scratch_bytes(B, n_a, n_types) bytes (one partial gradient per 128-row tile,
+ *               reduced in fixed order: theta_bar is bitwise reproducible)
  */
-size_t ofdft_cnf_gnn_bwd_scratch_bytes(int32_t n_types);
+size_t ofdft_cnf_gnn_bwd_scratch_bytes(int64_t B, int64_t n_a, int32_t n_types);
 int ofdft_cnf_gnn_bwd(void* stream, const float* theta, const float* nuclei, const float* onehot,
-                      const float* ckpt, const float* ybar1, float* theta_bar, float* ybar0,
+                      const float* ckpt, const float* act_ckpt, const float* ybar1, float* theta_bar, float* ybar0,
                       void* scratch, size_t scratch_bytes,
                       int64_t B, int64_t n_a, int32_t jets_a, int32_t jets_b, int32_t bar_stride,
                       int32_t Na, int32_t n_types, int32_t n_steps, float t0, float t1, float y0sign);

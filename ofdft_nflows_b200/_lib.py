@@ -28,10 +28,11 @@ SIGNATURES = {
     "ofdft_b200_strerror": (C.c_char_p, [C.c_int]),
     "ofdft_cnf_gnn_ckpt_bytes": (szt, [i64, i32]),
     "ofdft_cnf_gnn_fwd_scratch_bytes": (szt, []),
-    "ofdft_cnf_gnn_fwd": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, szt, i64, i64, i32, i32, i32, i32, i32, i32, i32,
+    "ofdft_cnf_gnn_act_ckpt_bytes": (szt, [i64, i64, i32, i32, i32, i32]),
+    "ofdft_cnf_gnn_fwd": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, szt, i64, i64, i32, i32, i32, i32, i32, i32, i32,
                                     f32, f32, f32]),
-    "ofdft_cnf_gnn_bwd_scratch_bytes": (szt, [i32]),
-    "ofdft_cnf_gnn_bwd": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, szt, i64, i64, i32, i32, i32, i32, i32, i32,
+    "ofdft_cnf_gnn_bwd_scratch_bytes": (szt, [i64, i64, i32]),
+    "ofdft_cnf_gnn_bwd": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, szt, i64, i64, i32, i32, i32, i32, i32, i32,
                                     f32, f32, f32]),
     "ofdft_cnf_gnn_rhs": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, szt, i64, i32, i32, i32, i32, f32, f32]),
     "ofdft_cnf_mlp1d_ckpt_bytes": (szt, [i64, i32]),

@@ -21,6 +21,7 @@ struct GnnFwdArgs {
   const float* y_in; float* y_out; float* ckpt; int* counter;
   long long B, n_a; int jets_a, jets_b; int in_stride, out_stride;
   int Na, n_types, n_steps; float t0, t1, y0; int rhs_only; float t_rhs;
+  float* act; long long act_rows_a, act_rows_b;   // optional layer-2 activation checkpoint (rows padded to kTP)
 };
 
 struct GnnBwdArgs {
@@ -28,6 +29,20 @@ struct GnnBwdArgs {
   const float* ckpt; const float* ybar1; float* ybar0; float* gpart; int* counter;
   long long B, n_a; int jets_a, jets_b; int bar_stride;
   int Na, n_types, n_steps; float t0, t1, y0;
+  const float* act; long long act_rows_a, act_rows_b;
+};
+
+// Layer-2 activation checkpoint (optional; trades 180 GB of HBM for the recompute GEMM of the backward pass):
+// for every RHS evaluation e = (step*4+stage)*Na + nucleus and both row segments, the jets (a2, p2', p2'') as
+// [jet][unit][row] with the row index contiguous (coalesced 8-byte stores per lane).
+struct ActLayout {
+  long long rows_a, rows_b, block; int ja, jb;
+  __host__ __device__ ActLayout(long long ra, long long rb, int ja_, int jb_) : rows_a(ra), rows_b(rb), ja(ja_), jb(jb_) {
+    block = (long long)kH * (ja * ra + jb * rb);
+  }
+  __host__ __device__ long long seg_base(long long e, bool seg_b) const {
+    return e * block + (seg_b ? (long long)kH * ja * rows_a : 0);
+  }
 };
 
 struct SmemFwd {
@@ -160,14 +175,18 @@ __device__ __forceinline__ void gemm64(float (&acc)[NJ][2][16], const float* __r
 template <int NJ>
 __device__ __forceinline__ void epilogue_fwd(const float (&acc)[NJ][2][16], const float* __restrict__ b2,
                                              const float* __restrict__ w3, float* __restrict__ Fpart,
-                                             int half, int ug, int lane) {
+                                             int half, int ug, int lane, float* __restrict__ act, long long act_rows) {
   float fp[3][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
+  const long long jet_stride = (long long)kH * act_rows;
+  if (act != nullptr) act += (long long)(ug * 16) * act_rows + (half * 64 + 2 * lane);
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
     const float b = b2[ug * 16 + j], w = w3[ug * 16 + j];
+    float av[2];
 #pragma unroll
     for (int tr = 0; tr < 2; ++tr) {
       const float a = tanh_f(acc[0][tr][j] + b);
+      av[tr] = a;
       fp[0][tr] = fmaf(w, a, fp[0][tr]);
       if (NJ >= 2) {
         const float sg = fmaf(-a, a, 1.0f);
@@ -179,6 +198,12 @@ __device__ __forceinline__ void epilogue_fwd(const float (&acc)[NJ][2][16], cons
           fp[2][tr] = fmaf(w, a2, fp[2][tr]);
         }
       }
+    }
+    if (act != nullptr) {
+      __stcs(reinterpret_cast<float2*>(act), make_float2(av[0], av[1]));
+      if (NJ >= 2) __stcs(reinterpret_cast<float2*>(act + jet_stride), make_float2(acc[1][0][j], acc[1][1][j]));
+      if (NJ == 3) __stcs(reinterpret_cast<float2*>(act + 2 * jet_stride), make_float2(acc[2][0][j], acc[2][1][j]));
+      act += act_rows;
     }
   }
   const int tp0 = half * 64 + 2 * lane;
@@ -223,7 +248,10 @@ __device__ __forceinline__ bool next_tile(int* counter, int* slot, long long n_t
 // forward tile
 // ------------------------------------------------------------------------------------------------
 template <int NJ>
-__device__ void fwd_tile(SmemFwd& sm, const GnnFwdArgs& a, long long row0, long long seg_end, float b3) {
+__device__ void fwd_tile(SmemFwd& sm, const GnnFwdArgs& a, long long row0, long long seg_end, float b3,
+                         bool seg_b, long long seg_row0) {
+  const ActLayout AL(a.act_rows_a, a.act_rows_b, a.jets_a, a.jets_b);
+  const long long act_rows = seg_b ? a.act_rows_b : a.act_rows_a;
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, half = w >> 2, ug = w & 3;
   const bool owner = tid < kTP;
   const long long row = row0 + tid;
@@ -296,7 +324,10 @@ __device__ void fwd_tile(SmemFwd& sm, const GnnFwdArgs& a, long long row0, long 
         first_layer<NJ, true>(sm.A, sm.xs, sm.wr, sm.wt, sm.cb + i * kH, sm.nuc + i * 4, tprime, half, ug, lane, rr);
         __syncthreads();
         gemm64<NJ, true>(acc, sm.A, sm.W2, nullptr, half, ug, lane);
-        epilogue_fwd<NJ>(acc, sm.b2, sm.w3, sm.Fpart, half, ug, lane);
+        float* actp = nullptr;
+        if (a.act != nullptr)
+          actp = a.act + AL.seg_base((long long)(step * 4 + stage) * a.Na + i, seg_b) + (row0 - seg_row0);
+        epilogue_fwd<NJ>(acc, sm.b2, sm.w3, sm.Fpart, half, ug, lane, actp, act_rows);
         __syncthreads();
       }
       if (owner) {
@@ -334,11 +365,12 @@ __global__ void __launch_bounds__(kThreads, 1) gnn_fwd_kernel(const GnnFwdArgs a
   long long tile;
   while (next_tile(a.counter, &sm.tile, tiles_a + tiles_b, tile)) {
     long long row0, seg_end; int nj;
-    if (tile < tiles_a) { row0 = tile * kTP; seg_end = a.n_a; nj = a.jets_a; }
-    else { row0 = a.n_a + (tile - tiles_a) * kTP; seg_end = a.B; nj = a.jets_b; }
-    if (nj == 3) fwd_tile<3>(sm, a, row0, seg_end, b3);
-    else if (nj == 2) fwd_tile<2>(sm, a, row0, seg_end, b3);
-    else fwd_tile<1>(sm, a, row0, seg_end, b3);
+    bool seg_b; long long seg_row0;
+    if (tile < tiles_a) { row0 = tile * kTP; seg_end = a.n_a; nj = a.jets_a; seg_b = false; seg_row0 = 0; }
+    else { row0 = a.n_a + (tile - tiles_a) * kTP; seg_end = a.B; nj = a.jets_b; seg_b = true; seg_row0 = a.n_a; }
+    if (nj == 3) fwd_tile<3>(sm, a, row0, seg_end, b3, seg_b, seg_row0);
+    else if (nj == 2) fwd_tile<2>(sm, a, row0, seg_end, b3, seg_b, seg_row0);
+    else fwd_tile<1>(sm, a, row0, seg_end, b3, seg_b, seg_row0);
   }
 }
 
@@ -353,7 +385,7 @@ struct BwdAccum {
 };
 
 // layer-2 tanh jet forward + reverse: writes Fpart and the pre-activation cotangent jets PB
-template <int NJ>
+template <int NJ, bool ACT>
 __device__ __forceinline__ void epilogue_bwd(const float (&acc)[NJ][2][16], SmemBwd& sm, BwdAccum& G,
                                              int half, int ug, int lane) {
   const int tp0 = half * 64 + 2 * lane;
@@ -373,7 +405,7 @@ __device__ __forceinline__ void epilogue_bwd(const float (&acc)[NJ][2][16], Smem
     float gw = 0.f;
 #pragma unroll
     for (int tr = 0; tr < 2; ++tr) {
-      const float a = tanh_f(acc[0][tr][j] + b);
+      const float a = ACT ? acc[0][tr][j] : tanh_f(acc[0][tr][j] + b);
       const float sg = fmaf(-a, a, 1.0f);
       fp[0][tr] = fmaf(w, a, fp[0][tr]);
       gw = fmaf(a, fb[0][tr], gw);
@@ -507,8 +539,11 @@ __device__ __forceinline__ void dw2_accum(BwdAccum& G, const SmemBwd& sm, int w,
   }
 }
 
-template <int NJ>
-__device__ void bwd_tile(SmemBwd& sm, const GnnBwdArgs& a, long long row0, long long seg_end, float b3, BwdAccum& G) {
+template <int NJ, bool ACT>
+__device__ void bwd_tile(SmemBwd& sm, const GnnBwdArgs& a, long long row0, long long seg_end, float b3, BwdAccum& G,
+                         bool seg_b, long long seg_row0) {
+  const ActLayout AL(a.act_rows_a, a.act_rows_b, a.jets_a, a.jets_b);
+  const long long act_rows = seg_b ? a.act_rows_b : a.act_rows_a;
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, half = w >> 2, ug = w & 3;
   const bool owner = tid < kTP;
   const long long row = row0 + tid;
@@ -621,10 +656,22 @@ __device__ void bwd_tile(SmemBwd& sm, const GnnBwdArgs& a, long long row0, long 
       }
       __syncthreads();
       for (int i = 0; i < a.Na; ++i) {
+        if (ACT) {
+          // issue the checkpoint loads first: their latency hides behind the first-layer phase
+          const float* src = a.act + AL.seg_base((long long)(step * 4 + stage) * a.Na + i, seg_b) + (row0 - seg_row0)
+                             + (long long)(ug * 16) * act_rows + (half * 64 + 2 * lane);
+#pragma unroll
+          for (int jt = 0; jt < NJ; ++jt)
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float2 v = __ldcs(reinterpret_cast<const float2*>(src + ((long long)jt * kH + j) * act_rows));
+              acc[jt][0][j] = v.x; acc[jt][1][j] = v.y;
+            }
+        }
         first_layer<NJ, false>(sm.A, sm.xs, sm.wr, sm.wt, sm.cb + i * kH, sm.nuc + i * 4, tprime, half, ug, lane, rr);
         __syncthreads();
-        gemm64<NJ, false>(acc, sm.A, sm.W2, sm.wr2, half, ug, lane);
-        epilogue_bwd<NJ>(acc, sm, G, half, ug, lane);
+        if (!ACT) gemm64<NJ, false>(acc, sm.A, sm.W2, sm.wr2, half, ug, lane);
+        epilogue_bwd<NJ, ACT>(acc, sm, G, half, ug, lane);
         __syncthreads();
         gemm64<NJ, true>(acc, sm.PB, sm.W2T, nullptr, half, ug, lane);
         epilogue_b1<NJ>(acc, sm, G, rr, tprime, i, half, ug, lane);
@@ -656,10 +703,62 @@ __device__ void bwd_tile(SmemBwd& sm, const GnnBwdArgs& a, long long row0, long 
   }
 }
 
+// per-TILE partial gradient -> gpart[tile][n_theta]; resets the accumulators.  One partial per tile (not per CTA)
+// makes the reduction order independent of the dynamic tile schedule: the gradient is bitwise reproducible.
+__device__ void flush_tile_grad(SmemBwd& sm, BwdAccum& G, float* __restrict__ out, const GnnThetaLayout& L,
+                                const float* __restrict__ onehot, int Na, int n_types) {
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, half = w >> 2, ug = w & 3;
+  {
+    const int kg = 4 * (w >> 1) + (lane & 3), jg = 8 * (w & 1) + (lane >> 2);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {             // theta offsets are odd: no vector stores
+        out[L.W2 + (4 * kg + i) * kH + 4 * jg + j] = G.dW2[i][j];
+        G.dW2[i][j] = 0.f;
+      }
+    }
+  }
+  // red[which][half][ug][lane]
+  sm.red[((0 * 2 + half) * 4 + ug) * 32 + lane] = G.g_b2w3;
+  sm.red[((1 * 2 + half) * 4 + ug) * 32 + lane] = G.g_wtwr;
+  const float b3w = warp_sum(G.g_b3);
+  G.g_b2w3 = 0.f; G.g_wtwr = 0.f; G.g_b3 = 0.f;
+  __syncthreads();
+  if (half == 0) {
+    const float v0 = sm.red[((0 * 2 + 0) * 4 + ug) * 32 + lane] + sm.red[((0 * 2 + 1) * 4 + ug) * 32 + lane];
+    const float v1 = sm.red[((1 * 2 + 0) * 4 + ug) * 32 + lane] + sm.red[((1 * 2 + 1) * 4 + ug) * 32 + lane];
+    if (lane < 16) { out[L.b2 + ug * 16 + lane] = v0; out[L.W1 + ug * 16 + lane] = v1; }
+    else { out[L.w3 + ug * 16 + lane - 16] = v0; out[L.W1 + kH + ug * 16 + lane - 16] = v1; }
+  }
+  __syncthreads();
+  if (lane == 0) sm.red[w] = b3w;
+  __syncthreads();
+  if (tid == 0) {
+    float s = 0.f;
+    for (int i = 0; i < 4; ++i) s += sm.red[i];     // owners are warps 0..3
+    out[L.b3] = s;
+  }
+  if (tid < kH) {
+    float sb1 = 0.f;
+    for (int n = 0; n < Na; ++n) sb1 += sm.S[(0 * kMaxNa + n) * kH + tid] + sm.S[(1 * kMaxNa + n) * kH + tid];
+    out[L.b1 + tid] = sb1;
+    for (int t = 0; t < n_types; ++t) {
+      float s = 0.f;
+      for (int n = 0; n < Na; ++n)
+        s = fmaf(onehot[n * n_types + t], sm.S[(0 * kMaxNa + n) * kH + tid] + sm.S[(1 * kMaxNa + n) * kH + tid], s);
+      out[L.W1 + (2 + t) * kH + tid] = s;
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < 2 * kMaxNa * kH; i += kThreads) sm.S[i] = 0.f;
+}
+
+template <bool ACT>
 __global__ void __launch_bounds__(kThreads, 1) gnn_bwd_kernel(const GnnBwdArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SmemBwd& sm = *reinterpret_cast<SmemBwd*>(smem_raw);
-  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, half = w >> 2, ug = w & 3;
+  const int tid = threadIdx.x;
   load_small(sm, a.theta, a.nuclei, a.onehot, a.Na, a.n_types);
   const GnnThetaLayout L(a.n_types);
   for (int i = tid; i < kH * kH; i += kThreads) sm.W2T[(i % kH) * kH + (i / kH)] = a.theta[L.W2 + i];
@@ -678,56 +777,18 @@ __global__ void __launch_bounds__(kThreads, 1) gnn_bwd_kernel(const GnnBwdArgs a
   long long tile;
   while (next_tile(a.counter, &sm.tile, tiles_a + tiles_b, tile)) {
     long long row0, seg_end; int nj;
-    if (tile < tiles_a) { row0 = tile * kTP; seg_end = a.n_a; nj = a.jets_a; }
-    else { row0 = a.n_a + (tile - tiles_a) * kTP; seg_end = a.B; nj = a.jets_b; }
-    if (nj == 3) bwd_tile<3>(sm, a, row0, seg_end, b3, G);
-    else if (nj == 2) bwd_tile<2>(sm, a, row0, seg_end, b3, G);
-    else bwd_tile<1>(sm, a, row0, seg_end, b3, G);
-  }
-  __syncthreads();
-
-  // ---- per-CTA partial gradient -> gpart[blockIdx.x][n_theta] ----
-  float* out = a.gpart + (size_t)blockIdx.x * L.n;
-  {
-    const int kg = 4 * (w >> 1) + (lane & 3), jg = 8 * (w & 1) + (lane >> 2);
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) out[L.W2 + (4 * kg + i) * kH + 4 * jg + j] = G.dW2[i][j];
-  }
-  // red[which][half][ug][lane]
-  sm.red[((0 * 2 + half) * 4 + ug) * 32 + lane] = G.g_b2w3;
-  sm.red[((1 * 2 + half) * 4 + ug) * 32 + lane] = G.g_wtwr;
-  const float b3w = warp_sum(G.g_b3);
-  __syncthreads();
-  if (half == 0) {
-    const float v0 = sm.red[((0 * 2 + 0) * 4 + ug) * 32 + lane] + sm.red[((0 * 2 + 1) * 4 + ug) * 32 + lane];
-    const float v1 = sm.red[((1 * 2 + 0) * 4 + ug) * 32 + lane] + sm.red[((1 * 2 + 1) * 4 + ug) * 32 + lane];
-    if (lane < 16) { out[L.b2 + ug * 16 + lane] = v0; out[L.W1 + ug * 16 + lane] = v1; }
-    else { out[L.w3 + ug * 16 + lane - 16] = v0; out[L.W1 + kH + ug * 16 + lane - 16] = v1; }
-  }
-  __syncthreads();
-  if (lane == 0) sm.red[w] = b3w;
-  __syncthreads();
-  if (tid == 0) {
-    float s = 0.f;
-    for (int i = 0; i < 4; ++i) s += sm.red[i];     // owners are warps 0..3
-    out[L.b3] = s;
-  }
-  if (tid < kH) {
-    float sb1 = 0.f;
-    for (int n = 0; n < a.Na; ++n) sb1 += sm.S[(0 * kMaxNa + n) * kH + tid] + sm.S[(1 * kMaxNa + n) * kH + tid];
-    out[L.b1 + tid] = sb1;
-    for (int t = 0; t < a.n_types; ++t) {
-      float s = 0.f;
-      for (int n = 0; n < a.Na; ++n)
-        s = fmaf(a.onehot[n * a.n_types + t], sm.S[(0 * kMaxNa + n) * kH + tid] + sm.S[(1 * kMaxNa + n) * kH + tid], s);
-      out[L.W1 + (2 + t) * kH + tid] = s;
-    }
+    bool seg_b; long long seg_row0;
+    if (tile < tiles_a) { row0 = tile * kTP; seg_end = a.n_a; nj = a.jets_a; seg_b = false; seg_row0 = 0; }
+    else { row0 = a.n_a + (tile - tiles_a) * kTP; seg_end = a.B; nj = a.jets_b; seg_b = true; seg_row0 = a.n_a; }
+    if (nj == 3) bwd_tile<3, ACT>(sm, a, row0, seg_end, b3, G, seg_b, seg_row0);
+    else if (nj == 2) bwd_tile<2, ACT>(sm, a, row0, seg_end, b3, G, seg_b, seg_row0);
+    else bwd_tile<1, ACT>(sm, a, row0, seg_end, b3, G, seg_b, seg_row0);
+    __syncthreads();
+    flush_tile_grad(sm, G, a.gpart + (size_t)tile * L.n, L, a.onehot, a.Na, a.n_types);
   }
 }
 
-// deterministic cross-CTA reduction of the partial gradients (float64 accumulation, fixed order)
+// deterministic reduction of the per-tile partial gradients (float64 accumulation, fixed tile order)
 __global__ void gnn_grad_reduce_kernel(const float* __restrict__ gpart, float* __restrict__ theta_bar, int n, int nblk) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
@@ -739,7 +800,6 @@ __global__ void gnn_grad_reduce_kernel(const float* __restrict__ gpart, float* _
 // ------------------------------------------------------------------------------------------------
 // host launchers
 // ------------------------------------------------------------------------------------------------
-constexpr int kMaxGrid = 160;
 constexpr size_t kCounterBytes = 256;
 
 static int num_sms() {
@@ -763,9 +823,18 @@ using namespace ofdft;
 extern "C" size_t ofdft_cnf_gnn_ckpt_bytes(int64_t B, int32_t n_steps) {
   return (size_t)n_steps * 4 * 6 * (size_t)B * sizeof(float);
 }
+static long long pad_rows(long long n) { return (n + kTP - 1) / kTP * kTP; }
+extern "C" size_t ofdft_cnf_gnn_act_ckpt_bytes(int64_t B, int64_t n_a, int32_t jets_a, int32_t jets_b, int32_t Na,
+                                               int32_t n_steps) {
+  if (B <= 0 || n_a < 0 || n_a > B || Na <= 0 || n_steps <= 0) return 0;
+  const ActLayout AL(pad_rows(n_a), pad_rows(B - n_a), jets_a, jets_b);
+  return (size_t)n_steps * 4 * (size_t)Na * (size_t)AL.block * sizeof(float);
+}
 extern "C" size_t ofdft_cnf_gnn_fwd_scratch_bytes(void) { return kCounterBytes; }
-extern "C" size_t ofdft_cnf_gnn_bwd_scratch_bytes(int32_t n_types) {
-  return kCounterBytes + (size_t)kMaxGrid * GnnThetaLayout(n_types).n * sizeof(float);
+static long long n_tiles_of(long long B, long long n_a) { return (n_a + kTP - 1) / kTP + (B - n_a + kTP - 1) / kTP; }
+extern "C" size_t ofdft_cnf_gnn_bwd_scratch_bytes(int64_t B, int64_t n_a, int32_t n_types) {
+  if (B <= 0 || n_a < 0 || n_a > B) return kCounterBytes;
+  return kCounterBytes + (size_t)n_tiles_of(B, n_a) * GnnThetaLayout(n_types).n * sizeof(float);
 }
 
 static int launch_fwd(void* stream, GnnFwdArgs& a, void* scratch, size_t scratch_bytes) {
@@ -786,7 +855,8 @@ static int launch_fwd(void* stream, GnnFwdArgs& a, void* scratch, size_t scratch
 }
 
 extern "C" int ofdft_cnf_gnn_fwd(void* stream, const float* theta, const float* nuclei, const float* onehot,
-                                 const float* y_in, float* y_out, float* ckpt, void* scratch, size_t scratch_bytes,
+                                 const float* y_in, float* y_out, float* ckpt, float* act_ckpt,
+                                 void* scratch, size_t scratch_bytes,
                                  int64_t B, int64_t n_a, int32_t jets_a, int32_t jets_b,
                                  int32_t in_stride, int32_t out_stride,
                                  int32_t Na, int32_t n_types, int32_t n_steps, float t0, float t1, float y0sign) {
@@ -796,7 +866,7 @@ extern "C" int ofdft_cnf_gnn_fwd(void* stream, const float* theta, const float* 
   const int need = jmax == 3 ? 7 : (jmax == 2 ? 4 : 3);
   if (in_stride < need || out_stride < need) return OFDFT_EINVAL;
   GnnFwdArgs a{theta, nuclei, onehot, y_in, y_out, ckpt, nullptr, B, n_a, jets_a, jets_b, in_stride, out_stride,
-               Na, n_types, n_steps, t0, t1, y0sign, 0, 0.f};
+               Na, n_types, n_steps, t0, t1, y0sign, 0, 0.f, act_ckpt, pad_rows(n_a), pad_rows(B - n_a)};
   return launch_fwd(stream, a, scratch, scratch_bytes);
 }
 
@@ -809,13 +879,13 @@ extern "C" int ofdft_cnf_gnn_rhs(void* stream, const float* theta, const float* 
   const int need = jets == 3 ? 7 : (jets == 2 ? 4 : 3);
   if (stride < need) return OFDFT_EINVAL;
   GnnFwdArgs a{theta, nuclei, onehot, y, dy, nullptr, nullptr, B, B, jets, jets, stride, stride,
-               Na, n_types, 1, 0.f, 1.f, y0sign, 1, t};
+               Na, n_types, 1, 0.f, 1.f, y0sign, 1, t, nullptr, 0, 0};
   return launch_fwd(stream, a, scratch, scratch_bytes);
 }
 
 extern "C" int ofdft_cnf_gnn_bwd(void* stream, const float* theta, const float* nuclei, const float* onehot,
-                                 const float* ckpt, const float* ybar1, float* theta_bar, float* ybar0,
-                                 void* scratch, size_t scratch_bytes,
+                                 const float* ckpt, const float* act_ckpt, const float* ybar1, float* theta_bar,
+                                 float* ybar0, void* scratch, size_t scratch_bytes,
                                  int64_t B, int64_t n_a, int32_t jets_a, int32_t jets_b, int32_t bar_stride,
                                  int32_t Na, int32_t n_types, int32_t n_steps, float t0, float t1, float y0sign) {
   int rc = check_common(B, n_a, jets_a, jets_b, Na, n_types, n_steps);
@@ -825,23 +895,25 @@ extern "C" int ofdft_cnf_gnn_bwd(void* stream, const float* theta, const float* 
   const int jmax = jets_a > jets_b ? jets_a : jets_b;
   const int need = jmax == 3 ? 7 : (jmax == 2 ? 4 : 3);
   if (bar_stride < need) return OFDFT_EINVAL;
-  if (scratch_bytes < ofdft_cnf_gnn_bwd_scratch_bytes(n_types)) return OFDFT_ESCRATCH;
+  if (scratch_bytes < ofdft_cnf_gnn_bwd_scratch_bytes(B, n_a, n_types)) return OFDFT_ESCRATCH;
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e = cudaMemsetAsync(scratch, 0, kCounterBytes, st);
   if (e != cudaSuccess) return (int)e;
-  e = cudaFuncSetAttribute(gnn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemBwd));
+  e = cudaFuncSetAttribute(gnn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemBwd));
+  if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(gnn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemBwd));
   if (e != cudaSuccess) return (int)e;
   const long long tiles = (n_a + kTP - 1) / kTP + (B - n_a + kTP - 1) / kTP;
   int sms = num_sms(); if (sms <= 0) sms = 148;
-  if (sms > kMaxGrid) sms = kMaxGrid;
   const int grid = (int)(tiles < sms ? tiles : sms);
   float* gpart = (float*)((char*)scratch + kCounterBytes);
   GnnBwdArgs a{theta, nuclei, onehot, ckpt, ybar1, ybar0, gpart, (int*)scratch, B, n_a, jets_a, jets_b, bar_stride,
-               Na, n_types, n_steps, t0, t1, y0sign};
-  gnn_bwd_kernel<<<grid, kThreads, sizeof(SmemBwd), st>>>(a);
+               Na, n_types, n_steps, t0, t1, y0sign, act_ckpt, pad_rows(n_a), pad_rows(B - n_a)};
+  if (act_ckpt != nullptr) gnn_bwd_kernel<true><<<grid, kThreads, sizeof(SmemBwd), st>>>(a);
+  else gnn_bwd_kernel<false><<<grid, kThreads, sizeof(SmemBwd), st>>>(a);
   e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
   const int n = GnnThetaLayout(n_types).n;
-  gnn_grad_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(gpart, theta_bar, n, grid);
+  gnn_grad_reduce_kernel<<<(n + 127) / 128, 128, 0, st>>>(gpart, theta_bar, n, (int)tiles);
   return (int)cudaGetLastError();
 }

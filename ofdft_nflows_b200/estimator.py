@@ -48,11 +48,15 @@ def shard_batch(batch, rank: int, world: int):
 
 class EnergyEstimator:
     def __init__(self, model: Any, spec: ops.EnergySpec, n_steps: int = DEFAULT_N_STEPS, t0: float = 0.0, t1: float = 1.0,
-                 skip_unused_jets: bool = True, group: Optional[Any] = None):
+                 skip_unused_jets: bool = True, group: Optional[Any] = None, act_ckpt: bool = True,
+                 act_ckpt_max_bytes: int = 64 << 30):
         self.model, self.spec, self.n_steps, self.t0, self.t1 = model, spec, int(n_steps), float(t0), float(t1)
         # rows of the second half only supply xp: integrate them without the logp/score channels
         self.jets_b = ops.JETS_X if skip_unused_jets else ops.JETS_FULL
         self.group = group
+        # keep the layer-2 activation jets of every RHS evaluation in HBM instead of recomputing them in the backward
+        # pass (B200: 180 GB); falls back to recomputation above ``act_ckpt_max_bytes``
+        self.act_ckpt, self.act_ckpt_max_bytes = bool(act_ckpt), int(act_ckpt_max_bytes)
         self._is_gnn = hasattr(model, "xyz_nuclei")
 
     def _dist(self) -> bool:
@@ -77,8 +81,10 @@ class EnergyEstimator:
 
         if self._is_gnn:
             e0 = mark()
+            want_act = self.act_ckpt and ops.gnn_act_ckpt_bytes(B, bs, ops.JETS_FULL, self.jets_b, m.xyz_nuclei.shape[0],
+                                                                self.n_steps) <= self.act_ckpt_max_bytes
             y1, ckpt = ops.gnn_fwd(theta, m.xyz_nuclei, m.z_one_hot, batch, bs, ops.JETS_FULL, self.jets_b, self.n_steps,
-                                   self.t0, self.t1, m.y0, want_ckpt=True)
+                                   self.t0, self.t1, m.y0, want_ckpt=True, want_act=want_act)
             e1 = mark()
             sums, ybar1 = ops.functionals_fwd_bwd(self.spec, y1)
             e2 = mark()

@@ -49,10 +49,16 @@ def gnn_theta_size(n_types: int) -> int:
     return 4289 + 64 * (2 + n_types)
 
 
+def gnn_act_ckpt_bytes(B: int, n_a: int, jets_a: int, jets_b: int, Na: int, n_steps: int) -> int:
+    return int(_lib.load().ofdft_cnf_gnn_act_ckpt_bytes(B, n_a, jets_a, jets_b, Na, n_steps))
+
+
 def gnn_fwd(theta, nuclei, onehot, y_in, n_a: int, jets_a: int, jets_b: int, n_steps: int,
-            t0: float, t1: float, y0sign: float, want_ckpt: bool = False, out: Optional[torch.Tensor] = None
-            ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
-    """ofdft_cnf_gnn_fwd: integrate rows [0,n_a) with jets_a and rows [n_a,B) with jets_b."""
+            t0: float, t1: float, y0sign: float, want_ckpt: bool = False, out: Optional[torch.Tensor] = None,
+            want_act: bool = False):
+    """ofdft_cnf_gnn_fwd: integrate rows [0,n_a) with jets_a and rows [n_a,B) with jets_b.
+    Returns (y1, ckpt) -- ckpt is None, the stage-state checkpoint, or (with ``want_act``) the pair
+    (stage states, layer-2 activation checkpoint)."""
     lib = _lib.load()
     theta, nuclei, onehot, y_in = _f32c(theta), _f32c(nuclei), _f32c(onehot), _f32c(y_in)
     B, stride = y_in.shape
@@ -63,12 +69,16 @@ def gnn_fwd(theta, nuclei, onehot, y_in, n_a: int, jets_a: int, jets_b: int, n_s
     ckpt = None
     if want_ckpt:
         ckpt = torch.empty(lib.ofdft_cnf_gnn_ckpt_bytes(B, n_steps) // 4, dtype=torch.float32, device=y_in.device)
+    act = None
+    if want_ckpt and want_act:
+        nb = lib.ofdft_cnf_gnn_act_ckpt_bytes(B, n_a, jets_a, jets_b, Na, n_steps)
+        act = torch.empty(nb // 4, dtype=torch.float32, device=y_in.device)
     sb = lib.ofdft_cnf_gnn_fwd_scratch_bytes()
     scratch = torch.empty(sb, dtype=torch.uint8, device=y_in.device)
     _lib.check(lib.ofdft_cnf_gnn_fwd(_stream(), _ptr(theta), _ptr(nuclei), _ptr(onehot), _ptr(y_in), _ptr(y_out),
-                                     _ptr(ckpt), _ptr(scratch), sb, B, n_a, jets_a, jets_b, stride, y_out.shape[1],
-                                     Na, n_types, n_steps, t0, t1, y0sign), "ofdft_cnf_gnn_fwd")
-    return y_out, ckpt
+                                     _ptr(ckpt), _ptr(act), _ptr(scratch), sb, B, n_a, jets_a, jets_b, stride,
+                                     y_out.shape[1], Na, n_types, n_steps, t0, t1, y0sign), "ofdft_cnf_gnn_fwd")
+    return y_out, ((ckpt, act) if act is not None else ckpt)
 
 
 def gnn_bwd(theta, nuclei, onehot, ckpt, ybar1, n_a: int, jets_a: int, jets_b: int, n_steps: int,
@@ -76,13 +86,16 @@ def gnn_bwd(theta, nuclei, onehot, ckpt, ybar1, n_a: int, jets_a: int, jets_b: i
     """ofdft_cnf_gnn_bwd: discrete adjoint; returns (theta_bar, ybar0 or None)."""
     lib = _lib.load()
     theta, nuclei, onehot, ybar1 = _f32c(theta), _f32c(nuclei), _f32c(onehot), _f32c(ybar1)
+    act = None
+    if isinstance(ckpt, tuple):
+        ckpt, act = ckpt
     B, stride = ybar1.shape
     Na, n_types = onehot.shape
     theta_bar = torch.empty_like(theta)
     ybar0 = torch.zeros_like(ybar1) if want_ybar0 else None
-    sb = lib.ofdft_cnf_gnn_bwd_scratch_bytes(n_types)
+    sb = lib.ofdft_cnf_gnn_bwd_scratch_bytes(B, n_a, n_types)
     scratch = torch.empty(sb, dtype=torch.uint8, device=ybar1.device)
-    _lib.check(lib.ofdft_cnf_gnn_bwd(_stream(), _ptr(theta), _ptr(nuclei), _ptr(onehot), _ptr(ckpt), _ptr(ybar1),
+    _lib.check(lib.ofdft_cnf_gnn_bwd(_stream(), _ptr(theta), _ptr(nuclei), _ptr(onehot), _ptr(ckpt), _ptr(act), _ptr(ybar1),
                                      _ptr(theta_bar), _ptr(ybar0), _ptr(scratch), sb, B, n_a, jets_a, jets_b, stride,
                                      Na, n_types, n_steps, t0, t1, y0sign), "ofdft_cnf_gnn_bwd")
     return theta_bar, ybar0

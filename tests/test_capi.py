@@ -42,7 +42,9 @@ def test_size_helpers():
     assert lib.ofdft_cnf_gnn_ckpt_bytes(131072, 16) == 16 * 4 * 6 * 131072 * 4
     assert lib.ofdft_cnf_gnn_fwd_scratch_bytes() >= 4
     n_theta = 4289 + 64 * 5
-    assert lib.ofdft_cnf_gnn_bwd_scratch_bytes(3) >= 148 * n_theta * 4
+    assert lib.ofdft_cnf_gnn_bwd_scratch_bytes(131072, 65536, 3) >= 1024 * n_theta * 4
+    assert lib.ofdft_cnf_gnn_act_ckpt_bytes(131072, 65536, 3, 1, 3, 16) == 16 * 4 * 3 * 64 * (3 * 65536 + 65536) * 4
+    assert lib.ofdft_cnf_gnn_act_ckpt_bytes(300, 150, 3, 1, 3, 2) == 2 * 4 * 3 * 64 * (3 * 256 + 256) * 4   # rows padded to 128
     assert lib.ofdft_functionals_scratch_bytes(65536) >= (65536 // 256) * 4 * 8
     assert lib.ofdft_hartree_allpairs_scratch_bytes(1000, 777) > 0
 
@@ -50,16 +52,12 @@ def test_size_helpers():
 def test_argument_validation_without_device():
     lib = _lib.load()
     # null pointers / bad sizes are rejected before any CUDA call
-    assert lib.ofdft_cnf_gnn_fwd(None, None, None, None, None, None, None, None, 0, 128, 128, 3, 3, 7, 7, 3, 3, 16,
-                                 0.0, 1.0, -1.0) == -1
-    assert lib.ofdft_cnf_gnn_fwd(None, None, None, None, None, None, None, None, 0, 0, 0, 3, 3, 7, 7, 3, 3, 16,
-                                 0.0, 1.0, -1.0) == -1            # B <= 0
-    assert lib.ofdft_cnf_gnn_fwd(None, None, None, None, None, None, None, None, 0, 128, 128, 3, 3, 7, 7, 99, 3, 16,
-                                 0.0, 1.0, -1.0) == -2            # too many nuclei for one launch
-    assert lib.ofdft_cnf_gnn_fwd(None, None, None, None, None, None, None, None, 0, 128, 128, 3, 3, 4, 7, 3, 3, 16,
-                                 0.0, 1.0, -1.0) == -1            # row stride too small for full jets
-    assert lib.ofdft_cnf_gnn_bwd(None, None, None, None, None, None, None, None, None, 0, 128, 128, 4, 3, 7, 3, 3, 16,
-                                 0.0, 1.0, -1.0) == -1            # jets out of range
+    N = None
+    assert lib.ofdft_cnf_gnn_fwd(N, N, N, N, N, N, N, N, N, 0, 128, 128, 3, 3, 7, 7, 3, 3, 16, 0.0, 1.0, -1.0) == -1
+    assert lib.ofdft_cnf_gnn_fwd(N, N, N, N, N, N, N, N, N, 0, 0, 0, 3, 3, 7, 7, 3, 3, 16, 0.0, 1.0, -1.0) == -1   # B <= 0
+    assert lib.ofdft_cnf_gnn_fwd(N, N, N, N, N, N, N, N, N, 0, 128, 128, 3, 3, 7, 7, 99, 3, 16, 0.0, 1.0, -1.0) == -2  # Na
+    assert lib.ofdft_cnf_gnn_fwd(N, N, N, N, N, N, N, N, N, 0, 128, 128, 3, 3, 4, 7, 3, 3, 16, 0.0, 1.0, -1.0) == -1  # stride
+    assert lib.ofdft_cnf_gnn_bwd(N, N, N, N, N, N, N, N, N, N, 0, 128, 128, 4, 3, 7, 3, 3, 16, 0.0, 1.0, -1.0) == -1  # jets
     spec = _lib.EnergySpecC(2, 3, 1, 1, 1, 0, 2.0, 0.0, 0.0, 0.0)   # d = 2 is not a thing
     assert lib.ofdft_functionals_fwd_bwd(None, C.byref(spec), None, None, None, 7, 16, None, None, None, 0) == -1
     assert lib.ofdft_hartree_allpairs(None, 1, 3, 2.0, None, None, 3, 10, 10, None, None, None, None, 0) == -1

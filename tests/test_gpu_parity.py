@@ -94,8 +94,8 @@ def test_training_step_matches_oracle_same_scheme(molname, bs, nuc):
     e_ref, terms_ref, g_ref, _ = O.loss_and_grad(fld, ospec, batch, n_steps=n_steps)
     model = Gen_EqvFlow(3, (64, 64), mol["coords"], mol["onehot"], bool_neg=True)
     spec = ops.EnergySpec(Ne=mol["Ne"], d=3, kin="tf-w", hart="hartree", nuc=nuc, x="lda", coords=mol["coords"], z=mol["z"])
-    for skip in (True, False):
-        est = EnergyEstimator(model, spec, n_steps=n_steps, skip_unused_jets=skip)
+    for skip, act in ((True, True), (True, False), (False, True), (False, False)):
+        est = EnergyEstimator(model, spec, n_steps=n_steps, skip_unused_jets=skip, act_ckpt=act)
         sums, tbar, _ = est.step_flat(dev(theta), dev(batch))
         sums = sums.cpu().numpy(); g = tbar.cpu().numpy()
         for i in range(4):
@@ -244,9 +244,12 @@ def test_full_size_roundtrip_self_convergence_and_determinism():
     a, b = s16.cpu().numpy(), s32.cpu().numpy()
     assert np.all(np.abs(a[:4] - b[:4]) <= E_TOL * np.abs(b[:4]))
     assert rel(g16.cpu().numpy(), g32.cpu().numpy()) <= G_TOL
-    # skipping the unused second-half jets does not change the result
+    # skipping the unused second-half jets does not change the result; neither does recomputing the layer-2
+    # activations in the backward pass instead of reading the HBM checkpoint
     s_full, g_full, _ = EnergyEstimator(model, spec, n_steps=16, skip_unused_jets=False).step_flat(th, y)
     assert np.allclose(s_full.cpu().numpy(), a, rtol=1e-12) and rel(g_full.cpu().numpy(), g16.cpu().numpy()) < 1e-6
+    s_rc, g_rc, _ = EnergyEstimator(model, spec, n_steps=16, act_ckpt=False).step_flat(th, y)
+    assert torch.equal(s_rc, s16) and rel(g_rc.cpu().numpy(), g16.cpu().numpy()) < 1e-6
     # sharding invariance: two half-batches (paired shards) average to the full-batch result (section 8e)
     from ofdft_nflows_b200.estimator import shard_batch
     est = EnergyEstimator(model, spec, n_steps=16)
