@@ -135,10 +135,13 @@ int ofdft_cnf_gnn_rhs(void* stream, const float* theta, const float* nuclei, con
 
 /* ---- 1-D tanh-MLP flow (Gen_CNFSimpleMLP, cn_flows.py:166-182; LiH.py:64-65 uses (512,512,512)) --
  * Same contract as the GNN entry points with d = 1: rows [x | logp | s]; theta per the layout above
- * with I = 2.  Supported: n_layers in [2,4], hidden width H multiple of 64 up to 512.
+ * with I = 2.  Supported: n_layers in [2,4], hidden width H multiple of 64 up to 512; the backward pass is
+ * instantiated for jets == OFDFT_JETS_FULL.  scratch (ofdft_cnf_mlp1d_scratch_bytes) holds 16-byte-aligned
+ * (and transposed) copies of the hidden kernels and, for the backward pass, the per-stage activation /
+ * cotangent jets of a 2048-row chunk that the weight-gradient GEMM contracts (~2 MB per row at H=512, RK4x16).
  */
 size_t ofdft_cnf_mlp1d_ckpt_bytes(int64_t B, int32_t n_steps);
-size_t ofdft_cnf_mlp1d_scratch_bytes(int64_t B, int32_t H, int32_t n_layers);
+size_t ofdft_cnf_mlp1d_scratch_bytes(int64_t B, int32_t H, int32_t n_layers, int32_t n_steps);
 int ofdft_cnf_mlp1d_fwd(void* stream, const float* theta, const float* y_in, float* y_out, float* ckpt,
                         void* scratch, size_t scratch_bytes, int64_t B, int32_t jets, int32_t stride,
                         int32_t H, int32_t n_layers, int32_t n_steps, float t0, float t1, float y0sign);

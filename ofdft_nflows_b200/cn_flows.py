@@ -62,7 +62,7 @@ def mlp_fwd(theta, batch, f: Gen_CNFSimpleMLP, t0: float, t1: float, jets: int, 
     ckpt = None
     if want_ckpt:
         ckpt = torch.empty(lib.ofdft_cnf_mlp1d_ckpt_bytes(B, n_steps) // 4, dtype=torch.float32, device=batch.device)
-    sb = lib.ofdft_cnf_mlp1d_scratch_bytes(B, f.H, f.n_layers)
+    sb = lib.ofdft_cnf_mlp1d_scratch_bytes(B, f.H, f.n_layers, n_steps)
     scratch = torch.empty(sb, dtype=torch.uint8, device=batch.device)
     _lib.check(lib.ofdft_cnf_mlp1d_fwd(ops._stream(), ops._ptr(theta), ops._ptr(batch), ops._ptr(y1), ops._ptr(ckpt),
                                        ops._ptr(scratch), sb, B, jets, stride, f.H, f.n_layers, n_steps,
@@ -78,7 +78,7 @@ def mlp_bwd(theta, ckpt, ybar1, f: Gen_CNFSimpleMLP, t0: float, t1: float, jets:
     B, stride = ybar1.shape
     tbar = torch.empty_like(theta)
     ybar0 = torch.zeros_like(ybar1) if want_ybar0 else None
-    sb = lib.ofdft_cnf_mlp1d_scratch_bytes(B, f.H, f.n_layers)
+    sb = lib.ofdft_cnf_mlp1d_scratch_bytes(B, f.H, f.n_layers, n_steps)
     scratch = torch.empty(sb, dtype=torch.uint8, device=ybar1.device)
     _lib.check(lib.ofdft_cnf_mlp1d_bwd(ops._stream(), ops._ptr(theta), ops._ptr(ckpt), ops._ptr(ybar1), ops._ptr(tbar),
                                        ops._ptr(ybar0), ops._ptr(scratch), sb, B, jets, stride, f.H, f.n_layers, n_steps,

@@ -1,16 +1,674 @@
-// mlp1d.cu -- 1-D tanh-MLP flow (Gen_CNFSimpleMLP, ofdft_normflows/cn_flows.py:117-182).
-// Placeholder entry points: implemented after the GNN path.
+// mlp1d.cu -- fused fixed-step (RK4) integrator and discrete adjoint for the 1-D tanh-MLP flow
+// g(x,t) = MLP([t', x])  (reference: ofdft_normflows/cn_flows.py:117-182 through jax_ode.py:9-110; LiH.py:64-65 uses
+// features (512,512,512)).  sm_100a, FP32 FFMA pipe (round 1; the tcgen05 3xTF32 GEMM tiles are the next step).
+//
+// One CTA = one tile of 8 trajectories, H/2 threads: thread = (trajectory t, column group g of 16 hidden units).
+// Per RHS evaluation the 2-jet (value, d/dx, d2/dx2) of every hidden layer is a [8 traj x 3 jets] x [H x H] GEMM:
+// the activation jets live in shared memory, the weights are streamed through a double-buffered shared-memory ring
+// with cp.async (16 rows per chunk; all CTAs sweep the same 1-2 MB of weights, which stays L2 resident).
+//
+// Backward = discrete adjoint of RK4 on the checkpointed stage states.  Per stage the sweep kernel recomputes the
+// forward jets, runs the transposed GEMMs (W_l^T streamed from a pre-transposed copy) and writes, for every hidden
+// layer, the jets (a, p', p'') and the pre-activation cotangent jets to HBM; the weight gradients
+// dW_l = sum_rows A_{l-1}^T Pbar_l (rows = stage x trajectory x jet, ~2e5 for bs=512) are then ONE split-K GEMM per
+// layer over those buffers -- a per-CTA accumulation would need 1 MB of accumulators per layer, and per-stage
+// atomics would be ~50x slower than the FFMA work.
 #include "common.cuh"
+
+namespace ofdft {
+namespace mlp {
+
+constexpr int kTT = 8;        // trajectories per tile
+constexpr int kKC = 16;       // weight rows per streamed chunk
+constexpr int kMaxL = 4;
+
+struct ThetaLayout {
+  int H, L, n;
+  __host__ __device__ ThetaLayout(int H_, int L_) : H(H_), L(L_) { n = 1 + H + 3 * H + (L - 1) * (H + H * H); }
+  __host__ __device__ int b_last() const { return 0; }
+  __host__ __device__ int w_last() const { return 1; }
+  __host__ __device__ int b(int i) const { return i == 0 ? 1 + H : 1 + 4 * H + (i - 1) * (H + H * H); }
+  __host__ __device__ int w(int i) const { return b(i) + H; }     // layer 0: (2,H) rows [t, x]; else (H,H)
+  // compact layout of everything except the hidden kernels (per-CTA partial buffers of the backward sweep)
+  __host__ __device__ int n_small() const { return 1 + 4 * H + (L - 1) * H; }
+  __host__ __device__ int c_wlast() const { return 1; }
+  __host__ __device__ int c_b0() const { return 1 + H; }
+  __host__ __device__ int c_w0() const { return 1 + 2 * H; }
+  __host__ __device__ int c_b(int l) const { return 1 + 4 * H + (l - 1) * H; }
+  // compact index -> theta offset
+  __host__ __device__ int small_to_theta(int c) const {
+    if (c < 1 + H) return c;                              // b_last, w_last
+    if (c < 1 + 4 * H) return c;                          // b0, w0 share the same offsets (1+H .. 1+4H)
+    const int l = (c - (1 + 4 * H)) / H + 1, i = (c - (1 + 4 * H)) % H;
+    return b(l) + i;
+  }
+};
+
+struct Args {
+  const float* theta;
+  const float* Wc;          // aligned copies of W_1..W_{L-1} (layer index i>=1), each H*H
+  const float* WTc;         // transposes
+  const float* y_in; float* y_out; float* ckpt;
+  const float* ybar1; float* ybar0;
+  float* acts; float* pbar; float* gsmall;   // backward scratch
+  long long B, row_begin, rows;              // this launch handles rows [row_begin, row_begin+rows)
+  int jets, stride, H, L, n_steps; float t0, t1, y0;
+};
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::); }
+
+struct Smem {
+  float *bufA, *bufB, *ws, *wx, *wt, *b1, *bl, *wl, *xs, *hpart, *hbar, *xpart;
+  __device__ Smem(float* base, int H, int L) {
+    bufA = base; base += 3 * H * kTT;
+    bufB = base; base += 3 * H * kTT;
+    ws = base; base += 2 * kKC * H;
+    wx = base; base += H;
+    wt = base; base += H;
+    b1 = base; base += H;
+    bl = base; base += (kMaxL - 1) * H;
+    wl = base; base += H;
+    xs = base; base += kTT;
+    hpart = base; base += (H / 64) * 3 * kTT;
+    hbar = base; base += 3 * kTT;
+    xpart = base; base += (H / 64) * kTT;
+  }
+};
+static size_t smem_bytes(int H) {
+  return sizeof(float) * (size_t)(6 * H * kTT + 2 * kKC * H + 4 * H + (kMaxL - 1) * H + kTT + (H / 64) * 3 * kTT + 3 * kTT +
+                                  (H / 64) * kTT);
+}
+
+__device__ __forceinline__ void issue_chunk(float* dst, const float* __restrict__ src, int H, int tid, int nthreads) {
+  const int n4 = kKC * H / 4;
+  for (int i = tid; i < n4; i += nthreads) cp_async16(dst + 4 * i, src + 4 * i);
+  cp_async_commit();
+}
+
+// acc[jet][c] = sum_k actIn[jet][k][t] * W[k][col(c)],  col(c) = (H/4)*(c>>2) + 4*g + (c&3)
+template <int NJ>
+__device__ __forceinline__ void layer_gemm(float (&acc)[NJ][16], const float* __restrict__ actIn,
+                                           const float* __restrict__ Wg, float* ws, int H, int t, int g, int tid, int nthreads) {
+#pragma unroll
+  for (int jt = 0; jt < NJ; ++jt)
+#pragma unroll
+    for (int c = 0; c < 16; ++c) acc[jt][c] = 0.f;
+  const int nchunks = H / kKC;
+  const int q = H / 4;
+  __syncthreads();                       // writers of actIn and readers of the ring are done
+  issue_chunk(ws, Wg, H, tid, nthreads);
+  for (int c = 0; c < nchunks; ++c) {
+    cp_async_wait_all();
+    __syncthreads();
+    if (c + 1 < nchunks) issue_chunk(ws + ((c + 1) & 1) * kKC * H, Wg + (size_t)(c + 1) * kKC * H, H, tid, nthreads);
+    const float* wb = ws + (c & 1) * kKC * H + 4 * g;
+    const float* ab = actIn + (size_t)(c * kKC) * kTT + t;
+#pragma unroll 4
+    for (int kk = 0; kk < kKC; ++kk) {
+      float av[3];
+      av[0] = ab[kk * kTT];
+      if (NJ >= 2) av[1] = ab[(H + kk) * kTT];
+      if (NJ == 3) av[2] = ab[(2 * H + kk) * kTT];
+      const float4 w0 = *reinterpret_cast<const float4*>(wb + kk * H);
+      const float4 w1 = *reinterpret_cast<const float4*>(wb + kk * H + q);
+      const float4 w2 = *reinterpret_cast<const float4*>(wb + kk * H + 2 * q);
+      const float4 w3 = *reinterpret_cast<const float4*>(wb + kk * H + 3 * q);
+      const float wv[16] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w, w3.x, w3.y, w3.z, w3.w};
+#pragma unroll
+      for (int jt = 0; jt < NJ; ++jt)
+#pragma unroll
+        for (int cc = 0; cc < 16; ++cc) acc[jt][cc] = fmaf(av[jt], wv[cc], acc[jt][cc]);
+    }
+  }
+}
+
+__device__ __forceinline__ int col_of(int c, int g, int H) { return (H / 4) * (c >> 2) + 4 * g + (c & 3); }
+
+// first layer: p = w_x x + (t' w_t + b1), p' = w_x, p'' = 0  ->  jets of a1 into act[jet][col][t]
+template <int NJ>
+__device__ __forceinline__ void first_layer(float* act, const Smem& sm, float x, float tprime, int H, int t, int g) {
+#pragma unroll
+  for (int c = 0; c < 16; ++c) {
+    const int col = col_of(c, g, H);
+    const float w = sm.wx[col];
+    const float a = tanh_f(fmaf(w, x, fmaf(tprime, sm.wt[col], sm.b1[col])));
+    const float sg = fmaf(-a, a, 1.0f);
+    const float a1 = sg * w;
+    act[(size_t)col * kTT + t] = a;
+    if (NJ >= 2) act[(size_t)(H + col) * kTT + t] = a1;
+    if (NJ == 3) act[(size_t)(2 * H + col) * kTT + t] = -2.0f * a * a1 * w;
+  }
+}
+
+// reduce per-thread partials over the column groups: in-warp over 4 groups, then across warps through smem
+template <int N>
+__device__ __forceinline__ void reduce_groups(float (&v)[N], float* part, int t, int g, int tid) {
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    v[i] += __shfl_xor_sync(0xffffffffu, v[i], 8);
+    v[i] += __shfl_xor_sync(0xffffffffu, v[i], 16);
+  }
+  if ((tid & 31) < kTT) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) part[((tid >> 5) * N + i) * kTT + t] = v[i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward kernel
+// ------------------------------------------------------------------------------------------------
+template <int NJ>
+__device__ void fwd_body(const Args& a, float* smem_base) {
+  const int H = a.H, L = a.L;
+  const int tid = threadIdx.x, nthreads = blockDim.x, t = tid & 7, g = tid >> 3, nwarps = nthreads >> 5;
+  Smem sm(smem_base, H, L);
+  const ThetaLayout TL(H, L);
+  for (int i = tid; i < H; i += nthreads) {
+    sm.wt[i] = a.theta[TL.w(0) + i];
+    sm.wx[i] = a.theta[TL.w(0) + H + i];
+    sm.b1[i] = a.theta[TL.b(0) + i];
+    sm.wl[i] = a.theta[TL.w_last() + i];
+    for (int l = 1; l < L; ++l) sm.bl[(l - 1) * H + i] = a.theta[TL.b(l) + i];
+  }
+  const float b_last = a.theta[0];
+  const float h = (a.t1 - a.t0) / (float)a.n_steps;
+  const long long n_tiles = (a.rows + kTT - 1) / kTT;
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const bool owner = tid < kTT;
+    const long long row = a.row_begin + tile * kTT + tid;
+    const bool valid = owner && (tile * kTT + tid) < a.rows;
+    const long long rowc = (tile * kTT + tid) < a.rows ? row : a.row_begin + a.rows - 1;
+    float y[3] = {0, 0, 0}, accw[3] = {0, 0, 0}, kst[3] = {0, 0, 0}, xst = 0.f, sst = 0.f;
+    if (owner) {
+      const float* src = a.y_in + rowc * a.stride;
+      y[0] = src[0];
+      if (NJ >= 2) y[1] = src[1];
+      if (NJ == 3) y[2] = src[2];
+    }
+    float acc[NJ][16];
+    for (int step = 0; step < a.n_steps; ++step) {
+      for (int stage = 0; stage < 4; ++stage) {
+        const float cs = stage == 0 ? 0.f : (stage == 3 ? h : 0.5f * h);
+        const float tprime = a.y0 * (a.t0 + h * (float)step + cs);
+        __syncthreads();
+        if (owner) {
+          xst = fmaf(cs, kst[0], y[0]);
+          if (NJ == 3) sst = fmaf(cs, kst[2], y[2]);
+          sm.xs[tid] = xst;
+          if (a.ckpt != nullptr && valid) {
+            float* ck = a.ckpt + ((long long)(step * 4 + stage) * 2) * a.B + row;
+            ck[0] = xst;
+            if (NJ == 3) ck[a.B] = sst;
+          }
+        }
+        __syncthreads();
+        first_layer<NJ>(sm.bufA, sm, sm.xs[t], tprime, H, t, g);
+        float* in = sm.bufA; float* out = sm.bufB;
+        float hp[3] = {0.f, 0.f, 0.f};
+        for (int l = 1; l < L; ++l) {
+          layer_gemm<NJ>(acc, in, a.Wc + (size_t)(l - 1) * H * H, sm.ws, H, t, g, tid, nthreads);
+          const float* bl = sm.bl + (l - 1) * H;
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            const int col = col_of(c, g, H);
+            const float av = tanh_f(acc[0][c] + bl[col]);
+            const float sg = fmaf(-av, av, 1.0f);
+            float a1 = 0.f, a2 = 0.f;
+            if (NJ >= 2) a1 = sg * acc[1][c];
+            if (NJ == 3) a2 = fmaf(sg, acc[2][c], -2.0f * av * a1 * acc[1][c]);
+            if (l + 1 < L) {
+              out[(size_t)col * kTT + t] = av;
+              if (NJ >= 2) out[(size_t)(H + col) * kTT + t] = a1;
+              if (NJ == 3) out[(size_t)(2 * H + col) * kTT + t] = a2;
+            } else {
+              const float w = sm.wl[col];
+              hp[0] = fmaf(w, av, hp[0]); hp[1] = fmaf(w, a1, hp[1]); hp[2] = fmaf(w, a2, hp[2]);
+            }
+          }
+          float* tmp = in; in = out; out = tmp;
+        }
+        reduce_groups<3>(hp, sm.hpart, t, g, tid);
+        __syncthreads();
+        if (owner) {
+          float h0 = b_last, h1 = 0.f, h2 = 0.f;
+          for (int w = 0; w < nwarps; ++w) {
+            h0 += sm.hpart[(w * 3 + 0) * kTT + tid]; h1 += sm.hpart[(w * 3 + 1) * kTT + tid]; h2 += sm.hpart[(w * 3 + 2) * kTT + tid];
+          }
+          kst[0] = a.y0 * h0;
+          if (NJ >= 2) kst[1] = -a.y0 * h1;
+          if (NJ == 3) kst[2] = -a.y0 * (h1 * sst + h2);
+          const float wgt = (stage == 0 || stage == 3) ? 1.0f : 2.0f;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) accw[c] = fmaf(wgt, kst[c], accw[c]);
+        }
+      }
+      if (owner) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { y[c] = fmaf(h * (1.0f / 6.0f), accw[c], y[c]); accw[c] = 0.f; }
+      }
+    }
+    if (valid) {
+      float* dst = a.y_out + row * a.stride;
+      dst[0] = y[0];
+      if (NJ >= 2) dst[1] = y[1];
+      if (NJ == 3) dst[2] = y[2];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256, 1) mlp_fwd_kernel(const Args a) {
+  extern __shared__ __align__(16) float smem_f[];
+  if (a.jets == 3) fwd_body<3>(a, smem_f);
+  else if (a.jets == 2) fwd_body<2>(a, smem_f);
+  else fwd_body<1>(a, smem_f);
+}
+
+// aligned copies (and transposes) of the hidden kernels: theta offsets are odd, cp.async needs 16-byte sources
+__global__ void mlp_prep_kernel(const float* __restrict__ theta, float* __restrict__ Wc, float* __restrict__ WTc, int H, int L) {
+  const ThetaLayout TL(H, L);
+  const long long n = (long long)(L - 1) * H * H;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int l = (int)(i / ((long long)H * H)) + 1;
+    const int r = (int)((i % ((long long)H * H)) / H), c = (int)(i % H);
+    const float v = theta[TL.w(l) + r * H + c];
+    Wc[i] = v;
+    if (WTc != nullptr) WTc[(long long)(l - 1) * H * H + (long long)c * H + r] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward sweep kernel (jets = 3 only: the training path)
+// ------------------------------------------------------------------------------------------------
+// HBM block of one (stage, tile): acts[blk][layer 0..L-1][jet: a, p', p''][H][8], pbar[blk][layer 1..L-1][3][H][8]
+__device__ __forceinline__ size_t act_blk(long long blk, int layer, int H, int L) { return ((size_t)blk * L + layer) * 3 * H * kTT; }
+__device__ __forceinline__ size_t pb_blk(long long blk, int layer, int H, int L) { return ((size_t)blk * (L - 1) + (layer - 1)) * 3 * H * kTT; }
+
+struct SmallGrad {          // per-thread partials for this thread's 16 columns (and trajectory t)
+  float gb1[16], gwx[16], gwt[16], gwl[16], gbl[kMaxL - 1][16];
+  float gblast;
+};
+
+__global__ void __launch_bounds__(256, 1) mlp_bwd_sweep_kernel(const Args a) {
+  extern __shared__ __align__(16) float smem_f[];
+  const int H = a.H, L = a.L;
+  const int tid = threadIdx.x, nthreads = blockDim.x, t = tid & 7, g = tid >> 3, nwarps = nthreads >> 5;
+  Smem sm(smem_f, H, L);
+  const ThetaLayout TL(H, L);
+  for (int i = tid; i < H; i += nthreads) {
+    sm.wt[i] = a.theta[TL.w(0) + i];
+    sm.wx[i] = a.theta[TL.w(0) + H + i];
+    sm.b1[i] = a.theta[TL.b(0) + i];
+    sm.wl[i] = a.theta[TL.w_last() + i];
+    for (int l = 1; l < L; ++l) sm.bl[(l - 1) * H + i] = a.theta[TL.b(l) + i];
+  }
+  const float b_last = a.theta[0];
+  const float h = (a.t1 - a.t0) / (float)a.n_steps;
+  const long long n_tiles = (a.rows + kTT - 1) / kTT;
+  SmallGrad G;
+#pragma unroll
+  for (int c = 0; c < 16; ++c) {
+    G.gb1[c] = G.gwx[c] = G.gwt[c] = G.gwl[c] = 0.f;
+#pragma unroll
+    for (int l = 0; l < kMaxL - 1; ++l) G.gbl[l][c] = 0.f;
+  }
+  G.gblast = 0.f;
+  float acc[3][16];
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const bool owner = tid < kTT;
+    const long long row = a.row_begin + tile * kTT + tid;
+    const bool valid = owner && (tile * kTT + tid) < a.rows;
+    const long long rowc = (tile * kTT + tid) < a.rows ? row : a.row_begin + a.rows - 1;
+    float xb = 0.f, lb = 0.f, sb = 0.f;
+    if (valid) { const float* src = a.ybar1 + row * a.stride; xb = src[0]; lb = src[1]; sb = src[2]; }
+    float prevx = 0.f, prevs = 0.f;
+    for (int step = a.n_steps - 1; step >= 0; --step) {
+      float sumx = 0.f, sums = 0.f;
+      for (int stage = 3; stage >= 0; --stage) {
+        const float cs = stage == 0 ? 0.f : (stage == 3 ? h : 0.5f * h);
+        const float tprime = a.y0 * (a.t0 + h * (float)step + cs);
+        const long long blk = (long long)(step * 4 + stage) * n_tiles + tile;
+        float kx = 0.f, kl = 0.f, ks = 0.f, xst = 0.f, sst = 0.f;
+        __syncthreads();
+        if (owner) {
+          const float ca = (stage == 0 || stage == 3) ? h * (1.0f / 6.0f) : h * (1.0f / 3.0f);
+          const float cp = stage == 3 ? 0.f : (stage == 2 ? h : 0.5f * h);
+          kx = fmaf(ca, xb, cp * prevx); ks = fmaf(ca, sb, cp * prevs); kl = ca * lb;
+          const float* ck = a.ckpt + ((long long)(step * 4 + stage) * 2) * a.B + rowc;
+          xst = ck[0]; sst = ck[a.B];
+          sm.xs[tid] = xst;
+          // dx = y0 h ; dlogp = -y0 h' ; ds = -y0 (h' s + h'')
+          const float hb0 = a.y0 * kx, hb1 = -a.y0 * (kl + sst * ks), hb2 = -a.y0 * ks;
+          sm.hbar[tid] = hb0; sm.hbar[kTT + tid] = hb1; sm.hbar[2 * kTT + tid] = hb2;
+          G.gblast += hb0;
+        }
+        __syncthreads();
+        const float x_t = sm.xs[t];
+        const float hb[3] = {sm.hbar[t], sm.hbar[kTT + t], sm.hbar[2 * kTT + t]};
+        // ---- forward recompute, storing (a, p', p'') of every hidden layer ----
+        first_layer<3>(sm.bufA, sm, x_t, tprime, H, t, g);
+        {
+          float* dst = a.acts + act_blk(blk, 0, H, L);
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            const int col = col_of(c, g, H);
+            dst[(size_t)col * kTT + t] = sm.bufA[(size_t)col * kTT + t];
+            dst[(size_t)(H + col) * kTT + t] = sm.wx[col];
+            dst[(size_t)(2 * H + col) * kTT + t] = 0.f;
+          }
+        }
+        float* in = sm.bufA; float* out = sm.bufB;
+        float hp[3] = {0.f, 0.f, 0.f};
+        for (int l = 1; l < L; ++l) {
+          layer_gemm<3>(acc, in, a.Wc + (size_t)(l - 1) * H * H, sm.ws, H, t, g, tid, nthreads);
+          const float* bl = sm.bl + (l - 1) * H;
+          float* dst = a.acts + act_blk(blk, l, H, L);
+          float* pdst = a.pbar + pb_blk(blk, l, H, L);
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            const int col = col_of(c, g, H);
+            const float av = tanh_f(acc[0][c] + bl[col]);
+            const float sg = fmaf(-av, av, 1.0f);
+            const float p1 = acc[1][c], p2 = acc[2][c];
+            const float a1 = sg * p1;
+            const float a2 = fmaf(sg, p2, -2.0f * av * a1 * p1);
+            dst[(size_t)col * kTT + t] = av;
+            dst[(size_t)(H + col) * kTT + t] = p1;
+            dst[(size_t)(2 * H + col) * kTT + t] = p2;
+            if (l + 1 < L) {
+              out[(size_t)col * kTT + t] = av; out[(size_t)(H + col) * kTT + t] = a1; out[(size_t)(2 * H + col) * kTT + t] = a2;
+            } else {
+              // last hidden layer: fused last-layer dot and its reverse
+              const float w = sm.wl[col];
+              hp[0] = fmaf(w, av, hp[0]); hp[1] = fmaf(w, a1, hp[1]); hp[2] = fmaf(w, a2, hp[2]);
+              G.gwl[c] += av * hb[0] + a1 * hb[1] + a2 * hb[2];
+              const float ab = w * hb[0], a1b = w * hb[1], a2b = w * hb[2];
+              const float p2b = a2b * sg;
+              const float p1b = sg * fmaf(-4.0f * av * p1, a2b, a1b);
+              const float pzb = sg * (ab - 2.0f * av * p1 * a1b + a2b * fmaf(-2.0f * av, p2, -2.0f * fmaf(-3.0f * av, av, 1.0f) * p1 * p1));
+#pragma unroll
+              for (int li = 0; li < kMaxL - 1; ++li) if (li == l - 1) G.gbl[li][c] += pzb;
+              out[(size_t)col * kTT + t] = pzb; out[(size_t)(H + col) * kTT + t] = p1b; out[(size_t)(2 * H + col) * kTT + t] = p2b;
+              pdst[(size_t)col * kTT + t] = pzb; pdst[(size_t)(H + col) * kTT + t] = p1b; pdst[(size_t)(2 * H + col) * kTT + t] = p2b;
+            }
+          }
+          float* tmp = in; in = out; out = tmp;
+        }
+        // `in` now holds Pbar_{L-1} (0-based layer index L-1); walk the hidden layers backwards
+        float xpart[1] = {0.f};
+        for (int l = L - 1; l >= 1; --l) {
+          layer_gemm<3>(acc, in, a.WTc + (size_t)(l - 1) * H * H, sm.ws, H, t, g, tid, nthreads);
+          const float* src = a.acts + act_blk(blk, l - 1, H, L);
+          float* pdst = l - 1 >= 1 ? a.pbar + pb_blk(blk, l - 1, H, L) : nullptr;
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            const int col = col_of(c, g, H);
+            const float av = src[(size_t)col * kTT + t];
+            const float p1 = src[(size_t)(H + col) * kTT + t];
+            const float p2 = src[(size_t)(2 * H + col) * kTT + t];
+            const float sg = fmaf(-av, av, 1.0f);
+            const float ab = acc[0][c], a1b = acc[1][c], a2b = acc[2][c];
+            const float p2b = a2b * sg;
+            const float p1b = sg * fmaf(-4.0f * av * p1, a2b, a1b);
+            const float pzb = sg * (ab - 2.0f * av * p1 * a1b + a2b * fmaf(-2.0f * av, p2, -2.0f * fmaf(-3.0f * av, av, 1.0f) * p1 * p1));
+            if (l - 1 >= 1) {
+#pragma unroll
+              for (int li = 0; li < kMaxL - 1; ++li) if (li == l - 2) G.gbl[li][c] += pzb;
+              out[(size_t)col * kTT + t] = pzb; out[(size_t)(H + col) * kTT + t] = p1b; out[(size_t)(2 * H + col) * kTT + t] = p2b;
+              pdst[(size_t)col * kTT + t] = pzb; pdst[(size_t)(H + col) * kTT + t] = p1b; pdst[(size_t)(2 * H + col) * kTT + t] = p2b;
+            } else {
+              // first layer: p = w_x x + t' w_t + b1, p' = w_x (a parameter), p'' = 0
+              G.gb1[c] += pzb;
+              G.gwt[c] = fmaf(tprime, pzb, G.gwt[c]);
+              G.gwx[c] += fmaf(pzb, x_t, p1b);
+              xpart[0] = fmaf(pzb, sm.wx[col], xpart[0]);
+            }
+          }
+          float* tmp = in; in = out; out = tmp;
+        }
+        reduce_groups<3>(hp, sm.hpart, t, g, tid);
+        reduce_groups<1>(xpart, sm.xpart, t, g, tid);
+        __syncthreads();
+        if (owner) {
+          float h1 = 0.f, xbar_net = 0.f;
+          for (int w = 0; w < nwarps; ++w) { h1 += sm.hpart[(w * 3 + 1) * kTT + tid]; xbar_net += sm.xpart[w * kTT + tid]; }
+          const float ysx = xbar_net;
+          const float yss = -a.y0 * h1 * ks;
+          sumx += ysx; prevx = ysx; sums += yss; prevs = yss;
+        }
+      }
+      if (owner) { xb += sumx; sb += sums; }
+    }
+    if (valid && a.ybar0 != nullptr) { float* dst = a.ybar0 + row * a.stride; dst[0] = xb; dst[1] = lb; dst[2] = sb; }
+  }
+  (void)b_last;
+  // ---- per-CTA small-parameter partials: sum over the 8 trajectories (lanes 0..7 of each group) ----
+  float* out = a.gsmall + (size_t)blockIdx.x * TL.n_small();
+  auto red8 = [](float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 1); v += __shfl_xor_sync(0xffffffffu, v, 2); v += __shfl_xor_sync(0xffffffffu, v, 4);
+    return v;
+  };
+#pragma unroll
+  for (int c = 0; c < 16; ++c) {
+    const int col = col_of(c, g, H);
+    const float v1 = red8(G.gb1[c]), v2 = red8(G.gwx[c]), v3 = red8(G.gwt[c]), v4 = red8(G.gwl[c]);
+    if (t == 0) { out[TL.c_b0() + col] = v1; out[TL.c_w0() + H + col] = v2; out[TL.c_w0() + col] = v3; out[TL.c_wlast() + col] = v4; }
+#pragma unroll
+    for (int l = 1; l < kMaxL; ++l) {
+      if (l < L) {
+        const float v = red8(G.gbl[l - 1][c]);
+        if (t == 0) out[TL.c_b(l) + col] = v;
+      }
+    }
+  }
+  const float gl = red8(G.gblast);        // owners are lanes 0..7 of warp 0
+  if (tid == 0) out[0] = gl;
+}
+
+// ------------------------------------------------------------------------------------------------
+// dW_l[k][j] = sum_blocks sum_{jet,t} A_{l-1}[blk][jet][k][t] * Pbar_l[blk][jet][j][t]   (split-K over blocks)
+// 64x64 output tile per CTA, 256 threads x (4x4); A jets are rebuilt from (a, p', p'') while staging.
+// ------------------------------------------------------------------------------------------------
+constexpr int kDwTile = 64;
+__global__ void __launch_bounds__(256) mlp_dw_gemm_kernel(const float* __restrict__ acts, const float* __restrict__ pbar,
+                                                         float* __restrict__ part, int H, int L, int layer,
+                                                         long long n_blocks, int splits) {
+  __shared__ __align__(16) float As[3 * kTT][kDwTile + 4];
+  __shared__ __align__(16) float Bs[3 * kTT][kDwTile + 4];
+  const int tid = threadIdx.x;
+  const int k0 = blockIdx.x * kDwTile, j0 = blockIdx.y * kDwTile, sp = blockIdx.z;
+  const int tk = (tid >> 4) * 4, tj = (tid & 15) * 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const long long per = (n_blocks + splits - 1) / splits;
+  const long long b_begin = sp * per, b_end = b_begin + per < n_blocks ? b_begin + per : n_blocks;
+  for (long long blk = b_begin; blk < b_end; ++blk) {
+    const float* asrc = acts + act_blk(blk, layer - 1, H, L);
+    const float* psrc = pbar + pb_blk(blk, layer, H, L);
+    __syncthreads();
+    // stage: 64 units x 8 traj per jet; thread -> (unit u = tid>>2, traj pair tt = (tid&3)*2)
+    {
+      const int u = tid >> 2, tt = (tid & 3) * 2;
+      const float2 av = *reinterpret_cast<const float2*>(asrc + (size_t)(k0 + u) * kTT + tt);
+      const float2 p1 = *reinterpret_cast<const float2*>(asrc + (size_t)(H + k0 + u) * kTT + tt);
+      const float2 p2 = *reinterpret_cast<const float2*>(asrc + (size_t)(2 * H + k0 + u) * kTT + tt);
+      const float sgx = fmaf(-av.x, av.x, 1.0f), sgy = fmaf(-av.y, av.y, 1.0f);
+      const float a1x = sgx * p1.x, a1y = sgy * p1.y;
+      As[tt][u] = av.x; As[tt + 1][u] = av.y;
+      As[kTT + tt][u] = a1x; As[kTT + tt + 1][u] = a1y;
+      As[2 * kTT + tt][u] = fmaf(sgx, p2.x, -2.0f * av.x * a1x * p1.x);
+      As[2 * kTT + tt + 1][u] = fmaf(sgy, p2.y, -2.0f * av.y * a1y * p1.y);
+#pragma unroll
+      for (int jt = 0; jt < 3; ++jt) {
+        const float2 pv = *reinterpret_cast<const float2*>(psrc + (size_t)(jt * H + j0 + u) * kTT + tt);
+        Bs[jt * kTT + tt][u] = pv.x; Bs[jt * kTT + tt + 1][u] = pv.y;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 3 * kTT; ++r) {
+      const float4 av = *reinterpret_cast<const float4*>(&As[r][tk]);
+      const float4 bv = *reinterpret_cast<const float4*>(&Bs[r][tj]);
+      const float a4[4] = {av.x, av.y, av.z, av.w}, b4[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a4[i], b4[j], acc[i][j]);
+    }
+  }
+  float* out = part + (size_t)sp * H * H;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) out[(size_t)(k0 + tk + i) * H + j0 + tj + j] = acc[i][j];
+}
+
+// theta_bar[w(l) + i] (+)= sum_splits part[s][i]
+__global__ void mlp_dw_reduce_kernel(const float* __restrict__ part, float* __restrict__ theta_bar, int off, int n, int splits,
+                                     int accumulate) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double s = accumulate ? (double)theta_bar[off + i] : 0.0;
+  for (int k = 0; k < splits; ++k) s += (double)part[(size_t)k * n + i];
+  theta_bar[off + i] = (float)s;
+}
+
+// small parameters: theta_bar[p] (+)= sum_ctas gsmall[c][p] for every p outside the hidden kernels
+__global__ void mlp_small_reduce_kernel(const float* __restrict__ gsmall, float* __restrict__ theta_bar, int H, int L, int nblk,
+                                        int accumulate) {
+  const ThetaLayout TL(H, L);
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ns = TL.n_small();
+  if (c >= ns) return;
+  const int p = TL.small_to_theta(c);                          // hidden kernels come from the dW GEMM
+  double s = accumulate ? (double)theta_bar[p] : 0.0;
+  for (int b = 0; b < nblk; ++b) s += (double)gsmall[(size_t)b * ns + c];
+  theta_bar[p] = (float)s;
+}
+
+constexpr long long kChunkRows = 2048;     // backward row chunk (bounds the HBM activation scratch)
+constexpr int kDwSplits = 16;
+static size_t al256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+struct ScratchLayout {
+  size_t wc, wtc, gsmall, part, acts, pbar, total;
+  ScratchLayout(long long B, int H, int L, int n_steps) {
+    const long long rows = B < kChunkRows ? B : kChunkRows;
+    const long long n_tiles = (rows + kTT - 1) / kTT;
+    const long long n_blocks = (long long)n_steps * 4 * n_tiles;
+    size_t o = 0;
+    wc = o; o += al256((size_t)(L - 1) * H * H * 4);
+    wtc = o; o += al256((size_t)(L - 1) * H * H * 4);
+    gsmall = o; o += al256((size_t)256 * ThetaLayout(H, L).n_small() * 4);
+    part = o; o += al256((size_t)kDwSplits * H * H * 4);
+    acts = o; o += al256((size_t)n_blocks * L * 3 * H * kTT * 4);
+    pbar = o; o += al256((size_t)n_blocks * (L - 1) * 3 * H * kTT * 4);
+    total = o;
+  }
+};
+
+static int check_shape(int64_t B, int jets, int stride, int H, int L, int n_steps) {
+  if (B <= 0 || n_steps <= 0 || jets < 1 || jets > 3) return OFDFT_EINVAL;
+  if (stride < (jets == 3 ? 3 : jets)) return OFDFT_EINVAL;
+  if (H < 64 || H > 512 || H % 64 || L < 2 || L > kMaxL) return OFDFT_EUNSUPPORTED;
+  return 0;
+}
+
+}  // namespace mlp
+}  // namespace ofdft
+
+using namespace ofdft;
+using namespace ofdft::mlp;
 
 extern "C" size_t ofdft_cnf_mlp1d_ckpt_bytes(int64_t B, int32_t n_steps) {
   return (size_t)n_steps * 4 * 2 * (size_t)B * sizeof(float);
 }
-extern "C" size_t ofdft_cnf_mlp1d_scratch_bytes(int64_t, int32_t, int32_t) { return 256; }
-extern "C" int ofdft_cnf_mlp1d_fwd(void*, const float*, const float*, float*, float*, void*, size_t, int64_t, int32_t,
-                                   int32_t, int32_t, int32_t, int32_t, float, float, float) {
-  return OFDFT_EUNSUPPORTED;
+extern "C" size_t ofdft_cnf_mlp1d_scratch_bytes(int64_t B, int32_t H, int32_t n_layers, int32_t n_steps) {
+  if (B <= 0 || H <= 0 || n_layers < 2 || n_layers > kMaxL || n_steps <= 0) return 256;
+  return ScratchLayout(B, H, n_layers, n_steps).total;
 }
-extern "C" int ofdft_cnf_mlp1d_bwd(void*, const float*, const float*, const float*, float*, float*, void*, size_t,
-                                   int64_t, int32_t, int32_t, int32_t, int32_t, int32_t, float, float, float) {
-  return OFDFT_EUNSUPPORTED;
+
+extern "C" int ofdft_cnf_mlp1d_fwd(void* stream, const float* theta, const float* y_in, float* y_out, float* ckpt,
+                                   void* scratch, size_t scratch_bytes, int64_t B, int32_t jets, int32_t stride,
+                                   int32_t H, int32_t n_layers, int32_t n_steps, float t0, float t1, float y0sign) {
+  int rc = check_shape(B, jets, stride, H, n_layers, n_steps);
+  if (rc) return rc;
+  if (!theta || !y_in || !y_out || !scratch) return OFDFT_EINVAL;
+  const ScratchLayout SL(B, H, n_layers, n_steps);
+  if (scratch_bytes < SL.wtc) return OFDFT_ESCRATCH;          // forward only needs the aligned weight copies
+  cudaStream_t st = (cudaStream_t)stream;
+  float* Wc = (float*)((char*)scratch + SL.wc);
+  mlp_prep_kernel<<<256, 256, 0, st>>>(theta, Wc, nullptr, H, n_layers);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return (int)e;
+  const size_t smem = smem_bytes(H);
+  e = cudaFuncSetAttribute(mlp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  Args a{};
+  a.theta = theta; a.Wc = Wc; a.y_in = y_in; a.y_out = y_out; a.ckpt = ckpt; a.B = B; a.row_begin = 0; a.rows = B;
+  a.jets = jets; a.stride = stride; a.H = H; a.L = n_layers; a.n_steps = n_steps; a.t0 = t0; a.t1 = t1; a.y0 = y0sign;
+  const long long n_tiles = (B + kTT - 1) / kTT;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = (int)(n_tiles < sms ? n_tiles : sms);
+  mlp_fwd_kernel<<<grid, H / 2, smem, st>>>(a);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int ofdft_cnf_mlp1d_bwd(void* stream, const float* theta, const float* ckpt, const float* ybar1,
+                                   float* theta_bar, float* ybar0, void* scratch, size_t scratch_bytes,
+                                   int64_t B, int32_t jets, int32_t stride, int32_t H, int32_t n_layers,
+                                   int32_t n_steps, float t0, float t1, float y0sign) {
+  int rc = check_shape(B, jets, stride, H, n_layers, n_steps);
+  if (rc) return rc;
+  if (jets != 3) return OFDFT_EUNSUPPORTED;                    // the adjoint is instantiated for the training path
+  if (!theta || !ckpt || !ybar1 || !theta_bar || !scratch) return OFDFT_EINVAL;
+  const int L = n_layers;
+  const ScratchLayout SL(B, H, L, n_steps);
+  if (scratch_bytes < SL.total) return OFDFT_ESCRATCH;
+  cudaStream_t st = (cudaStream_t)stream;
+  char* sc = (char*)scratch;
+  float* Wc = (float*)(sc + SL.wc); float* WTc = (float*)(sc + SL.wtc);
+  float* gsmall = (float*)(sc + SL.gsmall); float* part = (float*)(sc + SL.part);
+  mlp_prep_kernel<<<256, 256, 0, st>>>(theta, Wc, WTc, H, L);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return (int)e;
+  const size_t smem = smem_bytes(H);
+  e = cudaFuncSetAttribute(mlp_bwd_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (sms > 256) sms = 256;
+  const ThetaLayout TL(H, L);
+  int chunk_idx = 0;
+  for (long long r0 = 0; r0 < B; r0 += kChunkRows, ++chunk_idx) {
+    const long long rows = B - r0 < kChunkRows ? B - r0 : kChunkRows;
+    const long long n_tiles = (rows + kTT - 1) / kTT;
+    const long long n_blocks = (long long)n_steps * 4 * n_tiles;
+    Args a{};
+    a.theta = theta; a.Wc = Wc; a.WTc = WTc; a.ckpt = const_cast<float*>(ckpt); a.ybar1 = ybar1; a.ybar0 = ybar0;
+    a.acts = (float*)(sc + SL.acts); a.pbar = (float*)(sc + SL.pbar); a.gsmall = gsmall;
+    a.B = B; a.row_begin = r0; a.rows = rows; a.jets = 3; a.stride = stride; a.H = H; a.L = L; a.n_steps = n_steps;
+    a.t0 = t0; a.t1 = t1; a.y0 = y0sign;
+    const int grid = (int)(n_tiles < sms ? n_tiles : sms);
+    mlp_bwd_sweep_kernel<<<grid, H / 2, smem, st>>>(a);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    mlp_small_reduce_kernel<<<(TL.n_small() + 255) / 256, 256, 0, st>>>(gsmall, theta_bar, H, L, grid, chunk_idx > 0);
+    for (int l = 1; l < L; ++l) {
+      dim3 gg(H / kDwTile, H / kDwTile, kDwSplits);
+      mlp_dw_gemm_kernel<<<gg, 256, 0, st>>>(a.acts, a.pbar, part, H, L, l, n_blocks, kDwSplits);
+      mlp_dw_reduce_kernel<<<(H * H + 255) / 256, 256, 0, st>>>(part, theta_bar, TL.w(l), H * H, kDwSplits, chunk_idx > 0);
+    }
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+  }
+  return 0;
 }

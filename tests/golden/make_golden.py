@@ -48,7 +48,53 @@ def case_3d(name, molname, bs, nuc, seed, last_scale):
     print(name, "E", e, "terms", terms, "steps", stats)
 
 
+def theta_1d(seed, feat):
+    """Deterministic parameters + inputs of the 1-D golden case (shared with the tests)."""
+    rng = np.random.default_rng(seed)
+    p = O.init_params(rng, 2, feat, 1, last_scale=0.5)
+    for w, b in p.hidden:
+        b[:] = 0.1 * rng.standard_normal(b.shape)
+    p.last[1][:] = 0.05
+    return O.flatten_params(p).astype(np.float32).astype(np.float64), rng
+
+
+def tensor_slices_1d(feat):
+    H, L = feat[0], len(feat)
+    sl = {"b_last": (0, 1), "w_last": (1, 1 + H), "b0": (1 + H, 1 + 2 * H), "w0": (1 + 2 * H, 1 + 4 * H)}
+    o = 1 + 4 * H
+    for l in range(1, L):
+        sl[f"b{l}"] = (o, o + H); sl[f"w{l}"] = (o + H, o + H + H * H); o += H + H * H
+    return sl
+
+
+def tensor_norms_1d(g, feat):
+    return np.array([np.linalg.norm(g[a:b]) for a, b in tensor_slices_1d(feat).values()])
+
+
+def case_1d(name, bs, seed, feat=(512, 512, 512)):
+    """LiH 1-D (LiH.py defaults: CNF(1,(512,512,512)), tfw_1d + softc + attr, R=0.7, Z=(3,1), Ne=2)."""
+    theta, rng = theta_1d(seed, feat)
+    batch = O.batch_generator_1d(rng, bs).astype(np.float32).astype(np.float64)
+    spec = O.EnergySpec(Ne=2, kin="tfw_1d", hart="softc", nuc="attraction", x="", R=0.7, Z_alpha=3, Z_beta=1)
+    model = R.GenCNFSimpleMLP(1, feat, bool_neg=True)
+    e, terms, g, y1, stats = R.value_and_grad_loss(model, theta, 2, feat, batch, spec, method="dopri5")
+    fld = O.MLPField(O.unflatten_params(theta, 2, feat), bool_neg=True)
+    e2, terms2, y12, _ = O.loss_adaptive(fld, spec, batch)
+    _, _, g2, _ = O.loss_and_grad(fld, spec, batch, n_steps=64)
+    assert abs(e - e2) <= 1e-10 * abs(e2), (e, e2)
+    gdev = np.linalg.norm(g - g2) / np.linalg.norm(g2)
+    assert gdev <= 5e-6, gdev
+    # theta (527k floats) is regenerated from the seed by the tests (theta_1d below); the gradient is stored as
+    # per-tensor norms plus every 61st entry, which keeps the fixture small
+    tn = tensor_norms_1d(g2, feat)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), seed=seed, bs=bs, batch=batch.astype(np.float32),
+                        features=np.array(feat), y1=y1, energy=e, terms=terms, grad_norms=tn, grad_sub=g2[::61],
+                        grad_autodiff_dev=gdev, dopri_accepted=stats["accepted"], dopri_nfe=stats["nfe"])
+    print(name, "E", e, "terms", terms, "steps", stats, "gdev", gdev)
+
+
 if __name__ == "__main__":
+    case_1d("lih1d_512x3_bs48", 48, 105)
     case_3d("h2o_hgh_bs96", "H2O", 96, "hgh", 101, 0.5)
     case_3d("h2_point_bs80", "H2", 80, "nuclei_potential", 102, 0.5)
     case_3d("lih_point_bs64", "LiH", 64, "nuclei_potential", 103, 0.5)

@@ -208,7 +208,25 @@ def test_rk4_self_convergence_and_gradient_fd():
     assert abs(fd - g16 @ v) < 1e-6 * max(1.0, abs(fd))
 
 
-@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "*.npz"))))
+def test_oracle_reproduces_golden_vector_1d():
+    import importlib.util
+    spec_ = importlib.util.spec_from_file_location("make_golden", os.path.join(GOLD, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec_); spec_.loader.exec_module(mg)
+    g = np.load(os.path.join(GOLD, "lih1d_512x3_bs48.npz"))
+    feat = tuple(int(f) for f in g["features"])
+    theta, _ = mg.theta_1d(int(g["seed"]), feat)
+    fld = O.MLPField(O.unflatten_params(theta, 2, feat), bool_neg=True)
+    spec = O.EnergySpec(Ne=2, kin="tfw_1d", hart="softc", nuc="attraction", x="", R=0.7, Z_alpha=3, Z_beta=1)
+    e, terms, y1, st = O.loss_adaptive(fld, spec, g["batch"].astype(np.float64))
+    assert abs(e - float(g["energy"])) < 1e-10 * abs(float(g["energy"]))
+    assert np.abs(y1 - g["y1"]).max() < 1e-9
+    e16, t16, g16, _ = O.loss_and_grad(fld, spec, g["batch"].astype(np.float64), n_steps=16)
+    assert np.all(np.abs(t16[:3] - g["terms"][:3]) <= 1e-5 * np.abs(g["terms"][:3]))
+    assert np.allclose(mg.tensor_norms_1d(g16, feat), g["grad_norms"], rtol=1e-4)
+    assert np.linalg.norm(g16[::61] - g["grad_sub"]) <= 1e-4 * np.linalg.norm(g["grad_sub"])
+
+
+@pytest.mark.parametrize("path", sorted(p for p in glob.glob(os.path.join(GOLD, "*.npz")) if "1d" not in os.path.basename(p)))
 def test_oracle_reproduces_golden_vectors(path):
     """The committed fixtures were produced by oracle/ref_torch.py (autodiff transliteration, adaptive Dopri5);
     the closed-form oracle must reproduce them."""
