@@ -33,7 +33,9 @@ WORKLOADS = {
     "h2": ("H2", 4096, "nuclei_potential"),
     "lih": ("LiH", 131072, "nuclei_potential"),
     "c6h6": ("C6H6", 16384, "nuclei_potential"),
+    "lih1d": ("LiH-1D", 512, "attraction"),                   # BASELINE.json configs[0] (LiH.py defaults)
 }
+MLP_FEAT = (512, 512, 512)
 
 
 def algorithmic_flops_per_traj_eval(na: int, jets: int) -> float:
@@ -48,6 +50,15 @@ def make_problem(workload: str, bs: int, seed_offset: int = 0):
     last layer would make the field trivial).  Uses only the package's own host-side input producers."""
     from ofdft_nflows_b200 import utils as U
     molname, _, nuc = WORKLOADS[workload]
+    if workload == "lih1d":
+        rng = np.random.default_rng(4321)
+        Hm, L = MLP_FEAT[0], len(MLP_FEAT)
+        parts = [np.zeros(1), 0.5 * rng.standard_normal(Hm) / math.sqrt(Hm), np.zeros(Hm), rng.standard_normal(2 * Hm) / math.sqrt(2)]
+        for _ in range(L - 1):
+            parts += [np.zeros(Hm), rng.standard_normal(Hm * Hm) / math.sqrt(Hm)]
+        theta = np.concatenate(parts).astype(np.float32)
+        batch = next(U.batche_generator_1D(1234 + seed_offset, bs))
+        return {"Ne": 2, "coords": np.zeros((2, 3)), "z": np.array([3., 1.]), "onehot": None}, nuc, theta, batch
     Ne, atoms, z, coords = U.coordinates(molname)
     onehot = U.one_hot_encode(z) if molname == "C6H6" else U.jax_one_hot(z)     # OFDFT_NF.py:73 vs H20_...py:83-84
     mol = {"coords": coords, "z": z, "Ne": Ne, "onehot": onehot}
@@ -110,6 +121,12 @@ def cpu_reference_step(workload: str, bs: int, threads: int):
     from oracle import ofdft_oracle as O, ref_torch as R
     torch.set_num_threads(threads)
     mol, nuc, theta, batch = make_problem(workload, bs)
+    if workload == "lih1d":
+        spec = O.EnergySpec(Ne=2, kin="tfw_1d", hart="softc", nuc="attraction", x="", R=0.7, Z_alpha=3, Z_beta=1)
+        model = R.GenCNFSimpleMLP(1, MLP_FEAT, bool_neg=True)
+        t0 = time.perf_counter()
+        R.value_and_grad_loss(model, theta.astype(np.float64), 2, MLP_FEAT, batch.astype(np.float64), spec, method="dopri5")
+        return time.perf_counter() - t0, 2 * bs
     nt = mol["onehot"].shape[1]
     spec = O.EnergySpec(Ne=mol["Ne"], kin="tf-w", hart="hartree", nuc=nuc, x="lda", coords=mol["coords"], z=mol["z"])
     model = R.GenEqvFlow((H, H), mol["coords"], mol["onehot"], bool_neg=True)
@@ -129,10 +146,12 @@ def run_reference(args):
     wl = args.workload
     # size the sample so that (steps + warmup) steps take about two minutes
     cpu_reference_step(wl, 64, cores)                       # warm the thread pool / autograd caches
-    t_probe, n_probe = cpu_reference_step(wl, 1024, cores)
+    t_probe, n_probe = cpu_reference_step(wl, 1024 if wl != "lih1d" else 128, cores)
     per_traj = t_probe / n_probe
     budget = 120.0 / max(1, args.steps + args.warmup)
-    bs = int(max(256, min(8192, budget / per_traj / 2)))
+    bs = int(max(64 if wl == "lih1d" else 256, min(8192, budget / per_traj / 2)))
+    if wl == "lih1d":
+        bs = min(bs, 512)
     for _ in range(args.warmup):
         cpu_reference_step(wl, bs, cores)
     times = []
@@ -198,8 +217,14 @@ def main():
     mol, nuc, theta_np, batch_np = make_problem(args.workload, bs, seed_offset=rank)
     B = 2 * bs
     na = mol["coords"].shape[0]
-    model = Gen_EqvFlow(3, (H, H), mol["coords"], mol["onehot"], bool_neg=True, device=dev)
-    spec = ops.EnergySpec(Ne=mol["Ne"], d=3, kin="tf-w", hart="hartree", nuc=nuc, x="lda", coords=mol["coords"], z=mol["z"])
+    is_1d = args.workload == "lih1d"
+    if is_1d:
+        from ofdft_nflows_b200.cn_flows import Gen_CNFSimpleMLP
+        model = Gen_CNFSimpleMLP(1, MLP_FEAT, bool_neg=True, device=dev)
+        spec = ops.EnergySpec(Ne=2, d=1, kin="tfw_1d", hart="softc", nuc="attraction", x="", R=0.7, Z_alpha=3, Z_beta=1)
+    else:
+        model = Gen_EqvFlow(3, (H, H), mol["coords"], mol["onehot"], bool_neg=True, device=dev)
+        spec = ops.EnergySpec(Ne=mol["Ne"], d=3, kin="tf-w", hart="hartree", nuc=nuc, x="lda", coords=mol["coords"], z=mol["z"])
     est = EnergyEstimator(model, spec, n_steps=args.n_steps, skip_unused_jets=not args.full_jets, act_ckpt=not args.recompute)
     theta = torch.as_tensor(theta_np, device=dev)
     params = model.unravel(theta)
@@ -272,12 +297,17 @@ def main():
     # ---- roofline of the dominant kernel (the discrete-adjoint backward) ----
     jets_b = 3 if args.full_jets else 1
     evals = 4 * args.n_steps
-    fwd_flops = bs * evals * (algorithmic_flops_per_traj_eval(na, 3) + algorithmic_flops_per_traj_eval(na, jets_b))
+    if is_1d:
+        Hm, L = MLP_FEAT[0], len(MLP_FEAT)
+        fwd_flops = B * evals * ((L - 1) * 3 * 2.0 * Hm * Hm + 3 * 2.0 * Hm + 2 * 2.0 * Hm)    # 3.151 MFLOP
+    else:
+        fwd_flops = bs * evals * (algorithmic_flops_per_traj_eval(na, 3) + algorithmic_flops_per_traj_eval(na, jets_b))
     bwd_flops = 2.0 * fwd_flops
+    kern_avg.setdefault("gnn_bwd", kern_avg.get("mlp_bwd", 0.0)); kern_avg.setdefault("gnn_fwd", kern_avg.get("mlp_fwd", 0.0))
     bwd_s = kern_avg["gnn_bwd"] * 1e-3
     achieved = bwd_flops / bwd_s / 1e12
     roofline = {
-        "bound": "fp32", "kernel": "gnn_bwd_kernel", "achieved": achieved, "peak": ffma_peak / 1e12, "unit": "TFLOP/s",
+        "bound": "fp32", "kernel": "mlp_bwd_sweep_kernel + mlp_dw_gemm_kernel" if is_1d else "gnn_bwd_kernel", "achieved": achieved, "peak": ffma_peak / 1e12, "unit": "TFLOP/s",
         "frac": achieved / (ffma_peak / 1e12), "traffic": None,
         "peak_source": "ofdft_microbench_ffma measured in this run (FP32 FFMA pipe; MEASURED_PEAKS.json holds HBM/bf16 only)",
         "algorithmic_flops_per_launch": bwd_flops, "executed_over_algorithmic": 1.5 if args.recompute else 1.0,
@@ -294,21 +324,23 @@ def main():
             "metric": "training-step trajectories/s (CNF fwd+grad+energy)", "value": value, "unit": "trajectories/s",
             "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_s / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{molname} 3-D equivariant flow (64,64), TF+W / {nuc} / paired Hartree / LDA, "
-                                   f"bs={bs} per GPU ({B} trajectories), RK4 x{args.n_steps}",
+            "config": {"workload": (f"LiH 1-D tanh-MLP flow {MLP_FEAT}, TF1D+W / attraction / soft-Coulomb, bs={bs} per GPU "
+                                    f"({B} trajectories), RK4 x{args.n_steps}") if is_1d else
+                                   (f"{molname} 3-D equivariant flow (64,64), TF+W / {nuc} / paired Hartree / LDA, "
+                                    f"bs={bs} per GPU ({B} trajectories), RK4 x{args.n_steps}"),
                        "second_half_jets": "x only (denp/scorep are unused by the reference loss)" if not args.full_jets
                        else "full (reference dataflow)",
                        "l2": "flushed between timed iterations (256 MiB write)", "parallelism": f"batch-sharded x{n_gpus}"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "trajectories/s", "h2d_bytes_per_step": int(host_batch.numel() * 4),
                     "d2h_bytes_per_step": int(host_sums.numel() * 8 + host_grad.numel() * 4)},
-            "gpu_launches": 5 * args.steps,
+            "gpu_launches": (5 if not is_1d else 4 + 2 + 1 + 2 * (len(MLP_FEAT) - 1) + 2) * args.steps,
             "roofline": roofline,
             "energy_terms_last_step": [float(v) for v in sums.cpu().numpy()[:6]],
         }
         if n_gpus == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            cbs = 2048
+            cbs = 2048 if not is_1d else 256
             cpu_reference_step(args.workload, 64, cores)    # warm-up (thread pool, autograd caches)
             t, n = cpu_reference_step(args.workload, cbs, cores)
             line["cpu_baseline"] = {

@@ -95,9 +95,15 @@ class EnergyEstimator:
                 timers += [("gnn_fwd", e0, e1), ("functionals", e1, e2), ("gnn_bwd", e2, e3)]
         else:
             from .cn_flows import mlp_fwd, mlp_bwd
+            e0 = mark()
             y1, ckpt = mlp_fwd(theta, batch, m, self.t0, self.t1, ops.JETS_FULL, self.n_steps, want_ckpt=True)
+            e1 = mark()
             sums, ybar1 = ops.functionals_fwd_bwd(self.spec, y1)
+            e2 = mark()
             tbar, _ = mlp_bwd(theta, ckpt, ybar1, m, self.t0, self.t1, ops.JETS_FULL, self.n_steps)
+            e3 = mark()
+            if timers is not None:
+                timers += [("mlp_fwd", e0, e1), ("functionals", e1, e2), ("mlp_bwd", e2, e3)]
         if self._dist():
             import torch.distributed as dist
             ws = dist.get_world_size(self.group)
