@@ -318,6 +318,18 @@ def main():
         "step": {"algorithmic_flops": 3.0 * fwd_flops, "frac": 3.0 * fwd_flops / (total_s / args.steps) / ffma_peak},
     }
 
+    # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture (same workload only)
+    try:
+        if args.workload == "h2o" and bs == 65536 and args.n_steps == 16 and not args.recompute and not args.full_jets:
+            prof = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_full_gnn_kernels.json")))
+            for k in prof:
+                if "gnn_bwd_kernel" in k["kernel"]:
+                    gb = lambda v: float(v.split()[0]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[v.split()[1]]
+                    roofline["traffic"] = gb(k["dram__bytes_read.sum"]) + gb(k["dram__bytes_write.sum"])
+                    roofline["traffic_source"] = "profiles/r01_ncu_full_gnn_kernels.json (bytes per launch; 12.9 GB of it is the HBM activation checkpoint)"
+    except Exception:
+        pass
+
     line = None
     if rank == 0:
         line = {
