@@ -190,6 +190,11 @@ int ofdft_hartree_allpairs(void* stream, int32_t kind, int32_t d, float Ne, cons
 int ofdft_microbench_ffma(void* stream, float* sink, int32_t iters, double* ops_out);
 int ofdft_microbench_sfu(void* stream, float* sink, int32_t iters, double* ops_out);
 
+/* Diagnostic: D (128 x 64, all TMEM lanes dumped) = A (M x 64) . W (64 x 64) on tcgen05 kind::tf32 with
+ * `passes` = 1 (plain TF32) or 3 (3xTF32 error-compensated); M in {64, 128}.  Used by tests to pin the hand-written
+ * descriptor / TMEM plumbing that the tensor-core integrator builds on. */
+int ofdft_tc_gemm_test(void* stream, const float* A, const float* W, float* D, int32_t M, int32_t passes);
+
 #ifdef __cplusplus
 }
 #endif

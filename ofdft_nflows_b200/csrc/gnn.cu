@@ -12,38 +12,11 @@
 //   * backward = discrete adjoint of RK4 on the stage states checkpointed by the forward pass:
 //     recompute GEMM, transposed GEMM (W2^T) and the rank-(3*128) update of dW2 kept in a 4x4 register tile
 //     per thread for the whole kernel; small-parameter gradients are reduced with warp butterflies.
-#include "common.cuh"
+#include <cstdlib>
+
+#include "gnn_common.cuh"
 
 namespace ofdft {
-
-struct GnnFwdArgs {
-  const float* theta; const float* nuclei; const float* onehot;
-  const float* y_in; float* y_out; float* ckpt; int* counter;
-  long long B, n_a; int jets_a, jets_b; int in_stride, out_stride;
-  int Na, n_types, n_steps; float t0, t1, y0; int rhs_only; float t_rhs;
-  float* act; long long act_rows_a, act_rows_b;   // optional layer-2 activation checkpoint (rows padded to kTP)
-};
-
-struct GnnBwdArgs {
-  const float* theta; const float* nuclei; const float* onehot;
-  const float* ckpt; const float* ybar1; float* ybar0; float* gpart; int* counter;
-  long long B, n_a; int jets_a, jets_b; int bar_stride;
-  int Na, n_types, n_steps; float t0, t1, y0;
-  const float* act; long long act_rows_a, act_rows_b;
-};
-
-// Layer-2 activation checkpoint (optional; trades 180 GB of HBM for the recompute GEMM of the backward pass):
-// for every RHS evaluation e = (step*4+stage)*Na + nucleus and both row segments, the jets (a2, p2', p2'') as
-// [jet][unit][row] with the row index contiguous (coalesced 8-byte stores per lane).
-struct ActLayout {
-  long long rows_a, rows_b, block; int ja, jb;
-  __host__ __device__ ActLayout(long long ra, long long rb, int ja_, int jb_) : rows_a(ra), rows_b(rb), ja(ja_), jb(jb_) {
-    block = (long long)kH * (ja * ra + jb * rb);
-  }
-  __host__ __device__ long long seg_base(long long e, bool seg_b) const {
-    return e * block + (seg_b ? (long long)kH * ja * rows_a : 0);
-  }
-};
 
 struct SmemFwd {
   float W2[kH * kH];
@@ -234,14 +207,6 @@ __device__ __forceinline__ void load_small(SM& sm, const float* __restrict__ the
     sm.cb[i] = c;
   }
   if (tid < Na * 3) sm.nuc[(tid / 3) * 4 + (tid % 3)] = nuclei[tid];
-}
-
-__device__ __forceinline__ bool next_tile(int* counter, int* slot, long long n_tiles, long long& tile) {
-  __syncthreads();
-  if (threadIdx.x == 0) *slot = atomicAdd(counter, 1);
-  __syncthreads();
-  tile = *slot;
-  return tile < n_tiles;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -800,7 +765,6 @@ __global__ void gnn_grad_reduce_kernel(const float* __restrict__ gpart, float* _
 // ------------------------------------------------------------------------------------------------
 // host launchers
 // ------------------------------------------------------------------------------------------------
-constexpr size_t kCounterBytes = 256;
 
 static int num_sms() {
   int dev = 0, n = 0;
@@ -823,7 +787,6 @@ using namespace ofdft;
 extern "C" size_t ofdft_cnf_gnn_ckpt_bytes(int64_t B, int32_t n_steps) {
   return (size_t)n_steps * 4 * 6 * (size_t)B * sizeof(float);
 }
-static long long pad_rows(long long n) { return (n + kTP - 1) / kTP * kTP; }
 extern "C" size_t ofdft_cnf_gnn_act_ckpt_bytes(int64_t B, int64_t n_a, int32_t jets_a, int32_t jets_b, int32_t Na,
                                                int32_t n_steps) {
   if (B <= 0 || n_a < 0 || n_a > B || Na <= 0 || n_steps <= 0) return 0;
@@ -837,10 +800,17 @@ extern "C" size_t ofdft_cnf_gnn_bwd_scratch_bytes(int64_t B, int64_t n_a, int32_
   return kCounterBytes + (size_t)n_tiles_of(B, n_a) * GnnThetaLayout(n_types).n * sizeof(float);
 }
 
+// OFDFT_B200_GNN_FWD = "tc" (default: tcgen05 3xTF32 layer-2 GEMM) | "ffma" (FP32-pipe kernel of this file)
+static bool use_tc_forward() {
+  const char* e = getenv("OFDFT_B200_GNN_FWD");
+  return !(e != nullptr && e[0] == 'f');
+}
+
 static int launch_fwd(void* stream, GnnFwdArgs& a, void* scratch, size_t scratch_bytes) {
   if (!a.theta || !a.nuclei || !a.y_in || !a.y_out || !scratch) return OFDFT_EINVAL;
   if (a.n_types > 0 && !a.onehot) return OFDFT_EINVAL;
   if (scratch_bytes < kCounterBytes) return OFDFT_ESCRATCH;
+  if (use_tc_forward()) return launch_gnn_fwd_tc(stream, a, scratch, scratch_bytes);
   cudaStream_t st = (cudaStream_t)stream;
   a.counter = (int*)scratch;
   cudaError_t e = cudaMemsetAsync(scratch, 0, kCounterBytes, st);

@@ -1,0 +1,51 @@
+// gnn_common.cuh -- argument blocks and helpers shared by the FFMA (gnn.cu) and tensor-core (gnn_tc.cu) GNN kernels.
+#pragma once
+#include "common.cuh"
+
+namespace ofdft {
+
+struct GnnFwdArgs {
+  const float* theta; const float* nuclei; const float* onehot;
+  const float* y_in; float* y_out; float* ckpt; int* counter;
+  long long B, n_a; int jets_a, jets_b; int in_stride, out_stride;
+  int Na, n_types, n_steps; float t0, t1, y0; int rhs_only; float t_rhs;
+  float* act; long long act_rows_a, act_rows_b;   // optional layer-2 activation checkpoint (rows padded to kTP)
+};
+
+struct GnnBwdArgs {
+  const float* theta; const float* nuclei; const float* onehot;
+  const float* ckpt; const float* ybar1; float* ybar0; float* gpart; int* counter;
+  long long B, n_a; int jets_a, jets_b; int bar_stride;
+  int Na, n_types, n_steps; float t0, t1, y0;
+  const float* act; long long act_rows_a, act_rows_b;
+};
+
+// Layer-2 activation checkpoint (optional; trades 180 GB of HBM for the recompute GEMM of the backward pass):
+// for every RHS evaluation e = (step*4+stage)*Na + nucleus and both row segments, the jets (a2, p2', p2'') as
+// [jet][unit][row] with the row index contiguous (coalesced 8-byte stores per lane).
+struct ActLayout {
+  long long rows_a, rows_b, block; int ja, jb;
+  __host__ __device__ ActLayout(long long ra, long long rb, int ja_, int jb_) : rows_a(ra), rows_b(rb), ja(ja_), jb(jb_) {
+    block = (long long)kH * (ja * ra + jb * rb);
+  }
+  __host__ __device__ long long seg_base(long long e, bool seg_b) const {
+    return e * block + (seg_b ? (long long)kH * ja * rows_a : 0);
+  }
+};
+
+__device__ __forceinline__ bool next_tile(int* counter, int* slot, long long n_tiles, long long& tile) {
+  __syncthreads();
+  if (threadIdx.x == 0) *slot = atomicAdd(counter, 1);
+  __syncthreads();
+  tile = *slot;
+  return tile < n_tiles;
+}
+
+
+constexpr size_t kCounterBytes = 256;
+inline long long pad_rows(long long n) { return (n + kTP - 1) / kTP * kTP; }
+
+// tensor-core forward launcher (gnn_tc.cu); returns a cudaError_t / OFDFT_E* code
+int launch_gnn_fwd_tc(void* stream, GnnFwdArgs& a, void* scratch, size_t scratch_bytes);
+
+}  // namespace ofdft

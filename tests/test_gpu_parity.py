@@ -72,18 +72,19 @@ def test_forward_matches_oracle_same_scheme(molname, bs, n_steps):
     ref = O.odeint_rk4(lambda y, t: fld.rhs(t, y, True), batch, 0.0, 1.0, n_steps)
     th, nuc, oh, y = dev(theta), dev(mol["coords"]), dev(mol["onehot"]), dev(batch)
     y1 = ops.gnn_fwd(th, nuc, oh, y, B, 3, 3, n_steps, 0.0, 1.0, -1.0)[0].cpu().numpy()
-    assert np.abs(y1[:, :4] - ref[:, :4]).max() < 5e-6
+    # fp32 / 3xTF32 arithmetic: a few ulp of the largest state entry
+    assert np.abs(y1[:, :4] - ref[:, :4]).max() < 2e-6 * max(1.0, np.abs(ref[:, :4]).max())
     assert np.abs(y1[:, 4:] - ref[:, 4:]).max() < 5e-6 * max(1.0, np.abs(ref[:, 4:]).max())
     # mixed launch: first half full jets, second half x only; ragged tile tails on both segments
     y1m = ops.gnn_fwd(th, nuc, oh, y, bs, 3, 1, n_steps, 0.0, 1.0, -1.0)[0].cpu().numpy()
     assert np.array_equal(y1m[:bs], y1[:bs])
-    assert np.abs(y1m[bs:, :3] - ref[bs:, :3]).max() < 5e-6
+    assert np.abs(y1m[bs:, :3] - ref[bs:, :3]).max() < 2e-6 * max(1.0, np.abs(ref[:, :3]).max())
     # neural_ode (no score channel), reverse direction t in [-1, 0] with bool_neg=False (rho_rev, H20_...py:132-137)
     frev = O.GNNField(fld.params, mol["coords"], mol["onehot"], bool_neg=False)
     z4 = np.concatenate([batch[:, :3], np.zeros((B, 1))], 1)
     ref_rev = O.odeint_rk4(lambda yy, t: frev.rhs(t, yy, False), z4, -1.0, 0.0, n_steps)
     y_rev = ops.gnn_fwd(th, nuc, oh, dev(z4), B, 2, 2, n_steps, -1.0, 0.0, 1.0)[0].cpu().numpy()
-    assert np.abs(y_rev - ref_rev).max() < 5e-6
+    assert np.abs(y_rev - ref_rev).max() < 2e-6 * max(1.0, np.abs(ref_rev).max())
 
 
 @pytest.mark.parametrize("molname,bs,nuc", [("H2", 128, "nuclei_potential"), ("H2O", 150, "hgh"), ("C6H6", 70, "nuclei_potential")])
