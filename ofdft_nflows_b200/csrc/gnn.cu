@@ -879,7 +879,13 @@ extern "C" int ofdft_cnf_gnn_bwd(void* stream, const float* theta, const float* 
   float* gpart = (float*)((char*)scratch + kCounterBytes);
   GnnBwdArgs a{theta, nuclei, onehot, ckpt, ybar1, ybar0, gpart, (int*)scratch, B, n_a, jets_a, jets_b, bar_stride,
                Na, n_types, n_steps, t0, t1, y0sign, act_ckpt, pad_rows(n_a), pad_rows(B - n_a)};
-  if (act_ckpt != nullptr) gnn_bwd_kernel<true><<<grid, kThreads, sizeof(SmemBwd), st>>>(a);
+  // OFDFT_B200_GNN_BWD = "tc" (default with an activation checkpoint: tcgen05 3xTF32 GEMMs) | "ffma"
+  const char* envb = getenv("OFDFT_B200_GNN_BWD");
+  const bool tc_bwd = act_ckpt != nullptr && !(envb != nullptr && envb[0] == 'f');
+  if (tc_bwd) {
+    const int rc = launch_gnn_bwd_tc(stream, a, grid);
+    if (rc) return rc;
+  } else if (act_ckpt != nullptr) gnn_bwd_kernel<true><<<grid, kThreads, sizeof(SmemBwd), st>>>(a);
   else gnn_bwd_kernel<false><<<grid, kThreads, sizeof(SmemBwd), st>>>(a);
   e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;

@@ -47,5 +47,7 @@ inline long long pad_rows(long long n) { return (n + kTP - 1) / kTP * kTP; }
 
 // tensor-core forward launcher (gnn_tc.cu); returns a cudaError_t / OFDFT_E* code
 int launch_gnn_fwd_tc(void* stream, GnnFwdArgs& a, void* scratch, size_t scratch_bytes);
+// tensor-core backward (needs a.act != nullptr); the caller has reset the tile counter and reduces gpart afterwards
+int launch_gnn_bwd_tc(void* stream, GnnBwdArgs& a, int grid);
 
 }  // namespace ofdft

@@ -315,6 +315,497 @@ __global__ void __launch_bounds__(kThreads, 1) gnn_fwd_tc_kernel(const GnnFwdArg
   if (tid < 32) tc::tmem_dealloc(tmem, 256);
 }
 
+
+// =================================================================================================================
+// tensor-core backward (discrete adjoint) -- requires the layer-2 activation checkpoint
+// =================================================================================================================
+// Per (tile, nucleus, RHS evaluation) and jet:
+//   B1 :  Abar1[jet] (128 traj x 64 k)  = Pbar2[jet] (TMEM A operand, tcgen05.st) . W2^T      3xTF32, 24 MMAs
+//   dW2:  D_dw[(hi|lo) k][j] += A1[jet]^T Pbar2[jet]  with K = trajectory: both operands staged "transposed"
+//         ([chunk of 4 traj][row][4], chunk stride padded by 16 B so the scalar stores are conflict free),
+//         A rows stacked [hi k | lo k] so two MMAs give all four hi/lo cross terms                     32 MMAs
+// The tensor core accumulates with truncation: a D_dw chain spanning the whole tile (~4600 MMAs) biases the gradient by
+// ~1e-4.  D_dw is therefore restarted every (nucleus, RHS evaluation) -- 96 MMAs -- and folded into round-to-nearest fp32
+// accumulators in shared memory (measured: dW2 error 2.8e-4 -> see DESIGN.md).
+constexpr int kA1TChunk = kTP * 4 + 4;      // floats per trajectory-chunk of the stacked A1^T operand (128 rows)
+constexpr int kP2TChunk = kH * 4 + 4;       // floats per trajectory-chunk of a Pbar2^T operand (64 rows)
+constexpr int kColB1 = 0, kColDw = 192, kColA = 256;
+#ifndef OFDFT_TC_FLUSH_PER_EVAL
+#define OFDFT_TC_FLUSH_PER_EVAL 0
+#endif
+constexpr bool kFlushPerEval = OFDFT_TC_FLUSH_PER_EVAL != 0;   // else: once per RK4 stage (Na evaluations, Na*96 MMAs)
+
+struct SmemTcB {
+  float A1T[32 * kA1TChunk];
+  float P2Th[32 * kP2TChunk], P2Tl[32 * kP2TChunk];
+  float WTh[kH * kH], WTl[kH * kH];       // B operand of B1: [j/4][k][j%4] = W2[k][j]
+  float wr[kH], wt[kH], b2[kH], w3[kH];
+  float cb[kMaxNa * kH];
+  float nuc[kMaxNa * 4];
+  float S[8 * kMaxNa * 32];               // per warp, per nucleus: sum over the warp's trajectories of pbar1[k = 32 uh + lane]
+  float xs[3 * kTP];
+  float fbar[3 * kTP];
+  float Fpart[2 * 3 * kTP];
+  float Rpart[2 * kTP];
+  float red[8 * 32 * 4];
+  float DW[kTP * kH];                     // fp32 (round-to-nearest) accumulators of the stacked dW2 tile, [col j][row]
+  uint64_t bar;
+  unsigned int tmem_slot;
+  int tile;
+};
+
+struct TcBwdAccum {
+  float g_b2, g_w3;      // lane <-> unit j = 32 uh + lane, summed over this warp's 32 trajectories
+  float g_wt, g_wr;      // lane <-> unit k = 32 uh + lane
+  float g_b3;            // owner threads
+};
+
+template <int NJ>
+__device__ void bwd_tile_tc(SmemTcB& sm, const GnnBwdArgs& a, long long row0, long long seg_end, float b3, TcBwdAccum& G,
+                            bool seg_b, long long seg_row0, uint32_t tmem, uint32_t& phase, bool& dw_started) {
+  const ActLayout AL(a.act_rows_a, a.act_rows_b, a.jets_a, a.jets_b);
+  const long long act_rows = seg_b ? a.act_rows_b : a.act_rows_a;
+  const long long jet_stride = (long long)kH * act_rows;
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  const int m = 32 * (w & 3) + lane, uh = w >> 2;
+  const bool owner = tid < kTP;
+  const long long row = row0 + tid;
+  const bool valid = owner && row < seg_end;
+  const long long rowc = row < seg_end ? row : seg_end - 1;
+  float xb[3] = {0, 0, 0}, lb = 0.f, sb[3] = {0, 0, 0};
+  if (valid) {
+    const float* src = a.ybar1 + row * a.bar_stride;
+    xb[0] = src[0]; xb[1] = src[1]; xb[2] = src[2];
+    if (NJ >= 2) lb = src[3];
+    if (NJ == 3) { sb[0] = src[4]; sb[1] = src[5]; sb[2] = src[6]; }
+  }
+  const float h = (a.t1 - a.t0) / (float)a.n_steps;
+  float xst[3] = {0, 0, 0}, sst[3] = {0, 0, 0};
+  float kx[3] = {0, 0, 0}, kl = 0.f, ks[3] = {0, 0, 0};
+  float ysx[3] = {0, 0, 0}, yss[3] = {0, 0, 0};
+  float sumx[3], sums[3], prevx[3] = {0, 0, 0}, prevs[3] = {0, 0, 0};
+  const uint32_t idesc = tc::make_idesc_tf32(kTP, kH, 0, 0);
+  const uint32_t tlane = tmem + ((uint32_t)(32 * (w & 3)) << 16);
+  const uint64_t dA1T = tc::make_desc(tc::smem_u32(sm.A1T), kA1TChunk * 4, 128);
+  const uint64_t dP2h = tc::make_desc(tc::smem_u32(sm.P2Th), kP2TChunk * 4, 128);
+  const uint64_t dP2l = tc::make_desc(tc::smem_u32(sm.P2Tl), kP2TChunk * 4, 128);
+  const uint64_t dWTh = tc::make_desc(tc::smem_u32(sm.WTh), kH * 16, 128);
+  const uint64_t dWTl = tc::make_desc(tc::smem_u32(sm.WTl), kH * 16, 128);
+
+  auto pre = [&](int i) {
+    const float* nc = sm.nuc + i * 4;
+    const float d0 = xst[0] - nc[0], d1 = xst[1] - nc[1], d2 = xst[2] - nc[2];
+    const float alpha = fmaf(d0, kx[0], fmaf(d1, kx[1], d2 * kx[2]));
+    float f0b = alpha, f1b = 0.f, f2b = 0.f;
+    if (NJ >= 2) {
+      const float r = sqrtf(fmaf(d0, d0, fmaf(d1, d1, d2 * d2)));
+      f0b = fmaf(-3.0f, kl, f0b);
+      f1b = -r * kl;
+      if (NJ == 3) {
+        const float q = fmaf(d0, sst[0], fmaf(d1, sst[1], d2 * sst[2]));
+        const float beta = fmaf(ks[0], sst[0], fmaf(ks[1], sst[1], ks[2] * sst[2]));
+        const float gam = fmaf(d0, ks[0], fmaf(d1, ks[1], d2 * ks[2])) / r;
+        f0b -= beta;
+        f1b = fmaf(-(q + 4.0f), gam, f1b);
+        f2b = -r * gam;
+      }
+    }
+    f0b *= a.y0; f1b *= a.y0; f2b *= a.y0;
+    sm.fbar[tid] = f0b;
+    if (NJ >= 2) sm.fbar[kTP + tid] = f1b;
+    if (NJ == 3) sm.fbar[2 * kTP + tid] = f2b;
+    G.g_b3 += f0b;
+  };
+  auto post = [&](int i) {
+    const float* nc = sm.nuc + i * 4;
+    float f0 = b3 + sm.Fpart[0 * kTP + tid] + sm.Fpart[3 * kTP + tid], f1 = 0.f, f2 = 0.f;
+    if (NJ >= 2) f1 = sm.Fpart[1 * kTP + tid] + sm.Fpart[4 * kTP + tid];
+    if (NJ == 3) f2 = sm.Fpart[2 * kTP + tid] + sm.Fpart[5 * kTP + tid];
+    float rbar = sm.Rpart[tid] + sm.Rpart[kTP + tid];
+    const float d0 = xst[0] - nc[0], d1 = xst[1] - nc[1], d2 = xst[2] - nc[2];
+    const float r = sqrtf(fmaf(d0, d0, fmaf(d1, d1, d2 * d2)));
+    const float rinv = 1.0f / r;
+    const float u0 = d0 * rinv, u1 = d1 * rinv, u2 = d2 * rinv;
+    float db0 = a.y0 * f0 * kx[0], db1 = a.y0 * f0 * kx[1], db2 = a.y0 * f0 * kx[2];
+    if (NJ >= 2) rbar = fmaf(-a.y0 * f1, kl, rbar);
+    if (NJ == 3) {
+      const float q = fmaf(d0, sst[0], fmaf(d1, sst[1], d2 * sst[2]));
+      const float gam = fmaf(u0, ks[0], fmaf(u1, ks[1], u2 * ks[2]));
+      const float amp = fmaf(f1, q + 4.0f, f2 * r);
+      rbar = fmaf(-a.y0 * f2, gam, rbar);
+      const float qbar = -a.y0 * f1 * gam;
+      const float ua = -a.y0 * amp;
+      db0 = fmaf(qbar, sst[0], fmaf(ua * rinv, ks[0], db0));
+      db1 = fmaf(qbar, sst[1], fmaf(ua * rinv, ks[1], db1));
+      db2 = fmaf(qbar, sst[2], fmaf(ua * rinv, ks[2], db2));
+      rbar = fmaf(-ua * gam, rinv, rbar);
+      yss[0] += fmaf(qbar, d0, -a.y0 * f0 * ks[0]);
+      yss[1] += fmaf(qbar, d1, -a.y0 * f0 * ks[1]);
+      yss[2] += fmaf(qbar, d2, -a.y0 * f0 * ks[2]);
+    }
+    ysx[0] += fmaf(rbar, u0, db0);
+    ysx[1] += fmaf(rbar, u1, db1);
+    ysx[2] += fmaf(rbar, u2, db2);
+  };
+
+  for (int step = a.n_steps - 1; step >= 0; --step) {
+    sumx[0] = sumx[1] = sumx[2] = 0.f; sums[0] = sums[1] = sums[2] = 0.f;
+#pragma unroll 1
+    for (int stage = 3; stage >= 0; --stage) {
+      const float cs = stage == 0 ? 0.f : (stage == 3 ? h : 0.5f * h);
+      const float ts = a.t0 + h * (float)step + cs;
+      const float tprime = a.y0 * ts;
+      if (owner) {
+        const float ca = (stage == 0 || stage == 3) ? h * (1.0f / 6.0f) : h * (1.0f / 3.0f);
+        const float cp = stage == 3 ? 0.f : (stage == 2 ? h : 0.5f * h);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          kx[c] = fmaf(ca, xb[c], cp * prevx[c]);
+          if (NJ == 3) ks[c] = fmaf(ca, sb[c], cp * prevs[c]);
+        }
+        if (NJ >= 2) kl = ca * lb;
+        const float* ck = a.ckpt + ((long long)(step * 4 + stage) * 6) * a.B + rowc;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          xst[c] = ck[(long long)c * a.B];
+          sm.xs[c * kTP + tid] = xst[c];
+          if (NJ == 3) sst[c] = ck[(long long)(3 + c) * a.B];
+        }
+        ysx[0] = ysx[1] = ysx[2] = 0.f; yss[0] = yss[1] = yss[2] = 0.f;
+        pre(0);
+      }
+      __syncthreads();
+#pragma unroll 1
+      for (int i = 0; i < a.Na; ++i) {
+        // ---- layer-2 jets (a2, p2', p2'') of (trajectory m, units 32 uh ..) from the HBM checkpoint ----
+        float q0[32], q1[32], q2[32];
+        {
+          const float* src = a.act + AL.seg_base((long long)(step * 4 + stage) * a.Na + i, seg_b) + (row0 - seg_row0)
+                             + (long long)(32 * uh) * act_rows + m;
+#pragma unroll
+          for (int u = 0; u < 32; ++u) {
+            q0[u] = __ldcs(src + (long long)u * act_rows);
+            if (NJ >= 2) q1[u] = __ldcs(src + jet_stride + (long long)u * act_rows);
+            if (NJ == 3) q2[u] = __ldcs(src + 2 * jet_stride + (long long)u * act_rows);
+          }
+        }
+        // ---- first layer (recomputed): a1 = tanh(w_r r + c) ----
+        float av[32];
+        float r;
+        {
+          const float* nc = sm.nuc + i * 4;
+          const float d0 = sm.xs[m] - nc[0], d1 = sm.xs[kTP + m] - nc[1], d2 = sm.xs[2 * kTP + m] - nc[2];
+          r = sqrtf(fmaf(d0, d0, fmaf(d1, d1, d2 * d2)));
+          const float* cbi = sm.cb + i * kH + 32 * uh;
+#pragma unroll
+          for (int u = 0; u < 32; ++u)
+            av[u] = tanh_f(fmaf(sm.wr[32 * uh + u], r, fmaf(tprime, sm.wt[32 * uh + u], cbi[u])));
+        }
+        // ---- layer-2 tanh-jet: forward partials of f and reverse to the pre-activation cotangents (in place) ----
+        {
+          const float fb0 = sm.fbar[m], fb1 = NJ >= 2 ? sm.fbar[kTP + m] : 0.f, fb2 = NJ == 3 ? sm.fbar[2 * kTP + m] : 0.f;
+          float fp[3] = {0.f, 0.f, 0.f};
+          float v32[32], g32[32];
+#pragma unroll
+          for (int u = 0; u < 32; ++u) {
+            const float wv = sm.w3[32 * uh + u];
+            const float aa = q0[u];
+            const float sg = fmaf(-aa, aa, 1.0f);
+            fp[0] = fmaf(wv, aa, fp[0]);
+            float gw = aa * fb0;
+            float pzb = wv * fb0;
+            if (NJ >= 2) {
+              const float p1 = q1[u];
+              const float a1 = sg * p1;
+              fp[1] = fmaf(wv, a1, fp[1]);
+              gw = fmaf(a1, fb1, gw);
+              const float a1b = wv * fb1;
+              pzb = fmaf(-2.0f * aa * p1, a1b, pzb);
+              float t1 = a1b;
+              if (NJ == 3) {
+                const float p2 = q2[u];
+                const float a2 = fmaf(sg, p2, -2.0f * aa * a1 * p1);
+                fp[2] = fmaf(wv, a2, fp[2]);
+                gw = fmaf(a2, fb2, gw);
+                const float a2b = wv * fb2;
+                q2[u] = a2b * sg;
+                t1 = fmaf(-4.0f * aa * p1, a2b, t1);
+                pzb = fmaf(a2b, fmaf(-2.0f * aa, p2, -2.0f * fmaf(-3.0f * aa, aa, 1.0f) * p1 * p1), pzb);
+              }
+              q1[u] = sg * t1;
+            }
+            q0[u] = sg * pzb;
+            v32[u] = q0[u];
+            g32[u] = gw;
+          }
+#pragma unroll
+          for (int jt = 0; jt < NJ; ++jt) sm.Fpart[(uh * 3 + jt) * kTP + m] = fp[jt];
+          G.g_b2 += warp_vec32_sum(v32, lane);
+          G.g_w3 += warp_vec32_sum(g32, lane);
+        }
+        // ---- per jet: stage operands, run B1 (TS mode) and the dW2 update ----
+#pragma unroll
+        for (int jt = 0; jt < NJ; ++jt) {
+          if (jt > 0) { tc::mbar_wait(&sm.bar, phase); phase ^= 1; __syncwarp(); }
+          const int cbase = (m >> 2), csub = (m & 3);
+          float v32s[32];
+#pragma unroll
+          for (int u = 0; u < 32; ++u) {
+            const float wv = sm.wr[32 * uh + u];
+            const float sg1 = fmaf(-av[u], av[u], 1.0f);
+            const float a1j = jt == 0 ? av[u] : (jt == 1 ? sg1 * wv : -2.0f * av[u] * sg1 * wv * wv);
+            const float pbj = jt == 0 ? q0[u] : (jt == 1 ? q1[u] : q2[u]);
+            float hi, lo;
+            tc::split_tf32(a1j, hi, lo);
+            sm.A1T[cbase * kA1TChunk + (32 * uh + u) * 4 + csub] = hi;
+            sm.A1T[cbase * kA1TChunk + (kH + 32 * uh + u) * 4 + csub] = lo;
+            tc::split_tf32(pbj, hi, lo);
+            sm.P2Th[cbase * kP2TChunk + (32 * uh + u) * 4 + csub] = hi;
+            sm.P2Tl[cbase * kP2TChunk + (32 * uh + u) * 4 + csub] = lo;
+            if (jt == 0) { q0[u] = hi; v32s[u] = lo; } else if (jt == 1) { q1[u] = hi; v32s[u] = lo; } else { q2[u] = hi; v32s[u] = lo; }
+          }
+#pragma unroll
+          for (int c0 = 0; c0 < 32; c0 += 16) {
+            float hv[16], lv[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+              hv[u] = jt == 0 ? q0[c0 + u] : (jt == 1 ? q1[c0 + u] : q2[c0 + u]);
+              lv[u] = v32s[c0 + u];
+            }
+            tc::tmem_st16(tlane + kColA + 32 * uh + c0, hv);
+            tc::tmem_st16(tlane + kColA + kH + 32 * uh + c0, lv);
+          }
+          tc::tmem_st_wait();
+          tc::fence_async_smem();
+          tc::fence_before_sync();
+          __syncthreads();
+          if (w == 0) {
+            tc::fence_after_sync();
+            if (tc::elect_one()) {
+              // B1: D_b1[jt] = Pbar2 (TMEM) . W2^T, 3xTF32
+#pragma unroll
+              for (int p = 0; p < 3; ++p) {
+                const uint32_t acol = tmem + kColA + (p == 1 ? kH : 0);
+                const uint64_t wb = p == 2 ? dWTl : dWTh;
+#pragma unroll
+                for (int ksx = 0; ksx < 8; ++ksx)
+                  tc::mma_tf32_ts(tmem + kColB1 + jt * kH, acol + 8 * ksx, wb + ksx * ((2 * kH * 16) >> 4), idesc, (p | ksx) != 0);
+              }
+              // dW2: D_dw += [A1_hi ; A1_lo]^T-stacked . (P_hi, then P_lo), K = 128 trajectories
+#pragma unroll
+              for (int p = 0; p < 2; ++p) {
+                const uint64_t pb = p == 0 ? dP2h : dP2l;
+#pragma unroll
+                for (int ksx = 0; ksx < 16; ++ksx) {
+                  tc::mma_tf32(tmem + kColDw, dA1T + ksx * ((2 * kA1TChunk * 4) >> 4), pb + ksx * ((2 * kP2TChunk * 4) >> 4), idesc,
+                               (kFlushPerEval ? 0 : i) != 0 || (jt | p | ksx) != 0);
+                }
+              }
+              tc::commit(&sm.bar);
+            }
+            __syncwarp();
+          }
+          dw_started = true;
+        }
+        tc::mbar_wait(&sm.bar, phase); phase ^= 1;
+        __syncwarp();
+        tc::fence_after_sync();
+        // ---- layer-1 reverse from D_b1 (cotangent jets of a1 for trajectory m, units k = 32 uh ..) ----
+        {
+          float rp = 0.f;
+          float ps32[32], pr32[32];
+#pragma unroll
+          for (int c0 = 0; c0 < 32; c0 += 16) {
+            float b0[16], b1[16], b2v[16];
+            tc::tmem_ld16(tlane + kColB1 + 0 * kH + 32 * uh + c0, b0);
+            if (NJ >= 2) tc::tmem_ld16(tlane + kColB1 + 1 * kH + 32 * uh + c0, b1);
+            if (NJ == 3) tc::tmem_ld16(tlane + kColB1 + 2 * kH + 32 * uh + c0, b2v);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+              const float aa = av[c0 + u];
+              const float wv = sm.wr[32 * uh + c0 + u];
+              const float sg = fmaf(-aa, aa, 1.0f);
+              float t = b0[u];
+              float e = 0.f;
+              if (NJ >= 2) {
+                t = fmaf(-2.0f * aa * wv, b1[u], t);
+                e = b1[u];
+                if (NJ == 3) {
+                  t = fmaf(-2.0f * wv * wv * fmaf(-3.0f * aa, aa, 1.0f), b2v[u], t);
+                  e = fmaf(-4.0f * aa * wv, b2v[u], e);
+                }
+              }
+              const float pb = sg * t;
+              rp = fmaf(pb, wv, rp);
+              ps32[c0 + u] = pb;
+              pr32[c0 + u] = fmaf(pb, r, sg * e);
+            }
+          }
+          sm.Rpart[uh * kTP + m] = rp;
+          // fold the dW2 tile into the fp32 accumulators (row m, columns 32 uh ..)
+          if (kFlushPerEval || i == a.Na - 1)
+#pragma unroll
+          for (int c0 = 0; c0 < 32; c0 += 16) {
+            float t[16];
+            tc::tmem_ld16(tlane + kColDw + 32 * uh + c0, t);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int u = 0; u < 16; ++u) sm.DW[(32 * uh + c0 + u) * kTP + m] += t[u];
+          }
+          const float ps = warp_vec32_sum(ps32, lane);
+          const float pr = warp_vec32_sum(pr32, lane);
+          sm.S[(w * kMaxNa + i) * 32 + lane] += ps;
+          G.g_wt = fmaf(tprime, ps, G.g_wt);
+          G.g_wr += pr;
+        }
+        tc::fence_before_sync();
+        __syncthreads();
+        if (owner) {
+          post(i);
+          if (i + 1 < a.Na) pre(i + 1);
+        }
+        if (i + 1 < a.Na) __syncthreads();
+      }
+      if (owner) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          sumx[c] += ysx[c]; prevx[c] = ysx[c];
+          sums[c] += yss[c]; prevs[c] = yss[c];
+        }
+      }
+    }
+    if (owner) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { xb[c] += sumx[c]; sb[c] += sums[c]; }
+    }
+  }
+  if (valid && a.ybar0 != nullptr) {
+    float* dst = a.ybar0 + row * a.bar_stride;
+    dst[0] = xb[0]; dst[1] = xb[1]; dst[2] = xb[2];
+    if (NJ >= 2) dst[3] = lb;
+    if (NJ == 3) { dst[4] = sb[0]; dst[5] = sb[1]; dst[6] = sb[2]; }
+  }
+}
+
+// per-tile partial gradient (same layout and reduction kernel as the FFMA path)
+__device__ void flush_tile_grad_tc(SmemTcB& sm, TcBwdAccum& G, float* __restrict__ out, const GnnThetaLayout& L,
+                                   const float* __restrict__ onehot, int Na, int n_types, uint32_t tmem, bool dw_started) {
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  const int m = 32 * (w & 3) + lane, uh = w >> 2;
+  const uint32_t tlane = tmem + ((uint32_t)(32 * (w & 3)) << 16);
+  // DW rows 0..63 = (hi k) sums, rows 64..127 = (lo k) sums: dW2[k][j] = DW[k][j] + DW[64+k][j]
+  (void)tmem; (void)dw_started; (void)uh;
+  sm.red[(0 * 8 + w) * 32 + lane] = G.g_b2; sm.red[(1 * 8 + w) * 32 + lane] = G.g_w3;
+  sm.red[(2 * 8 + w) * 32 + lane] = G.g_wt; sm.red[(3 * 8 + w) * 32 + lane] = G.g_wr;
+  const float b3w = warp_sum(G.g_b3);
+  G.g_b2 = G.g_w3 = G.g_wt = G.g_wr = G.g_b3 = 0.f;
+  tc::fence_before_sync();
+  __syncthreads();
+  for (int i = tid; i < kH * kH; i += kThreads) {
+    const int k = i / kH, j = i % kH;
+    out[L.W2 + i] = sm.DW[j * kTP + k] + sm.DW[j * kTP + kH + k];
+  }
+  if (tid < kH) {
+    // unit j = k = tid: uh = tid >> 5, lane = tid & 31; the four warps (uh*4 .. uh*4+3) hold partial sums over trajectories
+    const int u2 = tid >> 5, l2 = tid & 31;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int q = 0; q < 4; ++q)
+      for (int ww = 0; ww < 4; ++ww) v[q] += sm.red[(q * 8 + u2 * 4 + ww) * 32 + l2];
+    out[L.b2 + tid] = v[0]; out[L.w3 + tid] = v[1]; out[L.W1 + tid] = v[2]; out[L.W1 + kH + tid] = v[3];
+    float sb1 = 0.f;
+    for (int n = 0; n < Na; ++n) {
+      float sn = 0.f;
+      for (int ww = 0; ww < 4; ++ww) sn += sm.S[((u2 * 4 + ww) * kMaxNa + n) * 32 + l2];
+      sb1 += sn;
+    }
+    out[L.b1 + tid] = sb1;
+    for (int t = 0; t < n_types; ++t) {
+      float s = 0.f;
+      for (int n = 0; n < Na; ++n) {
+        float sn = 0.f;
+        for (int ww = 0; ww < 4; ++ww) sn += sm.S[((u2 * 4 + ww) * kMaxNa + n) * 32 + l2];
+        s = fmaf(onehot[n * n_types + t], sn, s);
+      }
+      out[L.W1 + (2 + t) * kH + tid] = s;
+    }
+  }
+  __syncthreads();
+  if (lane == 0) sm.red[w] = b3w;
+  __syncthreads();
+  if (tid == 0) out[L.b3] = sm.red[0] + sm.red[1] + sm.red[2] + sm.red[3];
+  for (int i = tid; i < 8 * kMaxNa * 32; i += kThreads) sm.S[i] = 0.f;
+  __syncthreads();
+  for (int i = tid; i < kTP * kH; i += kThreads) sm.DW[i] = 0.f;
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kThreads, 1) gnn_bwd_tc_kernel(const GnnBwdArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  SmemTcB& sm = *reinterpret_cast<SmemTcB*>(smem_raw);
+  const int tid = threadIdx.x;
+  const GnnThetaLayout L(a.n_types);
+  for (int i = tid; i < kH * kH; i += kThreads) {
+    const int k = i / kH, j = i % kH;
+    float hi, lo;
+    tc::split_tf32(a.theta[L.W2 + i], hi, lo);
+    const int off = ((j >> 2) * kH + k) * 4 + (j & 3);
+    sm.WTh[off] = hi; sm.WTl[off] = lo;
+  }
+  if (tid < kH) {
+    sm.wt[tid] = a.theta[L.W1 + tid];
+    sm.wr[tid] = a.theta[L.W1 + kH + tid];
+    sm.b2[tid] = a.theta[L.b2 + tid];
+    sm.w3[tid] = a.theta[L.w3 + tid];
+  }
+  for (int i = tid; i < a.Na * kH; i += kThreads) {
+    const int n = i / kH, k = i % kH;
+    float c = a.theta[L.b1 + k];
+    for (int t = 0; t < a.n_types; ++t) c = fmaf(a.onehot[n * a.n_types + t], a.theta[L.W1 + (2 + t) * kH + k], c);
+    sm.cb[i] = c;
+  }
+  if (tid < a.Na * 3) sm.nuc[(tid / 3) * 4 + (tid % 3)] = a.nuclei[tid];
+  for (int i = tid; i < 8 * kMaxNa * 32; i += kThreads) sm.S[i] = 0.f;
+  for (int i = tid; i < kTP * kH; i += kThreads) sm.DW[i] = 0.f;
+  if (tid == 0) { tc::mbar_init(&sm.bar, 1); tc::fence_mbar_init(); }
+  if (tid < 32) tc::tmem_alloc(&sm.tmem_slot, 512);
+  tc::fence_async_smem();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = sm.tmem_slot;
+  uint32_t phase = 0;
+  const float b3 = a.theta[0];
+  TcBwdAccum G;
+  G.g_b2 = G.g_w3 = G.g_wt = G.g_wr = G.g_b3 = 0.f;
+  const long long tiles_a = (a.n_a + kTP - 1) / kTP;
+  const long long tiles_b = (a.B - a.n_a + kTP - 1) / kTP;
+  long long tile;
+  while (next_tile(a.counter, &sm.tile, tiles_a + tiles_b, tile)) {
+    long long row0, seg_end; int nj;
+    bool seg_b; long long seg_row0;
+    if (tile < tiles_a) { row0 = tile * kTP; seg_end = a.n_a; nj = a.jets_a; seg_b = false; seg_row0 = 0; }
+    else { row0 = a.n_a + (tile - tiles_a) * kTP; seg_end = a.B; nj = a.jets_b; seg_b = true; seg_row0 = a.n_a; }
+    bool dw_started = false;
+    if (nj == 3) bwd_tile_tc<3>(sm, a, row0, seg_end, b3, G, seg_b, seg_row0, tmem, phase, dw_started);
+    else if (nj == 2) bwd_tile_tc<2>(sm, a, row0, seg_end, b3, G, seg_b, seg_row0, tmem, phase, dw_started);
+    else bwd_tile_tc<1>(sm, a, row0, seg_end, b3, G, seg_b, seg_row0, tmem, phase, dw_started);
+    __syncthreads();
+    flush_tile_grad_tc(sm, G, a.gpart + (size_t)tile * L.n, L, a.onehot, a.Na, a.n_types, tmem, dw_started);
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (tid < 32) tc::tmem_dealloc(tmem, 512);
+}
+
+int launch_gnn_bwd_tc(void* stream, GnnBwdArgs& a, int grid) {
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaFuncSetAttribute(gnn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemTcB) + 1024);
+  if (e != cudaSuccess) return (int)e;
+  gnn_bwd_tc_kernel<<<grid, kThreads, sizeof(SmemTcB) + 1024, st>>>(a);
+  return (int)cudaGetLastError();
+}
+
 int launch_gnn_fwd_tc(void* stream, GnnFwdArgs& a, void* scratch, size_t scratch_bytes) {
   if (scratch_bytes < kCounterBytes) return OFDFT_ESCRATCH;
   cudaStream_t st = (cudaStream_t)stream;

@@ -106,9 +106,12 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) 
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// 3xTF32 split: hi keeps the top 19 bits (what kind::tf32 reads), lo = x - hi is exact in fp32
+// 3xTF32 split: hi = x rounded to nearest tf32 (ties away: add half an ulp to the sign-magnitude bit pattern, clear the
+// low 13 bits -- two full-rate integer ops; cvt.rna.tf32.f32 issues at a quarter of that rate), lo = x - hi (exact in
+// fp32; the tensor core truncates its low 13 bits).  Rounding hi keeps lo symmetric around zero, so that truncation is
+// unbiased -- it matters for the 1e7-term gradient sums -- and |lo| <= 2^-12 |x| makes the dropped lo.lo term ~2^-24.
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-  hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+  hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
   lo = x - hi;
 }
 

@@ -60,14 +60,15 @@ def main():
         # ---- forward ----
         n_steps = 4
         ref1 = O.odeint_rk4(lambda yy, t: fld.rhs(t, yy, True), batch, 0.0, 1.0, n_steps)
-        y1, ck = ops.gnn_fwd(th, nuc, oh, y, B, 3, 3, n_steps, 0.0, 1.0, -1.0, want_ckpt=True)
+        y1, ck = ops.gnn_fwd(th, nuc, oh, y, B, 3, 3, n_steps, 0.0, 1.0, -1.0, want_ckpt=True, want_act=True)
         y1n = y1.cpu().numpy()
         rep[f"{key}_fwd_j3_maxabs"] = maxabs(y1n, ref1)
         rep[f"{key}_fwd_j3_x"] = maxabs(y1n[:, :3], ref1[:, :3])
         rep[f"{key}_fwd_j3_logp"] = maxabs(y1n[:, 3], ref1[:, 3])
         rep[f"{key}_fwd_j3_s"] = maxabs(y1n[:, 4:], ref1[:, 4:])
+        rep[f"{key}_fwd_j3_s_relmax"] = maxabs(y1n[:, 4:], ref1[:, 4:]) / float(np.abs(ref1[:, 4:]).max())
         na = B // 2
-        y1m, ckm = ops.gnn_fwd(th, nuc, oh, y, na, 3, 1, n_steps, 0.0, 1.0, -1.0, want_ckpt=True)
+        y1m, ckm = ops.gnn_fwd(th, nuc, oh, y, na, 3, 1, n_steps, 0.0, 1.0, -1.0, want_ckpt=True, want_act=True)
         y1mn = y1m.cpu().numpy()
         rep[f"{key}_fwd_mixed_full"] = maxabs(y1mn[:na], ref1[:na])
         rep[f"{key}_fwd_mixed_xonly"] = maxabs(y1mn[na:, :3], ref1[na:, :3])

@@ -322,7 +322,7 @@ def test_full_size_roundtrip_self_convergence_and_determinism():
     s_full, g_full, _ = EnergyEstimator(model, spec, n_steps=16, skip_unused_jets=False).step_flat(th, y)
     assert np.allclose(s_full.cpu().numpy(), a, rtol=1e-12) and rel(g_full.cpu().numpy(), g16.cpu().numpy()) < 1e-6
     s_rc, g_rc, _ = EnergyEstimator(model, spec, n_steps=16, act_ckpt=False).step_flat(th, y)
-    assert torch.equal(s_rc, s16) and rel(g_rc.cpu().numpy(), g16.cpu().numpy()) < 1e-6
+    assert torch.equal(s_rc, s16) and rel(g_rc.cpu().numpy(), g16.cpu().numpy()) < 2e-5    # FFMA recompute vs tcgen05 path
     # sharding invariance: two half-batches (paired shards) average to the full-batch result (section 8e)
     from ofdft_nflows_b200.estimator import shard_batch
     est = EnergyEstimator(model, spec, n_steps=16)
