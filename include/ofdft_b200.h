@@ -172,6 +172,17 @@ int ofdft_functionals_fwd_bwd(void* stream, const ofdft_energy_spec* spec, const
 int ofdft_functionals_integrands(void* stream, const ofdft_energy_spec* spec, const float* coords, const float* z,
                                  const float* y1, int32_t stride, int64_t bs, float* e);
 
+/* One functional of the string-keyed factories on separate array arguments, with its derivatives (the reference's
+ * per-term call signatures, functionals.py):
+ *   family 0: _kinetic(name)(den, score, Ne)              a0 = den (n), a1 = score (n,d)   g0 = d/d den, g1 = d/d score
+ *   family 1: _exchange_correlation(name)(den, score, Ne)  same arguments
+ *   family 2: _hartree(name)(x, xp, Ne)                   a0 = x (n,d), a1 = xp (n,d)      g0 = d/dx, g1 = d/dxp
+ *   family 3: _nuclear(name)(x, Ne, mol_info) / attraction a0 = x (n,d)                     g0 = d/dx
+ * out (n) receives the per-sample integrand; g0 / g1 may be NULL.  The functional is selected by the matching
+ * field of `spec` (the others are ignored); coords / z are HOST pointers as above. */
+int ofdft_functional_eval(void* stream, int32_t family, const ofdft_energy_spec* spec, const float* coords, const float* z,
+                          const float* a0, const float* a1, int64_t n, float* out, float* g0, float* g1);
+
 /* ---- all-pairs Hartree (north-star generalisation of the paired estimator) ----------------------
  * sum_{i<n, j<m} w / sqrt(|x_i - xp_j|^2 + d*eps)   (kind COULOMB, d = 3, w = 0.5 Ne^2)
  * sum_{i,j}      w / sqrt(1 + (x_i - xp_j)^2)       (kind SOFTC,   d = 1, w = Ne^2)

@@ -258,6 +258,57 @@ __global__ void hartree_energy_reduce_kernel(const double* __restrict__ epart, i
   if (threadIdx.x == 0) { double s = 0.0; for (int w = 0; w < 8; ++w) s += red[w]; *out = s * scale; }
 }
 
+// ------------------------------------------------------------------------------------------------
+// string-keyed functional factories (functionals.py:21-43,164-183,425-436,504-521): per-sample integrand (n,1)
+// and its derivatives w.r.t. the two array arguments, on separate (den, score) / (x, xp) / (x) inputs
+// ------------------------------------------------------------------------------------------------
+struct FevArgs {
+  ofdft_energy_spec spec;
+  float coords[kFnMaxNuc * 3];
+  float z[kFnMaxNuc];
+  int family;                 // 0 kinetic(den, score)  1 exchange(den, score)  2 hartree(x, xp)  3 nuclear(x)
+  const float* a0; const float* a1; long long n;
+  float* out; float* g0; float* g1;
+};
+
+__global__ void __launch_bounds__(kFnThreads) functional_eval_kernel(const FevArgs a) {
+  const long long i = (long long)blockIdx.x * kFnThreads + threadIdx.x;
+  if (i >= a.n) return;
+  const int d = a.spec.d;
+  // pack the separate arguments into the fused-path row layout and reuse eval_row's arithmetic
+  float row[7] = {0, 0, 0, 0, 0, 0, 0}, rowp[7] = {0, 0, 0, 0, 0, 0, 0};
+  float den = 1.0f;
+  if (a.family <= 1) {
+    den = a.a0[i];
+    row[d] = logf(den);
+    for (int c = 0; c < d; ++c) row[d + 1 + c] = a.a1[i * d + c];
+  } else {
+    for (int c = 0; c < d; ++c) { row[c] = a.a0[i * d + c]; if (a.family == 2) rowp[c] = a.a1[i * d + c]; }
+  }
+  FnArgs f;
+  f.spec = a.spec;
+  if (a.family != 0) f.spec.kin = OFDFT_KIN_NONE;
+  if (a.family != 1) f.spec.x = OFDFT_X_NONE;
+  if (a.family != 2) f.spec.hart = OFDFT_HART_NONE;
+  if (a.family != 3) f.spec.nuc = OFDFT_NUC_NONE;
+  for (int k = 0; k < a.spec.n_nuclei * 3; ++k) f.coords[k] = a.coords[k];
+  for (int k = 0; k < a.spec.n_nuclei; ++k) f.z[k] = a.z[k];
+  float buf[14];
+  for (int c = 0; c < 7; ++c) { buf[c] = row[c]; buf[7 + c] = rowp[c]; }
+  f.y1 = buf; f.stride = 7; f.bs = 1;
+  // eval_row indexes the partner at (bs + i) * stride: bs = 1, i = 0 -> buf + 7
+  Terms t = eval_row(f, 0);
+  const float e = a.family == 0 ? t.kin : (a.family == 1 ? t.x : (a.family == 2 ? t.hart : t.nuc));
+  a.out[i] = e;
+  if (a.family <= 1) {
+    if (a.g0) a.g0[i] = t.gl / den;                              // d/d den = (d/d logp) / den
+    if (a.g1) for (int c = 0; c < d; ++c) a.g1[i * d + c] = t.gs[c];
+  } else {
+    if (a.g0) for (int c = 0; c < d; ++c) a.g0[i * d + c] = t.gx[c];
+    if (a.g1 && a.family == 2) for (int c = 0; c < d; ++c) a.g1[i * d + c] = t.gxp[c];
+  }
+}
+
 static int hp_splits(long long n, long long m) {
   const long long blocks_i = (n + kHpThreads * kHpPts - 1) / (kHpThreads * kHpPts);
   long long s = (592 + blocks_i - 1) / blocks_i;
@@ -367,6 +418,28 @@ extern "C" int ofdft_functionals_integrands(void* stream, const ofdft_energy_spe
                                             const float* y1, int32_t stride, int64_t bs, float* e) {
   if (!e) return OFDFT_EINVAL;
   return launch_functionals(stream, spec, coords, z, y1, stride, bs, nullptr, nullptr, e, nullptr, 0);
+}
+
+extern "C" int ofdft_functional_eval(void* stream, int32_t family, const ofdft_energy_spec* spec, const float* coords,
+                                     const float* z, const float* a0, const float* a1, int64_t n, float* out, float* g0,
+                                     float* g1) {
+  if (!spec || !a0 || !out || n <= 0 || family < 0 || family > 3) return OFDFT_EINVAL;
+  if ((family <= 2) && !a1) return OFDFT_EINVAL;
+  if (spec->d != 1 && spec->d != 3) return OFDFT_EUNSUPPORTED;
+  FevArgs a;
+  a.spec = *spec;
+  const bool needs_mol = family == 3 && spec->d == 3 && spec->nuc != OFDFT_NUC_NONE;
+  if (needs_mol) {
+    if (!coords || !z || spec->n_nuclei < 1) return OFDFT_EINVAL;
+    if (spec->n_nuclei > kFnMaxNuc) return OFDFT_EUNSUPPORTED;
+    for (int i = 0; i < spec->n_nuclei * 3; ++i) a.coords[i] = coords[i];
+    for (int i = 0; i < spec->n_nuclei; ++i) a.z[i] = z[i];
+  } else {
+    a.spec.n_nuclei = 0;
+  }
+  a.family = family; a.a0 = a0; a.a1 = a1; a.n = n; a.out = out; a.g0 = g0; a.g1 = g1;
+  functional_eval_kernel<<<(unsigned)((n + kFnThreads - 1) / kFnThreads), kFnThreads, 0, (cudaStream_t)stream>>>(a);
+  return (int)cudaGetLastError();
 }
 
 extern "C" size_t ofdft_hartree_allpairs_scratch_bytes(int64_t n, int64_t m) {

@@ -13,6 +13,8 @@
 //     live in TMEM (3 jets x 64 columns) and come back with tcgen05.ld (32x32b) for the tanh-jet epilogue;
 //   * two jet operand buffers (2 x 64 KB): jets 0 and 1 are staged together, jet 2 reuses buffer 0 once the jet-0
 //     MMAs have completed.
+#include <cstdlib>
+
 #include "gnn_common.cuh"
 #include "tc.cuh"
 
@@ -28,20 +30,21 @@ struct SmemTc {
   float cb[kMaxNa * kH];
   float nuc[kMaxNa * 4];
   float xs[3 * kTP];
-  float Fpart[2 * 3 * kTP];
+  float Fpart[4 * 3 * kTP];
   uint64_t bar[3];
   unsigned int tmem_slot;
   int tile;
 };
 
-// stage one jet (32 units of one trajectory) as hi/lo tf32 operands
-__device__ __forceinline__ void stage_jet(float* __restrict__ hi, float* __restrict__ lo, const float (&v)[32], int m, int uh) {
+// stage one jet (UPT units of one trajectory) as hi/lo tf32 operands
+template <int UPT>
+__device__ __forceinline__ void stage_jet(float* __restrict__ hi, float* __restrict__ lo, const float (&v)[UPT], int m, int uh) {
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
+  for (int c = 0; c < UPT / 4; ++c) {
     float4 h, l;
     tc::split_tf32(v[4 * c + 0], h.x, l.x); tc::split_tf32(v[4 * c + 1], h.y, l.y);
     tc::split_tf32(v[4 * c + 2], h.z, l.z); tc::split_tf32(v[4 * c + 3], h.w, l.w);
-    const int off = ((8 * uh + c) * kTP + m) * 4;
+    const int off = (((UPT / 4) * uh + c) * kTP + m) * 4;
     *reinterpret_cast<float4*>(hi + off) = h;
     *reinterpret_cast<float4*>(lo + off) = l;
   }
@@ -61,13 +64,14 @@ __device__ __forceinline__ void issue_jet_mma(uint32_t d_tmem, uint64_t a_hi, ui
   }
 }
 
-template <int NJ>
+template <int NJ, int NU>
 __device__ void fwd_tile_tc(SmemTc& sm, const GnnFwdArgs& a, long long row0, long long seg_end, float b3,
                             bool seg_b, long long seg_row0, uint32_t tmem, uint32_t (&phase)[3]) {
   const ActLayout AL(a.act_rows_a, a.act_rows_b, a.jets_a, a.jets_b);
   const long long act_rows = seg_b ? a.act_rows_b : a.act_rows_a;
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
-  const int m = 32 * (w & 3) + lane, uh = w >> 2;
+  constexpr int UPT = kH / NU;                      // hidden units per thread
+  const int m = 32 * (w & 3) + lane, uh = w >> 2;   // uh: unit group 0..NU-1
   const bool owner = tid < kTP;                     // tid == m for w < 4
   const long long row = row0 + tid;
   const bool valid = owner && row < seg_end;
@@ -94,9 +98,13 @@ __device__ void fwd_tile_tc(SmemTc& sm, const GnnFwdArgs& a, long long row0, lon
 
   auto combine = [&](int i) {
     const float* nc = sm.nuc + i * 4;
-    float f0 = b3 + sm.Fpart[0 * kTP + tid] + sm.Fpart[3 * kTP + tid], f1 = 0.f, f2 = 0.f;
-    if (NJ >= 2) f1 = sm.Fpart[1 * kTP + tid] + sm.Fpart[4 * kTP + tid];
-    if (NJ == 3) f2 = sm.Fpart[2 * kTP + tid] + sm.Fpart[5 * kTP + tid];
+    float f0 = b3, f1 = 0.f, f2 = 0.f;
+#pragma unroll
+    for (int q = 0; q < NU; ++q) {
+      f0 += sm.Fpart[(q * 3 + 0) * kTP + tid];
+      if (NJ >= 2) f1 += sm.Fpart[(q * 3 + 1) * kTP + tid];
+      if (NJ == 3) f2 += sm.Fpart[(q * 3 + 2) * kTP + tid];
+    }
     const float d0 = xst[0] - nc[0], d1 = xst[1] - nc[1], d2 = xst[2] - nc[2];
     g[0] = fmaf(f0, d0, g[0]); g[1] = fmaf(f0, d1, g[1]); g[2] = fmaf(f0, d2, g[2]);
     if (NJ >= 2) {
@@ -139,22 +147,22 @@ __device__ void fwd_tile_tc(SmemTc& sm, const GnnFwdArgs& a, long long row0, lon
       for (int i = 0; i < a.Na; ++i) {
         if (owner && i > 0) combine(i - 1);
         // ---- first layer for (trajectory m, units 32*uh ..): a = tanh(w_r r + c), a' = (1-a^2) w_r, a'' = -2 a a' w_r ----
-        float av[32];
+        float av[UPT];
         {
           const float* nc = sm.nuc + i * 4;
           const float d0 = sm.xs[m] - nc[0], d1 = sm.xs[kTP + m] - nc[1], d2 = sm.xs[2 * kTP + m] - nc[2];
           const float r = sqrtf(fmaf(d0, d0, fmaf(d1, d1, d2 * d2)));
-          const float* cbi = sm.cb + i * kH + 32 * uh;
+          const float* cbi = sm.cb + i * kH + UPT * uh;
 #pragma unroll
-          for (int u = 0; u < 32; ++u)
-            av[u] = tanh_f(fmaf(sm.wr[32 * uh + u], r, fmaf(tprime, sm.wt[32 * uh + u], cbi[u])));
+          for (int u = 0; u < UPT; ++u)
+            av[u] = tanh_f(fmaf(sm.wr[UPT * uh + u], r, fmaf(tprime, sm.wt[UPT * uh + u], cbi[u])));
         }
-        stage_jet(sm.Abuf[0][0], sm.Abuf[0][1], av, m, uh);
+        stage_jet<UPT>(sm.Abuf[0][0], sm.Abuf[0][1], av, m, uh);
         if (NJ >= 2) {
-          float a1[32];
+          float a1[UPT];
 #pragma unroll
-          for (int u = 0; u < 32; ++u) a1[u] = fmaf(-av[u], av[u], 1.0f) * sm.wr[32 * uh + u];
-          stage_jet(sm.Abuf[1][0], sm.Abuf[1][1], a1, m, uh);
+          for (int u = 0; u < UPT; ++u) a1[u] = fmaf(-av[u], av[u], 1.0f) * sm.wr[UPT * uh + u];
+          stage_jet<UPT>(sm.Abuf[1][0], sm.Abuf[1][1], a1, m, uh);
         }
         tc::fence_async_smem();
         __syncthreads();
@@ -171,15 +179,15 @@ __device__ void fwd_tile_tc(SmemTc& sm, const GnnFwdArgs& a, long long row0, lon
           __syncwarp();
         }
         if (NJ == 3) {
-          float a2[32];
+          float a2[UPT];
 #pragma unroll
-          for (int u = 0; u < 32; ++u) {
-            const float wv = sm.wr[32 * uh + u];
+          for (int u = 0; u < UPT; ++u) {
+            const float wv = sm.wr[UPT * uh + u];
             a2[u] = -2.0f * av[u] * fmaf(-av[u], av[u], 1.0f) * wv * wv;
           }
           tc::mbar_wait(&sm.bar[0], phase[0]);           // jet-0 MMAs have finished reading buffer 0
           __syncwarp();
-          stage_jet(sm.Abuf[0][0], sm.Abuf[0][1], a2, m, uh);
+          stage_jet<UPT>(sm.Abuf[0][0], sm.Abuf[0][1], a2, m, uh);
           tc::fence_async_smem();
           __syncthreads();
           if (w == 0) {
@@ -201,18 +209,18 @@ __device__ void fwd_tile_tc(SmemTc& sm, const GnnFwdArgs& a, long long row0, lon
         float* actp = nullptr;
         if (a.act != nullptr)
           actp = a.act + AL.seg_base((long long)(step * 4 + stage) * a.Na + i, seg_b) + (row0 - seg_row0)
-                 + (long long)(32 * uh) * act_rows + m;
+                 + (long long)(UPT * uh) * act_rows + m;
         const long long jet_stride = (long long)kH * act_rows;
 #pragma unroll
-        for (int c0 = 0; c0 < 32; c0 += 16) {
+        for (int c0 = 0; c0 < UPT; c0 += 16) {
           float p0[16], p1[16], p2[16];
-          tc::tmem_ld16(tlane + 0 * kH + 32 * uh + c0, p0);
-          if (NJ >= 2) tc::tmem_ld16(tlane + 1 * kH + 32 * uh + c0, p1);
-          if (NJ == 3) tc::tmem_ld16(tlane + 2 * kH + 32 * uh + c0, p2);
+          tc::tmem_ld16(tlane + 0 * kH + UPT * uh + c0, p0);
+          if (NJ >= 2) tc::tmem_ld16(tlane + 1 * kH + UPT * uh + c0, p1);
+          if (NJ == 3) tc::tmem_ld16(tlane + 2 * kH + UPT * uh + c0, p2);
           tc::tmem_ld_wait();
 #pragma unroll
           for (int u = 0; u < 16; ++u) {
-            const int j = 32 * uh + c0 + u;
+            const int j = UPT * uh + c0 + u;
             const float wv = sm.w3[j];
             const float aa = tanh_f(p0[u] + sm.b2[j]);
             fp[0] = fmaf(wv, aa, fp[0]);
@@ -260,13 +268,15 @@ __device__ void fwd_tile_tc(SmemTc& sm, const GnnFwdArgs& a, long long row0, lon
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 1) gnn_fwd_tc_kernel(const GnnFwdArgs a) {
+template <int NU>
+__global__ void __launch_bounds__(kTP * NU, 1) gnn_fwd_tc_kernel(const GnnFwdArgs a) {
+  constexpr int kThr = kTP * NU;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   SmemTc& sm = *reinterpret_cast<SmemTc*>(smem_raw);
   const int tid = threadIdx.x;
   const GnnThetaLayout L(a.n_types);
   // weight operand B[n = j][k] = W2[k][j], split hi/lo, layout [k/4][j][k%4]
-  for (int i = tid; i < kH * kH; i += kThreads) {
+  for (int i = tid; i < kH * kH; i += kThr) {
     const int k = i / kH, j = i % kH;
     float hi, lo;
     tc::split_tf32(a.theta[L.W2 + i], hi, lo);
@@ -279,7 +289,7 @@ __global__ void __launch_bounds__(kThreads, 1) gnn_fwd_tc_kernel(const GnnFwdArg
     sm.b2[tid] = a.theta[L.b2 + tid];
     sm.w3[tid] = a.theta[L.w3 + tid];
   }
-  for (int i = tid; i < a.Na * kH; i += kThreads) {
+  for (int i = tid; i < a.Na * kH; i += kThr) {
     const int n = i / kH, k = i % kH;
     float c = a.theta[L.b1 + k];
     for (int t = 0; t < a.n_types; ++t) c = fmaf(a.onehot[n * a.n_types + t], a.theta[L.W1 + (2 + t) * kH + k], c);
@@ -306,9 +316,9 @@ __global__ void __launch_bounds__(kThreads, 1) gnn_fwd_tc_kernel(const GnnFwdArg
     bool seg_b; long long seg_row0;
     if (tile < tiles_a) { row0 = tile * kTP; seg_end = a.n_a; nj = a.jets_a; seg_b = false; seg_row0 = 0; }
     else { row0 = a.n_a + (tile - tiles_a) * kTP; seg_end = a.B; nj = a.jets_b; seg_b = true; seg_row0 = a.n_a; }
-    if (nj == 3) fwd_tile_tc<3>(sm, a, row0, seg_end, b3, seg_b, seg_row0, tmem, phase);
-    else if (nj == 2) fwd_tile_tc<2>(sm, a, row0, seg_end, b3, seg_b, seg_row0, tmem, phase);
-    else fwd_tile_tc<1>(sm, a, row0, seg_end, b3, seg_b, seg_row0, tmem, phase);
+    if (nj == 3) fwd_tile_tc<3, NU>(sm, a, row0, seg_end, b3, seg_b, seg_row0, tmem, phase);
+    else if (nj == 2) fwd_tile_tc<2, NU>(sm, a, row0, seg_end, b3, seg_b, seg_row0, tmem, phase);
+    else fwd_tile_tc<1, NU>(sm, a, row0, seg_end, b3, seg_b, seg_row0, tmem, phase);
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -812,13 +822,18 @@ int launch_gnn_fwd_tc(void* stream, GnnFwdArgs& a, void* scratch, size_t scratch
   a.counter = (int*)scratch;
   cudaError_t e = cudaMemsetAsync(scratch, 0, kCounterBytes, st);
   if (e != cudaSuccess) return (int)e;
-  e = cudaFuncSetAttribute(gnn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemTc) + 1024);
+  // OFDFT_B200_TC_NU = 4 (default: 512 threads, 16 hidden units per thread) | 2 (256 threads, 32 units per thread)
+  const char* env = getenv("OFDFT_B200_TC_NU");
+  const bool nu2 = env != nullptr && env[0] == '2';
+  e = nu2 ? cudaFuncSetAttribute(gnn_fwd_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemTc) + 1024)
+          : cudaFuncSetAttribute(gnn_fwd_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemTc) + 1024);
   if (e != cudaSuccess) return (int)e;
   const long long tiles = (a.n_a + kTP - 1) / kTP + (a.B - a.n_a + kTP - 1) / kTP;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = (int)(tiles < sms ? tiles : sms);
-  gnn_fwd_tc_kernel<<<grid, kThreads, sizeof(SmemTc) + 1024, st>>>(a);
+  if (nu2) gnn_fwd_tc_kernel<2><<<grid, kTP * 2, sizeof(SmemTc) + 1024, st>>>(a);
+  else gnn_fwd_tc_kernel<4><<<grid, kTP * 4, sizeof(SmemTc) + 1024, st>>>(a);
   return (int)cudaGetLastError();
 }
 

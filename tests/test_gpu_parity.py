@@ -158,6 +158,51 @@ def test_functionals_all_modes_match_oracle():
     assert rel(yb.cpu().numpy(), O.energy_terms_vjp(ospec, y1d, 1)) < 1e-5
 
 
+def test_functional_factories_drop_in_and_autograd():
+    """_kinetic/_hartree/_nuclear/_exchange_correlation(name)(...) with the reference signatures, (bs,1) outputs and
+    gradients through torch.autograd: a `loss` written like H20_mol_ofdft_min_equiv_flows.py:150-173."""
+    from ofdft_nflows_b200.functionals import _kinetic, _hartree, _nuclear, _exchange_correlation
+    rng = np.random.default_rng(8)
+    mol = O.molecule("H2O")
+    bs = 257
+    y = O.batch_generator_3d(rng, bs, mol["coords"], mol["z"]).astype(np.float32).astype(np.float64)
+    den_np = np.exp(y[:bs, 3:4]); sc_np = y[:bs, 4:7]; x_np = y[:bs, :3]; xp_np = y[bs:, :3]
+    den = dev(den_np).requires_grad_(True); score = dev(sc_np).requires_grad_(True)
+    x = dev(x_np).requires_grad_(True); xp = dev(xp_np).requires_grad_(True)
+    Ne = 10
+    mol_info = {"coords": mol["coords"], "z": mol["z"]}
+    e_t = _kinetic("tf-w")(den, score, Ne)
+    e_h = _hartree("hartree")(x, xp, Ne)
+    e_n = _nuclear("hgh")(x, Ne, mol_info)
+    e_x = _exchange_correlation("lda")(den, score, Ne)
+    assert e_t.shape == (bs, 1) and e_h.shape == (bs, 1) and e_n.shape == (bs, 1) and e_x.shape == (bs, 1)
+    ref_t = O.thomas_fermi(den_np, sc_np, Ne) + O.weizsacker(den_np, sc_np, Ne)
+    ref_h = O.hartree_potential(x_np, xp_np, Ne)
+    ref_n = O.nuclei_potential_hgh(x_np, Ne, mol["coords"], mol["z"])
+    ref_x = O.lda(den_np, sc_np, Ne)
+    for got, ref in ((e_t, ref_t), (e_h, ref_h), (e_n, ref_n), (e_x, ref_x)):
+        assert np.allclose(got.detach().cpu().numpy(), ref, rtol=2e-6, atol=1e-6 * np.abs(ref).max())
+    energy = (e_t + e_n + e_h + e_x).mean()
+    energy.backward()
+    # cotangents == the fused kernel's (and the oracle's) d energy / d (x, logp, score)
+    ospec = O.EnergySpec(Ne=Ne, kin="tf-w", hart="hartree", nuc="hgh", x="lda", coords=mol["coords"], z=mol["z"])
+    g = O.energy_terms_vjp(ospec, y, 3)
+    assert rel(x.grad.cpu().numpy(), g[:bs, :3]) < 1e-5 and rel(xp.grad.cpu().numpy(), g[bs:, :3]) < 1e-5
+    assert rel(score.grad.cpu().numpy(), g[:bs, 4:7]) < 1e-5
+    assert rel((den.grad * den).detach().cpu().numpy(), g[:bs, 3:4]) < 1e-5          # d/dlogp = den * d/dden
+    # 1-D factories (LiH.py:118-138)
+    y1 = O.batch_generator_1d(rng, 64).astype(np.float32).astype(np.float64)
+    d1 = np.exp(y1[:64, 1:2]); s1 = y1[:64, 2:3]
+    k1 = _kinetic("tfw_1d")(dev(d1), dev(s1), 2).cpu().numpy()
+    assert np.allclose(k1, O.thomas_fermi_1D(d1, s1, 2) + O.weizsacker(d1, s1, 2), rtol=2e-6)
+    h1 = _hartree("softc")(dev(y1[:64, :1]), dev(y1[64:, :1]), 2).cpu().numpy()
+    assert np.allclose(h1, O.soft_coulomb(y1[:64, :1], y1[64:, :1], 2), rtol=2e-6)
+    n1 = _nuclear("attraction")(dev(y1[:64, :1]), 0.7, 3, 1, 2).cpu().numpy()
+    assert np.allclose(n1, O.attraction(y1[:64, :1], 0.7, 3, 1, 2), rtol=2e-6)
+    with pytest.raises(NotImplementedError):
+        _exchange_correlation("vwn_c_e")
+
+
 def test_hartree_allpairs_matches_numpy():
     rng = np.random.default_rng(5)
     x = rng.standard_normal((1500, 7)); xp = rng.standard_normal((1111, 7)) + 0.3
