@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define OFDFT_B200_ABI_VERSION 1
+#define OFDFT_B200_ABI_VERSION 2
 
 /* error codes (negative) */
 #define OFDFT_EINVAL      (-1)   /* bad argument (null pointer, size <= 0, ...)           */
@@ -61,7 +61,14 @@ enum {
   OFDFT_NUC_HGH_SPECIES = 4                         /* NON-reference: H/O tables by Z (hgh_pseudopotentials.py:8-11) */
 };
 enum {
-  OFDFT_X_NONE = 0, OFDFT_X_LDA = 1                 /* 'lda' functionals.py:391-417 ((3/pi)**1/3 as coded)     */
+  OFDFT_X_NONE = 0, OFDFT_X_LDA = 1,                /* 'lda' functionals.py:391-417 ((3/pi)**1/3 as coded)     */
+  OFDFT_X_B88 = 2,                                  /* 'b88_x_e' functionals.py:335-389                        */
+  OFDFT_X_DIRAC_B88 = 3                             /* 'dirac_b88_x_e' = lda + b88_x_e (functionals.py:181-183) */
+};
+enum {
+  OFDFT_C_NONE = 0, OFDFT_C_VWN = 1,                /* 'vwn_c_e'  functionals.py:185-245                       */
+  OFDFT_C_PW92 = 2,                                 /* 'pw92_c_e' functionals.py:247-292                       */
+  OFDFT_C_XC1D = 3                                  /* 'xc_1d'    functionals.py:294-332 (1-D, LiH.py:217)     */
 };
 
 /* energy-term slots of the float64 sums written by ofdft_functionals_fwd_bwd (F_values, H20_...py:43-49) */
@@ -75,6 +82,7 @@ enum {
 typedef struct {
   int32_t d;             /* 3 or 1                                                           */
   int32_t kin, hart, nuc, x;
+  int32_t c;             /* c-type functional (den, Ne): OFDFT_C_*                           */
   int32_t n_nuclei;      /* 3-D: rows of coords/z                                            */
   float   Ne;
   float   R, Z_alpha, Z_beta;     /* 1-D attraction (LiH.py:218-223)                         */
@@ -168,14 +176,15 @@ int ofdft_functionals_fwd_bwd(void* stream, const ofdft_energy_spec* spec, const
 
 /* Per-sample integrands (bs,1) of the string-keyed factories _kinetic/_hartree/_nuclear/
  * _exchange_correlation (functionals.py:21-43,164-183,425-436,504-521):
- *   e[term*bs + i] for term in {KIN, NUC, HART, X}; inputs as ofdft_functionals_fwd_bwd. */
+ *   e[term*bs + i] for term in {KIN, NUC, HART, X, C} (5*bs floats); inputs as ofdft_functionals_fwd_bwd. */
 int ofdft_functionals_integrands(void* stream, const ofdft_energy_spec* spec, const float* coords, const float* z,
                                  const float* y1, int32_t stride, int64_t bs, float* e);
 
 /* One functional of the string-keyed factories on separate array arguments, with its derivatives (the reference's
  * per-term call signatures, functionals.py):
  *   family 0: _kinetic(name)(den, score, Ne)              a0 = den (n), a1 = score (n,d)   g0 = d/d den, g1 = d/d score
- *   family 1: _exchange_correlation(name)(den, score, Ne)  same arguments
+ *   family 1: _exchange_correlation(name)(den, score, Ne)  same arguments (x-type: spec.x)
+ *   family 4: _exchange_correlation(name)(den, Ne)          a0 = den (n)  (c-type: spec.c; a1 ignored)   g0 = d/d den
  *   family 2: _hartree(name)(x, xp, Ne)                   a0 = x (n,d), a1 = xp (n,d)      g0 = d/dx, g1 = d/dxp
  *   family 3: _nuclear(name)(x, Ne, mol_info) / attraction a0 = x (n,d)                     g0 = d/dx
  * out (n) receives the per-sample integrand; g0 / g1 may be NULL.  The functional is selected by the matching

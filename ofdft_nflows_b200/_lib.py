@@ -17,7 +17,7 @@ vp, i32, i64, f32, szt = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t
 
 class EnergySpecC(C.Structure):
     """``ofdft_energy_spec`` (include/ofdft_b200.h)."""
-    _fields_ = [("d", i32), ("kin", i32), ("hart", i32), ("nuc", i32), ("x", i32), ("n_nuclei", i32),
+    _fields_ = [("d", i32), ("kin", i32), ("hart", i32), ("nuc", i32), ("x", i32), ("c", i32), ("n_nuclei", i32),
                 ("Ne", f32), ("R", f32), ("Z_alpha", f32), ("Z_beta", f32)]
 
 
@@ -71,7 +71,7 @@ def load():
         fn = getattr(lib, name)          # AttributeError if the build is stale: fail loudly
         fn.restype = res
         fn.argtypes = args
-    if lib.ofdft_b200_abi_version() != 1:
+    if lib.ofdft_b200_abi_version() != 2:
         raise RuntimeError("ofdft_nflows_b200: ABI version mismatch between _lib.py and libofdft_b200.so")
     _LIB = lib
     return lib

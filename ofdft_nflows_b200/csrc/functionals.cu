@@ -17,7 +17,7 @@ struct FnArgs {
   const float* y1; int stride; long long bs;
   double* partial;    // [grid][5]
   float* ybar1;       // (2bs, stride) or null
-  float* integrands;  // (4, bs) or null
+  float* integrands;  // (5, bs) or null
 };
 
 // HGH local pseudopotential parameters (ofdft_normflows/hgh_pseudopotentials.py:8-11)
@@ -25,7 +25,7 @@ struct Hgh { float zion, rloc, c1, c2, c3, c4; };
 __device__ __forceinline__ Hgh hgh_H() { return {1.f, 0.2f, -4.180237f, 0.725075f, 0.f, 0.f}; }
 __device__ __forceinline__ Hgh hgh_O() { return {6.f, 0.247621f, -16.580318f, 2.395701f, 0.f, 0.f}; }
 
-struct Terms { float kin, nuc, hart, x; float gx[3], gxp[3], gl, gs[3]; };
+struct Terms { float kin, nuc, hart, x, c; float gx[3], gxp[3], gl, gs[3]; };
 
 // one first-half row i with its partner row bs+i: integrands and their derivatives (un-normalised)
 __device__ __forceinline__ Terms eval_row(const FnArgs& a, long long i) {
@@ -35,7 +35,7 @@ __device__ __forceinline__ Terms eval_row(const FnArgs& a, long long i) {
   const float* row = a.y1 + i * a.stride;
   const float* rowp = a.y1 + (a.bs + i) * a.stride;
   Terms t;
-  t.kin = t.nuc = t.hart = t.x = 0.f; t.gl = 0.f;
+  t.kin = t.nuc = t.hart = t.x = t.c = 0.f; t.gl = 0.f;
   float x[3] = {0, 0, 0}, xp[3] = {0, 0, 0}, s[3] = {0, 0, 0};
   for (int c = 0; c < d; ++c) { x[c] = row[c]; xp[c] = rowp[c]; s[c] = row[d + 1 + c]; }
   const float logp = row[d];
@@ -58,10 +58,71 @@ __device__ __forceinline__ Terms eval_row(const FnArgs& a, long long i) {
     for (int c = 0; c < d; ++c) t.gs[c] = 2.0f * cw * s[c];
   }
   // ---- exchange: lda (functionals.py:391-417; (3/pi)**1/3 == 1/pi as coded) ----
-  if (sp.x == OFDFT_X_LDA) {
+  if (sp.x == OFDFT_X_LDA || sp.x == OFDFT_X_DIRAC_B88) {
     const float l = -0.75f * powf(Ne, 4.0f / 3.0f) * 0.3183098861837907f;
     const float e = l * expf((1.0f / 3.0f) * logp);
     t.x = e; t.gl += (1.0f / 3.0f) * e;
+  }
+  // ---- exchange: B88 gradient correction (functionals.py:335-389): -beta Ne^{2/3} S^2 den^{2/3} / (1 + 6 beta x asinh x),
+  //      x = S den^{-1/3}, S = |score|  (the reference evaluates it through log2/2** of clipped arguments) ----
+  if (sp.x == OFDFT_X_B88 || sp.x == OFDFT_X_DIRAC_B88) {
+    const float beta = 0.0042f;
+    const float S2 = s[0] * s[0] + s[1] * s[1] + s[2] * s[2];
+    const float S = sqrtf(S2);
+    const float d23 = expf((2.0f / 3.0f) * logp), dm13 = expf((-1.0f / 3.0f) * logp);
+    const float xs = S * dm13;
+    const float ash = asinhf(xs);
+    const float D = 1.0f + 6.0f * beta * xs * ash;
+    const float Nn = S2 * d23;
+    const float pre = -beta * powf(Ne, 2.0f / 3.0f);
+    const float e = pre * Nn / D;
+    const float dDdx = 6.0f * beta * (ash + xs / sqrtf(1.0f + xs * xs));
+    t.x += e;
+    t.gl += pre * ((2.0f / 3.0f) * Nn / D + Nn / (D * D) * dDdx * (xs * (1.0f / 3.0f)));
+    if (S > 0.f) {
+      const float cs = pre * (2.0f * d23 / D - Nn / (D * D) * dDdx * dm13 / S);
+      for (int c = 0; c < d; ++c) t.gs[c] += cs * s[c];
+    }
+  }
+  // ---- correlation (c-type functionals of the density only) ----
+  if (sp.c == OFDFT_C_VWN) {            // functionals.py:185-245
+    const float A = 0.0621814f, b = 3.72744f, cc = 12.9352f, x0 = -0.10498f;
+    const float rs = 0.6203504908994f * expf((-1.0f / 3.0f) * logp);       // (3/(4 pi))^{1/3} den^{-1/3}
+    const float x = sqrtf(rs);
+    const float X = x * x + b * x + cc, X0 = x0 * x0 + b * x0 + cc, Q = sqrtf(4.0f * cc - b * b);
+    const float at = atanf(Q / (2.0f * x + b));
+    const float e = 0.5f * A * (2.0f * logf(x) - logf(X) + 2.0f * b / Q * at
+                                - b * x0 / X0 * (logf((x - x0) * (x - x0) / X) + 2.0f * (2.0f * x0 + b) / Q * at));
+    const float Xp = 2.0f * x + b;
+    const float dat = -2.0f * Q / (Xp * Xp + Q * Q);
+    const float dedx = 0.5f * A * (2.0f / x - Xp / X + 2.0f * b / Q * dat
+                                   - b * x0 / X0 * (2.0f / (x - x0) - Xp / X + 2.0f * (2.0f * x0 + b) / Q * dat));
+    t.c = Ne * e;
+    t.gl += Ne * dedx * (-x * (1.0f / 6.0f));
+  } else if (sp.c == OFDFT_C_PW92) {    // functionals.py:247-292
+    const float A = 0.031091f, a1 = 0.21370f, b1 = 7.5957f, b2 = 3.5876f, b3 = 1.6382f, b4 = 0.49294f;
+    const float rs = 0.6203504908994f * expf((-1.0f / 3.0f) * logp);
+    const float sr = sqrtf(rs);
+    const float G = 2.0f * A * (b1 * sr + b2 * rs + b3 * rs * sr + b4 * rs * rs);
+    const float Gp = 2.0f * A * (0.5f * b1 / sr + b2 + 1.5f * b3 * sr + 2.0f * b4 * rs);
+    const float L = log1pf(1.0f / G);
+    const float e = -2.0f * A * (1.0f + a1 * rs) * L;
+    const float dedrs = -2.0f * A * a1 * L + 2.0f * A * (1.0f + a1 * rs) * Gp / (G * G + G);
+    t.c = Ne * e;
+    t.gl += Ne * dedrs * (-rs * (1.0f / 3.0f));
+  } else if (sp.c == OFDFT_C_XC1D) {    // functionals.py:294-332
+    const float a0 = -0.8862269f, b0 = -2.1414101f, c0 = 0.4721355f, d0 = 2.81423f, e0 = 0.529891f, f0 = 0.458513f;
+    const float g0 = -0.202642f, h0 = 0.470876f, al = 0.104435f, be = 4.11613f;
+    const float rs = 1.0f / (2.0f * Ne) * expf(-logp);
+    const float n1 = a0 + rs * (b0 + c0 * rs), d1 = 1.0f + rs * (d0 + rs * (e0 + f0 * rs));
+    const float n1p = b0 + 2.0f * c0 * rs, d1p = d0 + rs * (2.0f * e0 + 3.0f * f0 * rs);
+    const float rb = powf(rs, be);
+    const float u = rs + al * rb;
+    const float lu = logf(u);
+    const float n2 = g0 * rs * lu, d2 = 1.0f + h0 * rs * rs;
+    const float n2p = g0 * lu + g0 * rs * (1.0f + al * be * rb / rs) / u, d2p = 2.0f * h0 * rs;
+    t.c = Ne * (n1 / d1 + n2 / d2);
+    t.gl += Ne * ((n1p * d1 - n1 * d1p) / (d1 * d1) + (n2p * d2 - n2 * d2p) / (d2 * d2)) * (-rs);
   }
   // ---- Hartree, row-paired (functionals.py:439-496) ----
   if (sp.hart != OFDFT_HART_NONE) {
@@ -116,14 +177,14 @@ __device__ __forceinline__ Terms eval_row(const FnArgs& a, long long i) {
 
 __global__ void __launch_bounds__(kFnThreads) functionals_kernel(const FnArgs a) {
   const long long i = (long long)blockIdx.x * kFnThreads + threadIdx.x;
-  double acc[4] = {0, 0, 0, 0};
+  double acc[5] = {0, 0, 0, 0, 0};
   if (i < a.bs) {
     const Terms t = eval_row(a, i);
-    acc[0] = t.kin; acc[1] = t.nuc; acc[2] = t.hart; acc[3] = t.x;
+    acc[0] = t.kin; acc[1] = t.nuc; acc[2] = t.hart; acc[3] = t.x; acc[4] = t.c;
     const int d = a.spec.d;
     if (a.integrands) {
       a.integrands[0 * a.bs + i] = t.kin; a.integrands[1 * a.bs + i] = t.nuc;
-      a.integrands[2 * a.bs + i] = t.hart; a.integrands[3 * a.bs + i] = t.x;
+      a.integrands[2 * a.bs + i] = t.hart; a.integrands[3 * a.bs + i] = t.x; a.integrands[4 * a.bs + i] = t.c;
     }
     if (a.ybar1) {
       const float inv = 1.0f / (float)a.bs;
@@ -135,33 +196,33 @@ __global__ void __launch_bounds__(kFnThreads) functionals_kernel(const FnArgs a)
     }
   }
   if (a.partial == nullptr) return;
-  __shared__ double red[4][kFnThreads / 32];
+  __shared__ double red[5][kFnThreads / 32];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
+  for (int k = 0; k < 5; ++k) {
     double v = acc[k];
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     if ((threadIdx.x & 31) == 0) red[k][threadIdx.x >> 5] = v;
   }
   __syncthreads();
-  if (threadIdx.x < 4) {
+  if (threadIdx.x < 5) {
     double v = 0.0;
     for (int w = 0; w < kFnThreads / 32; ++w) v += red[threadIdx.x][w];
-    a.partial[(size_t)blockIdx.x * 4 + threadIdx.x] = v;
+    a.partial[(size_t)blockIdx.x * 5 + threadIdx.x] = v;
   }
 }
 
 __global__ void functionals_final_kernel(const double* __restrict__ partial, int nblk, long long bs, double* sums) {
-  __shared__ double red[4][8];
-  const int k = threadIdx.x >> 6, l = threadIdx.x & 63;   // 256 threads: 4 terms x 64 lanes
+  __shared__ double red[8];
+  const int k = threadIdx.x >> 5, l = threadIdx.x & 31;   // 256 threads: warp k reduces term k (5 used)
   double v = 0.0;
-  for (int b = l; b < nblk; b += 64) v += partial[(size_t)b * 4 + k];
+  if (k < 5) for (int b = l; b < nblk; b += 32) v += partial[(size_t)b * 5 + k];
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  if ((l & 31) == 0) red[k][l >> 5] = v;
+  if (l == 0) red[k] = v;
   __syncthreads();
   if (threadIdx.x == 0) {
     double tot = 0.0;
-    for (int t = 0; t < 4; ++t) { const double m = (red[t][0] + red[t][1]) / (double)bs; sums[t] = m; tot += m; }
-    sums[OFDFT_TERM_C] = 0.0; sums[5] = tot; sums[6] = 0.0; sums[7] = 0.0;
+    for (int t = 0; t < 5; ++t) { const double m = red[t] / (double)bs; sums[t] = m; tot += m; }
+    sums[5] = tot; sums[6] = 0.0; sums[7] = 0.0;
   }
 }
 
@@ -266,7 +327,7 @@ struct FevArgs {
   ofdft_energy_spec spec;
   float coords[kFnMaxNuc * 3];
   float z[kFnMaxNuc];
-  int family;                 // 0 kinetic(den, score)  1 exchange(den, score)  2 hartree(x, xp)  3 nuclear(x)
+  int family;                 // 0 kinetic(den, score)  1 exchange(den, score)  2 hartree(x, xp)  3 nuclear(x)  4 correlation(den)
   const float* a0; const float* a1; long long n;
   float* out; float* g0; float* g1;
 };
@@ -278,10 +339,10 @@ __global__ void __launch_bounds__(kFnThreads) functional_eval_kernel(const FevAr
   // pack the separate arguments into the fused-path row layout and reuse eval_row's arithmetic
   float row[7] = {0, 0, 0, 0, 0, 0, 0}, rowp[7] = {0, 0, 0, 0, 0, 0, 0};
   float den = 1.0f;
-  if (a.family <= 1) {
+  if (a.family <= 1 || a.family == 4) {
     den = a.a0[i];
     row[d] = logf(den);
-    for (int c = 0; c < d; ++c) row[d + 1 + c] = a.a1[i * d + c];
+    if (a.family <= 1) for (int c = 0; c < d; ++c) row[d + 1 + c] = a.a1[i * d + c];
   } else {
     for (int c = 0; c < d; ++c) { row[c] = a.a0[i * d + c]; if (a.family == 2) rowp[c] = a.a1[i * d + c]; }
   }
@@ -291,6 +352,7 @@ __global__ void __launch_bounds__(kFnThreads) functional_eval_kernel(const FevAr
   if (a.family != 1) f.spec.x = OFDFT_X_NONE;
   if (a.family != 2) f.spec.hart = OFDFT_HART_NONE;
   if (a.family != 3) f.spec.nuc = OFDFT_NUC_NONE;
+  if (a.family != 4) f.spec.c = OFDFT_C_NONE;
   for (int k = 0; k < a.spec.n_nuclei * 3; ++k) f.coords[k] = a.coords[k];
   for (int k = 0; k < a.spec.n_nuclei; ++k) f.z[k] = a.z[k];
   float buf[14];
@@ -298,11 +360,11 @@ __global__ void __launch_bounds__(kFnThreads) functional_eval_kernel(const FevAr
   f.y1 = buf; f.stride = 7; f.bs = 1;
   // eval_row indexes the partner at (bs + i) * stride: bs = 1, i = 0 -> buf + 7
   Terms t = eval_row(f, 0);
-  const float e = a.family == 0 ? t.kin : (a.family == 1 ? t.x : (a.family == 2 ? t.hart : t.nuc));
+  const float e = a.family == 0 ? t.kin : (a.family == 1 ? t.x : (a.family == 2 ? t.hart : (a.family == 3 ? t.nuc : t.c)));
   a.out[i] = e;
-  if (a.family <= 1) {
+  if (a.family <= 1 || a.family == 4) {
     if (a.g0) a.g0[i] = t.gl / den;                              // d/d den = (d/d logp) / den
-    if (a.g1) for (int c = 0; c < d; ++c) a.g1[i * d + c] = t.gs[c];
+    if (a.g1 && a.family <= 1) for (int c = 0; c < d; ++c) a.g1[i * d + c] = t.gs[c];
   } else {
     if (a.g0) for (int c = 0; c < d; ++c) a.g0[i * d + c] = t.gx[c];
     if (a.g1 && a.family == 2) for (int c = 0; c < d; ++c) a.g1[i * d + c] = t.gxp[c];
@@ -362,7 +424,7 @@ using namespace ofdft;
 
 extern "C" size_t ofdft_functionals_scratch_bytes(int64_t bs) {
   const size_t nblk = (size_t)((bs + kFnThreads - 1) / kFnThreads);
-  return align256(nblk * 4 * sizeof(double));
+  return align256(nblk * 5 * sizeof(double));
 }
 
 static int fill_fn_args(FnArgs& a, const ofdft_energy_spec* spec, const float* coords_dev_or_host, const float* z) {
@@ -423,7 +485,7 @@ extern "C" int ofdft_functionals_integrands(void* stream, const ofdft_energy_spe
 extern "C" int ofdft_functional_eval(void* stream, int32_t family, const ofdft_energy_spec* spec, const float* coords,
                                      const float* z, const float* a0, const float* a1, int64_t n, float* out, float* g0,
                                      float* g1) {
-  if (!spec || !a0 || !out || n <= 0 || family < 0 || family > 3) return OFDFT_EINVAL;
+  if (!spec || !a0 || !out || n <= 0 || family < 0 || family > 4) return OFDFT_EINVAL;
   if ((family <= 2) && !a1) return OFDFT_EINVAL;
   if (spec->d != 1 && spec->d != 3) return OFDFT_EUNSUPPORTED;
   FevArgs a;

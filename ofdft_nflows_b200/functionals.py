@@ -7,8 +7,9 @@ derivatives run in ``ofdft_functional_eval`` (CUDA), and ``torch.autograd`` play
 fused ``EnergyEstimator`` step does not go through these wrappers (one kernel evaluates all terms and their
 cotangents); they exist for drop-in use and for per-term inspection.
 
-Not implemented on the CUDA path (SURVEY.md section 8f "next"): ``b88_x_e``, ``vwn_c_e``, ``pw92_c_e``, ``xc_1d`` and
-the unused ``kinetic`` / ``madness`` / ``harmonic`` variants -- asking for them raises NotImplementedError.
+Covered: every functional the reference drivers select by default (tf / w / tf-w / tf1d / tfw_1d; hartree / softc /
+hartree_mt; nuclei_potential / hgh / attraction; lda / b88_x_e / dirac_b88_x_e; vwn_c_e / pw92_c_e / xc_1d).  The unused
+``kinetic`` / ``madness`` / ``harmonic`` variants raise NotImplementedError.
 """
 from __future__ import annotations
 
@@ -69,10 +70,16 @@ def _kinetic(name: str = "TF") -> Callable:
 
 
 def _exchange_correlation(name: str = "XC") -> Callable:
-    """functionals.py:164-183; only ``lda`` (x-type: ``wrapper(den, score, Ne)``) is on the CUDA path."""
+    """functionals.py:164-183.  x-type (``lda``, ``b88_x_e``, ``dirac_b88_x_e``): ``wrapper(den, score, Ne)``;
+    c-type (``vwn_c_e``, ``pw92_c_e``, ``xc_1d``): ``wrapper(den, Ne)``."""
     key = name.lower()
+    if key in ops.XC_C and ops.XC_C[key] != 0:
+        def wrapper_c(den, Ne):
+            d = 1 if key in ("xc_1d", "exchange_correlation_1d") else 3
+            return _Functional.apply(den.reshape(-1), None, 4, EnergySpec(Ne=float(Ne), d=d, kin="", hart="", nuc="", x="", c=key))
+        return wrapper_c
     if key not in ops.XC_X or ops.XC_X[key] == 0:
-        raise NotImplementedError(f"_exchange_correlation({name!r}) is not implemented by the CUDA path (SURVEY.md 8f)")
+        raise NotImplementedError(f"_exchange_correlation({name!r}) is not implemented by the CUDA path")
 
     def wrapper(den, score, Ne):
         d = score.shape[1]

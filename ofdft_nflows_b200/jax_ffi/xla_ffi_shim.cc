@@ -72,10 +72,10 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(OfdftGnnBwd, GnnBwdImpl,
 // sums, ybar1 <- functionals(y1)      replaces the functional calls + jnp.mean of `loss` (H20_...py:158-173)
 static ffi::Error FunctionalsImpl(cudaStream_t stream, ffi::Buffer<ffi::F32> y1, ffi::ResultBuffer<ffi::F64> sums,
                                   ffi::ResultBuffer<ffi::F32> ybar1, ffi::ResultBuffer<ffi::U8> scratch, int32_t d,
-                                  int32_t kin, int32_t hart, int32_t nuc, int32_t x, float Ne, float R, float Z_alpha,
+                                  int32_t kin, int32_t hart, int32_t nuc, int32_t x, int32_t c, float Ne, float R, float Z_alpha,
                                   float Z_beta, ffi::Span<const float> coords, ffi::Span<const float> z) {
   const auto yd = y1.dimensions();
-  ofdft_energy_spec spec{d, kin, hart, nuc, x, (int32_t)z.size(), Ne, R, Z_alpha, Z_beta};
+  ofdft_energy_spec spec{d, kin, hart, nuc, x, c, (int32_t)z.size(), Ne, R, Z_alpha, Z_beta};
   return as_error(ofdft_functionals_fwd_bwd(stream, &spec, coords.begin(), z.begin(), y1.typed_data(), (int32_t)yd[1],
                                             yd[0] / 2, sums->typed_data(), ybar1->typed_data(), scratch->typed_data(),
                                             scratch->element_count()),
@@ -87,6 +87,6 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(OfdftFunctionals, FunctionalsImpl,
                                   .Arg<ffi::Buffer<ffi::F32>>()
                                   .Ret<ffi::Buffer<ffi::F64>>().Ret<ffi::Buffer<ffi::F32>>().Ret<ffi::Buffer<ffi::U8>>()
                                   .Attr<int32_t>("d").Attr<int32_t>("kin").Attr<int32_t>("hart").Attr<int32_t>("nuc")
-                                  .Attr<int32_t>("x").Attr<float>("Ne").Attr<float>("R").Attr<float>("Z_alpha")
+                                  .Attr<int32_t>("x").Attr<int32_t>("c").Attr<float>("Ne").Attr<float>("R").Attr<float>("Z_alpha")
                                   .Attr<float>("Z_beta").Attr<ffi::Span<const float>>("coords")
                                   .Attr<ffi::Span<const float>>("z"));

@@ -22,7 +22,9 @@ KIN = {"": 0, "none": 0, "tf": 1, "thomas_fermi": 1, "w": 2, "weizsacker": 2, "w
 HART = {"": 0, "none": 0, "hartree": 1, "hartree_potential": 1, "softc": 2, "soft_coulomb": 2, "hartree_mt": 3}
 NUC = {"": 0, "none": 0, "nuclei_potential": 1, "nuclei": 1, "hgh": 2, "nuclei_potential_hgh": 2,
        "attraction": 3, "attr": 3, "hgh_species": 4}
-XC_X = {"": 0, "none": 0, "lda": 1, "local_density_approximation": 1}
+XC_X = {"": 0, "none": 0, "lda": 1, "local_density_approximation": 1, "b88_x_e": 2, "dirac_b88_x_e": 3}
+XC_C = {"": 0, "none": 0, "vwn_c_e": 1, "correlation_vwn_c_e": 1, "pw92_c_e": 2, "correlation_pw92_c_e": 2,
+        "xc_1d": 3, "exchange_correlation_1d": 3}
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -125,6 +127,7 @@ class EnergySpec:
     hart: str = "hartree"
     nuc: str = "nuclei_potential"
     x: str = "lda"
+    c: str = ""                       # c-type functional (den, Ne): vwn_c_e | pw92_c_e | xc_1d
     coords: Optional[object] = None   # (Na,3) host array (bohr)
     z: Optional[object] = None        # (Na,)
     R: float = 0.0
@@ -135,6 +138,7 @@ class EnergySpec:
         import numpy as np
         try:
             kin, hart, nuc, x = KIN[self.kin.lower()], HART[self.hart.lower()], NUC[self.nuc.lower()], XC_X[self.x.lower()]
+            cc = XC_C[self.c.lower()]
         except KeyError as e:
             raise NotImplementedError(f"functional {e} is not implemented by the CUDA path") from None
         n = 0
@@ -143,7 +147,7 @@ class EnergySpec:
             coords = np.ascontiguousarray(np.asarray(self.coords, dtype=np.float32).reshape(-1, 3))
             z = np.ascontiguousarray(np.asarray(self.z, dtype=np.float32).reshape(-1))
             n = coords.shape[0]
-        spec = EnergySpecC(self.d, kin, hart, nuc, x, n, float(self.Ne), float(self.R), float(self.Z_alpha), float(self.Z_beta))
+        spec = EnergySpecC(self.d, kin, hart, nuc, x, cc, n, float(self.Ne), float(self.R), float(self.Z_alpha), float(self.Z_beta))
         return spec, coords, z
 
 
@@ -168,13 +172,13 @@ def functionals_fwd_bwd(spec: EnergySpec, y1: torch.Tensor, want_bar: bool = Tru
 
 
 def functionals_integrands(spec: EnergySpec, y1: torch.Tensor) -> torch.Tensor:
-    """ofdft_functionals_integrands: (4, bs) per-sample integrands [kin, vnuc, hart, x]."""
+    """ofdft_functionals_integrands: (5, bs) per-sample integrands [kin, vnuc, hart, x, c]."""
     lib = _lib.load()
     y1 = _f32c(y1)
     B, stride = y1.shape
     bs = B // 2
     cs, coords, z = spec.to_c()
-    e = torch.empty((4, bs), dtype=torch.float32, device=y1.device)
+    e = torch.empty((5, bs), dtype=torch.float32, device=y1.device)
     _lib.check(lib.ofdft_functionals_integrands(_stream(), C.byref(cs), _host_ptr(coords), _host_ptr(z), _ptr(y1), stride,
                                                 bs, _ptr(e)), "ofdft_functionals_integrands")
     return e

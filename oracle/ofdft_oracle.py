@@ -746,6 +746,8 @@ def energy_terms_vjp(spec: EnergySpec, y1: np.ndarray, d: int):
     """Analytic cotangent d(mean energy)/d(y1) for the north-star functionals (TF/TF1D, W, lda,
     Hartree / soft-Coulomb / MT, nuclear / HGH / attraction).  XC "next" terms are not covered."""
     from scipy.special import erf
+    if spec.c or (spec.x and spec.x.lower() not in ("lda", "local_density_approximation")):
+        return energy_terms_grad(spec, y1, d)      # "next" XC terms: row-wise central differences
     bs = y1.shape[0] // 2
     Ne = spec.Ne
     g = np.zeros_like(y1)

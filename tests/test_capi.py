@@ -30,7 +30,7 @@ def test_header_symbols_are_exported_and_bound():
 
 def test_abi_version_and_strerror():
     lib = _lib.load()
-    assert lib.ofdft_b200_abi_version() == 1
+    assert lib.ofdft_b200_abi_version() == 2
     assert b"invalid" in lib.ofdft_b200_strerror(-1)
     assert b"unsupported" in lib.ofdft_b200_strerror(-2)
     assert b"scratch" in lib.ofdft_b200_strerror(-3)
@@ -45,7 +45,7 @@ def test_size_helpers():
     assert lib.ofdft_cnf_gnn_bwd_scratch_bytes(131072, 65536, 3) >= 1024 * n_theta * 4
     assert lib.ofdft_cnf_gnn_act_ckpt_bytes(131072, 65536, 3, 1, 3, 16) == 16 * 4 * 3 * 64 * (3 * 65536 + 65536) * 4
     assert lib.ofdft_cnf_gnn_act_ckpt_bytes(300, 150, 3, 1, 3, 2) == 2 * 4 * 3 * 64 * (3 * 256 + 256) * 4   # rows padded to 128
-    assert lib.ofdft_functionals_scratch_bytes(65536) >= (65536 // 256) * 4 * 8
+    assert lib.ofdft_functionals_scratch_bytes(65536) >= (65536 // 256) * 5 * 8
     assert lib.ofdft_hartree_allpairs_scratch_bytes(1000, 777) > 0
 
 
@@ -58,7 +58,7 @@ def test_argument_validation_without_device():
     assert lib.ofdft_cnf_gnn_fwd(N, N, N, N, N, N, N, N, N, 0, 128, 128, 3, 3, 7, 7, 99, 3, 16, 0.0, 1.0, -1.0) == -2  # Na
     assert lib.ofdft_cnf_gnn_fwd(N, N, N, N, N, N, N, N, N, 0, 128, 128, 3, 3, 4, 7, 3, 3, 16, 0.0, 1.0, -1.0) == -1  # stride
     assert lib.ofdft_cnf_gnn_bwd(N, N, N, N, N, N, N, N, N, N, 0, 128, 128, 4, 3, 7, 3, 3, 16, 0.0, 1.0, -1.0) == -1  # jets
-    spec = _lib.EnergySpecC(2, 3, 1, 1, 1, 0, 2.0, 0.0, 0.0, 0.0)   # d = 2 is not a thing
+    spec = _lib.EnergySpecC(2, 3, 1, 1, 1, 0, 0, 2.0, 0.0, 0.0, 0.0)   # d = 2 is not a thing
     assert lib.ofdft_functionals_fwd_bwd(None, C.byref(spec), None, None, None, 7, 16, None, None, None, 0) == -1
     assert lib.ofdft_hartree_allpairs(None, 1, 3, 2.0, None, None, 3, 10, 10, None, None, None, None, 0) == -1
 

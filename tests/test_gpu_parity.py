@@ -147,7 +147,7 @@ def test_functionals_all_modes_match_oracle():
                         assert abs(sums[i] - terms_ref[i]) <= 1e-6 * max(abs(terms_ref[i]), 1e-30)
                     assert rel(yb.cpu().numpy(), O.energy_terms_vjp(ospec, y1, 3)) < 1e-5
                     integ = ops.functionals_integrands(spec, dev(y1)).cpu().numpy().astype(np.float64)
-                    assert np.allclose(integ.mean(1), terms_ref[:4], rtol=1e-6, atol=1e-12)
+                    assert np.allclose(integ.mean(1)[:4], terms_ref[:4], rtol=1e-6, atol=1e-12)
     # 1-D functionals (LiH.py defaults)
     y1d = O.batch_generator_1d(rng, 257).astype(np.float32).astype(np.float64)
     ospec = O.EnergySpec(Ne=2, kin="tfw_1d", hart="softc", nuc="attraction", x="", R=0.7, Z_alpha=3, Z_beta=1)
@@ -156,6 +156,51 @@ def test_functionals_all_modes_match_oracle():
     sums, yb = ops.functionals_fwd_bwd(spec, dev(y1d))
     assert np.allclose(sums.cpu().numpy()[:3], terms_ref[:3], rtol=1e-6)
     assert rel(yb.cpu().numpy(), O.energy_terms_vjp(ospec, y1d, 1)) < 1e-5
+
+
+def test_xc_functionals_driver_defaults():
+    """The reference drivers' default XC selection: --x dirac_b88_x_e --c vwn_c_e (H20_...py:241-244), pw92_c_e,
+    and xc_1d (LiH.py:217) -- fused kernel terms, cotangents and a full training step."""
+    rng = np.random.default_rng(9)
+    mol = O.molecule("H2O")
+    y1 = O.batch_generator_3d(rng, 200, mol["coords"], mol["z"]).astype(np.float32).astype(np.float64)
+    for xname, cname in (("dirac_b88_x_e", "vwn_c_e"), ("b88_x_e", "pw92_c_e"), ("lda", "vwn_c_e")):
+        ospec = O.EnergySpec(Ne=10, kin="tf-w", hart="hartree", nuc="nuclei_potential", x=xname, c=cname, coords=mol["coords"], z=mol["z"])
+        spec = ops.EnergySpec(Ne=10, d=3, kin="tf-w", hart="hartree", nuc="nuclei_potential", x=xname, c=cname, coords=mol["coords"], z=mol["z"])
+        e_ref, terms_ref = O.energy_terms(ospec, y1, 3)
+        sums, yb = ops.functionals_fwd_bwd(spec, dev(y1))
+        sums = sums.cpu().numpy()
+        for i in range(5):
+            assert abs(sums[i] - terms_ref[i]) <= 2e-6 * max(abs(terms_ref[i]), 1e-30), (xname, cname, i, sums[i], terms_ref[i])
+        assert abs(sums[5] - e_ref) <= 2e-6 * abs(e_ref)
+        assert rel(yb.cpu().numpy(), O.energy_terms_grad(ospec, y1, 3)) < 2e-5
+    y1d = O.batch_generator_1d(rng, 300).astype(np.float32).astype(np.float64)
+    ospec = O.EnergySpec(Ne=2, kin="tfw_1d", hart="softc", nuc="attraction", x="", c="xc_1d", R=0.7, Z_alpha=3, Z_beta=1)
+    spec = ops.EnergySpec(Ne=2, d=1, kin="tfw_1d", hart="softc", nuc="attraction", x="", c="xc_1d", R=0.7, Z_alpha=3, Z_beta=1)
+    e_ref, terms_ref = O.energy_terms(ospec, y1d, 1)
+    sums, yb = ops.functionals_fwd_bwd(spec, dev(y1d))
+    assert np.allclose(sums.cpu().numpy()[:5], terms_ref, rtol=2e-6, atol=1e-12)
+    assert rel(yb.cpu().numpy(), O.energy_terms_grad(ospec, y1d, 1)) < 2e-5
+    # full training step with the H2O driver defaults (tf-w, nuclei_potential, hartree, dirac_b88_x_e, vwn_c_e)
+    mol, nt, theta, batch, fld = problem("H2O", 130, 10)
+    ospec = O.EnergySpec(Ne=10, kin="tf-w", hart="hartree", nuc="nuclei_potential", x="dirac_b88_x_e", c="vwn_c_e", coords=mol["coords"], z=mol["z"])
+    spec = ops.EnergySpec(Ne=10, d=3, kin="tf-w", hart="hartree", nuc="nuclei_potential", x="dirac_b88_x_e", c="vwn_c_e", coords=mol["coords"], z=mol["z"])
+    e_ref, terms_ref, g_ref, _ = O.loss_and_grad(fld, ospec, batch, n_steps=4)
+    model = Gen_EqvFlow(3, (64, 64), mol["coords"], mol["onehot"], bool_neg=True)
+    sums, tbar, _ = EnergyEstimator(model, spec, n_steps=4).step_flat(dev(theta), dev(batch))
+    sums = sums.cpu().numpy()
+    for i in range(5):
+        assert abs(sums[i] - terms_ref[i]) <= E_TOL * abs(terms_ref[i]), (i, sums[i], terms_ref[i])
+    for name, (a, b) in tensor_slices(nt).items():
+        assert rel(tbar.cpu().numpy()[a:b], g_ref[a:b]) <= G_TOL, name
+    # c-type factory signature (den, Ne)
+    from ofdft_nflows_b200.functionals import _exchange_correlation
+    den = np.exp(y1[:200, 3:4])
+    ec = _exchange_correlation("vwn_c_e")(dev(den), 10).cpu().numpy()
+    assert ec.shape == (200, 1) and np.allclose(ec, O.correlation_vwn_c_e(den.astype(np.float32).astype(np.float64), 10), rtol=5e-6)
+    ex = _exchange_correlation("dirac_b88_x_e")(dev(den), dev(y1[:200, 4:7]), 10).cpu().numpy()
+    d32 = den.astype(np.float32).astype(np.float64)
+    assert np.allclose(ex, O.lda(d32, y1[:200, 4:7], 10) + O.b88_x_e(d32, y1[:200, 4:7], 10), rtol=5e-6)
 
 
 def test_functional_factories_drop_in_and_autograd():
@@ -200,7 +245,7 @@ def test_functional_factories_drop_in_and_autograd():
     n1 = _nuclear("attraction")(dev(y1[:64, :1]), 0.7, 3, 1, 2).cpu().numpy()
     assert np.allclose(n1, O.attraction(y1[:64, :1], 0.7, 3, 1, 2), rtol=2e-6)
     with pytest.raises(NotImplementedError):
-        _exchange_correlation("vwn_c_e")
+        _kinetic("kinetic")
 
 
 def test_hartree_allpairs_matches_numpy():

@@ -63,7 +63,9 @@ def test_batch_generator_layout_and_prior():
 def test_energy_spec_mapping():
     Ne, atoms, z, coords = utils.coordinates("H2O")
     cs, c, zz = ops.EnergySpec(Ne=10, d=3, kin="TF-W", hart="hartree", nuc="HGH", x="lda", coords=coords, z=z).to_c()
-    assert (cs.d, cs.kin, cs.hart, cs.nuc, cs.x, cs.n_nuclei) == (3, 3, 1, 2, 1, 3) and c.dtype == np.float32
+    assert (cs.d, cs.kin, cs.hart, cs.nuc, cs.x, cs.c, cs.n_nuclei) == (3, 3, 1, 2, 1, 0, 3) and c.dtype == np.float32
+    cs2, _, _ = ops.EnergySpec(Ne=10, d=3, x="dirac_b88_x_e", c="vwn_c_e", coords=coords, z=z).to_c()
+    assert (cs2.x, cs2.c) == (3, 1)
     cs1, c1, z1 = ops.EnergySpec(Ne=2, d=1, kin="tfw_1d", hart="softc", nuc="attraction", x="", R=0.7, Z_alpha=3, Z_beta=1).to_c()
     assert (cs1.kin, cs1.hart, cs1.nuc, cs1.x) == (5, 2, 3, 0) and c1 is None
     with pytest.raises(NotImplementedError):
