@@ -822,9 +822,10 @@ int launch_gnn_fwd_tc(void* stream, GnnFwdArgs& a, void* scratch, size_t scratch
   a.counter = (int*)scratch;
   cudaError_t e = cudaMemsetAsync(scratch, 0, kCounterBytes, st);
   if (e != cudaSuccess) return (int)e;
-  // OFDFT_B200_TC_NU = 4 (default: 512 threads, 16 hidden units per thread) | 2 (256 threads, 32 units per thread)
+  // OFDFT_B200_TC_NU = 2 (default: 256 threads, 32 hidden units per thread; measured 6.2 ms) | 4 (512 threads, 16 units
+  // per thread; 6.7 ms -- the kernel is bound by its serialised phases, not by occupancy)
   const char* env = getenv("OFDFT_B200_TC_NU");
-  const bool nu2 = env != nullptr && env[0] == '2';
+  const bool nu2 = !(env != nullptr && env[0] == '4');
   e = nu2 ? cudaFuncSetAttribute(gnn_fwd_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemTc) + 1024)
           : cudaFuncSetAttribute(gnn_fwd_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemTc) + 1024);
   if (e != cudaSuccess) return (int)e;
