@@ -230,10 +230,10 @@ __global__ void functionals_final_kernel(const double* __restrict__ partial, int
 // all-pairs Hartree: E = (w/(n m)) sum_ij 1/sqrt(|x_i - xp_j|^2 + c), force on x_i
 // ------------------------------------------------------------------------------------------------
 constexpr int kHpThreads = 256;
-constexpr int kHpPts = 2;                 // i-points per thread
+constexpr int kHpPts = 4;                 // i-points per thread
 constexpr int kHpTile = 256;              // j-points per shared-memory tile
 
-template <int D>
+template <int D, bool FORCES>
 __global__ void __launch_bounds__(kHpThreads) hartree_pairs_kernel(const float* __restrict__ x, const float* __restrict__ xp,
                                                                   int stride, long long n, long long m, float cst,
                                                                   int splits, double* __restrict__ epart,
@@ -256,11 +256,10 @@ __global__ void __launch_bounds__(kHpThreads) hartree_pairs_kernel(const float* 
     __syncthreads();
     {
       const long long j = jt + threadIdx.x;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 v = make_float4(1e18f, 1e18f, 1e18f, 0.f);   // padded points sit "at infinity": rsqrt -> 0, force -> 0
       if (j < j_end) {
         v.x = xp[j * stride];
-        if (D == 3) { v.y = xp[j * stride + 1]; v.z = xp[j * stride + 2]; }
-        v.w = 1.0f;                           // w = 0 masks padded points
+        if (D == 3) { v.y = xp[j * stride + 1]; v.z = xp[j * stride + 2]; } else { v.y = 0.f; v.z = 0.f; }
       }
       tile[threadIdx.x] = v;
     }
@@ -274,11 +273,14 @@ __global__ void __launch_bounds__(kHpThreads) hartree_pairs_kernel(const float* 
         float zz = fmaf(d0, d0, cst);
         float d1 = 0.f, d2 = 0.f;
         if (D == 3) { d1 = xi[p][1] - q.y; d2 = xi[p][2] - q.z; zz = fmaf(d1, d1, zz); zz = fmaf(d2, d2, zz); }
-        const float rs = rsqrtf(zz) * q.w;
+        float rs;
+        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(zz));    // MUFU.RSQ without the denormal fix-up path
         e[p] += rs;
-        const float g = rs * rs * rs;         // q.w in {0,1}
-        f[p][0] = fmaf(g, d0, f[p][0]);
-        if (D == 3) { f[p][1] = fmaf(g, d1, f[p][1]); f[p][2] = fmaf(g, d2, f[p][2]); }
+        if (FORCES) {
+          const float g = rs * rs * rs;
+          f[p][0] = fmaf(g, d0, f[p][0]);
+          if (D == 3) { f[p][1] = fmaf(g, d1, f[p][1]); f[p][2] = fmaf(g, d2, f[p][2]); }
+        }
       }
     }
     // flush the fp32 tile sums into the float64 accumulator every tile
@@ -537,8 +539,10 @@ extern "C" int ofdft_hartree_allpairs(void* stream, int32_t kind, int32_t d, flo
     dim3 grid(blocks, (unsigned)splits);
     double* ep = pass == 0 ? epart : nullptr;
     float* fp = out ? fpart : nullptr;
-    if (d == 3) hartree_pairs_kernel<3><<<grid, kHpThreads, 0, st>>>(a, b, x_stride, na, nb, cst, splits, ep, fp);
-    else hartree_pairs_kernel<1><<<grid, kHpThreads, 0, st>>>(a, b, x_stride, na, nb, cst, splits, ep, fp);
+    if (d == 3 && fp) hartree_pairs_kernel<3, true><<<grid, kHpThreads, 0, st>>>(a, b, x_stride, na, nb, cst, splits, ep, fp);
+    else if (d == 3) hartree_pairs_kernel<3, false><<<grid, kHpThreads, 0, st>>>(a, b, x_stride, na, nb, cst, splits, ep, fp);
+    else if (fp) hartree_pairs_kernel<1, true><<<grid, kHpThreads, 0, st>>>(a, b, x_stride, na, nb, cst, splits, ep, fp);
+    else hartree_pairs_kernel<1, false><<<grid, kHpThreads, 0, st>>>(a, b, x_stride, na, nb, cst, splits, ep, fp);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
     if (pass == 0) {
