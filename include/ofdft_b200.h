@@ -197,13 +197,14 @@ int ofdft_functional_eval(void* stream, int32_t family, const ofdft_energy_spec*
  * sum_{i,j}      w / sqrt(1 + (x_i - xp_j)^2)       (kind SOFTC,   d = 1, w = Ne^2)
  *   x (n, x_stride), xp (m, x_stride): first d columns are coordinates
  *   esum   : 1 float64, the pair MEAN  (1/(n*m)) * sum
- *   xbar   : NULL or (n, d) d(esum)/dx ;  xpbar : NULL or (m, d)
+ *   xbar   : NULL or (n, bar_stride) d(esum)/dx in the first d columns;  xpbar : NULL or (m, bar_stride)
+ *   accumulate != 0 adds into xbar / xpbar (e.g. the x columns of a state cotangent) instead of overwriting
  *   scratch: ofdft_hartree_allpairs_scratch_bytes(n, m)
  */
 size_t ofdft_hartree_allpairs_scratch_bytes(int64_t n, int64_t m);
 int ofdft_hartree_allpairs(void* stream, int32_t kind, int32_t d, float Ne, const float* x, const float* xp,
                            int32_t x_stride, int64_t n, int64_t m, double* esum, float* xbar, float* xpbar,
-                           void* scratch, size_t scratch_bytes);
+                           int32_t bar_stride, int32_t accumulate, void* scratch, size_t scratch_bytes);
 
 /* FP32 FFMA / SFU peak microbenchmarks (roofline denominators; bench.py).  Run `iters` dependent
  * rounds on every SM; return via *out the number of FFMA (or MUFU.RSQ) lane-operations issued. */

@@ -44,7 +44,7 @@ SIGNATURES = {
     "ofdft_functionals_integrands": (C.c_int, [vp, C.POINTER(EnergySpecC), vp, vp, vp, i32, i64, vp]),
     "ofdft_functional_eval": (C.c_int, [vp, i32, C.POINTER(EnergySpecC), vp, vp, vp, vp, i64, vp, vp, vp]),
     "ofdft_hartree_allpairs_scratch_bytes": (szt, [i64, i64]),
-    "ofdft_hartree_allpairs": (C.c_int, [vp, i32, i32, f32, vp, vp, i32, i64, i64, vp, vp, vp, vp, szt]),
+    "ofdft_hartree_allpairs": (C.c_int, [vp, i32, i32, f32, vp, vp, i32, i64, i64, vp, vp, vp, i32, i32, vp, szt]),
     "ofdft_microbench_ffma": (C.c_int, [vp, vp, i32, C.POINTER(C.c_double)]),
     "ofdft_microbench_sfu": (C.c_int, [vp, vp, i32, C.POINTER(C.c_double)]),
     "ofdft_tc_gemm_test": (C.c_int, [vp, vp, vp, vp, i32, i32]),

@@ -303,12 +303,14 @@ __global__ void __launch_bounds__(kHpThreads) hartree_pairs_kernel(const float* 
 }
 
 __global__ void hartree_force_reduce_kernel(const float* __restrict__ fpart, float* __restrict__ out, long long n_el,
-                                            int splits, float scale) {
+                                            int splits, float scale, int d, int out_stride, int accumulate) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_el) return;
   float s = 0.f;
   for (int k = 0; k < splits; ++k) s += fpart[(size_t)k * n_el + i];
-  out[i] = -scale * s;     // d/dx_i of 1/sqrt(z) = -(x_i - x_j)/z^{3/2}
+  const long long o = (i / d) * out_stride + (i % d);
+  const float v = -scale * s;     // d/dx_i of 1/sqrt(z) = -(x_i - x_j)/z^{3/2}
+  out[o] = accumulate ? out[o] + v : v;
 }
 
 __global__ void hartree_energy_reduce_kernel(const double* __restrict__ epart, int nblk, double scale, double* out) {
@@ -516,8 +518,8 @@ extern "C" size_t ofdft_hartree_allpairs_scratch_bytes(int64_t n, int64_t m) {
 
 extern "C" int ofdft_hartree_allpairs(void* stream, int32_t kind, int32_t d, float Ne, const float* x, const float* xp,
                                       int32_t x_stride, int64_t n, int64_t m, double* esum, float* xbar, float* xpbar,
-                                      void* scratch, size_t scratch_bytes) {
-  if (!x || !xp || !esum || !scratch || n <= 0 || m <= 0 || x_stride < d) return OFDFT_EINVAL;
+                                      int32_t bar_stride, int32_t accumulate, void* scratch, size_t scratch_bytes) {
+  if (!x || !xp || !esum || !scratch || n <= 0 || m <= 0 || x_stride < d || bar_stride < d) return OFDFT_EINVAL;
   float cst, w;
   if (kind == OFDFT_HART_COULOMB && d == 3) { cst = 3e-5f; w = 0.5f * Ne * Ne; }
   else if (kind == OFDFT_HART_SOFTC && d == 1) { cst = 1.0f; w = Ne * Ne; }
@@ -552,7 +554,7 @@ extern "C" int ofdft_hartree_allpairs(void* stream, int32_t kind, int32_t d, flo
     }
     if (out) {
       const long long n_el = na * d;
-      hartree_force_reduce_kernel<<<(unsigned)((n_el + 255) / 256), 256, 0, st>>>(fpart, out, n_el, splits, (float)scale);
+      hartree_force_reduce_kernel<<<(unsigned)((n_el + 255) / 256), 256, 0, st>>>(fpart, out, n_el, splits, (float)scale, d, bar_stride, accumulate);
       e = cudaGetLastError();
       if (e != cudaSuccess) return (int)e;
     }

@@ -49,11 +49,22 @@ def shard_batch(batch, rank: int, world: int):
 class EnergyEstimator:
     def __init__(self, model: Any, spec: ops.EnergySpec, n_steps: int = DEFAULT_N_STEPS, t0: float = 0.0, t1: float = 1.0,
                  skip_unused_jets: bool = True, group: Optional[Any] = None, act_ckpt: bool = True,
-                 act_ckpt_max_bytes: int = 64 << 30):
+                 act_ckpt_max_bytes: int = 64 << 30, hartree_mode: str = "paired"):
         self.model, self.spec, self.n_steps, self.t0, self.t1 = model, spec, int(n_steps), float(t0), float(t1)
         # rows of the second half only supply xp: integrate them without the logp/score channels
         self.jets_b = ops.JETS_X if skip_unused_jets else ops.JETS_FULL
         self.group = group
+        # "paired": the reference's row-paired O(bs) Hartree estimator (functionals.py:463-486);
+        # "allpairs": the lower-variance O(bs^2) cross-half estimator of the same double integral (north star): the
+        # second half's coordinates (and the first half's, for the partner forces) are all-gathered over NCCL and every
+        # rank evaluates its bs/G x bs strip with the tiled pair kernel.
+        if hartree_mode not in ("paired", "allpairs"):
+            raise ValueError(hartree_mode)
+        self.hartree_mode = hartree_mode
+        if hartree_mode == "allpairs":
+            import dataclasses
+            self._hart_kind = spec.hart
+            self.spec = dataclasses.replace(spec, hart="")        # local functionals without the paired Hartree term
         # keep the layer-2 activation jets of every RHS evaluation in HBM instead of recomputing them in the backward
         # pass (B200: 180 GB); falls back to recomputation above ``act_ckpt_max_bytes``
         self.act_ckpt, self.act_ckpt_max_bytes = bool(act_ckpt), int(act_ckpt_max_bytes)
@@ -87,6 +98,8 @@ class EnergyEstimator:
                                    self.t0, self.t1, m.y0, want_ckpt=True, want_act=want_act)
             e1 = mark()
             sums, ybar1 = ops.functionals_fwd_bwd(self.spec, y1)
+            if self.hartree_mode == "allpairs":
+                self._allpairs_hartree(y1, ybar1, sums)
             e2 = mark()
             tbar, _ = ops.gnn_bwd(theta, m.xyz_nuclei, m.z_one_hot, ckpt, ybar1, bs, ops.JETS_FULL, self.jets_b,
                                   self.n_steps, self.t0, self.t1, m.y0)
@@ -113,6 +126,26 @@ class EnergyEstimator:
             sums /= ws
             tbar /= ws
         return sums, tbar, y1
+
+    def _allpairs_hartree(self, y1: torch.Tensor, ybar1: torch.Tensor, sums: torch.Tensor) -> None:
+        """Adds the all-pairs Hartree energy of this rank's strip to ``sums`` and its forces to ``ybar1`` (in place)."""
+        bs = y1.shape[0] // 2
+        x_loc, xp_loc = y1[:bs], y1[bs:]                       # contiguous row blocks; coordinates are the first d columns
+        x_all, xp_all = x_loc, xp_loc
+        if self._dist():
+            import torch.distributed as dist
+            ws = dist.get_world_size(self.group)
+            x_all = torch.empty((ws * bs, y1.shape[1]), dtype=y1.dtype, device=y1.device)
+            xp_all = torch.empty_like(x_all)
+            dist.all_gather_into_tensor(xp_all, xp_loc.contiguous(), group=self.group)
+            dist.all_gather_into_tensor(x_all, x_loc.contiguous(), group=self.group)
+        Ne = self.spec.Ne
+        # strip (local x) x (all xp): energy of the strip + forces on the local x rows
+        esum, _, _ = ops.hartree_allpairs(x_loc, xp_all, Ne, self._hart_kind, xbar_into=ybar1[:bs])
+        # strip (local xp) x (all x): forces on the local xp rows (same pair normalisation: equal shard sizes)
+        ops.hartree_allpairs(xp_loc, x_all, Ne, self._hart_kind, xbar_into=ybar1[bs:])
+        sums[2:3] += esum
+        sums[5:6] += esum
 
     def value_and_grad(self, params: Dict[str, Any], batch: torch.Tensor):
         """-> ((energy, F_values), grads) with ``grads`` shaped like ``params``."""

@@ -184,8 +184,11 @@ def functionals_integrands(spec: EnergySpec, y1: torch.Tensor) -> torch.Tensor:
     return e
 
 
-def hartree_allpairs(x: torch.Tensor, xp: torch.Tensor, Ne: float, kind: str = "hartree", want_grad: bool = True):
-    """ofdft_hartree_allpairs: cross-set pair mean + gradients.  x (n, >=d), xp (m, >=d)."""
+def hartree_allpairs(x: torch.Tensor, xp: torch.Tensor, Ne: float, kind: str = "hartree", want_grad: bool = True,
+                     xbar_into: Optional[torch.Tensor] = None, xpbar_into: Optional[torch.Tensor] = None):
+    """ofdft_hartree_allpairs: cross-set pair mean + gradients.  x (n, >=d), xp (m, >=d) sharing the row stride.
+    ``xbar_into`` / ``xpbar_into``: contiguous (n|m, stride) cotangent buffers whose first d columns are ADDED to
+    (the kernel accumulates in place); otherwise fresh (n|m, d) tensors are returned."""
     lib = _lib.load()
     x, xp = _f32c(x), _f32c(xp)
     d = 3 if HART[kind] == 1 else 1
@@ -193,12 +196,22 @@ def hartree_allpairs(x: torch.Tensor, xp: torch.Tensor, Ne: float, kind: str = "
         raise ValueError("x and xp must share the row stride")
     n, m = x.shape[0], xp.shape[0]
     esum = torch.empty(1, dtype=torch.float64, device=x.device)
-    xbar = torch.empty((n, d), dtype=torch.float32, device=x.device) if want_grad else None
-    xpbar = torch.empty((m, d), dtype=torch.float32, device=x.device) if want_grad else None
+    accumulate = xbar_into is not None or xpbar_into is not None
+    if accumulate:
+        xbar, xpbar = xbar_into, xpbar_into
+        strides = {t.shape[1] for t in (xbar, xpbar) if t is not None}
+        if len(strides) != 1 or any(not t.is_contiguous() or t.dtype != torch.float32 for t in (xbar, xpbar) if t is not None):
+            raise ValueError("xbar_into / xpbar_into must be contiguous float32 buffers with a common row stride")
+        bar_stride = strides.pop()
+    else:
+        xbar = torch.empty((n, d), dtype=torch.float32, device=x.device) if want_grad else None
+        xpbar = torch.empty((m, d), dtype=torch.float32, device=x.device) if want_grad else None
+        bar_stride = d
     sb = lib.ofdft_hartree_allpairs_scratch_bytes(n, m)
     scratch = torch.empty(sb, dtype=torch.uint8, device=x.device)
     _lib.check(lib.ofdft_hartree_allpairs(_stream(), HART[kind], d, float(Ne), _ptr(x), _ptr(xp), x.shape[1], n, m,
-                                          _ptr(esum), _ptr(xbar), _ptr(xpbar), _ptr(scratch), sb), "ofdft_hartree_allpairs")
+                                          _ptr(esum), _ptr(xbar), _ptr(xpbar), bar_stride, int(accumulate), _ptr(scratch), sb),
+               "ofdft_hartree_allpairs")
     return esum, xbar, xpbar
 
 

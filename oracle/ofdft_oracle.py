@@ -692,6 +692,17 @@ class EnergySpec:
     Z_beta: float = 0.0
 
 
+def hartree_allpairs(x, xp, Ne, eps=1e-5):
+    """North-star generalisation of the paired estimator (functionals.py:463-486): the same kernel averaged over ALL
+    cross-half pairs.  Returns (mean energy, d/dx, d/dxp)."""
+    diff = x[:, None, :] - xp[None]
+    zz = (diff * diff + eps).sum(-1)
+    n, m = zz.shape
+    e = 0.5 * Ne ** 2 * (1.0 / np.sqrt(zz)).mean()
+    gk = -0.5 * Ne ** 2 * diff / zz[..., None] ** 1.5 / (n * m)
+    return e, gk.sum(1), -gk.sum(0)
+
+
 def energy_terms(spec: EnergySpec, y1: np.ndarray, d: int):
     """Per-term means [kin, vnuc, hart, x, c] and total, from the t1 state (2*bs rows).
     Only the first half's den/score/x enter the local functionals; the second half supplies xp
@@ -701,7 +712,11 @@ def energy_terms(spec: EnergySpec, y1: np.ndarray, d: int):
     den = np.exp(y1[:bs, d:d + 1])
     score = y1[:bs, d + 1:2 * d + 1]
     e_t = _kinetic(spec.kin)(den, score, spec.Ne)
-    e_h = _hartree(spec.hart)(x, xp, spec.Ne)
+    allpairs = spec.hart.lower() == "hartree_allpairs"
+    if not spec.hart:
+        e_h = np.zeros_like(den)
+    else:
+        e_h = np.full_like(den, hartree_allpairs(x, xp, spec.Ne)[0]) if allpairs else _hartree(spec.hart)(x, xp, spec.Ne)
     if spec.nuc.lower() in ("attraction", "attr"):
         e_n = attraction(x, spec.R, spec.Z_alpha, spec.Z_beta, spec.Ne)
     else:
@@ -768,7 +783,14 @@ def energy_terms_vjp(spec: EnergySpec, y1: np.ndarray, d: int):
     assert not spec.c
     hn = spec.hart.lower()
     diff = x - xp
-    if hn in ("hartree_potential", "hartree"):
+    if not hn:
+        gx = np.zeros_like(diff)
+    elif hn == "hartree_allpairs":
+        _, gxa, gxpa = hartree_allpairs(x, xp, Ne)
+        g[:bs, :d] += gxa * bs          # the common 1/bs below is undone: the pair mean is already normalised
+        g[bs:, :d] += gxpa * bs
+        gx = np.zeros_like(diff)
+    elif hn in ("hartree_potential", "hartree"):
         zz = (diff * diff + 1e-5).sum(-1, keepdims=True)
         gx = -0.5 * Ne ** 2 * diff / zz ** 1.5
     elif hn in ("soft_coulomb", "softc"):

@@ -60,7 +60,7 @@ def test_argument_validation_without_device():
     assert lib.ofdft_cnf_gnn_bwd(N, N, N, N, N, N, N, N, N, N, 0, 128, 128, 4, 3, 7, 3, 3, 16, 0.0, 1.0, -1.0) == -1  # jets
     spec = _lib.EnergySpecC(2, 3, 1, 1, 1, 0, 0, 2.0, 0.0, 0.0, 0.0)   # d = 2 is not a thing
     assert lib.ofdft_functionals_fwd_bwd(None, C.byref(spec), None, None, None, 7, 16, None, None, None, 0) == -1
-    assert lib.ofdft_hartree_allpairs(None, 1, 3, 2.0, None, None, 3, 10, 10, None, None, None, None, 0) == -1
+    assert lib.ofdft_hartree_allpairs(None, 1, 3, 2.0, None, None, 3, 10, 10, None, None, None, 3, 0, None, 0) == -1
 
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):

@@ -50,17 +50,26 @@ def _install_fake_ops(mol, n_steps):
         _, tbar = O.rk4_adjoint(fld(theta), state["stages"], t0, t1, ybar1.numpy(), True)
         return torch.as_tensor(tbar), None
 
+    def hartree_allpairs(x, xp, Ne, kind="hartree", want_grad=True, xbar_into=None, xpbar_into=None):
+        e, gx, gxp = O.hartree_allpairs(x[:, :3].numpy().astype(np.float64), xp[:, :3].numpy().astype(np.float64), Ne)
+        if xbar_into is not None:
+            xbar_into[:, :3] += torch.as_tensor(gx)
+        if xpbar_into is not None:
+            xpbar_into[:, :3] += torch.as_tensor(gxp)
+        return torch.tensor([e], dtype=torch.float64), None, None
+
     ops.gnn_fwd, ops.functionals_fwd_bwd, ops.gnn_bwd = gnn_fwd, functionals_fwd_bwd, gnn_bwd
+    ops.hartree_allpairs = hartree_allpairs
     ops.gnn_act_ckpt_bytes = lambda *a: 0
 
 
-def _make_estimator(mol, n_steps):
+def _make_estimator(mol, n_steps, hartree_mode="paired"):
     from ofdft_nflows_b200 import ops
     from ofdft_nflows_b200.equiv_flows import Gen_EqvFlow
     from ofdft_nflows_b200.estimator import EnergyEstimator
     model = Gen_EqvFlow(3, (64, 64), mol["coords"], mol["onehot"], bool_neg=True, device="cpu")
     spec = ops.EnergySpec(Ne=10, d=3, kin="tf-w", hart="hartree", nuc="hgh", x="lda", coords=mol["coords"], z=mol["z"])
-    return EnergyEstimator(model, spec, n_steps=n_steps)
+    return EnergyEstimator(model, spec, n_steps=n_steps, hartree_mode=hartree_mode)
 
 
 def _worker(rank, world, port, out):
@@ -70,11 +79,14 @@ def _worker(rank, world, port, out):
     from ofdft_nflows_b200.estimator import shard_batch
     mol, theta, batch = _problem()
     _install_fake_ops(mol, 4)
-    est = _make_estimator(mol, 4)
     local = torch.as_tensor(shard_batch(batch, rank, world))
-    sums, tbar, _ = est.step_flat(torch.as_tensor(theta), local)
+    res = {}
+    for mode in ("paired", "allpairs"):
+        est = _make_estimator(mol, 4, mode)
+        sums, tbar, _ = est.step_flat(torch.as_tensor(theta), local)
+        res[f"sums_{mode}"] = sums.numpy(); res[f"tbar_{mode}"] = tbar.numpy()
     if rank == 0:
-        np.savez(out, sums=sums.numpy(), tbar=tbar.numpy())
+        np.savez(out, **res)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -85,10 +97,17 @@ def test_two_rank_step_equals_single_process(tmp_path):
     got = np.load(out)
     mol, theta, batch = _problem()
     _install_fake_ops(mol, 4)
-    est = _make_estimator(mol, 4)
-    sums, tbar, _ = est.step_flat(torch.as_tensor(theta), torch.as_tensor(batch))
-    assert np.allclose(got["sums"], sums.numpy(), rtol=1e-12, atol=1e-14)
-    assert np.linalg.norm(got["tbar"] - tbar.numpy()) < 1e-12 * np.linalg.norm(tbar.numpy())
+    for mode in ("paired", "allpairs"):          # allpairs: all-gather of coordinates + strip evaluation per rank
+        est = _make_estimator(mol, 4, mode)
+        sums, tbar, _ = est.step_flat(torch.as_tensor(theta), torch.as_tensor(batch))
+        assert np.allclose(got[f"sums_{mode}"], sums.numpy(), rtol=1e-12, atol=1e-14), mode
+        assert np.linalg.norm(got[f"tbar_{mode}"] - tbar.numpy()) < 1e-12 * np.linalg.norm(tbar.numpy()), mode
+    # and the single-process all-pairs step equals the oracle's all-pairs loss
+    fld = O.GNNField(O.unflatten_params(theta, 5, (64, 64)), mol["coords"], mol["onehot"], True)
+    ospec = O.EnergySpec(Ne=10, kin="tf-w", hart="hartree_allpairs", nuc="hgh", x="lda", coords=mol["coords"], z=mol["z"])
+    e_ref, _, g_ref, _ = O.loss_and_grad(fld, ospec, batch, n_steps=4)
+    assert abs(sums.numpy()[5] - e_ref) < 1e-12 * abs(e_ref)
+    assert np.linalg.norm(tbar.numpy() - g_ref) < 1e-11 * np.linalg.norm(g_ref)
 
 
 def test_shard_batch_pairs_partners():

@@ -158,6 +158,27 @@ def test_functionals_all_modes_match_oracle():
     assert rel(yb.cpu().numpy(), O.energy_terms_vjp(ospec, y1d, 1)) < 1e-5
 
 
+def test_allpairs_hartree_training_step_matches_oracle():
+    """hartree_mode='allpairs': the O(bs^2) cross-half estimator (north star) inside the fused step."""
+    mol, nt, theta, batch, fld = problem("H2O", 150, 12)
+    ospec = O.EnergySpec(Ne=10, kin="tf-w", hart="hartree_allpairs", nuc="nuclei_potential", x="lda", coords=mol["coords"], z=mol["z"])
+    e_ref, terms_ref, g_ref, y1_ref = O.loss_and_grad(fld, ospec, batch, n_steps=4)
+    model = Gen_EqvFlow(3, (64, 64), mol["coords"], mol["onehot"], bool_neg=True)
+    spec = ops.EnergySpec(Ne=10, d=3, kin="tf-w", hart="hartree", nuc="nuclei_potential", x="lda", coords=mol["coords"], z=mol["z"])
+    # the second half now needs no logp/score either: x-only jets stay valid
+    est = EnergyEstimator(model, spec, n_steps=4, hartree_mode="allpairs")
+    sums, tbar, _ = est.step_flat(dev(theta), dev(batch))
+    sums = sums.cpu().numpy()
+    for i in range(4):
+        assert abs(sums[i] - terms_ref[i]) <= E_TOL * abs(terms_ref[i]), (i, sums[i], terms_ref[i])
+    assert abs(sums[5] - e_ref) <= E_TOL * abs(e_ref)
+    for name, (a, b) in tensor_slices(nt).items():
+        assert rel(tbar.cpu().numpy()[a:b], g_ref[a:b]) <= G_TOL, name
+    # all-pairs estimates the same double integral as the paired estimator, with lower variance
+    e_pair = O.hartree_potential(y1_ref[:150, :3], y1_ref[150:, :3], 10).mean()
+    assert abs(terms_ref[2] - e_pair) < 0.2 * abs(e_pair)
+
+
 def test_xc_functionals_driver_defaults():
     """The reference drivers' default XC selection: --x dirac_b88_x_e --c vwn_c_e (H20_...py:241-244), pw92_c_e,
     and xc_1d (LiH.py:217) -- fused kernel terms, cotangents and a full training step."""
