@@ -206,6 +206,21 @@ int ofdft_hartree_allpairs(void* stream, int32_t kind, int32_t d, float Ne, cons
                            int32_t x_stride, int64_t n, int64_t m, double* esum, float* xbar, float* xpbar,
                            int32_t bar_stride, int32_t accumulate, void* scratch, size_t scratch_bytes);
 
+/* ---- callers either side of the path --------------------------------------------
+ * Promolecular prior (ofdft_normflows/promolecular_distrax.py:52-62,86-89): mixture of unit-variance Gaussians on the
+ * nuclei with weights Z_i / sum Z.  x (n, x_stride) -> out (n) = log p(x) [ - sub[i*sub_stride] ] [ exp() if exp_out ],
+ * score (n,3) = grad log p(x); out or score may be NULL.  With sub = Delta logp of the reverse flow and exp_out = 1
+ * this is the last step of rho_rev (H20_mol_ofdft_min_equiv_flows.py:132-137).  coords / z are HOST pointers. */
+int ofdft_promolecular_logp_score(void* stream, const float* coords, const float* z, int32_t n_nuclei, const float* x,
+                                  int32_t x_stride, int64_t n, const float* sub, int32_t sub_stride, int32_t exp_out,
+                                  float* out, float* score);
+/* batch_generator (ofdft_normflows/utils.py:76-108): out (2*bs, 7) rows [x, log rho0(x), grad log rho0(x)], two
+ * independent draws; Philox stream (seed, row, offset) -- advance `offset` every call.  1-D variant
+ * (utils.py:110-143 with the N(0,1) prior of LiH.py:78): out (2*bs, 3). */
+int ofdft_batch_generator_3d(void* stream, uint64_t seed, uint64_t offset, const float* coords, const float* z,
+                             int32_t n_nuclei, int64_t bs, float* out);
+int ofdft_batch_generator_1d(void* stream, uint64_t seed, uint64_t offset, int64_t bs, float* out);
+
 /* FP32 FFMA / SFU peak microbenchmarks (roofline denominators; bench.py).  Run `iters` dependent
  * rounds on every SM; return via *out the number of FFMA (or MUFU.RSQ) lane-operations issued. */
 int ofdft_microbench_ffma(void* stream, float* sink, int32_t iters, double* ops_out);

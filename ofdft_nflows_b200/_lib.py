@@ -45,6 +45,9 @@ SIGNATURES = {
     "ofdft_functional_eval": (C.c_int, [vp, i32, C.POINTER(EnergySpecC), vp, vp, vp, vp, i64, vp, vp, vp]),
     "ofdft_hartree_allpairs_scratch_bytes": (szt, [i64, i64]),
     "ofdft_hartree_allpairs": (C.c_int, [vp, i32, i32, f32, vp, vp, i32, i64, i64, vp, vp, vp, i32, i32, vp, szt]),
+    "ofdft_promolecular_logp_score": (C.c_int, [vp, vp, vp, i32, vp, i32, i64, vp, i32, i32, vp, vp]),
+    "ofdft_batch_generator_3d": (C.c_int, [vp, C.c_uint64, C.c_uint64, vp, vp, i32, i64, vp]),
+    "ofdft_batch_generator_1d": (C.c_int, [vp, C.c_uint64, C.c_uint64, i64, vp]),
     "ofdft_microbench_ffma": (C.c_int, [vp, vp, i32, C.POINTER(C.c_double)]),
     "ofdft_microbench_sfu": (C.c_int, [vp, vp, i32, C.POINTER(C.c_double)]),
     "ofdft_tc_gemm_test": (C.c_int, [vp, vp, vp, vp, i32, i32]),

@@ -1,0 +1,126 @@
+// prior.cu -- base-distribution kernels on the device (the callers either side of the
+// hot path): the promolecular prior's log-density / score (ofdft_normflows/promolecular_distrax.py:52-62,86-89), the
+// batch generators (ofdft_normflows/utils.py:76-143) and the last step of rho_rev (H20_mol_ofdft_min_equiv_flows.py:132-137).
+// Elementwise / HBM-bound; Philox counter-based RNG from curand's device API (reproducible per (seed, row)).
+#include <curand_kernel.h>
+
+#include "common.cuh"
+
+namespace ofdft {
+
+constexpr int kPriorMaxNuc = 64;
+struct PriorArgs {
+  float coords[kPriorMaxNuc * 3];
+  float logw[kPriorMaxNuc];     // log(Z_i / sum Z)
+  float cdf[kPriorMaxNuc];
+  int n_nuclei;
+};
+
+// log p(x) and grad log p(x) of the mixture of unit-variance Gaussians on the nuclei
+__device__ __forceinline__ void promolecular(const PriorArgs& P, const float (&x)[3], float& logp, float (&score)[3]) {
+  float mx = -INFINITY;
+  for (int i = 0; i < P.n_nuclei; ++i) {
+    const float d0 = x[0] - P.coords[3 * i], d1 = x[1] - P.coords[3 * i + 1], d2 = x[2] - P.coords[3 * i + 2];
+    mx = fmaxf(mx, P.logw[i] - 0.5f * (d0 * d0 + d1 * d1 + d2 * d2));
+  }
+  float tot = 0.f, s0 = 0.f, s1 = 0.f, s2 = 0.f;
+  for (int i = 0; i < P.n_nuclei; ++i) {
+    const float d0 = x[0] - P.coords[3 * i], d1 = x[1] - P.coords[3 * i + 1], d2 = x[2] - P.coords[3 * i + 2];
+    const float e = expf(P.logw[i] - 0.5f * (d0 * d0 + d1 * d1 + d2 * d2) - mx);
+    tot += e; s0 += e * d0; s1 += e * d1; s2 += e * d2;
+  }
+  logp = logf(tot) + mx - 2.756815599614018f;        // - (3/2) log(2 pi)
+  const float inv = 1.0f / tot;
+  score[0] = -s0 * inv; score[1] = -s1 * inv; score[2] = -s2 * inv;
+}
+
+__global__ void promolecular_kernel(const PriorArgs P, const float* __restrict__ x, int x_stride, long long n,
+                                    const float* __restrict__ sub, int sub_stride, int exp_out,
+                                    float* __restrict__ out, float* __restrict__ score) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float xv[3] = {x[i * x_stride], x[i * x_stride + 1], x[i * x_stride + 2]};
+  float lp, sc[3];
+  promolecular(P, xv, lp, sc);
+  if (sub != nullptr) lp -= sub[i * sub_stride];
+  if (out != nullptr) out[i] = exp_out ? expf(lp) : lp;
+  if (score != nullptr) { score[3 * i] = sc[0]; score[3 * i + 1] = sc[1]; score[3 * i + 2] = sc[2]; }
+}
+
+__global__ void batch_generator_3d_kernel(const PriorArgs P, unsigned long long seed, unsigned long long offset,
+                                          long long rows, float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows) return;
+  curandStatePhilox4_32_10_t st;
+  curand_init(seed, (unsigned long long)i, offset, &st);
+  const float u = curand_uniform(&st);
+  int c = 0;
+  while (c + 1 < P.n_nuclei && u > P.cdf[c]) ++c;
+  const float4 g = curand_normal4(&st);
+  const float xv[3] = {P.coords[3 * c] + g.x, P.coords[3 * c + 1] + g.y, P.coords[3 * c + 2] + g.z};
+  float lp, sc[3];
+  promolecular(P, xv, lp, sc);
+  float* o = out + i * 7;
+  o[0] = xv[0]; o[1] = xv[1]; o[2] = xv[2]; o[3] = lp; o[4] = sc[0]; o[5] = sc[1]; o[6] = sc[2];
+}
+
+__global__ void batch_generator_1d_kernel(unsigned long long seed, unsigned long long offset, long long rows,
+                                          float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows) return;
+  curandStatePhilox4_32_10_t st;
+  curand_init(seed, (unsigned long long)i, offset, &st);
+  const float x = curand_normal(&st);
+  out[3 * i] = x; out[3 * i + 1] = -0.5f * x * x - 0.9189385332046727f; out[3 * i + 2] = -x;
+}
+
+static int fill_prior(PriorArgs& P, const float* coords, const float* z, int n) {
+  if (!coords || !z || n < 1) return OFDFT_EINVAL;
+  if (n > kPriorMaxNuc) return OFDFT_EUNSUPPORTED;
+  double tot = 0.0;
+  for (int i = 0; i < n; ++i) tot += fabs((double)z[i]);
+  double acc = 0.0;
+  for (int i = 0; i < n; ++i) {
+    P.coords[3 * i] = coords[3 * i]; P.coords[3 * i + 1] = coords[3 * i + 1]; P.coords[3 * i + 2] = coords[3 * i + 2];
+    const double w = (double)z[i] / tot;
+    P.logw[i] = (float)log(w);
+    acc += w;
+    P.cdf[i] = (float)acc;
+  }
+  P.n_nuclei = n;
+  return 0;
+}
+
+}  // namespace ofdft
+
+using namespace ofdft;
+
+extern "C" int ofdft_promolecular_logp_score(void* stream, const float* coords, const float* z, int32_t n_nuclei,
+                                             const float* x, int32_t x_stride, int64_t n, const float* sub,
+                                             int32_t sub_stride, int32_t exp_out, float* out, float* score) {
+  if (!x || n <= 0 || x_stride < 3 || (!out && !score)) return OFDFT_EINVAL;
+  PriorArgs P;
+  int rc = fill_prior(P, coords, z, n_nuclei);
+  if (rc) return rc;
+  promolecular_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(P, x, x_stride, n, sub, sub_stride,
+                                                                                      exp_out, out, score);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int ofdft_batch_generator_3d(void* stream, uint64_t seed, uint64_t offset, const float* coords, const float* z,
+                                        int32_t n_nuclei, int64_t bs, float* out) {
+  if (!out || bs <= 0) return OFDFT_EINVAL;
+  PriorArgs P;
+  int rc = fill_prior(P, coords, z, n_nuclei);
+  if (rc) return rc;
+  const long long rows = 2 * bs;
+  batch_generator_3d_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(P, seed, offset, rows, out);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int ofdft_batch_generator_1d(void* stream, uint64_t seed, uint64_t offset, int64_t bs, float* out) {
+  if (!out || bs <= 0) return OFDFT_EINVAL;
+  const long long rows = 2 * bs;
+  batch_generator_1d_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(seed, offset, rows, out);
+  return (int)cudaGetLastError();
+}

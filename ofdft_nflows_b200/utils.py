@@ -110,3 +110,78 @@ def batche_generator_1D(seed: int, batch_size: int) -> Iterator[np.ndarray]:
             x = rng.standard_normal((batch_size, 1))
             halves.append(np.concatenate([x, -0.5 * x * x - 0.5 * math.log(2 * math.pi), -x], 1))
         yield np.concatenate(halves, 0).astype(np.float32)
+
+
+# ---- device-side variants (CUDA kernels of csrc/prior.cu) -----------------------------
+
+def _prior_tables(prior: ProMolecularDensity):
+    coords = np.ascontiguousarray(prior.loc, dtype=np.float32)
+    z = np.ascontiguousarray(prior.z, dtype=np.float32)
+    return coords, z
+
+
+def promolecular_log_prob_score_device(prior: ProMolecularDensity, x, want_score: bool = True):
+    """log rho0(x) (n,1) and grad log rho0(x) (n,3) for a CUDA tensor x (n, >=3) -- ofdft_promolecular_logp_score."""
+    import torch
+    from . import _lib, ops
+    lib = _lib.load()
+    x = ops._f32c(x)
+    n = x.shape[0]
+    coords, z = _prior_tables(prior)
+    out = torch.empty((n, 1), dtype=torch.float32, device=x.device)
+    score = torch.empty((n, 3), dtype=torch.float32, device=x.device) if want_score else None
+    _lib.check(lib.ofdft_promolecular_logp_score(ops._stream(), coords.ctypes.data, z.ctypes.data, len(z), ops._ptr(x), x.shape[1],
+                                                 n, None, 0, 0, ops._ptr(out), ops._ptr(score)), "ofdft_promolecular_logp_score")
+    return out, score
+
+
+def batch_generator_device(seed: int, batch_size: int, prior: ProMolecularDensity, device="cuda"):
+    """utils.py:76-108 on the device: yields (2*bs, 7) CUDA tensors [x, log rho0, grad log rho0] (Philox, reproducible
+    per (seed, call index)); no host input is needed for a training step."""
+    import torch
+    from . import _lib, ops
+    lib = _lib.load()
+    coords, z = _prior_tables(prior)
+    call = 0
+    while True:
+        out = torch.empty((2 * batch_size, 7), dtype=torch.float32, device=device)
+        with torch.cuda.device(out.device):
+            _lib.check(lib.ofdft_batch_generator_3d(ops._stream(), seed, call, coords.ctypes.data, z.ctypes.data, len(z),
+                                                    batch_size, ops._ptr(out)), "ofdft_batch_generator_3d")
+        call += 1
+        yield out
+
+
+def batche_generator_1D_device(seed: int, batch_size: int, device="cuda"):
+    """utils.py:110-143 on the device (N(0,1) prior of LiH.py:78): yields (2*bs, 3) CUDA tensors."""
+    import torch
+    from . import _lib, ops
+    lib = _lib.load()
+    call = 0
+    while True:
+        out = torch.empty((2 * batch_size, 3), dtype=torch.float32, device=device)
+        with torch.cuda.device(out.device):
+            _lib.check(lib.ofdft_batch_generator_1d(ops._stream(), seed, call, batch_size, ops._ptr(out)), "ofdft_batch_generator_1d")
+        call += 1
+        yield out
+
+
+def rho_rev(params, x, model_rev, prior: ProMolecularDensity, n_steps: int = None):
+    """rho_rev(params, x) of the 3-D drivers (H20_mol_ofdft_min_equiv_flows.py:132-137): density of the flow at the points
+    x (n,3): z_t = [x, 0] -> neural_ode(model_rev, -1 -> 0) -> exp(log rho0(z0) - Delta logp).  Returns (n,1)."""
+    import torch
+    from . import _lib, ops
+    from .jax_ode import DEFAULT_N_STEPS
+    lib = _lib.load()
+    x = ops._f32c(x)
+    n = x.shape[0]
+    zt = torch.zeros((n, 4), dtype=torch.float32, device=x.device)
+    zt[:, :3] = x[:, :3]
+    theta = model_rev.flat_theta(params).detach()
+    y0, _ = ops.gnn_fwd(theta, model_rev.xyz_nuclei, model_rev.z_one_hot, zt, n, ops.JETS_XLOGP, ops.JETS_XLOGP,
+                        n_steps or DEFAULT_N_STEPS, -1.0, 0.0, model_rev.y0)
+    coords, z = _prior_tables(prior)
+    rho = torch.empty((n, 1), dtype=torch.float32, device=x.device)
+    _lib.check(lib.ofdft_promolecular_logp_score(ops._stream(), coords.ctypes.data, z.ctypes.data, len(z), ops._ptr(y0), 4, n,
+                                                 y0.data_ptr() + 12, 4, 1, ops._ptr(rho), None), "ofdft_promolecular_logp_score")
+    return rho

@@ -308,6 +308,48 @@ def test_drop_in_neural_ode_score_autograd():
     assert np.abs(dy - fld.rhs(0.25, batch[:, :4], False)).max() < 2e-6 * max(1.0, np.abs(dy).max())
 
 
+def test_device_prior_batch_generator_and_rho_rev():
+    """prior log-density/score and the batch generators on the device; rho_rev
+    (H20_mol_ofdft_min_equiv_flows.py:132-137) = reverse no-score flow + prior."""
+    Ne, atoms, z, coords = utils.coordinates("H2O")
+    prior = utils.ProMolecularDensity(z, coords)
+    rng = np.random.default_rng(13)
+    x = (coords[rng.integers(0, 3, 500)] + rng.standard_normal((500, 3))).astype(np.float32)
+    lp, sc = utils.promolecular_log_prob_score_device(prior, dev(x))
+    lp_ref, sc_ref = O.promolecular_logp_score(x.astype(np.float64), coords, z)
+    assert np.abs(lp.cpu().numpy() - lp_ref).max() < 2e-6 * np.abs(lp_ref).max()
+    assert np.abs(sc.cpu().numpy() - sc_ref).max() < 2e-6 * max(1.0, np.abs(sc_ref).max())
+    gen = utils.batch_generator_device(7, 20000, prior)
+    b0 = next(gen); b1 = next(gen)
+    assert b0.shape == (40000, 7) and not torch.equal(b0, b1)
+    assert torch.equal(b0, next(utils.batch_generator_device(7, 20000, prior)))          # reproducible per (seed, call)
+    bn = b0.cpu().numpy().astype(np.float64)
+    lp_ref, sc_ref = O.promolecular_logp_score(bn[:, :3], coords, z)
+    assert np.abs(bn[:, 3] - lp_ref[:, 0]).max() < 1e-5 and np.abs(bn[:, 4:] - sc_ref).max() < 1e-5
+    w = z / z.sum()
+    assert np.abs(bn[:, :3].mean(0) - (w[:, None] * coords).sum(0)).max() < 0.03          # E[x] = sum w_i R_i, sigma/sqrt(n) ~ 0.006
+    second = (w[:, None] * (coords ** 2 + 1.0)).sum(0)
+    assert np.abs((bn[:, :3] ** 2).mean(0) - second).max() < 0.06
+    assert np.abs(np.corrcoef(bn[:20000, 0], bn[20000:, 0])[0, 1]) < 0.03                 # the two halves are independent draws
+    b1d = next(utils.batche_generator_1D_device(3, 50000)).cpu().numpy()
+    assert abs(b1d[:, 0].mean()) < 0.02 and abs(b1d[:, 0].std() - 1.0) < 0.02 and np.allclose(b1d[:, 2], -b1d[:, 0])
+    assert np.allclose(b1d[:, 1], -0.5 * b1d[:, 0] ** 2 - 0.5 * np.log(2 * np.pi), atol=1e-6)
+    # rho_rev: density of the flow evaluated at forward-flowed samples equals exp(logp) carried by the forward pass
+    mol, nt, theta, batch, fld = problem("H2O", 100, 14)
+    fwd = Gen_EqvFlow(3, (64, 64), mol["coords"], mol["onehot"], bool_neg=True)
+    rev = Gen_EqvFlow(3, (64, 64), mol["coords"], mol["onehot"], bool_neg=False)
+    params = fwd.unravel(dev(theta))
+    x1, logp1, _ = neural_ode_score(params, dev(batch), fwd, 0.0, 1.0, 3, n_steps=32)
+    rho = utils.rho_rev(params, x1, rev, prior, n_steps=32).cpu().numpy()
+    assert np.abs(rho[:, 0] - np.exp(logp1.cpu().numpy()[:, 0])).max() < 2e-4 * np.exp(logp1.cpu().numpy()).max()
+    # and against the float64 oracle with the same scheme
+    frev = O.GNNField(fld.params, mol["coords"], mol["onehot"], bool_neg=False)
+    x1n = x1.cpu().numpy().astype(np.float64)
+    y0 = O.odeint_rk4(lambda yy, t: frev.rhs(t, yy, False), np.concatenate([x1n, np.zeros((200, 1))], 1), -1.0, 0.0, 32)
+    rho_ref = np.exp(O.promolecular_logp_score(y0[:, :3], mol["coords"], mol["z"])[0][:, 0] - y0[:, 3])
+    assert np.abs(rho[:, 0] - rho_ref).max() < 1e-5 * rho_ref.max()
+
+
 # ---- 1-D tanh-MLP flow (LiH.py: CNF(1,(512,512,512)), tfw_1d + softc + attr) ------------------------------------
 
 def _mlp_problem(feat, bs, seed):
