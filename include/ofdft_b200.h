@@ -221,6 +221,12 @@ int ofdft_batch_generator_3d(void* stream, uint64_t seed, uint64_t offset, const
                              int32_t n_nuclei, int64_t bs, float* out);
 int ofdft_batch_generator_1d(void* stream, uint64_t seed, uint64_t offset, int64_t bs, float* out);
 
+/* Optimiser step of the drivers: optax.chain(clip_by_global_norm(max_norm), rmsprop(lr))
+ * (H20_mol_ofdft_min_equiv_flows.py:111-116; optax defaults decay = 0.9, eps = 1e-8 inside the square root, nu0 = 0).
+ * In place on theta (n) and the second-moment state nu (n); max_norm <= 0 disables the clip. */
+int ofdft_rmsprop_clip_step(void* stream, float* theta, const float* grad, float* nu, int64_t n, float lr, float decay,
+                            float eps, float max_norm);
+
 /* FP32 FFMA / SFU peak microbenchmarks (roofline denominators; bench.py).  Run `iters` dependent
  * rounds on every SM; return via *out the number of FFMA (or MUFU.RSQ) lane-operations issued. */
 int ofdft_microbench_ffma(void* stream, float* sink, int32_t iters, double* ops_out);

@@ -124,3 +124,44 @@ extern "C" int ofdft_batch_generator_1d(void* stream, uint64_t seed, uint64_t of
   batch_generator_1d_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(seed, offset, rows, out);
   return (int)cudaGetLastError();
 }
+
+// ------------------------------------------------------------------------------------------------
+// optimiser step: optax.chain(clip_by_global_norm(max_norm), rmsprop(lr))
+// as the drivers build it (H20_mol_ofdft_min_equiv_flows.py:111-116).  [third-party] optax semantics restated from
+// its published algorithm: scale = min(1, max_norm / ||g||_2);  nu <- decay nu + (1-decay) g^2;
+// theta <- theta - lr * g * rsqrt(nu + eps)   (eps inside the square root, initial nu = 0).
+// One CTA: theta has 4.6k-527k entries, the step is latency-bound and runs after the gradient all-reduce.
+// ------------------------------------------------------------------------------------------------
+namespace ofdft {
+__global__ void __launch_bounds__(1024) rmsprop_clip_kernel(float* __restrict__ theta, const float* __restrict__ grad,
+                                                            float* __restrict__ nu, long long n, float lr, float decay,
+                                                            float eps, float max_norm) {
+  __shared__ double red[32];
+  double s = 0.0;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) s += (double)grad[i] * (double)grad[i];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (threadIdx.x == 0) red[0] = v;
+  }
+  __syncthreads();
+  const float gnorm = (float)sqrt(red[0]);
+  const float scale = (max_norm > 0.f && gnorm > max_norm) ? max_norm / gnorm : 1.0f;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    const float g = grad[i] * scale;
+    const float v = decay * nu[i] + (1.0f - decay) * g * g;
+    nu[i] = v;
+    theta[i] -= lr * g * rsqrtf(v + eps);
+  }
+}
+}  // namespace ofdft
+
+extern "C" int ofdft_rmsprop_clip_step(void* stream, float* theta, const float* grad, float* nu, int64_t n, float lr,
+                                       float decay, float eps, float max_norm) {
+  if (!theta || !grad || !nu || n <= 0) return OFDFT_EINVAL;
+  ofdft::rmsprop_clip_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(theta, grad, nu, n, lr, decay, eps, max_norm);
+  return (int)cudaGetLastError();
+}

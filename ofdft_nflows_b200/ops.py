@@ -230,3 +230,14 @@ def microbench(kind: str, iters: int = 2000, repeat: int = 5) -> float:
         b.synchronize()
         best = min(best, a.elapsed_time(b) * 1e-3)
     return ops.value * (2.0 if kind == "ffma" else 1.0) / best
+
+
+def rmsprop_clip_step(theta: torch.Tensor, grad: torch.Tensor, nu: torch.Tensor, lr: float, decay: float = 0.9,
+                      eps: float = 1e-8, max_norm: float = 1.0) -> None:
+    """ofdft_rmsprop_clip_step: optax.chain(clip_by_global_norm(max_norm), rmsprop(lr)) in place on flat theta / nu."""
+    lib = _lib.load()
+    for t in (theta, grad, nu):
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+            raise ValueError("theta / grad / nu must be contiguous float32 CUDA tensors")
+    _lib.check(lib.ofdft_rmsprop_clip_step(_stream(), _ptr(theta), _ptr(grad), _ptr(nu), theta.numel(), float(lr), float(decay),
+                                           float(eps), float(max_norm)), "ofdft_rmsprop_clip_step")

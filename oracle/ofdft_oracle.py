@@ -927,3 +927,15 @@ def molecule(name: str):
                       [-1.2494488074, -2.1642720181, -0.0003281198], [-2.4988922798, 0.0006052813, -0.0002941369]]) * BOHR
         z = np.array([6.] * 6 + [1.] * 6); return dict(coords=c, z=z, Ne=42, onehot=index_one_hot(z))
     raise KeyError(name)
+
+
+# ----------------------------------------------------------------------------------------------
+# optimiser step (H20_mol_ofdft_min_equiv_flows.py:111-116) -- [third-party] optax semantics, restated from memory
+# ----------------------------------------------------------------------------------------------
+
+def rmsprop_clip_step(theta, grad, nu, lr, decay=0.9, eps=1e-8, max_norm=1.0):
+    """optax.chain(clip_by_global_norm(max_norm), rmsprop(lr)): returns (theta', nu')."""
+    gn = np.sqrt((grad * grad).sum())
+    g = grad * (max_norm / gn if gn > max_norm else 1.0)
+    nu2 = decay * nu + (1.0 - decay) * g * g
+    return theta - lr * g / np.sqrt(nu2 + eps), nu2

@@ -350,6 +350,31 @@ def test_device_prior_batch_generator_and_rho_rev():
     assert np.abs(rho[:, 0] - rho_ref).max() < 1e-5 * rho_ref.max()
 
 
+def test_rmsprop_clip_step_and_short_training_run():
+    """clip_by_global_norm(1.0) + rmsprop on the flat parameters, and a 20-step run of the whole
+    loop (device batch generator -> fused step -> optimiser) that must lower the energy."""
+    rng = np.random.default_rng(15)
+    th = rng.standard_normal(4609); g = 3.0 * rng.standard_normal(4609); nu = np.abs(rng.standard_normal(4609)) * 0.1
+    t_ref, nu_ref = O.rmsprop_clip_step(th, g, nu, 3e-4)
+    t_d, g_d, nu_d = dev(th), dev(g), dev(nu)
+    ops.rmsprop_clip_step(t_d, g_d, nu_d, 3e-4)
+    assert np.abs(t_d.cpu().numpy() - t_ref).max() < 1e-6 and np.abs(nu_d.cpu().numpy() - nu_ref).max() < 1e-6
+    Ne, atoms, z, coords = utils.coordinates("H2")
+    prior = utils.ProMolecularDensity(z, coords)
+    model = Gen_EqvFlow(3, (64, 64), coords, utils.jax_one_hot(z), bool_neg=True)
+    theta = model.flat_theta(model.init(0)).contiguous()            # reference default init: identity flow
+    nu_t = torch.zeros_like(theta)
+    spec = ops.EnergySpec(Ne=Ne, d=3, kin="tf-w", hart="hartree", nuc="nuclei_potential", x="lda", coords=coords, z=z)
+    est = EnergyEstimator(model, spec, n_steps=8)
+    gen = utils.batch_generator_device(0, 4096, prior)
+    energies = []
+    for _ in range(20):
+        sums, tbar, _ = est.step_flat(theta, next(gen))
+        energies.append(sums[5].item())
+        ops.rmsprop_clip_step(theta, tbar, nu_t, 3e-3)
+    assert np.mean(energies[-5:]) < np.mean(energies[:5]) - 0.02, energies
+
+
 # ---- 1-D tanh-MLP flow (LiH.py: CNF(1,(512,512,512)), tfw_1d + softc + attr) ------------------------------------
 
 def _mlp_problem(feat, bs, seed):
