@@ -108,6 +108,8 @@ const char* ofdft_b200_strerror(int code);
  *             remove the recompute GEMM from the backward pass; NULL selects recomputation)
  *   y0sign  : +1 (bool_neg=False) or -1 (bool_neg=True): t' = y0*t, output scaled by y0
  *   scratch : ofdft_cnf_gnn_fwd_scratch_bytes() bytes
+ *   B = 0 (an empty shard) is a no-op returning OFDFT_OK; the adjoint of an empty shard writes a zero theta_bar.
+ *   Na > 16 or n_types > 8 return OFDFT_EUNSUPPORTED (the kernels keep the per-nucleus first-layer offsets on chip).
  */
 size_t ofdft_cnf_gnn_ckpt_bytes(int64_t B, int32_t n_steps);
 size_t ofdft_cnf_gnn_act_ckpt_bytes(int64_t B, int64_t n_a, int32_t jets_a, int32_t jets_b, int32_t Na, int32_t n_steps);

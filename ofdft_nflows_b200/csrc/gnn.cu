@@ -774,7 +774,7 @@ static int num_sms() {
 }
 
 static int check_common(long long B, long long n_a, int ja, int jb, int Na, int nt, int n_steps) {
-  if (B <= 0 || n_a < 0 || n_a > B || n_steps <= 0) return OFDFT_EINVAL;
+  if (B < 0 || n_a < 0 || n_a > B || n_steps <= 0) return OFDFT_EINVAL;
   if (ja < 1 || ja > 3 || jb < 1 || jb > 3) return OFDFT_EINVAL;
   if (Na < 1 || Na > kMaxNa || nt < 0 || nt > kMaxTypes) return OFDFT_EUNSUPPORTED;
   return 0;
@@ -832,6 +832,7 @@ extern "C" int ofdft_cnf_gnn_fwd(void* stream, const float* theta, const float* 
                                  int32_t Na, int32_t n_types, int32_t n_steps, float t0, float t1, float y0sign) {
   int rc = check_common(B, n_a, jets_a, jets_b, Na, n_types, n_steps);
   if (rc) return rc;
+  if (B == 0) return 0;   // empty shard: nothing to integrate
   const int jmax = jets_a > jets_b ? jets_a : jets_b;
   const int need = jmax == 3 ? 7 : (jmax == 2 ? 4 : 3);
   if (in_stride < need || out_stride < need) return OFDFT_EINVAL;
@@ -846,6 +847,7 @@ extern "C" int ofdft_cnf_gnn_rhs(void* stream, const float* theta, const float* 
                                  float t, float y0sign) {
   int rc = check_common(B, B, jets, jets, Na, n_types, 1);
   if (rc) return rc;
+  if (B == 0) return 0;
   const int need = jets == 3 ? 7 : (jets == 2 ? 4 : 3);
   if (stride < need) return OFDFT_EINVAL;
   GnnFwdArgs a{theta, nuclei, onehot, y, dy, nullptr, nullptr, B, B, jets, jets, stride, stride,
@@ -860,6 +862,10 @@ extern "C" int ofdft_cnf_gnn_bwd(void* stream, const float* theta, const float* 
                                  int32_t Na, int32_t n_types, int32_t n_steps, float t0, float t1, float y0sign) {
   int rc = check_common(B, n_a, jets_a, jets_b, Na, n_types, n_steps);
   if (rc) return rc;
+  if (B == 0) {           // empty shard: the gradient of an empty sum
+    if (!theta_bar) return OFDFT_EINVAL;
+    return (int)cudaMemsetAsync(theta_bar, 0, (size_t)GnnThetaLayout(n_types).n * sizeof(float), (cudaStream_t)stream);
+  }
   if (!theta || !nuclei || !ckpt || !ybar1 || !theta_bar || !scratch) return OFDFT_EINVAL;
   if (n_types > 0 && !onehot) return OFDFT_EINVAL;
   const int jmax = jets_a > jets_b ? jets_a : jets_b;

@@ -343,7 +343,11 @@ constexpr int kColB1 = 0, kColDw = 192, kColA = 256;
 #ifndef OFDFT_TC_FLUSH_PER_EVAL
 #define OFDFT_TC_FLUSH_PER_EVAL 0
 #endif
-constexpr bool kFlushPerEval = OFDFT_TC_FLUSH_PER_EVAL != 0;   // else: once per RK4 stage (Na evaluations, Na*96 MMAs)
+constexpr bool kFlushPerEval = OFDFT_TC_FLUSH_PER_EVAL != 0;
+#ifndef OFDFT_TC_PREFETCH_L2
+#define OFDFT_TC_PREFETCH_L2 1
+#endif
+constexpr bool kPrefetchL2 = OFDFT_TC_PREFETCH_L2 != 0;   // else: once per RK4 stage (Na evaluations, Na*96 MMAs)
 
 struct SmemTcB {
   float A1T[32 * kA1TChunk];
@@ -497,6 +501,16 @@ __device__ void bwd_tile_tc(SmemTcB& sm, const GnnBwdArgs& a, long long row0, lo
             q0[u] = __ldcs(src + (long long)u * act_rows);
             if (NJ >= 2) q1[u] = __ldcs(src + jet_stride + (long long)u * act_rows);
             if (NJ == 3) q2[u] = __ldcs(src + 2 * jet_stride + (long long)u * act_rows);
+          }
+          // pull the next evaluation's jets (backward order: next nucleus, else the previous stage) into L2 behind these
+          // loads: one 128-B line per (unit, jet) of this warp's 32 trajectories, lane <-> unit
+          const long long ss = (long long)(step * 4 + stage);
+          const long long en = (i + 1 < a.Na) ? ss * a.Na + i + 1 : (ss - 1) * a.Na;
+          if (kPrefetchL2 && en >= 0) {
+            const float* nx = a.act + AL.seg_base(en, seg_b) + (row0 - seg_row0) + (long long)(32 * uh + lane) * act_rows
+                              + 32 * (w & 3);
+#pragma unroll
+            for (int jt = 0; jt < NJ; ++jt) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + jt * jet_stride));
           }
         }
         // ---- first layer (recomputed): a1 = tanh(w_r r + c) ----

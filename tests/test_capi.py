@@ -54,7 +54,8 @@ def test_argument_validation_without_device():
     # null pointers / bad sizes are rejected before any CUDA call
     N = None
     assert lib.ofdft_cnf_gnn_fwd(N, N, N, N, N, N, N, N, N, 0, 128, 128, 3, 3, 7, 7, 3, 3, 16, 0.0, 1.0, -1.0) == -1
-    assert lib.ofdft_cnf_gnn_fwd(N, N, N, N, N, N, N, N, N, 0, 0, 0, 3, 3, 7, 7, 3, 3, 16, 0.0, 1.0, -1.0) == -1   # B <= 0
+    assert lib.ofdft_cnf_gnn_fwd(N, N, N, N, N, N, N, N, N, 0, 0, 0, 3, 3, 7, 7, 3, 3, 16, 0.0, 1.0, -1.0) == 0    # empty shard: no-op
+    assert lib.ofdft_cnf_gnn_fwd(N, N, N, N, N, N, N, N, N, 0, -1, 0, 3, 3, 7, 7, 3, 3, 16, 0.0, 1.0, -1.0) == -1  # B < 0
     assert lib.ofdft_cnf_gnn_fwd(N, N, N, N, N, N, N, N, N, 0, 128, 128, 3, 3, 7, 7, 99, 3, 16, 0.0, 1.0, -1.0) == -2  # Na
     assert lib.ofdft_cnf_gnn_fwd(N, N, N, N, N, N, N, N, N, 0, 128, 128, 3, 3, 4, 7, 3, 3, 16, 0.0, 1.0, -1.0) == -1  # stride
     assert lib.ofdft_cnf_gnn_bwd(N, N, N, N, N, N, N, N, N, N, 0, 128, 128, 4, 3, 7, 3, 3, 16, 0.0, 1.0, -1.0) == -1  # jets

@@ -130,6 +130,79 @@ def test_golden_vectors_reference_semantics(path):
     assert np.abs(y1.cpu().numpy()[:bs, :3] - g["y1"][:bs, :3]).max() < 1e-4
 
 
+def _synthetic_field(Na, nt, seed):
+    """Random geometry with ``Na`` nuclei of ``nt`` species (not a reference molecule: exercises the kernel limits)."""
+    rng = np.random.default_rng(seed)
+    coords = 2.5 * rng.standard_normal((Na, 3))
+    onehot = np.zeros((Na, nt)); onehot[np.arange(Na), rng.integers(0, nt, Na)] = 1.0
+    p = O.init_params(rng, 2 + nt, (64, 64), 1, last_scale=0.5 * min(1.0, 3.0 / Na))
+    for w, b in p.hidden:
+        b[:] = 0.1 * rng.standard_normal(b.shape)
+    p.last[1][:] = 0.05
+    theta = O.flatten_params(p).astype(np.float32).astype(np.float64)
+    fld = O.GNNField(O.unflatten_params(theta, 2 + nt, (64, 64)), coords, onehot, bool_neg=True)
+    return coords, onehot, theta, fld
+
+
+@pytest.mark.parametrize("Na,nt,B,n_a,n_steps", [(1, 1, 1, 1, 1), (3, 2, 1, 0, 2), (16, 3, 130, 129, 2), (16, 4, 257, 0, 1),
+                                                 (5, 0, 40, 40, 3)])
+def test_edge_shapes_forward_and_adjoint_match_oracle(Na, nt, B, n_a, n_steps):
+    """Single-row batches, an empty first / second segment, tile tails of one row, the maximum nucleus count (16),
+    a species-free one-hot (n_types = 0) and a single RK4 step -- forward states and the discrete adjoint (both
+    checkpoint modes) against the float64 oracle with the same scheme."""
+    coords, onehot, theta, fld = _synthetic_field(Na, max(nt, 1), 11 + Na + B)
+    if nt == 0:
+        onehot = np.zeros((Na, 0))
+        I = 2
+        sl = tensor_slices(1)["W1"]
+        keep = np.ones(theta.size, bool); keep[sl[0] + 64 * I: sl[1]] = False
+        theta = theta[keep]
+        fld = O.GNNField(O.unflatten_params(theta, I, (64, 64)), coords, onehot, bool_neg=True)
+    rng = np.random.default_rng(5)
+    y0 = np.concatenate([coords[rng.integers(0, Na, B)] + rng.standard_normal((B, 3)), rng.standard_normal((B, 4))], 1)
+    y0 = y0.astype(np.float32).astype(np.float64)
+    ybar1 = rng.standard_normal((B, 7))
+    ybar1[n_a:, 3:] = 0.0                      # rows of the x-only segment have no logp / score cotangent
+    fn = lambda y, t: fld.rhs(t, y, True)
+    ref, stages = O.odeint_rk4(fn, y0, 0.0, 1.0, n_steps, keep=True)
+    ybar0_ref, g_ref = O.rk4_adjoint(fld, stages, 0.0, 1.0, ybar1, True)
+    th, nuc, oh = dev(theta), dev(coords), torch.zeros((Na, nt), device="cuda") if nt == 0 else dev(onehot)
+    for want_act in (True, False):
+        y1, ck = ops.gnn_fwd(th, nuc, oh, dev(y0), n_a, 3, 1, n_steps, 0.0, 1.0, -1.0, want_ckpt=True, want_act=want_act)
+        y1 = y1.cpu().numpy()
+        assert np.abs(y1[:n_a] - ref[:n_a]).max(initial=0.0) < 5e-6 * max(1.0, np.abs(ref).max())
+        assert np.abs(y1[n_a:, :3] - ref[n_a:, :3]).max(initial=0.0) < 5e-6 * max(1.0, np.abs(ref).max())
+        g, yb0 = ops.gnn_bwd(th, nuc, oh, ck, dev(ybar1), n_a, 3, 1, n_steps, 0.0, 1.0, -1.0, want_ybar0=True)
+        assert rel(g.cpu().numpy(), g_ref) <= G_TOL, rel(g.cpu().numpy(), g_ref)
+        yb0 = yb0.cpu().numpy()
+        assert rel(yb0[:n_a], ybar0_ref[:n_a]) <= G_TOL if n_a else True
+        assert rel(yb0[n_a:, :3], ybar0_ref[n_a:, :3]) <= G_TOL if n_a < B else True
+
+
+def test_error_behaviour_of_the_c_abi():
+    """Bad arguments are reported, never silently computed on: more nuclei than the kernels are instantiated for,
+    a theta of the wrong length, host tensors."""
+    coords, onehot, theta, _ = _synthetic_field(17, 2, 3)
+    y = torch.zeros((4, 7), device="cuda")
+    with pytest.raises(RuntimeError, match="code -2"):
+        ops.gnn_fwd(dev(theta), dev(coords), dev(onehot), y, 4, 3, 3, 2, 0.0, 1.0, -1.0)
+    coords, onehot, theta, _ = _synthetic_field(3, 2, 3)
+    # an empty shard is not an error: no states, a zero gradient
+    y1, ck = ops.gnn_fwd(dev(theta), dev(coords), dev(onehot), torch.zeros((0, 7), device="cuda"), 0, 3, 3, 2, 0.0, 1.0, -1.0,
+                         want_ckpt=True, want_act=True)
+    assert y1.shape == (0, 7)
+    g, _ = ops.gnn_bwd(dev(theta), dev(coords), dev(onehot), ck, torch.zeros((0, 7), device="cuda"), 0, 3, 3, 2, 0.0, 1.0, -1.0)
+    assert g.shape == (theta.size,) and float(g.abs().max()) == 0.0
+    with pytest.raises(RuntimeError, match="code -1"):
+        ops.gnn_fwd(dev(theta), dev(coords), dev(onehot), y, 5, 3, 3, 2, 0.0, 1.0, -1.0)        # n_a > B
+    with pytest.raises(RuntimeError, match="code -1"):
+        ops.gnn_fwd(dev(theta), dev(coords), dev(onehot), y, 4, 3, 3, 0, 0.0, 1.0, -1.0)        # n_steps = 0
+    with pytest.raises(ValueError):
+        ops.gnn_fwd(dev(theta)[:-1], dev(coords), dev(onehot), y, 4, 3, 3, 2, 0.0, 1.0, -1.0)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.gnn_fwd(torch.as_tensor(theta, dtype=torch.float32), dev(coords), dev(onehot), y, 4, 3, 3, 2, 0.0, 1.0, -1.0)
+
+
 def test_functionals_all_modes_match_oracle():
     rng = np.random.default_rng(4)
     mol = O.molecule("H2O")
