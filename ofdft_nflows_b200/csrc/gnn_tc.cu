@@ -23,8 +23,9 @@ namespace ofdft {
 constexpr int kChunkBytesA = kTP * 16;      // LBO of the activation operand (128 rows x 16 B)
 constexpr int kChunkBytesB = kH * 16;       // LBO of the weight operand (64 rows x 16 B)
 
-struct SmemTc {
-  float Abuf[2][2][kH * kTP];        // [jet buffer][hi/lo][16 chunks][128 rows][4]
+template <int NB>
+struct SmemTcT {
+  float Abuf[NB][2][kH * kTP];       // [jet buffer][hi/lo][16 chunks][128 rows][4]
   float Whi[kH * kH], Wlo[kH * kH];  // B operand: [16 chunks of k][64 rows j][4]
   float wr[kH], wt[kH], b2[kH], w3[kH];
   float cb[kMaxNa * kH];
@@ -35,6 +36,8 @@ struct SmemTc {
   unsigned int tmem_slot;
   int tile;
 };
+using SmemTc = SmemTcT<2>;     // one CTA per SM, jets 0 and 1 staged together
+using SmemTc1 = SmemTcT<1>;    // 107 KB: two CTAs per SM, jets staged one at a time (the co-resident CTA fills the waits)
 
 // stage one jet (UPT units of one trajectory) as hi/lo tf32 operands
 template <int UPT>
@@ -64,8 +67,8 @@ __device__ __forceinline__ void issue_jet_mma(uint32_t d_tmem, uint64_t a_hi, ui
   }
 }
 
-template <int NJ, int NU>
-__device__ void fwd_tile_tc(SmemTc& sm, const GnnFwdArgs& a, long long row0, long long seg_end, float b3,
+template <int NJ, int NU, int NB>
+__device__ void fwd_tile_tc(SmemTcT<NB>& sm, const GnnFwdArgs& a, long long row0, long long seg_end, float b3,
                             bool seg_b, long long seg_row0, uint32_t tmem, uint32_t (&phase)[3]) {
   const ActLayout AL(a.act_rows_a, a.act_rows_b, a.jets_a, a.jets_b);
   const long long act_rows = seg_b ? a.act_rows_b : a.act_rows_a;
@@ -91,8 +94,8 @@ __device__ void fwd_tile_tc(SmemTc& sm, const GnnFwdArgs& a, long long row0, lon
   const uint32_t tlane = tmem + ((uint32_t)(32 * (w & 3)) << 16);
   const uint64_t dA00 = tc::make_desc(tc::smem_u32(sm.Abuf[0][0]), kChunkBytesA, 128);
   const uint64_t dA01 = tc::make_desc(tc::smem_u32(sm.Abuf[0][1]), kChunkBytesA, 128);
-  const uint64_t dA10 = tc::make_desc(tc::smem_u32(sm.Abuf[1][0]), kChunkBytesA, 128);
-  const uint64_t dA11 = tc::make_desc(tc::smem_u32(sm.Abuf[1][1]), kChunkBytesA, 128);
+  const uint64_t dA10 = tc::make_desc(tc::smem_u32(sm.Abuf[NB - 1][0]), kChunkBytesA, 128);
+  const uint64_t dA11 = tc::make_desc(tc::smem_u32(sm.Abuf[NB - 1][1]), kChunkBytesA, 128);
   const uint64_t dWh = tc::make_desc(tc::smem_u32(sm.Whi), kChunkBytesB, 128);
   const uint64_t dWl = tc::make_desc(tc::smem_u32(sm.Wlo), kChunkBytesB, 128);
 
@@ -157,52 +160,82 @@ __device__ void fwd_tile_tc(SmemTc& sm, const GnnFwdArgs& a, long long row0, lon
           for (int u = 0; u < UPT; ++u)
             av[u] = tanh_f(fmaf(sm.wr[UPT * uh + u], r, fmaf(tprime, sm.wt[UPT * uh + u], cbi[u])));
         }
-        stage_jet<UPT>(sm.Abuf[0][0], sm.Abuf[0][1], av, m, uh);
-        if (NJ >= 2) {
-          float a1[UPT];
+        if (NB == 1) {
+          // single operand buffer: stage -> MMA -> wait, jet by jet, on one mbarrier
 #pragma unroll
-          for (int u = 0; u < UPT; ++u) a1[u] = fmaf(-av[u], av[u], 1.0f) * sm.wr[UPT * uh + u];
-          stage_jet<UPT>(sm.Abuf[1][0], sm.Abuf[1][1], a1, m, uh);
-        }
-        tc::fence_async_smem();
-        __syncthreads();
-        if (w == 0) {
-          tc::fence_after_sync();
-          if (tc::elect_one()) {
-            issue_jet_mma(tmem + 0 * kH, dA00, dA01, dWh, dWl, idesc);
-            tc::commit(&sm.bar[0]);
-            if (NJ >= 2) {
-              issue_jet_mma(tmem + 1 * kH, dA10, dA11, dWh, dWl, idesc);
-              tc::commit(&sm.bar[1]);
+          for (int jt = 0; jt < NJ; ++jt) {
+            if (jt > 0) { tc::mbar_wait(&sm.bar[0], phase[0]); phase[0] ^= 1; __syncwarp(); }
+            if (jt == 0) stage_jet<UPT>(sm.Abuf[0][0], sm.Abuf[0][1], av, m, uh);
+            else {
+              float aj[UPT];
+#pragma unroll
+              for (int u = 0; u < UPT; ++u) {
+                const float wv = sm.wr[UPT * uh + u];
+                const float a1 = fmaf(-av[u], av[u], 1.0f) * wv;
+                aj[u] = jt == 1 ? a1 : -2.0f * av[u] * a1 * wv;
+              }
+              stage_jet<UPT>(sm.Abuf[0][0], sm.Abuf[0][1], aj, m, uh);
+            }
+            tc::fence_async_smem();
+            __syncthreads();
+            if (w == 0) {
+              tc::fence_after_sync();
+              if (tc::elect_one()) {
+                issue_jet_mma(tmem + jt * kH, dA00, dA01, dWh, dWl, idesc);
+                tc::commit(&sm.bar[0]);
+              }
+              __syncwarp();
             }
           }
-          __syncwarp();
-        }
-        if (NJ == 3) {
-          float a2[UPT];
+          tc::mbar_wait(&sm.bar[0], phase[0]); phase[0] ^= 1;
+        } else {
+          stage_jet<UPT>(sm.Abuf[0][0], sm.Abuf[0][1], av, m, uh);
+          if (NJ >= 2) {
+            float a1[UPT];
 #pragma unroll
-          for (int u = 0; u < UPT; ++u) {
-            const float wv = sm.wr[UPT * uh + u];
-            a2[u] = -2.0f * av[u] * fmaf(-av[u], av[u], 1.0f) * wv * wv;
+            for (int u = 0; u < UPT; ++u) a1[u] = fmaf(-av[u], av[u], 1.0f) * sm.wr[UPT * uh + u];
+            stage_jet<UPT>(sm.Abuf[NB - 1][0], sm.Abuf[NB - 1][1], a1, m, uh);
           }
-          tc::mbar_wait(&sm.bar[0], phase[0]);           // jet-0 MMAs have finished reading buffer 0
-          __syncwarp();
-          stage_jet<UPT>(sm.Abuf[0][0], sm.Abuf[0][1], a2, m, uh);
           tc::fence_async_smem();
           __syncthreads();
           if (w == 0) {
             tc::fence_after_sync();
             if (tc::elect_one()) {
-              issue_jet_mma(tmem + 2 * kH, dA00, dA01, dWh, dWl, idesc);
-              tc::commit(&sm.bar[2]);
+              issue_jet_mma(tmem + 0 * kH, dA00, dA01, dWh, dWl, idesc);
+              tc::commit(&sm.bar[0]);
+              if (NJ >= 2) {
+                issue_jet_mma(tmem + 1 * kH, dA10, dA11, dWh, dWl, idesc);
+                tc::commit(&sm.bar[1]);
+              }
             }
             __syncwarp();
           }
+          if (NJ == 3) {
+            float a2[UPT];
+#pragma unroll
+            for (int u = 0; u < UPT; ++u) {
+              const float wv = sm.wr[UPT * uh + u];
+              a2[u] = -2.0f * av[u] * fmaf(-av[u], av[u], 1.0f) * wv * wv;
+            }
+            tc::mbar_wait(&sm.bar[0], phase[0]);           // jet-0 MMAs have finished reading buffer 0
+            __syncwarp();
+            stage_jet<UPT>(sm.Abuf[0][0], sm.Abuf[0][1], a2, m, uh);
+            tc::fence_async_smem();
+            __syncthreads();
+            if (w == 0) {
+              tc::fence_after_sync();
+              if (tc::elect_one()) {
+                issue_jet_mma(tmem + 2 * kH, dA00, dA01, dWh, dWl, idesc);
+                tc::commit(&sm.bar[2]);
+              }
+              __syncwarp();
+            }
+          }
+          // ---- wait for the last commit (commits complete in order), then the tanh-jet epilogue from TMEM ----
+          if (NJ == 3) { tc::mbar_wait(&sm.bar[2], phase[2]); phase[2] ^= 1; phase[0] ^= 1; tc::mbar_wait(&sm.bar[1], phase[1]); phase[1] ^= 1; }
+          else if (NJ == 2) { tc::mbar_wait(&sm.bar[1], phase[1]); phase[1] ^= 1; tc::mbar_wait(&sm.bar[0], phase[0]); phase[0] ^= 1; }
+          else { tc::mbar_wait(&sm.bar[0], phase[0]); phase[0] ^= 1; }
         }
-        // ---- wait for the last commit (commits complete in order), then the tanh-jet epilogue from TMEM ----
-        if (NJ == 3) { tc::mbar_wait(&sm.bar[2], phase[2]); phase[2] ^= 1; phase[0] ^= 1; tc::mbar_wait(&sm.bar[1], phase[1]); phase[1] ^= 1; }
-        else if (NJ == 2) { tc::mbar_wait(&sm.bar[1], phase[1]); phase[1] ^= 1; tc::mbar_wait(&sm.bar[0], phase[0]); phase[0] ^= 1; }
-        else { tc::mbar_wait(&sm.bar[0], phase[0]); phase[0] ^= 1; }
         __syncwarp();                                   // tcgen05.ld is .sync.aligned: reconverge after the spin loops
         tc::fence_after_sync();
         float fp[3] = {0.f, 0.f, 0.f};
@@ -268,11 +301,11 @@ __device__ void fwd_tile_tc(SmemTc& sm, const GnnFwdArgs& a, long long row0, lon
   }
 }
 
-template <int NU>
-__global__ void __launch_bounds__(kTP * NU, 1) gnn_fwd_tc_kernel(const GnnFwdArgs a) {
+template <int NU, int NB>
+__global__ void __launch_bounds__(kTP * NU, NB == 1 ? 2 : 1) gnn_fwd_tc_kernel(const GnnFwdArgs a) {
   constexpr int kThr = kTP * NU;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  SmemTc& sm = *reinterpret_cast<SmemTc*>(smem_raw);
+  SmemTcT<NB>& sm = *reinterpret_cast<SmemTcT<NB>*>(smem_raw);
   const int tid = threadIdx.x;
   const GnnThetaLayout L(a.n_types);
   // weight operand B[n = j][k] = W2[k][j], split hi/lo, layout [k/4][j][k%4]
@@ -316,9 +349,9 @@ __global__ void __launch_bounds__(kTP * NU, 1) gnn_fwd_tc_kernel(const GnnFwdArg
     bool seg_b; long long seg_row0;
     if (tile < tiles_a) { row0 = tile * kTP; seg_end = a.n_a; nj = a.jets_a; seg_b = false; seg_row0 = 0; }
     else { row0 = a.n_a + (tile - tiles_a) * kTP; seg_end = a.B; nj = a.jets_b; seg_b = true; seg_row0 = a.n_a; }
-    if (nj == 3) fwd_tile_tc<3, NU>(sm, a, row0, seg_end, b3, seg_b, seg_row0, tmem, phase);
-    else if (nj == 2) fwd_tile_tc<2, NU>(sm, a, row0, seg_end, b3, seg_b, seg_row0, tmem, phase);
-    else fwd_tile_tc<1, NU>(sm, a, row0, seg_end, b3, seg_b, seg_row0, tmem, phase);
+    if (nj == 3) fwd_tile_tc<3, NU, NB>(sm, a, row0, seg_end, b3, seg_b, seg_row0, tmem, phase);
+    else if (nj == 2) fwd_tile_tc<2, NU, NB>(sm, a, row0, seg_end, b3, seg_b, seg_row0, tmem, phase);
+    else fwd_tile_tc<1, NU, NB>(sm, a, row0, seg_end, b3, seg_b, seg_row0, tmem, phase);
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -579,14 +612,13 @@ __device__ void bwd_tile_tc(SmemTcB& sm, const GnnBwdArgs& a, long long row0, lo
             const float sg1 = fmaf(-av[u], av[u], 1.0f);
             const float a1j = jt == 0 ? av[u] : (jt == 1 ? sg1 * wv : -2.0f * av[u] * sg1 * wv * wv);
             const float pbj = jt == 0 ? q0[u] : (jt == 1 ? q1[u] : q2[u]);
-            float hi, lo;
-            tc::split_tf32(a1j, hi, lo);
-            sm.A1T[cbase * kA1TChunk + (32 * uh + u) * 4 + csub] = hi;
-            sm.A1T[cbase * kA1TChunk + (kH + 32 * uh + u) * 4 + csub] = lo;
-            tc::split_tf32(pbj, hi, lo);
-            sm.P2Th[cbase * kP2TChunk + (32 * uh + u) * 4 + csub] = hi;
-            sm.P2Tl[cbase * kP2TChunk + (32 * uh + u) * 4 + csub] = lo;
-            if (jt == 0) { q0[u] = hi; v32s[u] = lo; } else if (jt == 1) { q1[u] = hi; v32s[u] = lo; } else { q2[u] = hi; v32s[u] = lo; }
+            // operands go in unrounded: the tensor core truncates them to tf32, the remainders are the "lo" parts
+            const float la = tc::lo_tf32(a1j), lp = tc::lo_tf32(pbj);
+            sm.A1T[cbase * kA1TChunk + (32 * uh + u) * 4 + csub] = a1j;
+            sm.A1T[cbase * kA1TChunk + (kH + 32 * uh + u) * 4 + csub] = la;
+            sm.P2Th[cbase * kP2TChunk + (32 * uh + u) * 4 + csub] = pbj;
+            sm.P2Tl[cbase * kP2TChunk + (32 * uh + u) * 4 + csub] = lp;
+            v32s[u] = lp;
           }
 #pragma unroll
           for (int c0 = 0; c0 < 32; c0 += 16) {
@@ -836,19 +868,30 @@ int launch_gnn_fwd_tc(void* stream, GnnFwdArgs& a, void* scratch, size_t scratch
   a.counter = (int*)scratch;
   cudaError_t e = cudaMemsetAsync(scratch, 0, kCounterBytes, st);
   if (e != cudaSuccess) return (int)e;
-  // OFDFT_B200_TC_NU = 2 (default: 256 threads, 32 hidden units per thread; measured 6.2 ms) | 4 (512 threads, 16 units
-  // per thread; 6.7 ms -- the kernel is bound by its serialised phases, not by occupancy)
-  const char* env = getenv("OFDFT_B200_TC_NU");
-  const bool nu2 = !(env != nullptr && env[0] == '4');
-  e = nu2 ? cudaFuncSetAttribute(gnn_fwd_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemTc) + 1024)
-          : cudaFuncSetAttribute(gnn_fwd_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemTc) + 1024);
-  if (e != cudaSuccess) return (int)e;
+  // OFDFT_B200_TC_FWD = "2cta" (default: 256 threads, one 64 KB operand buffer, two co-resident CTAs per SM whose
+  // stage / MMA / epilogue phases interleave) | "1cta" (two operand buffers, one CTA per SM) | "nu4" (512 threads,
+  // 16 hidden units per thread, one CTA per SM)
+  const char* env = getenv("OFDFT_B200_TC_FWD");
+  const int mode = env == nullptr ? 0 : (env[0] == '1' ? 1 : (env[0] == 'n' ? 2 : 0));
   const long long tiles = (a.n_a + kTP - 1) / kTP + (a.B - a.n_a + kTP - 1) / kTP;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int grid = (int)(tiles < sms ? tiles : sms);
-  if (nu2) gnn_fwd_tc_kernel<2><<<grid, kTP * 2, sizeof(SmemTc) + 1024, st>>>(a);
-  else gnn_fwd_tc_kernel<4><<<grid, kTP * 4, sizeof(SmemTc) + 1024, st>>>(a);
+  if (mode == 0) {
+    e = cudaFuncSetAttribute(gnn_fwd_tc_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemTc1) + 1024);
+    if (e != cudaSuccess) return (int)e;
+    const int grid = (int)(tiles < 2 * sms ? tiles : 2 * sms);
+    gnn_fwd_tc_kernel<2, 1><<<grid, kTP * 2, sizeof(SmemTc1) + 1024, st>>>(a);
+  } else if (mode == 1) {
+    e = cudaFuncSetAttribute(gnn_fwd_tc_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemTc) + 1024);
+    if (e != cudaSuccess) return (int)e;
+    const int grid = (int)(tiles < sms ? tiles : sms);
+    gnn_fwd_tc_kernel<2, 2><<<grid, kTP * 2, sizeof(SmemTc) + 1024, st>>>(a);
+  } else {
+    e = cudaFuncSetAttribute(gnn_fwd_tc_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemTc) + 1024);
+    if (e != cudaSuccess) return (int)e;
+    const int grid = (int)(tiles < sms ? tiles : sms);
+    gnn_fwd_tc_kernel<4, 2><<<grid, kTP * 4, sizeof(SmemTc) + 1024, st>>>(a);
+  }
   return (int)cudaGetLastError();
 }
 

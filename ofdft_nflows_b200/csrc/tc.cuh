@@ -115,5 +115,9 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   lo = x - hi;
 }
 
+// The tensor core narrows fp32 operands to tf32 by TRUNCATION (measured: tests/tc_trunc_probe.py), so an unrounded
+// value can serve as its own "hi" part; this returns the matching remainder x - trunc_tf32(x) (exact in fp32).
+__device__ __forceinline__ float lo_tf32(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
 }  // namespace tc
 }  // namespace ofdft

@@ -20,6 +20,7 @@ __global__ void __launch_bounds__(128, 1) tc_gemm_test_kernel(const float* __res
     if (tid < M) {
       const float4 v = *reinterpret_cast<const float4*>(A + tid * 64 + 4 * kc);
       tc::split_tf32(v.x, h.x, l.x); tc::split_tf32(v.y, h.y, l.y); tc::split_tf32(v.z, h.z, l.z); tc::split_tf32(v.w, h.w, l.w);
+      if (mode == 3) h = v;        // raw fp32 bits: does the tensor core truncate or round its tf32 inputs?
     }
     *reinterpret_cast<float4*>(Ahi + (kc * 128 + tid) * 4) = h;
     *reinterpret_cast<float4*>(Alo + (kc * 128 + tid) * 4) = l;
@@ -34,6 +35,7 @@ __global__ void __launch_bounds__(128, 1) tc_gemm_test_kernel(const float* __res
       float4 wh, wl;
       tc::split_tf32(W[(4 * kc + 0) * 64 + tid], wh.x, wl.x); tc::split_tf32(W[(4 * kc + 1) * 64 + tid], wh.y, wl.y);
       tc::split_tf32(W[(4 * kc + 2) * 64 + tid], wh.z, wl.z); tc::split_tf32(W[(4 * kc + 3) * 64 + tid], wh.w, wl.w);
+      if (mode == 3) wh = make_float4(W[(4 * kc + 0) * 64 + tid], W[(4 * kc + 1) * 64 + tid], W[(4 * kc + 2) * 64 + tid], W[(4 * kc + 3) * 64 + tid]);
       *reinterpret_cast<float4*>(Whi + (kc * 64 + tid) * 4) = wh;
       *reinterpret_cast<float4*>(Wlo + (kc * 64 + tid) * 4) = wl;
     }
@@ -119,7 +121,7 @@ __global__ void __launch_bounds__(128, 1) tc_gemm_test_kernel(const float* __res
     }
     tc::commit(mbar);
   }
-  if (tid == 0 && !mn_major && mode == 0) {
+  if (tid == 0 && !mn_major && (mode == 0 || mode == 3)) {
     const uint32_t idesc = tc::make_idesc_tf32(M, 64, 0, 0);
     bool acc = false;
     for (int p = 0; p < passes; ++p) {
@@ -153,11 +155,12 @@ extern "C" int ofdft_tc_gemm_test(void* stream, const float* A, const float* W, 
   using namespace ofdft;
   // passes == 0: MN-major probe (unsupported layout for tf32, kept as a negative test);
   // passes == -1: A operand from tensor memory (tcgen05.st + TS-mode MMA);
+  // passes == -3: one pass on raw (unrounded) fp32 bits -- shows how the tensor core narrows its inputs;
   // passes == -2: K = trajectory operands in the padded K-major layout, stacked [hi;lo] rows (weight-gradient GEMM)
-  if (!A || !W || !D || (M != 64 && M != 128) || passes < -2 || passes > 3) return OFDFT_EINVAL;
+  if (!A || !W || !D || (M != 64 && M != 128) || passes < -3 || passes > 3) return OFDFT_EINVAL;
   const size_t smem = sizeof(float) * (32 * (128 * 4 + 4) + 2 * 32 * (64 * 4 + 4) + 256) + 64 + 4096;
   cudaError_t e = cudaFuncSetAttribute(tc_gemm_test_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  tc_gemm_test_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(A, W, D, M, passes < 0 ? 0 : passes, passes == 0 ? 1 : 0, passes < 0 ? -passes : 0);
+  tc_gemm_test_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(A, W, D, M, passes == -3 ? 1 : (passes < 0 ? 0 : passes), passes == 0 ? 1 : 0, passes < 0 ? -passes : 0);
   return (int)cudaGetLastError();
 }
