@@ -151,15 +151,16 @@ __device__ __forceinline__ void epilogue_fwd(const float (&acc)[NJ][2][16], cons
                                              int half, int ug, int lane, float* __restrict__ act, long long act_rows) {
   float fp[3][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
   const long long jet_stride = (long long)kH * act_rows;
-  if (act != nullptr) act += (long long)(ug * 16) * act_rows + (half * 64 + 2 * lane);
+  // act points at (unit group 0, this tile's first row) of jet 0; this thread owns groups 4 ug .. 4 ug + 3 of two rows
+  if (act != nullptr) act += act_group_off(ug * 4, half * 64 + 2 * lane, act_rows);
+  float a0[2][4];
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
     const float b = b2[ug * 16 + j], w = w3[ug * 16 + j];
-    float av[2];
 #pragma unroll
     for (int tr = 0; tr < 2; ++tr) {
       const float a = tanh_f(acc[0][tr][j] + b);
-      av[tr] = a;
+      a0[tr][j & 3] = a;
       fp[0][tr] = fmaf(w, a, fp[0][tr]);
       if (NJ >= 2) {
         const float sg = fmaf(-a, a, 1.0f);
@@ -172,11 +173,15 @@ __device__ __forceinline__ void epilogue_fwd(const float (&acc)[NJ][2][16], cons
         }
       }
     }
-    if (act != nullptr) {
-      __stcs(reinterpret_cast<float2*>(act), make_float2(av[0], av[1]));
-      if (NJ >= 2) __stcs(reinterpret_cast<float2*>(act + jet_stride), make_float2(acc[1][0][j], acc[1][1][j]));
-      if (NJ == 3) __stcs(reinterpret_cast<float2*>(act + 2 * jet_stride), make_float2(acc[2][0][j], acc[2][1][j]));
-      act += act_rows;
+    if (act != nullptr && (j & 3) == 3) {
+#pragma unroll
+      for (int tr = 0; tr < 2; ++tr) {
+        float* dst = act + tr * 4;
+        __stcs(reinterpret_cast<float4*>(dst), make_float4(a0[tr][0], a0[tr][1], a0[tr][2], a0[tr][3]));
+        if (NJ >= 2) __stcs(reinterpret_cast<float4*>(dst + jet_stride), make_float4(acc[1][tr][j - 3], acc[1][tr][j - 2], acc[1][tr][j - 1], acc[1][tr][j]));
+        if (NJ == 3) __stcs(reinterpret_cast<float4*>(dst + 2 * jet_stride), make_float4(acc[2][tr][j - 3], acc[2][tr][j - 2], acc[2][tr][j - 1], acc[2][tr][j]));
+      }
+      act += act_rows * 4;
     }
   }
   const int tp0 = half * 64 + 2 * lane;
@@ -291,7 +296,7 @@ __device__ void fwd_tile(SmemFwd& sm, const GnnFwdArgs& a, long long row0, long 
         gemm64<NJ, true>(acc, sm.A, sm.W2, nullptr, half, ug, lane);
         float* actp = nullptr;
         if (a.act != nullptr)
-          actp = a.act + AL.seg_base((long long)(step * 4 + stage) * a.Na + i, seg_b) + (row0 - seg_row0);
+          actp = a.act + AL.seg_base((long long)(step * 4 + stage) * a.Na + i, seg_b) + (row0 - seg_row0) * 4;
         epilogue_fwd<NJ>(acc, sm.b2, sm.w3, sm.Fpart, half, ug, lane, actp, act_rows);
         __syncthreads();
       }
@@ -623,15 +628,17 @@ __device__ void bwd_tile(SmemBwd& sm, const GnnBwdArgs& a, long long row0, long 
       for (int i = 0; i < a.Na; ++i) {
         if (ACT) {
           // issue the checkpoint loads first: their latency hides behind the first-layer phase
-          const float* src = a.act + AL.seg_base((long long)(step * 4 + stage) * a.Na + i, seg_b) + (row0 - seg_row0)
-                             + (long long)(ug * 16) * act_rows + (half * 64 + 2 * lane);
+          const float* src = a.act + AL.seg_base((long long)(step * 4 + stage) * a.Na + i, seg_b)
+                             + act_group_off(ug * 4, (row0 - seg_row0) + half * 64 + 2 * lane, act_rows);
 #pragma unroll
           for (int jt = 0; jt < NJ; ++jt)
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float2 v = __ldcs(reinterpret_cast<const float2*>(src + ((long long)jt * kH + j) * act_rows));
-              acc[jt][0][j] = v.x; acc[jt][1][j] = v.y;
-            }
+            for (int g = 0; g < 4; ++g)
+#pragma unroll
+              for (int tr = 0; tr < 2; ++tr) {
+                const float4 v = __ldcs(reinterpret_cast<const float4*>(src + (long long)jt * kH * act_rows + (long long)g * act_rows * 4 + tr * 4));
+                acc[jt][tr][4 * g] = v.x; acc[jt][tr][4 * g + 1] = v.y; acc[jt][tr][4 * g + 2] = v.z; acc[jt][tr][4 * g + 3] = v.w;
+              }
         }
         first_layer<NJ, false>(sm.A, sm.xs, sm.wr, sm.wt, sm.cb + i * kH, sm.nuc + i * 4, tprime, half, ug, lane, rr);
         __syncthreads();

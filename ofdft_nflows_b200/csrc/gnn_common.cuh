@@ -22,7 +22,8 @@ struct GnnBwdArgs {
 
 // Layer-2 activation checkpoint (optional; trades 180 GB of HBM for the recompute GEMM of the backward pass):
 // for every RHS evaluation e = (step*4+stage)*Na + nucleus and both row segments, the jets (a2, p2', p2'') as
-// [jet][unit][row] with the row index contiguous (coalesced 8-byte stores per lane).
+// [jet][group of 4 units][row][4 units]: a thread holding consecutive units of one trajectory moves them as float4, and
+// a warp (32 consecutive rows) touches 512 contiguous bytes per instruction.
 struct ActLayout {
   long long rows_a, rows_b, block; int ja, jb;
   __host__ __device__ ActLayout(long long ra, long long rb, int ja_, int jb_) : rows_a(ra), rows_b(rb), ja(ja_), jb(jb_) {
@@ -32,6 +33,9 @@ struct ActLayout {
     return e * block + (seg_b ? (long long)kH * ja * rows_a : 0);
   }
 };
+
+// offset of (unit group g = unit/4, row) inside one jet block of `rows` trajectories
+__host__ __device__ __forceinline__ long long act_group_off(int g, long long row, long long rows) { return ((long long)g * rows + row) * 4; }
 
 __device__ __forceinline__ bool next_tile(int* counter, int* slot, long long n_tiles, long long& tile) {
   __syncthreads();

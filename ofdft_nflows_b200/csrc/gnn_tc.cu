@@ -241,8 +241,8 @@ __device__ void fwd_tile_tc(SmemTcT<NB>& sm, const GnnFwdArgs& a, long long row0
         float fp[3] = {0.f, 0.f, 0.f};
         float* actp = nullptr;
         if (a.act != nullptr)
-          actp = a.act + AL.seg_base((long long)(step * 4 + stage) * a.Na + i, seg_b) + (row0 - seg_row0)
-                 + (long long)(UPT * uh) * act_rows + m;
+          actp = a.act + AL.seg_base((long long)(step * 4 + stage) * a.Na + i, seg_b)
+                 + act_group_off((UPT * uh) >> 2, (row0 - seg_row0) + m, act_rows);
         const long long jet_stride = (long long)kH * act_rows;
 #pragma unroll
         for (int c0 = 0; c0 < UPT; c0 += 16) {
@@ -256,6 +256,7 @@ __device__ void fwd_tile_tc(SmemTcT<NB>& sm, const GnnFwdArgs& a, long long row0
             const int j = UPT * uh + c0 + u;
             const float wv = sm.w3[j];
             const float aa = tanh_f(p0[u] + sm.b2[j]);
+            p0[u] = aa;
             fp[0] = fmaf(wv, aa, fp[0]);
             if (NJ >= 2) {
               const float sg = fmaf(-aa, aa, 1.0f);
@@ -263,11 +264,15 @@ __device__ void fwd_tile_tc(SmemTcT<NB>& sm, const GnnFwdArgs& a, long long row0
               fp[1] = fmaf(wv, a1, fp[1]);
               if (NJ == 3) fp[2] = fmaf(wv, fmaf(sg, p2[u], -2.0f * aa * a1 * p1[u]), fp[2]);
             }
-            if (actp != nullptr) {
-              float* dst = actp + (long long)(c0 + u) * act_rows;
-              __stcs(dst, aa);
-              if (NJ >= 2) __stcs(dst + jet_stride, p1[u]);
-              if (NJ == 3) __stcs(dst + 2 * jet_stride, p2[u]);
+          }
+          if (actp != nullptr) {
+            // layer-2 jets (a2, p2', p2'') -> HBM, four units per 16-byte store
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              float* dst = actp + ((long long)((c0 >> 2) + g) * act_rows) * 4;
+              __stcs(reinterpret_cast<float4*>(dst), make_float4(p0[4 * g], p0[4 * g + 1], p0[4 * g + 2], p0[4 * g + 3]));
+              if (NJ >= 2) __stcs(reinterpret_cast<float4*>(dst + jet_stride), make_float4(p1[4 * g], p1[4 * g + 1], p1[4 * g + 2], p1[4 * g + 3]));
+              if (NJ == 3) __stcs(reinterpret_cast<float4*>(dst + 2 * jet_stride), make_float4(p2[4 * g], p2[4 * g + 1], p2[4 * g + 2], p2[4 * g + 3]));
             }
           }
         }
@@ -372,7 +377,7 @@ __global__ void __launch_bounds__(kTP * NU, NB == 1 ? 2 : 1) gnn_fwd_tc_kernel(c
 // accumulators in shared memory (measured: dW2 error 2.8e-4 -> see DESIGN.md).
 constexpr int kA1TChunk = kTP * 4 + 4;      // floats per trajectory-chunk of the stacked A1^T operand (128 rows)
 constexpr int kP2TChunk = kH * 4 + 4;       // floats per trajectory-chunk of a Pbar2^T operand (64 rows)
-constexpr int kColB1 = 0, kColDw = 192, kColA = 256;
+constexpr int kColB1 = 0, kColDw = 192, kColA = 256;   // A: two 128-column (hi|lo) operand buffers, jet parity
 #ifndef OFDFT_TC_FLUSH_PER_EVAL
 #define OFDFT_TC_FLUSH_PER_EVAL 0
 #endif
@@ -396,7 +401,7 @@ struct SmemTcB {
   float Rpart[2 * kTP];
   float red[8 * 32 * 4];
   float DW[kTP * kH];                     // fp32 (round-to-nearest) accumulators of the stacked dW2 tile, [col j][row]
-  uint64_t bar;
+  uint64_t barB[3], barD[3];              // per jet: B1 batch done / dW2 batch done (each completes once per evaluation)
   unsigned int tmem_slot;
   int tile;
 };
@@ -409,7 +414,7 @@ struct TcBwdAccum {
 
 template <int NJ>
 __device__ void bwd_tile_tc(SmemTcB& sm, const GnnBwdArgs& a, long long row0, long long seg_end, float b3, TcBwdAccum& G,
-                            bool seg_b, long long seg_row0, uint32_t tmem, uint32_t& phase, bool& dw_started) {
+                            bool seg_b, long long seg_row0, uint32_t tmem, uint32_t& phase, bool& dw_pending) {
   const ActLayout AL(a.act_rows_a, a.act_rows_b, a.jets_a, a.jets_b);
   const long long act_rows = seg_b ? a.act_rows_b : a.act_rows_a;
   const long long jet_stride = (long long)kH * act_rows;
@@ -527,21 +532,28 @@ __device__ void bwd_tile_tc(SmemTcB& sm, const GnnBwdArgs& a, long long row0, lo
         // ---- layer-2 jets (a2, p2', p2'') of (trajectory m, units 32 uh ..) from the HBM checkpoint ----
         float q0[32], q1[32], q2[32];
         {
-          const float* src = a.act + AL.seg_base((long long)(step * 4 + stage) * a.Na + i, seg_b) + (row0 - seg_row0)
-                             + (long long)(32 * uh) * act_rows + m;
+          const float* src = a.act + AL.seg_base((long long)(step * 4 + stage) * a.Na + i, seg_b)
+                             + act_group_off(8 * uh, (row0 - seg_row0) + m, act_rows);
 #pragma unroll
-          for (int u = 0; u < 32; ++u) {
-            q0[u] = __ldcs(src + (long long)u * act_rows);
-            if (NJ >= 2) q1[u] = __ldcs(src + jet_stride + (long long)u * act_rows);
-            if (NJ == 3) q2[u] = __ldcs(src + 2 * jet_stride + (long long)u * act_rows);
+          for (int g = 0; g < 8; ++g) {
+            const float4 v0 = __ldcs(reinterpret_cast<const float4*>(src + (long long)g * act_rows * 4));
+            q0[4 * g] = v0.x; q0[4 * g + 1] = v0.y; q0[4 * g + 2] = v0.z; q0[4 * g + 3] = v0.w;
+            if (NJ >= 2) {
+              const float4 v1 = __ldcs(reinterpret_cast<const float4*>(src + jet_stride + (long long)g * act_rows * 4));
+              q1[4 * g] = v1.x; q1[4 * g + 1] = v1.y; q1[4 * g + 2] = v1.z; q1[4 * g + 3] = v1.w;
+            }
+            if (NJ == 3) {
+              const float4 v2 = __ldcs(reinterpret_cast<const float4*>(src + 2 * jet_stride + (long long)g * act_rows * 4));
+              q2[4 * g] = v2.x; q2[4 * g + 1] = v2.y; q2[4 * g + 2] = v2.z; q2[4 * g + 3] = v2.w;
+            }
           }
           // pull the next evaluation's jets (backward order: next nucleus, else the previous stage) into L2 behind these
-          // loads: one 128-B line per (unit, jet) of this warp's 32 trajectories, lane <-> unit
+          // loads: per jet this warp reads 8 unit groups x 512 B = 32 lines, lane <-> (group, line)
           const long long ss = (long long)(step * 4 + stage);
           const long long en = (i + 1 < a.Na) ? ss * a.Na + i + 1 : (ss - 1) * a.Na;
           if (kPrefetchL2 && en >= 0) {
-            const float* nx = a.act + AL.seg_base(en, seg_b) + (row0 - seg_row0) + (long long)(32 * uh + lane) * act_rows
-                              + 32 * (w & 3);
+            const float* nx = a.act + AL.seg_base(en, seg_b)
+                              + act_group_off(8 * uh + (lane >> 2), (row0 - seg_row0) + 32 * (w & 3) + 8 * (lane & 3), act_rows);
 #pragma unroll
             for (int jt = 0; jt < NJ; ++jt) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + jt * jet_stride));
           }
@@ -600,12 +612,46 @@ __device__ void bwd_tile_tc(SmemTcB& sm, const GnnBwdArgs& a, long long row0, lo
           G.g_b2 += warp_vec32_sum(v32, lane);
           G.g_w3 += warp_vec32_sum(g32, lane);
         }
-        // ---- per jet: stage operands, run B1 (TS mode) and the dW2 update ----
+        // ---- per jet: B1 (TS mode: Pbar2 hi|lo in tensor memory) and the dW2 update (operands in shared memory) ----
+        // Two decoupled batches per jet so that only the shared-memory operands serialise:
+        //   issue order  B1(0) | dW2(0) B1(1) | dW2(1) B1(2) | dW2(2);   waits: dW2(jt-1) before restaging shared memory,
+        //   B1(last) before the layer-1 reverse; dW2(last) overlaps the reverse and the next evaluation's first phase.
+        auto tmem_stage = [&](const float (&q)[32], int buf) {
+#pragma unroll
+          for (int c0 = 0; c0 < 32; c0 += 16) {
+            float hv[16], lv[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) { hv[u] = q[c0 + u]; lv[u] = tc::lo_tf32(q[c0 + u]); }
+            tc::tmem_st16(tlane + kColA + 128 * buf + 32 * uh + c0, hv);
+            tc::tmem_st16(tlane + kColA + 128 * buf + kH + 32 * uh + c0, lv);
+          }
+        };
+        auto issue_b1 = [&](int jt) {
+#pragma unroll
+          for (int p = 0; p < 3; ++p) {
+            const uint32_t acol = tmem + kColA + 128 * (jt & 1) + (p == 1 ? kH : 0);
+            const uint64_t wb = p == 2 ? dWTl : dWTh;
+#pragma unroll
+            for (int ksx = 0; ksx < 8; ++ksx)
+              tc::mma_tf32_ts(tmem + kColB1 + jt * kH, acol + 8 * ksx, wb + ksx * ((2 * kH * 16) >> 4), idesc, (p | ksx) != 0);
+          }
+          tc::commit(&sm.barB[jt]);
+        };
+        tmem_stage(q0, 0);
+        tc::tmem_st_wait();
+        tc::fence_before_sync();
+        __syncthreads();
+        if (w == 0) {
+          tc::fence_after_sync();
+          if (tc::elect_one()) issue_b1(0);
+          __syncwarp();
+        }
 #pragma unroll
         for (int jt = 0; jt < NJ; ++jt) {
-          if (jt > 0) { tc::mbar_wait(&sm.bar, phase); phase ^= 1; __syncwarp(); }
+          // the shared-memory operands are free once the previous dW2 batch has completed
+          if (jt > 0) { tc::mbar_wait(&sm.barD[jt - 1], (phase >> (3 + jt - 1)) & 1u); phase ^= 1u << (3 + jt - 1); __syncwarp(); }
+          else if (dw_pending) { tc::mbar_wait(&sm.barD[NJ - 1], (phase >> (3 + NJ - 1)) & 1u); phase ^= 1u << (3 + NJ - 1); __syncwarp(); }
           const int cbase = (m >> 2), csub = (m & 3);
-          float v32s[32];
 #pragma unroll
           for (int u = 0; u < 32; ++u) {
             const float wv = sm.wr[32 * uh + u];
@@ -613,40 +659,21 @@ __device__ void bwd_tile_tc(SmemTcB& sm, const GnnBwdArgs& a, long long row0, lo
             const float a1j = jt == 0 ? av[u] : (jt == 1 ? sg1 * wv : -2.0f * av[u] * sg1 * wv * wv);
             const float pbj = jt == 0 ? q0[u] : (jt == 1 ? q1[u] : q2[u]);
             // operands go in unrounded: the tensor core truncates them to tf32, the remainders are the "lo" parts
-            const float la = tc::lo_tf32(a1j), lp = tc::lo_tf32(pbj);
             sm.A1T[cbase * kA1TChunk + (32 * uh + u) * 4 + csub] = a1j;
-            sm.A1T[cbase * kA1TChunk + (kH + 32 * uh + u) * 4 + csub] = la;
+            sm.A1T[cbase * kA1TChunk + (kH + 32 * uh + u) * 4 + csub] = tc::lo_tf32(a1j);
             sm.P2Th[cbase * kP2TChunk + (32 * uh + u) * 4 + csub] = pbj;
-            sm.P2Tl[cbase * kP2TChunk + (32 * uh + u) * 4 + csub] = lp;
-            v32s[u] = lp;
+            sm.P2Tl[cbase * kP2TChunk + (32 * uh + u) * 4 + csub] = tc::lo_tf32(pbj);
           }
-#pragma unroll
-          for (int c0 = 0; c0 < 32; c0 += 16) {
-            float hv[16], lv[16];
-#pragma unroll
-            for (int u = 0; u < 16; ++u) {
-              hv[u] = jt == 0 ? q0[c0 + u] : (jt == 1 ? q1[c0 + u] : q2[c0 + u]);
-              lv[u] = v32s[c0 + u];
-            }
-            tc::tmem_st16(tlane + kColA + 32 * uh + c0, hv);
-            tc::tmem_st16(tlane + kColA + kH + 32 * uh + c0, lv);
+          if (jt + 1 < NJ) {
+            if (jt == 0) tmem_stage(q1, 1); else tmem_stage(q2, 0);
+            tc::tmem_st_wait();
           }
-          tc::tmem_st_wait();
           tc::fence_async_smem();
           tc::fence_before_sync();
           __syncthreads();
           if (w == 0) {
             tc::fence_after_sync();
             if (tc::elect_one()) {
-              // B1: D_b1[jt] = Pbar2 (TMEM) . W2^T, 3xTF32
-#pragma unroll
-              for (int p = 0; p < 3; ++p) {
-                const uint32_t acol = tmem + kColA + (p == 1 ? kH : 0);
-                const uint64_t wb = p == 2 ? dWTl : dWTh;
-#pragma unroll
-                for (int ksx = 0; ksx < 8; ++ksx)
-                  tc::mma_tf32_ts(tmem + kColB1 + jt * kH, acol + 8 * ksx, wb + ksx * ((2 * kH * 16) >> 4), idesc, (p | ksx) != 0);
-              }
               // dW2: D_dw += [A1_hi ; A1_lo]^T-stacked . (P_hi, then P_lo), K = 128 trajectories
 #pragma unroll
               for (int p = 0; p < 2; ++p) {
@@ -657,13 +684,16 @@ __device__ void bwd_tile_tc(SmemTcB& sm, const GnnBwdArgs& a, long long row0, lo
                                (kFlushPerEval ? 0 : i) != 0 || (jt | p | ksx) != 0);
                 }
               }
-              tc::commit(&sm.bar);
+              tc::commit(&sm.barD[jt]);
+              if (jt + 1 < NJ) issue_b1(jt + 1);
             }
             __syncwarp();
           }
-          dw_started = true;
         }
-        tc::mbar_wait(&sm.bar, phase); phase ^= 1;
+        dw_pending = true;
+        // B1 batches complete in order: wait for the last one, then retire the (already complete) earlier phases
+#pragma unroll
+        for (int jt = NJ - 1; jt >= 0; --jt) { tc::mbar_wait(&sm.barB[jt], (phase >> jt) & 1u); phase ^= 1u << jt; }
         __syncwarp();
         tc::fence_after_sync();
         // ---- layer-1 reverse from D_b1 (cotangent jets of a1 for trajectory m, units k = 32 uh ..) ----
@@ -700,7 +730,11 @@ __device__ void bwd_tile_tc(SmemTcB& sm, const GnnBwdArgs& a, long long row0, lo
           }
           sm.Rpart[uh * kTP + m] = rp;
           // fold the dW2 tile into the fp32 accumulators (row m, columns 32 uh ..)
-          if (kFlushPerEval || i == a.Na - 1)
+          if (kFlushPerEval || i == a.Na - 1) {
+            tc::mbar_wait(&sm.barD[NJ - 1], (phase >> (3 + NJ - 1)) & 1u); phase ^= 1u << (3 + NJ - 1);
+            dw_pending = false;
+            __syncwarp();
+            tc::fence_after_sync();
 #pragma unroll
           for (int c0 = 0; c0 < 32; c0 += 16) {
             float t[16];
@@ -708,6 +742,7 @@ __device__ void bwd_tile_tc(SmemTcB& sm, const GnnBwdArgs& a, long long row0, lo
             tc::tmem_ld_wait();
 #pragma unroll
             for (int u = 0; u < 16; ++u) sm.DW[(32 * uh + c0 + u) * kTP + m] += t[u];
+          }
           }
           const float ps = warp_vec32_sum(ps32, lane);
           const float pr = warp_vec32_sum(pr32, lane);
@@ -823,14 +858,17 @@ __global__ void __launch_bounds__(kThreads, 1) gnn_bwd_tc_kernel(const GnnBwdArg
   if (tid < a.Na * 3) sm.nuc[(tid / 3) * 4 + (tid % 3)] = a.nuclei[tid];
   for (int i = tid; i < 8 * kMaxNa * 32; i += kThreads) sm.S[i] = 0.f;
   for (int i = tid; i < kTP * kH; i += kThreads) sm.DW[i] = 0.f;
-  if (tid == 0) { tc::mbar_init(&sm.bar, 1); tc::fence_mbar_init(); }
+  if (tid == 0) {
+    for (int j = 0; j < 3; ++j) { tc::mbar_init(&sm.barB[j], 1); tc::mbar_init(&sm.barD[j], 1); }
+    tc::fence_mbar_init();
+  }
   if (tid < 32) tc::tmem_alloc(&sm.tmem_slot, 512);
   tc::fence_async_smem();
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem = sm.tmem_slot;
-  uint32_t phase = 0;
+  uint32_t phase = 0;            // bits 0..2: parity of barB[jet], bits 3..5: parity of barD[jet]
   const float b3 = a.theta[0];
   TcBwdAccum G;
   G.g_b2 = G.g_w3 = G.g_wt = G.g_wr = G.g_b3 = 0.f;
@@ -842,12 +880,12 @@ __global__ void __launch_bounds__(kThreads, 1) gnn_bwd_tc_kernel(const GnnBwdArg
     bool seg_b; long long seg_row0;
     if (tile < tiles_a) { row0 = tile * kTP; seg_end = a.n_a; nj = a.jets_a; seg_b = false; seg_row0 = 0; }
     else { row0 = a.n_a + (tile - tiles_a) * kTP; seg_end = a.B; nj = a.jets_b; seg_b = true; seg_row0 = a.n_a; }
-    bool dw_started = false;
-    if (nj == 3) bwd_tile_tc<3>(sm, a, row0, seg_end, b3, G, seg_b, seg_row0, tmem, phase, dw_started);
-    else if (nj == 2) bwd_tile_tc<2>(sm, a, row0, seg_end, b3, G, seg_b, seg_row0, tmem, phase, dw_started);
-    else bwd_tile_tc<1>(sm, a, row0, seg_end, b3, G, seg_b, seg_row0, tmem, phase, dw_started);
+    bool dw_pending = false;
+    if (nj == 3) bwd_tile_tc<3>(sm, a, row0, seg_end, b3, G, seg_b, seg_row0, tmem, phase, dw_pending);
+    else if (nj == 2) bwd_tile_tc<2>(sm, a, row0, seg_end, b3, G, seg_b, seg_row0, tmem, phase, dw_pending);
+    else bwd_tile_tc<1>(sm, a, row0, seg_end, b3, G, seg_b, seg_row0, tmem, phase, dw_pending);
     __syncthreads();
-    flush_tile_grad_tc(sm, G, a.gpart + (size_t)tile * L.n, L, a.onehot, a.Na, a.n_types, tmem, dw_started);
+    flush_tile_grad_tc(sm, G, a.gpart + (size_t)tile * L.n, L, a.onehot, a.Na, a.n_types, tmem, dw_pending);
   }
   tc::fence_before_sync();
   __syncthreads();
