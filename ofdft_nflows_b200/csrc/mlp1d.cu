@@ -13,36 +13,14 @@
 // dW_l = sum_rows A_{l-1}^T Pbar_l (rows = stage x trajectory x jet, ~2e5 for bs=512) are then ONE split-K GEMM per
 // layer over those buffers -- a per-CTA accumulation would need 1 MB of accumulators per layer, and per-stage
 // atomics would be ~50x slower than the FFMA work.
+#include <cstdlib>
+
 #include "common.cuh"
+#include "tc.cuh"
+#include "mlp1d_common.cuh"
 
 namespace ofdft {
 namespace mlp {
-
-constexpr int kTT = 8;        // trajectories per tile
-constexpr int kKC = 16;       // weight rows per streamed chunk
-constexpr int kMaxL = 4;
-
-struct ThetaLayout {
-  int H, L, n;
-  __host__ __device__ ThetaLayout(int H_, int L_) : H(H_), L(L_) { n = 1 + H + 3 * H + (L - 1) * (H + H * H); }
-  __host__ __device__ int b_last() const { return 0; }
-  __host__ __device__ int w_last() const { return 1; }
-  __host__ __device__ int b(int i) const { return i == 0 ? 1 + H : 1 + 4 * H + (i - 1) * (H + H * H); }
-  __host__ __device__ int w(int i) const { return b(i) + H; }     // layer 0: (2,H) rows [t, x]; else (H,H)
-  // compact layout of everything except the hidden kernels (per-CTA partial buffers of the backward sweep)
-  __host__ __device__ int n_small() const { return 1 + 4 * H + (L - 1) * H; }
-  __host__ __device__ int c_wlast() const { return 1; }
-  __host__ __device__ int c_b0() const { return 1 + H; }
-  __host__ __device__ int c_w0() const { return 1 + 2 * H; }
-  __host__ __device__ int c_b(int l) const { return 1 + 4 * H + (l - 1) * H; }
-  // compact index -> theta offset
-  __host__ __device__ int small_to_theta(int c) const {
-    if (c < 1 + H) return c;                              // b_last, w_last
-    if (c < 1 + 4 * H) return c;                          // b0, w0 share the same offsets (1+H .. 1+4H)
-    const int l = (c - (1 + 4 * H)) / H + 1, i = (c - (1 + 4 * H)) % H;
-    return b(l) + i;
-  }
-};
 
 struct Args {
   const float* theta;
@@ -530,6 +508,149 @@ __global__ void __launch_bounds__(256) mlp_dw_gemm_kernel(const float* __restric
     for (int j = 0; j < 4; ++j) out[(size_t)(k0 + tk + i) * H + j0 + tj + j] = acc[i][j];
 }
 
+// ------------------------------------------------------------------------------------------------
+// The same contraction on the tensor cores (tcgen05, error-compensated 3xTF32, accumulators in TMEM):
+//   D[(hi k | lo k) 128][j 64] += A^T-stacked (128 x 8 traj) . (P_hi, then P_lo) (8 traj x 64)      per (block, jet)
+// The HBM block layout [unit][8 traj] IS the K-major operand layout up to a regrouping of 16-byte chunks, so staging
+// is float4 loads -> (jets, lo parts) -> float4 stores; operands go in unrounded (the tensor core truncates to tf32,
+// the remainders are the "lo" parts).  Two 48 KB stages of two blocks each, one mbarrier per stage; the TMEM
+// accumulator is drained into fp32 registers every kDwFlush stages because tensor-core accumulation truncates.
+// Output: rows 0..63 (hi k) and 64..127 (lo k) go to two partial buffers, summed by mlp_dw_reduce_kernel.
+// ------------------------------------------------------------------------------------------------
+constexpr int kDwG = 2;           // HBM blocks per pipeline stage
+constexpr int kDwFlush = 8;       // stages per TMEM accumulation chain (8 x 2 x 6 = 96 MMAs)
+constexpr int kDwTcSplits = 4;    // 64 tiles x 4 = 256 CTAs, two per SM; 8 partial buffers
+struct DwStage {
+  float A[kDwG][3][2 * 128 * 4];  // [block][jet][chunk of 4 traj][row: hi k 0..63 | lo k 64..127][4]
+  float Ph[kDwG][3][2 * 64 * 4];  // [block][jet][chunk][row j][4]
+  float Pl[kDwG][3][2 * 64 * 4];
+};
+struct DwSmem {
+  DwStage st[2];
+  uint64_t bar[2];
+  unsigned int tmem_slot;
+};
+
+__global__ void __launch_bounds__(256, 2) mlp_dw_gemm_tc_kernel(const float* __restrict__ acts, const float* __restrict__ pbar,
+                                                               float* __restrict__ part, int H, int L, int layer,
+                                                               long long n_blocks, int splits) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  DwSmem& sm = *reinterpret_cast<DwSmem*>(smem_raw);
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  const int k0 = blockIdx.x * 64, j0 = blockIdx.y * 64, sp = blockIdx.z;
+  if (tid == 0) { tc::mbar_init(&sm.bar[0], 1); tc::mbar_init(&sm.bar[1], 1); tc::fence_mbar_init(); }
+  if (w == 0) tc::tmem_alloc(&sm.tmem_slot, 64);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = sm.tmem_slot;
+  const uint32_t idesc = tc::make_idesc_tf32(128, 64, 0, 0);
+  const long long per = (n_blocks + splits - 1) / splits;
+  const long long b_begin = sp * per, b_end = b_begin + per < n_blocks ? b_begin + per : n_blocks;
+  const long long n_it = b_end > b_begin ? (b_end - b_begin + kDwG - 1) / kDwG : 0;
+  float acc[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+  uint32_t phase = 0, pending = 0;      // bit s: parity / outstanding commit of stage s
+  int in_group = 0;
+  // staging role: threads 0..127 build the A operand (unit u, trajectory chunk c), 128..255 the P operand
+  const int role_p = tid >> 7, c = (tid >> 6) & 1, u = tid & 63;
+  for (long long it = 0; it < n_it; ++it) {
+    const int s = (int)(it & 1);
+    if (pending & (1u << s)) { tc::mbar_wait(&sm.bar[s], (phase >> s) & 1u); phase ^= 1u << s; pending &= ~(1u << s); }
+    DwStage& S = sm.st[s];
+#pragma unroll
+    for (int g = 0; g < kDwG; ++g) {
+      const long long blk = b_begin + it * kDwG + g;
+      if (blk < b_end) {
+        if (!role_p) {
+          const float* src = acts + act_blk(blk, layer - 1, H, L) + (size_t)(k0 + u) * kTT + 4 * c;
+          const float4 av = *reinterpret_cast<const float4*>(src);
+          const float4 p1 = *reinterpret_cast<const float4*>(src + (size_t)H * kTT);
+          const float4 p2 = *reinterpret_cast<const float4*>(src + (size_t)2 * H * kTT);
+          const float a0[4] = {av.x, av.y, av.z, av.w}, q1[4] = {p1.x, p1.y, p1.z, p1.w}, q2[4] = {p2.x, p2.y, p2.z, p2.w};
+          float j1[4], j2[4], l0[4], l1[4], l2[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float sg = fmaf(-a0[e], a0[e], 1.0f);
+            j1[e] = sg * q1[e];
+            j2[e] = fmaf(sg, q2[e], -2.0f * a0[e] * j1[e] * q1[e]);
+            l0[e] = tc::lo_tf32(a0[e]); l1[e] = tc::lo_tf32(j1[e]); l2[e] = tc::lo_tf32(j2[e]);
+          }
+          float* d0 = &S.A[g][0][(c * 128 + u) * 4];
+          *reinterpret_cast<float4*>(d0) = av;
+          *reinterpret_cast<float4*>(d0 + 64 * 4) = make_float4(l0[0], l0[1], l0[2], l0[3]);
+          float* d1 = &S.A[g][1][(c * 128 + u) * 4];
+          *reinterpret_cast<float4*>(d1) = make_float4(j1[0], j1[1], j1[2], j1[3]);
+          *reinterpret_cast<float4*>(d1 + 64 * 4) = make_float4(l1[0], l1[1], l1[2], l1[3]);
+          float* d2 = &S.A[g][2][(c * 128 + u) * 4];
+          *reinterpret_cast<float4*>(d2) = make_float4(j2[0], j2[1], j2[2], j2[3]);
+          *reinterpret_cast<float4*>(d2 + 64 * 4) = make_float4(l2[0], l2[1], l2[2], l2[3]);
+        } else {
+          const float* src = pbar + pb_blk(blk, layer, H, L) + (size_t)(j0 + u) * kTT + 4 * c;
+#pragma unroll
+          for (int jt = 0; jt < 3; ++jt) {
+            const float4 v = *reinterpret_cast<const float4*>(src + (size_t)jt * H * kTT);
+            *reinterpret_cast<float4*>(&S.Ph[g][jt][(c * 64 + u) * 4]) = v;
+            *reinterpret_cast<float4*>(&S.Pl[g][jt][(c * 64 + u) * 4]) =
+                make_float4(tc::lo_tf32(v.x), tc::lo_tf32(v.y), tc::lo_tf32(v.z), tc::lo_tf32(v.w));
+          }
+        }
+      }
+    }
+    tc::fence_async_smem();
+    __syncthreads();
+    if (w == 0) {
+      tc::fence_after_sync();
+      if (tc::elect_one()) {
+#pragma unroll
+        for (int g = 0; g < kDwG; ++g) {
+          if (b_begin + it * kDwG + g < b_end) {
+#pragma unroll
+            for (int jt = 0; jt < 3; ++jt) {
+              const uint64_t ad = tc::make_desc(tc::smem_u32(S.A[g][jt]), 128 * 16, 128);
+              tc::mma_tf32(tmem, ad, tc::make_desc(tc::smem_u32(S.Ph[g][jt]), 64 * 16, 128), idesc, (in_group | g | jt) != 0);
+              tc::mma_tf32(tmem, ad, tc::make_desc(tc::smem_u32(S.Pl[g][jt]), 64 * 16, 128), idesc, true);
+            }
+          }
+        }
+        tc::commit(&sm.bar[s]);
+      }
+      __syncwarp();
+    }
+    pending |= 1u << s;
+    ++in_group;
+    if (in_group == kDwFlush || it == n_it - 1) {
+      // drain the chain into the fp32 accumulators: lane quadrant w&3 <-> rows, warp half w>>2 <-> 32 columns
+#pragma unroll
+      for (int s2 = 0; s2 < 2; ++s2)
+        if (pending & (1u << s2)) { tc::mbar_wait(&sm.bar[s2], (phase >> s2) & 1u); phase ^= 1u << s2; pending &= ~(1u << s2); }
+      __syncwarp();
+      tc::fence_after_sync();
+#pragma unroll
+      for (int c0 = 0; c0 < 32; c0 += 16) {
+        float t[16];
+        tc::tmem_ld16(tmem + ((uint32_t)(32 * (w & 3)) << 16) + 32 * (w >> 2) + c0, t);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[c0 + i] += t[i];
+      }
+      tc::fence_before_sync();
+      __syncthreads();
+      in_group = 0;
+    }
+  }
+  {
+    const int r = 32 * (w & 3) + lane;                       // accumulator row: hi k (r < 64) or lo k
+    float* out = part + ((size_t)(2 * sp + (r >> 6)) * H + (k0 + (r & 63))) * H + j0 + 32 * (w >> 2);
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(out + i) = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (w == 0) tc::tmem_dealloc(tmem, 64);
+}
+
 // theta_bar[w(l) + i] (+)= sum_splits part[s][i]
 __global__ void mlp_dw_reduce_kernel(const float* __restrict__ part, float* __restrict__ theta_bar, int off, int n, int splits,
                                      int accumulate) {
@@ -552,27 +673,6 @@ __global__ void mlp_small_reduce_kernel(const float* __restrict__ gsmall, float*
   for (int b = 0; b < nblk; ++b) s += (double)gsmall[(size_t)b * ns + c];
   theta_bar[p] = (float)s;
 }
-
-constexpr long long kChunkRows = 2048;     // backward row chunk (bounds the HBM activation scratch)
-constexpr int kDwSplits = 16;
-static size_t al256(size_t v) { return (v + 255) & ~(size_t)255; }
-
-struct ScratchLayout {
-  size_t wc, wtc, gsmall, part, acts, pbar, total;
-  ScratchLayout(long long B, int H, int L, int n_steps) {
-    const long long rows = B < kChunkRows ? B : kChunkRows;
-    const long long n_tiles = (rows + kTT - 1) / kTT;
-    const long long n_blocks = (long long)n_steps * 4 * n_tiles;
-    size_t o = 0;
-    wc = o; o += al256((size_t)(L - 1) * H * H * 4);
-    wtc = o; o += al256((size_t)(L - 1) * H * H * 4);
-    gsmall = o; o += al256((size_t)256 * ThetaLayout(H, L).n_small() * 4);
-    part = o; o += al256((size_t)kDwSplits * H * H * 4);
-    acts = o; o += al256((size_t)n_blocks * L * 3 * H * kTT * 4);
-    pbar = o; o += al256((size_t)n_blocks * (L - 1) * 3 * H * kTT * 4);
-    total = o;
-  }
-};
 
 static int check_shape(int64_t B, int jets, int stride, int H, int L, int n_steps) {
   if (B <= 0 || n_steps <= 0 || jets < 1 || jets > 3) return OFDFT_EINVAL;
@@ -602,12 +702,24 @@ extern "C" int ofdft_cnf_mlp1d_fwd(void* stream, const float* theta, const float
   if (rc) return rc;
   if (!theta || !y_in || !y_out || !scratch) return OFDFT_EINVAL;
   const ScratchLayout SL(B, H, n_layers, n_steps);
-  if (scratch_bytes < SL.wtc) return OFDFT_ESCRATCH;          // forward only needs the aligned weight copies
+  // OFDFT_B200_MLP_FWD = "tc" (default: per-layer tcgen05 3xTF32 GEMM launches, mlp1d_tc.cu) | "ffma" (fused FP32 kernel)
+  const char* envf = getenv("OFDFT_B200_MLP_FWD");
+  const bool fwd_tc = !(envf != nullptr && envf[0] == 'f');
+  if (scratch_bytes < (fwd_tc ? SL.fwd_end : SL.wtc)) return OFDFT_ESCRATCH;
   cudaStream_t st = (cudaStream_t)stream;
   float* Wc = (float*)((char*)scratch + SL.wc);
-  mlp_prep_kernel<<<256, 256, 0, st>>>(theta, Wc, nullptr, H, n_layers);
+  float* WTc = (float*)((char*)scratch + SL.wtc);
+  mlp_prep_kernel<<<256, 256, 0, st>>>(theta, Wc, fwd_tc ? WTc : nullptr, H, n_layers);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
+  if (fwd_tc) {
+    const size_t sbuf = al256(3 * (size_t)((B + 127) / 128 * 128) * H * 4);
+    float* S0 = (float*)((char*)scratch + SL.fwd_s);
+    float* S1 = (float*)((char*)scratch + SL.fwd_s + sbuf);
+    float* state = (float*)((char*)scratch + SL.fwd_state);
+    return launch_mlp_fwd_tc(stream, theta, WTc, y_in, y_out, ckpt, S0, S1, state, B, jets, stride, H, n_layers, n_steps, t0, t1,
+                             y0sign);
+  }
   const size_t smem = smem_bytes(H);
   e = cudaFuncSetAttribute(mlp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
@@ -662,10 +774,23 @@ extern "C" int ofdft_cnf_mlp1d_bwd(void* stream, const float* theta, const float
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
     mlp_small_reduce_kernel<<<(TL.n_small() + 255) / 256, 256, 0, st>>>(gsmall, theta_bar, H, L, grid, chunk_idx > 0);
+    // OFDFT_B200_MLP_DW = "tc" (default: tcgen05 3xTF32 weight-gradient GEMM) | "ffma"
+    const char* envd = getenv("OFDFT_B200_MLP_DW");
+    const bool dw_tc = !(envd != nullptr && envd[0] == 'f');
+    if (dw_tc) {
+      e = cudaFuncSetAttribute(mlp_dw_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DwSmem) + 1024);
+      if (e != cudaSuccess) return (int)e;
+    }
     for (int l = 1; l < L; ++l) {
-      dim3 gg(H / kDwTile, H / kDwTile, kDwSplits);
-      mlp_dw_gemm_kernel<<<gg, 256, 0, st>>>(a.acts, a.pbar, part, H, L, l, n_blocks, kDwSplits);
-      mlp_dw_reduce_kernel<<<(H * H + 255) / 256, 256, 0, st>>>(part, theta_bar, TL.w(l), H * H, kDwSplits, chunk_idx > 0);
+      if (dw_tc) {
+        dim3 gg(H / 64, H / 64, kDwTcSplits);
+        mlp_dw_gemm_tc_kernel<<<gg, 256, sizeof(DwSmem) + 1024, st>>>(a.acts, a.pbar, part, H, L, l, n_blocks, kDwTcSplits);
+        mlp_dw_reduce_kernel<<<(H * H + 255) / 256, 256, 0, st>>>(part, theta_bar, TL.w(l), H * H, 2 * kDwTcSplits, chunk_idx > 0);
+      } else {
+        dim3 gg(H / kDwTile, H / kDwTile, kDwSplits);
+        mlp_dw_gemm_kernel<<<gg, 256, 0, st>>>(a.acts, a.pbar, part, H, L, l, n_blocks, kDwSplits);
+        mlp_dw_reduce_kernel<<<(H * H + 255) / 256, 256, 0, st>>>(part, theta_bar, TL.w(l), H * H, kDwSplits, chunk_idx > 0);
+      }
     }
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;

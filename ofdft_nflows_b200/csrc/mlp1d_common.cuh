@@ -1,0 +1,70 @@
+// mlp1d_common.cuh -- shared declarations of the 1-D tanh-MLP flow kernels (mlp1d.cu, mlp1d_tc.cu)
+#pragma once
+#include <cstddef>
+#include <cstdint>
+
+#include "../../include/ofdft_b200.h"
+
+namespace ofdft {
+namespace mlp {
+
+constexpr int kTT = 8;        // trajectories per tile
+constexpr int kKC = 16;       // weight rows per streamed chunk
+constexpr int kMaxL = 4;
+
+struct ThetaLayout {
+  int H, L, n;
+  __host__ __device__ ThetaLayout(int H_, int L_) : H(H_), L(L_) { n = 1 + H + 3 * H + (L - 1) * (H + H * H); }
+  __host__ __device__ int b_last() const { return 0; }
+  __host__ __device__ int w_last() const { return 1; }
+  __host__ __device__ int b(int i) const { return i == 0 ? 1 + H : 1 + 4 * H + (i - 1) * (H + H * H); }
+  __host__ __device__ int w(int i) const { return b(i) + H; }     // layer 0: (2,H) rows [t, x]; else (H,H)
+  // compact layout of everything except the hidden kernels (per-CTA partial buffers of the backward sweep)
+  __host__ __device__ int n_small() const { return 1 + 4 * H + (L - 1) * H; }
+  __host__ __device__ int c_wlast() const { return 1; }
+  __host__ __device__ int c_b0() const { return 1 + H; }
+  __host__ __device__ int c_w0() const { return 1 + 2 * H; }
+  __host__ __device__ int c_b(int l) const { return 1 + 4 * H + (l - 1) * H; }
+  // compact index -> theta offset
+  __host__ __device__ int small_to_theta(int c) const {
+    if (c < 1 + H) return c;                              // b_last, w_last
+    if (c < 1 + 4 * H) return c;                          // b0, w0 share the same offsets (1+H .. 1+4H)
+    const int l = (c - (1 + 4 * H)) / H + 1, i = (c - (1 + 4 * H)) % H;
+    return b(l) + i;
+  }
+};
+
+constexpr long long kChunkRows = 2048;     // backward row chunk (bounds the HBM activation scratch)
+constexpr int kDwSplits = 16;
+inline size_t al256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+struct ScratchLayout {
+  size_t wc, wtc, fwd_s, fwd_state, fwd_end, gsmall, part, acts, pbar, total;
+  ScratchLayout(long long B, int H, int L, int n_steps) {
+    const long long rows = B < kChunkRows ? B : kChunkRows;
+    const long long n_tiles = (rows + kTT - 1) / kTT;
+    const long long n_blocks = (long long)n_steps * 4 * n_tiles;
+    size_t o = 0;
+    wc = o; o += al256((size_t)(L - 1) * H * H * 4);
+    wtc = o; o += al256((size_t)(L - 1) * H * H * 4);
+    // tensor-core forward: two ping-pong layer buffers [jet: a, p', p''][B rows padded to 128][H] and the RK4 row state
+    const size_t rows_pad = (size_t)((B + 127) / 128 * 128);
+    fwd_s = o; o += 2 * al256(3 * rows_pad * H * 4);
+    fwd_state = o; o += al256(rows_pad * 8 * 4);
+    fwd_end = o;
+    gsmall = o; o += al256((size_t)256 * ThetaLayout(H, L).n_small() * 4);
+    part = o; o += al256((size_t)kDwSplits * H * H * 4);
+    acts = o; o += al256((size_t)n_blocks * L * 3 * H * kTT * 4);
+    pbar = o; o += al256((size_t)n_blocks * (L - 1) * 3 * H * kTT * 4);
+    total = o;
+  }
+};
+
+
+// tensor-core forward integrator (mlp1d_tc.cu): per-layer tcgen05 GEMM launches; returns a cudaError_t / OFDFT_E* code
+int launch_mlp_fwd_tc(void* stream, const float* theta, const float* WTc, const float* y_in, float* y_out, float* ckpt,
+                      float* S0, float* S1, float* state, long long B, int jets, int stride, int H, int L, int n_steps,
+                      float t0, float t1, float y0sign);
+
+}  // namespace mlp
+}  // namespace ofdft

@@ -1,0 +1,332 @@
+// mlp1d_tc.cu -- tensor-core (tcgen05 / TMEM) forward integrator of the 1-D tanh-MLP flow
+// (reference: ofdft_normflows/cn_flows.py:117-182 evaluated through jax_ode.py:9-110; LiH.py:64-65 uses 3 x 512).
+//
+// A 128-trajectory tile of a 512-wide layer does not fit on chip with its three jets (768 KB of activations), so the
+// integrator is a sequence of per-layer launches whose activations stay L2 resident (6 MB per layer at B = 1024):
+//   glue kernel  (one warp per trajectory): last layer + RHS + RK4 bookkeeping of evaluation e, stage checkpoint and
+//                first layer of evaluation e+1;
+//   layer kernel (one CTA per 128 trajectories x 64 output units): P[jet] = A[jet] . W_l for the jets (a, a', a'')
+//                as error-compensated 3xTF32 tcgen05 GEMMs with fp32 accumulators in tensor memory, tanh-jet epilogue.
+// Layer buffers hold (a, p', p'') row-major [jet][row][unit]; the operand jets (a, a' = (1-a^2) p', a'' = ...) and their
+// tf32 remainders are built while staging (float4 loads -> float4 stores into the K-major no-swizzle UMMA layout).
+// Operands go in unrounded: the tensor core truncates to tf32 (tests/tc_trunc_probe.py).  The TMEM accumulation chain is
+// kept short (two alternating accumulator sets, drained into fp32 registers every 128 k) because it truncates too.
+#include "common.cuh"
+#include "mlp1d_common.cuh"
+#include "tc.cuh"
+
+namespace ofdft {
+namespace mlp {
+
+constexpr int kGemmKC = 16;                       // k per pipeline stage (4 chunks of 4)
+constexpr int kGemmGroup = 8;                     // stages per accumulator set (128 k, 48 MMAs per jet)
+constexpr int kLboA = 128 * 16 + 32;              // chunk stride of the activation operand (bytes; +32: conflict-free stores)
+constexpr int kLboB = 64 * 16 + 32;               // chunk stride of the weight operand
+
+struct GemmStage {
+  float A[3][2][4 * (kLboA / 4)];                 // [jet][hi/lo][chunk][row 128][4]
+  float W[2][4 * (kLboB / 4)];                    // [hi/lo][chunk][row j 64][4]
+};
+struct GemmSmem {
+  GemmStage st[2];
+  uint64_t bar[2];
+  unsigned int tmem_slot;
+};
+
+struct GemmArgs {
+  const float* Sin; float* Sout;                  // [jet][rows_pad][H]
+  const float* WT;                                // [j][k]
+  const float* bias;                              // [H] (theta offset: may be unaligned -> scalar loads)
+  long long B, rows_pad; int H;
+};
+
+template <int NJ>
+__global__ void __launch_bounds__(256, 1) mlp_layer_gemm_tc_kernel(const GemmArgs g) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  GemmSmem& sm = *reinterpret_cast<GemmSmem*>(smem_raw);
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  const int H = g.H;
+  const long long row0 = (long long)blockIdx.x * 128;
+  const int j0 = blockIdx.y * 64;
+  if (tid == 0) { tc::mbar_init(&sm.bar[0], 1); tc::mbar_init(&sm.bar[1], 1); tc::fence_mbar_init(); }
+  if (w == 0) tc::tmem_alloc(&sm.tmem_slot, 512);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = sm.tmem_slot;
+  const uint32_t idesc = tc::make_idesc_tf32(128, 64, 0, 0);
+  const int n_it = H / kGemmKC;
+  const size_t jet_stride = (size_t)g.rows_pad * H;
+
+  // staging items: activation (row, chunk) pairs idx = tid + 256 q (4 threads cover 64 contiguous bytes of a row),
+  // weight (j, chunk) pairs idx = tid
+  float4 ra[2][3], rw;
+  auto load_regs = [&](int it) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int idx = tid + 256 * q, r = idx >> 2, c = idx & 3;
+      const float* src = g.Sin + (size_t)(row0 + r) * H + it * kGemmKC + 4 * c;
+#pragma unroll
+      for (int jt = 0; jt < NJ; ++jt) ra[q][jt] = *reinterpret_cast<const float4*>(src + jt * jet_stride);
+    }
+    rw = *reinterpret_cast<const float4*>(g.WT + (size_t)(j0 + (tid >> 2)) * H + it * kGemmKC + 4 * (tid & 3));
+  };
+  auto lo4 = [](const float4 v) { return make_float4(tc::lo_tf32(v.x), tc::lo_tf32(v.y), tc::lo_tf32(v.z), tc::lo_tf32(v.w)); };
+  auto store_regs = [&](GemmStage& S) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int idx = tid + 256 * q, r = idx >> 2, c = idx & 3;
+      const int off = c * (kLboA / 4) + r * 4;
+      const float4 a = ra[q][0];
+      *reinterpret_cast<float4*>(&S.A[0][0][off]) = a;
+      *reinterpret_cast<float4*>(&S.A[0][1][off]) = lo4(a);
+      if (NJ >= 2) {
+        const float4 p1 = ra[q][1];
+        const float4 sg = make_float4(fmaf(-a.x, a.x, 1.0f), fmaf(-a.y, a.y, 1.0f), fmaf(-a.z, a.z, 1.0f), fmaf(-a.w, a.w, 1.0f));
+        const float4 a1 = make_float4(sg.x * p1.x, sg.y * p1.y, sg.z * p1.z, sg.w * p1.w);
+        *reinterpret_cast<float4*>(&S.A[1][0][off]) = a1;
+        *reinterpret_cast<float4*>(&S.A[1][1][off]) = lo4(a1);
+        if (NJ == 3) {
+          const float4 p2 = ra[q][2];
+          const float4 a2 = make_float4(fmaf(sg.x, p2.x, -2.0f * a.x * a1.x * p1.x), fmaf(sg.y, p2.y, -2.0f * a.y * a1.y * p1.y),
+                                        fmaf(sg.z, p2.z, -2.0f * a.z * a1.z * p1.z), fmaf(sg.w, p2.w, -2.0f * a.w * a1.w * p1.w));
+          *reinterpret_cast<float4*>(&S.A[2][0][off]) = a2;
+          *reinterpret_cast<float4*>(&S.A[2][1][off]) = lo4(a2);
+        }
+      }
+    }
+    const int offw = (tid & 3) * (kLboB / 4) + (tid >> 2) * 4;
+    *reinterpret_cast<float4*>(&S.W[0][offw]) = rw;
+    *reinterpret_cast<float4*>(&S.W[1][offw]) = lo4(rw);
+  };
+
+  float acc[NJ][32];
+#pragma unroll
+  for (int jt = 0; jt < NJ; ++jt)
+#pragma unroll
+    for (int i = 0; i < 32; ++i) acc[jt][i] = 0.f;
+  const uint32_t tl = tmem + ((uint32_t)(32 * (w & 3)) << 16) + 32 * (w >> 2);   // this thread's row, its 32 columns
+  auto drain = [&](int set) {
+    tc::fence_after_sync();
+#pragma unroll
+    for (int jt = 0; jt < NJ; ++jt)
+#pragma unroll
+      for (int c0 = 0; c0 < 32; c0 += 16) {
+        float t[16];
+        tc::tmem_ld16(tl + set * 192 + jt * 64 + c0, t);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[jt][c0 + i] += t[i];
+      }
+    tc::fence_before_sync();
+  };
+
+  uint32_t phase = 0, pending = 0;
+  int drained = 0;                                  // accumulator groups already folded into acc
+  load_regs(0);
+  for (int it = 0; it < n_it; ++it) {
+    const int s = it & 1;
+    if (pending & (1u << s)) { tc::mbar_wait(&sm.bar[s], (phase >> s) & 1u); phase ^= 1u << s; pending &= ~(1u << s); }
+    // every MMA up to iteration it-2 has completed: fold the accumulator set of a group that ended there
+    if (it >= 2 && (it - 1) % kGemmGroup == 0) { __syncwarp(); drain(drained & 1); ++drained; }
+    store_regs(sm.st[s]);
+    if (it + 1 < n_it) load_regs(it + 1);
+    tc::fence_async_smem();
+    __syncthreads();
+    if (w == 0) {
+      tc::fence_after_sync();
+      if (tc::elect_one()) {
+        const int set = (it / kGemmGroup) & 1;
+        const bool first = (it % kGemmGroup) == 0;
+        const uint64_t wh = tc::make_desc(tc::smem_u32(sm.st[s].W[0]), kLboB, 128);
+        const uint64_t wl = tc::make_desc(tc::smem_u32(sm.st[s].W[1]), kLboB, 128);
+#pragma unroll
+        for (int jt = 0; jt < NJ; ++jt) {
+          const uint64_t ah = tc::make_desc(tc::smem_u32(sm.st[s].A[jt][0]), kLboA, 128);
+          const uint64_t al = tc::make_desc(tc::smem_u32(sm.st[s].A[jt][1]), kLboA, 128);
+#pragma unroll
+          for (int p = 0; p < 3; ++p)
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks)
+              tc::mma_tf32(tmem + set * 192 + jt * 64, (p == 1 ? al : ah) + ks * ((2 * kLboA) >> 4),
+                           (p == 2 ? wl : wh) + ks * ((2 * kLboB) >> 4), idesc, !(first && p == 0 && ks == 0));
+        }
+        tc::commit(&sm.bar[s]);
+      }
+      __syncwarp();
+    }
+    pending |= 1u << s;
+  }
+#pragma unroll
+  for (int s2 = 0; s2 < 2; ++s2)
+    if (pending & (1u << s2)) { tc::mbar_wait(&sm.bar[s2], (phase >> s2) & 1u); phase ^= 1u << s2; }
+  __syncwarp();
+  const int n_groups = (n_it + kGemmGroup - 1) / kGemmGroup;
+  for (; drained < n_groups; ++drained) drain(drained & 1);
+
+  // ---- epilogue: bias, tanh, store (a, p', p'') ----
+  const long long row = row0 + 32 * (w & 3) + lane;
+  if (row < g.B) {
+    const int jc = j0 + 32 * (w >> 2);
+    float* dst = g.Sout + (size_t)row * H + jc;
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      float4 a;
+      a.x = tanh_f(acc[0][i] + g.bias[jc + i]); a.y = tanh_f(acc[0][i + 1] + g.bias[jc + i + 1]);
+      a.z = tanh_f(acc[0][i + 2] + g.bias[jc + i + 2]); a.w = tanh_f(acc[0][i + 3] + g.bias[jc + i + 3]);
+      *reinterpret_cast<float4*>(dst + i) = a;
+      if (NJ >= 2) *reinterpret_cast<float4*>(dst + jet_stride + i) = make_float4(acc[1][i], acc[1][i + 1], acc[1][i + 2], acc[1][i + 3]);
+      if (NJ == 3) *reinterpret_cast<float4*>(dst + 2 * jet_stride + i) = make_float4(acc[2][i], acc[2][i + 1], acc[2][i + 2], acc[2][i + 3]);
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (w == 0) tc::tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
+// glue: one warp per trajectory.  eval >= 0: last layer + RHS + RK4 update of evaluation `eval` from the last hidden
+// layer's buffer; then (if another evaluation follows) the stage checkpoint and first layer of evaluation eval+1.
+// ------------------------------------------------------------------------------------------------
+struct GlueArgs {
+  const float* theta; const float* Slast; float* S0; float* state;
+  const float* y_in; float* y_out; float* ckpt;
+  long long B, rows_pad; int stride, H, L, n_steps, eval; float t0, t1, y0;
+};
+
+template <int NJ>
+__global__ void __launch_bounds__(256) mlp_glue_tc_kernel(const GlueArgs g) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= g.B) return;
+  const int H = g.H;
+  const ThetaLayout TL(H, g.L);
+  const size_t jet_stride = (size_t)g.rows_pad * H;
+  const float h = (g.t1 - g.t0) / (float)g.n_steps;
+  float* st = g.state + row * 8;                 // y[3], accw[3], x_stage, s_stage
+  float y[3] = {0, 0, 0}, accw[3] = {0, 0, 0}, xst, sst = 0.f;
+  if (g.eval < 0) {
+    const float* src = g.y_in + row * g.stride;
+    y[0] = src[0];
+    if (NJ >= 2) y[1] = src[1];
+    if (NJ == 3) y[2] = src[2];
+    xst = y[0]; sst = y[2];
+  } else {
+    float hp[3] = {0.f, 0.f, 0.f};
+    const float* s0 = g.Slast + (size_t)row * H;
+    for (int k = 4 * lane; k < H; k += 128) {
+      const float4 a = *reinterpret_cast<const float4*>(s0 + k);
+      float4 p1 = make_float4(0, 0, 0, 0), p2 = make_float4(0, 0, 0, 0);
+      if (NJ >= 2) p1 = *reinterpret_cast<const float4*>(s0 + jet_stride + k);
+      if (NJ == 3) p2 = *reinterpret_cast<const float4*>(s0 + 2 * jet_stride + k);
+      const float av[4] = {a.x, a.y, a.z, a.w}, q1[4] = {p1.x, p1.y, p1.z, p1.w}, q2[4] = {p2.x, p2.y, p2.z, p2.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float wl = g.theta[TL.w_last() + k + e];
+        const float sg = fmaf(-av[e], av[e], 1.0f);
+        const float a1 = sg * q1[e];
+        hp[0] = fmaf(wl, av[e], hp[0]);
+        if (NJ >= 2) hp[1] = fmaf(wl, a1, hp[1]);
+        if (NJ == 3) hp[2] = fmaf(wl, fmaf(sg, q2[e], -2.0f * av[e] * a1 * q1[e]), hp[2]);
+      }
+    }
+    const float h0 = warp_sum(hp[0]) + g.theta[0];
+    const float h1 = NJ >= 2 ? warp_sum(hp[1]) : 0.f;
+    const float h2 = NJ == 3 ? warp_sum(hp[2]) : 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { y[c] = st[c]; accw[c] = st[3 + c]; }
+    sst = st[7];
+    float k[3];
+    k[0] = g.y0 * h0; k[1] = -g.y0 * h1; k[2] = -g.y0 * (h1 * sst + h2);
+    const int stage = g.eval & 3;
+    const float wgt = (stage == 0 || stage == 3) ? 1.0f : 2.0f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) accw[c] = fmaf(wgt, k[c], accw[c]);
+    if (stage < 3) {
+      const float cs = stage == 2 ? h : 0.5f * h;
+      xst = fmaf(cs, k[0], y[0]);
+      sst = fmaf(cs, k[2], y[2]);
+    } else {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { y[c] = fmaf(h * (1.0f / 6.0f), accw[c], y[c]); accw[c] = 0.f; }
+      xst = y[0]; sst = y[2];
+    }
+  }
+  const int ne = g.eval + 1;
+  if (ne < 4 * g.n_steps) {
+    __syncwarp();
+    if (lane == 0) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { st[c] = y[c]; st[3 + c] = accw[c]; }
+      st[6] = xst; st[7] = sst;
+      if (g.ckpt != nullptr) {
+        float* ck = g.ckpt + ((long long)ne * 2) * g.B + row;
+        ck[0] = xst;
+        if (NJ == 3) ck[g.B] = sst;
+      }
+    }
+    const int stage = ne & 3;
+    const float cs = stage == 0 ? 0.f : (stage == 3 ? h : 0.5f * h);
+    const float tp = g.y0 * (g.t0 + h * (float)(ne >> 2) + cs);
+    float* d0 = g.S0 + (size_t)row * H;
+    for (int k = 4 * lane; k < H; k += 128) {
+      float a[4], wx[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        wx[e] = g.theta[TL.w(0) + H + k + e];
+        a[e] = tanh_f(fmaf(wx[e], xst, fmaf(tp, g.theta[TL.w(0) + k + e], g.theta[TL.b(0) + k + e])));
+      }
+      *reinterpret_cast<float4*>(d0 + k) = make_float4(a[0], a[1], a[2], a[3]);
+      if (NJ >= 2) *reinterpret_cast<float4*>(d0 + jet_stride + k) = make_float4(wx[0], wx[1], wx[2], wx[3]);
+      if (NJ == 3) *reinterpret_cast<float4*>(d0 + 2 * jet_stride + k) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  } else if (lane == 0) {
+    float* dst = g.y_out + row * g.stride;
+    dst[0] = y[0];
+    if (NJ >= 2) dst[1] = y[1];
+    if (NJ == 3) dst[2] = y[2];
+  }
+}
+
+template <int NJ>
+static int run_fwd_tc(cudaStream_t st, const float* theta, const float* WTc, const float* y_in, float* y_out, float* ckpt,
+                      float* S0, float* S1, float* state, long long B, int stride, int H, int L, int n_steps, float t0, float t1,
+                      float y0sign) {
+  const long long rows_pad = (B + 127) / 128 * 128;
+  const ThetaLayout TL(H, L);
+  cudaError_t e = cudaFuncSetAttribute(mlp_layer_gemm_tc_kernel<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)sizeof(GemmSmem) + 1024);
+  if (e != cudaSuccess) return (int)e;
+  // rows beyond B of both buffers are read by the last tile: keep them finite
+  e = cudaMemsetAsync(S0, 0, 3 * (size_t)rows_pad * H * sizeof(float), st);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaMemsetAsync(S1, 0, 3 * (size_t)rows_pad * H * sizeof(float), st);
+  if (e != cudaSuccess) return (int)e;
+  GlueArgs ga{theta, nullptr, S0, state, y_in, y_out, ckpt, B, rows_pad, stride, H, L, n_steps, -1, t0, t1, y0sign};
+  const int glue_grid = (int)((B + 7) / 8);
+  const dim3 gemm_grid((unsigned)(rows_pad / 128), (unsigned)(H / 64));
+  float* bufs[2] = {S0, S1};
+  for (int ev = -1; ev < 4 * n_steps; ++ev) {
+    // the last hidden layer of evaluation ev ended in bufs[(L-1) & 1]
+    ga.eval = ev; ga.Slast = bufs[(L - 1) & 1];
+    mlp_glue_tc_kernel<NJ><<<glue_grid, 256, 0, st>>>(ga);
+    if (ev + 1 == 4 * n_steps) break;
+    for (int l = 1; l < L; ++l) {
+      GemmArgs gg{bufs[(l - 1) & 1], bufs[l & 1], WTc + (size_t)(l - 1) * H * H, theta + TL.b(l), B, rows_pad, H};
+      mlp_layer_gemm_tc_kernel<NJ><<<gemm_grid, 256, sizeof(GemmSmem) + 1024, st>>>(gg);
+    }
+  }
+  return (int)cudaGetLastError();
+}
+
+int launch_mlp_fwd_tc(void* stream, const float* theta, const float* WTc, const float* y_in, float* y_out, float* ckpt,
+                      float* S0, float* S1, float* state, long long B, int jets, int stride, int H, int L, int n_steps,
+                      float t0, float t1, float y0sign) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (jets == 3) return run_fwd_tc<3>(st, theta, WTc, y_in, y_out, ckpt, S0, S1, state, B, stride, H, L, n_steps, t0, t1, y0sign);
+  if (jets == 2) return run_fwd_tc<2>(st, theta, WTc, y_in, y_out, ckpt, S0, S1, state, B, stride, H, L, n_steps, t0, t1, y0sign);
+  return run_fwd_tc<1>(st, theta, WTc, y_in, y_out, ckpt, S0, S1, state, B, stride, H, L, n_steps, t0, t1, y0sign);
+}
+
+}  // namespace mlp
+}  // namespace ofdft
