@@ -22,10 +22,11 @@ namespace ofdft {
 
 constexpr int kChunkBytesA = kTP * 16;      // LBO of the activation operand (128 rows x 16 B)
 constexpr int kChunkBytesB = kH * 16;       // LBO of the weight operand (64 rows x 16 B)
+constexpr int kColAhi = 3 * kH;             // forward, two-CTA variant: TMEM columns of the activation "hi" operand
 
 template <int NB>
 struct SmemTcT {
-  float Abuf[NB][2][kH * kTP];       // [jet buffer][hi/lo][16 chunks][128 rows][4]
+  float Abuf[NB][NB == 1 ? 1 : 2][kH * kTP];   // [jet buffer][hi/lo][16 chunks][128 rows][4]; NB == 1: lo only (hi in TMEM)
   float Whi[kH * kH], Wlo[kH * kH];  // B operand: [16 chunks of k][64 rows j][4]
   float wr[kH], wt[kH], b2[kH], w3[kH];
   float cb[kMaxNa * kH];
@@ -37,7 +38,7 @@ struct SmemTcT {
   int tile;
 };
 using SmemTc = SmemTcT<2>;     // one CTA per SM, jets 0 and 1 staged together
-using SmemTc1 = SmemTcT<1>;    // 107 KB: two CTAs per SM, jets staged one at a time (the co-resident CTA fills the waits)
+using SmemTc1 = SmemTcT<1>;    // 75 KB: two CTAs per SM, jets staged one at a time (the co-resident CTA fills the waits)
 
 // stage one jet (UPT units of one trajectory) as hi/lo tf32 operands
 template <int UPT>
@@ -93,9 +94,9 @@ __device__ void fwd_tile_tc(SmemTcT<NB>& sm, const GnnFwdArgs& a, long long row0
   const uint32_t idesc = tc::make_idesc_tf32(kTP, kH, 0, 0);
   const uint32_t tlane = tmem + ((uint32_t)(32 * (w & 3)) << 16);
   const uint64_t dA00 = tc::make_desc(tc::smem_u32(sm.Abuf[0][0]), kChunkBytesA, 128);
-  const uint64_t dA01 = tc::make_desc(tc::smem_u32(sm.Abuf[0][1]), kChunkBytesA, 128);
+  const uint64_t dA01 = tc::make_desc(tc::smem_u32(sm.Abuf[0][NB == 1 ? 0 : 1]), kChunkBytesA, 128);
   const uint64_t dA10 = tc::make_desc(tc::smem_u32(sm.Abuf[NB - 1][0]), kChunkBytesA, 128);
-  const uint64_t dA11 = tc::make_desc(tc::smem_u32(sm.Abuf[NB - 1][1]), kChunkBytesA, 128);
+  const uint64_t dA11 = tc::make_desc(tc::smem_u32(sm.Abuf[NB - 1][NB == 1 ? 0 : 1]), kChunkBytesA, 128);
   const uint64_t dWh = tc::make_desc(tc::smem_u32(sm.Whi), kChunkBytesB, 128);
   const uint64_t dWl = tc::make_desc(tc::smem_u32(sm.Wlo), kChunkBytesB, 128);
 
@@ -161,27 +162,47 @@ __device__ void fwd_tile_tc(SmemTcT<NB>& sm, const GnnFwdArgs& a, long long row0
             av[u] = tanh_f(fmaf(sm.wr[UPT * uh + u], r, fmaf(tprime, sm.wt[UPT * uh + u], cbi[u])));
         }
         if (NB == 1) {
-          // single operand buffer: stage -> MMA -> wait, jet by jet, on one mbarrier
+          // one jet at a time on one mbarrier.  The MMAs read 6 KB of operands per 32 clocks from shared memory when both
+          // come from there -- more than its 128 B/clk -- so the activation "hi" part (read by two of the three passes)
+          // goes to tensor memory (TS-mode MMA) and only the tf32 remainder is staged in shared memory.
 #pragma unroll
           for (int jt = 0; jt < NJ; ++jt) {
             if (jt > 0) { tc::mbar_wait(&sm.bar[0], phase[0]); phase[0] ^= 1; __syncwarp(); }
-            if (jt == 0) stage_jet<UPT>(sm.Abuf[0][0], sm.Abuf[0][1], av, m, uh);
-            else {
-              float aj[UPT];
+            float aj[UPT];
 #pragma unroll
-              for (int u = 0; u < UPT; ++u) {
-                const float wv = sm.wr[UPT * uh + u];
-                const float a1 = fmaf(-av[u], av[u], 1.0f) * wv;
-                aj[u] = jt == 1 ? a1 : -2.0f * av[u] * a1 * wv;
-              }
-              stage_jet<UPT>(sm.Abuf[0][0], sm.Abuf[0][1], aj, m, uh);
+            for (int u = 0; u < UPT; ++u) {
+              const float wv = sm.wr[UPT * uh + u];
+              const float a1 = fmaf(-av[u], av[u], 1.0f) * wv;
+              aj[u] = jt == 0 ? av[u] : (jt == 1 ? a1 : -2.0f * av[u] * a1 * wv);
             }
+#pragma unroll
+            for (int c0 = 0; c0 < UPT; c0 += 16) {
+              float hv[16];
+#pragma unroll
+              for (int u = 0; u < 16; ++u) hv[u] = aj[c0 + u];
+              tc::tmem_st16(tlane + kColAhi + UPT * uh + c0, hv);
+            }
+#pragma unroll
+            for (int c = 0; c < UPT / 4; ++c) {
+              const int off = (((UPT / 4) * uh + c) * kTP + m) * 4;
+              *reinterpret_cast<float4*>(sm.Abuf[0][0] + off) =
+                  make_float4(tc::lo_tf32(aj[4 * c]), tc::lo_tf32(aj[4 * c + 1]), tc::lo_tf32(aj[4 * c + 2]), tc::lo_tf32(aj[4 * c + 3]));
+            }
+            tc::tmem_st_wait();
             tc::fence_async_smem();
+            tc::fence_before_sync();
             __syncthreads();
             if (w == 0) {
               tc::fence_after_sync();
               if (tc::elect_one()) {
-                issue_jet_mma(tmem + jt * kH, dA00, dA01, dWh, dWl, idesc);
+                constexpr uint64_t stepA = (2 * kChunkBytesA) >> 4, stepB = (2 * kChunkBytesB) >> 4;
+                const uint32_t d = tmem + jt * kH;
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) tc::mma_tf32_ts(d, tmem + kColAhi + 8 * ks, dWh + ks * stepB, idesc, ks != 0);
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) tc::mma_tf32_ts(d, tmem + kColAhi + 8 * ks, dWl + ks * stepB, idesc, true);
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) tc::mma_tf32(d, dA01 + ks * stepA, dWh + ks * stepB, idesc, true);
                 tc::commit(&sm.bar[0]);
               }
               __syncwarp();

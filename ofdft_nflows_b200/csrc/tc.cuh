@@ -46,6 +46,9 @@ __device__ __forceinline__ void commit(uint64_t* mbar) {
 __device__ __forceinline__ void mbar_init(uint64_t* mbar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(mbar)), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* mbar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(mbar)) : "memory");
+}
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
 __device__ __forceinline__ void mbar_wait(uint64_t* mbar, uint32_t parity) {
