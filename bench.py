@@ -382,7 +382,13 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "trajectories/s", "h2d_bytes_per_step": int(host_batch.numel() * 4),
                     "d2h_bytes_per_step": int(host_sums.numel() * 8 + host_grad.numel() * 4)},
-            "gpu_launches": (5 if not is_1d else 4 + 2 + 1 + 2 * (len(MLP_FEAT) - 1) + 2) * args.steps,
+            # 3-D: fwd, functionals x2, bwd, gradient reduce.  1-D: forward = weight prep + (4 n_steps + 1) glue launches +
+            # 4 n_steps (L-1) layer-GEMM launches (tcgen05 path); functionals x2; backward = prep + sweep + small reduce +
+            # (L-1) x (weight-gradient GEMM + reduce)
+            "gpu_launches": (5 if not is_1d else
+                             (1 + (4 * args.n_steps + 1) + 4 * args.n_steps * (len(MLP_FEAT) - 1)
+                              if os.environ.get("OFDFT_B200_MLP_FWD", "tc")[0] != "f" else 2)
+                             + 2 + 3 + 2 * (len(MLP_FEAT) - 1)) * args.steps,
             "roofline": roofline,
             "energy_terms_last_step": [float(v) for v in sums.cpu().numpy()[:6]],
         }
