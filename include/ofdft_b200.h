@@ -229,6 +229,12 @@ int ofdft_batch_generator_1d(void* stream, uint64_t seed, uint64_t offset, int64
 int ofdft_rmsprop_clip_step(void* stream, float* theta, const float* grad, float* nu, int64_t n, float lr, float decay,
                             float eps, float max_norm);
 
+/* Running average of the per-term energy means, optax.ema(decay, debias=True) as the drivers log it
+ * (H20_mol_ofdft_min_equiv_flows.py:117-118, 193-196): state <- decay*state + (1-decay)*values, out = state / (1 - decay^step).
+ * values / state / out are DEVICE doubles (values is the `sums` output of ofdft_functionals_fwd_bwd), so a training loop can
+ * append to a device-resident history (out = history + step*n) without a host synchronisation per epoch.  step is 1-based. */
+int ofdft_ema_update(void* stream, const double* values, double* state, double* out, int32_t n, int64_t step, double decay);
+
 /* FP32 FFMA / SFU peak microbenchmarks (roofline denominators; bench.py).  Run `iters` dependent
  * rounds on every SM; return via *out the number of FFMA (or MUFU.RSQ) lane-operations issued. */
 int ofdft_microbench_ffma(void* stream, float* sink, int32_t iters, double* ops_out);

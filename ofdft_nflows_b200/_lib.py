@@ -49,6 +49,7 @@ SIGNATURES = {
     "ofdft_batch_generator_3d": (C.c_int, [vp, C.c_uint64, C.c_uint64, vp, vp, i32, i64, vp]),
     "ofdft_batch_generator_1d": (C.c_int, [vp, C.c_uint64, C.c_uint64, i64, vp]),
     "ofdft_rmsprop_clip_step": (C.c_int, [vp, vp, vp, vp, i64, f32, f32, f32, f32]),
+    "ofdft_ema_update": (C.c_int, [vp, vp, vp, vp, i32, i64, C.c_double]),
     "ofdft_microbench_ffma": (C.c_int, [vp, vp, i32, C.POINTER(C.c_double)]),
     "ofdft_microbench_sfu": (C.c_int, [vp, vp, i32, C.POINTER(C.c_double)]),
     "ofdft_tc_gemm_test": (C.c_int, [vp, vp, vp, vp, i32, i32]),

@@ -4,6 +4,8 @@
 // Elementwise / HBM-bound; Philox counter-based RNG from curand's device API (reproducible per (seed, row)).
 #include <curand_kernel.h>
 
+#include <cmath>
+
 #include "common.cuh"
 
 namespace ofdft {
@@ -157,7 +159,23 @@ __global__ void __launch_bounds__(1024) rmsprop_clip_kernel(float* __restrict__ 
     theta[i] -= lr * g * rsqrtf(v + eps);
   }
 }
+__global__ void ema_update_kernel(const double* __restrict__ values, double* __restrict__ state, double* __restrict__ out, int n,
+                                  double decay, double debias) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double v = decay * state[i] + (1.0 - decay) * values[i];
+  state[i] = v;
+  out[i] = v / debias;
+}
 }  // namespace ofdft
+
+extern "C" int ofdft_ema_update(void* stream, const double* values, double* state, double* out, int32_t n, int64_t step,
+                                double decay) {
+  if (!values || !state || !out || n <= 0 || step < 1 || !(decay >= 0.0 && decay < 1.0)) return OFDFT_EINVAL;
+  const double debias = 1.0 - pow(decay, (double)step);
+  ofdft::ema_update_kernel<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(values, state, out, n, decay, debias);
+  return (int)cudaGetLastError();
+}
 
 extern "C" int ofdft_rmsprop_clip_step(void* stream, float* theta, const float* grad, float* nu, int64_t n, float lr,
                                        float decay, float eps, float max_norm) {

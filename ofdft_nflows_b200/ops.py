@@ -241,3 +241,27 @@ def rmsprop_clip_step(theta: torch.Tensor, grad: torch.Tensor, nu: torch.Tensor,
             raise ValueError("theta / grad / nu must be contiguous float32 CUDA tensors")
     _lib.check(lib.ofdft_rmsprop_clip_step(_stream(), _ptr(theta), _ptr(grad), _ptr(nu), theta.numel(), float(lr), float(decay),
                                            float(eps), float(max_norm)), "ofdft_rmsprop_clip_step")
+
+
+class EnergyEMA:
+    """optax.ema(decay, debias=True) of the per-term energy means as the drivers log it
+    (H20_mol_ofdft_min_equiv_flows.py:117-118, 193-196), device-resident: ``update(sums)`` takes the float64 device
+    vector returned by the fused step and returns the debiased averages; ``history`` keeps every update on the device so
+    a training loop reads it back once at the end instead of once per epoch."""
+
+    def __init__(self, n: int = 6, decay: float = 0.99, capacity: int = 0, device="cuda"):
+        self.decay, self.n, self.step = float(decay), int(n), 0
+        self.state = torch.zeros(n, dtype=torch.float64, device=device)
+        self.history = torch.zeros((max(capacity, 1), n), dtype=torch.float64, device=device)
+        self.capacity = int(capacity)
+
+    def update(self, values: torch.Tensor) -> torch.Tensor:
+        lib = _lib.load()
+        if not values.is_cuda or values.dtype != torch.float64 or values.numel() != self.n:
+            raise ValueError("values must be a float64 CUDA vector of length n")
+        self.step += 1
+        row = (self.step - 1) % self.history.shape[0] if self.capacity else 0
+        out = self.history[row]
+        _lib.check(lib.ofdft_ema_update(_stream(), _ptr(values.contiguous()), _ptr(self.state), _ptr(out), self.n, self.step,
+                                        self.decay), "ofdft_ema_update")
+        return out

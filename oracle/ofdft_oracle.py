@@ -939,3 +939,10 @@ def rmsprop_clip_step(theta, grad, nu, lr, decay=0.9, eps=1e-8, max_norm=1.0):
     g = grad * (max_norm / gn if gn > max_norm else 1.0)
     nu2 = decay * nu + (1.0 - decay) * g * g
     return theta - lr * g / np.sqrt(nu2 + eps), nu2
+
+
+def ema_update(values, state, step: int, decay: float = 0.99):
+    """[third-party] optax.ema(decay, debias=True), restated from memory (call sites H20_mol_ofdft_min_equiv_flows.py:117-118,
+    193-196): returns (debiased average, new biased state); ``step`` is the 1-based update count."""
+    new = decay * np.asarray(state, dtype=np.float64) + (1.0 - decay) * np.asarray(values, dtype=np.float64)
+    return new / (1.0 - decay ** step), new

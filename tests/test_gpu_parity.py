@@ -470,6 +470,20 @@ def _mlp_slices(feat):
     return sl
 
 
+def test_energy_ema_matches_optax_semantics():
+    rng = np.random.default_rng(3)
+    ema = ops.EnergyEMA(n=6, decay=0.99, capacity=8)
+    state = np.zeros(6)
+    for t in range(1, 12):
+        v = rng.standard_normal(6)
+        ref, state = O.ema_update(v, state, t, 0.99)
+        out = ema.update(torch.as_tensor(v, dtype=torch.float64, device="cuda")).cpu().numpy()
+        assert np.allclose(out, ref, rtol=1e-10, atol=1e-14)   # fused multiply-add in the kernel vs two roundings in numpy
+    assert np.allclose(ema.history[(11 - 1) % 8].cpu().numpy(), ref, rtol=1e-10, atol=1e-14)
+    with pytest.raises(ValueError):
+        ema.update(torch.zeros(5, dtype=torch.float64, device="cuda"))
+
+
 @pytest.mark.parametrize("feat,bs", [((64, 64), 37), ((128, 128, 128), 20), ((512, 512, 512), 24), ((256, 256, 256, 256), 9)])
 def test_mlp1d_forward_and_training_step_match_oracle(feat, bs):
     from ofdft_nflows_b200.cn_flows import Gen_CNFSimpleMLP, mlp_fwd

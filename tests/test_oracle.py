@@ -245,3 +245,11 @@ def test_oracle_reproduces_golden_vectors(path):
     assert np.all(np.abs(t32[:4] - g["terms"][:4]) <= 1e-5 * np.abs(g["terms"][:4]))
     gn = np.linalg.norm(g["grad"])
     assert np.linalg.norm(g32 - g["grad"]) <= 1e-4 * gn
+
+
+def test_ema_debias_returns_a_constant_signal_exactly():
+    """optax.ema(debias=True): a constant input is reproduced at every step (the bias 1 - decay^t cancels)."""
+    state = np.zeros(3)
+    for t in range(1, 20):
+        out, state = O.ema_update(np.array([1.5, -2.0, 0.25]), state, t, 0.99)
+        assert np.allclose(out, [1.5, -2.0, 0.25], rtol=1e-12)
