@@ -149,7 +149,8 @@ def run_reference(args):
     t_probe, n_probe = cpu_reference_step(wl, 1024 if wl != "lih1d" else 128, cores)
     per_traj = t_probe / n_probe
     budget = 120.0 / max(1, args.steps + args.warmup)
-    bs = int(max(64 if wl == "lih1d" else 256, min(8192, budget / per_traj / 2)))
+    # capped at 2048: the reverse-mode graph of the adaptive solve grows with the batch (bs=8192 exceeds 62 GB of host RAM)
+    bs = int(max(64 if wl == "lih1d" else 256, min(2048, budget / per_traj / 2)))
     if wl == "lih1d":
         bs = min(bs, 512)
     for _ in range(args.warmup):
