@@ -189,6 +189,8 @@ def main():
     ap.add_argument("--n-steps", type=int, default=16, help="RK4 steps of the fixed-step integrator")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--full-jets", action="store_true", help="carry logp/score on the second half too (reference dataflow)")
+    ap.add_argument("--hartree", default="paired", choices=["paired", "allpairs"],
+                    help="allpairs: O(bs^2) cross-half Hartree estimator (coordinates all-gathered over NCCL, tiled pair kernel)")
     ap.add_argument("--recompute", action="store_true", help="recompute layer-2 activations in the backward pass (no HBM activation checkpoint)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -226,7 +228,8 @@ def main():
     else:
         model = Gen_EqvFlow(3, (H, H), mol["coords"], mol["onehot"], bool_neg=True, device=dev)
         spec = ops.EnergySpec(Ne=mol["Ne"], d=3, kin="tf-w", hart="hartree", nuc=nuc, x="lda", coords=mol["coords"], z=mol["z"])
-    est = EnergyEstimator(model, spec, n_steps=args.n_steps, skip_unused_jets=not args.full_jets, act_ckpt=not args.recompute)
+    est = EnergyEstimator(model, spec, n_steps=args.n_steps, skip_unused_jets=not args.full_jets, act_ckpt=not args.recompute,
+                          hartree_mode=args.hartree)
     theta = torch.as_tensor(theta_np, device=dev)
     params = model.unravel(theta)
     batch = torch.as_tensor(batch_np, device=dev)
@@ -392,6 +395,10 @@ def main():
                              + 2 + 3 + 2 * (len(MLP_FEAT) - 1)) * args.steps,
             "roofline": roofline,
             "energy_terms_last_step": [float(v) for v in sums.cpu().numpy()[:6]],
+            "hartree": ({"mode": "paired"} if args.hartree == "paired" else
+                        {"mode": "allpairs (energy + forces on both halves)",
+                         "pair_evaluations_per_step": 2.0 * (bs * n_gpus) ** 2,
+                         "pair_evaluations_per_s": 2.0 * (bs * n_gpus) ** 2 / (total_s / args.steps)}),
         }
         if n_gpus == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
