@@ -247,7 +247,8 @@ __global__ void __launch_bounds__(256, 1) mlp_fwd_kernel(const Args a) {
 }
 
 // aligned copies (and transposes) of the hidden kernels: theta offsets are odd, cp.async needs 16-byte sources
-__global__ void mlp_prep_kernel(const float* __restrict__ theta, float* __restrict__ Wc, float* __restrict__ WTc, int H, int L) {
+__global__ void mlp_prep_kernel(const float* __restrict__ theta, float* __restrict__ Wc, float* __restrict__ WTc, int H, int L,
+                                float* __restrict__ WTlo = nullptr) {
   const ThetaLayout TL(H, L);
   const long long n = (long long)(L - 1) * H * H;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -256,6 +257,7 @@ __global__ void mlp_prep_kernel(const float* __restrict__ theta, float* __restri
     const float v = theta[TL.w(l) + r * H + c];
     Wc[i] = v;
     if (WTc != nullptr) WTc[(long long)(l - 1) * H * H + (long long)c * H + r] = v;
+    if (WTlo != nullptr) WTlo[(long long)(l - 1) * H * H + (long long)c * H + r] = tc::lo_tf32(v);
   }
 }
 
@@ -709,7 +711,8 @@ extern "C" int ofdft_cnf_mlp1d_fwd(void* stream, const float* theta, const float
   cudaStream_t st = (cudaStream_t)stream;
   float* Wc = (float*)((char*)scratch + SL.wc);
   float* WTc = (float*)((char*)scratch + SL.wtc);
-  mlp_prep_kernel<<<256, 256, 0, st>>>(theta, Wc, fwd_tc ? WTc : nullptr, H, n_layers);
+  float* WTlo = (float*)((char*)scratch + SL.wtlo);
+  mlp_prep_kernel<<<256, 256, 0, st>>>(theta, Wc, fwd_tc ? WTc : nullptr, H, n_layers, fwd_tc ? WTlo : nullptr);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
   if (fwd_tc) {
@@ -717,7 +720,7 @@ extern "C" int ofdft_cnf_mlp1d_fwd(void* stream, const float* theta, const float
     float* S0 = (float*)((char*)scratch + SL.fwd_s);
     float* S1 = (float*)((char*)scratch + SL.fwd_s + sbuf);
     float* state = (float*)((char*)scratch + SL.fwd_state);
-    return launch_mlp_fwd_tc(stream, theta, WTc, y_in, y_out, ckpt, S0, S1, state, B, jets, stride, H, n_layers, n_steps, t0, t1,
+    return launch_mlp_fwd_tc(stream, theta, WTc, WTlo, y_in, y_out, ckpt, S0, S1, state, B, jets, stride, H, n_layers, n_steps, t0, t1,
                              y0sign);
   }
   const size_t smem = smem_bytes(H);

@@ -39,7 +39,7 @@ constexpr int kDwSplits = 16;
 inline size_t al256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 struct ScratchLayout {
-  size_t wc, wtc, fwd_s, fwd_state, fwd_end, gsmall, part, acts, pbar, total;
+  size_t wc, wtc, wtlo, fwd_s, fwd_state, fwd_end, gsmall, part, acts, pbar, total;
   ScratchLayout(long long B, int H, int L, int n_steps) {
     const long long rows = B < kChunkRows ? B : kChunkRows;
     const long long n_tiles = (rows + kTT - 1) / kTT;
@@ -47,7 +47,8 @@ struct ScratchLayout {
     size_t o = 0;
     wc = o; o += al256((size_t)(L - 1) * H * H * 4);
     wtc = o; o += al256((size_t)(L - 1) * H * H * 4);
-    // tensor-core forward: two ping-pong layer buffers [jet: a, p', p''][B rows padded to 128][H] and the RK4 row state
+    wtlo = o; o += al256((size_t)(L - 1) * H * H * 4);    // tf32 remainders of the transposed kernels
+    // tensor-core forward: two ping-pong layer buffers [jet: a, p', p''][H/4][B rows padded to 128][4 units] and the RK4 row state
     const size_t rows_pad = (size_t)((B + 127) / 128 * 128);
     fwd_s = o; o += 2 * al256(3 * rows_pad * H * 4);
     fwd_state = o; o += al256(rows_pad * 8 * 4);
@@ -62,7 +63,7 @@ struct ScratchLayout {
 
 
 // tensor-core forward integrator (mlp1d_tc.cu): per-layer tcgen05 GEMM launches; returns a cudaError_t / OFDFT_E* code
-int launch_mlp_fwd_tc(void* stream, const float* theta, const float* WTc, const float* y_in, float* y_out, float* ckpt,
+int launch_mlp_fwd_tc(void* stream, const float* theta, const float* WTc, const float* WTlo, const float* y_in, float* y_out, float* ckpt,
                       float* S0, float* S1, float* state, long long B, int jets, int stride, int H, int L, int n_steps,
                       float t0, float t1, float y0sign);
 

@@ -18,165 +18,201 @@
 namespace ofdft {
 namespace mlp {
 
-constexpr int kGemmKC = 16;                       // k per pipeline stage (4 chunks of 4)
-constexpr int kGemmGroup = 8;                     // stages per accumulator set (128 k, 48 MMAs per jet)
-constexpr int kLboA = 128 * 16 + 32;              // chunk stride of the activation operand (bytes; +32: conflict-free stores)
-constexpr int kLboB = 64 * 16 + 32;               // chunk stride of the weight operand
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tc::smem_u32(smem)), "l"(gmem) : "memory");
+}
 
-struct GemmStage {
-  float A[3][2][4 * (kLboA / 4)];                 // [jet][hi/lo][chunk][row 128][4]
-  float W[2][4 * (kLboB / 4)];                    // [hi/lo][chunk][row j 64][4]
-};
+constexpr int kGemmKC = 16;                       // k per pipeline stage (4 chunks of 4)
+constexpr int kGemmGroup = 8;                     // stages per TMEM accumulation chain (128 k, 48 MMAs per jet)
+constexpr int kGemmSlots = 3;                     // activation-operand ring in tensor memory
+constexpr int kGemmWSlots = 6;                    // weight-operand ring in shared memory (deeper: its copies are issued two
+                                                  // stages ahead and must never wait on an MMA that was only just submitted)
+constexpr int kLboB = 64 * 16 + 32;               // chunk stride of the weight operand (bytes; +32: conflict-free stores)
+constexpr int kColAcc = 0;                        // TMEM: accumulators 3 jets x 64 columns
+constexpr int kColOp = 192;                       // TMEM: operand ring, per slot [jet][hi 16 | lo 16] = 96 columns
+constexpr int kGemmThreads = 512 + 32;            // 16 staging warps + 1 MMA warp (17 warps: at most 96 registers per thread)
+
+// layer buffers: [jet: a, p', p''][unit / 4][row (padded to 128)][4 units] -- 32 consecutive rows x 4 units are 512
+// contiguous bytes, which is what a warp whose lanes are rows (the TMEM lane constraint) loads or stores at once
+__host__ __device__ __forceinline__ size_t sbuf_off(int unit_group, long long row, long long rows_pad) {
+  return ((size_t)unit_group * rows_pad + row) * 4;
+}
+
 struct GemmSmem {
-  GemmStage st[2];
-  uint64_t bar[2];
+  float W[kGemmWSlots][2][4 * (kLboB / 4)];       // [slot][hi/lo][chunk][row j 64][4]
+  uint64_t full[kGemmSlots], empty[kGemmSlots], accf, acce;
   unsigned int tmem_slot;
 };
 
 struct GemmArgs {
-  const float* Sin; float* Sout;                  // [jet][rows_pad][H]
-  const float* WT;                                // [j][k]
+  const float* Sin; float* Sout;                  // layer buffers
+  const float* WT; const float* WTlo;             // [j][k]: kernel transposed (unrounded) and its tf32 remainder
   const float* bias;                              // [H] (theta offset: may be unaligned -> scalar loads)
   long long B, rows_pad; int H;
 };
 
+// Layer GEMM P[jet] = A[jet] . W for the jets (a, a', a'') of 128 trajectories x 64 output units, 3xTF32 on tcgen05.
+// An SS-mode M128.N64.K8 tf32 MMA reads 6 KB of operands per 32 clocks -- 192 B/clk against the 128 B/clk of the
+// shared-memory port -- so the activation operand goes through TENSOR MEMORY (TS mode): warp w of the 16 staging warps
+// owns rows 32 (w & 3).. (the TMEM lanes it may access) and the 4-wide k chunk w >> 2; each thread loads (a, p', p'')
+// of its (row, chunk), builds the jets and their tf32 remainders and writes them with tcgen05.st; only the 8 KB
+// weight stage goes through shared memory (cp.async, two stages ahead).  Warp 16 issues the MMAs.
+//   full[s]  : staging warps -> MMA warp (16 arrivals)      empty[s] : tcgen05.commit -> stagers
+//   accf     : tcgen05.commit -> stagers (chain finished)   acce     : stagers -> MMA warp (16 arrivals: chain drained)
+// The accumulation chain is drained into fp32 registers every kGemmGroup stages because it truncates.
 template <int NJ>
-__global__ void __launch_bounds__(256, 1) mlp_layer_gemm_tc_kernel(const GemmArgs g) {
+__global__ void __launch_bounds__(kGemmThreads, 1) mlp_layer_gemm_tc_kernel(const GemmArgs g) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   GemmSmem& sm = *reinterpret_cast<GemmSmem*>(smem_raw);
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
   const int H = g.H;
   const long long row0 = (long long)blockIdx.x * 128;
   const int j0 = blockIdx.y * 64;
-  if (tid == 0) { tc::mbar_init(&sm.bar[0], 1); tc::mbar_init(&sm.bar[1], 1); tc::fence_mbar_init(); }
+  if (tid == 0) {
+    for (int i = 0; i < kGemmSlots; ++i) { tc::mbar_init(&sm.full[i], 16); tc::mbar_init(&sm.empty[i], 1); }
+    tc::mbar_init(&sm.accf, 1); tc::mbar_init(&sm.acce, 16);
+    tc::fence_mbar_init();
+  }
   if (w == 0) tc::tmem_alloc(&sm.tmem_slot, 512);
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem = sm.tmem_slot;
-  const uint32_t idesc = tc::make_idesc_tf32(128, 64, 0, 0);
   const int n_it = H / kGemmKC;
   const size_t jet_stride = (size_t)g.rows_pad * H;
 
-  // staging items: activation (row, chunk) pairs idx = tid + 256 q (4 threads cover 64 contiguous bytes of a row),
-  // weight (j, chunk) pairs idx = tid
-  float4 ra[2][3], rw;
-  auto load_regs = [&](int it) {
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const int idx = tid + 256 * q, r = idx >> 2, c = idx & 3;
-      const float* src = g.Sin + (size_t)(row0 + r) * H + it * kGemmKC + 4 * c;
-#pragma unroll
-      for (int jt = 0; jt < NJ; ++jt) ra[q][jt] = *reinterpret_cast<const float4*>(src + jt * jet_stride);
-    }
-    rw = *reinterpret_cast<const float4*>(g.WT + (size_t)(j0 + (tid >> 2)) * H + it * kGemmKC + 4 * (tid & 3));
-  };
-  auto lo4 = [](const float4 v) { return make_float4(tc::lo_tf32(v.x), tc::lo_tf32(v.y), tc::lo_tf32(v.z), tc::lo_tf32(v.w)); };
-  auto store_regs = [&](GemmStage& S) {
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const int idx = tid + 256 * q, r = idx >> 2, c = idx & 3;
-      const int off = c * (kLboA / 4) + r * 4;
-      const float4 a = ra[q][0];
-      *reinterpret_cast<float4*>(&S.A[0][0][off]) = a;
-      *reinterpret_cast<float4*>(&S.A[0][1][off]) = lo4(a);
-      if (NJ >= 2) {
-        const float4 p1 = ra[q][1];
-        const float4 sg = make_float4(fmaf(-a.x, a.x, 1.0f), fmaf(-a.y, a.y, 1.0f), fmaf(-a.z, a.z, 1.0f), fmaf(-a.w, a.w, 1.0f));
-        const float4 a1 = make_float4(sg.x * p1.x, sg.y * p1.y, sg.z * p1.z, sg.w * p1.w);
-        *reinterpret_cast<float4*>(&S.A[1][0][off]) = a1;
-        *reinterpret_cast<float4*>(&S.A[1][1][off]) = lo4(a1);
-        if (NJ == 3) {
-          const float4 p2 = ra[q][2];
-          const float4 a2 = make_float4(fmaf(sg.x, p2.x, -2.0f * a.x * a1.x * p1.x), fmaf(sg.y, p2.y, -2.0f * a.y * a1.y * p1.y),
-                                        fmaf(sg.z, p2.z, -2.0f * a.z * a1.z * p1.z), fmaf(sg.w, p2.w, -2.0f * a.w * a1.w * p1.w));
-          *reinterpret_cast<float4*>(&S.A[2][0][off]) = a2;
-          *reinterpret_cast<float4*>(&S.A[2][1][off]) = lo4(a2);
-        }
-      }
-    }
-    const int offw = (tid & 3) * (kLboB / 4) + (tid >> 2) * 4;
-    *reinterpret_cast<float4*>(&S.W[0][offw]) = rw;
-    *reinterpret_cast<float4*>(&S.W[1][offw]) = lo4(rw);
-  };
-
-  float acc[NJ][32];
-#pragma unroll
-  for (int jt = 0; jt < NJ; ++jt)
-#pragma unroll
-    for (int i = 0; i < 32; ++i) acc[jt][i] = 0.f;
-  const uint32_t tl = tmem + ((uint32_t)(32 * (w & 3)) << 16) + 32 * (w >> 2);   // this thread's row, its 32 columns
-  auto drain = [&](int set) {
-    tc::fence_after_sync();
-#pragma unroll
-    for (int jt = 0; jt < NJ; ++jt)
-#pragma unroll
-      for (int c0 = 0; c0 < 32; c0 += 16) {
-        float t[16];
-        tc::tmem_ld16(tl + set * 192 + jt * 64 + c0, t);
-        tc::tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 16; ++i) acc[jt][c0 + i] += t[i];
-      }
-    tc::fence_before_sync();
-  };
-
-  uint32_t phase = 0, pending = 0;
-  int drained = 0;                                  // accumulator groups already folded into acc
-  load_regs(0);
-  for (int it = 0; it < n_it; ++it) {
-    const int s = it & 1;
-    if (pending & (1u << s)) { tc::mbar_wait(&sm.bar[s], (phase >> s) & 1u); phase ^= 1u << s; pending &= ~(1u << s); }
-    // every MMA up to iteration it-2 has completed: fold the accumulator set of a group that ended there
-    if (it >= 2 && (it - 1) % kGemmGroup == 0) { __syncwarp(); drain(drained & 1); ++drained; }
-    store_regs(sm.st[s]);
-    if (it + 1 < n_it) load_regs(it + 1);
-    tc::fence_async_smem();
-    __syncthreads();
-    if (w == 0) {
+  if (w == 16) {
+    // ---------------- MMA issue warp ----------------
+    const uint32_t idesc = tc::make_idesc_tf32(128, 64, 0, 0);
+    uint32_t ph_full = 0, ph_acce = 0;
+    for (int it = 0; it < n_it; ++it) {
+      const int s = it % kGemmSlots;
+      const bool first = (it % kGemmGroup) == 0;
+      tc::mbar_wait(&sm.full[s], (ph_full >> s) & 1u); ph_full ^= 1u << s;
+      if (first && it > 0) { tc::mbar_wait(&sm.acce, ph_acce); ph_acce ^= 1u; }
+      __syncwarp();
       tc::fence_after_sync();
       if (tc::elect_one()) {
-        const int set = (it / kGemmGroup) & 1;
-        const bool first = (it % kGemmGroup) == 0;
-        const uint64_t wh = tc::make_desc(tc::smem_u32(sm.st[s].W[0]), kLboB, 128);
-        const uint64_t wl = tc::make_desc(tc::smem_u32(sm.st[s].W[1]), kLboB, 128);
+        const uint64_t wh = tc::make_desc(tc::smem_u32(sm.W[it % kGemmWSlots][0]), kLboB, 128);
+        const uint64_t wl = tc::make_desc(tc::smem_u32(sm.W[it % kGemmWSlots][1]), kLboB, 128);
 #pragma unroll
         for (int jt = 0; jt < NJ; ++jt) {
-          const uint64_t ah = tc::make_desc(tc::smem_u32(sm.st[s].A[jt][0]), kLboA, 128);
-          const uint64_t al = tc::make_desc(tc::smem_u32(sm.st[s].A[jt][1]), kLboA, 128);
+          const uint32_t ahi = tmem + kColOp + 96 * s + 32 * jt, alo = ahi + 16;
 #pragma unroll
           for (int p = 0; p < 3; ++p)
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks)
-              tc::mma_tf32(tmem + set * 192 + jt * 64, (p == 1 ? al : ah) + ks * ((2 * kLboA) >> 4),
-                           (p == 2 ? wl : wh) + ks * ((2 * kLboB) >> 4), idesc, !(first && p == 0 && ks == 0));
+              tc::mma_tf32_ts(tmem + kColAcc + jt * 64, (p == 1 ? alo : ahi) + 8 * ks, (p == 2 ? wl : wh) + ks * ((2 * kLboB) >> 4),
+                              idesc, !(first && p == 0 && ks == 0));
         }
-        tc::commit(&sm.bar[s]);
+        tc::commit(&sm.empty[s]);
+        if ((it + 1) % kGemmGroup == 0 || it + 1 == n_it) tc::commit(&sm.accf);
       }
       __syncwarp();
     }
-    pending |= 1u << s;
-  }
+  } else {
+    // ---------------- staging warps ----------------
+    const int r = 32 * (w & 3) + lane, c = w >> 2;          // row (TMEM lane) and k chunk of this thread
+    const float* a_src = g.Sin + sbuf_off(c, row0 + r, g.rows_pad);       // + 4 unit groups per stage
+    const size_t stage_stride = sbuf_off(4, 0, g.rows_pad);
+    const uint32_t tl = tmem + ((uint32_t)(32 * (w & 3)) << 16);
+    // weight stage: 64 rows x 4 chunks x (hi, lo) = 512 16-byte copies, one per thread
+    const int wj = (tid & 255) >> 2, wc = tid & 3, wpart = tid >> 8;
+    const float* w_src = (wpart ? g.WTlo : g.WT) + (size_t)(j0 + wj) * H + 4 * wc;
+    const int offw = wc * (kLboB / 4) + wj * 4;
+    auto copy_w = [&](int it) { cp_async16(&sm.W[it % kGemmWSlots][wpart][offw], w_src + it * kGemmKC); };
+    struct Regs { float4 a[3]; };
+    auto load_regs = [&](Regs& R, int it) {
 #pragma unroll
-  for (int s2 = 0; s2 < 2; ++s2)
-    if (pending & (1u << s2)) { tc::mbar_wait(&sm.bar[s2], (phase >> s2) & 1u); phase ^= 1u << s2; }
-  __syncwarp();
-  const int n_groups = (n_it + kGemmGroup - 1) / kGemmGroup;
-  for (; drained < n_groups; ++drained) drain(drained & 1);
+      for (int jt = 0; jt < NJ; ++jt) R.a[jt] = *reinterpret_cast<const float4*>(a_src + jt * jet_stride + it * stage_stride);
+    };
+    auto store_tmem = [&](const Regs& R, int s) {
+      const uint32_t base = tl + kColOp + 96 * s + 4 * c;
+      const float4 a = R.a[0];
+      tc::tmem_st4(base, a.x, a.y, a.z, a.w);
+      tc::tmem_st4(base + 16, tc::lo_tf32(a.x), tc::lo_tf32(a.y), tc::lo_tf32(a.z), tc::lo_tf32(a.w));
+      if (NJ >= 2) {
+        const float4 p1 = R.a[1];
+        const float4 sg = make_float4(fmaf(-a.x, a.x, 1.0f), fmaf(-a.y, a.y, 1.0f), fmaf(-a.z, a.z, 1.0f), fmaf(-a.w, a.w, 1.0f));
+        const float4 a1 = make_float4(sg.x * p1.x, sg.y * p1.y, sg.z * p1.z, sg.w * p1.w);
+        tc::tmem_st4(base + 32, a1.x, a1.y, a1.z, a1.w);
+        tc::tmem_st4(base + 48, tc::lo_tf32(a1.x), tc::lo_tf32(a1.y), tc::lo_tf32(a1.z), tc::lo_tf32(a1.w));
+        if (NJ == 3) {
+          const float4 p2 = R.a[2];
+          const float4 a2 = make_float4(fmaf(sg.x, p2.x, -2.0f * a.x * a1.x * p1.x), fmaf(sg.y, p2.y, -2.0f * a.y * a1.y * p1.y),
+                                        fmaf(sg.z, p2.z, -2.0f * a.z * a1.z * p1.z), fmaf(sg.w, p2.w, -2.0f * a.w * a1.w * p1.w));
+          tc::tmem_st4(base + 64, a2.x, a2.y, a2.z, a2.w);
+          tc::tmem_st4(base + 80, tc::lo_tf32(a2.x), tc::lo_tf32(a2.y), tc::lo_tf32(a2.z), tc::lo_tf32(a2.w));
+        }
+      }
+    };
+    // accumulators: warp w <-> rows 32 (w & 3).. and the 16 output columns 16 (w >> 2)..
+    float acc[NJ][16];
+#pragma unroll
+    for (int jt = 0; jt < NJ; ++jt)
+#pragma unroll
+      for (int i = 0; i < 16; ++i) acc[jt][i] = 0.f;
+    uint32_t ph_empty = 0, ph_accf = 0;
+    auto drain = [&]() {
+      tc::mbar_wait(&sm.accf, ph_accf); ph_accf ^= 1u;
+      __syncwarp();
+      tc::fence_after_sync();
+#pragma unroll
+      for (int jt = 0; jt < NJ; ++jt) {
+        float t[16];
+        tc::tmem_ld16(tl + kColAcc + jt * 64 + 16 * c, t);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[jt][i] += t[i];
+      }
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&sm.acce);
+    };
+    auto step = [&](Regs& R, int it) {
+      const int s = it % kGemmSlots;
+      // the TMEM slot of this stage is free once the MMAs of stage it-3 have completed (they were submitted two stages ago)
+      if (it >= kGemmSlots) { tc::mbar_wait(&sm.empty[s], (ph_empty >> s) & 1u); ph_empty ^= 1u << s; }
+      store_tmem(R, s);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");        // this thread's weight chunk of stage `it` has landed
+      tc::tmem_st_wait();
+      tc::fence_async_smem();
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&sm.full[s]);
+      // two stages ahead: weight copy (its ring slot was last read by stage it-4) and activation loads
+      if (it + 2 < n_it) { copy_w(it + 2); load_regs(R, it + 2); }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      if ((it + 1) % kGemmGroup == 0 && it + 1 < n_it) drain();
+    };
+    copy_w(0);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    if (n_it > 1) copy_w(1);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    Regs R0, R1;
+    load_regs(R0, 0);
+    if (n_it > 1) load_regs(R1, 1);
+    for (int it = 0; it < n_it; it += 2) {
+      step(R0, it);
+      if (it + 1 < n_it) step(R1, it + 1);
+    }
+    drain();
 
-  // ---- epilogue: bias, tanh, store (a, p', p'') ----
-  const long long row = row0 + 32 * (w & 3) + lane;
-  if (row < g.B) {
-    const int jc = j0 + 32 * (w >> 2);
-    float* dst = g.Sout + (size_t)row * H + jc;
+    // ---- epilogue: bias, tanh, store (a, p', p'') ----
+    const long long row = row0 + r;
+    if (row < g.B) {
+      const int jc = j0 + 16 * c;
+      float* dst = g.Sout + sbuf_off(jc >> 2, row, g.rows_pad);
 #pragma unroll
-    for (int i = 0; i < 32; i += 4) {
-      float4 a;
-      a.x = tanh_f(acc[0][i] + g.bias[jc + i]); a.y = tanh_f(acc[0][i + 1] + g.bias[jc + i + 1]);
-      a.z = tanh_f(acc[0][i + 2] + g.bias[jc + i + 2]); a.w = tanh_f(acc[0][i + 3] + g.bias[jc + i + 3]);
-      *reinterpret_cast<float4*>(dst + i) = a;
-      if (NJ >= 2) *reinterpret_cast<float4*>(dst + jet_stride + i) = make_float4(acc[1][i], acc[1][i + 1], acc[1][i + 2], acc[1][i + 3]);
-      if (NJ == 3) *reinterpret_cast<float4*>(dst + 2 * jet_stride + i) = make_float4(acc[2][i], acc[2][i + 1], acc[2][i + 2], acc[2][i + 3]);
+      for (int i = 0; i < 16; i += 4) {
+        float4 a;
+        a.x = tanh_f(acc[0][i] + g.bias[jc + i]); a.y = tanh_f(acc[0][i + 1] + g.bias[jc + i + 1]);
+        a.z = tanh_f(acc[0][i + 2] + g.bias[jc + i + 2]); a.w = tanh_f(acc[0][i + 3] + g.bias[jc + i + 3]);
+        float* d = dst + sbuf_off(i >> 2, 0, g.rows_pad);
+        *reinterpret_cast<float4*>(d) = a;
+        if (NJ >= 2) *reinterpret_cast<float4*>(d + jet_stride) = make_float4(acc[1][i], acc[1][i + 1], acc[1][i + 2], acc[1][i + 3]);
+        if (NJ == 3) *reinterpret_cast<float4*>(d + 2 * jet_stride) = make_float4(acc[2][i], acc[2][i + 1], acc[2][i + 2], acc[2][i + 3]);
+      }
     }
   }
   tc::fence_before_sync();
@@ -213,12 +249,12 @@ __global__ void __launch_bounds__(256) mlp_glue_tc_kernel(const GlueArgs g) {
     xst = y[0]; sst = y[2];
   } else {
     float hp[3] = {0.f, 0.f, 0.f};
-    const float* s0 = g.Slast + (size_t)row * H;
     for (int k = 4 * lane; k < H; k += 128) {
-      const float4 a = *reinterpret_cast<const float4*>(s0 + k);
+      const float* s0 = g.Slast + sbuf_off(k >> 2, row, g.rows_pad);
+      const float4 a = *reinterpret_cast<const float4*>(s0);
       float4 p1 = make_float4(0, 0, 0, 0), p2 = make_float4(0, 0, 0, 0);
-      if (NJ >= 2) p1 = *reinterpret_cast<const float4*>(s0 + jet_stride + k);
-      if (NJ == 3) p2 = *reinterpret_cast<const float4*>(s0 + 2 * jet_stride + k);
+      if (NJ >= 2) p1 = *reinterpret_cast<const float4*>(s0 + jet_stride);
+      if (NJ == 3) p2 = *reinterpret_cast<const float4*>(s0 + 2 * jet_stride);
       const float av[4] = {a.x, a.y, a.z, a.w}, q1[4] = {p1.x, p1.y, p1.z, p1.w}, q2[4] = {p2.x, p2.y, p2.z, p2.w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
@@ -268,17 +304,17 @@ __global__ void __launch_bounds__(256) mlp_glue_tc_kernel(const GlueArgs g) {
     const int stage = ne & 3;
     const float cs = stage == 0 ? 0.f : (stage == 3 ? h : 0.5f * h);
     const float tp = g.y0 * (g.t0 + h * (float)(ne >> 2) + cs);
-    float* d0 = g.S0 + (size_t)row * H;
     for (int k = 4 * lane; k < H; k += 128) {
+      float* d0 = g.S0 + sbuf_off(k >> 2, row, g.rows_pad);
       float a[4], wx[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         wx[e] = g.theta[TL.w(0) + H + k + e];
         a[e] = tanh_f(fmaf(wx[e], xst, fmaf(tp, g.theta[TL.w(0) + k + e], g.theta[TL.b(0) + k + e])));
       }
-      *reinterpret_cast<float4*>(d0 + k) = make_float4(a[0], a[1], a[2], a[3]);
-      if (NJ >= 2) *reinterpret_cast<float4*>(d0 + jet_stride + k) = make_float4(wx[0], wx[1], wx[2], wx[3]);
-      if (NJ == 3) *reinterpret_cast<float4*>(d0 + 2 * jet_stride + k) = make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(d0) = make_float4(a[0], a[1], a[2], a[3]);
+      if (NJ >= 2) *reinterpret_cast<float4*>(d0 + jet_stride) = make_float4(wx[0], wx[1], wx[2], wx[3]);
+      if (NJ == 3) *reinterpret_cast<float4*>(d0 + 2 * jet_stride) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   } else if (lane == 0) {
     float* dst = g.y_out + row * g.stride;
@@ -289,7 +325,7 @@ __global__ void __launch_bounds__(256) mlp_glue_tc_kernel(const GlueArgs g) {
 }
 
 template <int NJ>
-static int run_fwd_tc(cudaStream_t st, const float* theta, const float* WTc, const float* y_in, float* y_out, float* ckpt,
+static int run_fwd_tc(cudaStream_t st, const float* theta, const float* WTc, const float* WTlo, const float* y_in, float* y_out, float* ckpt,
                       float* S0, float* S1, float* state, long long B, int stride, int H, int L, int n_steps, float t0, float t1,
                       float y0sign) {
   const long long rows_pad = (B + 127) / 128 * 128;
@@ -312,20 +348,20 @@ static int run_fwd_tc(cudaStream_t st, const float* theta, const float* WTc, con
     mlp_glue_tc_kernel<NJ><<<glue_grid, 256, 0, st>>>(ga);
     if (ev + 1 == 4 * n_steps) break;
     for (int l = 1; l < L; ++l) {
-      GemmArgs gg{bufs[(l - 1) & 1], bufs[l & 1], WTc + (size_t)(l - 1) * H * H, theta + TL.b(l), B, rows_pad, H};
-      mlp_layer_gemm_tc_kernel<NJ><<<gemm_grid, 256, sizeof(GemmSmem) + 1024, st>>>(gg);
+      GemmArgs gg{bufs[(l - 1) & 1], bufs[l & 1], WTc + (size_t)(l - 1) * H * H, WTlo + (size_t)(l - 1) * H * H, theta + TL.b(l), B, rows_pad, H};
+      mlp_layer_gemm_tc_kernel<NJ><<<gemm_grid, kGemmThreads, sizeof(GemmSmem) + 1024, st>>>(gg);
     }
   }
   return (int)cudaGetLastError();
 }
 
-int launch_mlp_fwd_tc(void* stream, const float* theta, const float* WTc, const float* y_in, float* y_out, float* ckpt,
+int launch_mlp_fwd_tc(void* stream, const float* theta, const float* WTc, const float* WTlo, const float* y_in, float* y_out, float* ckpt,
                       float* S0, float* S1, float* state, long long B, int jets, int stride, int H, int L, int n_steps,
                       float t0, float t1, float y0sign) {
   cudaStream_t st = (cudaStream_t)stream;
-  if (jets == 3) return run_fwd_tc<3>(st, theta, WTc, y_in, y_out, ckpt, S0, S1, state, B, stride, H, L, n_steps, t0, t1, y0sign);
-  if (jets == 2) return run_fwd_tc<2>(st, theta, WTc, y_in, y_out, ckpt, S0, S1, state, B, stride, H, L, n_steps, t0, t1, y0sign);
-  return run_fwd_tc<1>(st, theta, WTc, y_in, y_out, ckpt, S0, S1, state, B, stride, H, L, n_steps, t0, t1, y0sign);
+  if (jets == 3) return run_fwd_tc<3>(st, theta, WTc, WTlo, y_in, y_out, ckpt, S0, S1, state, B, stride, H, L, n_steps, t0, t1, y0sign);
+  if (jets == 2) return run_fwd_tc<2>(st, theta, WTc, WTlo, y_in, y_out, ckpt, S0, S1, state, B, stride, H, L, n_steps, t0, t1, y0sign);
+  return run_fwd_tc<1>(st, theta, WTc, WTlo, y_in, y_out, ckpt, S0, S1, state, B, stride, H, L, n_steps, t0, t1, y0sign);
 }
 
 }  // namespace mlp
