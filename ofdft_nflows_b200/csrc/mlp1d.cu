@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(256, 1) mlp_fwd_kernel(const Args a) {
 
 // aligned copies (and transposes) of the hidden kernels: theta offsets are odd, cp.async needs 16-byte sources
 __global__ void mlp_prep_kernel(const float* __restrict__ theta, float* __restrict__ Wc, float* __restrict__ WTc, int H, int L,
-                                float* __restrict__ WTlo = nullptr) {
+                                float* __restrict__ WTlo = nullptr, float* __restrict__ Wclo = nullptr) {
   const ThetaLayout TL(H, L);
   const long long n = (long long)(L - 1) * H * H;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -256,6 +256,7 @@ __global__ void mlp_prep_kernel(const float* __restrict__ theta, float* __restri
     const int r = (int)((i % ((long long)H * H)) / H), c = (int)(i % H);
     const float v = theta[TL.w(l) + r * H + c];
     Wc[i] = v;
+    if (Wclo != nullptr) Wclo[i] = tc::lo_tf32(v);
     if (WTc != nullptr) WTc[(long long)(l - 1) * H * H + (long long)c * H + r] = v;
     if (WTlo != nullptr) WTlo[(long long)(l - 1) * H * H + (long long)c * H + r] = tc::lo_tf32(v);
   }
@@ -752,7 +753,11 @@ extern "C" int ofdft_cnf_mlp1d_bwd(void* stream, const float* theta, const float
   char* sc = (char*)scratch;
   float* Wc = (float*)(sc + SL.wc); float* WTc = (float*)(sc + SL.wtc);
   float* gsmall = (float*)(sc + SL.gsmall); float* part = (float*)(sc + SL.part);
-  mlp_prep_kernel<<<256, 256, 0, st>>>(theta, Wc, WTc, H, L);
+  // OFDFT_B200_MLP_BWD = "tc" (default: adjoint sweep as per-layer tcgen05 GEMM launches, mlp1d_tc.cu) | "ffma" (fused FP32 sweep)
+  const char* envb = getenv("OFDFT_B200_MLP_BWD");
+  const bool bwd_tc = !(envb != nullptr && envb[0] == 'f');
+  float* WTlo = (float*)(sc + SL.wtlo); float* Wclo = (float*)(sc + SL.wclo);
+  mlp_prep_kernel<<<256, 256, 0, st>>>(theta, Wc, WTc, H, L, bwd_tc ? WTlo : nullptr, bwd_tc ? Wclo : nullptr);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
   const size_t smem = smem_bytes(H);
@@ -772,8 +777,20 @@ extern "C" int ofdft_cnf_mlp1d_bwd(void* stream, const float* theta, const float
     a.acts = (float*)(sc + SL.acts); a.pbar = (float*)(sc + SL.pbar); a.gsmall = gsmall;
     a.B = B; a.row_begin = r0; a.rows = rows; a.jets = 3; a.stride = stride; a.H = H; a.L = L; a.n_steps = n_steps;
     a.t0 = t0; a.t1 = t1; a.y0 = y0sign;
-    const int grid = (int)(n_tiles < sms ? n_tiles : sms);
-    mlp_bwd_sweep_kernel<<<grid, H / 2, smem, st>>>(a);
+    int grid = (int)(n_tiles < sms ? n_tiles : sms);
+    if (bwd_tc) {
+      const size_t rows_pad_c = (size_t)((rows + 127) / 128 * 128);
+      const size_t sb = al256(3 * rows_pad_c * H * 4);
+      float* S[kMaxL];
+      for (int l = 0; l < L; ++l) S[l] = (float*)(sc + SL.bwd_s + (size_t)l * sb);
+      const int rc2 = launch_mlp_bwd_sweep_tc(stream, theta, Wc, Wclo, WTc, WTlo, ckpt, ybar1, ybar0, S, (float*)(sc + SL.bwd_pb),
+                                              (float*)(sc + SL.bwd_pb + sb), (float*)(sc + SL.bwd_bst), (float*)(sc + SL.bwd_xpart),
+                                              gsmall, a.acts, a.pbar, B, r0, rows, stride, H, L, n_steps, t0, t1, y0sign);
+      if (rc2) return rc2;
+      grid = (int)n_tiles;                       // small-gradient slots: one per 8-row tile (<= 256 per chunk)
+    } else {
+      mlp_bwd_sweep_kernel<<<grid, H / 2, smem, st>>>(a);
+    }
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
     mlp_small_reduce_kernel<<<(TL.n_small() + 255) / 256, 256, 0, st>>>(gsmall, theta_bar, H, L, grid, chunk_idx > 0);

@@ -39,7 +39,7 @@ constexpr int kDwSplits = 16;
 inline size_t al256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 struct ScratchLayout {
-  size_t wc, wtc, wtlo, fwd_s, fwd_state, fwd_end, gsmall, part, acts, pbar, total;
+  size_t wc, wtc, wtlo, wclo, fwd_s, fwd_state, fwd_end, bwd_s, bwd_pb, bwd_bst, bwd_xpart, gsmall, part, acts, pbar, total;
   ScratchLayout(long long B, int H, int L, int n_steps) {
     const long long rows = B < kChunkRows ? B : kChunkRows;
     const long long n_tiles = (rows + kTT - 1) / kTT;
@@ -53,6 +53,13 @@ struct ScratchLayout {
     fwd_s = o; o += 2 * al256(3 * rows_pad * H * 4);
     fwd_state = o; o += al256(rows_pad * 8 * 4);
     fwd_end = o;
+    // tensor-core adjoint sweep (per 2048-row chunk): L layer buffers, two cotangent buffers, row state, x partials
+    const size_t rows_pad_c = (size_t)((rows + 127) / 128 * 128);
+    wclo = o; o += al256((size_t)(L - 1) * H * H * 4);
+    bwd_s = o; o += (size_t)L * al256(3 * rows_pad_c * H * 4);
+    bwd_pb = o; o += 2 * al256(3 * rows_pad_c * H * 4);
+    bwd_bst = o; o += al256(rows_pad_c * 8 * 4);
+    bwd_xpart = o; o += al256((size_t)(H / 64 > 0 ? H / 64 : 1) * rows_pad_c * 4);
     gsmall = o; o += al256((size_t)256 * ThetaLayout(H, L).n_small() * 4);
     part = o; o += al256((size_t)kDwSplits * H * H * 4);
     acts = o; o += al256((size_t)n_blocks * L * 3 * H * kTT * 4);
@@ -66,6 +73,14 @@ struct ScratchLayout {
 int launch_mlp_fwd_tc(void* stream, const float* theta, const float* WTc, const float* WTlo, const float* y_in, float* y_out, float* ckpt,
                       float* S0, float* S1, float* state, long long B, int jets, int stride, int H, int L, int n_steps,
                       float t0, float t1, float y0sign);
+
+// tensor-core adjoint sweep of one row chunk (mlp1d_tc.cu): fills the HBM blocks the weight-gradient GEMM contracts and
+// the per-CTA small-gradient partials; returns a cudaError_t / OFDFT_E* code
+int launch_mlp_bwd_sweep_tc(void* stream, const float* theta, const float* Wc, const float* Wclo, const float* WTc,
+                            const float* WTlo, const float* ckpt, const float* ybar1, float* ybar0, float* const* S,
+                            float* Pb0, float* Pb1, float* bst, float* xpart, float* gsmall, float* acts, float* pbar,
+                            long long Bglob, long long r0, long long rows, int stride, int H, int L, int n_steps, float t0,
+                            float t1, float y0sign);
 
 }  // namespace mlp
 }  // namespace ofdft
