@@ -717,6 +717,8 @@ extern "C" int ofdft_cnf_mlp1d_fwd(void* stream, const float* theta, const float
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
   if (fwd_tc) {
+    const int rcp = launch_mlp_prep_tc(stream, theta, WTc, WTlo, nullptr, nullptr, H, n_layers);
+    if (rcp) return rcp;
     const size_t sbuf = al256(3 * (size_t)((B + 127) / 128 * 128) * H * 4);
     float* S0 = (float*)((char*)scratch + SL.fwd_s);
     float* S1 = (float*)((char*)scratch + SL.fwd_s + sbuf);
@@ -779,11 +781,15 @@ extern "C" int ofdft_cnf_mlp1d_bwd(void* stream, const float* theta, const float
     a.t0 = t0; a.t1 = t1; a.y0 = y0sign;
     int grid = (int)(n_tiles < sms ? n_tiles : sms);
     if (bwd_tc) {
+      if (chunk_idx == 0) {
+        const int rcp = launch_mlp_prep_tc(stream, theta, WTc, WTlo, (float*)(sc + SL.wbi), Wclo, H, L);
+        if (rcp) return rcp;
+      }
       const size_t rows_pad_c = (size_t)((rows + 127) / 128 * 128);
       const size_t sb = al256(3 * rows_pad_c * H * 4);
       float* S[kMaxL];
       for (int l = 0; l < L; ++l) S[l] = (float*)(sc + SL.bwd_s + (size_t)l * sb);
-      const int rc2 = launch_mlp_bwd_sweep_tc(stream, theta, Wc, Wclo, WTc, WTlo, ckpt, ybar1, ybar0, S, (float*)(sc + SL.bwd_pb),
+      const int rc2 = launch_mlp_bwd_sweep_tc(stream, theta, (float*)(sc + SL.wbi), Wclo, WTc, WTlo, ckpt, ybar1, ybar0, S, (float*)(sc + SL.bwd_pb),
                                               (float*)(sc + SL.bwd_pb + sb), (float*)(sc + SL.bwd_bst), (float*)(sc + SL.bwd_xpart),
                                               gsmall, a.acts, a.pbar, B, r0, rows, stride, H, L, n_steps, t0, t1, y0sign);
       if (rc2) return rc2;

@@ -39,7 +39,7 @@ constexpr int kDwSplits = 16;
 inline size_t al256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 struct ScratchLayout {
-  size_t wc, wtc, wtlo, wclo, fwd_s, fwd_state, fwd_end, bwd_s, bwd_pb, bwd_bst, bwd_xpart, gsmall, part, acts, pbar, total;
+  size_t wc, wtc, wtlo, wclo, wbi, fwd_s, fwd_state, fwd_end, bwd_s, bwd_pb, bwd_bst, bwd_xpart, gsmall, part, acts, pbar, total;
   ScratchLayout(long long B, int H, int L, int n_steps) {
     const long long rows = B < kChunkRows ? B : kChunkRows;
     const long long n_tiles = (rows + kTT - 1) / kTT;
@@ -56,6 +56,7 @@ struct ScratchLayout {
     // tensor-core adjoint sweep (per 2048-row chunk): L layer buffers, two cotangent buffers, row state, x partials
     const size_t rows_pad_c = (size_t)((rows + 127) / 128 * 128);
     wclo = o; o += al256((size_t)(L - 1) * H * H * 4);
+    wbi = o; o += al256((size_t)(L - 1) * H * H * 4);
     bwd_s = o; o += (size_t)L * al256(3 * rows_pad_c * H * 4);
     bwd_pb = o; o += 2 * al256(3 * rows_pad_c * H * 4);
     bwd_bst = o; o += al256(rows_pad_c * 8 * 4);
@@ -70,6 +71,9 @@ struct ScratchLayout {
 
 
 // tensor-core forward integrator (mlp1d_tc.cu): per-layer tcgen05 GEMM launches; returns a cudaError_t / OFDFT_E* code
+// interleaved [k/4][n][4] copies of the hidden kernels for the TMA-fed GEMM: forward operand (n = output unit), adjoint
+// operand (n = input unit), each with its tf32 remainder
+int launch_mlp_prep_tc(void* stream, const float* theta, float* Wf, float* Wf_lo, float* Wb, float* Wb_lo, int H, int L);
 int launch_mlp_fwd_tc(void* stream, const float* theta, const float* WTc, const float* WTlo, const float* y_in, float* y_out, float* ckpt,
                       float* S0, float* S1, float* state, long long B, int jets, int stride, int H, int L, int n_steps,
                       float t0, float t1, float y0sign);

@@ -26,12 +26,11 @@ constexpr int kGemmKC = 16;                       // k per pipeline stage (4 chu
 constexpr int kGemmGroup = 16;                    // stages per TMEM accumulation chain (256 k, 96 MMAs per jet); measured max
                                                   // state error vs the float64 oracle (3x512): 6e-7 / 1.1e-6 / 1.7e-6 for 8 / 16 / 32
 constexpr int kGemmSlots = 3;                     // activation-operand ring in tensor memory
-constexpr int kGemmWSlots = 6;                    // weight-operand ring in shared memory (deeper: its copies are issued two
-                                                  // stages ahead and must never wait on an MMA that was only just submitted)
-constexpr int kLboB = 64 * 16 + 32;               // chunk stride of the weight operand (bytes; +32: conflict-free stores)
+constexpr int kGemmRaw = 4;                       // shared-memory ring fed by TMA bulk copies: raw activation jets + weight stage
+constexpr int kLboB = 64 * 16;                    // chunk stride of the weight operand (bytes): 64 rows x 16 B, as TMA lays it
 constexpr int kColAcc = 0;                        // TMEM: accumulators 3 jets x 64 columns
 constexpr int kColOp = 192;                       // TMEM: operand ring, per slot [jet][hi 16 | lo 16] = 96 columns
-constexpr int kGemmThreads = 512 + 32;            // 16 staging warps + 1 MMA warp (17 warps: at most 96 registers per thread)
+constexpr int kGemmThreads = 512 + 64;            // 16 staging warps + MMA warp + TMA warp (18 warps: at most 96 registers/thread)
 
 // layer buffers: [jet: a, p', p''][unit / 4][row (padded to 128)][4 units] -- 32 consecutive rows x 4 units are 512
 // contiguous bytes, which is what a warp whose lanes are rows (the TMEM lane constraint) loads or stores at once
@@ -40,15 +39,17 @@ __host__ __device__ __forceinline__ size_t sbuf_off(int unit_group, long long ro
 }
 
 struct GemmSmem {
-  float W[kGemmWSlots][2][4 * (kLboB / 4)];       // [slot][hi/lo][chunk][row j 64][4]
+  float4 A[kGemmRaw][3][4][128];                  // [slot][jet][k chunk][row]: (a, p', p'') or cotangent jets as stored
+  float W[kGemmRaw][2][4 * 64 * 4];               // [slot][hi/lo][k chunk][row n 64][4]: canonical K-major UMMA operand
   float red[1024];                                // adjoint epilogues: cross-warp column sums / x partials
+  uint64_t rfull[kGemmRaw], rempty[kGemmRaw];     // TMA -> consumers (tx bytes) / consumers -> TMA (16 stager warps + 1 commit)
   uint64_t full[kGemmSlots], empty[kGemmSlots], accf, acce;
   unsigned int tmem_slot;
 };
 
 struct GemmArgs {
   const float* Sin; float* Sout;                  // layer buffers (A operand source / epilogue destination)
-  const float* WT; const float* WTlo;             // B operand [n][k], k contiguous (unrounded) and its tf32 remainder
+  const float* WT; const float* WTlo;             // B operand, interleaved [k/4][n][4] (unrounded) and its tf32 remainder
   const float* bias;                              // MODE 0: [H] (theta offset: may be unaligned -> scalar loads)
   long long B, rows_pad; int H;                   // B: valid rows of this chunk
   // adjoint sweep only
@@ -81,6 +82,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) mlp_layer_gemm_tc_kernel(cons
   const int j0 = blockIdx.y * 64;
   if (tid == 0) {
     for (int i = 0; i < kGemmSlots; ++i) { tc::mbar_init(&sm.full[i], 16); tc::mbar_init(&sm.empty[i], 1); }
+    for (int i = 0; i < kGemmRaw; ++i) { tc::mbar_init(&sm.rfull[i], 1); tc::mbar_init(&sm.rempty[i], 17); }
     tc::mbar_init(&sm.accf, 1); tc::mbar_init(&sm.acce, 16);
     tc::fence_mbar_init();
   }
@@ -104,8 +106,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) mlp_layer_gemm_tc_kernel(cons
       __syncwarp();
       tc::fence_after_sync();
       if (tc::elect_one()) {
-        const uint64_t wh = tc::make_desc(tc::smem_u32(sm.W[it % kGemmWSlots][0]), kLboB, 128);
-        const uint64_t wl = tc::make_desc(tc::smem_u32(sm.W[it % kGemmWSlots][1]), kLboB, 128);
+        const uint64_t wh = tc::make_desc(tc::smem_u32(sm.W[it % kGemmRaw][0]), kLboB, 128);
+        const uint64_t wl = tc::make_desc(tc::smem_u32(sm.W[it % kGemmRaw][1]), kLboB, 128);
 #pragma unroll
         for (int jt = 0; jt < NJ; ++jt) {
           const uint32_t ahi = tmem + kColOp + 96 * s + 32 * jt, alo = ahi + 16;
@@ -117,25 +119,43 @@ __global__ void __launch_bounds__(kGemmThreads, 1) mlp_layer_gemm_tc_kernel(cons
                               idesc, !(first && p == 0 && ks == 0));
         }
         tc::commit(&sm.empty[s]);
+        tc::commit(&sm.rempty[it % kGemmRaw]);                 // the weight stage of this ring slot has been read
         if ((it + 1) % kGemmGroup == 0 || it + 1 == n_it) tc::commit(&sm.accf);
       }
       __syncwarp();
     }
+  } else if (w == 17) {
+    // ---------------- TMA warp: bulk copies global/L2 -> shared-memory ring ----------------
+    // per stage: 3 jets x 4 unit groups x (128 rows x 16 B = 2 KB contiguous in the interleaved layer buffer) and
+    // (hi, lo) x 4 k groups x (64 rows x 16 B = 1 KB contiguous in the interleaved weight copy)
+    if (tc::elect_one()) {
+      uint32_t ph = 0;
+      for (int it = 0; it < n_it; ++it) {
+        const int s = it % kGemmRaw;
+        if (it >= kGemmRaw) { tc::mbar_wait(&sm.rempty[s], (ph >> s) & 1u); ph ^= 1u << s; }
+        tc::mbar_arrive_expect_tx(&sm.rfull[s], (uint32_t)(NJ * 4 * 2048 + 2 * 4 * 1024));
+#pragma unroll
+        for (int jt = 0; jt < NJ; ++jt)
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            tc::bulk_g2s(&sm.A[s][jt][c][0], g.Sin + jt * jet_stride + sbuf_off(4 * it + c, row0, g.rows_pad), 2048, &sm.rfull[s]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const size_t off = ((size_t)(4 * it + c) * H + j0) * 4;
+          tc::bulk_g2s(&sm.W[s][0][c * 256], g.WT + off, 1024, &sm.rfull[s]);
+          tc::bulk_g2s(&sm.W[s][1][c * 256], g.WTlo + off, 1024, &sm.rfull[s]);
+        }
+      }
+    }
+    __syncwarp();
   } else {
     // ---------------- staging warps ----------------
     const int r = 32 * (w & 3) + lane, c = w >> 2;          // row (TMEM lane) and k chunk of this thread
-    const float* a_src = g.Sin + sbuf_off(c, row0 + r, g.rows_pad);       // + 4 unit groups per stage
-    const size_t stage_stride = sbuf_off(4, 0, g.rows_pad);
     const uint32_t tl = tmem + ((uint32_t)(32 * (w & 3)) << 16);
-    // weight stage: 64 rows x 4 chunks x (hi, lo) = 512 16-byte copies, one per thread
-    const int wj = (tid & 255) >> 2, wc = tid & 3, wpart = tid >> 8;
-    const float* w_src = (wpart ? g.WTlo : g.WT) + (size_t)(j0 + wj) * H + 4 * wc;
-    const int offw = wc * (kLboB / 4) + wj * 4;
-    auto copy_w = [&](int it) { cp_async16(&sm.W[it % kGemmWSlots][wpart][offw], w_src + it * kGemmKC); };
     struct Regs { float4 a[3]; };
     auto load_regs = [&](Regs& R, int it) {
 #pragma unroll
-      for (int jt = 0; jt < NJ; ++jt) R.a[jt] = *reinterpret_cast<const float4*>(a_src + jt * jet_stride + it * stage_stride);
+      for (int jt = 0; jt < NJ; ++jt) R.a[jt] = sm.A[it % kGemmRaw][jt][c][r];
     };
     auto store_tmem = [&](const Regs& R, int s) {
       const uint32_t base = tl + kColOp + 96 * s + 4 * c;
@@ -187,32 +207,20 @@ __global__ void __launch_bounds__(kGemmThreads, 1) mlp_layer_gemm_tc_kernel(cons
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&sm.acce);
     };
-    auto step = [&](Regs& R, int it) {
-      const int s = it % kGemmSlots;
-      // the TMEM slot of this stage is free once the MMAs of stage it-3 have completed (they were submitted two stages ago)
+    uint32_t ph_rfull = 0;
+    for (int it = 0; it < n_it; ++it) {
+      const int s = it % kGemmSlots, rs = it % kGemmRaw;
+      tc::mbar_wait(&sm.rfull[rs], (ph_rfull >> rs) & 1u); ph_rfull ^= 1u << rs;          // TMA data of this stage has landed
+      Regs R;
+      load_regs(R, it);
+      // the TMEM slot of this stage is free once the MMAs of stage it-3 have completed
       if (it >= kGemmSlots) { tc::mbar_wait(&sm.empty[s], (ph_empty >> s) & 1u); ph_empty ^= 1u << s; }
       store_tmem(R, s);
-      asm volatile("cp.async.wait_group 1;" ::: "memory");        // this thread's weight chunk of stage `it` has landed
       tc::tmem_st_wait();
-      tc::fence_async_smem();
       tc::fence_before_sync();
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&sm.full[s]);
-      // two stages ahead: weight copy (its ring slot was last read by stage it-4) and activation loads
-      if (it + 2 < n_it) { copy_w(it + 2); load_regs(R, it + 2); }
-      asm volatile("cp.async.commit_group;" ::: "memory");
+      if (lane == 0) { tc::mbar_arrive(&sm.full[s]); tc::mbar_arrive(&sm.rempty[rs]); }
       if ((it + 1) % kGemmGroup == 0 && it + 1 < n_it) drain();
-    };
-    copy_w(0);
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    if (n_it > 1) copy_w(1);
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    Regs R0, R1;
-    load_regs(R0, 0);
-    if (n_it > 1) load_regs(R1, 1);
-    for (int it = 0; it < n_it; it += 2) {
-      step(R0, it);
-      if (it + 1 < n_it) step(R1, it + 1);
     }
     drain();
 
@@ -685,6 +693,27 @@ int launch_mlp_bwd_sweep_tc(void* stream, const float* theta, const float* Wc, c
     }
     // the head of the next stage writes Pb0 again; MODE 1 outputs alternate between the two buffers
   }
+  return (int)cudaGetLastError();
+}
+
+__global__ void mlp_prep_tc_kernel(const float* __restrict__ theta, float* __restrict__ Wf, float* __restrict__ Wf_lo,
+                                   float* __restrict__ Wb, float* __restrict__ Wb_lo, int H, int L) {
+  const ThetaLayout TL(H, L);
+  const long long n = (long long)(L - 1) * H * H;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int l = (int)(i / ((long long)H * H)) + 1;
+    const int k = (int)((i % ((long long)H * H)) / H), j = (int)(i % H);       // W_l[k][j], (in, out)
+    const float v = theta[TL.w(l) + k * H + j];
+    const size_t base = (size_t)(l - 1) * H * H;
+    const size_t of = base + ((size_t)(k >> 2) * H + j) * 4 + (k & 3);         // forward: contraction over k, rows n = j
+    const size_t ob = base + ((size_t)(j >> 2) * H + k) * 4 + (j & 3);         // adjoint: contraction over j, rows n = k
+    Wf[of] = v; Wf_lo[of] = tc::lo_tf32(v);
+    if (Wb != nullptr) { Wb[ob] = v; Wb_lo[ob] = tc::lo_tf32(v); }
+  }
+}
+
+int launch_mlp_prep_tc(void* stream, const float* theta, float* Wf, float* Wf_lo, float* Wb, float* Wb_lo, int H, int L) {
+  mlp_prep_tc_kernel<<<256, 256, 0, (cudaStream_t)stream>>>(theta, Wf, Wf_lo, Wb, Wb_lo, H, L);
   return (int)cudaGetLastError();
 }
 
