@@ -178,6 +178,12 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def _launches_1d(n: int, L: int) -> int:
+    fwd = 2 + (n + 1) + n * (L - 1) if os.environ.get("OFDFT_B200_MLP_FWD", "tc")[0] != "f" else 2
+    bwd = 2 + (n + 1) + n + 2 * n * (L - 1) if os.environ.get("OFDFT_B200_MLP_BWD", "tc")[0] != "f" else 2
+    return fwd + 2 + bwd + 1 + 2 * (L - 1)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -316,7 +322,36 @@ def main():
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    if tensor_path:
+    mlp_tc = is_1d and all(os.environ.get(k, "tc")[0] != "f" for k in ("OFDFT_B200_MLP_FWD", "OFDFT_B200_MLP_BWD", "OFDFT_B200_MLP_DW"))
+    if mlp_tc:
+        # 1-D flow, tensor-core path: every hidden-layer GEMM launch executes (rows padded to 128) x H x H x 3 jets x
+        # 3 passes; the adjoint adds the recompute and the transposed GEMMs, the weight gradients a stacked [hi|lo] GEMM
+        # with two passes over n_evals x B x 3 jets contraction rows.
+        Hm, L = MLP_FEAT[0], len(MLP_FEAT)
+        rows_pad = math.ceil(B / 128) * 128
+        gemm = 2.0 * rows_pad * Hm * Hm * 3 * 3
+        fwd_tensor_flops = evals * (L - 1) * gemm
+        dw_flops = (L - 1) * 2.0 * (2 * Hm) * Hm * (evals * math.ceil(B / 8) * 8 * 3) * 2
+        bwd_tensor_flops = 2.0 * evals * (L - 1) * gemm + dw_flops
+        tf32_peak = 0.5 * peaks.get("bf16_tflops_sustained", 1400.0)
+        roofline = {
+            "bound": "tensor", "kernel": "mlp_layer_gemm_tc_kernel (+ mlp_dw_gemm_tc_kernel) launches of the adjoint",
+            "achieved": bwd_tensor_flops / bwd_s / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
+            "frac": bwd_tensor_flops / bwd_s / 1e12 / tf32_peak, "traffic": None,
+            "peak_source": ("1/2 x bf16_tflops_sustained of MEASURED_PEAKS.json (dense TF32 rate; of measured)" if peaks else
+                            "1/2 x 1.4 PFLOP/s (B200_PROFILING.md fallback; of fallback)"),
+            "executed_tensor_flops_per_launch": bwd_tensor_flops,
+            "note": "3xTF32; one launch per hidden layer and RHS evaluation (a 128-row x 512-unit layer with three jets does "
+                    "not fit on chip); 64 of 148 SMs busy at bs=512 -- see DESIGN.md section 3c",
+            "fp32_equivalent": {"algorithmic_flops_per_launch": bwd_flops, "achieved": bwd_flops / bwd_s / 1e12,
+                                "ffma_peak": ffma_peak / 1e12, "frac_of_ffma_peak": bwd_flops / bwd_s / ffma_peak,
+                                "peak_source": "ofdft_microbench_ffma measured in this run"},
+            "kernel_ms": kern_avg,
+            "fwd": {"kernel": "mlp_layer_gemm_tc_kernel + mlp_glue_tc_kernel", "achieved": fwd_tensor_flops / fwd_s / 1e12,
+                    "frac": fwd_tensor_flops / fwd_s / 1e12 / tf32_peak, "fp32_equivalent_frac_of_ffma_peak": fwd_flops / fwd_s / ffma_peak},
+            "step": {"algorithmic_flops": 3.0 * fwd_flops, "frac_of_ffma_peak": 3.0 * fwd_flops / (total_s / args.steps) / ffma_peak},
+        }
+    elif tensor_path:
         # tcgen05 kernels: the GEMM phases run as 3xTF32 on the tensor pipe.  Executed tensor work per launch =
         # MMAs issued x (2*128*64*8 flop); peak = dense TF32 = 1/2 of the MEASURED sustained bf16 figure (the kernel is
         # timed inside the step loop), else 1/2 of the profiling guide's 1.4 PFLOP/s fallback.
@@ -386,13 +421,11 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "trajectories/s", "h2d_bytes_per_step": int(host_batch.numel() * 4),
                     "d2h_bytes_per_step": int(host_sums.numel() * 8 + host_grad.numel() * 4)},
-            # 3-D: fwd, functionals x2, bwd, gradient reduce.  1-D: forward = weight prep + (4 n_steps + 1) glue launches +
-            # 4 n_steps (L-1) layer-GEMM launches (tcgen05 path); functionals x2; backward = prep + sweep + small reduce +
-            # (L-1) x (weight-gradient GEMM + reduce)
-            "gpu_launches": (5 if not is_1d else
-                             (1 + (4 * args.n_steps + 1) + 4 * args.n_steps * (len(MLP_FEAT) - 1)
-                              if os.environ.get("OFDFT_B200_MLP_FWD", "tc")[0] != "f" else 2)
-                             + 2 + 3 + 2 * (len(MLP_FEAT) - 1)) * args.steps,
+            # 3-D: fwd, functionals x2, bwd, gradient reduce.  1-D (n = 4 n_steps evaluations, L-1 hidden GEMM layers):
+            #   forward  tc: 2 weight preps + (n+1) glue + n (L-1) layer GEMMs          | ffma: prep + fused kernel
+            #   adjoint  tc: 2 preps + (n+1) tail + n head + 2 n (L-1) layer GEMMs      | ffma: prep + fused sweep
+            #   both: functionals x2, small-gradient reduce, (L-1) x (weight-gradient GEMM + reduce)
+            "gpu_launches": (5 if not is_1d else _launches_1d(4 * args.n_steps, len(MLP_FEAT))) * args.steps,
             "roofline": roofline,
             "energy_terms_last_step": [float(v) for v in sums.cpu().numpy()[:6]],
             "hartree": ({"mode": "paired"} if args.hartree == "paired" else
