@@ -654,6 +654,129 @@ __global__ void __launch_bounds__(256, 2) mlp_dw_gemm_tc_kernel(const float* __r
   if (w == 0) tc::tmem_dealloc(tmem, 64);
 }
 
+// ------------------------------------------------------------------------------------------------
+// 128 x 128 output tiles (H a multiple of 128): the 64 x 64 kernel above re-reads every HBM block for 8 column tiles and
+// is bound by that traffic (6.4 GB per layer at H = 512, B = 1024, RK4x16); this one halves it.  Per (block, jet):
+//   D[k 128][j 128] += A_hi . P_hi + A_lo . P_hi + A_hi . P_lo        (three M128 N128 K8 MMAs; the lo.lo term is dropped)
+// one HBM block per 48 KB stage, two stages, two CTAs per SM, 16 tiles x 16 splits; the TMEM chain is drained into fp32
+// registers every kDw2Flush stages.
+// ------------------------------------------------------------------------------------------------
+constexpr int kDw2Flush = 32;     // 32 x 9 = 288 MMAs per chain (the chain length the 3-D backward kernel uses per stage)
+struct Dw2Stage {
+  float Ah[3][2 * 128 * 4], Al[3][2 * 128 * 4];   // [jet][chunk of 4 traj][row k 128][4]
+  float Ph[3][2 * 128 * 4], Pl[3][2 * 128 * 4];   // [jet][chunk][row j 128][4]
+};
+struct Dw2Smem {
+  Dw2Stage st[2];
+  uint64_t bar[2];
+  unsigned int tmem_slot;
+};
+
+__global__ void __launch_bounds__(256, 2) mlp_dw_gemm_tc128_kernel(const float* __restrict__ acts, const float* __restrict__ pbar,
+                                                                  float* __restrict__ part, int H, int L, int layer,
+                                                                  long long n_blocks, int splits) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  Dw2Smem& sm = *reinterpret_cast<Dw2Smem*>(smem_raw);
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  const int k0 = blockIdx.x * 128, j0 = blockIdx.y * 128, sp = blockIdx.z;
+  if (tid == 0) { tc::mbar_init(&sm.bar[0], 1); tc::mbar_init(&sm.bar[1], 1); tc::fence_mbar_init(); }
+  if (w == 0) tc::tmem_alloc(&sm.tmem_slot, 128);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = sm.tmem_slot;
+  const uint32_t idesc = tc::make_idesc_tf32(128, 128, 0, 0);
+  const long long per = (n_blocks + splits - 1) / splits;
+  const long long b_begin = sp * per, b_end = b_begin + per < n_blocks ? b_begin + per : n_blocks;
+  const long long n_it = b_end > b_begin ? b_end - b_begin : 0;
+  float acc[64];                                   // row 32 (w & 3) + lane, columns 64 (w >> 2) ..
+#pragma unroll
+  for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+  uint32_t phase = 0, pending = 0;
+  int in_group = 0;
+  const int u = tid & 127, c = tid >> 7;           // unit row of the tile, trajectory chunk
+  for (long long it = 0; it < n_it; ++it) {
+    const int s = (int)(it & 1);
+    if (pending & (1u << s)) { tc::mbar_wait(&sm.bar[s], (phase >> s) & 1u); phase ^= 1u << s; pending &= ~(1u << s); }
+    Dw2Stage& S = sm.st[s];
+    const long long blk = b_begin + it;
+    {
+      const float* src = acts + act_blk(blk, layer - 1, H, L) + (size_t)(k0 + u) * kTT + 4 * c;
+      const float4 av = *reinterpret_cast<const float4*>(src);
+      const float4 p1 = *reinterpret_cast<const float4*>(src + (size_t)H * kTT);
+      const float4 p2 = *reinterpret_cast<const float4*>(src + (size_t)2 * H * kTT);
+      const float a0[4] = {av.x, av.y, av.z, av.w}, q1[4] = {p1.x, p1.y, p1.z, p1.w}, q2[4] = {p2.x, p2.y, p2.z, p2.w};
+      float j1[4], j2[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float sg = fmaf(-a0[e], a0[e], 1.0f);
+        j1[e] = sg * q1[e];
+        j2[e] = fmaf(sg, q2[e], -2.0f * a0[e] * j1[e] * q1[e]);
+      }
+      const int off = (c * 128 + u) * 4;
+      *reinterpret_cast<float4*>(&S.Ah[0][off]) = av;
+      *reinterpret_cast<float4*>(&S.Al[0][off]) = make_float4(tc::lo_tf32(a0[0]), tc::lo_tf32(a0[1]), tc::lo_tf32(a0[2]), tc::lo_tf32(a0[3]));
+      *reinterpret_cast<float4*>(&S.Ah[1][off]) = make_float4(j1[0], j1[1], j1[2], j1[3]);
+      *reinterpret_cast<float4*>(&S.Al[1][off]) = make_float4(tc::lo_tf32(j1[0]), tc::lo_tf32(j1[1]), tc::lo_tf32(j1[2]), tc::lo_tf32(j1[3]));
+      *reinterpret_cast<float4*>(&S.Ah[2][off]) = make_float4(j2[0], j2[1], j2[2], j2[3]);
+      *reinterpret_cast<float4*>(&S.Al[2][off]) = make_float4(tc::lo_tf32(j2[0]), tc::lo_tf32(j2[1]), tc::lo_tf32(j2[2]), tc::lo_tf32(j2[3]));
+      const float* psrc = pbar + pb_blk(blk, layer, H, L) + (size_t)(j0 + u) * kTT + 4 * c;
+#pragma unroll
+      for (int jt = 0; jt < 3; ++jt) {
+        const float4 v = *reinterpret_cast<const float4*>(psrc + (size_t)jt * H * kTT);
+        *reinterpret_cast<float4*>(&S.Ph[jt][off]) = v;
+        *reinterpret_cast<float4*>(&S.Pl[jt][off]) = make_float4(tc::lo_tf32(v.x), tc::lo_tf32(v.y), tc::lo_tf32(v.z), tc::lo_tf32(v.w));
+      }
+    }
+    tc::fence_async_smem();
+    __syncthreads();
+    if (w == 0) {
+      tc::fence_after_sync();
+      if (tc::elect_one()) {
+#pragma unroll
+        for (int jt = 0; jt < 3; ++jt) {
+          const uint64_t ah = tc::make_desc(tc::smem_u32(S.Ah[jt]), 128 * 16, 128), al = tc::make_desc(tc::smem_u32(S.Al[jt]), 128 * 16, 128);
+          const uint64_t ph = tc::make_desc(tc::smem_u32(S.Ph[jt]), 128 * 16, 128), pl = tc::make_desc(tc::smem_u32(S.Pl[jt]), 128 * 16, 128);
+          tc::mma_tf32(tmem, ah, ph, idesc, (in_group | jt) != 0);
+          tc::mma_tf32(tmem, al, ph, idesc, true);
+          tc::mma_tf32(tmem, ah, pl, idesc, true);
+        }
+        tc::commit(&sm.bar[s]);
+      }
+      __syncwarp();
+    }
+    pending |= 1u << s;
+    ++in_group;
+    if (in_group == kDw2Flush || it == n_it - 1) {
+#pragma unroll
+      for (int s2 = 0; s2 < 2; ++s2)
+        if (pending & (1u << s2)) { tc::mbar_wait(&sm.bar[s2], (phase >> s2) & 1u); phase ^= 1u << s2; pending &= ~(1u << s2); }
+      __syncwarp();
+      tc::fence_after_sync();
+#pragma unroll
+      for (int c0 = 0; c0 < 64; c0 += 16) {
+        float t[16];
+        tc::tmem_ld16(tmem + ((uint32_t)(32 * (w & 3)) << 16) + 64 * (w >> 2) + c0, t);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[c0 + i] += t[i];
+      }
+      tc::fence_before_sync();
+      __syncthreads();
+      in_group = 0;
+    }
+  }
+  {
+    const int r = 32 * (w & 3) + lane;
+    float* out = part + ((size_t)sp * H + (k0 + r)) * H + j0 + 64 * (w >> 2);
+#pragma unroll
+    for (int i = 0; i < 64; i += 4) *reinterpret_cast<float4*>(out + i) = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (w == 0) tc::tmem_dealloc(tmem, 128);
+}
+
 // theta_bar[w(l) + i] (+)= sum_splits part[s][i]
 __global__ void mlp_dw_reduce_kernel(const float* __restrict__ part, float* __restrict__ theta_bar, int off, int n, int splits,
                                      int accumulate) {
@@ -806,9 +929,15 @@ extern "C" int ofdft_cnf_mlp1d_bwd(void* stream, const float* theta, const float
     if (dw_tc) {
       e = cudaFuncSetAttribute(mlp_dw_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DwSmem) + 1024);
       if (e != cudaSuccess) return (int)e;
+      e = cudaFuncSetAttribute(mlp_dw_gemm_tc128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Dw2Smem) + 1024);
+      if (e != cudaSuccess) return (int)e;
     }
     for (int l = 1; l < L; ++l) {
-      if (dw_tc) {
+      if (dw_tc && H % 128 == 0) {
+        dim3 gg(H / 128, H / 128, kDwSplits);
+        mlp_dw_gemm_tc128_kernel<<<gg, 256, sizeof(Dw2Smem) + 1024, st>>>(a.acts, a.pbar, part, H, L, l, n_blocks, kDwSplits);
+        mlp_dw_reduce_kernel<<<(H * H + 255) / 256, 256, 0, st>>>(part, theta_bar, TL.w(l), H * H, kDwSplits, chunk_idx > 0);
+      } else if (dw_tc) {
         dim3 gg(H / 64, H / 64, kDwTcSplits);
         mlp_dw_gemm_tc_kernel<<<gg, 256, sizeof(DwSmem) + 1024, st>>>(a.acts, a.pbar, part, H, L, l, n_blocks, kDwTcSplits);
         mlp_dw_reduce_kernel<<<(H * H + 255) / 256, 256, 0, st>>>(part, theta_bar, TL.w(l), H * H, 2 * kDwTcSplits, chunk_idx > 0);
