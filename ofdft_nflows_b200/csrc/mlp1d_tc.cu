@@ -347,27 +347,39 @@ struct GlueArgs {
   long long B, rows_pad; int stride, H, L, n_steps, eval; float t0, t1, y0;
 };
 
+// Thread mapping of the row kernels: one CTA per tile of 8 trajectories, thread = (row t = tid & 7, unit-group slot
+// tid >> 3); a warp then touches 4 unit groups x (8 rows x 16 B = 128 contiguous bytes) of an interleaved layer buffer and
+// 32-byte runs of an HBM block.  Sums over units: shuffles across the 4 lanes of a row, then across the 8 warps through
+// shared memory; sums over the 8 rows of a tile: shuffles across lanes 0..7.
+__device__ __forceinline__ float row_lanes_sum(float v) {      // over the 4 lanes that share a row within a warp
+  v += __shfl_xor_sync(0xffffffffu, v, 8);
+  v += __shfl_xor_sync(0xffffffffu, v, 16);
+  return v;
+}
+__device__ __forceinline__ float tile_rows_sum(float v) {      // over the 8 rows of the tile (lanes t = 0..7)
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  return v;
+}
+
 template <int NJ>
 __global__ void __launch_bounds__(256) mlp_glue_tc_kernel(const GlueArgs g) {
-  const int lane = threadIdx.x & 31;
-  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (row >= g.B) return;
+  __shared__ float part[3][8][8];                 // [quantity][warp][row]
+  __shared__ float bc[8][2];                      // per row: x and s of the next stage
+  const int tid = threadIdx.x, t = tid & 7, gs = tid >> 3, wp = tid >> 5;
+  const long long row = (long long)blockIdx.x * 8 + t;
+  const bool valid = row < g.B;
+  const long long rowc = valid ? row : g.B - 1;
   const int H = g.H;
   const ThetaLayout TL(H, g.L);
   const size_t jet_stride = (size_t)g.rows_pad * H;
   const float h = (g.t1 - g.t0) / (float)g.n_steps;
-  float* st = g.state + row * 8;                 // y[3], accw[3], x_stage, s_stage
-  float y[3] = {0, 0, 0}, accw[3] = {0, 0, 0}, xst, sst = 0.f;
-  if (g.eval < 0) {
-    const float* src = g.y_in + row * g.stride;
-    y[0] = src[0];
-    if (NJ >= 2) y[1] = src[1];
-    if (NJ == 3) y[2] = src[2];
-    xst = y[0]; sst = y[2];
-  } else {
+  if (g.eval >= 0) {
     float hp[3] = {0.f, 0.f, 0.f};
-    for (int k = 4 * lane; k < H; k += 128) {
-      const float* s0 = g.Slast + sbuf_off(k >> 2, row, g.rows_pad);
+    for (int grp = gs; grp < H / 4; grp += 32) {
+      const int k = 4 * grp;
+      const float* s0 = g.Slast + sbuf_off(grp, rowc, g.rows_pad);
       const float4 a = *reinterpret_cast<const float4*>(s0);
       float4 p1 = make_float4(0, 0, 0, 0), p2 = make_float4(0, 0, 0, 0);
       if (NJ >= 2) p1 = *reinterpret_cast<const float4*>(s0 + jet_stride);
@@ -383,61 +395,85 @@ __global__ void __launch_bounds__(256) mlp_glue_tc_kernel(const GlueArgs g) {
         if (NJ == 3) hp[2] = fmaf(wl, fmaf(sg, q2[e], -2.0f * av[e] * a1 * q1[e]), hp[2]);
       }
     }
-    const float h0 = warp_sum(hp[0]) + g.theta[0];
-    const float h1 = NJ >= 2 ? warp_sum(hp[1]) : 0.f;
-    const float h2 = NJ == 3 ? warp_sum(hp[2]) : 0.f;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) { y[c] = st[c]; accw[c] = st[3 + c]; }
-    sst = st[7];
-    float k[3];
-    k[0] = g.y0 * h0; k[1] = -g.y0 * h1; k[2] = -g.y0 * (h1 * sst + h2);
-    const int stage = g.eval & 3;
-    const float wgt = (stage == 0 || stage == 3) ? 1.0f : 2.0f;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) accw[c] = fmaf(wgt, k[c], accw[c]);
-    if (stage < 3) {
-      const float cs = stage == 2 ? h : 0.5f * h;
-      xst = fmaf(cs, k[0], y[0]);
-      sst = fmaf(cs, k[2], y[2]);
-    } else {
-#pragma unroll
-      for (int c = 0; c < 3; ++c) { y[c] = fmaf(h * (1.0f / 6.0f), accw[c], y[c]); accw[c] = 0.f; }
+    for (int q = 0; q < 3; ++q) {
+      const float v = row_lanes_sum(hp[q]);
+      if ((tid & 31) < 8) part[q][wp][t] = v;
+    }
+  }
+  __syncthreads();
+  if (tid < 8) {                                  // thread t owns the RK4 state of row t
+    float* st = g.state + rowc * 8;               // y[3], accw[3], x_stage, s_stage
+    float y[3] = {0, 0, 0}, accw[3] = {0, 0, 0}, xst, sst = 0.f;
+    if (g.eval < 0) {
+      const float* src = g.y_in + rowc * g.stride;
+      y[0] = src[0];
+      if (NJ >= 2) y[1] = src[1];
+      if (NJ == 3) y[2] = src[2];
       xst = y[0]; sst = y[2];
+    } else {
+      float h0 = g.theta[0], h1 = 0.f, h2 = 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { h0 += part[0][q][t]; h1 += part[1][q][t]; h2 += part[2][q][t]; }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { y[c] = st[c]; accw[c] = st[3 + c]; }
+      sst = st[7];
+      float k[3];
+      k[0] = g.y0 * h0; k[1] = -g.y0 * h1; k[2] = -g.y0 * (h1 * sst + h2);
+      const int stage = g.eval & 3;
+      const float wgt = (stage == 0 || stage == 3) ? 1.0f : 2.0f;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) accw[c] = fmaf(wgt, k[c], accw[c]);
+      if (stage < 3) {
+        const float cs = stage == 2 ? h : 0.5f * h;
+        xst = fmaf(cs, k[0], y[0]);
+        sst = fmaf(cs, k[2], y[2]);
+      } else {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { y[c] = fmaf(h * (1.0f / 6.0f), accw[c], y[c]); accw[c] = 0.f; }
+        xst = y[0]; sst = y[2];
+      }
+    }
+    bc[t][0] = xst; bc[t][1] = sst;
+    if (valid) {
+      const int ne = g.eval + 1;
+      if (ne < 4 * g.n_steps) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { st[c] = y[c]; st[3 + c] = accw[c]; }
+        st[6] = xst; st[7] = sst;
+        if (g.ckpt != nullptr) {
+          float* ck = g.ckpt + ((long long)ne * 2) * g.B + row;
+          ck[0] = xst;
+          if (NJ == 3) ck[g.B] = sst;
+        }
+      } else {
+        float* dst = g.y_out + row * g.stride;
+        dst[0] = y[0];
+        if (NJ >= 2) dst[1] = y[1];
+        if (NJ == 3) dst[2] = y[2];
+      }
     }
   }
   const int ne = g.eval + 1;
-  if (ne < 4 * g.n_steps) {
-    __syncwarp();
-    if (lane == 0) {
+  if (ne >= 4 * g.n_steps) return;
+  __syncthreads();
+  const float xst = bc[t][0];
+  const int stage = ne & 3;
+  const float cs = stage == 0 ? 0.f : (stage == 3 ? h : 0.5f * h);
+  const float tp = g.y0 * (g.t0 + h * (float)(ne >> 2) + cs);
+  if (!valid) return;
+  for (int grp = gs; grp < H / 4; grp += 32) {
+    const int k = 4 * grp;
+    float* d0 = g.S0 + sbuf_off(grp, row, g.rows_pad);
+    float a[4], wx[4];
 #pragma unroll
-      for (int c = 0; c < 3; ++c) { st[c] = y[c]; st[3 + c] = accw[c]; }
-      st[6] = xst; st[7] = sst;
-      if (g.ckpt != nullptr) {
-        float* ck = g.ckpt + ((long long)ne * 2) * g.B + row;
-        ck[0] = xst;
-        if (NJ == 3) ck[g.B] = sst;
-      }
+    for (int e = 0; e < 4; ++e) {
+      wx[e] = g.theta[TL.w(0) + H + k + e];
+      a[e] = tanh_f(fmaf(wx[e], xst, fmaf(tp, g.theta[TL.w(0) + k + e], g.theta[TL.b(0) + k + e])));
     }
-    const int stage = ne & 3;
-    const float cs = stage == 0 ? 0.f : (stage == 3 ? h : 0.5f * h);
-    const float tp = g.y0 * (g.t0 + h * (float)(ne >> 2) + cs);
-    for (int k = 4 * lane; k < H; k += 128) {
-      float* d0 = g.S0 + sbuf_off(k >> 2, row, g.rows_pad);
-      float a[4], wx[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        wx[e] = g.theta[TL.w(0) + H + k + e];
-        a[e] = tanh_f(fmaf(wx[e], xst, fmaf(tp, g.theta[TL.w(0) + k + e], g.theta[TL.b(0) + k + e])));
-      }
-      *reinterpret_cast<float4*>(d0) = make_float4(a[0], a[1], a[2], a[3]);
-      if (NJ >= 2) *reinterpret_cast<float4*>(d0 + jet_stride) = make_float4(wx[0], wx[1], wx[2], wx[3]);
-      if (NJ == 3) *reinterpret_cast<float4*>(d0 + 2 * jet_stride) = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-  } else if (lane == 0) {
-    float* dst = g.y_out + row * g.stride;
-    dst[0] = y[0];
-    if (NJ >= 2) dst[1] = y[1];
-    if (NJ == 3) dst[2] = y[2];
+    *reinterpret_cast<float4*>(d0) = make_float4(a[0], a[1], a[2], a[3]);
+    if (NJ >= 2) *reinterpret_cast<float4*>(d0 + jet_stride) = make_float4(wx[0], wx[1], wx[2], wx[3]);
+    if (NJ == 3) *reinterpret_cast<float4*>(d0 + 2 * jet_stride) = make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
 
@@ -497,19 +533,17 @@ struct SweepArgs {
 };
 
 __global__ void __launch_bounds__(256) mlp_sweep_tail_kernel(const SweepArgs g) {
-  const int lane = threadIdx.x & 31;
-  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);      // chunk-local
-  const long long rows8 = (g.rows + 7) / 8 * 8;
-  if (row >= rows8) return;
+  const int tid = threadIdx.x, t = tid & 7, gs = tid >> 3;
+  const long long row = (long long)blockIdx.x * 8 + t;      // chunk-local
   const bool valid = row < g.rows;
   const int H = g.H;
   const ThetaLayout TL(H, g.L);
   const size_t jet_stride = (size_t)g.rows_pad * H;
   const float h = (g.t1 - g.t0) / (float)g.n_steps;
-  float* st = g.bst + row * 8;
-  if (lane == 0) {
+  if (tid < 8) {
+    float* st = g.bst + row * 8;
     if (g.e_done < 0) {
-      const float* src = g.ybar1 + (g.r0 + row) * g.stride;
+      const float* src = g.ybar1 + (g.r0 + (valid ? row : 0)) * g.stride;
       st[0] = valid ? src[0] : 0.f; st[1] = valid ? src[1] : 0.f; st[2] = valid ? src[2] : 0.f;
       st[3] = st[4] = st[5] = st[6] = st[7] = 0.f;
     } else {
@@ -533,8 +567,9 @@ __global__ void __launch_bounds__(256) mlp_sweep_tail_kernel(const SweepArgs g) 
   const float tp = g.y0 * (g.t0 + h * (float)(g.e_next >> 2) + cs);
   const long long rowc = valid ? row : g.rows - 1;
   const float xst = g.ckpt[((long long)g.e_next * 2) * g.Bglob + g.r0 + rowc];
-  float* blk = g.acts0 + (size_t)(row >> 3) * g.act_tile_stride + (row & 7);
-  for (int k = 4 * lane; k < H; k += 128) {
+  float* blk = g.acts0 + (size_t)blockIdx.x * g.act_tile_stride + t;
+  for (int grp = gs; grp < H / 4; grp += 32) {
+    const int k = 4 * grp;
     float a[4], wx[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -545,7 +580,7 @@ __global__ void __launch_bounds__(256) mlp_sweep_tail_kernel(const SweepArgs g) 
       blk[(size_t)(2 * H + k + e) * kTT] = 0.f;
     }
     if (valid) {
-      float* d0 = g.S0 + sbuf_off(k >> 2, row, g.rows_pad);
+      float* d0 = g.S0 + sbuf_off(grp, row, g.rows_pad);
       *reinterpret_cast<float4*>(d0) = make_float4(a[0], a[1], a[2], a[3]);
       *reinterpret_cast<float4*>(d0 + jet_stride) = make_float4(wx[0], wx[1], wx[2], wx[3]);
       *reinterpret_cast<float4*>(d0 + 2 * jet_stride) = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -553,18 +588,18 @@ __global__ void __launch_bounds__(256) mlp_sweep_tail_kernel(const SweepArgs g) 
   }
 }
 
-// head: one warp per trajectory, one CTA per tile of 8 (its small-gradient slot)
+// head: one CTA per tile of 8 trajectories (= its small-gradient slot)
 __global__ void __launch_bounds__(256) mlp_sweep_head_kernel(const SweepArgs g) {
-  extern __shared__ float red[];                 // [2][8 warps][H] : w_last and b_{L-1} partials
-  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
-  const long long row = (long long)blockIdx.x * 8 + wp;
+  __shared__ float part[8][8];                    // h' partials [warp][row]
+  const int tid = threadIdx.x, t = tid & 7, gs = tid >> 3, wp = tid >> 5;
+  const long long row = (long long)blockIdx.x * 8 + t;
   const bool valid = row < g.rows;
   const int H = g.H, L = g.L;
   const ThetaLayout TL(H, L);
   const size_t jet_stride = (size_t)g.rows_pad * H;
   const float h = (g.t1 - g.t0) / (float)g.n_steps;
   const int stage = g.e & 3;
-  float* st = g.bst + row * 8;
+  const float* st = g.bst + row * 8;
   const float ca = (stage == 0 || stage == 3) ? h * (1.0f / 6.0f) : h * (1.0f / 3.0f);
   const float cp = stage == 3 ? 0.f : (stage == 2 ? h : 0.5f * h);
   const float xb = st[0], lb = st[1], sb = st[2], prevx = st[3], prevs = st[4];
@@ -574,9 +609,11 @@ __global__ void __launch_bounds__(256) mlp_sweep_head_kernel(const SweepArgs g) 
   // dx = y0 h ; dlogp = -y0 h' ; ds = -y0 (h' s + h'')
   const float hb0 = valid ? g.y0 * kx : 0.f, hb1 = valid ? -g.y0 * (kl + sst * ks) : 0.f, hb2 = valid ? -g.y0 * ks : 0.f;
   float h1 = 0.f;
-  float* blk = g.pbar_last + (size_t)(row >> 3) * g.pb_tile_stride + (row & 7);
-  for (int k = 4 * lane; k < H; k += 128) {
-    const float* s0 = g.Slast + sbuf_off(k >> 2, row, g.rows_pad);
+  float* blk = g.pbar_last + (size_t)blockIdx.x * g.pb_tile_stride + t;
+  float* gsl = g.gsm + (size_t)blockIdx.x * TL.n_small();
+  for (int grp = gs; grp < H / 4; grp += 32) {
+    const int k = 4 * grp;
+    const float* s0 = g.Slast + sbuf_off(grp, row, g.rows_pad);
     const float4 a4 = *reinterpret_cast<const float4*>(s0);
     const float4 p14 = *reinterpret_cast<const float4*>(s0 + jet_stride);
     const float4 p24 = *reinterpret_cast<const float4*>(s0 + 2 * jet_stride);
@@ -589,41 +626,35 @@ __global__ void __launch_bounds__(256) mlp_sweep_head_kernel(const SweepArgs g) 
       const float a1 = sg * p1[e];
       const float a2 = fmaf(sg, p2[e], -2.0f * av[e] * a1 * p1[e]);
       h1 = fmaf(wl, a1, h1);
-      red[(0 * 8 + wp) * H + k + e] = av[e] * hb0 + a1 * hb1 + a2 * hb2;
       const float ab = wl * hb0, a1b = wl * hb1, a2b = wl * hb2;
       q2[e] = a2b * sg;
       q1[e] = sg * fmaf(-4.0f * av[e] * p1[e], a2b, a1b);
       q0[e] = sg * (ab - 2.0f * av[e] * p1[e] * a1b + a2b * fmaf(-2.0f * av[e], p2[e], -2.0f * fmaf(-3.0f * av[e], av[e], 1.0f) * p1[e] * p1[e]));
-      red[(1 * 8 + wp) * H + k + e] = q0[e];
       blk[(size_t)(k + e) * kTT] = q0[e];
       blk[(size_t)(H + k + e) * kTT] = q1[e];
       blk[(size_t)(2 * H + k + e) * kTT] = q2[e];
+      // last-layer kernel and last hidden bias gradients: sums over the 8 rows of the tile, one writer per unit
+      const float gw = tile_rows_sum(av[e] * hb0 + a1 * hb1 + a2 * hb2);
+      const float gb = tile_rows_sum(q0[e]);
+      if (t == 0) { gsl[TL.c_wlast() + k + e] += gw; gsl[TL.c_b(L - 1) + k + e] += gb; }
     }
     if (valid) {
-      float* d0 = g.Pb + sbuf_off(k >> 2, row, g.rows_pad);
+      float* d0 = g.Pb + sbuf_off(grp, row, g.rows_pad);
       *reinterpret_cast<float4*>(d0) = make_float4(q0[0], q0[1], q0[2], q0[3]);
       *reinterpret_cast<float4*>(d0 + jet_stride) = make_float4(q1[0], q1[1], q1[2], q1[3]);
       *reinterpret_cast<float4*>(d0 + 2 * jet_stride) = make_float4(q2[0], q2[1], q2[2], q2[3]);
     }
   }
-  h1 = warp_sum(h1);
-  if (lane == 0) {
-    st[7] = valid ? -g.y0 * h1 * ks : 0.f;          // direct s cotangent of this stage
-    red[2 * 8 * H + wp] = hb0;
-  }
+  h1 = row_lanes_sum(h1);
+  if ((tid & 31) < 8) part[wp][t] = h1;
+  const float gl = tile_rows_sum(hb0);            // last-layer bias gradient of the tile (all lanes take part)
   __syncthreads();
-  float* gs = g.gsm + (size_t)blockIdx.x * TL.n_small();
-  for (int k = threadIdx.x; k < H; k += 256) {
-    float s0 = 0.f, s1 = 0.f;
+  if (tid < 8) {
+    float hs = 0.f;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) { s0 += red[(0 * 8 + q) * H + k]; s1 += red[(1 * 8 + q) * H + k]; }
-    gs[TL.c_wlast() + k] += s0;
-    gs[TL.c_b(L - 1) + k] += s1;
-  }
-  if (threadIdx.x == 0) {
-    float s = 0.f;
-    for (int q = 0; q < 8; ++q) s += red[2 * 8 * H + q];
-    gs[0] += s;
+    for (int q = 0; q < 8; ++q) hs += part[q][t];
+    g.bst[row * 8 + 7] = valid ? -g.y0 * hs * ks : 0.f;          // direct s cotangent of this stage
+    if (t == 0) gsl[0] += gl;
   }
 }
 
@@ -640,8 +671,6 @@ int launch_mlp_bwd_sweep_tc(void* stream, const float* theta, const float* Wc, c
   cudaError_t e = cudaFuncSetAttribute(mlp_layer_gemm_tc_kernel<3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GemmSmem) + 1024);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_layer_gemm_tc_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GemmSmem) + 1024);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_layer_gemm_tc_kernel<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GemmSmem) + 1024);
-  const size_t head_smem = (size_t)(2 * 8 * H + 8) * sizeof(float);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_sweep_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)head_smem);
   if (e != cudaSuccess) return (int)e;
   for (int l = 0; l < L; ++l) if ((e = cudaMemsetAsync(S[l], 0, sbytes, st)) != cudaSuccess) return (int)e;
   if ((e = cudaMemsetAsync(Pb0, 0, sbytes, st)) != cudaSuccess) return (int)e;
@@ -672,7 +701,7 @@ int launch_mlp_bwd_sweep_tc(void* stream, const float* theta, const float* Wc, c
     }
     sa.e = ev;
     sa.pbar_last = pbar + (size_t)ev * n_tiles * pb_tile + (size_t)(L - 2) * 3 * H * kTT;
-    mlp_sweep_head_kernel<<<glue_grid, 256, head_smem, st>>>(sa);
+    mlp_sweep_head_kernel<<<glue_grid, 256, 0, st>>>(sa);
     const int stage = ev & 3;
     const float cs = stage == 0 ? 0.f : (stage == 3 ? hstep : 0.5f * hstep);
     float* pin = Pb0; float* pout = Pb1;
