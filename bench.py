@@ -325,13 +325,13 @@ def main():
     mlp_tc = is_1d and all(os.environ.get(k, "tc")[0] != "f" for k in ("OFDFT_B200_MLP_FWD", "OFDFT_B200_MLP_BWD", "OFDFT_B200_MLP_DW"))
     if mlp_tc:
         # 1-D flow, tensor-core path: every hidden-layer GEMM launch executes (rows padded to 128) x H x H x 3 jets x
-        # 3 passes; the adjoint adds the recompute and the transposed GEMMs, the weight gradients a stacked [hi|lo] GEMM
-        # with two passes over n_evals x B x 3 jets contraction rows.
+        # 3 passes; the adjoint adds the recompute and the transposed GEMMs plus the weight-gradient GEMMs.
         Hm, L = MLP_FEAT[0], len(MLP_FEAT)
         rows_pad = math.ceil(B / 128) * 128
         gemm = 2.0 * rows_pad * Hm * Hm * 3 * 3
         fwd_tensor_flops = evals * (L - 1) * gemm
-        dw_flops = (L - 1) * 2.0 * (2 * Hm) * Hm * (evals * math.ceil(B / 8) * 8 * 3) * 2
+        # weight gradients: 3 passes (hi.hi, lo.hi, hi.lo) over n_evals x B x 3 jets contraction rows (128 x 128 tiles)
+        dw_flops = (L - 1) * 2.0 * Hm * Hm * (evals * math.ceil(B / 8) * 8 * 3) * 3
         bwd_tensor_flops = 2.0 * evals * (L - 1) * gemm + dw_flops
         tf32_peak = 0.5 * peaks.get("bf16_tflops_sustained", 1400.0)
         roofline = {
