@@ -92,17 +92,25 @@ class EnergyEstimator:
 
         if self._is_gnn:
             e0 = mark()
-            want_act = self.act_ckpt and ops.gnn_act_ckpt_bytes(B, bs, ops.JETS_FULL, self.jets_b, m.xyz_nuclei.shape[0],
-                                                                self.n_steps) <= self.act_ckpt_max_bytes
+            Na = m.xyz_nuclei.shape[0]
+            act_bytes = ops.gnn_act_ckpt_bytes(B, bs, ops.JETS_FULL, self.jets_b, Na, self.n_steps)
+            want_act = self.act_ckpt and act_bytes <= self.act_ckpt_max_bytes
+            # activation checkpoint above the cap (many nuclei x large batch): integrate once without checkpoints, then
+            # re-integrate and reverse the rows in chunks whose checkpoint fits -- one extra forward pass keeps the
+            # backward on the tensor-core kernel, which is ~3x faster than the FP32 recompute kernel
+            chunked = self.act_ckpt and not want_act and B > 0
             y1, ckpt = ops.gnn_fwd(theta, m.xyz_nuclei, m.z_one_hot, batch, bs, ops.JETS_FULL, self.jets_b, self.n_steps,
-                                   self.t0, self.t1, m.y0, want_ckpt=True, want_act=want_act)
+                                   self.t0, self.t1, m.y0, want_ckpt=not chunked, want_act=want_act)
             e1 = mark()
             sums, ybar1 = ops.functionals_fwd_bwd(self.spec, y1)
             if self.hartree_mode == "allpairs":
                 self._allpairs_hartree(y1, ybar1, sums)
             e2 = mark()
-            tbar, _ = ops.gnn_bwd(theta, m.xyz_nuclei, m.z_one_hot, ckpt, ybar1, bs, ops.JETS_FULL, self.jets_b,
-                                  self.n_steps, self.t0, self.t1, m.y0)
+            if chunked:
+                tbar = self._gnn_bwd_chunked(theta, batch, ybar1, bs, Na)
+            else:
+                tbar, _ = ops.gnn_bwd(theta, m.xyz_nuclei, m.z_one_hot, ckpt, ybar1, bs, ops.JETS_FULL, self.jets_b,
+                                      self.n_steps, self.t0, self.t1, m.y0)
             e3 = mark()
             if timers is not None:
                 timers += [("gnn_fwd", e0, e1), ("functionals", e1, e2), ("gnn_bwd", e2, e3)]
@@ -126,6 +134,28 @@ class EnergyEstimator:
             sums /= ws
             tbar /= ws
         return sums, tbar, y1
+
+    def _gnn_bwd_chunked(self, theta: torch.Tensor, batch: torch.Tensor, ybar1: torch.Tensor, bs: int, Na: int) -> torch.Tensor:
+        """theta_bar = sum over row chunks of [re-integrate the chunk with both checkpoints, reverse it]; the chunks never
+        straddle the two halves (their jets differ) and are sized so that one activation checkpoint fits the cap."""
+        m = self.model
+        tbar = torch.zeros_like(theta)
+        B = batch.shape[0]
+        for lo, hi, jets in ((0, bs, ops.JETS_FULL), (bs, B, self.jets_b)):
+            n = hi - lo
+            if n <= 0:
+                continue
+            per_row = max(1, ops.gnn_act_ckpt_bytes(128, 128, jets, jets, Na, self.n_steps) // 128)
+            rows = max(128, (self.act_ckpt_max_bytes // per_row) // 128 * 128)
+            for r0 in range(lo, hi, rows):
+                r1 = min(hi, r0 + rows)
+                _, ck = ops.gnn_fwd(theta, m.xyz_nuclei, m.z_one_hot, batch[r0:r1], r1 - r0, jets, jets, self.n_steps,
+                                    self.t0, self.t1, m.y0, want_ckpt=True, want_act=True)
+                g, _ = ops.gnn_bwd(theta, m.xyz_nuclei, m.z_one_hot, ck, ybar1[r0:r1], r1 - r0, jets, jets, self.n_steps,
+                                   self.t0, self.t1, m.y0)
+                tbar += g
+                del ck
+        return tbar
 
     def _allpairs_hartree(self, y1: torch.Tensor, ybar1: torch.Tensor, sums: torch.Tensor) -> None:
         """Adds the all-pairs Hartree energy of this rank's strip to ``sums`` and its forces to ``ybar1`` (in place)."""

@@ -203,6 +203,25 @@ def test_error_behaviour_of_the_c_abi():
         ops.gnn_fwd(torch.as_tensor(theta, dtype=torch.float32), dev(coords), dev(onehot), y, 4, 3, 3, 2, 0.0, 1.0, -1.0)
 
 
+def test_chunked_backward_above_the_activation_checkpoint_cap():
+    """When the layer-2 activation checkpoint of the whole batch exceeds the cap the estimator re-integrates and reverses
+    the rows in chunks (tensor-core backward kept): same energies, same gradient as the single-launch path."""
+    mol, nt, theta, batch, fld = problem("H2O", 300, 7)
+    model = Gen_EqvFlow(3, (64, 64), mol["coords"], mol["onehot"], bool_neg=True)
+    spec = ops.EnergySpec(Ne=mol["Ne"], d=3, kin="tf-w", hart="hartree", nuc="hgh", x="lda", coords=mol["coords"], z=mol["z"])
+    full = EnergyEstimator(model, spec, n_steps=4)
+    per_row = ops.gnn_act_ckpt_bytes(128, 128, 3, 3, 3, 4) // 128
+    small = EnergyEstimator(model, spec, n_steps=4, act_ckpt_max_bytes=130 * per_row)       # chunks of 128 rows
+    s0, g0, _ = full.step_flat(dev(theta), dev(batch))
+    s1, g1, _ = small.step_flat(dev(theta), dev(batch))
+    assert torch.equal(s0, s1)
+    assert rel(g1.cpu().numpy(), g0.cpu().numpy()) < 2e-6
+    ospec = O.EnergySpec(Ne=mol["Ne"], kin="tf-w", hart="hartree", nuc="hgh", x="lda", coords=mol["coords"], z=mol["z"])
+    _, _, g_ref, _ = O.loss_and_grad(fld, ospec, batch, n_steps=4)
+    for name, (a, b) in tensor_slices(nt).items():
+        assert rel(g1.cpu().numpy()[a:b], g_ref[a:b]) <= G_TOL, name
+
+
 def test_functionals_all_modes_match_oracle():
     rng = np.random.default_rng(4)
     mol = O.molecule("H2O")
