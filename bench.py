@@ -169,8 +169,11 @@ def run_reference(args):
         "unit": "trajectories/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{molname} 3-D equivariant flow, TF+W / {nuc} / Hartree / LDA, bs={full_bs} per GPU "
-                               f"(CPU arm: bounded sample bs={bs})"},
+        "config": {"workload": ((f"LiH 1-D tanh-MLP flow {MLP_FEAT}, TF1D+W / attraction / soft-Coulomb, bs={full_bs} per GPU "
+                                 f"({2 * full_bs} trajectories)") if wl == "lih1d" else
+                                (f"{molname} 3-D equivariant flow (64,64), TF+W / {nuc} / paired Hartree / LDA, "
+                                 f"bs={full_bs} per GPU ({2 * full_bs} trajectories)")) +
+                               f"; reference arm: adaptive Dopri5 1e-7 in float64 on a bounded sample bs={bs} per step"},
         "cpu_baseline": {"value": value, "unit": "trajectories/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "trajectories/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
