@@ -49,7 +49,7 @@ def shard_batch(batch, rank: int, world: int):
 class EnergyEstimator:
     def __init__(self, model: Any, spec: ops.EnergySpec, n_steps: int = DEFAULT_N_STEPS, t0: float = 0.0, t1: float = 1.0,
                  skip_unused_jets: bool = True, group: Optional[Any] = None, act_ckpt: bool = True,
-                 act_ckpt_max_bytes: int = 64 << 30, hartree_mode: str = "paired"):
+                 act_ckpt_max_bytes: Optional[int] = None, hartree_mode: str = "paired"):
         self.model, self.spec, self.n_steps, self.t0, self.t1 = model, spec, int(n_steps), float(t0), float(t1)
         # rows of the second half only supply xp: integrate them without the logp/score channels
         self.jets_b = ops.JETS_X if skip_unused_jets else ops.JETS_FULL
@@ -67,7 +67,9 @@ class EnergyEstimator:
             self.spec = dataclasses.replace(spec, hart="")        # local functionals without the paired Hartree term
         # keep the layer-2 activation jets of every RHS evaluation in HBM instead of recomputing them in the backward
         # pass (B200: 180 GB); falls back to recomputation above ``act_ckpt_max_bytes``
-        self.act_ckpt, self.act_ckpt_max_bytes = bool(act_ckpt), int(act_ckpt_max_bytes)
+        # default cap: 64 GB, but never more than half of the device memory that is free at the first step
+        self.act_ckpt = bool(act_ckpt)
+        self.act_ckpt_max_bytes = None if act_ckpt_max_bytes is None else int(act_ckpt_max_bytes)
         self._is_gnn = hasattr(model, "xyz_nuclei")
 
     def _dist(self) -> bool:
@@ -93,6 +95,9 @@ class EnergyEstimator:
         if self._is_gnn:
             e0 = mark()
             Na = m.xyz_nuclei.shape[0]
+            if self.act_ckpt_max_bytes is None:
+                free = torch.cuda.mem_get_info(batch.device)[0] if batch.is_cuda else (64 << 30)
+                self.act_ckpt_max_bytes = int(min(64 << 30, free // 2))
             act_bytes = ops.gnn_act_ckpt_bytes(B, bs, ops.JETS_FULL, self.jets_b, Na, self.n_steps)
             want_act = self.act_ckpt and act_bytes <= self.act_ckpt_max_bytes
             # activation checkpoint above the cap (many nuclei x large batch): integrate once without checkpoints, then
