@@ -18,6 +18,24 @@
 namespace ofdft {
 namespace mlp {
 
+// Programmatic dependent launch: every kernel of the per-layer chain is launched with the "programmatic stream
+// serialization" attribute, calls pdl_wait() before it touches anything its predecessor wrote and pdl_trigger() once its
+// successor may start being scheduled -- so a kernel's prologue (TMEM allocation, barrier init, scheduling) overlaps the
+// tail of the one before it.  ~380 dependent launches per 1-D step make the fixed cost per launch matter.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename Arg>
+static cudaError_t launch_pdl(void (*kernel)(Arg), dim3 grid, dim3 block, size_t smem, cudaStream_t st, const Arg& arg) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, arg);
+}
+
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tc::smem_u32(smem)), "l"(gmem) : "memory");
 }
@@ -93,6 +111,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) mlp_layer_gemm_tc_kernel(cons
   const uint32_t tmem = sm.tmem_slot;
   const int n_it = H / kGemmKC;
   const size_t jet_stride = (size_t)g.rows_pad * H;
+  pdl_wait();                                     // everything above overlapped the previous kernel's tail
 
   if (w == 16) {
     // ---------------- MMA issue warp ----------------
@@ -223,6 +242,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) mlp_layer_gemm_tc_kernel(cons
       if ((it + 1) % kGemmGroup == 0 && it + 1 < n_it) drain();
     }
     drain();
+    pdl_trigger();                                // the next kernel of the chain may be scheduled during this epilogue
 
     const long long row = row0 + r;
     const int jc = j0 + 16 * c;
@@ -367,6 +387,8 @@ template <int NJ>
 __global__ void __launch_bounds__(256) mlp_glue_tc_kernel(const GlueArgs g) {
   __shared__ float part[3][8][8];                 // [quantity][warp][row]
   __shared__ float bc[8][2];                      // per row: x and s of the next stage
+  pdl_trigger();                                  // short kernel: let the next layer GEMM run its prologue underneath
+  pdl_wait();
   const int tid = threadIdx.x, t = tid & 7, gs = tid >> 3, wp = tid >> 5;
   const long long row = (long long)blockIdx.x * 8 + t;
   const bool valid = row < g.B;
@@ -498,13 +520,13 @@ static int run_fwd_tc(cudaStream_t st, const float* theta, const float* WTc, con
   for (int ev = -1; ev < 4 * n_steps; ++ev) {
     // the last hidden layer of evaluation ev ended in bufs[(L-1) & 1]
     ga.eval = ev; ga.Slast = bufs[(L - 1) & 1];
-    mlp_glue_tc_kernel<NJ><<<glue_grid, 256, 0, st>>>(ga);
+    if ((e = launch_pdl(mlp_glue_tc_kernel<NJ>, dim3(glue_grid), dim3(256), 0, st, ga)) != cudaSuccess) return (int)e;
     if (ev + 1 == 4 * n_steps) break;
     for (int l = 1; l < L; ++l) {
       GemmArgs gg{};
       gg.Sin = bufs[(l - 1) & 1]; gg.Sout = bufs[l & 1]; gg.WT = WTc + (size_t)(l - 1) * H * H; gg.WTlo = WTlo + (size_t)(l - 1) * H * H;
       gg.bias = theta + TL.b(l); gg.B = B; gg.rows_pad = rows_pad; gg.H = H;
-      mlp_layer_gemm_tc_kernel<NJ, 0><<<gemm_grid, kGemmThreads, sizeof(GemmSmem) + 1024, st>>>(gg);
+      if ((e = launch_pdl(mlp_layer_gemm_tc_kernel<NJ, 0>, gemm_grid, dim3(kGemmThreads), sizeof(GemmSmem) + 1024, st, gg)) != cudaSuccess) return (int)e;
     }
   }
   return (int)cudaGetLastError();
@@ -533,6 +555,8 @@ struct SweepArgs {
 };
 
 __global__ void __launch_bounds__(256) mlp_sweep_tail_kernel(const SweepArgs g) {
+  pdl_trigger();
+  pdl_wait();
   const int tid = threadIdx.x, t = tid & 7, gs = tid >> 3;
   const long long row = (long long)blockIdx.x * 8 + t;      // chunk-local
   const bool valid = row < g.rows;
@@ -591,6 +615,8 @@ __global__ void __launch_bounds__(256) mlp_sweep_tail_kernel(const SweepArgs g) 
 // head: one CTA per tile of 8 trajectories (= its small-gradient slot)
 __global__ void __launch_bounds__(256) mlp_sweep_head_kernel(const SweepArgs g) {
   __shared__ float part[8][8];                    // h' partials [warp][row]
+  pdl_trigger();
+  pdl_wait();
   const int tid = threadIdx.x, t = tid & 7, gs = tid >> 3, wp = tid >> 5;
   const long long row = (long long)blockIdx.x * 8 + t;
   const bool valid = row < g.rows;
@@ -690,18 +716,18 @@ int launch_mlp_bwd_sweep_tc(void* stream, const float* theta, const float* Wc, c
     // finish stage ev+1 (or initialise), prepare stage ev
     sa.e_done = ev + 1 < n_evals ? ev + 1 : -1; sa.e_next = ev;
     sa.acts0 = ev >= 0 ? acts + (size_t)ev * n_tiles * act_tile : nullptr;                       // layer 0 slot of the tile block
-    mlp_sweep_tail_kernel<<<glue_grid, 256, 0, st>>>(sa);
+    if ((e = launch_pdl(mlp_sweep_tail_kernel, dim3(glue_grid), dim3(256), 0, st, sa)) != cudaSuccess) return (int)e;
     if (ev < 0) break;
     for (int l = 1; l < L; ++l) {
       GemmArgs gg{};
       gg.Sin = S[l - 1]; gg.Sout = S[l]; gg.WT = WTc + (size_t)(l - 1) * H * H; gg.WTlo = WTlo + (size_t)(l - 1) * H * H;
       gg.bias = theta + TL.b(l); gg.B = rows; gg.rows_pad = rows_pad; gg.H = H;
       gg.blk_out = acts + (size_t)ev * n_tiles * act_tile + (size_t)l * 3 * H * kTT; gg.blk_tile_stride = act_tile;
-      mlp_layer_gemm_tc_kernel<3, 0><<<gemm_grid, kGemmThreads, sizeof(GemmSmem) + 1024, st>>>(gg);
+      if ((e = launch_pdl(mlp_layer_gemm_tc_kernel<3, 0>, gemm_grid, dim3(kGemmThreads), sizeof(GemmSmem) + 1024, st, gg)) != cudaSuccess) return (int)e;
     }
     sa.e = ev;
     sa.pbar_last = pbar + (size_t)ev * n_tiles * pb_tile + (size_t)(L - 2) * 3 * H * kTT;
-    mlp_sweep_head_kernel<<<glue_grid, 256, 0, st>>>(sa);
+    if ((e = launch_pdl(mlp_sweep_head_kernel, dim3(glue_grid), dim3(256), 0, st, sa)) != cudaSuccess) return (int)e;
     const int stage = ev & 3;
     const float cs = stage == 0 ? 0.f : (stage == 3 ? hstep : 0.5f * hstep);
     float* pin = Pb0; float* pout = Pb1;
@@ -712,12 +738,12 @@ int launch_mlp_bwd_sweep_tc(void* stream, const float* theta, const float* Wc, c
       if (l >= 2) {
         gg.off_b = TL.c_b(l - 1);
         gg.blk_out = pbar + (size_t)ev * n_tiles * pb_tile + (size_t)(l - 2) * 3 * H * kTT; gg.blk_tile_stride = pb_tile;
-        mlp_layer_gemm_tc_kernel<3, 1><<<gemm_grid, kGemmThreads, sizeof(GemmSmem) + 1024, st>>>(gg);
+        if ((e = launch_pdl(mlp_layer_gemm_tc_kernel<3, 1>, gemm_grid, dim3(kGemmThreads), sizeof(GemmSmem) + 1024, st, gg)) != cudaSuccess) return (int)e;
         float* t = pin; pin = pout; pout = t;
       } else {
         gg.off_b = TL.c_b0(); gg.off_w0 = TL.c_w0(); gg.wx = theta + TL.w(0) + H;
         gg.xs = ckpt + ((long long)ev * 2) * Bglob + r0; gg.tprime = y0sign * (t0 + hstep * (float)(ev >> 2) + cs); gg.xpart = xpart;
-        mlp_layer_gemm_tc_kernel<3, 2><<<gemm_grid, kGemmThreads, sizeof(GemmSmem) + 1024, st>>>(gg);
+        if ((e = launch_pdl(mlp_layer_gemm_tc_kernel<3, 2>, gemm_grid, dim3(kGemmThreads), sizeof(GemmSmem) + 1024, st, gg)) != cudaSuccess) return (int)e;
       }
     }
     // the head of the next stage writes Pb0 again; MODE 1 outputs alternate between the two buffers
