@@ -48,7 +48,11 @@ constexpr int kGemmRaw = 4;                       // shared-memory ring fed by T
 constexpr int kLboB = 64 * 16;                    // chunk stride of the weight operand (bytes): 64 rows x 16 B, as TMA lays it
 constexpr int kColAcc = 0;                        // TMEM: accumulators 3 jets x 64 columns
 constexpr int kColOp = 192;                       // TMEM: operand ring, per slot [jet][hi 16 | lo 16] = 96 columns
-constexpr int kGemmThreads = 512 + 64;            // 16 staging warps + MMA warp + TMA warp (18 warps: at most 96 registers/thread)
+constexpr int kSW = 8;                            // staging warps: 4 row quadrants x (kSW/4) column groups; 8 warps do a stage in a
+                                                  // third fewer instructions than 16 (the per-warp waits/fences/arrivals halve)
+constexpr int kCT = 64 / (kSW / 4);               // output columns per staging thread (epilogue)
+constexpr int kCH = 4 / (kSW / 4);                // 4-wide k chunks per staging thread and stage
+constexpr int kGemmThreads = (kSW + 2) * 32;      // staging warps + MMA warp + TMA warp
 
 // layer buffers: [jet: a, p', p''][unit / 4][row (padded to 128)][4 units] -- 32 consecutive rows x 4 units are 512
 // contiguous bytes, which is what a warp whose lanes are rows (the TMEM lane constraint) loads or stores at once
@@ -99,9 +103,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) mlp_layer_gemm_tc_kernel(cons
   const long long row0 = (long long)blockIdx.x * 128;
   const int j0 = blockIdx.y * 64;
   if (tid == 0) {
-    for (int i = 0; i < kGemmSlots; ++i) { tc::mbar_init(&sm.full[i], 16); tc::mbar_init(&sm.empty[i], 1); }
-    for (int i = 0; i < kGemmRaw; ++i) { tc::mbar_init(&sm.rfull[i], 1); tc::mbar_init(&sm.rempty[i], 17); }
-    tc::mbar_init(&sm.accf, 1); tc::mbar_init(&sm.acce, 16);
+    for (int i = 0; i < kGemmSlots; ++i) { tc::mbar_init(&sm.full[i], kSW); tc::mbar_init(&sm.empty[i], 1); }
+    for (int i = 0; i < kGemmRaw; ++i) { tc::mbar_init(&sm.rfull[i], 1); tc::mbar_init(&sm.rempty[i], kSW + 1); }
+    tc::mbar_init(&sm.accf, 1); tc::mbar_init(&sm.acce, kSW);
     tc::fence_mbar_init();
   }
   if (w == 0) tc::tmem_alloc(&sm.tmem_slot, 512);
@@ -113,7 +117,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) mlp_layer_gemm_tc_kernel(cons
   const size_t jet_stride = (size_t)g.rows_pad * H;
   pdl_wait();                                     // everything above overlapped the previous kernel's tail
 
-  if (w == 16) {
+  if (w == kSW) {
     // ---------------- MMA issue warp ----------------
     const uint32_t idesc = tc::make_idesc_tf32(128, 64, 0, 0);
     uint32_t ph_full = 0, ph_acce = 0;
@@ -143,7 +147,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) mlp_layer_gemm_tc_kernel(cons
       }
       __syncwarp();
     }
-  } else if (w == 17) {
+  } else if (w == kSW + 1) {
     // ---------------- TMA warp: bulk copies global/L2 -> shared-memory ring ----------------
     // per stage: 3 jets x 4 unit groups x (128 rows x 16 B = 2 KB contiguous in the interleaved layer buffer) and
     // (hi, lo) x 4 k groups x (64 rows x 16 B = 1 KB contiguous in the interleaved weight copy)
@@ -171,44 +175,49 @@ __global__ void __launch_bounds__(kGemmThreads, 1) mlp_layer_gemm_tc_kernel(cons
     // ---------------- staging warps ----------------
     const int r = 32 * (w & 3) + lane, c = w >> 2;          // row (TMEM lane) and k chunk of this thread
     const uint32_t tl = tmem + ((uint32_t)(32 * (w & 3)) << 16);
-    struct Regs { float4 a[3]; };
+    struct Regs { float4 a[3][kCH]; };
     auto load_regs = [&](Regs& R, int it) {
 #pragma unroll
-      for (int jt = 0; jt < NJ; ++jt) R.a[jt] = sm.A[it % kGemmRaw][jt][c][r];
+      for (int jt = 0; jt < NJ; ++jt)
+#pragma unroll
+        for (int q = 0; q < kCH; ++q) R.a[jt][q] = sm.A[it % kGemmRaw][jt][kCH * c + q][r];
     };
     auto store_tmem = [&](const Regs& R, int s) {
-      const uint32_t base = tl + kColOp + 96 * s + 4 * c;
-      const float4 a = R.a[0];
-      tc::tmem_st4(base, a.x, a.y, a.z, a.w);
-      tc::tmem_st4(base + 16, tc::lo_tf32(a.x), tc::lo_tf32(a.y), tc::lo_tf32(a.z), tc::lo_tf32(a.w));
-      if (MODE != 0) {
 #pragma unroll
-        for (int jt = 1; jt < NJ; ++jt) {
-          const float4 v = R.a[jt];
-          tc::tmem_st4(base + 32 * jt, v.x, v.y, v.z, v.w);
-          tc::tmem_st4(base + 32 * jt + 16, tc::lo_tf32(v.x), tc::lo_tf32(v.y), tc::lo_tf32(v.z), tc::lo_tf32(v.w));
-        }
-      } else if (NJ >= 2) {
-        const float4 p1 = R.a[1];
-        const float4 sg = make_float4(fmaf(-a.x, a.x, 1.0f), fmaf(-a.y, a.y, 1.0f), fmaf(-a.z, a.z, 1.0f), fmaf(-a.w, a.w, 1.0f));
-        const float4 a1 = make_float4(sg.x * p1.x, sg.y * p1.y, sg.z * p1.z, sg.w * p1.w);
-        tc::tmem_st4(base + 32, a1.x, a1.y, a1.z, a1.w);
-        tc::tmem_st4(base + 48, tc::lo_tf32(a1.x), tc::lo_tf32(a1.y), tc::lo_tf32(a1.z), tc::lo_tf32(a1.w));
-        if (NJ == 3) {
-          const float4 p2 = R.a[2];
-          const float4 a2 = make_float4(fmaf(sg.x, p2.x, -2.0f * a.x * a1.x * p1.x), fmaf(sg.y, p2.y, -2.0f * a.y * a1.y * p1.y),
-                                        fmaf(sg.z, p2.z, -2.0f * a.z * a1.z * p1.z), fmaf(sg.w, p2.w, -2.0f * a.w * a1.w * p1.w));
-          tc::tmem_st4(base + 64, a2.x, a2.y, a2.z, a2.w);
-          tc::tmem_st4(base + 80, tc::lo_tf32(a2.x), tc::lo_tf32(a2.y), tc::lo_tf32(a2.z), tc::lo_tf32(a2.w));
+      for (int q = 0; q < kCH; ++q) {
+        const uint32_t base = tl + kColOp + 96 * s + 4 * (kCH * c + q);
+        const float4 a = R.a[0][q];
+        tc::tmem_st4(base, a.x, a.y, a.z, a.w);
+        tc::tmem_st4(base + 16, tc::lo_tf32(a.x), tc::lo_tf32(a.y), tc::lo_tf32(a.z), tc::lo_tf32(a.w));
+        if (MODE != 0) {
+#pragma unroll
+          for (int jt = 1; jt < NJ; ++jt) {
+            const float4 v = R.a[jt][q];
+            tc::tmem_st4(base + 32 * jt, v.x, v.y, v.z, v.w);
+            tc::tmem_st4(base + 32 * jt + 16, tc::lo_tf32(v.x), tc::lo_tf32(v.y), tc::lo_tf32(v.z), tc::lo_tf32(v.w));
+          }
+        } else if (NJ >= 2) {
+          const float4 p1 = R.a[1][q];
+          const float4 sg = make_float4(fmaf(-a.x, a.x, 1.0f), fmaf(-a.y, a.y, 1.0f), fmaf(-a.z, a.z, 1.0f), fmaf(-a.w, a.w, 1.0f));
+          const float4 a1 = make_float4(sg.x * p1.x, sg.y * p1.y, sg.z * p1.z, sg.w * p1.w);
+          tc::tmem_st4(base + 32, a1.x, a1.y, a1.z, a1.w);
+          tc::tmem_st4(base + 48, tc::lo_tf32(a1.x), tc::lo_tf32(a1.y), tc::lo_tf32(a1.z), tc::lo_tf32(a1.w));
+          if (NJ == 3) {
+            const float4 p2 = R.a[2][q];
+            const float4 a2 = make_float4(fmaf(sg.x, p2.x, -2.0f * a.x * a1.x * p1.x), fmaf(sg.y, p2.y, -2.0f * a.y * a1.y * p1.y),
+                                          fmaf(sg.z, p2.z, -2.0f * a.z * a1.z * p1.z), fmaf(sg.w, p2.w, -2.0f * a.w * a1.w * p1.w));
+            tc::tmem_st4(base + 64, a2.x, a2.y, a2.z, a2.w);
+            tc::tmem_st4(base + 80, tc::lo_tf32(a2.x), tc::lo_tf32(a2.y), tc::lo_tf32(a2.z), tc::lo_tf32(a2.w));
+          }
         }
       }
     };
-    // accumulators: warp w <-> rows 32 (w & 3).. and the 16 output columns 16 (w >> 2)..
-    float acc[NJ][16];
+    // accumulators: warp w <-> rows 32 (w & 3).. and the kCT output columns kCT (w >> 2)..
+    float acc[NJ][kCT];
 #pragma unroll
     for (int jt = 0; jt < NJ; ++jt)
 #pragma unroll
-      for (int i = 0; i < 16; ++i) acc[jt][i] = 0.f;
+      for (int i = 0; i < kCT; ++i) acc[jt][i] = 0.f;
     uint32_t ph_empty = 0, ph_accf = 0;
     auto drain = [&]() {
       tc::mbar_wait(&sm.accf, ph_accf); ph_accf ^= 1u;
@@ -216,11 +225,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1) mlp_layer_gemm_tc_kernel(cons
       tc::fence_after_sync();
 #pragma unroll
       for (int jt = 0; jt < NJ; ++jt) {
-        float t[16];
-        tc::tmem_ld16(tl + kColAcc + jt * 64 + 16 * c, t);
-        tc::tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 16; ++i) acc[jt][i] += t[i];
+        for (int c0 = 0; c0 < kCT; c0 += 16) {
+          float t[16];
+          tc::tmem_ld16(tl + kColAcc + jt * 64 + kCT * c + c0, t);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) acc[jt][c0 + i] += t[i];
+        }
       }
       tc::fence_before_sync();
       __syncwarp();
@@ -245,7 +257,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) mlp_layer_gemm_tc_kernel(cons
     pdl_trigger();                                // the next kernel of the chain may be scheduled during this epilogue
 
     const long long row = row0 + r;
-    const int jc = j0 + 16 * c;
+    const int jc = j0 + kCT * c;
     const long long rows8 = (g.B + 7) / 8 * 8;
     // HBM block slot of (row, unit): [tile = row / 8][jet][unit][row % 8]
     float* blk = g.blk_out != nullptr ? g.blk_out + (size_t)(row >> 3) * g.blk_tile_stride + (size_t)jc * kTT + (row & 7) : nullptr;
@@ -254,7 +266,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) mlp_layer_gemm_tc_kernel(cons
       if (row < rows8) {
         float* dst = g.Sout + sbuf_off(jc >> 2, row, g.rows_pad);
 #pragma unroll
-        for (int i = 0; i < 16; i += 4) {
+        for (int i = 0; i < kCT; i += 4) {
           float4 a;
           a.x = tanh_f(acc[0][i] + g.bias[jc + i]); a.y = tanh_f(acc[0][i + 1] + g.bias[jc + i + 1]);
           a.z = tanh_f(acc[0][i + 2] + g.bias[jc + i + 2]); a.w = tanh_f(acc[0][i + 3] + g.bias[jc + i + 3]);
@@ -277,10 +289,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) mlp_layer_gemm_tc_kernel(cons
       }
     } else {
       // ---- epilogue: reverse of the tanh jet of the layer below: (abar, abar', abar'') -> (pbar, pbar', pbar'') ----
-      float q0[16], q1[16], q2[16];
+      float q0[kCT], q1[kCT], q2[kCT];
       const float* sp = g.Sprev + sbuf_off(jc >> 2, row, g.rows_pad);
 #pragma unroll
-      for (int i = 0; i < 16; i += 4) {
+      for (int i = 0; i < kCT; i += 4) {
         const float4 a4 = *reinterpret_cast<const float4*>(sp + sbuf_off(i >> 2, 0, g.rows_pad));
         const float4 p14 = *reinterpret_cast<const float4*>(sp + sbuf_off(i >> 2, 0, g.rows_pad) + jet_stride);
         const float4 p24 = *reinterpret_cast<const float4*>(sp + sbuf_off(i >> 2, 0, g.rows_pad) + 2 * jet_stride);
@@ -300,7 +312,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) mlp_layer_gemm_tc_kernel(cons
         if (row < rows8) {
           float* dst = g.Sout + sbuf_off(jc >> 2, row, g.rows_pad);
 #pragma unroll
-          for (int i = 0; i < 16; i += 4) {
+          for (int i = 0; i < kCT; i += 4) {
             float* d = dst + sbuf_off(i >> 2, 0, g.rows_pad);
             if (row < g.B) {
               *reinterpret_cast<float4*>(d) = make_float4(q0[i], q0[i + 1], q0[i + 2], q0[i + 3]);
@@ -317,11 +329,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) mlp_layer_gemm_tc_kernel(cons
         }
         // bias gradient of the layer below: column sums over this tile's rows (rows >= B hold zeros)
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
+        for (int i = 0; i < kCT; ++i) {
           const float v = warp_sum(q0[i]);
-          if (lane == 0) red[(w & 3) * 64 + 16 * c + i] = v;
+          if (lane == 0) red[(w & 3) * 64 + kCT * c + i] = v;
         }
-        asm volatile("bar.sync 1, 512;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(kSW * 32) : "memory");
         if (tid < 64) {
           float* gs = g.gsm + (size_t)blockIdx.x * g.n_small + g.off_b + j0 + tid;
           *gs += (red[tid] + red[64 + tid]) + (red[128 + tid] + red[192 + tid]);
@@ -331,14 +343,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1) mlp_layer_gemm_tc_kernel(cons
         const float x_row = row < g.B ? g.xs[row] : 0.f;
         float xp = 0.f;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
+        for (int i = 0; i < kCT; ++i) {
           xp = fmaf(q0[i], g.wx[jc + i], xp);
           const float v0 = warp_sum(q0[i]);
           const float v1 = warp_sum(fmaf(q0[i], x_row, q1[i]));
-          if (lane == 0) { red[(w & 3) * 64 + 16 * c + i] = v0; red[256 + (w & 3) * 64 + 16 * c + i] = v1; }
+          if (lane == 0) { red[(w & 3) * 64 + kCT * c + i] = v0; red[256 + (w & 3) * 64 + kCT * c + i] = v1; }
         }
         red[512 + c * 128 + r] = xp;
-        asm volatile("bar.sync 1, 512;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(kSW * 32) : "memory");
         if (tid < 64) {
           const float sb = (red[tid] + red[64 + tid]) + (red[128 + tid] + red[192 + tid]);
           const float sx = (red[256 + tid] + red[320 + tid]) + (red[384 + tid] + red[448 + tid]);
@@ -347,8 +359,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) mlp_layer_gemm_tc_kernel(cons
           gs[g.off_w0 + j0 + tid] = fmaf(g.tprime, sb, gs[g.off_w0 + j0 + tid]);     // w_t row
           gs[g.off_w0 + g.H + j0 + tid] += sx;                 // w_x row
         }
-        if (tid < 128) g.xpart[(size_t)blockIdx.y * g.rows_pad + row0 + tid] =
-            (red[512 + tid] + red[640 + tid]) + (red[768 + tid] + red[896 + tid]);
+        if (tid < 128) {
+          float xs = 0.f;
+#pragma unroll
+          for (int q = 0; q < kSW / 4; ++q) xs += red[512 + q * 128 + tid];
+          g.xpart[(size_t)blockIdx.y * g.rows_pad + row0 + tid] = xs;
+        }
       }
     }
   }
