@@ -660,7 +660,7 @@ __global__ void __launch_bounds__(256) mlp_sweep_head_kernel(const SweepArgs g) 
     const float4 p14 = *reinterpret_cast<const float4*>(s0 + jet_stride);
     const float4 p24 = *reinterpret_cast<const float4*>(s0 + 2 * jet_stride);
     const float av[4] = {a4.x, a4.y, a4.z, a4.w}, p1[4] = {p14.x, p14.y, p14.z, p14.w}, p2[4] = {p24.x, p24.y, p24.z, p24.w};
-    float q0[4], q1[4], q2[4];
+    float q0[4], q1[4], q2[4], gwv[4], gbv[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const float wl = g.theta[TL.w_last() + k + e];
@@ -676,9 +676,16 @@ __global__ void __launch_bounds__(256) mlp_sweep_head_kernel(const SweepArgs g) 
       blk[(size_t)(H + k + e) * kTT] = q1[e];
       blk[(size_t)(2 * H + k + e) * kTT] = q2[e];
       // last-layer kernel and last hidden bias gradients: sums over the 8 rows of the tile, one writer per unit
-      const float gw = tile_rows_sum(av[e] * hb0 + a1 * hb1 + a2 * hb2);
-      const float gb = tile_rows_sum(q0[e]);
-      if (t == 0) { gsl[TL.c_wlast() + k + e] += gw; gsl[TL.c_b(L - 1) + k + e] += gb; }
+      gwv[e] = tile_rows_sum(av[e] * hb0 + a1 * hb1 + a2 * hb2);
+      gbv[e] = tile_rows_sum(q0[e]);
+    }
+    if (t == 0) {          // read-modify-write of the tile's slot: all loads first, then the stores (compact offsets are odd: scalar)
+      float* __restrict__ gw_p = gsl + TL.c_wlast() + k;
+      float* __restrict__ gb_p = gsl + TL.c_b(L - 1) + k;
+      const float w0 = gw_p[0], w1 = gw_p[1], w2 = gw_p[2], w3 = gw_p[3];
+      const float b0 = gb_p[0], b1 = gb_p[1], b2 = gb_p[2], b3 = gb_p[3];
+      gw_p[0] = w0 + gwv[0]; gw_p[1] = w1 + gwv[1]; gw_p[2] = w2 + gwv[2]; gw_p[3] = w3 + gwv[3];
+      gb_p[0] = b0 + gbv[0]; gb_p[1] = b1 + gbv[1]; gb_p[2] = b2 + gbv[2]; gb_p[3] = b3 + gbv[3];
     }
     if (valid) {
       float* d0 = g.Pb + sbuf_off(grp, row, g.rows_pad);
