@@ -16,7 +16,7 @@ BOHR = 1.8897259886
 
 
 def coordinates(mol_name: str, BOHR: float = BOHR) -> Tuple[int, list, np.ndarray, np.ndarray]:
-    """utils.py:276-326: (Ne, atoms, z, coords[bohr]) for H2, LiH, H2O, CH4, C6H6."""
+    """utils.py:276-418: (Ne, atoms, z, coords[bohr]) for H2, LiH, H2O, CH4, C6H6, C27H46O."""
     if mol_name == "H2":
         return 2, ["H", "H"], np.array([1., 1.]), np.array([[0., 0., -1.4008538753 / 2], [0., 0., 1.4008538753 / 2]]) * BOHR
     if mol_name == "LiH":
@@ -36,6 +36,12 @@ def coordinates(mol_name: str, BOHR: float = BOHR) -> Tuple[int, list, np.ndarra
                       [-1.2497352350, 2.1640355443, 0.0000873078], [1.2495192781, -2.1641211865, -0.0004652006],
                       [-1.2494488074, -2.1642720181, -0.0003281198], [-2.4988922798, 0.0006052813, -0.0002941369]]) * BOHR
         return 42, ["C"] * 6 + ["H"] * 6, np.array([6.] * 6 + [1.] * 6), c
+    if mol_name == "C27H46O":
+        from ._c27h46o import XYZ
+        rows = [ln.split() for ln in XYZ.strip().splitlines()]
+        atoms = [r[0] for r in rows]
+        c = np.array([[float(v) for v in r[1:]] for r in rows]) * BOHR
+        return 216, atoms, np.array([{"O": 8., "C": 6., "H": 1.}[a] for a in atoms]), c
     raise KeyError(mol_name)
 
 

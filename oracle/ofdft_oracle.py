@@ -528,9 +528,12 @@ def soft_coulomb(x, xp, Ne):
 
 
 def hartree_potential_mt(x, xp, Ne, alpha=0.5):
-    """functionals.py:489-496: 0.5 Ne^2 (erf(a r) + erfc(a r)) / r = 0.5 Ne^2 / r (no eps)."""
+    """functionals.py:489-496: 0.5 Ne^2 (erf(a r)/r + erfc(a r)/r) = 0.5 Ne^2 / r (no eps).  Evaluated as coded, so an
+    exactly coincident pair gives 0/0 + 1/0 = NaN like the reference (the CUDA kernel returns +inf there)."""
+    from scipy.special import erf, erfc
     r = np.sqrt(((x - xp) ** 2).sum(-1, keepdims=True))
-    return 0.5 * (Ne ** 2) / r
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return 0.5 * (Ne ** 2) * (erf(alpha * r) / r + erfc(alpha * r) / r)
 
 
 def nuclei_potential(x, Ne, coords, z, eps=1e-4):
@@ -615,8 +618,10 @@ def exchange_correlation_one_dimensional(den, Ne):
 
 
 def _kinetic(name: str):
-    """functionals.py:21-43."""
+    """functionals.py:21-43 ("" = term switched off: zeros)."""
     n = name.lower()
+    if not n:
+        return lambda den, score, Ne: np.zeros_like(den)
     if n in ("tf", "thomas_fermi"):
         return thomas_fermi
     if n in ("tf1d", "thomas_fermi_1d"):
@@ -633,6 +638,8 @@ def _kinetic(name: str):
 def _hartree(name: str):
     """functionals.py:425-436."""
     n = name.lower()
+    if not n:
+        return lambda x, xp, Ne: np.zeros((x.shape[0], 1))
     if n in ("hartree_potential", "hartree"):
         return hartree_potential
     if n in ("soft_coulomb", "softc"):

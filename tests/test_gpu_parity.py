@@ -106,7 +106,8 @@ def test_training_step_matches_oracle_same_scheme(molname, bs, nuc):
             assert rel(g[a:b], g_ref[a:b]) <= G_TOL, (name, rel(g[a:b], g_ref[a:b]))
 
 
-@pytest.mark.parametrize("path", sorted(p for p in glob.glob(os.path.join(GOLD, "*.npz")) if "1d" not in os.path.basename(p)))
+@pytest.mark.parametrize("path", sorted(p for p in glob.glob(os.path.join(GOLD, "*.npz"))
+                                         if "1d" not in os.path.basename(p) and not os.path.basename(p).startswith("ref_")))
 def test_golden_vectors_reference_semantics(path):
     """Committed fixtures = the reference's semantics (adaptive Dopri5 1e-7, float64, autodiff gradient).
     The fixed-step fp32 kernels must land within the north-star tolerances."""
@@ -551,6 +552,83 @@ def test_mlp1d_golden_reference_semantics_lih_config():
     x, logp, score = neural_ode_score(params, dev(g["batch"]), model, 0.0, 1.0, 1, n_steps=16)
     assert np.abs(x.detach().cpu().numpy() - g["y1"][:, :1]).max() < 1e-4
     (x.sum() + logp.sum() + score.sum()).backward()
+
+
+# ---- fixtures produced by the reference's own source (tests/golden/make_ref_golden.py, tests/_jaxstub) -----------------
+
+def gnn_slices(n_in, feats):
+    out, o = {}, 0
+    out["b_last"] = (o, o + 1); o += 1
+    out["w_last"] = (o, o + feats[-1]); o += feats[-1]
+    prev = n_in
+    for i, h in enumerate(feats):
+        out[f"b{i}"] = (o, o + h); o += h
+        out[f"W{i}"] = (o, o + prev * h); o += prev * h
+        prev = h
+    return out
+
+
+REF_STEP_3D = [("ref_step_h2_bs40", 32), ("ref_step_lih_bs32", 32), ("ref_step_h2o_hgh_b88_vwn_bs48", 32),
+               ("ref_step_c6h6_b88_pw92_bs24", 64), ("ref_step_h2o_zero_init_bs32", 16), ("ref_step_h2o_bench_bs512", 16),
+               ("ref_step_h2o_L1_bs32", 32), ("ref_step_h2o_L3_bs32", 32)]
+
+
+@pytest.mark.parametrize("name,n_steps", REF_STEP_3D)
+def test_reference_source_fixtures_3d(name, n_steps):
+    """y(t1), every energy term and dE/dtheta as the REFERENCE'S OWN SOURCE computes them (unmodified functionals.py /
+    jax_ode.py / equiv_flows.py run under the jax stand-in, adaptive Dopri5 1e-7, float64): the driver-default functional
+    sets (dirac_b88_x_e + vwn_c_e / pw92_c_e), benzene, the --nn 1 / --nn 3 architectures and the benchmark's own
+    parameters at RK4 x16.  North-star tolerances: energy terms 1e-5, gradient 1e-4 per tensor."""
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    feats = tuple(int(v) for v in g["features"])
+    kin, nuc, hart, x, c = (str(v) for v in g["names"])
+    nt = g["onehot"].shape[1]
+    model = Gen_EqvFlow(3, feats, g["coords"], g["onehot"], bool_neg=True)
+    spec = ops.EnergySpec(Ne=float(g["Ne"]), d=3, kin=kin, hart=hart, nuc=nuc, x=x, c=c, coords=g["coords"], z=g["z"])
+    est = EnergyEstimator(model, spec, n_steps=n_steps)
+    sums, tbar, y1 = est.step_flat(dev(g["theta"]), dev(g["batch"]))
+    sums = sums.cpu().numpy(); grad = tbar.cpu().numpy().astype(np.float64)
+    ref_terms = g["terms"]
+    scale = np.abs(ref_terms[:5]).max()
+    for i in range(5):
+        # a term that is a small difference of large per-sample values (e.g. the 1e-3 TF+W mean of benzene) is held to the
+        # tolerance of the total it enters
+        assert abs(sums[i] - ref_terms[i]) <= E_TOL * max(abs(ref_terms[i]), 1e-2 * scale), (i, sums[i], ref_terms[i])
+    assert abs(sums[5] - float(g["energy"])) <= E_TOL * max(abs(float(g["energy"])), 1e-2 * scale)
+    gref = g["grad"].astype(np.float64)
+    for tname, (a, b) in gnn_slices(2 + nt, feats).items():
+        if np.linalg.norm(gref[a:b]) == 0.0:
+            assert np.linalg.norm(grad[a:b]) == 0.0, tname
+        else:
+            assert rel(grad[a:b], gref[a:b]) <= G_TOL, (tname, rel(grad[a:b], gref[a:b]))
+    bs = g["batch"].shape[0] // 2
+    y1 = y1.cpu().numpy()
+    assert np.abs(y1[:bs] - g["y1"][:bs]).max() < 2e-5 * max(1.0, np.abs(g["y1"][:bs]).max())
+    if "rev_x" in g.files:          # rho_rev through the package helper (H20_...py:132-137)
+        rho = utils.rho_rev(model.unravel(dev(g["theta"])), dev(g["rev_x"]), Gen_EqvFlow(3, feats, g["coords"], g["onehot"], bool_neg=False),
+                            utils.ProMolecularDensity(g["z"], g["coords"]), n_steps=n_steps)
+        assert np.abs(rho.cpu().numpy().reshape(-1) / g["rev_rho"][:, 0] - 1.0).max() < 2e-5
+
+
+@pytest.mark.parametrize("name,n_steps", [("ref_step_lih1d_512x3_bs24", 16), ("ref_step_mlp1d_64x2_bs40", 16)])
+def test_reference_source_fixtures_1d(name, n_steps):
+    """LiH.py defaults (tfw_1d / attr / softc / xc_1d, 3 x 512 MLP) from the reference's own cn_flows.py / functionals.py."""
+    from ofdft_nflows_b200.cn_flows import Gen_CNFSimpleMLP
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    feats = tuple(int(v) for v in g["features"])
+    kin, nuc, hart, c = (str(v) for v in g["names"])
+    model = Gen_CNFSimpleMLP(1, feats, bool_neg=True)
+    spec = ops.EnergySpec(Ne=float(g["Ne"]), d=1, kin=kin, hart=hart, nuc=nuc, x="", c=c, R=float(g["R"]), Z_alpha=float(g["Z_alpha"]),
+                          Z_beta=float(g["Z_beta"]))
+    sums, tbar, y1 = EnergyEstimator(model, spec, n_steps=n_steps).step_flat(dev(g["theta"]), dev(g["batch"]))
+    sums = sums.cpu().numpy(); grad = tbar.cpu().numpy().astype(np.float64)
+    for i in (0, 1, 2, 4):
+        assert abs(sums[i] - g["terms"][i]) <= E_TOL * max(abs(g["terms"][i]), 1e-12), (i, sums[i], g["terms"][i])
+    assert abs(sums[5] - float(g["energy"])) <= E_TOL * abs(float(g["energy"]))
+    gref = g["grad"].astype(np.float64)
+    for tname, (a, b) in _mlp_slices(feats).items():
+        assert rel(grad[a:b], gref[a:b]) <= G_TOL, (tname, rel(grad[a:b], gref[a:b]))
+    assert np.abs(y1.cpu().numpy() - g["y1"]).max() < 2e-5 * max(1.0, np.abs(g["y1"]).max())
 
 
 # ---- full-size (BASELINE.json config) properties ---------------------------------------------------------------
