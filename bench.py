@@ -181,10 +181,138 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def _launches_1d(n: int, L: int) -> int:
-    fwd = 2 + (n + 1) + n * (L - 1) if os.environ.get("OFDFT_B200_MLP_FWD", "tc")[0] != "f" else 2
-    bwd = 2 + (n + 1) + n + 2 * n * (L - 1) if os.environ.get("OFDFT_B200_MLP_BWD", "tc")[0] != "f" else 2
+def _launches_1d(n: int, L: int, ffma: bool) -> int:
+    fwd = 2 + (n + 1) + n * (L - 1) if not ffma else 2
+    bwd = 2 + (n + 1) + n + 2 * n * (L - 1) if not ffma else 2
     return fwd + 2 + bwd + 1 + 2 * (L - 1)
+
+
+def _timed(fn, reps: int, warm: int = 1) -> float:
+    """Seconds per call of ``fn`` (device time, CUDA events on the current stream, after ``warm`` untimed calls)."""
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record(); b.synchronize()
+    return a.elapsed_time(b) * 1e-3 / reps
+
+
+def hartree_pairs_block(dev, n: int, ffma_peak: float, sfu_peak: float):
+    """Second half of BASELINE.json's metric: Hartree pairs/s of the tiled all-pairs kernel (north-star item 2) on one GPU,
+    n x n cross-set pairs resident in HBM: energy only, energy + forces on both point sets (two strip passes), and the 1-D
+    soft-Coulomb variant.  Rooflines: one MUFU.RSQ per pair against the measured SFU rate (energy only: 7 FP32 + 1 MUFU
+    per pair; 1-D: 3-6 FP32 + 1 MUFU) and 12 FP32 instructions per pair against the measured FP32 issue rate (3-D forces)."""
+    import torch
+    from ofdft_nflows_b200 import ops
+    g = torch.Generator(device=dev); g.manual_seed(7)
+    x = torch.randn((n, 7), device=dev, generator=g); xp = torch.randn((n, 7), device=dev, generator=g)
+    x1 = torch.randn((n, 3), device=dev, generator=g); xp1 = torch.randn((n, 3), device=dev, generator=g)
+    fp32_slots = ffma_peak / 2.0                      # FP32 instructions per second
+    out = {"n": n, "m": n, "sfu_peak_per_s": sfu_peak, "fp32_instr_peak_per_s": fp32_slots,
+           "peak_source": "ofdft_microbench_sfu / ofdft_microbench_ffma measured in this run"}
+    t = _timed(lambda: ops.hartree_allpairs(x, xp, 10.0, "hartree", want_grad=False), 2)
+    out["energy_only_3d"] = {"kernel": "hartree_pairs_kernel<3,false>", "seconds": t, "pairs_per_s": float(n) * n / t,
+                             "roofline": {"bound": "sfu", "achieved": float(n) * n / t, "peak": sfu_peak, "unit": "rsqrt/s",
+                                          "frac": float(n) * n / t / sfu_peak}}
+    t = _timed(lambda: ops.hartree_allpairs(x, xp, 10.0, "hartree", want_grad=True), 2)
+    ev = 2.0 * n * n
+    bound = min(fp32_slots / 12.0, sfu_peak)
+    out["energy_forces_3d"] = {"kernel": "hartree_pairs_kernel<3,true> x2 (forces on x, then on xp)", "seconds": t,
+                               "pairs_per_s": float(n) * n / t, "pair_evals_per_s": ev / t,
+                               "roofline": {"bound": "fp32", "achieved": ev / t, "peak": bound, "unit": "pair-evals/s",
+                                            "frac": ev / t / bound, "fp32_instr_per_pair_eval": 12}}
+    t = _timed(lambda: ops.hartree_allpairs(x1, xp1, 2.0, "softc", want_grad=True), 2)
+    out["energy_forces_1d_softc"] = {"kernel": "hartree_pairs_kernel<1,true> x2", "seconds": t, "pairs_per_s": float(n) * n / t,
+                                     "pair_evals_per_s": ev / t,
+                                     "roofline": {"bound": "sfu", "achieved": ev / t, "peak": sfu_peak, "unit": "rsqrt/s",
+                                                  "frac": ev / t / sfu_peak}}
+    return out
+
+
+def _gnn_estimator(workload: str, bs: int, rank: int, dev, n_steps: int, hartree_mode: str = "paired", **kw):
+    import torch
+    from ofdft_nflows_b200 import ops
+    from ofdft_nflows_b200.equiv_flows import Gen_EqvFlow
+    from ofdft_nflows_b200.estimator import EnergyEstimator
+    molname, _, nuc = WORKLOADS[workload]
+    mol, nuc, theta_np, batch_np = make_problem(workload, bs, seed_offset=rank)
+    model = Gen_EqvFlow(3, (H, H), mol["coords"], mol["onehot"], bool_neg=True, device=dev)
+    spec = ops.EnergySpec(Ne=mol["Ne"], d=3, kin="tf-w", hart="hartree", nuc=nuc, x="lda", coords=mol["coords"], z=mol["z"])
+    est = EnergyEstimator(model, spec, n_steps=n_steps, hartree_mode=hartree_mode, **kw)
+    return est, torch.as_tensor(theta_np, device=dev), torch.as_tensor(batch_np, device=dev), mol
+
+
+def _max_over_ranks(seconds: float, dev, world: int) -> float:
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([seconds], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t.item()
+
+
+def strong_scaling_block(dev, rank: int, world: int, n_steps: int, global_bs: int, steps: int = 3):
+    """BASELINE.json configs[3]: LiH 3-D equivariant flow, GLOBAL bs = 2^20 sharded over the N ranks (strong scaling: the total
+    work is fixed), and the same global batch on one GPU alone (rank 0; the other ranks wait) for the speed-up."""
+    import torch
+    import torch.distributed as dist
+    bs = global_bs // world
+    est, theta, batch, _ = _gnn_estimator("lih", bs, rank, dev, n_steps)
+    dist.barrier(); torch.cuda.synchronize()
+    t_n = _max_over_ranks(_timed(lambda: est.step_flat(theta, batch), steps), dev, world)
+    del batch
+    torch.cuda.empty_cache()
+    t_1 = 0.0
+    if rank == 0:
+        est1, theta1, batch1, _ = _gnn_estimator("lih", global_bs, 0, dev, n_steps, group=dist.new_group([0]) if False else None)
+        est1._dist = lambda: False                        # this rank alone: no collectives
+        t_1 = _timed(lambda: est1.step_flat(theta1, batch1), 2)
+        del batch1
+        torch.cuda.empty_cache()
+    dist.barrier()
+    t_1 = _max_over_ranks(t_1, dev, world)
+    return {"workload": f"LiH 3-D equivariant flow (64,64), global bs={global_bs} ({2 * global_bs} trajectories) sharded over {world} GPUs, "
+                        f"RK4 x{n_steps}, paired Hartree", "scaling": "strong", "n_gpus": world, "per_gpu_bs": bs,
+            "ms_per_step": 1e3 * t_n, "trajectories_per_s": 2.0 * global_bs / t_n,
+            "one_gpu_same_global_batch": {"ms_per_step": 1e3 * t_1, "trajectories_per_s": 2.0 * global_bs / t_1,
+                                          "note": "rank 0 alone; above the 64 GB activation-checkpoint cap the estimator "
+                                                  "re-integrates row chunks (one extra forward pass)"},
+            "speedup_vs_one_gpu": t_1 / t_n, "collectives_per_step": "2 all-reduces (8 doubles, n_theta floats); no data-path exchange"}
+
+
+def allpairs_block(dev, rank: int, world: int, n_steps: int, bs: int, steps: int = 3):
+    """BASELINE.json configs[4]: benzene-sized (12 nuclei) GNN field with the all-pairs Hartree estimator: coordinates
+    all-gathered over NCCL, every rank evaluates its (bs x N bs) strips with the tiled pair kernel (energy + forces on both
+    halves), energy terms and theta-gradient all-reduced."""
+    import torch
+    import torch.distributed as dist
+    est, theta, batch, _ = _gnn_estimator("c6h6", bs, rank, dev, n_steps, hartree_mode="allpairs")
+    dist.barrier(); torch.cuda.synchronize()
+    timers = []
+    t = _max_over_ranks(_timed(lambda: est.step_flat(theta, batch, timers=timers), steps), dev, world)
+    torch.cuda.synchronize()
+    phase = {}
+    for name, a, b in timers[-3 * 1:] if False else timers:
+        phase.setdefault(name, []).append(a.elapsed_time(b))
+    phase = {k: sum(v[1:]) / max(1, len(v) - 1) for k, v in phase.items()}          # skip the warm-up call
+    pair_s = _max_over_ranks(est.last_pair_seconds, dev, world) if getattr(est, "last_pair_seconds", None) else None
+    gather_s = _max_over_ranks(est.last_gather_seconds, dev, world) if getattr(est, "last_gather_seconds", None) else None
+    evals = 2.0 * bs * (bs * world) * world                 # both strips of every rank
+    out = {"workload": f"C6H6 3-D equivariant flow (64,64), all-pairs Hartree, bs={bs} per GPU ({bs * world} global), RK4 x{n_steps}",
+           "n_gpus": world, "ms_per_step": 1e3 * t, "trajectories_per_s": 2.0 * bs * world / t,
+           "pair_evals_per_step": evals, "phase_ms": phase,
+           "gathered_bytes_per_rank_per_step": 2 * 12 * bs * world}
+    if pair_s:
+        out["pair_phase_ms"] = 1e3 * pair_s
+        out["pair_evals_per_s"] = evals / pair_s
+        out["pair_evals_per_s_per_gpu"] = evals / pair_s / world
+    if gather_s is not None:
+        out["all_gather_ms"] = 1e3 * gather_s
+    return out
 
 
 def main():
@@ -201,6 +329,12 @@ def main():
     ap.add_argument("--hartree", default="paired", choices=["paired", "allpairs"],
                     help="allpairs: O(bs^2) cross-half Hartree estimator (coordinates all-gathered over NCCL, tiled pair kernel)")
     ap.add_argument("--recompute", action="store_true", help="recompute layer-2 activations in the backward pass (no HBM activation checkpoint)")
+    ap.add_argument("--ffma", action="store_true", help="FP32-pipe kernels (ops.PATH_FFMA) instead of the tcgen05 kernels")
+    ap.add_argument("--no-extra-blocks", action="store_true",
+                    help="skip the hartree_pairs block (N=1) and the strong / allpairs blocks (N>1) of the default run")
+    ap.add_argument("--pairs-n", type=int, default=1 << 20, help="points per set of the hartree_pairs block")
+    ap.add_argument("--strong-global-bs", type=int, default=1 << 20, help="global batch of the strong-scaling block (N>1)")
+    ap.add_argument("--allpairs-bs", type=int, default=16384, help="per-GPU batch of the all-pairs block (N>1)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
@@ -237,8 +371,9 @@ def main():
     else:
         model = Gen_EqvFlow(3, (H, H), mol["coords"], mol["onehot"], bool_neg=True, device=dev)
         spec = ops.EnergySpec(Ne=mol["Ne"], d=3, kin="tf-w", hart="hartree", nuc=nuc, x="lda", coords=mol["coords"], z=mol["z"])
+    path = (ops.PATH_FFMA | ops.PATH_FFMA_DW) if args.ffma else ops.PATH_DEFAULT
     est = EnergyEstimator(model, spec, n_steps=args.n_steps, skip_unused_jets=not args.full_jets, act_ckpt=not args.recompute,
-                          hartree_mode=args.hartree)
+                          hartree_mode=args.hartree, path=path)
     theta = torch.as_tensor(theta_np, device=dev)
     params = model.unravel(theta)
     batch = torch.as_tensor(batch_np, device=dev)
@@ -319,13 +454,13 @@ def main():
     kern_avg.setdefault("gnn_bwd", kern_avg.get("mlp_bwd", 0.0)); kern_avg.setdefault("gnn_fwd", kern_avg.get("mlp_fwd", 0.0))
     bwd_s = kern_avg["gnn_bwd"] * 1e-3
     fwd_s = kern_avg["gnn_fwd"] * 1e-3
-    tensor_path = (not is_1d) and (not args.recompute) and os.environ.get("OFDFT_B200_GNN_BWD", "tc")[0] != "f"
+    tensor_path = (not is_1d) and (not args.recompute) and not args.ffma
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    mlp_tc = is_1d and all(os.environ.get(k, "tc")[0] != "f" for k in ("OFDFT_B200_MLP_FWD", "OFDFT_B200_MLP_BWD", "OFDFT_B200_MLP_DW"))
+    mlp_tc = is_1d and not args.ffma
     if mlp_tc:
         # 1-D flow, tensor-core path: every hidden-layer GEMM launch executes (rows padded to 128) x H x H x 3 jets x
         # 3 passes; the adjoint adds the recompute and the transposed GEMMs plus the weight-gradient GEMMs.
@@ -337,21 +472,26 @@ def main():
         dw_flops = (L - 1) * 2.0 * Hm * Hm * (evals * math.ceil(B / 8) * 8 * 3) * 3
         bwd_tensor_flops = 2.0 * evals * (L - 1) * gemm + dw_flops
         tf32_peak = 0.5 * peaks.get("bf16_tflops_sustained", 1400.0)
+        peak3 = tf32_peak / 3.0
         roofline = {
             "bound": "tensor", "kernel": "mlp_layer_gemm_tc_kernel (+ mlp_dw_gemm_tc_kernel) launches of the adjoint",
-            "achieved": bwd_tensor_flops / bwd_s / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
-            "frac": bwd_tensor_flops / bwd_s / 1e12 / tf32_peak, "traffic": None,
-            "peak_source": ("1/2 x bf16_tflops_sustained of MEASURED_PEAKS.json (dense TF32 rate; of measured)" if peaks else
-                            "1/2 x 1.4 PFLOP/s (B200_PROFILING.md fallback; of fallback)"),
+            "achieved": bwd_flops / bwd_s / 1e12, "peak": peak3, "unit": "TFLOP/s (fp32-equivalent)",
+            "frac": bwd_flops / bwd_s / 1e12 / peak3, "traffic": None,
+            "peak_source": ("3xTF32 = 1/3 x 1/2 x bf16_tflops_sustained of MEASURED_PEAKS.json (kernel timed inside the step; of measured)"
+                            if peaks else "1/3 x 1/2 x 1.4 PFLOP/s (B200_PROFILING.md fallback; of fallback)"),
+            "frac_vs_burst_peak": bwd_flops / bwd_s / 1e12 / (0.5 * peaks.get("bf16_tflops", 1640.0) / 3.0),
+            "algorithmic_flops_per_launch": bwd_flops,
             "executed_tensor_flops_per_launch": bwd_tensor_flops,
+            "executed_tensor_frac_of_dense_tf32": bwd_tensor_flops / bwd_s / 1e12 / tf32_peak,
             "note": "3xTF32; one launch per hidden layer and RHS evaluation (a 128-row x 512-unit layer with three jets does "
                     "not fit on chip); 64 of 148 SMs busy at bs=512 -- see DESIGN.md section 3c",
             "fp32_equivalent": {"algorithmic_flops_per_launch": bwd_flops, "achieved": bwd_flops / bwd_s / 1e12,
                                 "ffma_peak": ffma_peak / 1e12, "frac_of_ffma_peak": bwd_flops / bwd_s / ffma_peak,
                                 "peak_source": "ofdft_microbench_ffma measured in this run"},
             "kernel_ms": kern_avg,
-            "fwd": {"kernel": "mlp_layer_gemm_tc_kernel + mlp_glue_tc_kernel", "achieved": fwd_tensor_flops / fwd_s / 1e12,
-                    "frac": fwd_tensor_flops / fwd_s / 1e12 / tf32_peak, "fp32_equivalent_frac_of_ffma_peak": fwd_flops / fwd_s / ffma_peak},
+            "fwd": {"kernel": "mlp_layer_gemm_tc_kernel + mlp_glue_tc_kernel", "achieved": fwd_flops / fwd_s / 1e12,
+                    "frac": fwd_flops / fwd_s / 1e12 / peak3, "executed_tensor_frac_of_dense_tf32": fwd_tensor_flops / fwd_s / 1e12 / tf32_peak,
+                    "fp32_equivalent_frac_of_ffma_peak": fwd_flops / fwd_s / ffma_peak},
             "step": {"algorithmic_flops": 3.0 * fwd_flops, "frac_of_ffma_peak": 3.0 * fwd_flops / (total_s / args.steps) / ffma_peak},
         }
     elif tensor_path:
@@ -364,12 +504,16 @@ def main():
         bwd_tensor_flops = evals * na * mma * (tiles_h * per_h + tiles_l * per_l)
         fwd_tensor_flops = evals * na * mma * (tiles_h * 72 + tiles_l * (24 if jets_b == 1 else 72))
         tf32_peak = 0.5 * peaks.get("bf16_tflops_sustained", 1400.0)
+        peak3 = tf32_peak / 3.0            # an fp32-accurate GEMM costs three TF32 passes
         roofline = {
-            "bound": "tensor", "kernel": "gnn_bwd_tc_kernel", "achieved": bwd_tensor_flops / bwd_s / 1e12, "peak": tf32_peak,
-            "unit": "TFLOP/s", "frac": bwd_tensor_flops / bwd_s / 1e12 / tf32_peak, "traffic": None,
-            "peak_source": ("1/2 x bf16_tflops_sustained of MEASURED_PEAKS.json (dense TF32 rate; of measured)" if peaks else
-                            "1/2 x 1.4 PFLOP/s (B200_PROFILING.md fallback; of fallback)"),
+            "bound": "tensor", "kernel": "gnn_bwd_tc_kernel", "achieved": bwd_flops / bwd_s / 1e12, "peak": peak3,
+            "unit": "TFLOP/s (fp32-equivalent)", "frac": bwd_flops / bwd_s / 1e12 / peak3, "traffic": None,
+            "peak_source": ("3xTF32 = 1/3 x 1/2 x bf16_tflops_sustained of MEASURED_PEAKS.json (kernel timed inside the step; of measured)"
+                            if peaks else "1/3 x 1/2 x 1.4 PFLOP/s (B200_PROFILING.md fallback; of fallback)"),
+            "frac_vs_burst_peak": bwd_flops / bwd_s / 1e12 / (0.5 * peaks.get("bf16_tflops", 1640.0) / 3.0),
+            "algorithmic_flops_per_launch": bwd_flops,
             "executed_tensor_flops_per_launch": bwd_tensor_flops,
+            "executed_tensor_frac_of_dense_tf32": bwd_tensor_flops / bwd_s / 1e12 / tf32_peak,
             "note": "3xTF32 (+1 stacked lo.lo pass in the weight-gradient GEMM): executed tensor flops are 3-4x the "
                     "algorithmic fp32 flops; the kernel is bounded by its FP32/SFU tanh-jet epilogues and operand staging, "
                     "see DESIGN.md section 3",
@@ -377,7 +521,8 @@ def main():
                                 "ffma_peak": ffma_peak / 1e12, "frac_of_ffma_peak": bwd_flops / bwd_s / ffma_peak,
                                 "peak_source": "ofdft_microbench_ffma measured in this run"},
             "kernel_ms": kern_avg,
-            "fwd": {"kernel": "gnn_fwd_tc_kernel", "achieved": fwd_tensor_flops / fwd_s / 1e12, "frac": fwd_tensor_flops / fwd_s / 1e12 / tf32_peak,
+            "fwd": {"kernel": "gnn_fwd_tc_kernel", "achieved": fwd_flops / fwd_s / 1e12, "frac": fwd_flops / fwd_s / 1e12 / peak3,
+                    "executed_tensor_frac_of_dense_tf32": fwd_tensor_flops / fwd_s / 1e12 / tf32_peak,
                     "fp32_equivalent_frac_of_ffma_peak": fwd_flops / fwd_s / ffma_peak},
             "step": {"algorithmic_flops": 3.0 * fwd_flops, "frac_of_ffma_peak": 3.0 * fwd_flops / (total_s / args.steps) / ffma_peak},
         }
@@ -408,6 +553,20 @@ def main():
     except Exception:
         pass
 
+    # ---- the rest of BASELINE.json's metric in the same line: Hartree pairs/s (N = 1) and, where the path communicates,
+    # the strong-scaling (configs[3]) and all-pairs (configs[4]) blocks (N > 1) -------------------------------------------
+    extra = {}
+    default_run = (args.workload == "h2o" and not args.bs and args.hartree == "paired" and not args.no_extra_blocks
+                   and not args.recompute and not args.ffma)
+    if default_run:
+        del batch, flush
+        torch.cuda.empty_cache()
+        if world == 1:
+            extra["hartree_pairs"] = hartree_pairs_block(dev, args.pairs_n, ffma_peak, ops.microbench("sfu"))
+        else:
+            extra["strong"] = strong_scaling_block(dev, rank, world, args.n_steps, args.strong_global_bs)
+            extra["allpairs"] = allpairs_block(dev, rank, world, args.n_steps, args.allpairs_bs)
+
     line = None
     if rank == 0:
         line = {
@@ -428,7 +587,7 @@ def main():
             #   forward  tc: 2 weight preps + (n+1) glue + n (L-1) layer GEMMs          | ffma: prep + fused kernel
             #   adjoint  tc: 2 preps + (n+1) tail + n head + 2 n (L-1) layer GEMMs      | ffma: prep + fused sweep
             #   both: functionals x2, small-gradient reduce, (L-1) x (weight-gradient GEMM + reduce)
-            "gpu_launches": (5 if not is_1d else _launches_1d(4 * args.n_steps, len(MLP_FEAT))) * args.steps,
+            "gpu_launches": (5 if not is_1d else _launches_1d(4 * args.n_steps, len(MLP_FEAT), args.ffma)) * args.steps,
             "roofline": roofline,
             "energy_terms_last_step": [float(v) for v in sums.cpu().numpy()[:6]],
             "hartree": ({"mode": "paired"} if args.hartree == "paired" else
@@ -436,6 +595,7 @@ def main():
                          "pair_evaluations_per_step": 2.0 * (bs * n_gpus) ** 2,
                          "pair_evaluations_per_s": 2.0 * (bs * n_gpus) ** 2 / (total_s / args.steps)}),
         }
+        line.update(extra)
         if n_gpus == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             cbs = 2048 if not is_1d else 256

@@ -32,12 +32,19 @@
 extern "C" {
 #endif
 
-#define OFDFT_B200_ABI_VERSION 2
+#define OFDFT_B200_ABI_VERSION 3
 
 /* error codes (negative) */
 #define OFDFT_EINVAL      (-1)   /* bad argument (null pointer, size <= 0, ...)           */
 #define OFDFT_EUNSUPPORTED (-2)  /* shape outside what the kernels are instantiated for   */
 #define OFDFT_ESCRATCH    (-3)   /* scratch buffer too small                               */
+
+/* kernel-path selector (last argument of the integrator entry points).  The default runs every GEMM-shaped phase on the
+ * tcgen05 tensor cores as 3xTF32; the FP32-pipe kernels are kept as an independently written second implementation that
+ * the parity tests run against the same oracle (and as the recompute path of the GNN adjoint). */
+#define OFDFT_PATH_DEFAULT 0
+#define OFDFT_PATH_FFMA    1     /* integrator / adjoint sweep on the FP32 FFMA pipe                       */
+#define OFDFT_PATH_FFMA_DW 2     /* 1-D flow: weight-gradient GEMM on the FP32 pipe (bit-or with the above) */
 
 /* jets carried per trajectory */
 #define OFDFT_JETS_X      1      /* x only                  (second-half rows: only xp is used, H20_...py:154-156) */
@@ -96,8 +103,11 @@ const char* ofdft_b200_strerror(int code);
 
 /* ---- 3-D equivariant GNN flow: fused fixed-step (RK4) integrator -------------------------------
  * Replaces neural_ode / neural_ode_score (ofdft_normflows/jax_ode.py:9-49, 51-110) evaluated on
- * Gen_EqvFlow (ofdft_normflows/equiv_flows.py:108-127) with features = (64, 64).
- *   theta   : 4289 + 64*(2+n_types) floats          nuclei : (Na,3)     onehot : (Na,n_types)
+ * Gen_EqvFlow (ofdft_normflows/equiv_flows.py:108-127) with features = (64,) * n_layers, n_layers in {1, 2, 3}
+ * (OFDFT_NF.py:320-326; every other driver hard-codes (64, 64)).  n_layers = 2 runs on the tcgen05 tile kernels,
+ * 1 and 3 on a plain FP32 kernel pair (no activation checkpoint: act_ckpt is ignored there).
+ *   theta   : ofdft_cnf_gnn_theta_size(n_types, n_layers) floats (4289 + 64*(2+n_types) for two layers)
+ *   nuclei  : (Na,3)     onehot : (Na,n_types)
  *   y_in    : (B, in_stride)  rows [x | logp | s]; columns beyond what the row's jets need are ignored
  *   y_out   : (B, out_stride) same layout at t1 (only the carried columns are written)
  *   rows [0, n_a) carry jets_a, rows [n_a, B) carry jets_b (one launch, heavy tiles first)
@@ -109,8 +119,11 @@ const char* ofdft_b200_strerror(int code);
  *   y0sign  : +1 (bool_neg=False) or -1 (bool_neg=True): t' = y0*t, output scaled by y0
  *   scratch : ofdft_cnf_gnn_fwd_scratch_bytes() bytes
  *   B = 0 (an empty shard) is a no-op returning OFDFT_OK; the adjoint of an empty shard writes a zero theta_bar.
- *   Na > 16 or n_types > 8 return OFDFT_EUNSUPPORTED (the kernels keep the per-nucleus first-layer offsets on chip).
+ *   Na <= 128 (C27H46O, utils.py:327, has 74), n_types <= 8 and at most 8 DISTINCT one-hot rows (the kernels keep the
+ *   first-layer offset b1 + onehot_i . W1[2:,:] on chip per distinct row); larger shapes return OFDFT_EUNSUPPORTED
+ *   (more than 8 distinct rows trap in the kernel: the rows live in device memory).
  */
+int64_t ofdft_cnf_gnn_theta_size(int32_t n_types, int32_t n_layers);
 size_t ofdft_cnf_gnn_ckpt_bytes(int64_t B, int32_t n_steps);
 size_t ofdft_cnf_gnn_act_ckpt_bytes(int64_t B, int64_t n_a, int32_t jets_a, int32_t jets_b, int32_t Na, int32_t n_steps);
 size_t ofdft_cnf_gnn_fwd_scratch_bytes(void);
@@ -119,7 +132,8 @@ int ofdft_cnf_gnn_fwd(void* stream, const float* theta, const float* nuclei, con
                       void* scratch, size_t scratch_bytes,
                       int64_t B, int64_t n_a, int32_t jets_a, int32_t jets_b,
                       int32_t in_stride, int32_t out_stride,
-                      int32_t Na, int32_t n_types, int32_t n_steps, float t0, float t1, float y0sign);
+                      int32_t Na, int32_t n_types, int32_t n_layers, int32_t n_steps, float t0, float t1, float y0sign,
+                      int32_t path);
 
 /* Discrete adjoint of ofdft_cnf_gnn_fwd (replaces the odeint custom_vjp the reference reaches through
  * jax.value_and_grad, H20_mol_ofdft_min_equiv_flows.py:177-178).
@@ -127,21 +141,23 @@ int ofdft_cnf_gnn_fwd(void* stream, const float* theta, const float* nuclei, con
  *   ybar1     : (B, bar_stride) cotangent of y(t1), rows [xbar | logpbar | sbar]
  *   theta_bar : n_theta floats, OVERWRITTEN with d<ybar1, y(t1)>/d theta
  *   ybar0     : NULL or (B, bar_stride) cotangent of y(t0)
- *   scratch   : ofdft_cnf_gnn_bwd_scratch_bytes(B, n_a, n_types) bytes (one partial gradient per 128-row tile,
+ *   scratch   : ofdft_cnf_gnn_bwd_scratch_bytes(B, n_a, n_types, n_layers) bytes (one partial gradient per 128-row tile,
  *               reduced in fixed order: theta_bar is bitwise reproducible)
  */
-size_t ofdft_cnf_gnn_bwd_scratch_bytes(int64_t B, int64_t n_a, int32_t n_types);
+size_t ofdft_cnf_gnn_bwd_scratch_bytes(int64_t B, int64_t n_a, int32_t n_types, int32_t n_layers);
 int ofdft_cnf_gnn_bwd(void* stream, const float* theta, const float* nuclei, const float* onehot,
                       const float* ckpt, const float* act_ckpt, const float* ybar1, float* theta_bar, float* ybar0,
                       void* scratch, size_t scratch_bytes,
                       int64_t B, int64_t n_a, int32_t jets_a, int32_t jets_b, int32_t bar_stride,
-                      int32_t Na, int32_t n_types, int32_t n_steps, float t0, float t1, float y0sign);
+                      int32_t Na, int32_t n_types, int32_t n_layers, int32_t n_steps, float t0, float t1, float y0sign,
+                      int32_t path);
 
 /* One evaluation of the vector field, f.apply(params, t, states) (equiv_flows.py:124-127) or the
  * score-augmented right-hand side _evol_fn_i (jax_ode.py:80-94):  dy (B, stride) <- d/dt y. */
 int ofdft_cnf_gnn_rhs(void* stream, const float* theta, const float* nuclei, const float* onehot,
                       const float* y, float* dy, void* scratch, size_t scratch_bytes,
-                      int64_t B, int32_t jets, int32_t stride, int32_t Na, int32_t n_types, float t, float y0sign);
+                      int64_t B, int32_t jets, int32_t stride, int32_t Na, int32_t n_types, int32_t n_layers, float t,
+                      float y0sign, int32_t path);
 
 /* ---- 1-D tanh-MLP flow (Gen_CNFSimpleMLP, cn_flows.py:166-182; LiH.py:64-65 uses (512,512,512)) --
  * Same contract as the GNN entry points with d = 1: rows [x | logp | s]; theta per the layout above
@@ -154,18 +170,22 @@ size_t ofdft_cnf_mlp1d_ckpt_bytes(int64_t B, int32_t n_steps);
 size_t ofdft_cnf_mlp1d_scratch_bytes(int64_t B, int32_t H, int32_t n_layers, int32_t n_steps);
 int ofdft_cnf_mlp1d_fwd(void* stream, const float* theta, const float* y_in, float* y_out, float* ckpt,
                         void* scratch, size_t scratch_bytes, int64_t B, int32_t jets, int32_t stride,
-                        int32_t H, int32_t n_layers, int32_t n_steps, float t0, float t1, float y0sign);
+                        int32_t H, int32_t n_layers, int32_t n_steps, float t0, float t1, float y0sign, int32_t path);
+/* One evaluation of the vector field, f.apply(params, t, states) (cn_flows.py:179-182), or of the score-augmented
+ * right-hand side _evol_fn_i (jax_ode.py:80-94):  dy (B, stride) <- d/dt y at time t. */
+int ofdft_cnf_mlp1d_rhs(void* stream, const float* theta, const float* y, float* dy, void* scratch, size_t scratch_bytes,
+                        int64_t B, int32_t jets, int32_t stride, int32_t H, int32_t n_layers, float t, float y0sign);
 int ofdft_cnf_mlp1d_bwd(void* stream, const float* theta, const float* ckpt, const float* ybar1,
                         float* theta_bar, float* ybar0, void* scratch, size_t scratch_bytes,
                         int64_t B, int32_t jets, int32_t stride, int32_t H, int32_t n_layers,
-                        int32_t n_steps, float t0, float t1, float y0sign);
+                        int32_t n_steps, float t0, float t1, float y0sign, int32_t path);
 
 /* ---- functionals: fused per-term reductions + cotangents ----------------------------------------
  * Replaces the functional calls + jnp.mean of `loss` (H20_mol_ofdft_min_equiv_flows.py:150-173,
  * LiH.py:118-138) and their VJP.
  *   y1     : (2*bs, stride) state at t1; rows [0,bs) = x/logp/score, rows [bs,2bs) supply xp
  *   coords : (n_nuclei,3), z : (n_nuclei)  (mol_info, H20_...py:76); HOST pointers (static molecule
- *            tables -- XLA attributes under jax.ffi -- copied into the launch arguments; n_nuclei <= 64);
+ *            tables -- XLA attributes under jax.ffi -- copied into the launch arguments; n_nuclei <= 128);
  *            ignored when d == 1
  *   sums   : OFDFT_N_TERMS float64: per-term MEANS [kin, vnuc, hart, x, c, total, 0, 0]
  *   ybar1  : NULL or (2*bs, stride): d(total mean)/d y1 (all columns written)
@@ -197,16 +217,19 @@ int ofdft_functional_eval(void* stream, int32_t family, const ofdft_energy_spec*
 /* ---- all-pairs Hartree (north-star generalisation of the paired estimator) ----------------------
  * sum_{i<n, j<m} w / sqrt(|x_i - xp_j|^2 + d*eps)   (kind COULOMB, d = 3, w = 0.5 Ne^2)
  * sum_{i,j}      w / sqrt(1 + (x_i - xp_j)^2)       (kind SOFTC,   d = 1, w = Ne^2)
- *   x (n, x_stride), xp (m, x_stride): first d columns are coordinates
- *   esum   : 1 float64, the pair MEAN  (1/(n*m)) * sum
- *   xbar   : NULL or (n, bar_stride) d(esum)/dx in the first d columns;  xpbar : NULL or (m, bar_stride)
- *   accumulate != 0 adds into xbar / xpbar (e.g. the x columns of a state cotangent) instead of overwriting
+ *   x (n, x_stride), xp (m, xp_stride): first d columns are coordinates (state rows as they lie, or packed coordinates)
+ *   norm_pairs : number of pairs the MEAN is taken over; 0 selects n*m.  A rank that evaluates one block of a larger
+ *                pair set (its strip of the all-gathered batch) passes the size of the whole set
+ *   esum   : 1 float64, (1/norm_pairs) * sum
+ *   xbar   : NULL or (n, xbar_stride) d(esum)/dx in the first d columns;  xpbar : NULL or (m, xpbar_stride)
+ *   accumulate != 0 ADDS into esum / xbar / xpbar (e.g. the x columns of a state cotangent) instead of overwriting
  *   scratch: ofdft_hartree_allpairs_scratch_bytes(n, m)
  */
 size_t ofdft_hartree_allpairs_scratch_bytes(int64_t n, int64_t m);
-int ofdft_hartree_allpairs(void* stream, int32_t kind, int32_t d, float Ne, const float* x, const float* xp,
-                           int32_t x_stride, int64_t n, int64_t m, double* esum, float* xbar, float* xpbar,
-                           int32_t bar_stride, int32_t accumulate, void* scratch, size_t scratch_bytes);
+int ofdft_hartree_allpairs(void* stream, int32_t kind, int32_t d, float Ne, const float* x, int32_t x_stride,
+                           const float* xp, int32_t xp_stride, int64_t n, int64_t m, double norm_pairs, double* esum,
+                           float* xbar, int32_t xbar_stride, float* xpbar, int32_t xpbar_stride, int32_t accumulate,
+                           void* scratch, size_t scratch_bytes);
 
 /* ---- callers either side of the path --------------------------------------------
  * Promolecular prior (ofdft_normflows/promolecular_distrax.py:52-62,86-89): mixture of unit-variance Gaussians on the
@@ -217,7 +240,8 @@ int ofdft_promolecular_logp_score(void* stream, const float* coords, const float
                                   int32_t x_stride, int64_t n, const float* sub, int32_t sub_stride, int32_t exp_out,
                                   float* out, float* score);
 /* batch_generator (ofdft_normflows/utils.py:76-108): out (2*bs, 7) rows [x, log rho0(x), grad log rho0(x)], two
- * independent draws; Philox stream (seed, row, offset) -- advance `offset` every call.  1-D variant
+ * independent draws; Philox stream (seed, subsequence = row, skip-ahead = 8*offset outputs): pass offset = call index
+ * (0, 1, 2, ...) -- every call then reads a disjoint stretch of each row's stream (a row consumes 5 outputs per call).  1-D variant
  * (utils.py:110-143 with the N(0,1) prior of LiH.py:78): out (2*bs, 3). */
 int ofdft_batch_generator_3d(void* stream, uint64_t seed, uint64_t offset, const float* coords, const float* z,
                              int32_t n_nuclei, int64_t bs, float* out);
@@ -228,6 +252,12 @@ int ofdft_batch_generator_1d(void* stream, uint64_t seed, uint64_t offset, int64
  * In place on theta (n) and the second-moment state nu (n); max_norm <= 0 disables the clip. */
 int ofdft_rmsprop_clip_step(void* stream, float* theta, const float* grad, float* nu, int64_t n, float lr, float decay,
                             float eps, float max_norm);
+
+/* optax.chain(clip_by_global_norm(max_norm), adam(lr)) as OFDFT_NF.py:104-108 builds it (optax defaults b1 = 0.9, b2 = 0.999,
+ * eps = 1e-8 outside the square root, eps_root = 0).  In place on theta and the moment states mu, nu (n each, initially zero);
+ * step is the 1-based update count (bias correction). */
+int ofdft_adam_clip_step(void* stream, float* theta, const float* grad, float* mu, float* nu, int64_t n, int64_t step, float lr,
+                         float b1, float b2, float eps, float max_norm);
 
 /* Running average of the per-term energy means, optax.ema(decay, debias=True) as the drivers log it
  * (H20_mol_ofdft_min_equiv_flows.py:117-118, 193-196): state <- decay*state + (1-decay)*values, out = state / (1 - decay^step).

@@ -29,26 +29,29 @@ SIGNATURES = {
     "ofdft_cnf_gnn_ckpt_bytes": (szt, [i64, i32]),
     "ofdft_cnf_gnn_fwd_scratch_bytes": (szt, []),
     "ofdft_cnf_gnn_act_ckpt_bytes": (szt, [i64, i64, i32, i32, i32, i32]),
-    "ofdft_cnf_gnn_fwd": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, szt, i64, i64, i32, i32, i32, i32, i32, i32, i32,
-                                    f32, f32, f32]),
-    "ofdft_cnf_gnn_bwd_scratch_bytes": (szt, [i64, i64, i32]),
-    "ofdft_cnf_gnn_bwd": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, szt, i64, i64, i32, i32, i32, i32, i32, i32,
-                                    f32, f32, f32]),
-    "ofdft_cnf_gnn_rhs": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, szt, i64, i32, i32, i32, i32, f32, f32]),
+    "ofdft_cnf_gnn_theta_size": (i64, [i32, i32]),
+    "ofdft_cnf_gnn_fwd": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, szt, i64, i64, i32, i32, i32, i32, i32, i32, i32, i32,
+                                    f32, f32, f32, i32]),
+    "ofdft_cnf_gnn_bwd_scratch_bytes": (szt, [i64, i64, i32, i32]),
+    "ofdft_cnf_gnn_bwd": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, szt, i64, i64, i32, i32, i32, i32, i32, i32, i32,
+                                    f32, f32, f32, i32]),
+    "ofdft_cnf_gnn_rhs": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, szt, i64, i32, i32, i32, i32, i32, f32, f32, i32]),
     "ofdft_cnf_mlp1d_ckpt_bytes": (szt, [i64, i32]),
     "ofdft_cnf_mlp1d_scratch_bytes": (szt, [i64, i32, i32, i32]),
-    "ofdft_cnf_mlp1d_fwd": (C.c_int, [vp, vp, vp, vp, vp, vp, szt, i64, i32, i32, i32, i32, i32, f32, f32, f32]),
-    "ofdft_cnf_mlp1d_bwd": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, szt, i64, i32, i32, i32, i32, i32, f32, f32, f32]),
+    "ofdft_cnf_mlp1d_fwd": (C.c_int, [vp, vp, vp, vp, vp, vp, szt, i64, i32, i32, i32, i32, i32, f32, f32, f32, i32]),
+    "ofdft_cnf_mlp1d_rhs": (C.c_int, [vp, vp, vp, vp, vp, szt, i64, i32, i32, i32, i32, f32, f32]),
+    "ofdft_cnf_mlp1d_bwd": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, szt, i64, i32, i32, i32, i32, i32, f32, f32, f32, i32]),
     "ofdft_functionals_scratch_bytes": (szt, [i64]),
     "ofdft_functionals_fwd_bwd": (C.c_int, [vp, C.POINTER(EnergySpecC), vp, vp, vp, i32, i64, vp, vp, vp, szt]),
     "ofdft_functionals_integrands": (C.c_int, [vp, C.POINTER(EnergySpecC), vp, vp, vp, i32, i64, vp]),
     "ofdft_functional_eval": (C.c_int, [vp, i32, C.POINTER(EnergySpecC), vp, vp, vp, vp, i64, vp, vp, vp]),
     "ofdft_hartree_allpairs_scratch_bytes": (szt, [i64, i64]),
-    "ofdft_hartree_allpairs": (C.c_int, [vp, i32, i32, f32, vp, vp, i32, i64, i64, vp, vp, vp, i32, i32, vp, szt]),
+    "ofdft_hartree_allpairs": (C.c_int, [vp, i32, i32, f32, vp, i32, vp, i32, i64, i64, C.c_double, vp, vp, i32, vp, i32, i32, vp, szt]),
     "ofdft_promolecular_logp_score": (C.c_int, [vp, vp, vp, i32, vp, i32, i64, vp, i32, i32, vp, vp]),
     "ofdft_batch_generator_3d": (C.c_int, [vp, C.c_uint64, C.c_uint64, vp, vp, i32, i64, vp]),
     "ofdft_batch_generator_1d": (C.c_int, [vp, C.c_uint64, C.c_uint64, i64, vp]),
     "ofdft_rmsprop_clip_step": (C.c_int, [vp, vp, vp, vp, i64, f32, f32, f32, f32]),
+    "ofdft_adam_clip_step": (C.c_int, [vp, vp, vp, vp, vp, i64, i64, f32, f32, f32, f32, f32]),
     "ofdft_ema_update": (C.c_int, [vp, vp, vp, vp, i32, i64, C.c_double]),
     "ofdft_microbench_ffma": (C.c_int, [vp, vp, i32, C.POINTER(C.c_double)]),
     "ofdft_microbench_sfu": (C.c_int, [vp, vp, i32, C.POINTER(C.c_double)]),
@@ -76,7 +79,7 @@ def load():
         fn = getattr(lib, name)          # AttributeError if the build is stale: fail loudly
         fn.restype = res
         fn.argtypes = args
-    if lib.ofdft_b200_abi_version() != 2:
+    if lib.ofdft_b200_abi_version() != 3:
         raise RuntimeError("ofdft_nflows_b200: ABI version mismatch between _lib.py and libofdft_b200.so")
     _LIB = lib
     return lib

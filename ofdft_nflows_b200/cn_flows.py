@@ -36,7 +36,10 @@ class Gen_CNFSimpleMLP:
         return {"params": {"cnf": {"net": _init_dense_stack(int(key), 2, self.features, 1, self.device)}}}
 
     def apply(self, params: Dict[str, Any], t: Any, states: torch.Tensor) -> torch.Tensor:
-        raise NotImplementedError("Gen_CNFSimpleMLP.apply: use neural_ode / neural_ode_score (fused integrator)")
+        """``f.apply(params, t, states)`` (jax_ode.py:37, cn_flows.py:173-182): d/dt [x, logp] for states (B, 2); rows
+        (B, 3) also get the score channel of ``_evol_fn_i`` (jax_ode.py:80-98)."""
+        jets = {1: ops.JETS_X, 2: ops.JETS_XLOGP, 3: ops.JETS_FULL}[states.shape[1]]
+        return mlp_rhs(self.flat_theta(params), states, self, float(t), jets)
 
     def flat_theta(self, params: Dict[str, Any]) -> torch.Tensor:
         return _ravel(params["params"]["cnf"]["net"])
@@ -52,8 +55,22 @@ class Gen_CNFSimpleMLP:
 CNF = Gen_CNFSimpleMLP   # LiH.py alias
 
 
-def mlp_fwd(theta, batch, f: Gen_CNFSimpleMLP, t0: float, t1: float, jets: int, n_steps: int, want_ckpt: bool = False
-            ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+def mlp_rhs(theta, y, f: Gen_CNFSimpleMLP, t: float, jets: int) -> torch.Tensor:
+    """ofdft_cnf_mlp1d_rhs: one evaluation of the vector field / score-augmented right-hand side at time t."""
+    lib = _lib.load()
+    theta, y = ops._f32c(theta), ops._f32c(y)
+    B, stride = y.shape
+    dy = torch.zeros_like(y)
+    sb = lib.ofdft_cnf_mlp1d_scratch_bytes(B, f.H, f.n_layers, 1)
+    scratch = torch.empty(sb, dtype=torch.uint8, device=y.device)
+    with ops._on(y):
+        _lib.check(lib.ofdft_cnf_mlp1d_rhs(ops._stream(y), ops._ptr(theta), ops._ptr(y), ops._ptr(dy), ops._ptr(scratch), sb, B,
+                                           jets, stride, f.H, f.n_layers, float(t), f.y0), "ofdft_cnf_mlp1d_rhs")
+    return dy
+
+
+def mlp_fwd(theta, batch, f: Gen_CNFSimpleMLP, t0: float, t1: float, jets: int, n_steps: int, want_ckpt: bool = False,
+            path: int = ops.PATH_DEFAULT) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     """ofdft_cnf_mlp1d_fwd: rows [x | logp | s]."""
     lib = _lib.load()
     theta, batch = ops._f32c(theta), ops._f32c(batch)
@@ -64,14 +81,15 @@ def mlp_fwd(theta, batch, f: Gen_CNFSimpleMLP, t0: float, t1: float, jets: int, 
         ckpt = torch.empty(lib.ofdft_cnf_mlp1d_ckpt_bytes(B, n_steps) // 4, dtype=torch.float32, device=batch.device)
     sb = lib.ofdft_cnf_mlp1d_scratch_bytes(B, f.H, f.n_layers, n_steps)
     scratch = torch.empty(sb, dtype=torch.uint8, device=batch.device)
-    _lib.check(lib.ofdft_cnf_mlp1d_fwd(ops._stream(), ops._ptr(theta), ops._ptr(batch), ops._ptr(y1), ops._ptr(ckpt),
-                                       ops._ptr(scratch), sb, B, jets, stride, f.H, f.n_layers, n_steps,
-                                       float(t0), float(t1), f.y0), "ofdft_cnf_mlp1d_fwd")
+    with ops._on(batch):
+        _lib.check(lib.ofdft_cnf_mlp1d_fwd(ops._stream(batch), ops._ptr(theta), ops._ptr(batch), ops._ptr(y1), ops._ptr(ckpt),
+                                           ops._ptr(scratch), sb, B, jets, stride, f.H, f.n_layers, n_steps,
+                                           float(t0), float(t1), f.y0, int(path)), "ofdft_cnf_mlp1d_fwd")
     return y1, ckpt
 
 
 def mlp_bwd(theta, ckpt, ybar1, f: Gen_CNFSimpleMLP, t0: float, t1: float, jets: int, n_steps: int,
-            want_ybar0: bool = False):
+            want_ybar0: bool = False, path: int = ops.PATH_DEFAULT):
     """ofdft_cnf_mlp1d_bwd: discrete adjoint; returns (theta_bar, ybar0 or None)."""
     lib = _lib.load()
     theta, ybar1 = ops._f32c(theta), ops._f32c(ybar1)
@@ -80,9 +98,10 @@ def mlp_bwd(theta, ckpt, ybar1, f: Gen_CNFSimpleMLP, t0: float, t1: float, jets:
     ybar0 = torch.zeros_like(ybar1) if want_ybar0 else None
     sb = lib.ofdft_cnf_mlp1d_scratch_bytes(B, f.H, f.n_layers, n_steps)
     scratch = torch.empty(sb, dtype=torch.uint8, device=ybar1.device)
-    _lib.check(lib.ofdft_cnf_mlp1d_bwd(ops._stream(), ops._ptr(theta), ops._ptr(ckpt), ops._ptr(ybar1), ops._ptr(tbar),
-                                       ops._ptr(ybar0), ops._ptr(scratch), sb, B, jets, stride, f.H, f.n_layers, n_steps,
-                                       float(t0), float(t1), f.y0), "ofdft_cnf_mlp1d_bwd")
+    with ops._on(ybar1):
+        _lib.check(lib.ofdft_cnf_mlp1d_bwd(ops._stream(ybar1), ops._ptr(theta), ops._ptr(ckpt), ops._ptr(ybar1), ops._ptr(tbar),
+                                           ops._ptr(ybar0), ops._ptr(scratch), sb, B, jets, stride, f.H, f.n_layers, n_steps,
+                                           float(t0), float(t1), f.y0, int(path)), "ofdft_cnf_mlp1d_bwd")
     return tbar, ybar0
 
 
@@ -90,6 +109,11 @@ class _MlpOde(torch.autograd.Function):
     @staticmethod
     def forward(ctx, theta, batch, field, t0, t1, jets, n_steps):
         need = theta.requires_grad or batch.requires_grad
+        if need and jets != ops.JETS_FULL:
+            # the adjoint kernels carry all three channels: differentiate neural_ode through neural_ode_score instead
+            # (pad the rows with a zero score column and leave its cotangent zero)
+            raise NotImplementedError("Gen_CNFSimpleMLP: gradients are implemented for neural_ode_score (rows [x, logp, score]); "
+                                      "pad the batch with a score column to differentiate neural_ode")
         y1, ckpt = mlp_fwd(theta, batch, field, t0, t1, jets, n_steps, want_ckpt=need)
         ctx.field, ctx.cfg = field, (float(t0), float(t1), jets, n_steps)
         ctx.save_for_backward(theta.detach(), ckpt if ckpt is not None else torch.empty(0, device=batch.device))

@@ -9,8 +9,10 @@ namespace ofdft {
 constexpr int kH = 64;          // hidden width of the GNN radial MLP (features = (64, 64))
 constexpr int kTP = 128;        // trajectories per CTA tile
 constexpr int kThreads = 256;   // threads per CTA: warp = (traj-half, unit-group), lane = trajectory pair
-constexpr int kMaxNa = 16;      // nuclei per launch (C6H6 has 12)
+constexpr int kMaxNa = 128;     // nuclei per launch: C27H46O (utils.py:327) has 74
 constexpr int kMaxTypes = 8;
+constexpr int kMaxClasses = 8;  // distinct one-hot rows: the first-layer offset b1 + onehot_i . W1[2:,:] is kept on chip per class
+constexpr int kMaxLayers = 3;   // hidden layers: --nn 1|2|3 selects (64,), (64,64), (64,64,64) (OFDFT_NF.py:320-326)
 
 // theta offsets of the GNN (H = 64, I = 2 + n_types); see include/ofdft_b200.h
 struct GnnThetaLayout {
@@ -21,6 +23,7 @@ struct GnnThetaLayout {
   }
 };
 
+#ifndef OFDFT_HOST_SIM   // (tests/hostsim compiles gnn_general.cu for the CPU: no PTX, no warp intrinsics there)
 // tanh with absolute error ~1e-7: 1 - 2/(2^(2x log2 e) + 1) on the SFU (MUFU.EX2 + MUFU.RCP).
 // tanh.approx.f32 (one MUFU, 2^-11 relative) is too coarse for the 1e-5 energy parity bar.
 __device__ __forceinline__ float tanh_f(float x) {
@@ -79,6 +82,8 @@ __device__ __forceinline__ float warp_vec32_sum(float (&v)[32], int lane) {
   }
   return v[0];
 }
+
+#endif  // OFDFT_HOST_SIM
 
 // activation tiles in shared memory: [jet][unit 0..63][trajectory 0..127] with the 16-byte trajectory
 // chunk XOR-swizzled by the unit index so that both access patterns are conflict-free:

@@ -8,7 +8,7 @@
 namespace ofdft {
 
 constexpr int kFnThreads = 256;
-constexpr int kFnMaxNuc = 64;
+constexpr int kFnMaxNuc = 128;
 
 struct FnArgs {
   ofdft_energy_spec spec;
@@ -235,7 +235,7 @@ constexpr int kHpTile = 256;              // j-points per shared-memory tile
 
 template <int D, bool FORCES>
 __global__ void __launch_bounds__(kHpThreads) hartree_pairs_kernel(const float* __restrict__ x, const float* __restrict__ xp,
-                                                                  int stride, long long n, long long m, float cst,
+                                                                  int stride, int stride_p, long long n, long long m, float cst,
                                                                   int splits, double* __restrict__ epart,
                                                                   float* __restrict__ fpart) {
   __shared__ float4 tile[kHpTile];
@@ -258,8 +258,8 @@ __global__ void __launch_bounds__(kHpThreads) hartree_pairs_kernel(const float* 
       const long long j = jt + threadIdx.x;
       float4 v = make_float4(1e18f, 1e18f, 1e18f, 0.f);   // padded points sit "at infinity": rsqrt -> 0, force -> 0
       if (j < j_end) {
-        v.x = xp[j * stride];
-        if (D == 3) { v.y = xp[j * stride + 1]; v.z = xp[j * stride + 2]; } else { v.y = 0.f; v.z = 0.f; }
+        v.x = xp[j * stride_p];
+        if (D == 3) { v.y = xp[j * stride_p + 1]; v.z = xp[j * stride_p + 2]; } else { v.y = 0.f; v.z = 0.f; }
       }
       tile[threadIdx.x] = v;
     }
@@ -313,14 +313,14 @@ __global__ void hartree_force_reduce_kernel(const float* __restrict__ fpart, flo
   out[o] = accumulate ? out[o] + v : v;
 }
 
-__global__ void hartree_energy_reduce_kernel(const double* __restrict__ epart, int nblk, double scale, double* out) {
+__global__ void hartree_energy_reduce_kernel(const double* __restrict__ epart, int nblk, double scale, double* out, int accumulate) {
   __shared__ double red[8];
   double v = 0.0;
   for (int b = threadIdx.x; b < nblk; b += 256) v += epart[b];
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
   __syncthreads();
-  if (threadIdx.x == 0) { double s = 0.0; for (int w = 0; w < 8; ++w) s += red[w]; *out = s * scale; }
+  if (threadIdx.x == 0) { double s = 0.0; for (int w = 0; w < 8; ++w) s += red[w]; *out = accumulate ? *out + s * scale : s * scale; }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -375,10 +375,13 @@ __global__ void __launch_bounds__(kFnThreads) functional_eval_kernel(const FevAr
   }
 }
 
+// j-range splits per i-block.  Every CTA does the same amount of work, so the grid is made MANY residency waves deep
+// (148 SMs x 8 CTAs): with a grid of only one to two waves a bs/8 x bs strip left 14 % of the SM slots idle
+// (640 CTAs = 4.3 per SM -> the SMs holding 4 waited for those holding 5).  A split keeps at least 8 tiles of j points.
 static int hp_splits(long long n, long long m) {
   const long long blocks_i = (n + kHpThreads * kHpPts - 1) / (kHpThreads * kHpPts);
-  long long s = (592 + blocks_i - 1) / blocks_i;
-  const long long max_s = (m + kHpTile - 1) / kHpTile;
+  long long s = (8 * 1184 + blocks_i - 1) / blocks_i;
+  const long long max_s = (m + 8 * kHpTile - 1) / (8 * kHpTile);
   if (s > max_s) s = max_s;
   if (s > 64) s = 64;
   if (s < 1) s = 1;
@@ -516,22 +519,26 @@ extern "C" size_t ofdft_hartree_allpairs_scratch_bytes(int64_t n, int64_t m) {
   return align256(s1 * blocks1 * sizeof(double)) + align256(f1 > f2 ? f1 : f2);
 }
 
-extern "C" int ofdft_hartree_allpairs(void* stream, int32_t kind, int32_t d, float Ne, const float* x, const float* xp,
-                                      int32_t x_stride, int64_t n, int64_t m, double* esum, float* xbar, float* xpbar,
-                                      int32_t bar_stride, int32_t accumulate, void* scratch, size_t scratch_bytes) {
-  if (!x || !xp || !esum || !scratch || n <= 0 || m <= 0 || x_stride < d || bar_stride < d) return OFDFT_EINVAL;
+extern "C" int ofdft_hartree_allpairs(void* stream, int32_t kind, int32_t d, float Ne, const float* x, int32_t x_stride,
+                                      const float* xp, int32_t xp_stride, int64_t n, int64_t m, double norm_pairs, double* esum,
+                                      float* xbar, int32_t xbar_stride, float* xpbar, int32_t xpbar_stride, int32_t accumulate,
+                                      void* scratch, size_t scratch_bytes) {
+  if (!x || !xp || !esum || !scratch || n <= 0 || m <= 0 || x_stride < d || xp_stride < d) return OFDFT_EINVAL;
+  if ((xbar && xbar_stride < d) || (xpbar && xpbar_stride < d) || norm_pairs < 0.0) return OFDFT_EINVAL;
   float cst, w;
   if (kind == OFDFT_HART_COULOMB && d == 3) { cst = 3e-5f; w = 0.5f * Ne * Ne; }
   else if (kind == OFDFT_HART_SOFTC && d == 1) { cst = 1.0f; w = Ne * Ne; }
   else return OFDFT_EUNSUPPORTED;
   if (scratch_bytes < ofdft_hartree_allpairs_scratch_bytes(n, m)) return OFDFT_ESCRATCH;
   cudaStream_t st = (cudaStream_t)stream;
-  const double scale = (double)w / ((double)n * (double)m);
+  const double scale = (double)w / (norm_pairs > 0.0 ? norm_pairs : (double)n * (double)m);
   for (int pass = 0; pass < 2; ++pass) {
     const float* a = pass == 0 ? x : xp;
     const float* b = pass == 0 ? xp : x;
     const long long na = pass == 0 ? n : m, nb = pass == 0 ? m : n;
     float* out = pass == 0 ? xbar : xpbar;
+    const int sa = pass == 0 ? x_stride : xp_stride, sb = pass == 0 ? xp_stride : x_stride;
+    const int bar_stride = pass == 0 ? xbar_stride : xpbar_stride;
     if (pass == 1 && out == nullptr) break;
     const int splits = hp_splits(na, nb);
     const unsigned blocks = (unsigned)((na + kHpThreads * kHpPts - 1) / (kHpThreads * kHpPts));
@@ -541,14 +548,14 @@ extern "C" int ofdft_hartree_allpairs(void* stream, int32_t kind, int32_t d, flo
     dim3 grid(blocks, (unsigned)splits);
     double* ep = pass == 0 ? epart : nullptr;
     float* fp = out ? fpart : nullptr;
-    if (d == 3 && fp) hartree_pairs_kernel<3, true><<<grid, kHpThreads, 0, st>>>(a, b, x_stride, na, nb, cst, splits, ep, fp);
-    else if (d == 3) hartree_pairs_kernel<3, false><<<grid, kHpThreads, 0, st>>>(a, b, x_stride, na, nb, cst, splits, ep, fp);
-    else if (fp) hartree_pairs_kernel<1, true><<<grid, kHpThreads, 0, st>>>(a, b, x_stride, na, nb, cst, splits, ep, fp);
-    else hartree_pairs_kernel<1, false><<<grid, kHpThreads, 0, st>>>(a, b, x_stride, na, nb, cst, splits, ep, fp);
+    if (d == 3 && fp) hartree_pairs_kernel<3, true><<<grid, kHpThreads, 0, st>>>(a, b, sa, sb, na, nb, cst, splits, ep, fp);
+    else if (d == 3) hartree_pairs_kernel<3, false><<<grid, kHpThreads, 0, st>>>(a, b, sa, sb, na, nb, cst, splits, ep, fp);
+    else if (fp) hartree_pairs_kernel<1, true><<<grid, kHpThreads, 0, st>>>(a, b, sa, sb, na, nb, cst, splits, ep, fp);
+    else hartree_pairs_kernel<1, false><<<grid, kHpThreads, 0, st>>>(a, b, sa, sb, na, nb, cst, splits, ep, fp);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
     if (pass == 0) {
-      hartree_energy_reduce_kernel<<<1, 256, 0, st>>>(epart, (int)(blocks * splits), scale, esum);
+      hartree_energy_reduce_kernel<<<1, 256, 0, st>>>(epart, (int)(blocks * splits), scale, esum, accumulate);
       e = cudaGetLastError();
       if (e != cudaSuccess) return (int)e;
     }

@@ -22,8 +22,7 @@ struct SmemFwd {
   float W2[kH * kH];
   float A[3 * kJetStride];           // layer-1 activation jets a, a', a''
   float wr[kH], wt[kH], b2[kH], w3[kH];
-  float cb[kMaxNa * kH];             // b1 + onehot_i . W1[2:,:]
-  float nuc[kMaxNa * 4];
+  NucTables T;                       // nuclei, per-class b1 + onehot_i . W1[2:,:]
   float xs[3 * kTP];                 // stage positions of the tile
   float Fpart[4 * 3 * kTP];          // per unit-group partial f, f', f''
   int tile;
@@ -35,9 +34,8 @@ struct SmemBwd {
   float A[2 * kJetStride];           // a, a'   (a'' = -2 w_r a a' is recomputed)
   float PB[3 * kJetStride];          // cotangents of the layer-2 pre-activation jets
   float wr[kH], wt[kH], b2[kH], w3[kH], wr2[kH];
-  float cb[kMaxNa * kH];
-  float nuc[kMaxNa * 4];
-  float S[2 * kMaxNa * kH];          // per (half, nucleus): sum of layer-1 pre-activation cotangents
+  NucTables T;
+  float S[2 * kMaxClasses * kH];     // per (half, nucleus class): sum of layer-1 pre-activation cotangents
   float xs[3 * kTP];
   float fbar[3 * kTP];
   float Fpart[4 * 3 * kTP];
@@ -205,13 +203,7 @@ __device__ __forceinline__ void load_small(SM& sm, const float* __restrict__ the
     sm.b2[tid] = theta[L.b2 + tid];
     sm.w3[tid] = theta[L.w3 + tid];
   }
-  for (int i = tid; i < Na * kH; i += kThreads) {
-    const int n = i / kH, k = i % kH;
-    float c = theta[L.b1 + k];
-    for (int t = 0; t < n_types; ++t) c = fmaf(onehot[n * n_types + t], theta[L.W1 + (2 + t) * kH + k], c);
-    sm.cb[i] = c;
-  }
-  if (tid < Na * 3) sm.nuc[(tid / 3) * 4 + (tid % 3)] = nuclei[tid];
+  load_nuc_tables<kThreads>(sm.T, theta, L, nuclei, onehot, Na, n_types);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -242,7 +234,7 @@ __device__ void fwd_tile(SmemFwd& sm, const GnnFwdArgs& a, long long row0, long 
   float rr[2];
 
   auto combine = [&](int i) {
-    const float* nc = sm.nuc + i * 4;
+    const float* nc = sm.T.nuc + i * 4;
     float f0 = b3, f1 = 0.f, f2 = 0.f;
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -291,7 +283,7 @@ __device__ void fwd_tile(SmemFwd& sm, const GnnFwdArgs& a, long long row0, long 
       __syncthreads();
       for (int i = 0; i < a.Na; ++i) {
         if (owner && i > 0) combine(i - 1);
-        first_layer<NJ, true>(sm.A, sm.xs, sm.wr, sm.wt, sm.cb + i * kH, sm.nuc + i * 4, tprime, half, ug, lane, rr);
+        first_layer<NJ, true>(sm.A, sm.xs, sm.wr, sm.wt, sm.T.cb + sm.T.cls[i] * kH, sm.T.nuc + i * 4, tprime, half, ug, lane, rr);
         __syncthreads();
         gemm64<NJ, true>(acc, sm.A, sm.W2, nullptr, half, ug, lane);
         float* actp = nullptr;
@@ -458,7 +450,7 @@ __device__ __forceinline__ void epilogue_b1(const float (&acc)[NJ][2][16], SmemB
   *reinterpret_cast<float2*>(sm.Rpart + ug * kTP + tp0) = make_float2(rp[0], rp[1]);
   const float red = warp_vec32_sum(v32, lane);
   if (lane < 16) {
-    sm.S[(half * kMaxNa + nucleus) * kH + ug * 16 + lane] += red;
+    sm.S[(half * kMaxClasses + nucleus) * kH + ug * 16 + lane] += red;
     G.g_wtwr = fmaf(tprime, red, G.g_wtwr);
   } else {
     G.g_wtwr += red;
@@ -537,7 +529,7 @@ __device__ void bwd_tile(SmemBwd& sm, const GnnBwdArgs& a, long long row0, long 
 
   // owner: cotangents of f, f', f'' for nucleus i -> sm.fbar
   auto pre = [&](int i) {
-    const float* nc = sm.nuc + i * 4;
+    const float* nc = sm.T.nuc + i * 4;
     const float d0 = xst[0] - nc[0], d1 = xst[1] - nc[1], d2 = xst[2] - nc[2];
     const float alpha = fmaf(d0, kx[0], fmaf(d1, kx[1], d2 * kx[2]));
     float f0b = alpha, f1b = 0.f, f2b = 0.f;
@@ -562,7 +554,7 @@ __device__ void bwd_tile(SmemBwd& sm, const GnnBwdArgs& a, long long row0, long 
   };
   // owner: explicit + network contributions of nucleus i to the stage-state cotangent
   auto post = [&](int i) {
-    const float* nc = sm.nuc + i * 4;
+    const float* nc = sm.T.nuc + i * 4;
     float f0 = b3, f1 = 0.f, f2 = 0.f, rbar = 0.f;
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -640,13 +632,13 @@ __device__ void bwd_tile(SmemBwd& sm, const GnnBwdArgs& a, long long row0, long 
                 acc[jt][tr][4 * g] = v.x; acc[jt][tr][4 * g + 1] = v.y; acc[jt][tr][4 * g + 2] = v.z; acc[jt][tr][4 * g + 3] = v.w;
               }
         }
-        first_layer<NJ, false>(sm.A, sm.xs, sm.wr, sm.wt, sm.cb + i * kH, sm.nuc + i * 4, tprime, half, ug, lane, rr);
+        first_layer<NJ, false>(sm.A, sm.xs, sm.wr, sm.wt, sm.T.cb + sm.T.cls[i] * kH, sm.T.nuc + i * 4, tprime, half, ug, lane, rr);
         __syncthreads();
         if (!ACT) gemm64<NJ, false>(acc, sm.A, sm.W2, sm.wr2, half, ug, lane);
         epilogue_bwd<NJ, ACT>(acc, sm, G, half, ug, lane);
         __syncthreads();
         gemm64<NJ, true>(acc, sm.PB, sm.W2T, nullptr, half, ug, lane);
-        epilogue_b1<NJ>(acc, sm, G, rr, tprime, i, half, ug, lane);
+        epilogue_b1<NJ>(acc, sm, G, rr, tprime, sm.T.cls[i], half, ug, lane);
         dw2_accum<NJ>(G, sm, w, lane);
         __syncthreads();
         if (owner) {
@@ -713,17 +705,17 @@ __device__ void flush_tile_grad(SmemBwd& sm, BwdAccum& G, float* __restrict__ ou
   }
   if (tid < kH) {
     float sb1 = 0.f;
-    for (int n = 0; n < Na; ++n) sb1 += sm.S[(0 * kMaxNa + n) * kH + tid] + sm.S[(1 * kMaxNa + n) * kH + tid];
+    for (int c = 0; c < sm.T.n_cls; ++c) sb1 += sm.S[(0 * kMaxClasses + c) * kH + tid] + sm.S[(1 * kMaxClasses + c) * kH + tid];
     out[L.b1 + tid] = sb1;
     for (int t = 0; t < n_types; ++t) {
       float s = 0.f;
-      for (int n = 0; n < Na; ++n)
-        s = fmaf(onehot[n * n_types + t], sm.S[(0 * kMaxNa + n) * kH + tid] + sm.S[(1 * kMaxNa + n) * kH + tid], s);
+      for (int c = 0; c < sm.T.n_cls; ++c)
+        s = fmaf(onehot[sm.T.rep[c] * n_types + t], sm.S[(0 * kMaxClasses + c) * kH + tid] + sm.S[(1 * kMaxClasses + c) * kH + tid], s);
       out[L.W1 + (2 + t) * kH + tid] = s;
     }
   }
   __syncthreads();
-  for (int i = tid; i < 2 * kMaxNa * kH; i += kThreads) sm.S[i] = 0.f;
+  for (int i = tid; i < 2 * kMaxClasses * kH; i += kThreads) sm.S[i] = 0.f;
 }
 
 template <bool ACT>
@@ -735,7 +727,7 @@ __global__ void __launch_bounds__(kThreads, 1) gnn_bwd_kernel(const GnnBwdArgs a
   const GnnThetaLayout L(a.n_types);
   for (int i = tid; i < kH * kH; i += kThreads) sm.W2T[(i % kH) * kH + (i / kH)] = a.theta[L.W2 + i];
   if (tid < kH) sm.wr2[tid] = -2.0f * a.theta[L.W1 + kH + tid];
-  for (int i = tid; i < 2 * kMaxNa * kH; i += kThreads) sm.S[i] = 0.f;
+  for (int i = tid; i < 2 * kMaxClasses * kH; i += kThreads) sm.S[i] = 0.f;
   const float b3 = a.theta[0];
   BwdAccum G;
 #pragma unroll
@@ -780,10 +772,10 @@ static int num_sms() {
   return n;
 }
 
-static int check_common(long long B, long long n_a, int ja, int jb, int Na, int nt, int n_steps) {
+static int check_common(long long B, long long n_a, int ja, int jb, int Na, int nt, int L, int n_steps) {
   if (B < 0 || n_a < 0 || n_a > B || n_steps <= 0) return OFDFT_EINVAL;
   if (ja < 1 || ja > 3 || jb < 1 || jb > 3) return OFDFT_EINVAL;
-  if (Na < 1 || Na > kMaxNa || nt < 0 || nt > kMaxTypes) return OFDFT_EUNSUPPORTED;
+  if (Na < 1 || Na > kMaxNa || nt < 0 || nt > kMaxTypes || L < 1 || L > kMaxLayers) return OFDFT_EUNSUPPORTED;
   return 0;
 }
 
@@ -802,22 +794,22 @@ extern "C" size_t ofdft_cnf_gnn_act_ckpt_bytes(int64_t B, int64_t n_a, int32_t j
 }
 extern "C" size_t ofdft_cnf_gnn_fwd_scratch_bytes(void) { return kCounterBytes; }
 static long long n_tiles_of(long long B, long long n_a) { return (n_a + kTP - 1) / kTP + (B - n_a + kTP - 1) / kTP; }
-extern "C" size_t ofdft_cnf_gnn_bwd_scratch_bytes(int64_t B, int64_t n_a, int32_t n_types) {
+extern "C" int64_t ofdft_cnf_gnn_theta_size(int32_t n_types, int32_t n_layers) {
+  if (n_types < 0 || n_types > kMaxTypes || n_layers < 1 || n_layers > kMaxLayers) return 0;
+  return gnn_general_theta_size(n_types, n_layers);
+}
+extern "C" size_t ofdft_cnf_gnn_bwd_scratch_bytes(int64_t B, int64_t n_a, int32_t n_types, int32_t n_layers) {
   if (B <= 0 || n_a < 0 || n_a > B) return kCounterBytes;
-  return kCounterBytes + (size_t)n_tiles_of(B, n_a) * GnnThetaLayout(n_types).n * sizeof(float);
+  return kCounterBytes + (size_t)n_tiles_of(B, n_a) * (size_t)ofdft_cnf_gnn_theta_size(n_types, n_layers) * sizeof(float);
 }
 
-// OFDFT_B200_GNN_FWD = "tc" (default: tcgen05 3xTF32 layer-2 GEMM) | "ffma" (FP32-pipe kernel of this file)
-static bool use_tc_forward() {
-  const char* e = getenv("OFDFT_B200_GNN_FWD");
-  return !(e != nullptr && e[0] == 'f');
-}
-
-static int launch_fwd(void* stream, GnnFwdArgs& a, void* scratch, size_t scratch_bytes) {
+// path: OFDFT_PATH_DEFAULT (tcgen05 3xTF32 layer-2 GEMM, gnn_tc.cu) | OFDFT_PATH_FFMA (FP32-pipe kernel of this file)
+static int launch_fwd(void* stream, GnnFwdArgs& a, void* scratch, size_t scratch_bytes, int path, int n_layers) {
   if (!a.theta || !a.nuclei || !a.y_in || !a.y_out || !scratch) return OFDFT_EINVAL;
   if (a.n_types > 0 && !a.onehot) return OFDFT_EINVAL;
   if (scratch_bytes < kCounterBytes) return OFDFT_ESCRATCH;
-  if (use_tc_forward()) return launch_gnn_fwd_tc(stream, a, scratch, scratch_bytes);
+  if (n_layers != 2) return launch_gnn_general_fwd(stream, a, scratch, scratch_bytes, n_layers);   // gnn_general.cu
+  if (!(path & OFDFT_PATH_FFMA)) return launch_gnn_fwd_tc(stream, a, scratch, scratch_bytes);
   cudaStream_t st = (cudaStream_t)stream;
   a.counter = (int*)scratch;
   cudaError_t e = cudaMemsetAsync(scratch, 0, kCounterBytes, st);
@@ -836,49 +828,52 @@ extern "C" int ofdft_cnf_gnn_fwd(void* stream, const float* theta, const float* 
                                  void* scratch, size_t scratch_bytes,
                                  int64_t B, int64_t n_a, int32_t jets_a, int32_t jets_b,
                                  int32_t in_stride, int32_t out_stride,
-                                 int32_t Na, int32_t n_types, int32_t n_steps, float t0, float t1, float y0sign) {
-  int rc = check_common(B, n_a, jets_a, jets_b, Na, n_types, n_steps);
+                                 int32_t Na, int32_t n_types, int32_t n_layers, int32_t n_steps, float t0, float t1,
+                                 float y0sign, int32_t path) {
+  int rc = check_common(B, n_a, jets_a, jets_b, Na, n_types, n_layers, n_steps);
   if (rc) return rc;
   if (B == 0) return 0;   // empty shard: nothing to integrate
   const int jmax = jets_a > jets_b ? jets_a : jets_b;
   const int need = jmax == 3 ? 7 : (jmax == 2 ? 4 : 3);
   if (in_stride < need || out_stride < need) return OFDFT_EINVAL;
   GnnFwdArgs a{theta, nuclei, onehot, y_in, y_out, ckpt, nullptr, B, n_a, jets_a, jets_b, in_stride, out_stride,
-               Na, n_types, n_steps, t0, t1, y0sign, 0, 0.f, act_ckpt, pad_rows(n_a), pad_rows(B - n_a)};
-  return launch_fwd(stream, a, scratch, scratch_bytes);
+               Na, n_types, n_steps, t0, t1, y0sign, 0, 0.f, n_layers == 2 ? act_ckpt : nullptr, pad_rows(n_a), pad_rows(B - n_a)};
+  return launch_fwd(stream, a, scratch, scratch_bytes, path, n_layers);
 }
 
 extern "C" int ofdft_cnf_gnn_rhs(void* stream, const float* theta, const float* nuclei, const float* onehot,
                                  const float* y, float* dy, void* scratch, size_t scratch_bytes,
-                                 int64_t B, int32_t jets, int32_t stride, int32_t Na, int32_t n_types,
-                                 float t, float y0sign) {
-  int rc = check_common(B, B, jets, jets, Na, n_types, 1);
+                                 int64_t B, int32_t jets, int32_t stride, int32_t Na, int32_t n_types, int32_t n_layers,
+                                 float t, float y0sign, int32_t path) {
+  int rc = check_common(B, B, jets, jets, Na, n_types, n_layers, 1);
   if (rc) return rc;
   if (B == 0) return 0;
   const int need = jets == 3 ? 7 : (jets == 2 ? 4 : 3);
   if (stride < need) return OFDFT_EINVAL;
   GnnFwdArgs a{theta, nuclei, onehot, y, dy, nullptr, nullptr, B, B, jets, jets, stride, stride,
                Na, n_types, 1, 0.f, 1.f, y0sign, 1, t, nullptr, 0, 0};
-  return launch_fwd(stream, a, scratch, scratch_bytes);
+  return launch_fwd(stream, a, scratch, scratch_bytes, path, n_layers);
 }
 
 extern "C" int ofdft_cnf_gnn_bwd(void* stream, const float* theta, const float* nuclei, const float* onehot,
                                  const float* ckpt, const float* act_ckpt, const float* ybar1, float* theta_bar,
                                  float* ybar0, void* scratch, size_t scratch_bytes,
                                  int64_t B, int64_t n_a, int32_t jets_a, int32_t jets_b, int32_t bar_stride,
-                                 int32_t Na, int32_t n_types, int32_t n_steps, float t0, float t1, float y0sign) {
-  int rc = check_common(B, n_a, jets_a, jets_b, Na, n_types, n_steps);
+                                 int32_t Na, int32_t n_types, int32_t n_layers, int32_t n_steps, float t0, float t1,
+                                 float y0sign, int32_t path) {
+  int rc = check_common(B, n_a, jets_a, jets_b, Na, n_types, n_layers, n_steps);
   if (rc) return rc;
+  const int n_theta = (int)ofdft_cnf_gnn_theta_size(n_types, n_layers);
   if (B == 0) {           // empty shard: the gradient of an empty sum
     if (!theta_bar) return OFDFT_EINVAL;
-    return (int)cudaMemsetAsync(theta_bar, 0, (size_t)GnnThetaLayout(n_types).n * sizeof(float), (cudaStream_t)stream);
+    return (int)cudaMemsetAsync(theta_bar, 0, (size_t)n_theta * sizeof(float), (cudaStream_t)stream);
   }
   if (!theta || !nuclei || !ckpt || !ybar1 || !theta_bar || !scratch) return OFDFT_EINVAL;
   if (n_types > 0 && !onehot) return OFDFT_EINVAL;
   const int jmax = jets_a > jets_b ? jets_a : jets_b;
   const int need = jmax == 3 ? 7 : (jmax == 2 ? 4 : 3);
   if (bar_stride < need) return OFDFT_EINVAL;
-  if (scratch_bytes < ofdft_cnf_gnn_bwd_scratch_bytes(B, n_a, n_types)) return OFDFT_ESCRATCH;
+  if (scratch_bytes < ofdft_cnf_gnn_bwd_scratch_bytes(B, n_a, n_types, n_layers)) return OFDFT_ESCRATCH;
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e = cudaMemsetAsync(scratch, 0, kCounterBytes, st);
   if (e != cudaSuccess) return (int)e;
@@ -892,17 +887,18 @@ extern "C" int ofdft_cnf_gnn_bwd(void* stream, const float* theta, const float* 
   float* gpart = (float*)((char*)scratch + kCounterBytes);
   GnnBwdArgs a{theta, nuclei, onehot, ckpt, ybar1, ybar0, gpart, (int*)scratch, B, n_a, jets_a, jets_b, bar_stride,
                Na, n_types, n_steps, t0, t1, y0sign, act_ckpt, pad_rows(n_a), pad_rows(B - n_a)};
-  // OFDFT_B200_GNN_BWD = "tc" (default with an activation checkpoint: tcgen05 3xTF32 GEMMs) | "ffma"
-  const char* envb = getenv("OFDFT_B200_GNN_BWD");
-  const bool tc_bwd = act_ckpt != nullptr && !(envb != nullptr && envb[0] == 'f');
-  if (tc_bwd) {
+  // default with an activation checkpoint: tcgen05 3xTF32 GEMMs; OFDFT_PATH_FFMA or no checkpoint: FP32-pipe kernels
+  const bool tc_bwd = act_ckpt != nullptr && !(path & OFDFT_PATH_FFMA);
+  if (n_layers != 2) {
+    const int rc2 = launch_gnn_general_bwd(stream, a, n_layers);      // gnn_general.cu (no activation checkpoint)
+    if (rc2) return rc2;
+  } else if (tc_bwd) {
     const int rc = launch_gnn_bwd_tc(stream, a, grid);
     if (rc) return rc;
   } else if (act_ckpt != nullptr) gnn_bwd_kernel<true><<<grid, kThreads, sizeof(SmemBwd), st>>>(a);
   else gnn_bwd_kernel<false><<<grid, kThreads, sizeof(SmemBwd), st>>>(a);
   e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
-  const int n = GnnThetaLayout(n_types).n;
-  gnn_grad_reduce_kernel<<<(n + 127) / 128, 128, 0, st>>>(gpart, theta_bar, n, (int)tiles);
+  gnn_grad_reduce_kernel<<<(n_theta + 127) / 128, 128, 0, st>>>(gpart, theta_bar, n_theta, (int)tiles);
   return (int)cudaGetLastError();
 }

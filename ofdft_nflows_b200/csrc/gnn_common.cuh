@@ -34,6 +34,55 @@ struct ActLayout {
   }
 };
 
+// Per-nucleus tables on chip.  Nuclei with identical one-hot rows share the first-layer offset cb = b1 + onehot . W1[2:,:]
+// (a "class": one per species), so 128 nuclei cost 2.5 KB of shared memory instead of 32 KB; the adjoint accumulates the
+// first-layer pre-activation cotangents per class as well.  More than kMaxClasses distinct rows trap.
+struct alignas(16) NucTables {
+  float nuc[kMaxNa * 4];
+  float cb[kMaxClasses * kH];
+  int cls[kMaxNa];        // nucleus -> class
+  int rep[kMaxClasses];   // class -> first nucleus carrying that one-hot row
+  int n_cls;
+};
+
+template <int THREADS>
+__device__ __forceinline__ void load_nuc_tables(NucTables& T, const float* __restrict__ theta, const GnnThetaLayout& L,
+                                                const float* __restrict__ nuclei, const float* __restrict__ onehot, int Na,
+                                                int n_types) {
+  const int tid = threadIdx.x;
+  for (int n = tid; n < Na; n += THREADS) {
+    T.nuc[n * 4 + 0] = nuclei[n * 3 + 0]; T.nuc[n * 4 + 1] = nuclei[n * 3 + 1]; T.nuc[n * 4 + 2] = nuclei[n * 3 + 2];
+    T.nuc[n * 4 + 3] = 0.f;
+    int first = n;
+    for (int m = 0; m < n && first == n; ++m) {
+      bool same = true;
+      for (int t = 0; t < n_types; ++t) same = same && (onehot[m * n_types + t] == onehot[n * n_types + t]);
+      if (same) first = m;
+    }
+    T.cls[n] = first;       // provisional: index of the first nucleus with the same row
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int c = 0;
+    for (int n = 0; n < Na; ++n) {
+      if (T.cls[n] == n) {
+        if (c == kMaxClasses) __trap();
+        T.rep[c] = n; T.cls[n] = c++;
+      } else {
+        T.cls[n] = T.cls[T.cls[n]];
+      }
+    }
+    T.n_cls = c;
+  }
+  __syncthreads();
+  for (int i = tid; i < T.n_cls * kH; i += THREADS) {
+    const int n = T.rep[i / kH], k = i % kH;
+    float c = theta[L.b1 + k];
+    for (int t = 0; t < n_types; ++t) c = fmaf(onehot[n * n_types + t], theta[L.W1 + (2 + t) * kH + k], c);
+    T.cb[i] = c;
+  }
+}
+
 // offset of (unit group g = unit/4, row) inside one jet block of `rows` trajectories
 __host__ __device__ __forceinline__ long long act_group_off(int g, long long row, long long rows) { return ((long long)g * rows + row) * 4; }
 
@@ -53,5 +102,10 @@ inline long long pad_rows(long long n) { return (n + kTP - 1) / kTP * kTP; }
 int launch_gnn_fwd_tc(void* stream, GnnFwdArgs& a, void* scratch, size_t scratch_bytes);
 // tensor-core backward (needs a.act != nullptr); the caller has reset the tile counter and reduces gpart afterwards
 int launch_gnn_bwd_tc(void* stream, GnnBwdArgs& a, int grid);
+
+// general-depth kernels (gnn_general.cu): 1 or 3 hidden layers
+int gnn_general_theta_size(int n_types, int n_layers);
+int launch_gnn_general_fwd(void* stream, GnnFwdArgs& a, void* scratch, size_t scratch_bytes, int n_layers);
+int launch_gnn_general_bwd(void* stream, GnnBwdArgs& a, int n_layers);
 
 }  // namespace ofdft

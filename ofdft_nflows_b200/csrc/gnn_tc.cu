@@ -29,8 +29,7 @@ struct SmemTcT {
   float Abuf[NB][NB == 1 ? 1 : 2][kH * kTP];   // [jet buffer][hi/lo][16 chunks][128 rows][4]; NB == 1: lo only (hi in TMEM)
   float Whi[kH * kH], Wlo[kH * kH];  // B operand: [16 chunks of k][64 rows j][4]
   float wr[kH], wt[kH], b2[kH], w3[kH];
-  float cb[kMaxNa * kH];
-  float nuc[kMaxNa * 4];
+  NucTables T;
   float xs[3 * kTP];
   float Fpart[4 * 3 * kTP];
   uint64_t bar[3];
@@ -101,7 +100,7 @@ __device__ void fwd_tile_tc(SmemTcT<NB>& sm, const GnnFwdArgs& a, long long row0
   const uint64_t dWl = tc::make_desc(tc::smem_u32(sm.Wlo), kChunkBytesB, 128);
 
   auto combine = [&](int i) {
-    const float* nc = sm.nuc + i * 4;
+    const float* nc = sm.T.nuc + i * 4;
     float f0 = b3, f1 = 0.f, f2 = 0.f;
 #pragma unroll
     for (int q = 0; q < NU; ++q) {
@@ -153,10 +152,10 @@ __device__ void fwd_tile_tc(SmemTcT<NB>& sm, const GnnFwdArgs& a, long long row0
         // ---- first layer for (trajectory m, units 32*uh ..): a = tanh(w_r r + c), a' = (1-a^2) w_r, a'' = -2 a a' w_r ----
         float av[UPT];
         {
-          const float* nc = sm.nuc + i * 4;
+          const float* nc = sm.T.nuc + i * 4;
           const float d0 = sm.xs[m] - nc[0], d1 = sm.xs[kTP + m] - nc[1], d2 = sm.xs[2 * kTP + m] - nc[2];
           const float r = sqrtf(fmaf(d0, d0, fmaf(d1, d1, d2 * d2)));
-          const float* cbi = sm.cb + i * kH + UPT * uh;
+          const float* cbi = sm.T.cb + sm.T.cls[i] * kH + UPT * uh;
 #pragma unroll
           for (int u = 0; u < UPT; ++u)
             av[u] = tanh_f(fmaf(sm.wr[UPT * uh + u], r, fmaf(tprime, sm.wt[UPT * uh + u], cbi[u])));
@@ -348,13 +347,7 @@ __global__ void __launch_bounds__(kTP * NU, NB == 1 ? 2 : 1) gnn_fwd_tc_kernel(c
     sm.b2[tid] = a.theta[L.b2 + tid];
     sm.w3[tid] = a.theta[L.w3 + tid];
   }
-  for (int i = tid; i < a.Na * kH; i += kThr) {
-    const int n = i / kH, k = i % kH;
-    float c = a.theta[L.b1 + k];
-    for (int t = 0; t < a.n_types; ++t) c = fmaf(a.onehot[n * a.n_types + t], a.theta[L.W1 + (2 + t) * kH + k], c);
-    sm.cb[i] = c;
-  }
-  if (tid < a.Na * 3) sm.nuc[(tid / 3) * 4 + (tid % 3)] = a.nuclei[tid];
+  load_nuc_tables<kThr>(sm.T, a.theta, L, a.nuclei, a.onehot, a.Na, a.n_types);
   if (tid == 0) {
     tc::mbar_init(&sm.bar[0], 1); tc::mbar_init(&sm.bar[1], 1); tc::mbar_init(&sm.bar[2], 1);
     tc::fence_mbar_init();
@@ -413,9 +406,8 @@ struct SmemTcB {
   float P2Th[32 * kP2TChunk], P2Tl[32 * kP2TChunk];
   float WTh[kH * kH], WTl[kH * kH];       // B operand of B1: [j/4][k][j%4] = W2[k][j]
   float wr[kH], wt[kH], b2[kH], w3[kH];
-  float cb[kMaxNa * kH];
-  float nuc[kMaxNa * 4];
-  float S[8 * kMaxNa * 32];               // per warp, per nucleus: sum over the warp's trajectories of pbar1[k = 32 uh + lane]
+  NucTables T;
+  float S[8 * kMaxClasses * 32];          // per warp, per nucleus class: sum over the warp's trajectories of pbar1[k = 32 uh + lane]
   float xs[3 * kTP];
   float fbar[3 * kTP];
   float Fpart[2 * 3 * kTP];
@@ -426,6 +418,9 @@ struct SmemTcB {
   unsigned int tmem_slot;
   int tile;
 };
+
+static_assert(sizeof(SmemTcB) + 1024 <= 227 * 1024, "backward tile state exceeds the 227 KB of shared memory per CTA");
+static_assert(2 * (sizeof(SmemTc1) + 1024) <= 227 * 1024, "two forward CTAs must fit one SM");
 
 struct TcBwdAccum {
   float g_b2, g_w3;      // lane <-> unit j = 32 uh + lane, summed over this warp's 32 trajectories
@@ -466,7 +461,7 @@ __device__ void bwd_tile_tc(SmemTcB& sm, const GnnBwdArgs& a, long long row0, lo
   const uint64_t dWTl = tc::make_desc(tc::smem_u32(sm.WTl), kH * 16, 128);
 
   auto pre = [&](int i) {
-    const float* nc = sm.nuc + i * 4;
+    const float* nc = sm.T.nuc + i * 4;
     const float d0 = xst[0] - nc[0], d1 = xst[1] - nc[1], d2 = xst[2] - nc[2];
     const float alpha = fmaf(d0, kx[0], fmaf(d1, kx[1], d2 * kx[2]));
     float f0b = alpha, f1b = 0.f, f2b = 0.f;
@@ -490,7 +485,7 @@ __device__ void bwd_tile_tc(SmemTcB& sm, const GnnBwdArgs& a, long long row0, lo
     G.g_b3 += f0b;
   };
   auto post = [&](int i) {
-    const float* nc = sm.nuc + i * 4;
+    const float* nc = sm.T.nuc + i * 4;
     float f0 = b3 + sm.Fpart[0 * kTP + tid] + sm.Fpart[3 * kTP + tid], f1 = 0.f, f2 = 0.f;
     if (NJ >= 2) f1 = sm.Fpart[1 * kTP + tid] + sm.Fpart[4 * kTP + tid];
     if (NJ == 3) f2 = sm.Fpart[2 * kTP + tid] + sm.Fpart[5 * kTP + tid];
@@ -583,10 +578,10 @@ __device__ void bwd_tile_tc(SmemTcB& sm, const GnnBwdArgs& a, long long row0, lo
         float av[32];
         float r;
         {
-          const float* nc = sm.nuc + i * 4;
+          const float* nc = sm.T.nuc + i * 4;
           const float d0 = sm.xs[m] - nc[0], d1 = sm.xs[kTP + m] - nc[1], d2 = sm.xs[2 * kTP + m] - nc[2];
           r = sqrtf(fmaf(d0, d0, fmaf(d1, d1, d2 * d2)));
-          const float* cbi = sm.cb + i * kH + 32 * uh;
+          const float* cbi = sm.T.cb + sm.T.cls[i] * kH + 32 * uh;
 #pragma unroll
           for (int u = 0; u < 32; ++u)
             av[u] = tanh_f(fmaf(sm.wr[32 * uh + u], r, fmaf(tprime, sm.wt[32 * uh + u], cbi[u])));
@@ -767,7 +762,7 @@ __device__ void bwd_tile_tc(SmemTcB& sm, const GnnBwdArgs& a, long long row0, lo
           }
           const float ps = warp_vec32_sum(ps32, lane);
           const float pr = warp_vec32_sum(pr32, lane);
-          sm.S[(w * kMaxNa + i) * 32 + lane] += ps;
+          sm.S[(w * kMaxClasses + sm.T.cls[i]) * 32 + lane] += ps;
           G.g_wt = fmaf(tprime, ps, G.g_wt);
           G.g_wr += pr;
         }
@@ -826,18 +821,18 @@ __device__ void flush_tile_grad_tc(SmemTcB& sm, TcBwdAccum& G, float* __restrict
       for (int ww = 0; ww < 4; ++ww) v[q] += sm.red[(q * 8 + u2 * 4 + ww) * 32 + l2];
     out[L.b2 + tid] = v[0]; out[L.w3 + tid] = v[1]; out[L.W1 + tid] = v[2]; out[L.W1 + kH + tid] = v[3];
     float sb1 = 0.f;
-    for (int n = 0; n < Na; ++n) {
+    for (int c = 0; c < sm.T.n_cls; ++c) {
       float sn = 0.f;
-      for (int ww = 0; ww < 4; ++ww) sn += sm.S[((u2 * 4 + ww) * kMaxNa + n) * 32 + l2];
+      for (int ww = 0; ww < 4; ++ww) sn += sm.S[((u2 * 4 + ww) * kMaxClasses + c) * 32 + l2];
       sb1 += sn;
     }
     out[L.b1 + tid] = sb1;
     for (int t = 0; t < n_types; ++t) {
       float s = 0.f;
-      for (int n = 0; n < Na; ++n) {
+      for (int c = 0; c < sm.T.n_cls; ++c) {
         float sn = 0.f;
-        for (int ww = 0; ww < 4; ++ww) sn += sm.S[((u2 * 4 + ww) * kMaxNa + n) * 32 + l2];
-        s = fmaf(onehot[n * n_types + t], sn, s);
+        for (int ww = 0; ww < 4; ++ww) sn += sm.S[((u2 * 4 + ww) * kMaxClasses + c) * 32 + l2];
+        s = fmaf(onehot[sm.T.rep[c] * n_types + t], sn, s);
       }
       out[L.W1 + (2 + t) * kH + tid] = s;
     }
@@ -846,7 +841,7 @@ __device__ void flush_tile_grad_tc(SmemTcB& sm, TcBwdAccum& G, float* __restrict
   if (lane == 0) sm.red[w] = b3w;
   __syncthreads();
   if (tid == 0) out[L.b3] = sm.red[0] + sm.red[1] + sm.red[2] + sm.red[3];
-  for (int i = tid; i < 8 * kMaxNa * 32; i += kThreads) sm.S[i] = 0.f;
+  for (int i = tid; i < 8 * kMaxClasses * 32; i += kThreads) sm.S[i] = 0.f;
   __syncthreads();
   for (int i = tid; i < kTP * kH; i += kThreads) sm.DW[i] = 0.f;
   __syncthreads();
@@ -870,14 +865,8 @@ __global__ void __launch_bounds__(kThreads, 1) gnn_bwd_tc_kernel(const GnnBwdArg
     sm.b2[tid] = a.theta[L.b2 + tid];
     sm.w3[tid] = a.theta[L.w3 + tid];
   }
-  for (int i = tid; i < a.Na * kH; i += kThreads) {
-    const int n = i / kH, k = i % kH;
-    float c = a.theta[L.b1 + k];
-    for (int t = 0; t < a.n_types; ++t) c = fmaf(a.onehot[n * a.n_types + t], a.theta[L.W1 + (2 + t) * kH + k], c);
-    sm.cb[i] = c;
-  }
-  if (tid < a.Na * 3) sm.nuc[(tid / 3) * 4 + (tid % 3)] = a.nuclei[tid];
-  for (int i = tid; i < 8 * kMaxNa * 32; i += kThreads) sm.S[i] = 0.f;
+  load_nuc_tables<kThreads>(sm.T, a.theta, L, a.nuclei, a.onehot, a.Na, a.n_types);
+  for (int i = tid; i < 8 * kMaxClasses * 32; i += kThreads) sm.S[i] = 0.f;
   for (int i = tid; i < kTP * kH; i += kThreads) sm.DW[i] = 0.f;
   if (tid == 0) {
     for (int j = 0; j < 3; ++j) { tc::mbar_init(&sm.barB[j], 1); tc::mbar_init(&sm.barD[j], 1); }
@@ -927,30 +916,14 @@ int launch_gnn_fwd_tc(void* stream, GnnFwdArgs& a, void* scratch, size_t scratch
   a.counter = (int*)scratch;
   cudaError_t e = cudaMemsetAsync(scratch, 0, kCounterBytes, st);
   if (e != cudaSuccess) return (int)e;
-  // OFDFT_B200_TC_FWD = "2cta" (default: 256 threads, one 64 KB operand buffer, two co-resident CTAs per SM whose
-  // stage / MMA / epilogue phases interleave) | "1cta" (two operand buffers, one CTA per SM) | "nu4" (512 threads,
-  // 16 hidden units per thread, one CTA per SM)
-  const char* env = getenv("OFDFT_B200_TC_FWD");
-  const int mode = env == nullptr ? 0 : (env[0] == '1' ? 1 : (env[0] == 'n' ? 2 : 0));
+  // 256 threads, one 64 KB operand buffer, two co-resident CTAs per SM whose stage / MMA / epilogue phases interleave
   const long long tiles = (a.n_a + kTP - 1) / kTP + (a.B - a.n_a + kTP - 1) / kTP;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  if (mode == 0) {
-    e = cudaFuncSetAttribute(gnn_fwd_tc_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemTc1) + 1024);
-    if (e != cudaSuccess) return (int)e;
-    const int grid = (int)(tiles < 2 * sms ? tiles : 2 * sms);
-    gnn_fwd_tc_kernel<2, 1><<<grid, kTP * 2, sizeof(SmemTc1) + 1024, st>>>(a);
-  } else if (mode == 1) {
-    e = cudaFuncSetAttribute(gnn_fwd_tc_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemTc) + 1024);
-    if (e != cudaSuccess) return (int)e;
-    const int grid = (int)(tiles < sms ? tiles : sms);
-    gnn_fwd_tc_kernel<2, 2><<<grid, kTP * 2, sizeof(SmemTc) + 1024, st>>>(a);
-  } else {
-    e = cudaFuncSetAttribute(gnn_fwd_tc_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemTc) + 1024);
-    if (e != cudaSuccess) return (int)e;
-    const int grid = (int)(tiles < sms ? tiles : sms);
-    gnn_fwd_tc_kernel<4, 2><<<grid, kTP * 4, sizeof(SmemTc) + 1024, st>>>(a);
-  }
+  e = cudaFuncSetAttribute(gnn_fwd_tc_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemTc1) + 1024);
+  if (e != cudaSuccess) return (int)e;
+  const int grid = (int)(tiles < 2 * sms ? tiles : 2 * sms);
+  gnn_fwd_tc_kernel<2, 1><<<grid, kTP * 2, sizeof(SmemTc1) + 1024, st>>>(a);
   return (int)cudaGetLastError();
 }
 

@@ -31,6 +31,7 @@ struct Args {
   float* acts; float* pbar; float* gsmall;   // backward scratch
   long long B, row_begin, rows;              // this launch handles rows [row_begin, row_begin+rows)
   int jets, stride, H, L, n_steps; float t0, t1, y0;
+  int rhs_only; float t_rhs;                 // one evaluation of the vector field at t_rhs: y_out <- d/dt y
 };
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
@@ -169,10 +170,11 @@ __device__ void fwd_body(const Args& a, float* smem_base) {
       if (NJ == 3) y[2] = src[2];
     }
     float acc[NJ][16];
-    for (int step = 0; step < a.n_steps; ++step) {
-      for (int stage = 0; stage < 4; ++stage) {
+    const int n_steps = a.rhs_only ? 1 : a.n_steps;
+    for (int step = 0; step < n_steps; ++step) {
+      for (int stage = 0; stage < (a.rhs_only ? 1 : 4); ++stage) {
         const float cs = stage == 0 ? 0.f : (stage == 3 ? h : 0.5f * h);
-        const float tprime = a.y0 * (a.t0 + h * (float)step + cs);
+        const float tprime = a.y0 * (a.rhs_only ? a.t_rhs : a.t0 + h * (float)step + cs);
         __syncthreads();
         if (owner) {
           xst = fmaf(cs, kst[0], y[0]);
@@ -225,16 +227,17 @@ __device__ void fwd_body(const Args& a, float* smem_base) {
           for (int c = 0; c < 3; ++c) accw[c] = fmaf(wgt, kst[c], accw[c]);
         }
       }
-      if (owner) {
+      if (owner && !a.rhs_only) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) { y[c] = fmaf(h * (1.0f / 6.0f), accw[c], y[c]); accw[c] = 0.f; }
       }
     }
     if (valid) {
       float* dst = a.y_out + row * a.stride;
-      dst[0] = y[0];
-      if (NJ >= 2) dst[1] = y[1];
-      if (NJ == 3) dst[2] = y[2];
+      const float* o = a.rhs_only ? kst : y;
+      dst[0] = o[0];
+      if (NJ >= 2) dst[1] = o[1];
+      if (NJ == 3) dst[2] = o[2];
     }
   }
 }
@@ -801,7 +804,7 @@ __global__ void mlp_small_reduce_kernel(const float* __restrict__ gsmall, float*
 }
 
 static int check_shape(int64_t B, int jets, int stride, int H, int L, int n_steps) {
-  if (B <= 0 || n_steps <= 0 || jets < 1 || jets > 3) return OFDFT_EINVAL;
+  if (B < 0 || n_steps <= 0 || jets < 1 || jets > 3) return OFDFT_EINVAL;
   if (stride < (jets == 3 ? 3 : jets)) return OFDFT_EINVAL;
   if (H < 64 || H > 512 || H % 64 || L < 2 || L > kMaxL) return OFDFT_EUNSUPPORTED;
   return 0;
@@ -823,14 +826,15 @@ extern "C" size_t ofdft_cnf_mlp1d_scratch_bytes(int64_t B, int32_t H, int32_t n_
 
 extern "C" int ofdft_cnf_mlp1d_fwd(void* stream, const float* theta, const float* y_in, float* y_out, float* ckpt,
                                    void* scratch, size_t scratch_bytes, int64_t B, int32_t jets, int32_t stride,
-                                   int32_t H, int32_t n_layers, int32_t n_steps, float t0, float t1, float y0sign) {
+                                   int32_t H, int32_t n_layers, int32_t n_steps, float t0, float t1, float y0sign,
+                                   int32_t path) {
   int rc = check_shape(B, jets, stride, H, n_layers, n_steps);
   if (rc) return rc;
+  if (B == 0) return 0;                                        // empty shard: nothing to integrate
   if (!theta || !y_in || !y_out || !scratch) return OFDFT_EINVAL;
   const ScratchLayout SL(B, H, n_layers, n_steps);
-  // OFDFT_B200_MLP_FWD = "tc" (default: per-layer tcgen05 3xTF32 GEMM launches, mlp1d_tc.cu) | "ffma" (fused FP32 kernel)
-  const char* envf = getenv("OFDFT_B200_MLP_FWD");
-  const bool fwd_tc = !(envf != nullptr && envf[0] == 'f');
+  // default: per-layer tcgen05 3xTF32 GEMM launches (mlp1d_tc.cu); OFDFT_PATH_FFMA: the fused FP32 kernel of this file
+  const bool fwd_tc = !(path & OFDFT_PATH_FFMA);
   if (scratch_bytes < (fwd_tc ? SL.fwd_end : SL.wtc)) return OFDFT_ESCRATCH;
   cudaStream_t st = (cudaStream_t)stream;
   float* Wc = (float*)((char*)scratch + SL.wc);
@@ -863,13 +867,47 @@ extern "C" int ofdft_cnf_mlp1d_fwd(void* stream, const float* theta, const float
   return (int)cudaGetLastError();
 }
 
+// One evaluation of the vector field (Gen_CNFSimpleMLP.apply, cn_flows.py:179-182) or of the score-augmented right-hand side
+// (jax_ode.py:80-98): the fused FP32 kernel with a single stage.
+extern "C" int ofdft_cnf_mlp1d_rhs(void* stream, const float* theta, const float* y, float* dy, void* scratch, size_t scratch_bytes,
+                                   int64_t B, int32_t jets, int32_t stride, int32_t H, int32_t n_layers, float t, float y0sign) {
+  int rc = check_shape(B, jets, stride, H, n_layers, 1);
+  if (rc) return rc;
+  if (B == 0) return 0;
+  if (!theta || !y || !dy || !scratch) return OFDFT_EINVAL;
+  const ScratchLayout SL(B, H, n_layers, 1);
+  if (scratch_bytes < SL.wtc) return OFDFT_ESCRATCH;
+  cudaStream_t st = (cudaStream_t)stream;
+  float* Wc = (float*)((char*)scratch + SL.wc);
+  mlp_prep_kernel<<<256, 256, 0, st>>>(theta, Wc, nullptr, H, n_layers, nullptr);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return (int)e;
+  const size_t smem = smem_bytes(H);
+  e = cudaFuncSetAttribute(mlp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  Args a{};
+  a.theta = theta; a.Wc = Wc; a.y_in = y; a.y_out = dy; a.ckpt = nullptr; a.B = B; a.row_begin = 0; a.rows = B;
+  a.jets = jets; a.stride = stride; a.H = H; a.L = n_layers; a.n_steps = 1; a.t0 = 0.f; a.t1 = 1.f; a.y0 = y0sign;
+  a.rhs_only = 1; a.t_rhs = t;
+  const long long n_tiles = (B + kTT - 1) / kTT;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = (int)(n_tiles < sms ? n_tiles : sms);
+  mlp_fwd_kernel<<<grid, H / 2, smem, st>>>(a);
+  return (int)cudaGetLastError();
+}
+
 extern "C" int ofdft_cnf_mlp1d_bwd(void* stream, const float* theta, const float* ckpt, const float* ybar1,
                                    float* theta_bar, float* ybar0, void* scratch, size_t scratch_bytes,
                                    int64_t B, int32_t jets, int32_t stride, int32_t H, int32_t n_layers,
-                                   int32_t n_steps, float t0, float t1, float y0sign) {
+                                   int32_t n_steps, float t0, float t1, float y0sign, int32_t path) {
   int rc = check_shape(B, jets, stride, H, n_layers, n_steps);
   if (rc) return rc;
   if (jets != 3) return OFDFT_EUNSUPPORTED;                    // the adjoint is instantiated for the training path
+  if (B == 0) {                                                // empty shard: the gradient of an empty sum
+    if (!theta_bar) return OFDFT_EINVAL;
+    return (int)cudaMemsetAsync(theta_bar, 0, (size_t)ThetaLayout(H, n_layers).n * sizeof(float), (cudaStream_t)stream);
+  }
   if (!theta || !ckpt || !ybar1 || !theta_bar || !scratch) return OFDFT_EINVAL;
   const int L = n_layers;
   const ScratchLayout SL(B, H, L, n_steps);
@@ -878,9 +916,8 @@ extern "C" int ofdft_cnf_mlp1d_bwd(void* stream, const float* theta, const float
   char* sc = (char*)scratch;
   float* Wc = (float*)(sc + SL.wc); float* WTc = (float*)(sc + SL.wtc);
   float* gsmall = (float*)(sc + SL.gsmall); float* part = (float*)(sc + SL.part);
-  // OFDFT_B200_MLP_BWD = "tc" (default: adjoint sweep as per-layer tcgen05 GEMM launches, mlp1d_tc.cu) | "ffma" (fused FP32 sweep)
-  const char* envb = getenv("OFDFT_B200_MLP_BWD");
-  const bool bwd_tc = !(envb != nullptr && envb[0] == 'f');
+  // default: adjoint sweep as per-layer tcgen05 GEMM launches (mlp1d_tc.cu); OFDFT_PATH_FFMA: fused FP32 sweep
+  const bool bwd_tc = !(path & OFDFT_PATH_FFMA);
   float* WTlo = (float*)(sc + SL.wtlo); float* Wclo = (float*)(sc + SL.wclo);
   mlp_prep_kernel<<<256, 256, 0, st>>>(theta, Wc, WTc, H, L, bwd_tc ? WTlo : nullptr, bwd_tc ? Wclo : nullptr);
   cudaError_t e = cudaGetLastError();
@@ -923,9 +960,8 @@ extern "C" int ofdft_cnf_mlp1d_bwd(void* stream, const float* theta, const float
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
     mlp_small_reduce_kernel<<<(TL.n_small() + 255) / 256, 256, 0, st>>>(gsmall, theta_bar, H, L, grid, chunk_idx > 0);
-    // OFDFT_B200_MLP_DW = "tc" (default: tcgen05 3xTF32 weight-gradient GEMM) | "ffma"
-    const char* envd = getenv("OFDFT_B200_MLP_DW");
-    const bool dw_tc = !(envd != nullptr && envd[0] == 'f');
+    // default: tcgen05 3xTF32 weight-gradient GEMM; OFDFT_PATH_FFMA_DW: FP32-pipe split-K GEMM
+    const bool dw_tc = !(path & OFDFT_PATH_FFMA_DW);
     if (dw_tc) {
       e = cudaFuncSetAttribute(mlp_dw_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DwSmem) + 1024);
       if (e != cudaSuccess) return (int)e;

@@ -10,7 +10,7 @@
 
 namespace ofdft {
 
-constexpr int kPriorMaxNuc = 64;
+constexpr int kPriorMaxNuc = 128;   // C27H46O (utils.py:327) has 74
 struct PriorArgs {
   float coords[kPriorMaxNuc * 3];
   float logw[kPriorMaxNuc];     // log(Z_i / sum Z)
@@ -54,7 +54,9 @@ __global__ void batch_generator_3d_kernel(const PriorArgs P, unsigned long long 
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows) return;
   curandStatePhilox4_32_10_t st;
-  curand_init(seed, (unsigned long long)i, offset, &st);
+  // Philox skip-ahead counts single 32-bit outputs: a row consumes 5 per call (1 uniform + normal4), so consecutive calls
+  // are spaced 8 outputs apart -- every batch draws from a disjoint stretch of the row's subsequence
+  curand_init(seed, (unsigned long long)i, offset * 8ull, &st);
   const float u = curand_uniform(&st);
   int c = 0;
   while (c + 1 < P.n_nuclei && u > P.cdf[c]) ++c;
@@ -71,7 +73,7 @@ __global__ void batch_generator_1d_kernel(unsigned long long seed, unsigned long
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows) return;
   curandStatePhilox4_32_10_t st;
-  curand_init(seed, (unsigned long long)i, offset, &st);
+  curand_init(seed, (unsigned long long)i, offset * 8ull, &st);   // 2 outputs per row and call; calls spaced 8 apart
   const float x = curand_normal(&st);
   out[3 * i] = x; out[3 * i + 1] = -0.5f * x * x - 0.9189385332046727f; out[3 * i + 2] = -x;
 }
@@ -159,6 +161,35 @@ __global__ void __launch_bounds__(1024) rmsprop_clip_kernel(float* __restrict__ 
     theta[i] -= lr * g * rsqrtf(v + eps);
   }
 }
+
+// optax.chain(clip_by_global_norm(max_norm), adam(lr)) as OFDFT_NF.py:104-108 builds it.  [third-party] optax.adam restated:
+// mu <- b1 mu + (1-b1) g;  nu <- b2 nu + (1-b2) g^2;  theta <- theta - lr * (mu / (1-b1^t)) / (sqrt(nu / (1-b2^t)) + eps)
+// (eps outside the square root, eps_root = 0, t = 1-based update count; defaults b1 = 0.9, b2 = 0.999, eps = 1e-8).
+__global__ void __launch_bounds__(1024) adam_clip_kernel(float* __restrict__ theta, const float* __restrict__ grad,
+                                                         float* __restrict__ mu, float* __restrict__ nu, long long n, float lr,
+                                                         float b1, float b2, float eps, float max_norm, float c1, float c2) {
+  __shared__ double red[32];
+  double s = 0.0;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) s += (double)grad[i] * (double)grad[i];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (threadIdx.x == 0) red[0] = v;
+  }
+  __syncthreads();
+  const float gnorm = (float)sqrt(red[0]);
+  const float scale = (max_norm > 0.f && gnorm > max_norm) ? max_norm / gnorm : 1.0f;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    const float g = grad[i] * scale;
+    const float m = fmaf(b1, mu[i], (1.0f - b1) * g);
+    const float v = fmaf(b2, nu[i], (1.0f - b2) * g * g);
+    mu[i] = m; nu[i] = v;
+    theta[i] -= lr * (m * c1) / (sqrtf(v * c2) + eps);       // c1 = 1/(1-b1^t), c2 = 1/(1-b2^t)
+  }
+}
 __global__ void ema_update_kernel(const double* __restrict__ values, double* __restrict__ state, double* __restrict__ out, int n,
                                   double decay, double debias) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -181,5 +212,14 @@ extern "C" int ofdft_rmsprop_clip_step(void* stream, float* theta, const float* 
                                        float decay, float eps, float max_norm) {
   if (!theta || !grad || !nu || n <= 0) return OFDFT_EINVAL;
   ofdft::rmsprop_clip_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(theta, grad, nu, n, lr, decay, eps, max_norm);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int ofdft_adam_clip_step(void* stream, float* theta, const float* grad, float* mu, float* nu, int64_t n, int64_t step,
+                                    float lr, float b1, float b2, float eps, float max_norm) {
+  if (!theta || !grad || !mu || !nu || n <= 0 || step < 1) return OFDFT_EINVAL;
+  const float c1 = (float)(1.0 / (1.0 - pow((double)b1, (double)step)));
+  const float c2 = (float)(1.0 / (1.0 - pow((double)b2, (double)step)));
+  ofdft::adam_clip_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(theta, grad, mu, nu, n, lr, b1, b2, eps, max_norm, c1, c2);
   return (int)cudaGetLastError();
 }

@@ -72,18 +72,21 @@ class Gen_EqvFlow:
     """``Gen_EqvFlow(in_out_dim, features, xyz_nuclei, z_one_hot, bool_neg=False)`` (equiv_flows.py:108-114).
 
     g(x,t) = sum_i f_theta(y0 t, |x-R_i|, onehot_i) (x-R_i), exact trace, output scaled by y0 (-1 if bool_neg).
-    Only ``in_out_dim == 3`` and ``features == (64, 64)`` (what every 3-D driver passes, e.g.
-    H20_mol_ofdft_min_equiv_flows.py:263) are instantiated in CUDA; other shapes raise NotImplementedError.
+    ``in_out_dim == 3`` and ``features`` = one to three hidden layers of 64 units are instantiated in CUDA ((64, 64), what every
+    driver but OFDFT_NF.py hard-codes, e.g. H20_mol_ofdft_min_equiv_flows.py:263, runs on the tensor-core kernels); other
+    shapes raise NotImplementedError.
     """
 
     def __init__(self, in_out_dim: Any, features: Sequence[int], xyz_nuclei: Any, z_one_hot: Any, bool_neg: bool = False,
                  device: str = "cuda"):
         if int(in_out_dim) != 3:
             raise NotImplementedError("Gen_EqvFlow: only in_out_dim == 3 is supported")
-        if tuple(int(f) for f in features) != (64, 64):
-            raise NotImplementedError("Gen_EqvFlow: CUDA kernels are instantiated for features == (64, 64)")
+        feats = tuple(int(f) for f in features)
+        if not (1 <= len(feats) <= 3) or any(f != 64 for f in feats):
+            # the drivers expose (64,), (64, 64) and (64, 64, 64) (OFDFT_NF.py:320-326); everything else hard-codes (64, 64)
+            raise NotImplementedError("Gen_EqvFlow: CUDA kernels are instantiated for 1-3 hidden layers of 64 units")
         self.in_out_dim = 3
-        self.features = (64, 64)
+        self.features = feats
         self.bool_neg = bool(bool_neg)
         self.y0 = -1.0 if self.bool_neg else 1.0
         self.device = torch.device(device)
@@ -92,6 +95,8 @@ class Gen_EqvFlow:
         self.z_one_hot = torch.as_tensor(oh).reshape(self.xyz_nuclei.shape[0], -1).to(self.device).contiguous()
         self.n_types = self.z_one_hot.shape[1]
         self.n_in = 2 + self.n_types
+        if self.xyz_nuclei.shape[0] > 128 or self.n_types > 8 or len({tuple(r) for r in oh.reshape(len(oh), -1).tolist()}) > 8:
+            raise NotImplementedError("Gen_EqvFlow: at most 128 nuclei, 8 species and 8 distinct one-hot rows")
 
     # ---- Flax-like API -------------------------------------------------------------------------
     def init(self, key: Any = 0, t: Any = None, test_inputs: Any = None) -> Dict[str, Any]:

@@ -49,11 +49,12 @@ def shard_batch(batch, rank: int, world: int):
 class EnergyEstimator:
     def __init__(self, model: Any, spec: ops.EnergySpec, n_steps: int = DEFAULT_N_STEPS, t0: float = 0.0, t1: float = 1.0,
                  skip_unused_jets: bool = True, group: Optional[Any] = None, act_ckpt: bool = True,
-                 act_ckpt_max_bytes: Optional[int] = None, hartree_mode: str = "paired"):
+                 act_ckpt_max_bytes: Optional[int] = None, hartree_mode: str = "paired", path: int = ops.PATH_DEFAULT):
         self.model, self.spec, self.n_steps, self.t0, self.t1 = model, spec, int(n_steps), float(t0), float(t1)
         # rows of the second half only supply xp: integrate them without the logp/score channels
         self.jets_b = ops.JETS_X if skip_unused_jets else ops.JETS_FULL
         self.group = group
+        self.path = int(path)          # kernel-path selector (ops.PATH_*): tcgen05 kernels by default
         # "paired": the reference's row-paired O(bs) Hartree estimator (functionals.py:463-486);
         # "allpairs": the lower-variance O(bs^2) cross-half estimator of the same double integral (north star): the
         # second half's coordinates (and the first half's, for the partner forces) are all-gathered over NCCL and every
@@ -103,30 +104,32 @@ class EnergyEstimator:
             # activation checkpoint above the cap (many nuclei x large batch): integrate once without checkpoints, then
             # re-integrate and reverse the rows in chunks whose checkpoint fits -- one extra forward pass keeps the
             # backward on the tensor-core kernel, which is ~3x faster than the FP32 recompute kernel
-            chunked = self.act_ckpt and not want_act and B > 0
+            chunked = self.act_ckpt and not want_act and B > 0 and len(getattr(m, "features", (64, 64))) == 2
             y1, ckpt = ops.gnn_fwd(theta, m.xyz_nuclei, m.z_one_hot, batch, bs, ops.JETS_FULL, self.jets_b, self.n_steps,
-                                   self.t0, self.t1, m.y0, want_ckpt=not chunked, want_act=want_act)
+                                   self.t0, self.t1, m.y0, want_ckpt=not chunked, want_act=want_act, path=self.path)
             e1 = mark()
             sums, ybar1 = ops.functionals_fwd_bwd(self.spec, y1)
             if self.hartree_mode == "allpairs":
-                self._allpairs_hartree(y1, ybar1, sums)
+                self._allpairs_hartree(y1, ybar1, sums, timers)
             e2 = mark()
             if chunked:
                 tbar = self._gnn_bwd_chunked(theta, batch, ybar1, bs, Na)
             else:
                 tbar, _ = ops.gnn_bwd(theta, m.xyz_nuclei, m.z_one_hot, ckpt, ybar1, bs, ops.JETS_FULL, self.jets_b,
-                                      self.n_steps, self.t0, self.t1, m.y0)
+                                      self.n_steps, self.t0, self.t1, m.y0, path=self.path)
             e3 = mark()
             if timers is not None:
                 timers += [("gnn_fwd", e0, e1), ("functionals", e1, e2), ("gnn_bwd", e2, e3)]
         else:
             from .cn_flows import mlp_fwd, mlp_bwd
             e0 = mark()
-            y1, ckpt = mlp_fwd(theta, batch, m, self.t0, self.t1, ops.JETS_FULL, self.n_steps, want_ckpt=True)
+            y1, ckpt = mlp_fwd(theta, batch, m, self.t0, self.t1, ops.JETS_FULL, self.n_steps, want_ckpt=True, path=self.path)
             e1 = mark()
             sums, ybar1 = ops.functionals_fwd_bwd(self.spec, y1)
+            if self.hartree_mode == "allpairs":
+                self._allpairs_hartree(y1, ybar1, sums, timers)      # soft-Coulomb pairs: coordinates are column 0
             e2 = mark()
-            tbar, _ = mlp_bwd(theta, ckpt, ybar1, m, self.t0, self.t1, ops.JETS_FULL, self.n_steps)
+            tbar, _ = mlp_bwd(theta, ckpt, ybar1, m, self.t0, self.t1, ops.JETS_FULL, self.n_steps, path=self.path)
             e3 = mark()
             if timers is not None:
                 timers += [("mlp_fwd", e0, e1), ("functionals", e1, e2), ("mlp_bwd", e2, e3)]
@@ -162,23 +165,54 @@ class EnergyEstimator:
                 del ck
         return tbar
 
-    def _allpairs_hartree(self, y1: torch.Tensor, ybar1: torch.Tensor, sums: torch.Tensor) -> None:
-        """Adds the all-pairs Hartree energy of this rank's strip to ``sums`` and its forces to ``ybar1`` (in place)."""
+    def _allpairs_hartree(self, y1: torch.Tensor, ybar1: torch.Tensor, sums: torch.Tensor, timers: Optional[list] = None) -> None:
+        """Adds the all-pairs Hartree energy of this rank's strips to ``sums`` and its forces to ``ybar1`` (in place).
+
+        Distributed: only the coordinates travel -- (bs, d) float32 per half, 12 B per row in 3-D -- in two asynchronous
+        NCCL all-gathers; the local block (this rank's x against its own xp: energy and forces on both halves) is evaluated
+        while they are in flight, then the strips against the remote rows.  Every pair of the global cross set is visited by
+        exactly one rank for the energy and for each of its two forces."""
         bs = y1.shape[0] // 2
-        x_loc, xp_loc = y1[:bs], y1[bs:]                       # contiguous row blocks; coordinates are the first d columns
-        x_all, xp_all = x_loc, xp_loc
-        if self._dist():
-            import torch.distributed as dist
-            ws = dist.get_world_size(self.group)
-            x_all = torch.empty((ws * bs, y1.shape[1]), dtype=y1.dtype, device=y1.device)
-            xp_all = torch.empty_like(x_all)
-            dist.all_gather_into_tensor(xp_all, xp_loc.contiguous(), group=self.group)
-            dist.all_gather_into_tensor(x_all, x_loc.contiguous(), group=self.group)
+        d = 3 if ops.HART[self._hart_kind] == 1 else 1
         Ne = self.spec.Ne
-        # strip (local x) x (all xp): energy of the strip + forces on the local x rows
-        esum, _, _ = ops.hartree_allpairs(x_loc, xp_all, Ne, self._hart_kind, xbar_into=ybar1[:bs])
-        # strip (local xp) x (all x): forces on the local xp rows (same pair normalisation: equal shard sizes)
-        ops.hartree_allpairs(xp_loc, x_all, Ne, self._hart_kind, xbar_into=ybar1[bs:])
+        x_loc, xp_loc = y1[:bs], y1[bs:]                       # contiguous row blocks; coordinates are the first d columns
+        esum = torch.zeros(1, dtype=torch.float64, device=y1.device)
+
+        def mark():
+            if timers is None:
+                return None
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            return ev
+
+        e0 = mark()
+        if not self._dist():
+            ops.hartree_allpairs(x_loc, xp_loc, Ne, self._hart_kind, xbar_into=ybar1[:bs], xpbar_into=ybar1[bs:], esum_into=esum)
+        else:
+            import torch.distributed as dist
+            ws, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+            xs = x_loc[:, :d].contiguous()
+            xps = xp_loc[:, :d].contiguous()
+            x_all = torch.empty((ws * bs, d), dtype=y1.dtype, device=y1.device)
+            xp_all = torch.empty_like(x_all)
+            w1 = dist.all_gather_into_tensor(xp_all, xps, group=self.group, async_op=True)
+            w2 = dist.all_gather_into_tensor(x_all, xs, group=self.group, async_op=True)
+            norm = float(bs) * float(bs) * ws                  # pairs of this rank's strip
+            ops.hartree_allpairs(x_loc, xp_loc, Ne, self._hart_kind, xbar_into=ybar1[:bs], xpbar_into=ybar1[bs:], esum_into=esum,
+                                 norm_pairs=norm)
+            w1.wait(); w2.wait()
+            if timers is not None:
+                timers.append(("all_gather_wait", e0, mark()))
+            for lo, hi in ((0, rank), (rank + 1, ws)):
+                if hi > lo:
+                    # (local x) x (remote xp): energy + forces on the local x rows; (local xp) x (remote x): forces on xp
+                    ops.hartree_allpairs(x_loc, xp_all[lo * bs:hi * bs], Ne, self._hart_kind, xbar_into=ybar1[:bs], esum_into=esum,
+                                         norm_pairs=norm)
+                    scratch_e = torch.zeros(1, dtype=torch.float64, device=y1.device)
+                    ops.hartree_allpairs(xp_loc, x_all[lo * bs:hi * bs], Ne, self._hart_kind, xbar_into=ybar1[bs:],
+                                         esum_into=scratch_e, norm_pairs=norm)
+        if timers is not None:
+            timers.append(("hartree_pairs", e0, mark()))
         sums[2:3] += esum
         sums[5:6] += esum
 

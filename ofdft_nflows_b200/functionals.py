@@ -32,9 +32,10 @@ def _eval(family: int, spec: EnergySpec, a0: torch.Tensor, a1, want_grad: bool):
     out = torch.empty((n, 1), dtype=torch.float32, device=a0.device)
     g0 = torch.empty_like(a0) if want_grad else None
     g1 = torch.empty_like(a1) if (want_grad and a1 is not None) else None
-    _lib.check(lib.ofdft_functional_eval(ops._stream(), family, C.byref(cs), ops._host_ptr(coords), ops._host_ptr(z),
-                                         ops._ptr(a0), ops._ptr(a1), n, ops._ptr(out), ops._ptr(g0), ops._ptr(g1)),
-               "ofdft_functional_eval")
+    with ops._on(a0):
+        _lib.check(lib.ofdft_functional_eval(ops._stream(a0), family, C.byref(cs), ops._host_ptr(coords), ops._host_ptr(z),
+                                             ops._ptr(a0), ops._ptr(a1), n, ops._ptr(out), ops._ptr(g0), ops._ptr(g1)),
+                   "ofdft_functional_eval")
     return out, g0, g1
 
 

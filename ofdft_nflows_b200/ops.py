@@ -15,6 +15,9 @@ from . import _lib
 from ._lib import EnergySpecC
 
 JETS_X, JETS_XLOGP, JETS_FULL = 1, 2, 3
+# kernel-path selector of the integrator entry points (include/ofdft_b200.h): the default runs the GEMM-shaped phases on
+# the tcgen05 tensor cores; PATH_FFMA / PATH_FFMA_DW select the independently written FP32-pipe kernels
+PATH_DEFAULT, PATH_FFMA, PATH_FFMA_DW = 0, 1, 2
 
 KIN = {"": 0, "none": 0, "tf": 1, "thomas_fermi": 1, "w": 2, "weizsacker": 2, "w1d": 2, "weizsacker1d": 2,
        "tf-w": 3, "thomas_fermi_weizsacker": 3, "tf1d": 4, "thomas_fermi_1d": 4,
@@ -31,8 +34,13 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
 
-def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+def _stream(t: Optional[torch.Tensor] = None) -> int:
+    return torch.cuda.current_stream(None if t is None else t.device).cuda_stream
+
+
+def _on(t: torch.Tensor):
+    """The C launchers query the current device: make it the tensors' device for the duration of the call."""
+    return torch.cuda.device(t.device)
 
 
 def _f32c(t: torch.Tensor) -> torch.Tensor:
@@ -47,8 +55,16 @@ def _cols(jets: int, d: int = 3) -> int:
     return {1: d, 2: d + 1, 3: 2 * d + 1}[jets]
 
 
-def gnn_theta_size(n_types: int) -> int:
-    return 4289 + 64 * (2 + n_types)
+def gnn_theta_size(n_types: int, n_layers: int = 2) -> int:
+    return 1 + 64 + 64 + 64 * (2 + n_types) + (n_layers - 1) * (64 + 64 * 64)
+
+
+def gnn_n_layers(theta: torch.Tensor, n_types: int) -> int:
+    for L in (1, 2, 3):
+        if theta.numel() == gnn_theta_size(n_types, L):
+            return L
+    raise ValueError(f"theta has {theta.numel()} entries: not a Gen_EqvFlow stack of 1-3 hidden layers of 64 units "
+                     f"with {n_types} species")
 
 
 def gnn_act_ckpt_bytes(B: int, n_a: int, jets_a: int, jets_b: int, Na: int, n_steps: int) -> int:
@@ -57,7 +73,7 @@ def gnn_act_ckpt_bytes(B: int, n_a: int, jets_a: int, jets_b: int, Na: int, n_st
 
 def gnn_fwd(theta, nuclei, onehot, y_in, n_a: int, jets_a: int, jets_b: int, n_steps: int,
             t0: float, t1: float, y0sign: float, want_ckpt: bool = False, out: Optional[torch.Tensor] = None,
-            want_act: bool = False):
+            want_act: bool = False, path: int = PATH_DEFAULT):
     """ofdft_cnf_gnn_fwd: integrate rows [0,n_a) with jets_a and rows [n_a,B) with jets_b.
     Returns (y1, ckpt) -- ckpt is None, the stage-state checkpoint, or (with ``want_act``) the pair
     (stage states, layer-2 activation checkpoint)."""
@@ -65,26 +81,26 @@ def gnn_fwd(theta, nuclei, onehot, y_in, n_a: int, jets_a: int, jets_b: int, n_s
     theta, nuclei, onehot, y_in = _f32c(theta), _f32c(nuclei), _f32c(onehot), _f32c(y_in)
     B, stride = y_in.shape
     Na, n_types = onehot.shape
-    if theta.numel() != gnn_theta_size(n_types):
-        raise ValueError(f"theta has {theta.numel()} entries, expected {gnn_theta_size(n_types)} (features must be (64, 64))")
+    L = gnn_n_layers(theta, n_types)
     y_out = out if out is not None else torch.zeros_like(y_in)
     ckpt = None
     if want_ckpt:
         ckpt = torch.empty(lib.ofdft_cnf_gnn_ckpt_bytes(B, n_steps) // 4, dtype=torch.float32, device=y_in.device)
     act = None
-    if want_ckpt and want_act:
+    if want_ckpt and want_act and L == 2:
         nb = lib.ofdft_cnf_gnn_act_ckpt_bytes(B, n_a, jets_a, jets_b, Na, n_steps)
         act = torch.empty(nb // 4, dtype=torch.float32, device=y_in.device)
     sb = lib.ofdft_cnf_gnn_fwd_scratch_bytes()
     scratch = torch.empty(sb, dtype=torch.uint8, device=y_in.device)
-    _lib.check(lib.ofdft_cnf_gnn_fwd(_stream(), _ptr(theta), _ptr(nuclei), _ptr(onehot), _ptr(y_in), _ptr(y_out),
-                                     _ptr(ckpt), _ptr(act), _ptr(scratch), sb, B, n_a, jets_a, jets_b, stride,
-                                     y_out.shape[1], Na, n_types, n_steps, t0, t1, y0sign), "ofdft_cnf_gnn_fwd")
+    with _on(y_in):
+        _lib.check(lib.ofdft_cnf_gnn_fwd(_stream(y_in), _ptr(theta), _ptr(nuclei), _ptr(onehot), _ptr(y_in), _ptr(y_out),
+                                         _ptr(ckpt), _ptr(act), _ptr(scratch), sb, B, n_a, jets_a, jets_b, stride,
+                                         y_out.shape[1], Na, n_types, L, n_steps, t0, t1, y0sign, int(path)), "ofdft_cnf_gnn_fwd")
     return y_out, ((ckpt, act) if act is not None else ckpt)
 
 
 def gnn_bwd(theta, nuclei, onehot, ckpt, ybar1, n_a: int, jets_a: int, jets_b: int, n_steps: int,
-            t0: float, t1: float, y0sign: float, want_ybar0: bool = False):
+            t0: float, t1: float, y0sign: float, want_ybar0: bool = False, path: int = PATH_DEFAULT):
     """ofdft_cnf_gnn_bwd: discrete adjoint; returns (theta_bar, ybar0 or None)."""
     lib = _lib.load()
     theta, nuclei, onehot, ybar1 = _f32c(theta), _f32c(nuclei), _f32c(onehot), _f32c(ybar1)
@@ -95,15 +111,17 @@ def gnn_bwd(theta, nuclei, onehot, ckpt, ybar1, n_a: int, jets_a: int, jets_b: i
     Na, n_types = onehot.shape
     theta_bar = torch.empty_like(theta)
     ybar0 = torch.zeros_like(ybar1) if want_ybar0 else None
-    sb = lib.ofdft_cnf_gnn_bwd_scratch_bytes(B, n_a, n_types)
+    L = gnn_n_layers(theta, n_types)
+    sb = lib.ofdft_cnf_gnn_bwd_scratch_bytes(B, n_a, n_types, L)
     scratch = torch.empty(sb, dtype=torch.uint8, device=ybar1.device)
-    _lib.check(lib.ofdft_cnf_gnn_bwd(_stream(), _ptr(theta), _ptr(nuclei), _ptr(onehot), _ptr(ckpt), _ptr(act), _ptr(ybar1),
-                                     _ptr(theta_bar), _ptr(ybar0), _ptr(scratch), sb, B, n_a, jets_a, jets_b, stride,
-                                     Na, n_types, n_steps, t0, t1, y0sign), "ofdft_cnf_gnn_bwd")
+    with _on(ybar1):
+        _lib.check(lib.ofdft_cnf_gnn_bwd(_stream(ybar1), _ptr(theta), _ptr(nuclei), _ptr(onehot), _ptr(ckpt), _ptr(act),
+                                         _ptr(ybar1), _ptr(theta_bar), _ptr(ybar0), _ptr(scratch), sb, B, n_a, jets_a, jets_b,
+                                         stride, Na, n_types, L, n_steps, t0, t1, y0sign, int(path)), "ofdft_cnf_gnn_bwd")
     return theta_bar, ybar0
 
 
-def gnn_rhs(theta, nuclei, onehot, y, jets: int, t: float, y0sign: float) -> torch.Tensor:
+def gnn_rhs(theta, nuclei, onehot, y, jets: int, t: float, y0sign: float, path: int = PATH_DEFAULT) -> torch.Tensor:
     """ofdft_cnf_gnn_rhs: one evaluation of d/dt [x, logp, (score)]."""
     lib = _lib.load()
     theta, nuclei, onehot, y = _f32c(theta), _f32c(nuclei), _f32c(onehot), _f32c(y)
@@ -112,8 +130,10 @@ def gnn_rhs(theta, nuclei, onehot, y, jets: int, t: float, y0sign: float) -> tor
     dy = torch.zeros_like(y)
     sb = lib.ofdft_cnf_gnn_fwd_scratch_bytes()
     scratch = torch.empty(sb, dtype=torch.uint8, device=y.device)
-    _lib.check(lib.ofdft_cnf_gnn_rhs(_stream(), _ptr(theta), _ptr(nuclei), _ptr(onehot), _ptr(y), _ptr(dy),
-                                     _ptr(scratch), sb, B, jets, stride, Na, n_types, t, y0sign), "ofdft_cnf_gnn_rhs")
+    with _on(y):
+        _lib.check(lib.ofdft_cnf_gnn_rhs(_stream(y), _ptr(theta), _ptr(nuclei), _ptr(onehot), _ptr(y), _ptr(dy), _ptr(scratch),
+                                         sb, B, jets, stride, Na, n_types, gnn_n_layers(theta, n_types), t, y0sign, int(path)),
+                   "ofdft_cnf_gnn_rhs")
     return dy
 
 
@@ -166,8 +186,9 @@ def functionals_fwd_bwd(spec: EnergySpec, y1: torch.Tensor, want_bar: bool = Tru
     ybar1 = torch.empty_like(y1) if want_bar else None
     sb = lib.ofdft_functionals_scratch_bytes(bs)
     scratch = torch.empty(sb, dtype=torch.uint8, device=y1.device)
-    _lib.check(lib.ofdft_functionals_fwd_bwd(_stream(), C.byref(cs), _host_ptr(coords), _host_ptr(z), _ptr(y1), stride,
-                                             bs, _ptr(sums), _ptr(ybar1), _ptr(scratch), sb), "ofdft_functionals_fwd_bwd")
+    with _on(y1):
+        _lib.check(lib.ofdft_functionals_fwd_bwd(_stream(y1), C.byref(cs), _host_ptr(coords), _host_ptr(z), _ptr(y1), stride,
+                                                 bs, _ptr(sums), _ptr(ybar1), _ptr(scratch), sb), "ofdft_functionals_fwd_bwd")
     return sums, ybar1
 
 
@@ -179,39 +200,39 @@ def functionals_integrands(spec: EnergySpec, y1: torch.Tensor) -> torch.Tensor:
     bs = B // 2
     cs, coords, z = spec.to_c()
     e = torch.empty((5, bs), dtype=torch.float32, device=y1.device)
-    _lib.check(lib.ofdft_functionals_integrands(_stream(), C.byref(cs), _host_ptr(coords), _host_ptr(z), _ptr(y1), stride,
-                                                bs, _ptr(e)), "ofdft_functionals_integrands")
+    with _on(y1):
+        _lib.check(lib.ofdft_functionals_integrands(_stream(y1), C.byref(cs), _host_ptr(coords), _host_ptr(z), _ptr(y1), stride,
+                                                    bs, _ptr(e)), "ofdft_functionals_integrands")
     return e
 
 
 def hartree_allpairs(x: torch.Tensor, xp: torch.Tensor, Ne: float, kind: str = "hartree", want_grad: bool = True,
-                     xbar_into: Optional[torch.Tensor] = None, xpbar_into: Optional[torch.Tensor] = None):
-    """ofdft_hartree_allpairs: cross-set pair mean + gradients.  x (n, >=d), xp (m, >=d) sharing the row stride.
-    ``xbar_into`` / ``xpbar_into``: contiguous (n|m, stride) cotangent buffers whose first d columns are ADDED to
-    (the kernel accumulates in place); otherwise fresh (n|m, d) tensors are returned."""
+                     xbar_into: Optional[torch.Tensor] = None, xpbar_into: Optional[torch.Tensor] = None,
+                     norm_pairs: float = 0.0, esum_into: Optional[torch.Tensor] = None):
+    """ofdft_hartree_allpairs: cross-set pair mean + gradients.  x (n, >=d), xp (m, >=d): state rows or packed coordinates
+    (the row strides may differ).  ``xbar_into`` / ``xpbar_into``: contiguous (n|m, stride) cotangent buffers whose first d
+    columns are ADDED to (the kernel accumulates in place, and into ``esum_into`` when given); otherwise fresh (n|m, d)
+    tensors are returned.  ``norm_pairs``: size of the pair set the mean is taken over (default n*m)."""
     lib = _lib.load()
     x, xp = _f32c(x), _f32c(xp)
     d = 3 if HART[kind] == 1 else 1
-    if x.shape[1] != xp.shape[1]:
-        raise ValueError("x and xp must share the row stride")
     n, m = x.shape[0], xp.shape[0]
-    esum = torch.empty(1, dtype=torch.float64, device=x.device)
-    accumulate = xbar_into is not None or xpbar_into is not None
+    accumulate = xbar_into is not None or xpbar_into is not None or esum_into is not None
+    esum = esum_into if esum_into is not None else torch.zeros(1, dtype=torch.float64, device=x.device)
     if accumulate:
         xbar, xpbar = xbar_into, xpbar_into
-        strides = {t.shape[1] for t in (xbar, xpbar) if t is not None}
-        if len(strides) != 1 or any(not t.is_contiguous() or t.dtype != torch.float32 for t in (xbar, xpbar) if t is not None):
-            raise ValueError("xbar_into / xpbar_into must be contiguous float32 buffers with a common row stride")
-        bar_stride = strides.pop()
+        if any(not t.is_contiguous() or t.dtype != torch.float32 for t in (xbar, xpbar) if t is not None):
+            raise ValueError("xbar_into / xpbar_into must be contiguous float32 buffers")
     else:
         xbar = torch.empty((n, d), dtype=torch.float32, device=x.device) if want_grad else None
         xpbar = torch.empty((m, d), dtype=torch.float32, device=x.device) if want_grad else None
-        bar_stride = d
     sb = lib.ofdft_hartree_allpairs_scratch_bytes(n, m)
     scratch = torch.empty(sb, dtype=torch.uint8, device=x.device)
-    _lib.check(lib.ofdft_hartree_allpairs(_stream(), HART[kind], d, float(Ne), _ptr(x), _ptr(xp), x.shape[1], n, m,
-                                          _ptr(esum), _ptr(xbar), _ptr(xpbar), bar_stride, int(accumulate), _ptr(scratch), sb),
-               "ofdft_hartree_allpairs")
+    with _on(x):
+        _lib.check(lib.ofdft_hartree_allpairs(_stream(x), HART[kind], d, float(Ne), _ptr(x), x.shape[1], _ptr(xp), xp.shape[1],
+                                              n, m, float(norm_pairs), _ptr(esum), _ptr(xbar), 0 if xbar is None else xbar.shape[1],
+                                              _ptr(xpbar), 0 if xpbar is None else xpbar.shape[1], int(accumulate),
+                                              _ptr(scratch), sb), "ofdft_hartree_allpairs")
     return esum, xbar, xpbar
 
 
@@ -239,8 +260,22 @@ def rmsprop_clip_step(theta: torch.Tensor, grad: torch.Tensor, nu: torch.Tensor,
     for t in (theta, grad, nu):
         if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
             raise ValueError("theta / grad / nu must be contiguous float32 CUDA tensors")
-    _lib.check(lib.ofdft_rmsprop_clip_step(_stream(), _ptr(theta), _ptr(grad), _ptr(nu), theta.numel(), float(lr), float(decay),
-                                           float(eps), float(max_norm)), "ofdft_rmsprop_clip_step")
+    with _on(theta):
+        _lib.check(lib.ofdft_rmsprop_clip_step(_stream(theta), _ptr(theta), _ptr(grad), _ptr(nu), theta.numel(), float(lr),
+                                               float(decay), float(eps), float(max_norm)), "ofdft_rmsprop_clip_step")
+
+
+def adam_clip_step(theta: torch.Tensor, grad: torch.Tensor, mu: torch.Tensor, nu: torch.Tensor, step: int, lr: float,
+                   b1: float = 0.9, b2: float = 0.999, eps: float = 1e-8, max_norm: float = 1.0) -> None:
+    """ofdft_adam_clip_step: optax.chain(clip_by_global_norm(max_norm), adam(lr)) (OFDFT_NF.py:104-108) in place on the flat
+    theta and the moment states mu / nu; ``step`` is the 1-based update count."""
+    lib = _lib.load()
+    for t in (theta, grad, mu, nu):
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+            raise ValueError("theta / grad / mu / nu must be contiguous float32 CUDA tensors")
+    with _on(theta):
+        _lib.check(lib.ofdft_adam_clip_step(_stream(theta), _ptr(theta), _ptr(grad), _ptr(mu), _ptr(nu), theta.numel(), int(step),
+                                            float(lr), float(b1), float(b2), float(eps), float(max_norm)), "ofdft_adam_clip_step")
 
 
 class EnergyEMA:
@@ -262,6 +297,7 @@ class EnergyEMA:
         self.step += 1
         row = (self.step - 1) % self.history.shape[0] if self.capacity else 0
         out = self.history[row]
-        _lib.check(lib.ofdft_ema_update(_stream(), _ptr(values.contiguous()), _ptr(self.state), _ptr(out), self.n, self.step,
-                                        self.decay), "ofdft_ema_update")
+        with _on(values):
+            _lib.check(lib.ofdft_ema_update(_stream(values), _ptr(values.contiguous()), _ptr(self.state), _ptr(out), self.n,
+                                            self.step, self.decay), "ofdft_ema_update")
         return out

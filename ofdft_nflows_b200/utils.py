@@ -136,8 +136,10 @@ def promolecular_log_prob_score_device(prior: ProMolecularDensity, x, want_score
     coords, z = _prior_tables(prior)
     out = torch.empty((n, 1), dtype=torch.float32, device=x.device)
     score = torch.empty((n, 3), dtype=torch.float32, device=x.device) if want_score else None
-    _lib.check(lib.ofdft_promolecular_logp_score(ops._stream(), coords.ctypes.data, z.ctypes.data, len(z), ops._ptr(x), x.shape[1],
-                                                 n, None, 0, 0, ops._ptr(out), ops._ptr(score)), "ofdft_promolecular_logp_score")
+    with ops._on(x):
+        _lib.check(lib.ofdft_promolecular_logp_score(ops._stream(x), coords.ctypes.data, z.ctypes.data, len(z), ops._ptr(x),
+                                                     x.shape[1], n, None, 0, 0, ops._ptr(out), ops._ptr(score)),
+                   "ofdft_promolecular_logp_score")
     return out, score
 
 
@@ -152,7 +154,7 @@ def batch_generator_device(seed: int, batch_size: int, prior: ProMolecularDensit
     while True:
         out = torch.empty((2 * batch_size, 7), dtype=torch.float32, device=device)
         with torch.cuda.device(out.device):
-            _lib.check(lib.ofdft_batch_generator_3d(ops._stream(), seed, call, coords.ctypes.data, z.ctypes.data, len(z),
+            _lib.check(lib.ofdft_batch_generator_3d(ops._stream(out), seed, call, coords.ctypes.data, z.ctypes.data, len(z),
                                                     batch_size, ops._ptr(out)), "ofdft_batch_generator_3d")
         call += 1
         yield out
@@ -167,7 +169,7 @@ def batche_generator_1D_device(seed: int, batch_size: int, device="cuda"):
     while True:
         out = torch.empty((2 * batch_size, 3), dtype=torch.float32, device=device)
         with torch.cuda.device(out.device):
-            _lib.check(lib.ofdft_batch_generator_1d(ops._stream(), seed, call, batch_size, ops._ptr(out)), "ofdft_batch_generator_1d")
+            _lib.check(lib.ofdft_batch_generator_1d(ops._stream(out), seed, call, batch_size, ops._ptr(out)), "ofdft_batch_generator_1d")
         call += 1
         yield out
 
@@ -188,6 +190,36 @@ def rho_rev(params, x, model_rev, prior: ProMolecularDensity, n_steps: int = Non
                         n_steps or DEFAULT_N_STEPS, -1.0, 0.0, model_rev.y0)
     coords, z = _prior_tables(prior)
     rho = torch.empty((n, 1), dtype=torch.float32, device=x.device)
-    _lib.check(lib.ofdft_promolecular_logp_score(ops._stream(), coords.ctypes.data, z.ctypes.data, len(z), ops._ptr(y0), 4, n,
-                                                 y0.data_ptr() + 12, 4, 1, ops._ptr(rho), None), "ofdft_promolecular_logp_score")
+    with ops._on(y0):
+        _lib.check(lib.ofdft_promolecular_logp_score(ops._stream(y0), coords.ctypes.data, z.ctypes.data, len(z), ops._ptr(y0), 4, n,
+                                                     y0.data_ptr() + 12, 4, 1, ops._ptr(rho), None), "ofdft_promolecular_logp_score")
     return rho
+
+
+def rho_rev_1d(params, x, model_rev, n_steps: int = None):
+    """rho_rev(params, x) of the 1-D driver (LiH.py:104-109): density of the flow at the points x (n,1) under the N(0,1) prior
+    (LiH.py:78): z_t = [x, 0] -> neural_ode(model_rev, -1 -> 0) -> exp(log N(z0) - Delta logp).  Returns (n,1)."""
+    import math
+    import torch
+    from . import ops
+    from .cn_flows import mlp_fwd
+    from .jax_ode import DEFAULT_N_STEPS
+    x = ops._f32c(x)
+    n = x.shape[0]
+    zt = torch.zeros((n, 2), dtype=torch.float32, device=x.device)
+    zt[:, 0] = x[:, 0]
+    theta = model_rev.flat_theta(params).detach()
+    y0, _ = mlp_fwd(theta, zt, model_rev, -1.0, 0.0, ops.JETS_XLOGP, n_steps or DEFAULT_N_STEPS)
+    # the base log-density is three flops per point: plain tensor arithmetic on the device result
+    logp0 = -0.5 * y0[:, 0:1] ** 2 - 0.5 * math.log(2.0 * math.pi)
+    return torch.exp(logp0 - y0[:, 1:2])
+
+
+def compute_integral(params, grid_array, rho, Ne: float, bs: int = 0):
+    """compute_integral (H20_mol_ofdft_min_equiv_flows.py:35-39): Ne * <grid_weights, rho(params, grid_coords)>; ``rho`` is a
+    callable such as ``lambda p, x: rho_rev(p, x, model_rev, prior)``."""
+    import torch
+    grid_coords, grid_weights = grid_array
+    rho_val = Ne * rho(params, grid_coords)
+    w = torch.as_tensor(grid_weights, dtype=rho_val.dtype, device=rho_val.device).reshape(-1)
+    return torch.dot(w, rho_val.reshape(-1))

@@ -710,6 +710,21 @@ def hartree_allpairs(x, xp, Ne, eps=1e-5):
     return e, gk.sum(1), -gk.sum(0)
 
 
+def softc_allpairs(x, xp, Ne):
+    """The 1-D soft-Coulomb kernel (functionals.py:439-461, no 1/2 factor) averaged over ALL cross-half pairs.
+    Returns (mean energy, d/dx, d/dxp)."""
+    diff = x[:, None, :] - xp[None]
+    zz = 1.0 + (diff * diff).sum(-1)
+    n, m = zz.shape
+    e = Ne ** 2 * (1.0 / np.sqrt(zz)).mean()
+    gk = -(Ne ** 2) * diff / zz[..., None] ** 1.5 / (n * m)
+    return e, gk.sum(1), -gk.sum(0)
+
+
+def _allpairs_fn(name: str):
+    return {"hartree_allpairs": hartree_allpairs, "softc_allpairs": softc_allpairs}.get(name.lower())
+
+
 def energy_terms(spec: EnergySpec, y1: np.ndarray, d: int):
     """Per-term means [kin, vnuc, hart, x, c] and total, from the t1 state (2*bs rows).
     Only the first half's den/score/x enter the local functionals; the second half supplies xp
@@ -719,11 +734,11 @@ def energy_terms(spec: EnergySpec, y1: np.ndarray, d: int):
     den = np.exp(y1[:bs, d:d + 1])
     score = y1[:bs, d + 1:2 * d + 1]
     e_t = _kinetic(spec.kin)(den, score, spec.Ne)
-    allpairs = spec.hart.lower() == "hartree_allpairs"
+    allpairs = _allpairs_fn(spec.hart)
     if not spec.hart:
         e_h = np.zeros_like(den)
     else:
-        e_h = np.full_like(den, hartree_allpairs(x, xp, spec.Ne)[0]) if allpairs else _hartree(spec.hart)(x, xp, spec.Ne)
+        e_h = np.full_like(den, allpairs(x, xp, spec.Ne)[0]) if allpairs else _hartree(spec.hart)(x, xp, spec.Ne)
     if spec.nuc.lower() in ("attraction", "attr"):
         e_n = attraction(x, spec.R, spec.Z_alpha, spec.Z_beta, spec.Ne)
     else:
@@ -792,8 +807,8 @@ def energy_terms_vjp(spec: EnergySpec, y1: np.ndarray, d: int):
     diff = x - xp
     if not hn:
         gx = np.zeros_like(diff)
-    elif hn == "hartree_allpairs":
-        _, gxa, gxpa = hartree_allpairs(x, xp, Ne)
+    elif _allpairs_fn(hn) is not None:
+        _, gxa, gxpa = _allpairs_fn(hn)(x, xp, Ne)
         g[:bs, :d] += gxa * bs          # the common 1/bs below is undone: the pair mean is already normalised
         g[bs:, :d] += gxpa * bs
         gx = np.zeros_like(diff)
@@ -946,6 +961,19 @@ def rmsprop_clip_step(theta, grad, nu, lr, decay=0.9, eps=1e-8, max_norm=1.0):
     g = grad * (max_norm / gn if gn > max_norm else 1.0)
     nu2 = decay * nu + (1.0 - decay) * g * g
     return theta - lr * g / np.sqrt(nu2 + eps), nu2
+
+
+def adam_clip_step(theta, grad, mu, nu, step: int, lr, b1=0.9, b2=0.999, eps=1e-8, max_norm=1.0):
+    """[third-party] optax.chain(clip_by_global_norm(max_norm), adam(lr)) as OFDFT_NF.py:104-108 builds it, restated from the
+    published algorithm (optax is not in the image): bias-corrected moments, eps OUTSIDE the square root (eps_root = 0);
+    ``step`` is the 1-based update count.  Returns (theta', mu', nu')."""
+    gn = np.sqrt((grad * grad).sum())
+    g = grad * (max_norm / gn if gn > max_norm else 1.0)
+    mu2 = b1 * mu + (1.0 - b1) * g
+    nu2 = b2 * nu + (1.0 - b2) * g * g
+    mhat = mu2 / (1.0 - b1 ** step)
+    vhat = nu2 / (1.0 - b2 ** step)
+    return theta - lr * mhat / (np.sqrt(vhat) + eps), mu2, nu2
 
 
 def ema_update(values, state, step: int, decay: float = 0.99):

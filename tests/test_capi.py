@@ -30,7 +30,7 @@ def test_header_symbols_are_exported_and_bound():
 
 def test_abi_version_and_strerror():
     lib = _lib.load()
-    assert lib.ofdft_b200_abi_version() == 2
+    assert lib.ofdft_b200_abi_version() == 3
     assert b"invalid" in lib.ofdft_b200_strerror(-1)
     assert b"unsupported" in lib.ofdft_b200_strerror(-2)
     assert b"scratch" in lib.ofdft_b200_strerror(-3)
@@ -42,7 +42,11 @@ def test_size_helpers():
     assert lib.ofdft_cnf_gnn_ckpt_bytes(131072, 16) == 16 * 4 * 6 * 131072 * 4
     assert lib.ofdft_cnf_gnn_fwd_scratch_bytes() >= 4
     n_theta = 4289 + 64 * 5
-    assert lib.ofdft_cnf_gnn_bwd_scratch_bytes(131072, 65536, 3) >= 1024 * n_theta * 4
+    assert lib.ofdft_cnf_gnn_theta_size(3, 2) == n_theta
+    assert lib.ofdft_cnf_gnn_theta_size(3, 1) == n_theta - 64 - 4096 and lib.ofdft_cnf_gnn_theta_size(3, 3) == n_theta + 64 + 4096
+    assert lib.ofdft_cnf_gnn_theta_size(3, 4) == 0
+    assert lib.ofdft_cnf_gnn_bwd_scratch_bytes(131072, 65536, 3, 2) >= 1024 * n_theta * 4
+    assert lib.ofdft_cnf_gnn_bwd_scratch_bytes(131072, 65536, 3, 3) >= 1024 * (n_theta + 4160) * 4
     assert lib.ofdft_cnf_gnn_act_ckpt_bytes(131072, 65536, 3, 1, 3, 16) == 16 * 4 * 3 * 64 * (3 * 65536 + 65536) * 4
     assert lib.ofdft_cnf_gnn_act_ckpt_bytes(300, 150, 3, 1, 3, 2) == 2 * 4 * 3 * 64 * (3 * 256 + 256) * 4   # rows padded to 128
     assert lib.ofdft_functionals_scratch_bytes(65536) >= (65536 // 256) * 5 * 8
@@ -53,15 +57,19 @@ def test_argument_validation_without_device():
     lib = _lib.load()
     # null pointers / bad sizes are rejected before any CUDA call
     N = None
-    assert lib.ofdft_cnf_gnn_fwd(N, N, N, N, N, N, N, N, N, 0, 128, 128, 3, 3, 7, 7, 3, 3, 16, 0.0, 1.0, -1.0) == -1
-    assert lib.ofdft_cnf_gnn_fwd(N, N, N, N, N, N, N, N, N, 0, 0, 0, 3, 3, 7, 7, 3, 3, 16, 0.0, 1.0, -1.0) == 0    # empty shard: no-op
-    assert lib.ofdft_cnf_gnn_fwd(N, N, N, N, N, N, N, N, N, 0, -1, 0, 3, 3, 7, 7, 3, 3, 16, 0.0, 1.0, -1.0) == -1  # B < 0
-    assert lib.ofdft_cnf_gnn_fwd(N, N, N, N, N, N, N, N, N, 0, 128, 128, 3, 3, 7, 7, 99, 3, 16, 0.0, 1.0, -1.0) == -2  # Na
-    assert lib.ofdft_cnf_gnn_fwd(N, N, N, N, N, N, N, N, N, 0, 128, 128, 3, 3, 4, 7, 3, 3, 16, 0.0, 1.0, -1.0) == -1  # stride
-    assert lib.ofdft_cnf_gnn_bwd(N, N, N, N, N, N, N, N, N, N, 0, 128, 128, 4, 3, 7, 3, 3, 16, 0.0, 1.0, -1.0) == -1  # jets
+    assert lib.ofdft_cnf_gnn_fwd(N, N, N, N, N, N, N, N, N, 0, 128, 128, 3, 3, 7, 7, 3, 3, 2, 16, 0.0, 1.0, -1.0, 0) == -1
+    assert lib.ofdft_cnf_gnn_fwd(N, N, N, N, N, N, N, N, N, 0, 0, 0, 3, 3, 7, 7, 3, 3, 2, 16, 0.0, 1.0, -1.0, 0) == 0    # empty shard: no-op
+    assert lib.ofdft_cnf_gnn_fwd(N, N, N, N, N, N, N, N, N, 0, -1, 0, 3, 3, 7, 7, 3, 3, 2, 16, 0.0, 1.0, -1.0, 0) == -1  # B < 0
+    assert lib.ofdft_cnf_gnn_fwd(N, N, N, N, N, N, N, N, N, 0, 128, 128, 3, 3, 7, 7, 129, 3, 2, 16, 0.0, 1.0, -1.0, 0) == -2  # Na
+    assert lib.ofdft_cnf_gnn_fwd(N, N, N, N, N, N, N, N, N, 0, 128, 128, 3, 3, 7, 7, 3, 3, 4, 16, 0.0, 1.0, -1.0, 0) == -2  # layers
+    assert lib.ofdft_cnf_gnn_fwd(N, N, N, N, N, N, N, N, N, 0, 128, 128, 3, 3, 4, 7, 3, 3, 2, 16, 0.0, 1.0, -1.0, 0) == -1  # stride
+    assert lib.ofdft_cnf_gnn_bwd(N, N, N, N, N, N, N, N, N, N, 0, 128, 128, 4, 3, 7, 3, 3, 2, 16, 0.0, 1.0, -1.0, 0) == -1  # jets
+    assert lib.ofdft_cnf_mlp1d_fwd(N, N, N, N, N, N, 0, 0, 3, 3, 512, 3, 16, 0.0, 1.0, -1.0, 0) == 0          # empty shard: no-op
+    assert lib.ofdft_cnf_mlp1d_rhs(N, N, N, N, N, 0, 16, 3, 3, 100, 3, 0.5, -1.0) == -2                         # width
+    assert lib.ofdft_adam_clip_step(N, N, N, N, N, 10, 0, 1e-3, 0.9, 0.999, 1e-8, 1.0) == -1
     spec = _lib.EnergySpecC(2, 3, 1, 1, 1, 0, 0, 2.0, 0.0, 0.0, 0.0)   # d = 2 is not a thing
     assert lib.ofdft_functionals_fwd_bwd(None, C.byref(spec), None, None, None, 7, 16, None, None, None, 0) == -1
-    assert lib.ofdft_hartree_allpairs(None, 1, 3, 2.0, None, None, 3, 10, 10, None, None, None, 3, 0, None, 0) == -1
+    assert lib.ofdft_hartree_allpairs(None, 1, 3, 2.0, None, 3, None, 3, 10, 10, 0.0, None, None, 3, None, 3, 0, None, 0) == -1
 
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):

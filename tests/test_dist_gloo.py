@@ -33,7 +33,7 @@ def _install_fake_ops(mol, n_steps):
     def fld(theta):
         return O.GNNField(O.unflatten_params(theta.numpy().astype(np.float64), 5, (64, 64)), mol["coords"], mol["onehot"], True)
 
-    def gnn_fwd(theta, nuclei, onehot, y_in, n_a, ja, jb, n_steps_, t0, t1, y0, want_ckpt=False, out=None, want_act=False):
+    def gnn_fwd(theta, nuclei, onehot, y_in, n_a, ja, jb, n_steps_, t0, t1, y0, want_ckpt=False, out=None, want_act=False, path=0):
         f = fld(theta)
         y1, stages = O.odeint_rk4(lambda y, t: f.rhs(t, y, True), y_in.numpy().astype(np.float64), t0, t1, n_steps_, keep=True)
         state["stages"] = stages
@@ -46,17 +46,21 @@ def _install_fake_ops(mol, n_steps):
         sums[:5] = torch.as_tensor(terms); sums[5] = e
         return sums, torch.as_tensor(O.energy_terms_vjp(ospec, y1.numpy(), 3))
 
-    def gnn_bwd(theta, nuclei, onehot, ckpt, ybar1, n_a, ja, jb, n_steps_, t0, t1, y0, want_ybar0=False):
+    def gnn_bwd(theta, nuclei, onehot, ckpt, ybar1, n_a, ja, jb, n_steps_, t0, t1, y0, want_ybar0=False, path=0):
         _, tbar = O.rk4_adjoint(fld(theta), state["stages"], t0, t1, ybar1.numpy(), True)
         return torch.as_tensor(tbar), None
 
-    def hartree_allpairs(x, xp, Ne, kind="hartree", want_grad=True, xbar_into=None, xpbar_into=None):
+    def hartree_allpairs(x, xp, Ne, kind="hartree", want_grad=True, xbar_into=None, xpbar_into=None, norm_pairs=0.0, esum_into=None):
         e, gx, gxp = O.hartree_allpairs(x[:, :3].numpy().astype(np.float64), xp[:, :3].numpy().astype(np.float64), Ne)
+        f = (x.shape[0] * xp.shape[0] / norm_pairs) if norm_pairs else 1.0         # block of a larger pair set
         if xbar_into is not None:
-            xbar_into[:, :3] += torch.as_tensor(gx)
+            xbar_into[:, :3] += f * torch.as_tensor(gx)
         if xpbar_into is not None:
-            xpbar_into[:, :3] += torch.as_tensor(gxp)
-        return torch.tensor([e], dtype=torch.float64), None, None
+            xpbar_into[:, :3] += f * torch.as_tensor(gxp)
+        if esum_into is not None:
+            esum_into += f * e
+            return esum_into, None, None
+        return torch.tensor([f * e], dtype=torch.float64), None, None
 
     ops.gnn_fwd, ops.functionals_fwd_bwd, ops.gnn_bwd = gnn_fwd, functionals_fwd_bwd, gnn_bwd
     ops.hartree_allpairs = hartree_allpairs

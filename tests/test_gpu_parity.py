@@ -58,10 +58,11 @@ def test_rhs_matches_oracle(molname, bs):
     for y0sign, neg in ((-1.0, True), (1.0, False)):
         f = O.GNNField(fld.params, mol["coords"], mol["onehot"], bool_neg=neg)
         for jets, w in ((3, 7), (2, 4), (1, 3)):
-            dy = ops.gnn_rhs(dev(theta), dev(mol["coords"]), dev(mol["onehot"]), dev(batch), jets, 0.3, y0sign).cpu().numpy()
             ref = f.rhs(0.3, batch, jets == 3)
             scale = np.abs(ref[:, :w]).max()
-            assert np.abs(dy[:, :w] - ref[:, :w]).max() < 2e-6 * max(1.0, scale)
+            for path in (ops.PATH_DEFAULT, ops.PATH_FFMA):
+                dy = ops.gnn_rhs(dev(theta), dev(mol["coords"]), dev(mol["onehot"]), dev(batch), jets, 0.3, y0sign, path=path).cpu().numpy()
+                assert np.abs(dy[:, :w] - ref[:, :w]).max() < 2e-6 * max(1.0, scale), path
 
 
 @pytest.mark.parametrize("molname,bs,n_steps", [("H2", 128, 4), ("H2O", 150, 8), ("C6H6", 70, 4)])
@@ -95,8 +96,11 @@ def test_training_step_matches_oracle_same_scheme(molname, bs, nuc):
     e_ref, terms_ref, g_ref, _ = O.loss_and_grad(fld, ospec, batch, n_steps=n_steps)
     model = Gen_EqvFlow(3, (64, 64), mol["coords"], mol["onehot"], bool_neg=True)
     spec = ops.EnergySpec(Ne=mol["Ne"], d=3, kin="tf-w", hart="hartree", nuc=nuc, x="lda", coords=mol["coords"], z=mol["z"])
-    for skip, act in ((True, True), (True, False), (False, True), (False, False)):
-        est = EnergyEstimator(model, spec, n_steps=n_steps, skip_unused_jets=skip, act_ckpt=act)
+    # every kernel pair: tcgen05 forward + backward, tcgen05 forward + FP32 recompute backward, and the FP32-pipe
+    # (PATH_FFMA) forward with its checkpoint-reading / recomputing backward kernels
+    for skip, act, path in ((True, True, ops.PATH_DEFAULT), (True, False, ops.PATH_DEFAULT), (False, True, ops.PATH_DEFAULT),
+                            (False, False, ops.PATH_DEFAULT), (True, True, ops.PATH_FFMA), (True, False, ops.PATH_FFMA)):
+        est = EnergyEstimator(model, spec, n_steps=n_steps, skip_unused_jets=skip, act_ckpt=act, path=path)
         sums, tbar, _ = est.step_flat(dev(theta), dev(batch))
         sums = sums.cpu().numpy(); g = tbar.cpu().numpy()
         for i in range(4):
@@ -146,11 +150,12 @@ def _synthetic_field(Na, nt, seed):
 
 
 @pytest.mark.parametrize("Na,nt,B,n_a,n_steps", [(1, 1, 1, 1, 1), (3, 2, 1, 0, 2), (16, 3, 130, 129, 2), (16, 4, 257, 0, 1),
-                                                 (5, 0, 40, 40, 3)])
+                                                 (5, 0, 40, 40, 3), (74, 3, 70, 40, 1), (128, 8, 33, 20, 1)])
 def test_edge_shapes_forward_and_adjoint_match_oracle(Na, nt, B, n_a, n_steps):
-    """Single-row batches, an empty first / second segment, tile tails of one row, the maximum nucleus count (16),
-    a species-free one-hot (n_types = 0) and a single RK4 step -- forward states and the discrete adjoint (both
-    checkpoint modes) against the float64 oracle with the same scheme."""
+    """Single-row batches, an empty first / second segment, tile tails of one row, 74 nuclei of 3 species (the size of
+    C27H46O, utils.py:327), the maximum nucleus and species counts (128 / 8), a species-free one-hot (n_types = 0) and a
+    single RK4 step -- forward states and the discrete adjoint (both checkpoint modes) against the float64 oracle with
+    the same scheme."""
     coords, onehot, theta, fld = _synthetic_field(Na, max(nt, 1), 11 + Na + B)
     if nt == 0:
         onehot = np.zeros((Na, 0))
@@ -183,10 +188,14 @@ def test_edge_shapes_forward_and_adjoint_match_oracle(Na, nt, B, n_a, n_steps):
 def test_error_behaviour_of_the_c_abi():
     """Bad arguments are reported, never silently computed on: more nuclei than the kernels are instantiated for,
     a theta of the wrong length, host tensors."""
-    coords, onehot, theta, _ = _synthetic_field(17, 2, 3)
+    coords, onehot, theta, _ = _synthetic_field(129, 2, 3)
     y = torch.zeros((4, 7), device="cuda")
     with pytest.raises(RuntimeError, match="code -2"):
         ops.gnn_fwd(dev(theta), dev(coords), dev(onehot), y, 4, 3, 3, 2, 0.0, 1.0, -1.0)
+    with pytest.raises(NotImplementedError):
+        Gen_EqvFlow(3, (64, 64), coords, onehot)
+    with pytest.raises(NotImplementedError):
+        Gen_EqvFlow(3, (64, 32), coords[:3], onehot[:3])
     coords, onehot, theta, _ = _synthetic_field(3, 2, 3)
     # an empty shard is not an error: no states, a zero gradient
     y1, ck = ops.gnn_fwd(dev(theta), dev(coords), dev(onehot), torch.zeros((0, 7), device="cuda"), 0, 3, 3, 2, 0.0, 1.0, -1.0,
@@ -468,6 +477,39 @@ def test_rmsprop_clip_step_and_short_training_run():
     assert np.mean(energies[-5:]) < np.mean(energies[:5]) - 0.02, energies
 
 
+def test_adam_clip_step_matches_optax_semantics():
+    """OFDFT_NF.py:104-108: optax.chain(clip_by_global_norm(1.0), adam(lr)); three consecutive updates (bias correction)."""
+    rng = np.random.default_rng(16)
+    th = rng.standard_normal(8769); mu = np.zeros(8769); nu = np.zeros(8769)
+    t_d, mu_d, nu_d = dev(th), dev(mu), dev(nu)
+    th = t_d.cpu().numpy().astype(np.float64)
+    for step in (1, 2, 3):
+        g = (0.02 if step == 3 else 3.0) * rng.standard_normal(8769)          # clipped twice, unclipped once
+        g = dev(g).cpu().numpy().astype(np.float64)
+        th, mu, nu = O.adam_clip_step(th, g, mu, nu, step, 3e-4)
+        ops.adam_clip_step(t_d, dev(g), mu_d, nu_d, step, 3e-4)
+        assert np.abs(t_d.cpu().numpy() - th).max() < 2e-6 and np.abs(mu_d.cpu().numpy() - mu).max() < 1e-7
+        assert np.abs(nu_d.cpu().numpy() - nu).max() < 1e-8
+
+
+def test_device_batches_of_consecutive_calls_are_independent():
+    """Philox streams of consecutive generator calls are disjoint: row-wise correlation between batch k and k+1 (and
+    between the raw normal draws that make them) vanishes.  (Skip-ahead counts single outputs; a 3-D row consumes 5.)"""
+    Ne, atoms, z, coords = utils.coordinates("H2")
+    prior = utils.ProMolecularDensity(z, coords)
+    gen = utils.batch_generator_device(11, 100000, prior)
+    b = [next(gen).cpu().numpy().astype(np.float64) for _ in range(3)]
+    for k in range(2):
+        for c0 in range(3):
+            for c1 in range(3):
+                assert abs(np.corrcoef(b[k][:, c0], b[k + 1][:, c1])[0, 1]) < 0.02, (k, c0, c1)
+    g1 = utils.batche_generator_1D_device(11, 100000)
+    d = [next(g1).cpu().numpy().astype(np.float64)[:, 0] for _ in range(3)]
+    for k in range(2):
+        assert abs(np.corrcoef(d[k], d[k + 1])[0, 1]) < 0.02
+        assert abs(np.corrcoef(d[k] ** 2, d[k + 1] ** 2)[0, 1]) < 0.02
+
+
 # ---- 1-D tanh-MLP flow (LiH.py: CNF(1,(512,512,512)), tfw_1d + softc + attr) ------------------------------------
 
 def _mlp_problem(feat, bs, seed):
@@ -518,15 +560,66 @@ def test_mlp1d_forward_and_training_step_match_oracle(feat, bs):
     ospec = O.EnergySpec(Ne=2, kin="tfw_1d", hart="softc", nuc="attraction", x="", R=0.7, Z_alpha=3, Z_beta=1)
     spec = ops.EnergySpec(Ne=2, d=1, kin="tfw_1d", hart="softc", nuc="attraction", x="", R=0.7, Z_alpha=3, Z_beta=1)
     e_ref, terms_ref, g_ref, _ = O.loss_and_grad(fld, ospec, batch, n_steps=n_steps)
+    # tcgen05 kernels (default), the fused FP32 integrator / adjoint sweep and the FP32 weight-gradient GEMM
+    for path in (ops.PATH_DEFAULT, ops.PATH_FFMA, ops.PATH_FFMA | ops.PATH_FFMA_DW, ops.PATH_FFMA_DW):
+        sums, tbar, _ = EnergyEstimator(model, spec, n_steps=n_steps, path=path).step_flat(dev(theta), dev(batch))
+        sums = sums.cpu().numpy(); g = tbar.cpu().numpy()
+        for i in range(3):
+            assert abs(sums[i] - terms_ref[i]) <= E_TOL * abs(terms_ref[i]), (path, i, sums[i], terms_ref[i])
+        for name, (a, b) in _mlp_slices(feat).items():
+            assert rel(g[a:b], g_ref[a:b]) <= G_TOL, (path, name, rel(g[a:b], g_ref[a:b]))
     sums, tbar, _ = EnergyEstimator(model, spec, n_steps=n_steps).step_flat(dev(theta), dev(batch))
-    sums = sums.cpu().numpy(); g = tbar.cpu().numpy()
-    for i in range(3):
-        assert abs(sums[i] - terms_ref[i]) <= E_TOL * abs(terms_ref[i]), (i, sums[i], terms_ref[i])
-    for name, (a, b) in _mlp_slices(feat).items():
-        assert rel(g[a:b], g_ref[a:b]) <= G_TOL, (name, rel(g[a:b], g_ref[a:b]))
+    # f.apply(params, t, states) (cn_flows.py:173-182) and the score-augmented right-hand side
+    params = model.unravel(dev(theta))
+    for w in (2, 3):
+        dy = model.apply(params, 0.3, dev(batch[:, :w])).cpu().numpy()
+        ref_dy = fld.rhs(0.3, batch[:, :w] if w == 3 else batch[:, :2], w == 3)
+        assert np.abs(dy - ref_dy[:, :w]).max() < 5e-6 * max(1.0, np.abs(ref_dy).max()), w
     # bitwise reproducible
     sums2, tbar2, _ = EnergyEstimator(model, spec, n_steps=n_steps).step_flat(dev(theta), dev(batch))
     assert torch.equal(tbar, tbar2)
+
+
+def test_mlp1d_multi_tile_multi_chunk_batch():
+    """B = 2*bs = 2300 rows: 18 row tiles (the last one ragged) and two 2048-row chunks of the adjoint (accumulate path),
+    small widths to keep the oracle cheap; all-pairs soft-Coulomb mode of the estimator against the oracle as well."""
+    from ofdft_nflows_b200.cn_flows import Gen_CNFSimpleMLP
+    feat, bs, n_steps = (64, 64), 1150, 2
+    theta, batch, fld = _mlp_problem(feat, bs, 23)
+    model = Gen_CNFSimpleMLP(1, feat, bool_neg=True)
+    for hart, mode in (("softc", "paired"), ("softc_allpairs", "allpairs")):
+        ospec = O.EnergySpec(Ne=2, kin="tfw_1d", hart=hart, nuc="attraction", x="", R=0.7, Z_alpha=3, Z_beta=1)
+        spec = ops.EnergySpec(Ne=2, d=1, kin="tfw_1d", hart="softc", nuc="attraction", x="", R=0.7, Z_alpha=3, Z_beta=1)
+        e_ref, terms_ref, g_ref, _ = O.loss_and_grad(fld, ospec, batch, n_steps=n_steps)
+        est = EnergyEstimator(model, spec, n_steps=n_steps, hartree_mode=mode)
+        sums, tbar, _ = est.step_flat(dev(theta), dev(batch))
+        sums_n = sums.cpu().numpy(); g = tbar.cpu().numpy()
+        for i in range(3):
+            assert abs(sums_n[i] - terms_ref[i]) <= E_TOL * abs(terms_ref[i]), (mode, i, sums_n[i], terms_ref[i])
+        assert abs(sums_n[5] - e_ref) <= E_TOL * abs(e_ref)
+        for name, (a, b) in _mlp_slices(feat).items():
+            assert rel(g[a:b], g_ref[a:b]) <= G_TOL, (mode, name, rel(g[a:b], g_ref[a:b]))
+        _, tbar2, _ = est.step_flat(dev(theta), dev(batch))
+        assert torch.equal(tbar, tbar2)
+
+
+def test_rho_rev_1d_and_compute_integral():
+    """LiH.py:104-111: density of the 1-D flow on a grid (reverse no-score flow + N(0,1) prior) and its trapezoid integral;
+    compute_integral (H20_mol_ofdft_min_equiv_flows.py:35-39) over a weighted grid."""
+    from ofdft_nflows_b200.cn_flows import Gen_CNFSimpleMLP
+    feat = (64, 64)
+    theta, _, fld = _mlp_problem(feat, 8, 29)
+    rev = Gen_CNFSimpleMLP(1, feat, bool_neg=False)
+    frev = O.MLPField(fld.params, bool_neg=False)
+    xg = np.linspace(-6.0, 6.0, 400)[:, None]
+    params = rev.unravel(dev(theta))
+    rho = utils.rho_rev_1d(params, dev(xg), rev, n_steps=16).cpu().numpy().astype(np.float64)
+    y0 = O.odeint_rk4(lambda yy, t: frev.rhs(t, yy, False), np.concatenate([xg, np.zeros_like(xg)], 1), -1.0, 0.0, 16)
+    rho_ref = np.exp(-0.5 * y0[:, 0] ** 2 - 0.5 * np.log(2 * np.pi) - y0[:, 1])
+    assert np.abs(rho[:, 0] - rho_ref).max() < 1e-5 * rho_ref.max()
+    w = np.full(400, xg[1, 0] - xg[0, 0]); w[[0, -1]] *= 0.5
+    tot = utils.compute_integral(params, (dev(xg), w), lambda p, x: utils.rho_rev_1d(p, x, rev, n_steps=16), 2.0)
+    assert abs(float(tot) - 2.0) < 2e-3            # the flow preserves the normalisation of the prior
 
 
 def test_mlp1d_golden_reference_semantics_lih_config():
