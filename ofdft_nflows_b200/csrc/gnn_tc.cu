@@ -391,7 +391,9 @@ __global__ void __launch_bounds__(kTP * NU, NB == 1 ? 2 : 1) gnn_fwd_tc_kernel(c
 // accumulators in shared memory (measured: dW2 error 2.8e-4 -> see DESIGN.md).
 constexpr int kA1TChunk = kTP * 4 + 4;      // floats per trajectory-chunk of the stacked A1^T operand (128 rows)
 constexpr int kP2TChunk = kH * 4 + 4;       // floats per trajectory-chunk of a Pbar2^T operand (64 rows)
-constexpr int kColB1 = 0, kColDw = 192, kColA = 256;   // A: two 128-column (hi|lo) operand buffers, jet parity
+// tensor-memory map (512 columns): B1 accumulators of the three jets | dW2 accumulator | Pbar2 of the three jets (the
+// unrounded values double as the "hi" operand of B1: the tensor core truncates) | tf32 remainder of the jet being staged
+constexpr int kColB1 = 0, kColDw = 192, kColP = 256, kColPlo = 448;
 #ifndef OFDFT_TC_FLUSH_PER_EVAL
 #define OFDFT_TC_FLUSH_PER_EVAL 0
 #endif
@@ -408,10 +410,8 @@ struct SmemTcB {
   float wr[kH], wt[kH], b2[kH], w3[kH];
   NucTables T;
   float S[8 * kMaxClasses * 32];          // per warp, per nucleus class: sum over the warp's trajectories of pbar1[k = 32 uh + lane]
-  float xs[3 * kTP];
-  float fbar[3 * kTP];
-  float Fpart[2 * 3 * kTP];
-  float Rpart[2 * kTP];
+  float Fpart[2][2 * 3 * kTP];            // [nucleus parity][unit half][jet][trajectory]: exchanged between the two warps of a trajectory
+  float Rpart[2][2 * kTP];
   float red[8 * 32 * 4];
   float DW[kTP * kH];                     // fp32 (round-to-nearest) accumulators of the stacked dW2 tile, [col j][row]
   uint64_t barB[3], barD[3];              // per jet: B1 batch done / dW2 batch done (each completes once per evaluation)
@@ -421,6 +421,83 @@ struct SmemTcB {
 
 static_assert(sizeof(SmemTcB) + 1024 <= 227 * 1024, "backward tile state exceeds the 227 KB of shared memory per CTA");
 static_assert(2 * (sizeof(SmemTc1) + 1024) <= 227 * 1024, "two forward CTAs must fit one SM");
+
+// named barriers of the backward kernel (0 = __syncthreads of the whole CTA)
+constexpr int kBarPair = 1;          // 1..4: the two warps of a trajectory quarter (64 threads)
+constexpr int kBarCompute = 5;       // the 256 compute threads
+constexpr int kBarStaged0 = 6;       // compute -> MMA warp: jet-0 operand of B1 is in tensor memory
+constexpr int kBarStagedJet = 7;     // 7..9: compute -> MMA warp: weight-gradient operands of jet jt (and the B1 operand of jt + 1)
+constexpr int kBwdThreads = kThreads + 128;      // two compute warpgroups + the MMA-issue warpgroup
+
+__device__ __forceinline__ void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+// The MMA-issue warp: mirrors the control flow of bwd_tile_tc and issues, per (RK4 stage, nucleus),
+//   B1hi(0..2) | B1lo(0) dW2(0) | B1lo(1) dW2(1) | B1lo(2) dW2(2)
+// as soon as all 256 compute threads have ARRIVED at the matching named barrier.  The compute warps never block on each
+// other for an MMA hand-off (they only wait on the completion mbarriers they depend on), so they drift apart and their
+// load / SFU / shared-memory phases overlap instead of running in lock-step.
+template <int NJ>
+__device__ void bwd_mma_tile(SmemTcB& sm, const GnnBwdArgs& a, uint32_t tmem) {
+  const uint32_t idesc = tc::make_idesc_tf32(kTP, kH, 0, 0);
+  const uint64_t dA1T = tc::make_desc(tc::smem_u32(sm.A1T), kA1TChunk * 4, 128);
+  const uint64_t dP2h = tc::make_desc(tc::smem_u32(sm.P2Th), kP2TChunk * 4, 128);
+  const uint64_t dP2l = tc::make_desc(tc::smem_u32(sm.P2Tl), kP2TChunk * 4, 128);
+  const uint64_t dWTh = tc::make_desc(tc::smem_u32(sm.WTh), kH * 16, 128);
+  const uint64_t dWTl = tc::make_desc(tc::smem_u32(sm.WTl), kH * 16, 128);
+  constexpr uint64_t stepW = (2 * kH * 16) >> 4;
+  // B1[jt] = Pbar2[jt] . W2^T as 3xTF32: the two passes that read the parked jet itself (x W_hi, x W_lo) ...
+  auto issue_b1_hi = [&](int jt) {
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+      const uint64_t wb = p == 1 ? dWTl : dWTh;
+#pragma unroll 1
+      for (int ksx = 0; ksx < 8; ++ksx)
+        tc::mma_tf32_ts(tmem + kColB1 + jt * kH, tmem + kColP + jt * kH + 8 * ksx, wb + ksx * stepW, idesc, (p | ksx) != 0);
+    }
+  };
+  // ... and the pass that reads its tf32 remainder from the single staging buffer (x W_hi), once that jet is staged
+  auto issue_b1_lo = [&](int jt) {
+#pragma unroll 1
+    for (int ksx = 0; ksx < 8; ++ksx)
+      tc::mma_tf32_ts(tmem + kColB1 + jt * kH, tmem + kColPlo + 8 * ksx, dWTh + ksx * stepW, idesc, true);
+    tc::commit(&sm.barB[jt]);
+  };
+  const int n_eval = a.n_steps * 4;
+#pragma unroll 1
+  for (int ev = 0; ev < n_eval; ++ev) {
+#pragma unroll 1
+    for (int i = 0; i < a.Na; ++i) {
+      bar_sync(kBarStaged0, kThreads + 32);
+      tc::fence_after_sync();
+      if (tc::elect_one()) {
+#pragma unroll
+        for (int jt = 0; jt < NJ; ++jt) issue_b1_hi(jt);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int jt = 0; jt < NJ; ++jt) {
+        bar_sync(kBarStagedJet + jt, kThreads + 32);
+        tc::fence_after_sync();
+        if (tc::elect_one()) {
+          issue_b1_lo(jt);
+          // dW2: D_dw += [A1_hi ; A1_lo]^T-stacked . (P_hi, then P_lo), K = 128 trajectories
+#pragma unroll
+          for (int p = 0; p < 2; ++p) {
+            const uint64_t pb = p == 0 ? dP2h : dP2l;
+#pragma unroll 1
+            for (int ksx = 0; ksx < 16; ++ksx) {
+              tc::mma_tf32(tmem + kColDw, dA1T + ksx * ((2 * kA1TChunk * 4) >> 4), pb + ksx * ((2 * kP2TChunk * 4) >> 4), idesc,
+                           (kFlushPerEval ? 0 : i) != 0 || (jt | p | ksx) != 0);
+            }
+          }
+          tc::commit(&sm.barD[jt]);
+        }
+        __syncwarp();
+      }
+    }
+  }
+}
 
 struct TcBwdAccum {
   float g_b2, g_w3;      // lane <-> unit j = 32 uh + lane, summed over this warp's 32 trajectories
@@ -436,9 +513,12 @@ __device__ void bwd_tile_tc(SmemTcB& sm, const GnnBwdArgs& a, long long row0, lo
   const long long jet_stride = (long long)kH * act_rows;
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
   const int m = 32 * (w & 3) + lane, uh = w >> 2;
-  const bool owner = tid < kTP;
-  const long long row = row0 + tid;
-  const bool valid = owner && row < seg_end;
+  // Both threads of a trajectory (unit halves uh = 0 / 1) carry its adjoint state and do the per-nucleus scalar algebra
+  // redundantly: nothing is serialised on an "owner" warp, and the only exchange per nucleus -- the partial dot products of
+  // the two unit halves -- needs a 64-thread named barrier between the two warps of the trajectory quarter, not the CTA.
+  const bool owner = uh == 0;                       // writes results / accumulates per-trajectory scalars once
+  const long long row = row0 + m;
+  const bool valid = row < seg_end;
   const long long rowc = row < seg_end ? row : seg_end - 1;
   float xb[3] = {0, 0, 0}, lb = 0.f, sb[3] = {0, 0, 0};
   if (valid) {
@@ -452,13 +532,9 @@ __device__ void bwd_tile_tc(SmemTcB& sm, const GnnBwdArgs& a, long long row0, lo
   float kx[3] = {0, 0, 0}, kl = 0.f, ks[3] = {0, 0, 0};
   float ysx[3] = {0, 0, 0}, yss[3] = {0, 0, 0};
   float sumx[3], sums[3], prevx[3] = {0, 0, 0}, prevs[3] = {0, 0, 0};
-  const uint32_t idesc = tc::make_idesc_tf32(kTP, kH, 0, 0);
+  float fb0 = 0.f, fb1 = 0.f, fb2 = 0.f;            // cotangents of (f, f', f'') of the current nucleus
+  int par = 0;                                      // parity of the Fpart / Rpart exchange buffers
   const uint32_t tlane = tmem + ((uint32_t)(32 * (w & 3)) << 16);
-  const uint64_t dA1T = tc::make_desc(tc::smem_u32(sm.A1T), kA1TChunk * 4, 128);
-  const uint64_t dP2h = tc::make_desc(tc::smem_u32(sm.P2Th), kP2TChunk * 4, 128);
-  const uint64_t dP2l = tc::make_desc(tc::smem_u32(sm.P2Tl), kP2TChunk * 4, 128);
-  const uint64_t dWTh = tc::make_desc(tc::smem_u32(sm.WTh), kH * 16, 128);
-  const uint64_t dWTl = tc::make_desc(tc::smem_u32(sm.WTl), kH * 16, 128);
 
   auto pre = [&](int i) {
     const float* nc = sm.T.nuc + i * 4;
@@ -478,18 +554,16 @@ __device__ void bwd_tile_tc(SmemTcB& sm, const GnnBwdArgs& a, long long row0, lo
         f2b = -r * gam;
       }
     }
-    f0b *= a.y0; f1b *= a.y0; f2b *= a.y0;
-    sm.fbar[tid] = f0b;
-    if (NJ >= 2) sm.fbar[kTP + tid] = f1b;
-    if (NJ == 3) sm.fbar[2 * kTP + tid] = f2b;
-    G.g_b3 += f0b;
+    fb0 = f0b * a.y0; fb1 = f1b * a.y0; fb2 = f2b * a.y0;
+    if (owner) G.g_b3 += fb0;
   };
   auto post = [&](int i) {
     const float* nc = sm.T.nuc + i * 4;
-    float f0 = b3 + sm.Fpart[0 * kTP + tid] + sm.Fpart[3 * kTP + tid], f1 = 0.f, f2 = 0.f;
-    if (NJ >= 2) f1 = sm.Fpart[1 * kTP + tid] + sm.Fpart[4 * kTP + tid];
-    if (NJ == 3) f2 = sm.Fpart[2 * kTP + tid] + sm.Fpart[5 * kTP + tid];
-    float rbar = sm.Rpart[tid] + sm.Rpart[kTP + tid];
+    const float* Fp = sm.Fpart[par];
+    float f0 = b3 + Fp[0 * kTP + m] + Fp[3 * kTP + m], f1 = 0.f, f2 = 0.f;
+    if (NJ >= 2) f1 = Fp[1 * kTP + m] + Fp[4 * kTP + m];
+    if (NJ == 3) f2 = Fp[2 * kTP + m] + Fp[5 * kTP + m];
+    float rbar = sm.Rpart[par][m] + sm.Rpart[par][kTP + m];
     const float d0 = xst[0] - nc[0], d1 = xst[1] - nc[1], d2 = xst[2] - nc[2];
     const float r = sqrtf(fmaf(d0, d0, fmaf(d1, d1, d2 * d2)));
     const float rinv = 1.0f / r;
@@ -523,7 +597,7 @@ __device__ void bwd_tile_tc(SmemTcB& sm, const GnnBwdArgs& a, long long row0, lo
       const float cs = stage == 0 ? 0.f : (stage == 3 ? h : 0.5f * h);
       const float ts = a.t0 + h * (float)step + cs;
       const float tprime = a.y0 * ts;
-      if (owner) {
+      {
         const float ca = (stage == 0 || stage == 3) ? h * (1.0f / 6.0f) : h * (1.0f / 3.0f);
         const float cp = stage == 3 ? 0.f : (stage == 2 ? h : 0.5f * h);
 #pragma unroll
@@ -536,13 +610,11 @@ __device__ void bwd_tile_tc(SmemTcB& sm, const GnnBwdArgs& a, long long row0, lo
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
           xst[c] = ck[(long long)c * a.B];
-          sm.xs[c * kTP + tid] = xst[c];
           if (NJ == 3) sst[c] = ck[(long long)(3 + c) * a.B];
         }
         ysx[0] = ysx[1] = ysx[2] = 0.f; yss[0] = yss[1] = yss[2] = 0.f;
         pre(0);
       }
-      __syncthreads();
 #pragma unroll 1
       for (int i = 0; i < a.Na; ++i) {
         // ---- layer-2 jets (a2, p2', p2'') of (trajectory m, units 32 uh ..) from the HBM checkpoint ----
@@ -579,7 +651,7 @@ __device__ void bwd_tile_tc(SmemTcB& sm, const GnnBwdArgs& a, long long row0, lo
         float r;
         {
           const float* nc = sm.T.nuc + i * 4;
-          const float d0 = sm.xs[m] - nc[0], d1 = sm.xs[kTP + m] - nc[1], d2 = sm.xs[2 * kTP + m] - nc[2];
+          const float d0 = xst[0] - nc[0], d1 = xst[1] - nc[1], d2 = xst[2] - nc[2];
           r = sqrtf(fmaf(d0, d0, fmaf(d1, d1, d2 * d2)));
           const float* cbi = sm.T.cb + sm.T.cls[i] * kH + 32 * uh;
 #pragma unroll
@@ -587,10 +659,9 @@ __device__ void bwd_tile_tc(SmemTcB& sm, const GnnBwdArgs& a, long long row0, lo
             av[u] = tanh_f(fmaf(sm.wr[32 * uh + u], r, fmaf(tprime, sm.wt[32 * uh + u], cbi[u])));
         }
         // ---- layer-2 tanh-jet: forward partials of f and reverse to the pre-activation cotangents (in place) ----
+        float g32[32];
         {
-          const float fb0 = sm.fbar[m], fb1 = NJ >= 2 ? sm.fbar[kTP + m] : 0.f, fb2 = NJ == 3 ? sm.fbar[2 * kTP + m] : 0.f;
           float fp[3] = {0.f, 0.f, 0.f};
-          float v32[32], g32[32];
 #pragma unroll
           for (int u = 0; u < 32; ++u) {
             const float wv = sm.w3[32 * uh + u];
@@ -620,92 +691,88 @@ __device__ void bwd_tile_tc(SmemTcB& sm, const GnnBwdArgs& a, long long row0, lo
               q1[u] = sg * t1;
             }
             q0[u] = sg * pzb;
-            v32[u] = q0[u];
             g32[u] = gw;
           }
 #pragma unroll
-          for (int jt = 0; jt < NJ; ++jt) sm.Fpart[(uh * 3 + jt) * kTP + m] = fp[jt];
-          G.g_b2 += warp_vec32_sum(v32, lane);
-          G.g_w3 += warp_vec32_sum(g32, lane);
+          for (int jt = 0; jt < NJ; ++jt) sm.Fpart[par][(uh * 3 + jt) * kTP + m] = fp[jt];
         }
         // ---- per jet: B1 (TS mode: Pbar2 hi|lo in tensor memory) and the dW2 update (operands in shared memory) ----
         // Two decoupled batches per jet so that only the shared-memory operands serialise:
         //   issue order  B1(0) | dW2(0) B1(1) | dW2(1) B1(2) | dW2(2);   waits: dW2(jt-1) before restaging shared memory,
         //   B1(last) before the layer-1 reverse; dW2(last) overlaps the reverse and the next evaluation's first phase.
-        auto tmem_stage = [&](const float (&q)[32], int buf) {
+        // Park the three cotangent jets in tensor memory (they are the unrounded "hi" operand of B1) and let the MMA warp
+        // start the B1 passes that only need them; from here on a jet lives in registers only while it is being staged.
 #pragma unroll
-          for (int c0 = 0; c0 < 32; c0 += 16) {
-            float hv[16], lv[16];
+        for (int c0 = 0; c0 < 32; c0 += 16) {
+          float hv[16];
 #pragma unroll
-            for (int u = 0; u < 16; ++u) { hv[u] = q[c0 + u]; lv[u] = tc::lo_tf32(q[c0 + u]); }
-            tc::tmem_st16(tlane + kColA + 128 * buf + 32 * uh + c0, hv);
-            tc::tmem_st16(tlane + kColA + 128 * buf + kH + 32 * uh + c0, lv);
+          for (int u = 0; u < 16; ++u) hv[u] = q0[c0 + u];
+          tc::tmem_st16(tlane + kColP + 0 * kH + 32 * uh + c0, hv);
+          if (NJ >= 2) {
+#pragma unroll
+            for (int u = 0; u < 16; ++u) hv[u] = q1[c0 + u];
+            tc::tmem_st16(tlane + kColP + 1 * kH + 32 * uh + c0, hv);
           }
-        };
-        auto issue_b1 = [&](int jt) {
+          if (NJ == 3) {
 #pragma unroll
-          for (int p = 0; p < 3; ++p) {
-            const uint32_t acol = tmem + kColA + 128 * (jt & 1) + (p == 1 ? kH : 0);
-            const uint64_t wb = p == 2 ? dWTl : dWTh;
-#pragma unroll
-            for (int ksx = 0; ksx < 8; ++ksx)
-              tc::mma_tf32_ts(tmem + kColB1 + jt * kH, acol + 8 * ksx, wb + ksx * ((2 * kH * 16) >> 4), idesc, (p | ksx) != 0);
+            for (int u = 0; u < 16; ++u) hv[u] = q2[c0 + u];
+            tc::tmem_st16(tlane + kColP + 2 * kH + 32 * uh + c0, hv);
           }
-          tc::commit(&sm.barB[jt]);
-        };
-        tmem_stage(q0, 0);
+        }
         tc::tmem_st_wait();
         tc::fence_before_sync();
-        __syncthreads();
-        if (w == 0) {
-          tc::fence_after_sync();
-          if (tc::elect_one()) issue_b1(0);
-          __syncwarp();
-        }
+        bar_arrive(kBarStaged0, kThreads + 32);          // -> MMA warp: B1hi(0 .. NJ-1)
+        G.g_w3 += warp_vec32_sum(g32, lane);
 #pragma unroll
         for (int jt = 0; jt < NJ; ++jt) {
-          // the shared-memory operands are free once the previous dW2 batch has completed
+          // the bias gradient sum_traj Pbar2[0] needs q0, which is dead once jet 0 has been staged: its butterfly runs in the
+          // shadow of the first weight-gradient batch instead of in front of the staging
+          if (jt == 1) G.g_b2 += warp_vec32_sum(q0, lane);
+          // the shared-memory operands and the remainder buffer are free once the previous dW2 batch has completed
+          // (its commit also covers the B1lo pass issued in front of it)
           if (jt > 0) { tc::mbar_wait(&sm.barD[jt - 1], (phase >> (3 + jt - 1)) & 1u); phase ^= 1u << (3 + jt - 1); __syncwarp(); }
           else if (dw_pending) { tc::mbar_wait(&sm.barD[NJ - 1], (phase >> (3 + NJ - 1)) & 1u); phase ^= 1u << (3 + NJ - 1); __syncwarp(); }
+          float pj[32];
+          if (jt == 0) {
+#pragma unroll
+            for (int u = 0; u < 32; ++u) pj[u] = q0[u];
+          } else {
+            tc::fence_after_sync();
+#pragma unroll
+            for (int c0 = 0; c0 < 32; c0 += 16) {
+              float t16[16];
+              tc::tmem_ld16(tlane + kColP + jt * kH + 32 * uh + c0, t16);
+              tc::tmem_ld_wait();
+#pragma unroll
+              for (int u = 0; u < 16; ++u) pj[c0 + u] = t16[u];
+            }
+          }
           const int cbase = (m >> 2), csub = (m & 3);
 #pragma unroll
-          for (int u = 0; u < 32; ++u) {
-            const float wv = sm.wr[32 * uh + u];
-            const float sg1 = fmaf(-av[u], av[u], 1.0f);
-            const float a1j = jt == 0 ? av[u] : (jt == 1 ? sg1 * wv : -2.0f * av[u] * sg1 * wv * wv);
-            const float pbj = jt == 0 ? q0[u] : (jt == 1 ? q1[u] : q2[u]);
-            // operands go in unrounded: the tensor core truncates them to tf32, the remainders are the "lo" parts
-            sm.A1T[cbase * kA1TChunk + (32 * uh + u) * 4 + csub] = a1j;
-            sm.A1T[cbase * kA1TChunk + (kH + 32 * uh + u) * 4 + csub] = tc::lo_tf32(a1j);
-            sm.P2Th[cbase * kP2TChunk + (32 * uh + u) * 4 + csub] = pbj;
-            sm.P2Tl[cbase * kP2TChunk + (32 * uh + u) * 4 + csub] = tc::lo_tf32(pbj);
+          for (int c0 = 0; c0 < 32; c0 += 16) {
+            float lv[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+              const int uu = c0 + u;
+              const float wv = sm.wr[32 * uh + uu];
+              const float sg1 = fmaf(-av[uu], av[uu], 1.0f);
+              const float a1j = jt == 0 ? av[uu] : (jt == 1 ? sg1 * wv : -2.0f * av[uu] * sg1 * wv * wv);
+              const float pbj = pj[uu];
+              lv[u] = tc::lo_tf32(pbj);
+              // operands go in unrounded: the tensor core truncates them to tf32, the remainders are the "lo" parts
+              sm.A1T[cbase * kA1TChunk + (32 * uh + uu) * 4 + csub] = a1j;
+              sm.A1T[cbase * kA1TChunk + (kH + 32 * uh + uu) * 4 + csub] = tc::lo_tf32(a1j);
+              sm.P2Th[cbase * kP2TChunk + (32 * uh + uu) * 4 + csub] = pbj;
+              sm.P2Tl[cbase * kP2TChunk + (32 * uh + uu) * 4 + csub] = lv[u];
+            }
+            tc::tmem_st16(tlane + kColPlo + 32 * uh + c0, lv);
           }
-          if (jt + 1 < NJ) {
-            if (jt == 0) tmem_stage(q1, 1); else tmem_stage(q2, 0);
-            tc::tmem_st_wait();
-          }
+          tc::tmem_st_wait();
           tc::fence_async_smem();
           tc::fence_before_sync();
-          __syncthreads();
-          if (w == 0) {
-            tc::fence_after_sync();
-            if (tc::elect_one()) {
-              // dW2: D_dw += [A1_hi ; A1_lo]^T-stacked . (P_hi, then P_lo), K = 128 trajectories
-#pragma unroll
-              for (int p = 0; p < 2; ++p) {
-                const uint64_t pb = p == 0 ? dP2h : dP2l;
-#pragma unroll
-                for (int ksx = 0; ksx < 16; ++ksx) {
-                  tc::mma_tf32(tmem + kColDw, dA1T + ksx * ((2 * kA1TChunk * 4) >> 4), pb + ksx * ((2 * kP2TChunk * 4) >> 4), idesc,
-                               (kFlushPerEval ? 0 : i) != 0 || (jt | p | ksx) != 0);
-                }
-              }
-              tc::commit(&sm.barD[jt]);
-              if (jt + 1 < NJ) issue_b1(jt + 1);
-            }
-            __syncwarp();
-          }
+          bar_arrive(kBarStagedJet + jt, kThreads + 32);   // -> MMA warp: B1lo(jt), dW2(jt)
         }
+        if (NJ == 1) G.g_b2 += warp_vec32_sum(q0, lane);
         dw_pending = true;
         // B1 batches complete in order: wait for the last one, then retire the (already complete) earlier phases
 #pragma unroll
@@ -744,7 +811,7 @@ __device__ void bwd_tile_tc(SmemTcB& sm, const GnnBwdArgs& a, long long row0, lo
               pr32[c0 + u] = fmaf(pb, r, sg * e);
             }
           }
-          sm.Rpart[uh * kTP + m] = rp;
+          sm.Rpart[par][uh * kTP + m] = rp;
           // fold the dW2 tile into the fp32 accumulators (row m, columns 32 uh ..)
           if (kFlushPerEval || i == a.Na - 1) {
             tc::mbar_wait(&sm.barD[NJ - 1], (phase >> (3 + NJ - 1)) & 1u); phase ^= 1u << (3 + NJ - 1);
@@ -767,27 +834,22 @@ __device__ void bwd_tile_tc(SmemTcB& sm, const GnnBwdArgs& a, long long row0, lo
           G.g_wr += pr;
         }
         tc::fence_before_sync();
-        __syncthreads();
-        if (owner) {
-          post(i);
-          if (i + 1 < a.Na) pre(i + 1);
-        }
-        if (i + 1 < a.Na) __syncthreads();
+        // the partner warp (same trajectories, other unit half) has published its Fpart / Rpart of this nucleus
+        bar_sync(kBarPair + (w & 3), 64);
+        post(i);
+        par ^= 1;
+        if (i + 1 < a.Na) pre(i + 1);
       }
-      if (owner) {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          sumx[c] += ysx[c]; prevx[c] = ysx[c];
-          sums[c] += yss[c]; prevs[c] = yss[c];
-        }
+      for (int c = 0; c < 3; ++c) {
+        sumx[c] += ysx[c]; prevx[c] = ysx[c];
+        sums[c] += yss[c]; prevs[c] = yss[c];
       }
     }
-    if (owner) {
 #pragma unroll
-      for (int c = 0; c < 3; ++c) { xb[c] += sumx[c]; sb[c] += sums[c]; }
-    }
+    for (int c = 0; c < 3; ++c) { xb[c] += sumx[c]; sb[c] += sums[c]; }
   }
-  if (valid && a.ybar0 != nullptr) {
+  if (owner && valid && a.ybar0 != nullptr) {
     float* dst = a.ybar0 + row * a.bar_stride;
     dst[0] = xb[0]; dst[1] = xb[1]; dst[2] = xb[2];
     if (NJ >= 2) dst[3] = lb;
@@ -808,7 +870,7 @@ __device__ void flush_tile_grad_tc(SmemTcB& sm, TcBwdAccum& G, float* __restrict
   const float b3w = warp_sum(G.g_b3);
   G.g_b2 = G.g_w3 = G.g_wt = G.g_wr = G.g_b3 = 0.f;
   tc::fence_before_sync();
-  __syncthreads();
+  bar_sync(kBarCompute, kThreads);
   for (int i = tid; i < kH * kH; i += kThreads) {
     const int k = i / kH, j = i % kH;
     out[L.W2 + i] = sm.DW[j * kTP + k] + sm.DW[j * kTP + kH + k];
@@ -837,22 +899,22 @@ __device__ void flush_tile_grad_tc(SmemTcB& sm, TcBwdAccum& G, float* __restrict
       out[L.W1 + (2 + t) * kH + tid] = s;
     }
   }
-  __syncthreads();
+  bar_sync(kBarCompute, kThreads);
   if (lane == 0) sm.red[w] = b3w;
-  __syncthreads();
+  bar_sync(kBarCompute, kThreads);
   if (tid == 0) out[L.b3] = sm.red[0] + sm.red[1] + sm.red[2] + sm.red[3];
   for (int i = tid; i < 8 * kMaxClasses * 32; i += kThreads) sm.S[i] = 0.f;
-  __syncthreads();
+  bar_sync(kBarCompute, kThreads);
   for (int i = tid; i < kTP * kH; i += kThreads) sm.DW[i] = 0.f;
-  __syncthreads();
+  bar_sync(kBarCompute, kThreads);
 }
 
-__global__ void __launch_bounds__(kThreads, 1) gnn_bwd_tc_kernel(const GnnBwdArgs a) {
+__global__ void __launch_bounds__(kBwdThreads, 1) gnn_bwd_tc_kernel(const GnnBwdArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   SmemTcB& sm = *reinterpret_cast<SmemTcB*>(smem_raw);
   const int tid = threadIdx.x;
   const GnnThetaLayout L(a.n_types);
-  for (int i = tid; i < kH * kH; i += kThreads) {
+  for (int i = tid; i < kH * kH; i += kBwdThreads) {
     const int k = i / kH, j = i % kH;
     float hi, lo;
     tc::split_tf32(a.theta[L.W2 + i], hi, lo);
@@ -865,9 +927,9 @@ __global__ void __launch_bounds__(kThreads, 1) gnn_bwd_tc_kernel(const GnnBwdArg
     sm.b2[tid] = a.theta[L.b2 + tid];
     sm.w3[tid] = a.theta[L.w3 + tid];
   }
-  load_nuc_tables<kThreads>(sm.T, a.theta, L, a.nuclei, a.onehot, a.Na, a.n_types);
-  for (int i = tid; i < 8 * kMaxClasses * 32; i += kThreads) sm.S[i] = 0.f;
-  for (int i = tid; i < kTP * kH; i += kThreads) sm.DW[i] = 0.f;
+  load_nuc_tables<kBwdThreads>(sm.T, a.theta, L, a.nuclei, a.onehot, a.Na, a.n_types);
+  for (int i = tid; i < 8 * kMaxClasses * 32; i += kBwdThreads) sm.S[i] = 0.f;
+  for (int i = tid; i < kTP * kH; i += kBwdThreads) sm.DW[i] = 0.f;
   if (tid == 0) {
     for (int j = 0; j < 3; ++j) { tc::mbar_init(&sm.barB[j], 1); tc::mbar_init(&sm.barD[j], 1); }
     tc::fence_mbar_init();
@@ -878,24 +940,43 @@ __global__ void __launch_bounds__(kThreads, 1) gnn_bwd_tc_kernel(const GnnBwdArg
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem = sm.tmem_slot;
-  uint32_t phase = 0;            // bits 0..2: parity of barB[jet], bits 3..5: parity of barD[jet]
-  const float b3 = a.theta[0];
-  TcBwdAccum G;
-  G.g_b2 = G.g_w3 = G.g_wt = G.g_wr = G.g_b3 = 0.f;
   const long long tiles_a = (a.n_a + kTP - 1) / kTP;
   const long long tiles_b = (a.B - a.n_a + kTP - 1) / kTP;
-  long long tile;
-  while (next_tile(a.counter, &sm.tile, tiles_a + tiles_b, tile)) {
-    long long row0, seg_end; int nj;
-    bool seg_b; long long seg_row0;
-    if (tile < tiles_a) { row0 = tile * kTP; seg_end = a.n_a; nj = a.jets_a; seg_b = false; seg_row0 = 0; }
-    else { row0 = a.n_a + (tile - tiles_a) * kTP; seg_end = a.B; nj = a.jets_b; seg_b = true; seg_row0 = a.n_a; }
-    bool dw_pending = false;
-    if (nj == 3) bwd_tile_tc<3>(sm, a, row0, seg_end, b3, G, seg_b, seg_row0, tmem, phase, dw_pending);
-    else if (nj == 2) bwd_tile_tc<2>(sm, a, row0, seg_end, b3, G, seg_b, seg_row0, tmem, phase, dw_pending);
-    else bwd_tile_tc<1>(sm, a, row0, seg_end, b3, G, seg_b, seg_row0, tmem, phase, dw_pending);
-    __syncthreads();
-    flush_tile_grad_tc(sm, G, a.gpart + (size_t)tile * L.n, L, a.onehot, a.Na, a.n_types, tmem, dw_pending);
+  // warp roles: warpgroups 0-1 (256 threads) do the CUDA-core work of a tile with (almost) the whole register file; warp 8
+  // of warpgroup 2 issues every tcgen05.mma; the register budget moves from the MMA warpgroup to the compute warpgroups
+  // (the launch allocates 168 registers x 384 threads = 64 512; 256 x 232 + 128 x 40 uses exactly that pool -- a larger
+  // request would make setmaxnreg.inc wait forever)
+  static_assert(kThreads * 232 + 128 * 40 <= 168 * kBwdThreads, "setmaxnreg budget exceeds the registers allocated at launch");
+  if (tid < kThreads) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    uint32_t phase = 0;            // bits 0..2: parity of barB[jet], bits 3..5: parity of barD[jet]
+    const float b3 = a.theta[0];
+    TcBwdAccum G;
+    G.g_b2 = G.g_w3 = G.g_wt = G.g_wr = G.g_b3 = 0.f;
+    long long tile;
+    while (next_tile(a.counter, &sm.tile, tiles_a + tiles_b, tile)) {
+      long long row0, seg_end; int nj;
+      bool seg_b; long long seg_row0;
+      if (tile < tiles_a) { row0 = tile * kTP; seg_end = a.n_a; nj = a.jets_a; seg_b = false; seg_row0 = 0; }
+      else { row0 = a.n_a + (tile - tiles_a) * kTP; seg_end = a.B; nj = a.jets_b; seg_b = true; seg_row0 = a.n_a; }
+      bool dw_pending = false;
+      if (nj == 3) bwd_tile_tc<3>(sm, a, row0, seg_end, b3, G, seg_b, seg_row0, tmem, phase, dw_pending);
+      else if (nj == 2) bwd_tile_tc<2>(sm, a, row0, seg_end, b3, G, seg_b, seg_row0, tmem, phase, dw_pending);
+      else bwd_tile_tc<1>(sm, a, row0, seg_end, b3, G, seg_b, seg_row0, tmem, phase, dw_pending);
+      bar_sync(kBarCompute, kThreads);
+      flush_tile_grad_tc(sm, G, a.gpart + (size_t)tile * L.n, L, a.onehot, a.Na, a.n_types, tmem, dw_pending);
+    }
+  } else {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    long long tile;
+    while (next_tile(a.counter, &sm.tile, tiles_a + tiles_b, tile)) {
+      if (tid < kThreads + 32) {
+        const int nj = tile < tiles_a ? a.jets_a : a.jets_b;
+        if (nj == 3) bwd_mma_tile<3>(sm, a, tmem);
+        else if (nj == 2) bwd_mma_tile<2>(sm, a, tmem);
+        else bwd_mma_tile<1>(sm, a, tmem);
+      }
+    }
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -906,7 +987,7 @@ int launch_gnn_bwd_tc(void* stream, GnnBwdArgs& a, int grid) {
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e = cudaFuncSetAttribute(gnn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemTcB) + 1024);
   if (e != cudaSuccess) return (int)e;
-  gnn_bwd_tc_kernel<<<grid, kThreads, sizeof(SmemTcB) + 1024, st>>>(a);
+  gnn_bwd_tc_kernel<<<grid, kBwdThreads, sizeof(SmemTcB) + 1024, st>>>(a);
   return (int)cudaGetLastError();
 }
 
