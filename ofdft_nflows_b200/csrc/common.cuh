@@ -46,6 +46,9 @@ __device__ __forceinline__ float warp_sum(float v) {
 // Butterfly reduction of a 32-vector held by every lane: on return lane l holds sum over lanes of v[l]
 // (31 shuffles instead of 160).
 __device__ __forceinline__ float warp_vec32_sum(float (&v)[32], int lane) {
+#ifdef OFDFT_ABL_NOBFLY      // timing ablation only (results invalid)
+  return v[lane & 31 ? 1 : 0];
+#endif
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
     const bool up = lane & 16;

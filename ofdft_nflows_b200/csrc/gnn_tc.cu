@@ -433,7 +433,7 @@ __device__ __forceinline__ void bar_arrive(int id, int count) { asm volatile("ba
 __device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
 // The MMA-issue warp: mirrors the control flow of bwd_tile_tc and issues, per (RK4 stage, nucleus),
-//   B1hi(0..2) | B1lo(0) dW2(0) | B1lo(1) dW2(1) | B1lo(2) dW2(2)
+//   B1hi(0) | dW2(0) B1lo(0) B1hi(1) | dW2(1) B1lo(1) B1hi(2) | B1lo(2) dW2(2)
 // as soon as all 256 compute threads have ARRIVED at the matching named barrier.  The compute warps never block on each
 // other for an MMA hand-off (they only wait on the completion mbarriers they depend on), so they drift apart and their
 // load / SFU / shared-memory phases overlap instead of running in lock-step.
@@ -470,18 +470,17 @@ __device__ void bwd_mma_tile(SmemTcB& sm, const GnnBwdArgs& a, uint32_t tmem) {
     for (int i = 0; i < a.Na; ++i) {
       bar_sync(kBarStaged0, kThreads + 32);
       tc::fence_after_sync();
-      if (tc::elect_one()) {
-#pragma unroll
-        for (int jt = 0; jt < NJ; ++jt) issue_b1_hi(jt);
-      }
+      if (tc::elect_one()) issue_b1_hi(0);
       __syncwarp();
 #pragma unroll
       for (int jt = 0; jt < NJ; ++jt) {
         bar_sync(kBarStagedJet + jt, kThreads + 32);
         tc::fence_after_sync();
         if (tc::elect_one()) {
-          issue_b1_lo(jt);
-          // dW2: D_dw += [A1_hi ; A1_lo]^T-stacked . (P_hi, then P_lo), K = 128 trajectories
+          // dW2: D_dw += [A1_hi ; A1_lo]^T-stacked . (P_hi, then P_lo), K = 128 trajectories.  It goes first: the compute
+          // warps restage shared memory as soon as it completes, the short B1lo pass behind it finishes under that staging
+          // (last jet: B1lo first -- the layer-1 reverse waits for it while dW2 runs underneath)
+          if (jt == NJ - 1) issue_b1_lo(jt);
 #pragma unroll
           for (int p = 0; p < 2; ++p) {
             const uint64_t pb = p == 0 ? dP2h : dP2l;
@@ -492,6 +491,9 @@ __device__ void bwd_mma_tile(SmemTcB& sm, const GnnBwdArgs& a, uint32_t tmem) {
             }
           }
           tc::commit(&sm.barD[jt]);
+          if (jt < NJ - 1) issue_b1_lo(jt);
+          // the hi passes of the next jet go behind the batch the compute warps are waiting for
+          if (jt + 1 < NJ) issue_b1_hi(jt + 1);
         }
         __syncwarp();
       }
@@ -623,6 +625,9 @@ __device__ void bwd_tile_tc(SmemTcB& sm, const GnnBwdArgs& a, long long row0, lo
           const float* src = a.act + AL.seg_base((long long)(step * 4 + stage) * a.Na + i, seg_b)
                              + act_group_off(8 * uh, (row0 - seg_row0) + m, act_rows);
 #pragma unroll
+#ifdef OFDFT_ABL_NOLOAD     // timing ablation only (results invalid): the same 2 KB for every evaluation
+          src = a.act + (threadIdx.x & 127) * 4;
+#endif
           for (int g = 0; g < 8; ++g) {
             const float4 v0 = __ldcs(reinterpret_cast<const float4*>(src + (long long)g * act_rows * 4));
             q0[4 * g] = v0.x; q0[4 * g + 1] = v0.y; q0[4 * g + 2] = v0.z; q0[4 * g + 3] = v0.w;
@@ -748,9 +753,9 @@ __device__ void bwd_tile_tc(SmemTcB& sm, const GnnBwdArgs& a, long long row0, lo
             }
           }
           const int cbase = (m >> 2), csub = (m & 3);
+          float lv[32];
 #pragma unroll
           for (int c0 = 0; c0 < 32; c0 += 16) {
-            float lv[16];
 #pragma unroll
             for (int u = 0; u < 16; ++u) {
               const int uu = c0 + u;
@@ -758,14 +763,26 @@ __device__ void bwd_tile_tc(SmemTcB& sm, const GnnBwdArgs& a, long long row0, lo
               const float sg1 = fmaf(-av[uu], av[uu], 1.0f);
               const float a1j = jt == 0 ? av[uu] : (jt == 1 ? sg1 * wv : -2.0f * av[uu] * sg1 * wv * wv);
               const float pbj = pj[uu];
-              lv[u] = tc::lo_tf32(pbj);
+              lv[uu] = tc::lo_tf32(pbj);
               // operands go in unrounded: the tensor core truncates them to tf32, the remainders are the "lo" parts
+#ifdef OFDFT_ABL_NOSTAGE     // timing ablation only (results invalid)
+              if (a1j == 123.456f) sm.A1T[uu] = pbj;
+#else
               sm.A1T[cbase * kA1TChunk + (32 * uh + uu) * 4 + csub] = a1j;
               sm.A1T[cbase * kA1TChunk + (kH + 32 * uh + uu) * 4 + csub] = tc::lo_tf32(a1j);
               sm.P2Th[cbase * kP2TChunk + (32 * uh + uu) * 4 + csub] = pbj;
-              sm.P2Tl[cbase * kP2TChunk + (32 * uh + uu) * 4 + csub] = lv[u];
+              sm.P2Tl[cbase * kP2TChunk + (32 * uh + uu) * 4 + csub] = lv[uu];
+#endif
             }
-            tc::tmem_st16(tlane + kColPlo + 32 * uh + c0, lv);
+          }
+          // the remainder buffer is free once the previous jet's B1lo pass (issued behind its dW2 batch) has completed
+          if (jt > 0) { tc::mbar_wait(&sm.barB[jt - 1], (phase >> (jt - 1)) & 1u); phase ^= 1u << (jt - 1); __syncwarp(); }
+#pragma unroll
+          for (int c0 = 0; c0 < 32; c0 += 16) {
+            float l16[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) l16[u] = lv[c0 + u];
+            tc::tmem_st16(tlane + kColPlo + 32 * uh + c0, l16);
           }
           tc::tmem_st_wait();
           tc::fence_async_smem();
@@ -774,9 +791,8 @@ __device__ void bwd_tile_tc(SmemTcB& sm, const GnnBwdArgs& a, long long row0, lo
         }
         if (NJ == 1) G.g_b2 += warp_vec32_sum(q0, lane);
         dw_pending = true;
-        // B1 batches complete in order: wait for the last one, then retire the (already complete) earlier phases
-#pragma unroll
-        for (int jt = NJ - 1; jt >= 0; --jt) { tc::mbar_wait(&sm.barB[jt], (phase >> jt) & 1u); phase ^= 1u << jt; }
+        // the earlier B1 batches were retired before their remainder buffer was reused: wait for the last one
+        tc::mbar_wait(&sm.barB[NJ - 1], (phase >> (NJ - 1)) & 1u); phase ^= 1u << (NJ - 1);
         __syncwarp();
         tc::fence_after_sync();
         // ---- layer-1 reverse from D_b1 (cotangent jets of a1 for trajectory m, units k = 32 uh ..) ----

@@ -23,6 +23,9 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, int a_major
 }
 
 __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool accumulate) {
+#ifdef OFDFT_ABL_NOMMA       // timing ablation only (results invalid)
+  return;
+#endif
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
@@ -32,6 +35,9 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64
 
 // A operand from tensor memory (M lanes x K 32-bit columns), B from shared memory
 __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, bool accumulate) {
+#ifdef OFDFT_ABL_NOMMA_TS    // timing ablation only (results invalid)
+  return;
+#endif
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem),
