@@ -3,12 +3,15 @@ size helpers / argument validation behave (no compute calls: there is no GPU her
 import ctypes as C
 import os
 import re
+import shutil
+import subprocess
+from pathlib import Path
 
 import pytest
 
 from ofdft_nflows_b200 import _lib
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = Path(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 HEADER = os.path.join(ROOT, "include", "ofdft_b200.h")
 
 
@@ -77,3 +80,51 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "_LIB", None)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         _lib.load()
+
+
+# ---- jax.ffi binding (xla_ffi_shim.cc / bindings.py): JAX is not installed here, so these are static / compile checks ----
+SHIM = ROOT / "ofdft_nflows_b200" / "jax_ffi" / "xla_ffi_shim.cc"
+BINDINGS = ROOT / "ofdft_nflows_b200" / "jax_ffi" / "bindings.py"
+STUB_INC = ROOT / "tests" / "xla_ffi_stub"
+CUDA_INC = Path(os.environ.get("CUDA_HOME", "/usr/local/cuda")) / "include"
+
+
+def _gxx(args, **kw):
+    return subprocess.run(["g++", "-std=c++17", "-fsyntax-only", f"-I{STUB_INC}", f"-I{ROOT / 'include'}", f"-I{CUDA_INC}"] + args,
+                          capture_output=True, text=True, **kw)
+
+
+@pytest.mark.skipif(shutil.which("g++") is None or not (CUDA_INC / "cuda_runtime_api.h").exists(), reason="needs g++ and CUDA headers")
+def test_xla_ffi_shim_compiles_against_the_c_abi(tmp_path):
+    """Every XLA FFI handler calls its C-ABI entry point with the argument list include/ofdft_b200.h declares and is callable
+    with the argument list its own binding declares (checked by the stand-in ffi.h of tests/xla_ffi_stub)."""
+    r = _gxx([str(SHIM)])
+    assert r.returncode == 0, r.stderr[-3000:]
+    # the stand-in really checks: a handler whose binding lacks one attribute must not compile
+    bad = tmp_path / "bad.cc"
+    bad.write_text('#include <cuda_runtime_api.h>\n#include "xla/ffi/api/ffi.h"\nnamespace ffi = xla::ffi;\n'
+                   "static ffi::Error Impl(cudaStream_t, ffi::Buffer<ffi::F32>, ffi::ResultBuffer<ffi::F32>, int32_t, float) { return ffi::Error::Success(); }\n"
+                   "XLA_FFI_DEFINE_HANDLER_SYMBOL(Bad, Impl, ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>()"
+                   '.Arg<ffi::Buffer<ffi::F32>>().Ret<ffi::Buffer<ffi::F32>>().Attr<int32_t>("n"));\n')
+    assert _gxx([str(bad)]).returncode != 0
+
+
+def test_jax_bindings_are_consistent_with_the_shim_and_the_library():
+    import ast
+    import re
+    src = BINDINGS.read_text()
+    tree = ast.parse(src)
+    consts = {}
+    for node in tree.body:
+        if isinstance(node, ast.Assign) and isinstance(node.targets[0], ast.Name) and node.targets[0].id in ("FFI_TARGETS", "SIZE_HELPERS"):
+            consts[node.targets[0].id] = [e.value for e in node.value.elts]
+    defined = set(re.findall(r"XLA_FFI_DEFINE_HANDLER_SYMBOL\((\w+)", SHIM.read_text()))
+    assert set(consts["FFI_TARGETS"]) == defined
+    called = set(re.findall(r'ffi_call\("(\w+)"', src))
+    assert called == defined                                   # every handler is wrapped, nothing else is called
+    lib = _lib.load()
+    for name in consts["SIZE_HELPERS"] + ["ofdft_cnf_gnn_theta_size"]:
+        assert hasattr(lib, name), name
+    # the attribute names of every binding appear in the Python wrapper
+    for attr in set(re.findall(r'\.Attr<[^>]+>+\("(\w+)"\)', SHIM.read_text())):
+        assert re.search(rf"\b{attr}=", src), attr
