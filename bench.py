@@ -284,6 +284,27 @@ def strong_scaling_block(dev, rank: int, world: int, n_steps: int, global_bs: in
             "speedup_vs_one_gpu": t_1 / t_n, "collectives_per_step": "2 all-reduces (8 doubles, n_theta floats); no data-path exchange"}
 
 
+def allpairs_block_single(dev, n_steps: int, bs: int, steps: int = 2):
+    """The all-pairs step on one GPU (no process group): same report as allpairs_block."""
+    import torch
+    est, theta, batch, _ = _gnn_estimator("c6h6", bs, 0, dev, n_steps, hartree_mode="allpairs")
+    timers = []
+    t = _timed(lambda: est.step_flat(theta, batch, timers=timers), steps)
+    torch.cuda.synchronize()
+    phase = {}
+    for name, a, b in timers:
+        phase.setdefault(name, []).append(a.elapsed_time(b))
+    phase = {k: sum(v[1:]) / max(1, len(v) - 1) for k, v in phase.items()}
+    pair_s = phase.get("hartree_pairs", 0.0) * 1e-3
+    evals = 2.0 * bs * bs
+    del batch
+    torch.cuda.empty_cache()
+    return {"workload": f"C6H6 3-D equivariant flow (64,64), all-pairs Hartree, bs={bs} on one GPU, RK4 x{n_steps}",
+            "n_gpus": 1, "ms_per_step": 1e3 * t, "trajectories_per_s": 2.0 * bs / t, "pair_evals_per_step": evals,
+            "pair_phase_ms": 1e3 * pair_s, "pair_evals_per_s": evals / pair_s if pair_s else None,
+            "pair_evals_per_s_per_gpu": evals / pair_s if pair_s else None, "phase_ms_rank0": phase}
+
+
 def allpairs_block(dev, rank: int, world: int, n_steps: int, bs: int, steps: int = 3):
     """BASELINE.json configs[4]: benzene-sized (12 nuclei) GNN field with the all-pairs Hartree estimator: coordinates
     all-gathered over NCCL (12 B per row; the local block is evaluated while the gather is in flight), every rank evaluates
@@ -334,6 +355,10 @@ def main():
     ap.add_argument("--no-extra-blocks", action="store_true",
                     help="skip the hartree_pairs block (N=1) and the strong / allpairs blocks (N>1) of the default run")
     ap.add_argument("--pairs-n", type=int, default=1 << 20, help="points per set of the hartree_pairs block")
+    ap.add_argument("--sweep", action="store_true",
+                    help="BASELINE.json configs[4]: all-pairs Hartree + functional sweep over GLOBAL bs = 16K .. 4M on the "
+                         "benzene-sized GNN field at this GPU count (prints one JSON line with the list and exits)")
+    ap.add_argument("--sweep-max", type=int, default=1 << 22, help="largest global batch of --sweep")
     ap.add_argument("--strong-global-bs", type=int, default=1 << 20, help="global batch of the strong-scaling block (N>1)")
     ap.add_argument("--allpairs-bs", type=int, default=16384,
                     help="per-GPU batch of the all-pairs block (N>1); the block also runs 8x this size (2^20 global on 8 GPUs)")
@@ -360,6 +385,23 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     n_gpus = world
 
+    if args.sweep:
+        pts = []
+        gbs = 1 << 14
+        while gbs <= args.sweep_max:
+            if world > 1:
+                dist.barrier()
+            blk = (allpairs_block(dev, rank, world, args.n_steps, gbs // world, steps=1 if gbs >= (1 << 20) else 2)
+                   if world > 1 else allpairs_block_single(dev, args.n_steps, gbs, steps=1 if gbs >= (1 << 20) else 2))
+            blk["global_bs"] = gbs
+            pts.append(blk)
+            gbs *= 4
+        if rank == 0:
+            print(json.dumps({"sweep": "C6H6 (12 nuclei) GNN field, all-pairs Hartree + functionals, global bs 16K-4M",
+                              "n_gpus": world, "points": pts}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     molname, bs_default, nuc = WORKLOADS[args.workload]
     bs = args.bs or bs_default
     mol, nuc, theta_np, batch_np = make_problem(args.workload, bs, seed_offset=rank)

@@ -1,18 +1,20 @@
-// gnn_tc.cu -- tensor-core (tcgen05 / TMEM) forward integrator for the 3-D equivariant GNN flow.
+// gnn_tc.cu -- tensor-core (tcgen05 / TMEM) kernels of the 3-D equivariant GNN flow: forward integrator and discrete adjoint.
 //
-// Same contract and results as gnn_fwd_kernel (gnn.cu); the [128 traj x 3 jets] x [64 x 64] layer-2 GEMM of every
+// Same contract and results as the FP32-pipe kernels of gnn.cu; every [128 trajectories x jet] x [64 x 64] GEMM of a
 // (tile, nucleus, RHS evaluation) runs on the 5th-generation tensor cores as error-compensated 3xTF32:
-//     a.w ~= a_hi.w_hi + a_lo.w_hi + a_hi.w_lo      (hi = top 19 bits, lo = exact remainder; fp32 accumulate in TMEM)
+//     a.w ~= a_hi.w_hi + a_lo.w_hi + a_hi.w_lo      (fp32 accumulate in TMEM; the tensor core TRUNCATES fp32 operands to
+//     tf32, so an unrounded value serves as its own "hi" part and lo = x - trunc(x))
 // which holds fp32-level accuracy (measured 1.6e-6 max-relative on the diagnostic GEMM, tests/tc_diag.py).
 //
-//   * thread (warp w, lane l) owns trajectory m = 32*(w&3) + l -- the TMEM lane its warp may read -- and the unit
-//     half uh = w>>2 (32 hidden units); threads with w < 4 also own the RK4 state of trajectory m;
-//   * operands are staged by the threads themselves in the canonical no-swizzle K-major UMMA layout
-//     ([16-byte chunk of 4 k][row][4 floats]: SBO = 128 B, LBO = rows*16 B), no TMA (operands are produced on chip);
-//   * one elected thread issues 24 tcgen05.mma (M=128, N=64, K=8) per jet and commits to an mbarrier; accumulators
-//     live in TMEM (3 jets x 64 columns) and come back with tcgen05.ld (32x32b) for the tanh-jet epilogue;
-//   * two jet operand buffers (2 x 64 KB): jets 0 and 1 are staged together, jet 2 reuses buffer 0 once the jet-0
-//     MMAs have completed.
+//   * thread (warp w, lane l) owns trajectory m = 32*(w&3) + l -- the TMEM lane its warp may access -- and the unit half
+//     uh = w>>2 (32 hidden units);
+//   * operands are produced on chip by the threads themselves (no TMA: nothing is fetched from HBM but the 16 KB of
+//     weights): the "hi" A operand goes to tensor memory (tcgen05.st, TS-mode MMA), remainders and the K = trajectory
+//     operands of the weight gradient to shared memory in the canonical no-swizzle K-major UMMA layout
+//     ([16-byte chunk of 4 k][row][4 floats]: SBO = 128 B, LBO = rows*16 B);
+//   * forward: 256 threads, two co-resident CTAs per SM (one tile's staging / epilogue runs under the other's MMAs);
+//   * backward: one CTA per SM, 256 compute threads + a dedicated MMA-issue warpgroup (setmaxnreg moves its registers to
+//     the compute warpgroups), hand-offs by arrive-only named barriers, completions by mbarriers (see bwd_mma_tile).
 #include <cstdlib>
 
 #include "gnn_common.cuh"
@@ -24,9 +26,8 @@ constexpr int kChunkBytesA = kTP * 16;      // LBO of the activation operand (12
 constexpr int kChunkBytesB = kH * 16;       // LBO of the weight operand (64 rows x 16 B)
 constexpr int kColAhi = 3 * kH;             // forward, two-CTA variant: TMEM columns of the activation "hi" operand
 
-template <int NB>
-struct SmemTcT {
-  float Abuf[NB][NB == 1 ? 1 : 2][kH * kTP];   // [jet buffer][hi/lo][16 chunks][128 rows][4]; NB == 1: lo only (hi in TMEM)
+struct SmemTc1 {
+  float Alo[kH * kTP];               // tf32 remainder of the jet being staged: [16 chunks][128 rows][4] (the "hi" part is in TMEM)
   float Whi[kH * kH], Wlo[kH * kH];  // B operand: [16 chunks of k][64 rows j][4]
   float wr[kH], wt[kH], b2[kH], w3[kH];
   NucTables T;
@@ -36,39 +37,8 @@ struct SmemTcT {
   unsigned int tmem_slot;
   int tile;
 };
-using SmemTc = SmemTcT<2>;     // one CTA per SM, jets 0 and 1 staged together
-using SmemTc1 = SmemTcT<1>;    // 75 KB: two CTAs per SM, jets staged one at a time (the co-resident CTA fills the waits)
-
-// stage one jet (UPT units of one trajectory) as hi/lo tf32 operands
-template <int UPT>
-__device__ __forceinline__ void stage_jet(float* __restrict__ hi, float* __restrict__ lo, const float (&v)[UPT], int m, int uh) {
-#pragma unroll
-  for (int c = 0; c < UPT / 4; ++c) {
-    float4 h, l;
-    tc::split_tf32(v[4 * c + 0], h.x, l.x); tc::split_tf32(v[4 * c + 1], h.y, l.y);
-    tc::split_tf32(v[4 * c + 2], h.z, l.z); tc::split_tf32(v[4 * c + 3], h.w, l.w);
-    const int off = (((UPT / 4) * uh + c) * kTP + m) * 4;
-    *reinterpret_cast<float4*>(hi + off) = h;
-    *reinterpret_cast<float4*>(lo + off) = l;
-  }
-}
-
-// D[jet] = A_hi.W_hi + A_lo.W_hi + A_hi.W_lo  (24 MMAs), issued by one elected lane of a converged warp.
-// The four base descriptors are built once; a K step of 8 (two 16-byte chunks) only advances the address field.
-__device__ __forceinline__ void issue_jet_mma(uint32_t d_tmem, uint64_t a_hi, uint64_t a_lo, uint64_t w_hi, uint64_t w_lo,
-                                              uint32_t idesc) {
-  constexpr uint64_t stepA = (2 * kChunkBytesA) >> 4, stepB = (2 * kChunkBytesB) >> 4;
-#pragma unroll
-  for (int p = 0; p < 3; ++p) {
-    const uint64_t ab = p == 1 ? a_lo : a_hi;
-    const uint64_t wb = p == 2 ? w_lo : w_hi;
-#pragma unroll
-    for (int ks = 0; ks < 8; ++ks) tc::mma_tf32(d_tmem, ab + ks * stepA, wb + ks * stepB, idesc, (p | ks) != 0);
-  }
-}
-
-template <int NJ, int NU, int NB>
-__device__ void fwd_tile_tc(SmemTcT<NB>& sm, const GnnFwdArgs& a, long long row0, long long seg_end, float b3,
+template <int NJ, int NU>
+__device__ void fwd_tile_tc(SmemTc1& sm, const GnnFwdArgs& a, long long row0, long long seg_end, float b3,
                             bool seg_b, long long seg_row0, uint32_t tmem, uint32_t (&phase)[3]) {
   const ActLayout AL(a.act_rows_a, a.act_rows_b, a.jets_a, a.jets_b);
   const long long act_rows = seg_b ? a.act_rows_b : a.act_rows_a;
@@ -92,10 +62,7 @@ __device__ void fwd_tile_tc(SmemTcT<NB>& sm, const GnnFwdArgs& a, long long row0
   const float h = (a.t1 - a.t0) / (float)a.n_steps;
   const uint32_t idesc = tc::make_idesc_tf32(kTP, kH, 0, 0);
   const uint32_t tlane = tmem + ((uint32_t)(32 * (w & 3)) << 16);
-  const uint64_t dA00 = tc::make_desc(tc::smem_u32(sm.Abuf[0][0]), kChunkBytesA, 128);
-  const uint64_t dA01 = tc::make_desc(tc::smem_u32(sm.Abuf[0][NB == 1 ? 0 : 1]), kChunkBytesA, 128);
-  const uint64_t dA10 = tc::make_desc(tc::smem_u32(sm.Abuf[NB - 1][0]), kChunkBytesA, 128);
-  const uint64_t dA11 = tc::make_desc(tc::smem_u32(sm.Abuf[NB - 1][NB == 1 ? 0 : 1]), kChunkBytesA, 128);
+  const uint64_t dAlo = tc::make_desc(tc::smem_u32(sm.Alo), kChunkBytesA, 128);
   const uint64_t dWh = tc::make_desc(tc::smem_u32(sm.Whi), kChunkBytesB, 128);
   const uint64_t dWl = tc::make_desc(tc::smem_u32(sm.Wlo), kChunkBytesB, 128);
 
@@ -160,7 +127,7 @@ __device__ void fwd_tile_tc(SmemTcT<NB>& sm, const GnnFwdArgs& a, long long row0
           for (int u = 0; u < UPT; ++u)
             av[u] = tanh_f(fmaf(sm.wr[UPT * uh + u], r, fmaf(tprime, sm.wt[UPT * uh + u], cbi[u])));
         }
-        if (NB == 1) {
+        {
           // one jet at a time on one mbarrier.  The MMAs read 6 KB of operands per 32 clocks from shared memory when both
           // come from there -- more than its 128 B/clk -- so the activation "hi" part (read by two of the three passes)
           // goes to tensor memory (TS-mode MMA) and only the tf32 remainder is staged in shared memory.
@@ -184,7 +151,7 @@ __device__ void fwd_tile_tc(SmemTcT<NB>& sm, const GnnFwdArgs& a, long long row0
 #pragma unroll
             for (int c = 0; c < UPT / 4; ++c) {
               const int off = (((UPT / 4) * uh + c) * kTP + m) * 4;
-              *reinterpret_cast<float4*>(sm.Abuf[0][0] + off) =
+              *reinterpret_cast<float4*>(sm.Alo + off) =
                   make_float4(tc::lo_tf32(aj[4 * c]), tc::lo_tf32(aj[4 * c + 1]), tc::lo_tf32(aj[4 * c + 2]), tc::lo_tf32(aj[4 * c + 3]));
             }
             tc::tmem_st_wait();
@@ -201,60 +168,13 @@ __device__ void fwd_tile_tc(SmemTcT<NB>& sm, const GnnFwdArgs& a, long long row0
 #pragma unroll
                 for (int ks = 0; ks < 8; ++ks) tc::mma_tf32_ts(d, tmem + kColAhi + 8 * ks, dWl + ks * stepB, idesc, true);
 #pragma unroll
-                for (int ks = 0; ks < 8; ++ks) tc::mma_tf32(d, dA01 + ks * stepA, dWh + ks * stepB, idesc, true);
+                for (int ks = 0; ks < 8; ++ks) tc::mma_tf32(d, dAlo + ks * stepA, dWh + ks * stepB, idesc, true);
                 tc::commit(&sm.bar[0]);
               }
               __syncwarp();
             }
           }
           tc::mbar_wait(&sm.bar[0], phase[0]); phase[0] ^= 1;
-        } else {
-          stage_jet<UPT>(sm.Abuf[0][0], sm.Abuf[0][1], av, m, uh);
-          if (NJ >= 2) {
-            float a1[UPT];
-#pragma unroll
-            for (int u = 0; u < UPT; ++u) a1[u] = fmaf(-av[u], av[u], 1.0f) * sm.wr[UPT * uh + u];
-            stage_jet<UPT>(sm.Abuf[NB - 1][0], sm.Abuf[NB - 1][1], a1, m, uh);
-          }
-          tc::fence_async_smem();
-          __syncthreads();
-          if (w == 0) {
-            tc::fence_after_sync();
-            if (tc::elect_one()) {
-              issue_jet_mma(tmem + 0 * kH, dA00, dA01, dWh, dWl, idesc);
-              tc::commit(&sm.bar[0]);
-              if (NJ >= 2) {
-                issue_jet_mma(tmem + 1 * kH, dA10, dA11, dWh, dWl, idesc);
-                tc::commit(&sm.bar[1]);
-              }
-            }
-            __syncwarp();
-          }
-          if (NJ == 3) {
-            float a2[UPT];
-#pragma unroll
-            for (int u = 0; u < UPT; ++u) {
-              const float wv = sm.wr[UPT * uh + u];
-              a2[u] = -2.0f * av[u] * fmaf(-av[u], av[u], 1.0f) * wv * wv;
-            }
-            tc::mbar_wait(&sm.bar[0], phase[0]);           // jet-0 MMAs have finished reading buffer 0
-            __syncwarp();
-            stage_jet<UPT>(sm.Abuf[0][0], sm.Abuf[0][1], a2, m, uh);
-            tc::fence_async_smem();
-            __syncthreads();
-            if (w == 0) {
-              tc::fence_after_sync();
-              if (tc::elect_one()) {
-                issue_jet_mma(tmem + 2 * kH, dA00, dA01, dWh, dWl, idesc);
-                tc::commit(&sm.bar[2]);
-              }
-              __syncwarp();
-            }
-          }
-          // ---- wait for the last commit (commits complete in order), then the tanh-jet epilogue from TMEM ----
-          if (NJ == 3) { tc::mbar_wait(&sm.bar[2], phase[2]); phase[2] ^= 1; phase[0] ^= 1; tc::mbar_wait(&sm.bar[1], phase[1]); phase[1] ^= 1; }
-          else if (NJ == 2) { tc::mbar_wait(&sm.bar[1], phase[1]); phase[1] ^= 1; tc::mbar_wait(&sm.bar[0], phase[0]); phase[0] ^= 1; }
-          else { tc::mbar_wait(&sm.bar[0], phase[0]); phase[0] ^= 1; }
         }
         __syncwarp();                                   // tcgen05.ld is .sync.aligned: reconverge after the spin loops
         tc::fence_after_sync();
@@ -285,7 +205,11 @@ __device__ void fwd_tile_tc(SmemTcT<NB>& sm, const GnnFwdArgs& a, long long row0
               if (NJ == 3) fp[2] = fmaf(wv, fmaf(sg, p2[u], -2.0f * aa * a1 * p1[u]), fp[2]);
             }
           }
+#ifdef OFDFT_ABL_NOACTSTORE    // timing ablation only (the backward then reads garbage)
+          if (false) {
+#else
           if (actp != nullptr) {
+#endif
             // layer-2 jets (a2, p2', p2'') -> HBM, four units per 16-byte store
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
@@ -326,11 +250,11 @@ __device__ void fwd_tile_tc(SmemTcT<NB>& sm, const GnnFwdArgs& a, long long row0
   }
 }
 
-template <int NU, int NB>
-__global__ void __launch_bounds__(kTP * NU, NB == 1 ? 2 : 1) gnn_fwd_tc_kernel(const GnnFwdArgs a) {
+template <int NU>
+__global__ void __launch_bounds__(kTP * NU, 2) gnn_fwd_tc_kernel(const GnnFwdArgs a) {
   constexpr int kThr = kTP * NU;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  SmemTcT<NB>& sm = *reinterpret_cast<SmemTcT<NB>*>(smem_raw);
+  SmemTc1& sm = *reinterpret_cast<SmemTc1*>(smem_raw);
   const int tid = threadIdx.x;
   const GnnThetaLayout L(a.n_types);
   // weight operand B[n = j][k] = W2[k][j], split hi/lo, layout [k/4][j][k%4]
@@ -368,9 +292,9 @@ __global__ void __launch_bounds__(kTP * NU, NB == 1 ? 2 : 1) gnn_fwd_tc_kernel(c
     bool seg_b; long long seg_row0;
     if (tile < tiles_a) { row0 = tile * kTP; seg_end = a.n_a; nj = a.jets_a; seg_b = false; seg_row0 = 0; }
     else { row0 = a.n_a + (tile - tiles_a) * kTP; seg_end = a.B; nj = a.jets_b; seg_b = true; seg_row0 = a.n_a; }
-    if (nj == 3) fwd_tile_tc<3, NU, NB>(sm, a, row0, seg_end, b3, seg_b, seg_row0, tmem, phase);
-    else if (nj == 2) fwd_tile_tc<2, NU, NB>(sm, a, row0, seg_end, b3, seg_b, seg_row0, tmem, phase);
-    else fwd_tile_tc<1, NU, NB>(sm, a, row0, seg_end, b3, seg_b, seg_row0, tmem, phase);
+    if (nj == 3) fwd_tile_tc<3, NU>(sm, a, row0, seg_end, b3, seg_b, seg_row0, tmem, phase);
+    else if (nj == 2) fwd_tile_tc<2, NU>(sm, a, row0, seg_end, b3, seg_b, seg_row0, tmem, phase);
+    else fwd_tile_tc<1, NU>(sm, a, row0, seg_end, b3, seg_b, seg_row0, tmem, phase);
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -390,10 +314,13 @@ __global__ void __launch_bounds__(kTP * NU, NB == 1 ? 2 : 1) gnn_fwd_tc_kernel(c
 // ~1e-4.  D_dw is therefore restarted every (nucleus, RHS evaluation) -- 96 MMAs -- and folded into round-to-nearest fp32
 // accumulators in shared memory (measured: dW2 error 2.8e-4 -> see DESIGN.md).
 constexpr int kA1TChunk = kTP * 4 + 4;      // floats per trajectory-chunk of the stacked A1^T operand (128 rows)
-constexpr int kP2TChunk = kH * 4 + 4;       // floats per trajectory-chunk of a Pbar2^T operand (64 rows)
+constexpr int kP2TChunk = 2 * kH * 4 + 4;   // floats per trajectory-chunk of the stacked [hi j | lo j] Pbar2^T operand (128 rows)
 // tensor-memory map (512 columns): B1 accumulators of the three jets | dW2 accumulator | Pbar2 of the three jets (the
 // unrounded values double as the "hi" operand of B1: the tensor core truncates) | tf32 remainder of the jet being staged
-constexpr int kColB1 = 0, kColDw = 192, kColP = 256, kColPlo = 448;
+// The remainder of jet 0 borrows the accumulator columns of jet 2 (B1lo(0) has run before B1hi(2) is issued), the remainder
+// of jet jt >= 1 the parked columns of jet jt - 1 (dead once B1(jt - 1) has completed): no dedicated remainder buffer.
+constexpr int kColB1 = 0, kColDw = 192, kColP = 320;
+__host__ __device__ constexpr int col_plo(int jt) { return jt == 0 ? kColB1 + 2 * kH : kColP + (jt - 1) * kH; }
 #ifndef OFDFT_TC_FLUSH_PER_EVAL
 #define OFDFT_TC_FLUSH_PER_EVAL 0
 #endif
@@ -405,7 +332,7 @@ constexpr bool kPrefetchL2 = OFDFT_TC_PREFETCH_L2 != 0;   // else: once per RK4 
 
 struct SmemTcB {
   float A1T[32 * kA1TChunk];
-  float P2Th[32 * kP2TChunk], P2Tl[32 * kP2TChunk];
+  float P2T[32 * kP2TChunk];              // rows 0..63: Pbar2 (hi), rows 64..127: its tf32 remainder -- one N = 128 B operand
   float WTh[kH * kH], WTl[kH * kH];       // B operand of B1: [j/4][k][j%4] = W2[k][j]
   float wr[kH], wt[kH], b2[kH], w3[kH];
   NucTables T;
@@ -441,8 +368,8 @@ template <int NJ>
 __device__ void bwd_mma_tile(SmemTcB& sm, const GnnBwdArgs& a, uint32_t tmem) {
   const uint32_t idesc = tc::make_idesc_tf32(kTP, kH, 0, 0);
   const uint64_t dA1T = tc::make_desc(tc::smem_u32(sm.A1T), kA1TChunk * 4, 128);
-  const uint64_t dP2h = tc::make_desc(tc::smem_u32(sm.P2Th), kP2TChunk * 4, 128);
-  const uint64_t dP2l = tc::make_desc(tc::smem_u32(sm.P2Tl), kP2TChunk * 4, 128);
+  const uint64_t dP2 = tc::make_desc(tc::smem_u32(sm.P2T), kP2TChunk * 4, 128);
+  const uint32_t idesc_dw = tc::make_idesc_tf32(kTP, 2 * kH, 0, 0);      // M = 128 (hi k | lo k), N = 128 (hi j | lo j)
   const uint64_t dWTh = tc::make_desc(tc::smem_u32(sm.WTh), kH * 16, 128);
   const uint64_t dWTl = tc::make_desc(tc::smem_u32(sm.WTl), kH * 16, 128);
   constexpr uint64_t stepW = (2 * kH * 16) >> 4;
@@ -460,7 +387,7 @@ __device__ void bwd_mma_tile(SmemTcB& sm, const GnnBwdArgs& a, uint32_t tmem) {
   auto issue_b1_lo = [&](int jt) {
 #pragma unroll 1
     for (int ksx = 0; ksx < 8; ++ksx)
-      tc::mma_tf32_ts(tmem + kColB1 + jt * kH, tmem + kColPlo + 8 * ksx, dWTh + ksx * stepW, idesc, true);
+      tc::mma_tf32_ts(tmem + kColB1 + jt * kH, tmem + col_plo(jt) + 8 * ksx, dWTh + ksx * stepW, idesc, true);
     tc::commit(&sm.barB[jt]);
   };
   const int n_eval = a.n_steps * 4;
@@ -481,14 +408,10 @@ __device__ void bwd_mma_tile(SmemTcB& sm, const GnnBwdArgs& a, uint32_t tmem) {
           // warps restage shared memory as soon as it completes, the short B1lo pass behind it finishes under that staging
           // (last jet: B1lo first -- the layer-1 reverse waits for it while dW2 runs underneath)
           if (jt == NJ - 1) issue_b1_lo(jt);
-#pragma unroll
-          for (int p = 0; p < 2; ++p) {
-            const uint64_t pb = p == 0 ? dP2h : dP2l;
 #pragma unroll 1
-            for (int ksx = 0; ksx < 16; ++ksx) {
-              tc::mma_tf32(tmem + kColDw, dA1T + ksx * ((2 * kA1TChunk * 4) >> 4), pb + ksx * ((2 * kP2TChunk * 4) >> 4), idesc,
-                           (kFlushPerEval ? 0 : i) != 0 || (jt | p | ksx) != 0);
-            }
+          for (int ksx = 0; ksx < 16; ++ksx) {
+            tc::mma_tf32(tmem + kColDw, dA1T + ksx * ((2 * kA1TChunk * 4) >> 4), dP2 + ksx * ((2 * kP2TChunk * 4) >> 4), idesc_dw,
+                         (kFlushPerEval ? 0 : i) != 0 || (jt | ksx) != 0);
           }
           tc::commit(&sm.barD[jt]);
           if (jt < NJ - 1) issue_b1_lo(jt);
@@ -770,8 +693,8 @@ __device__ void bwd_tile_tc(SmemTcB& sm, const GnnBwdArgs& a, long long row0, lo
 #else
               sm.A1T[cbase * kA1TChunk + (32 * uh + uu) * 4 + csub] = a1j;
               sm.A1T[cbase * kA1TChunk + (kH + 32 * uh + uu) * 4 + csub] = tc::lo_tf32(a1j);
-              sm.P2Th[cbase * kP2TChunk + (32 * uh + uu) * 4 + csub] = pbj;
-              sm.P2Tl[cbase * kP2TChunk + (32 * uh + uu) * 4 + csub] = lv[uu];
+              sm.P2T[cbase * kP2TChunk + (32 * uh + uu) * 4 + csub] = pbj;
+              sm.P2T[cbase * kP2TChunk + (kH + 32 * uh + uu) * 4 + csub] = lv[uu];
 #endif
             }
           }
@@ -782,7 +705,7 @@ __device__ void bwd_tile_tc(SmemTcB& sm, const GnnBwdArgs& a, long long row0, lo
             float l16[16];
 #pragma unroll
             for (int u = 0; u < 16; ++u) l16[u] = lv[c0 + u];
-            tc::tmem_st16(tlane + kColPlo + 32 * uh + c0, l16);
+            tc::tmem_st16(tlane + col_plo(jt) + 32 * uh + c0, l16);
           }
           tc::tmem_st_wait();
           tc::fence_async_smem();
@@ -837,10 +760,12 @@ __device__ void bwd_tile_tc(SmemTcB& sm, const GnnBwdArgs& a, long long row0, lo
 #pragma unroll
           for (int c0 = 0; c0 < 32; c0 += 16) {
             float t[16];
-            tc::tmem_ld16(tlane + kColDw + 32 * uh + c0, t);
+            float t2[16];
+            tc::tmem_ld16(tlane + kColDw + 32 * uh + c0, t);            // columns j: A1 (hi|lo rows) x Pbar2 hi
+            tc::tmem_ld16(tlane + kColDw + kH + 32 * uh + c0, t2);      // columns 64 + j:           x Pbar2 lo
             tc::tmem_ld_wait();
 #pragma unroll
-            for (int u = 0; u < 16; ++u) sm.DW[(32 * uh + c0 + u) * kTP + m] += t[u];
+            for (int u = 0; u < 16; ++u) sm.DW[(32 * uh + c0 + u) * kTP + m] += t[u] + t2[u];
           }
           }
           const float ps = warp_vec32_sum(ps32, lane);
@@ -1017,10 +942,10 @@ int launch_gnn_fwd_tc(void* stream, GnnFwdArgs& a, void* scratch, size_t scratch
   const long long tiles = (a.n_a + kTP - 1) / kTP + (a.B - a.n_a + kTP - 1) / kTP;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  e = cudaFuncSetAttribute(gnn_fwd_tc_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemTc1) + 1024);
+  e = cudaFuncSetAttribute(gnn_fwd_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemTc1) + 1024);
   if (e != cudaSuccess) return (int)e;
   const int grid = (int)(tiles < 2 * sms ? tiles : 2 * sms);
-  gnn_fwd_tc_kernel<2, 1><<<grid, kTP * 2, sizeof(SmemTc1) + 1024, st>>>(a);
+  gnn_fwd_tc_kernel<2><<<grid, kTP * 2, sizeof(SmemTc1) + 1024, st>>>(a);
   return (int)cudaGetLastError();
 }
 
