@@ -233,21 +233,38 @@ constexpr int kHpThreads = 256;
 constexpr int kHpPts = 4;                 // i-points per thread
 constexpr int kHpTile = 256;              // j-points per shared-memory tile
 
-template <int D, bool FORCES>
+// packed FP32 pairs (Blackwell FFMA2 / FADD2 / FMUL2: two independent fp32 operations per issue slot)
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void unpack2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+
+// One (i-block, j-split) CTA: every thread keeps kHpPts = 4 i-points as two PACKED pairs, so a pair evaluation costs
+// 6 issue slots (+ 1 MUFU.RSQ) with forces and 3.5 (+ 1 MUFU) without, instead of 12 / 7 scalar FP32 instructions: the
+// kernel is then bounded by the FP32 pipe (forces) or the SFU (energy only), not by the issue rate.  The j-tile holds the
+// NEGATED xp coordinates so that the difference is one packed add.
+template <int D, bool FORCES, bool ENERGY>
 __global__ void __launch_bounds__(kHpThreads) hartree_pairs_kernel(const float* __restrict__ x, const float* __restrict__ xp,
                                                                   int stride, int stride_p, long long n, long long m, float cst,
                                                                   int splits, double* __restrict__ epart,
                                                                   float* __restrict__ fpart) {
+  static_assert(kHpPts == 4, "two packed pairs of i-points per thread");
   __shared__ float4 tile[kHpTile];
   const long long i0 = ((long long)blockIdx.x * kHpThreads + threadIdx.x) * kHpPts;
-  float xi[kHpPts][3], f[kHpPts][3], e[kHpPts];
+  f32x2 xi[2][3], f[2][3], e[2];
 #pragma unroll
-  for (int p = 0; p < kHpPts; ++p) {
-    const long long i = i0 + p < n ? i0 + p : n - 1;
+  for (int pp = 0; pp < 2; ++pp) {
+    const long long ia = i0 + 2 * pp < n ? i0 + 2 * pp : n - 1, ib = i0 + 2 * pp + 1 < n ? i0 + 2 * pp + 1 : n - 1;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) { xi[p][c] = c < D ? x[i * stride + c] : 0.f; f[p][c] = 0.f; }
-    e[p] = 0.f;
+    for (int c = 0; c < 3; ++c) {
+      xi[pp][c] = c < D ? pack2(x[ia * stride + c], x[ib * stride + c]) : pack2(0.f, 0.f);
+      f[pp][c] = pack2(0.f, 0.f);
+    }
+    e[pp] = pack2(0.f, 0.f);
   }
+  const f32x2 cst2 = pack2(cst, cst);
   const long long per = (m + splits - 1) / splits;
   const long long j_begin = (long long)blockIdx.y * per;
   const long long j_end = j_begin + per < m ? j_begin + per : m;
@@ -256,10 +273,10 @@ __global__ void __launch_bounds__(kHpThreads) hartree_pairs_kernel(const float* 
     __syncthreads();
     {
       const long long j = jt + threadIdx.x;
-      float4 v = make_float4(1e18f, 1e18f, 1e18f, 0.f);   // padded points sit "at infinity": rsqrt -> 0, force -> 0
+      float4 v = make_float4(-1e18f, -1e18f, -1e18f, 0.f);   // padded points sit "at infinity": rsqrt -> 0, force -> 0
       if (j < j_end) {
-        v.x = xp[j * stride_p];
-        if (D == 3) { v.y = xp[j * stride_p + 1]; v.z = xp[j * stride_p + 2]; } else { v.y = 0.f; v.z = 0.f; }
+        v.x = -xp[j * stride_p];
+        if (D == 3) { v.y = -xp[j * stride_p + 1]; v.z = -xp[j * stride_p + 2]; } else { v.y = 0.f; v.z = 0.f; }
       }
       tile[threadIdx.x] = v;
     }
@@ -267,38 +284,59 @@ __global__ void __launch_bounds__(kHpThreads) hartree_pairs_kernel(const float* 
 #pragma unroll 8
     for (int jj = 0; jj < kHpTile; ++jj) {
       const float4 q = tile[jj];
+      const f32x2 q0 = pack2(q.x, q.x), q1 = pack2(q.y, q.y), q2 = pack2(q.z, q.z);
 #pragma unroll
-      for (int p = 0; p < kHpPts; ++p) {
-        const float d0 = xi[p][0] - q.x;
-        float zz = fmaf(d0, d0, cst);
-        float d1 = 0.f, d2 = 0.f;
-        if (D == 3) { d1 = xi[p][1] - q.y; d2 = xi[p][2] - q.z; zz = fmaf(d1, d1, zz); zz = fmaf(d2, d2, zz); }
-        float rs;
-        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(zz));    // MUFU.RSQ without the denormal fix-up path
-        e[p] += rs;
+      for (int pp = 0; pp < 2; ++pp) {
+        const f32x2 d0 = add2(xi[pp][0], q0);
+        f32x2 zz = fma2(d0, d0, cst2);
+        f32x2 d1 = 0, d2 = 0;
+        if (D == 3) { d1 = add2(xi[pp][1], q1); d2 = add2(xi[pp][2], q2); zz = fma2(d1, d1, zz); zz = fma2(d2, d2, zz); }
+        float za, zb, ra, rb;
+        unpack2(zz, za, zb);
+        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(ra) : "f"(za));    // MUFU.RSQ without the denormal fix-up path
+        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rb) : "f"(zb));
+        const f32x2 rs = pack2(ra, rb);
+        if (ENERGY) e[pp] = add2(e[pp], rs);
         if (FORCES) {
-          const float g = rs * rs * rs;
-          f[p][0] = fmaf(g, d0, f[p][0]);
-          if (D == 3) { f[p][1] = fmaf(g, d1, f[p][1]); f[p][2] = fmaf(g, d2, f[p][2]); }
+          const f32x2 g = mul2(mul2(rs, rs), rs);
+          f[pp][0] = fma2(g, d0, f[pp][0]);
+          if (D == 3) { f[pp][1] = fma2(g, d1, f[pp][1]); f[pp][2] = fma2(g, d2, f[pp][2]); }
         }
       }
     }
     // flush the fp32 tile sums into the float64 accumulator every tile
+    if (ENERGY) {
 #pragma unroll
-    for (int p = 0; p < kHpPts; ++p) { if (i0 + p < n) esum += (double)e[p]; e[p] = 0.f; }
+      for (int pp = 0; pp < 2; ++pp) {
+        float ea, eb;
+        unpack2(e[pp], ea, eb);
+        if (i0 + 2 * pp < n) esum += (double)ea;
+        if (i0 + 2 * pp + 1 < n) esum += (double)eb;
+        e[pp] = pack2(0.f, 0.f);
+      }
+    }
   }
+  if (fpart != nullptr) {
 #pragma unroll
-  for (int p = 0; p < kHpPts; ++p)
-    if (i0 + p < n && fpart != nullptr)
-      for (int c = 0; c < D; ++c) fpart[((size_t)blockIdx.y * n + (i0 + p)) * D + c] = f[p][c];
-  __shared__ double red[kHpThreads / 32];
-  for (int o = 16; o > 0; o >>= 1) esum += __shfl_xor_sync(0xffffffffu, esum, o);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = esum;
-  __syncthreads();
-  if (threadIdx.x == 0 && epart != nullptr) {
-    double v = 0.0;
-    for (int w = 0; w < kHpThreads / 32; ++w) v += red[w];
-    epart[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = v;
+    for (int pp = 0; pp < 2; ++pp)
+#pragma unroll
+      for (int c = 0; c < D; ++c) {
+        float fa, fb;
+        unpack2(f[pp][c], fa, fb);
+        if (i0 + 2 * pp < n) fpart[((size_t)blockIdx.y * n + (i0 + 2 * pp)) * D + c] = fa;
+        if (i0 + 2 * pp + 1 < n) fpart[((size_t)blockIdx.y * n + (i0 + 2 * pp + 1)) * D + c] = fb;
+      }
+  }
+  if (ENERGY) {
+    __shared__ double red[kHpThreads / 32];
+    for (int o = 16; o > 0; o >>= 1) esum += __shfl_xor_sync(0xffffffffu, esum, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = esum;
+    __syncthreads();
+    if (threadIdx.x == 0 && epart != nullptr) {
+      double v = 0.0;
+      for (int w = 0; w < kHpThreads / 32; ++w) v += red[w];
+      epart[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = v;
+    }
   }
 }
 
@@ -548,10 +586,13 @@ extern "C" int ofdft_hartree_allpairs(void* stream, int32_t kind, int32_t d, flo
     dim3 grid(blocks, (unsigned)splits);
     double* ep = pass == 0 ? epart : nullptr;
     float* fp = out ? fpart : nullptr;
-    if (d == 3 && fp) hartree_pairs_kernel<3, true><<<grid, kHpThreads, 0, st>>>(a, b, sa, sb, na, nb, cst, splits, ep, fp);
-    else if (d == 3) hartree_pairs_kernel<3, false><<<grid, kHpThreads, 0, st>>>(a, b, sa, sb, na, nb, cst, splits, ep, fp);
-    else if (fp) hartree_pairs_kernel<1, true><<<grid, kHpThreads, 0, st>>>(a, b, sa, sb, na, nb, cst, splits, ep, fp);
-    else hartree_pairs_kernel<1, false><<<grid, kHpThreads, 0, st>>>(a, b, sa, sb, na, nb, cst, splits, ep, fp);
+    // pass 0 carries the energy (and the forces on x when requested), pass 1 only the forces on xp
+    if (d == 3 && fp && ep) hartree_pairs_kernel<3, true, true><<<grid, kHpThreads, 0, st>>>(a, b, sa, sb, na, nb, cst, splits, ep, fp);
+    else if (d == 3 && fp) hartree_pairs_kernel<3, true, false><<<grid, kHpThreads, 0, st>>>(a, b, sa, sb, na, nb, cst, splits, ep, fp);
+    else if (d == 3) hartree_pairs_kernel<3, false, true><<<grid, kHpThreads, 0, st>>>(a, b, sa, sb, na, nb, cst, splits, ep, fp);
+    else if (fp && ep) hartree_pairs_kernel<1, true, true><<<grid, kHpThreads, 0, st>>>(a, b, sa, sb, na, nb, cst, splits, ep, fp);
+    else if (fp) hartree_pairs_kernel<1, true, false><<<grid, kHpThreads, 0, st>>>(a, b, sa, sb, na, nb, cst, splits, ep, fp);
+    else hartree_pairs_kernel<1, false, true><<<grid, kHpThreads, 0, st>>>(a, b, sa, sb, na, nb, cst, splits, ep, fp);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
     if (pass == 0) {
