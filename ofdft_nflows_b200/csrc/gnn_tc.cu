@@ -582,45 +582,79 @@ __device__ void bwd_tile_tc(SmemTcB& sm, const GnnBwdArgs& a, long long row0, lo
           const float d0 = xst[0] - nc[0], d1 = xst[1] - nc[1], d2 = xst[2] - nc[2];
           r = sqrtf(fmaf(d0, d0, fmaf(d1, d1, d2 * d2)));
           const float* cbi = sm.T.cb + sm.T.cls[i] * kH + 32 * uh;
+          // tanh(x) = 1 - 2 / (2^(2 x log2 e) + 1), two units per FP32 instruction (packed), one MUFU.EX2 + MUFU.RCP each
+          using namespace tc;
+          const f32x2 r2 = splat2(r), tp2 = splat2(tprime), one = splat2(1.0f), m2 = splat2(-2.0f), k2 = splat2(2.8853900817779268f);
 #pragma unroll
-          for (int u = 0; u < 32; ++u)
-            av[u] = tanh_f(fmaf(sm.wr[32 * uh + u], r, fmaf(tprime, sm.wt[32 * uh + u], cbi[u])));
+          for (int u = 0; u < 32; u += 2) {
+            const float2 w2 = *reinterpret_cast<const float2*>(&sm.wr[32 * uh + u]);
+            const float2 t2 = *reinterpret_cast<const float2*>(&sm.wt[32 * uh + u]);
+            const float2 c2 = *reinterpret_cast<const float2*>(&cbi[u]);
+            const f32x2 arg = mul2(fma2(pack2(w2.x, w2.y), r2, fma2(tp2, pack2(t2.x, t2.y), pack2(c2.x, c2.y))), k2);
+            float x0, x1, e0, e1, q0r, q1r;
+            unpack2(arg, x0, x1);
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(x0));
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(x1));
+            const f32x2 den = add2(pack2(e0, e1), one);
+            float d0, d1;
+            unpack2(den, d0, d1);
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(q0r) : "f"(d0));
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(q1r) : "f"(d1));
+            unpack2(fma2(m2, pack2(q0r, q1r), one), av[u], av[u + 1]);
+          }
         }
         // ---- layer-2 tanh-jet: forward partials of f and reverse to the pre-activation cotangents (in place) ----
         float g32[32];
         {
-          float fp[3] = {0.f, 0.f, 0.f};
+          // two hidden units per instruction (packed FP32): same formulas as the scalar epilogue of gnn.cu
+          using namespace tc;
+          const f32x2 one = splat2(1.0f), m1 = splat2(-1.0f), two = splat2(2.0f), four = splat2(4.0f), m3 = splat2(-3.0f), m2 = splat2(-2.0f);
+          const f32x2 fb0p = splat2(fb0), fb1p = splat2(fb1), fb2p = splat2(fb2);
+          f32x2 fpp[3] = {0ull, 0ull, 0ull};
 #pragma unroll
-          for (int u = 0; u < 32; ++u) {
-            const float wv = sm.w3[32 * uh + u];
-            const float aa = q0[u];
-            const float sg = fmaf(-aa, aa, 1.0f);
-            fp[0] = fmaf(wv, aa, fp[0]);
-            float gw = aa * fb0;
-            float pzb = wv * fb0;
+          for (int u = 0; u < 32; u += 2) {
+            const float2 w2 = *reinterpret_cast<const float2*>(&sm.w3[32 * uh + u]);
+            const f32x2 wv = pack2(w2.x, w2.y);
+            const f32x2 aa = pack2(q0[u], q0[u + 1]);
+            const f32x2 naa = mul2(aa, m1);                       // -a
+            const f32x2 sg = fma2(naa, aa, one);                  // 1 - a^2
+            fpp[0] = fma2(wv, aa, fpp[0]);
+            f32x2 gw = mul2(aa, fb0p);
+            f32x2 pzb = mul2(wv, fb0p);
             if (NJ >= 2) {
-              const float p1 = q1[u];
-              const float a1 = sg * p1;
-              fp[1] = fmaf(wv, a1, fp[1]);
-              gw = fmaf(a1, fb1, gw);
-              const float a1b = wv * fb1;
-              pzb = fmaf(-2.0f * aa * p1, a1b, pzb);
-              float t1 = a1b;
+              const f32x2 p1 = pack2(q1[u], q1[u + 1]);
+              const f32x2 a1 = mul2(sg, p1);
+              fpp[1] = fma2(wv, a1, fpp[1]);
+              gw = fma2(a1, fb1p, gw);
+              const f32x2 a1b = mul2(wv, fb1p);
+              const f32x2 nap1 = mul2(naa, p1);                   // -a p1
+              const f32x2 m2ap1 = mul2(nap1, two);                // -2 a p1
+              pzb = fma2(m2ap1, a1b, pzb);
+              f32x2 t1 = a1b;
               if (NJ == 3) {
-                const float p2 = q2[u];
-                const float a2 = fmaf(sg, p2, -2.0f * aa * a1 * p1);
-                fp[2] = fmaf(wv, a2, fp[2]);
-                gw = fmaf(a2, fb2, gw);
-                const float a2b = wv * fb2;
-                q2[u] = a2b * sg;
-                t1 = fmaf(-4.0f * aa * p1, a2b, t1);
-                pzb = fmaf(a2b, fmaf(-2.0f * aa, p2, -2.0f * fmaf(-3.0f * aa, aa, 1.0f) * p1 * p1), pzb);
+                const f32x2 p2 = pack2(q2[u], q2[u + 1]);
+                const f32x2 a2 = fma2(sg, p2, mul2(m2ap1, a1));   // (1 - a^2) p2 - 2 a a1 p1
+                fpp[2] = fma2(wv, a2, fpp[2]);
+                gw = fma2(a2, fb2p, gw);
+                const f32x2 a2b = mul2(wv, fb2p);
+                const f32x2 o2 = mul2(a2b, sg);
+                unpack2(o2, q2[u], q2[u + 1]);
+                t1 = fma2(mul2(nap1, four), a2b, t1);             // a1b - 4 a p1 a2b
+                // -2 a p2 - 2 (1 - 3 a^2) p1^2
+                const f32x2 c3 = fma2(mul2(aa, m3), aa, one);     // 1 - 3 a^2
+                const f32x2 inner = fma2(mul2(naa, two), p2, mul2(mul2(c3, m2), mul2(p1, p1)));
+                pzb = fma2(a2b, inner, pzb);
               }
-              q1[u] = sg * t1;
+              const f32x2 o1 = mul2(sg, t1);
+              unpack2(o1, q1[u], q1[u + 1]);
             }
-            q0[u] = sg * pzb;
-            g32[u] = gw;
+            const f32x2 o0 = mul2(sg, pzb);
+            unpack2(o0, q0[u], q0[u + 1]);
+            unpack2(gw, g32[u], g32[u + 1]);
           }
+          float fp[3];
+#pragma unroll
+          for (int jt = 0; jt < 3; ++jt) { float x0, x1; unpack2(fpp[jt], x0, x1); fp[jt] = x0 + x1; }
 #pragma unroll
           for (int jt = 0; jt < NJ; ++jt) sm.Fpart[par][(uh * 3 + jt) * kTP + m] = fp[jt];
         }
@@ -680,22 +714,39 @@ __device__ void bwd_tile_tc(SmemTcB& sm, const GnnBwdArgs& a, long long row0, lo
 #pragma unroll
           for (int c0 = 0; c0 < 32; c0 += 16) {
 #pragma unroll
-            for (int u = 0; u < 16; ++u) {
-              const int uu = c0 + u;
-              const float wv = sm.wr[32 * uh + uu];
-              const float sg1 = fmaf(-av[uu], av[uu], 1.0f);
-              const float a1j = jt == 0 ? av[uu] : (jt == 1 ? sg1 * wv : -2.0f * av[uu] * sg1 * wv * wv);
-              const float pbj = pj[uu];
-              lv[uu] = tc::lo_tf32(pbj);
+            for (int u2 = 0; u2 < 16; u2 += 2) {
+              // the jet of the first-layer activation and the tf32 remainders, two units per instruction (packed FP32)
+              using namespace tc;
+              const f32x2 a2v = pack2(av[c0 + u2], av[c0 + u2 + 1]);
+              f32x2 a1p = a2v;
+              if (jt > 0) {
+                const float2 w2 = *reinterpret_cast<const float2*>(&sm.wr[32 * uh + c0 + u2]);
+                const f32x2 wv2 = pack2(w2.x, w2.y);
+                const f32x2 sg1 = fma2(mul2(a2v, splat2(-1.0f)), a2v, splat2(1.0f));
+                a1p = jt == 1 ? mul2(sg1, wv2) : mul2(mul2(mul2(a2v, sg1), splat2(-2.0f)), mul2(wv2, wv2));
+              }
+              const f32x2 pbp = pack2(pj[c0 + u2], pj[c0 + u2 + 1]);
+              // remainder x - trunc_tf32(x) = trunc * (-1) + x (exact)
+              const f32x2 a1lo = fma2(a1p & 0xFFFFE000FFFFE000ull, splat2(-1.0f), a1p);
+              const f32x2 pblo = fma2(pbp & 0xFFFFE000FFFFE000ull, splat2(-1.0f), pbp);
+              float a1j_[2], a1l_[2], pbj_[2];
+              unpack2(a1p, a1j_[0], a1j_[1]); unpack2(a1lo, a1l_[0], a1l_[1]); unpack2(pbp, pbj_[0], pbj_[1]);
+              unpack2(pblo, lv[c0 + u2], lv[c0 + u2 + 1]);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int uu = c0 + u2 + h;
+              const float a1j = a1j_[h], pbj = pbj_[h];
+              const float a1lo_s = a1l_[h];
               // operands go in unrounded: the tensor core truncates them to tf32, the remainders are the "lo" parts
 #ifdef OFDFT_ABL_NOSTAGE     // timing ablation only (results invalid)
               if (a1j == 123.456f) sm.A1T[uu] = pbj;
 #else
               sm.A1T[cbase * kA1TChunk + (32 * uh + uu) * 4 + csub] = a1j;
-              sm.A1T[cbase * kA1TChunk + (kH + 32 * uh + uu) * 4 + csub] = tc::lo_tf32(a1j);
+              sm.A1T[cbase * kA1TChunk + (kH + 32 * uh + uu) * 4 + csub] = a1lo_s;
               sm.P2T[cbase * kP2TChunk + (32 * uh + uu) * 4 + csub] = pbj;
               sm.P2T[cbase * kP2TChunk + (kH + 32 * uh + uu) * 4 + csub] = lv[uu];
 #endif
+            }
             }
           }
           // the remainder buffer is free once the previous jet's B1lo pass (issued behind its dW2 batch) has completed
@@ -721,6 +772,7 @@ __device__ void bwd_tile_tc(SmemTcB& sm, const GnnBwdArgs& a, long long row0, lo
         // ---- layer-1 reverse from D_b1 (cotangent jets of a1 for trajectory m, units k = 32 uh ..) ----
         {
           float rp = 0.f;
+          tc::f32x2 rp2 = 0ull;
           float ps32[32], pr32[32];
 #pragma unroll
           for (int c0 = 0; c0 < 32; c0 += 16) {
@@ -729,26 +781,40 @@ __device__ void bwd_tile_tc(SmemTcB& sm, const GnnBwdArgs& a, long long row0, lo
             if (NJ >= 2) tc::tmem_ld16(tlane + kColB1 + 1 * kH + 32 * uh + c0, b1);
             if (NJ == 3) tc::tmem_ld16(tlane + kColB1 + 2 * kH + 32 * uh + c0, b2v);
             tc::tmem_ld_wait();
+            // two units per instruction (packed FP32)
+            using namespace tc;
+            const f32x2 one = splat2(1.0f), m2 = splat2(-2.0f), m3 = splat2(-3.0f), m4 = splat2(-4.0f), rr2 = splat2(r);
 #pragma unroll
-            for (int u = 0; u < 16; ++u) {
-              const float aa = av[c0 + u];
-              const float wv = sm.wr[32 * uh + c0 + u];
-              const float sg = fmaf(-aa, aa, 1.0f);
-              float t = b0[u];
-              float e = 0.f;
+            for (int u = 0; u < 16; u += 2) {
+              const f32x2 aa = pack2(av[c0 + u], av[c0 + u + 1]);
+              const float2 w2 = *reinterpret_cast<const float2*>(&sm.wr[32 * uh + c0 + u]);
+              const f32x2 wv = pack2(w2.x, w2.y);
+              const f32x2 aw = mul2(aa, wv);                                  // a w
+              const f32x2 sg = fma2(mul2(aa, splat2(-1.0f)), aa, one);        // 1 - a^2
+              f32x2 t = pack2(b0[u], b0[u + 1]);
+              f32x2 e = 0ull;
               if (NJ >= 2) {
-                t = fmaf(-2.0f * aa * wv, b1[u], t);
-                e = b1[u];
+                const f32x2 c1 = pack2(b1[u], b1[u + 1]);
+                t = fma2(mul2(aw, m2), c1, t);                                // - 2 a w b1
+                e = c1;
                 if (NJ == 3) {
-                  t = fmaf(-2.0f * wv * wv * fmaf(-3.0f * aa, aa, 1.0f), b2v[u], t);
-                  e = fmaf(-4.0f * aa * wv, b2v[u], e);
+                  const f32x2 c2 = pack2(b2v[u], b2v[u + 1]);
+                  const f32x2 c3 = fma2(mul2(aa, m3), aa, one);               // 1 - 3 a^2
+                  t = fma2(mul2(mul2(mul2(wv, wv), m2), c3), c2, t);          // - 2 w^2 (1 - 3 a^2) b2
+                  e = fma2(mul2(aw, m4), c2, e);                              // b1 - 4 a w b2
                 }
               }
-              const float pb = sg * t;
-              rp = fmaf(pb, wv, rp);
-              ps32[c0 + u] = pb;
-              pr32[c0 + u] = fmaf(pb, r, sg * e);
+              const f32x2 pb = mul2(sg, t);
+              rp2 = fma2(pb, wv, rp2);
+              unpack2(pb, ps32[c0 + u], ps32[c0 + u + 1]);
+              const f32x2 prv = fma2(pb, rr2, mul2(sg, e));
+              unpack2(prv, pr32[c0 + u], pr32[c0 + u + 1]);
             }
+          }
+          {
+            float r0, r1;
+            tc::unpack2(rp2, r0, r1);
+            rp = r0 + r1;
           }
           sm.Rpart[par][uh * kTP + m] = rp;
           // fold the dW2 tile into the fp32 accumulators (row m, columns 32 uh ..)

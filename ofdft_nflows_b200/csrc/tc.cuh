@@ -142,5 +142,18 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
 // value can serve as its own "hi" part; this returns the matching remainder x - trunc_tf32(x) (exact in fp32).
 __device__ __forceinline__ float lo_tf32(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
+// ---- packed FP32 pairs: Blackwell executes FFMA2 / FADD2 / FMUL2 on two independent fp32 lanes of a 64-bit register pair,
+// i.e. two IEEE fp32 operations per issue slot.  The elementwise phases of the kernels (one thread = 32 hidden units of one
+// trajectory) are issue-bound, so they process the units two at a time.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ f32x2 splat2(float a) { return pack2(a, a); }
+__device__ __forceinline__ void unpack2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ float lo2(f32x2 v) { float a, b; unpack2(v, a, b); return a; }
+__device__ __forceinline__ float hi2(f32x2 v) { float a, b; unpack2(v, a, b); return b; }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+
 }  // namespace tc
 }  // namespace ofdft
