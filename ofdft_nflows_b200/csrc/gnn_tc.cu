@@ -37,6 +37,19 @@ struct SmemTc1 {
   unsigned int tmem_slot;
   int tile;
 };
+// tanh of two values: 1 - 2 / (2^(2 x log2 e) + 1) with the FP32 steps packed (one MUFU.EX2 + MUFU.RCP per value)
+__device__ __forceinline__ tc::f32x2 tanh2(tc::f32x2 x) {
+  using namespace tc;
+  float x0, x1, e0, e1, d0, d1, r0, r1;
+  unpack2(mul2(x, splat2(2.8853900817779268f)), x0, x1);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(x0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(x1));
+  unpack2(add2(pack2(e0, e1), splat2(1.0f)), d0, d1);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(d0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(d1));
+  return fma2(splat2(-2.0f), pack2(r0, r1), splat2(1.0f));
+}
+
 template <int NJ, int NU>
 __device__ void fwd_tile_tc(SmemTc1& sm, const GnnFwdArgs& a, long long row0, long long seg_end, float b3,
                             bool seg_b, long long seg_row0, uint32_t tmem, uint32_t (&phase)[3]) {
@@ -123,9 +136,16 @@ __device__ void fwd_tile_tc(SmemTc1& sm, const GnnFwdArgs& a, long long row0, lo
           const float d0 = sm.xs[m] - nc[0], d1 = sm.xs[kTP + m] - nc[1], d2 = sm.xs[2 * kTP + m] - nc[2];
           const float r = sqrtf(fmaf(d0, d0, fmaf(d1, d1, d2 * d2)));
           const float* cbi = sm.T.cb + sm.T.cls[i] * kH + UPT * uh;
+          // two units per FP32 instruction (packed)
+          const tc::f32x2 r2 = tc::splat2(r), tp2 = tc::splat2(tprime);
 #pragma unroll
-          for (int u = 0; u < UPT; ++u)
-            av[u] = tanh_f(fmaf(sm.wr[UPT * uh + u], r, fmaf(tprime, sm.wt[UPT * uh + u], cbi[u])));
+          for (int u = 0; u < UPT; u += 2) {
+            const float2 w2 = *reinterpret_cast<const float2*>(&sm.wr[UPT * uh + u]);
+            const float2 t2 = *reinterpret_cast<const float2*>(&sm.wt[UPT * uh + u]);
+            const float2 c2 = *reinterpret_cast<const float2*>(&cbi[u]);
+            tc::unpack2(tanh2(tc::fma2(tc::pack2(w2.x, w2.y), r2, tc::fma2(tp2, tc::pack2(t2.x, t2.y), tc::pack2(c2.x, c2.y)))),
+                        av[u], av[u + 1]);
+          }
         }
         {
           // one jet at a time on one mbarrier.  The MMAs read 6 KB of operands per 32 clocks from shared memory when both
@@ -136,10 +156,17 @@ __device__ void fwd_tile_tc(SmemTc1& sm, const GnnFwdArgs& a, long long row0, lo
             if (jt > 0) { tc::mbar_wait(&sm.bar[0], phase[0]); phase[0] ^= 1; __syncwarp(); }
             float aj[UPT];
 #pragma unroll
-            for (int u = 0; u < UPT; ++u) {
-              const float wv = sm.wr[UPT * uh + u];
-              const float a1 = fmaf(-av[u], av[u], 1.0f) * wv;
-              aj[u] = jt == 0 ? av[u] : (jt == 1 ? a1 : -2.0f * av[u] * a1 * wv);
+            for (int u = 0; u < UPT; u += 2) {
+              using namespace tc;
+              const f32x2 a2v = pack2(av[u], av[u + 1]);
+              f32x2 ajp = a2v;
+              if (jt > 0) {
+                const float2 w2 = *reinterpret_cast<const float2*>(&sm.wr[UPT * uh + u]);
+                const f32x2 wv = pack2(w2.x, w2.y);
+                const f32x2 a1 = mul2(fma2(mul2(a2v, splat2(-1.0f)), a2v, splat2(1.0f)), wv);      // (1 - a^2) w
+                ajp = jt == 1 ? a1 : mul2(mul2(mul2(a2v, splat2(-2.0f)), a1), wv);               // -2 a a' w
+              }
+              unpack2(ajp, aj[u], aj[u + 1]);
             }
 #pragma unroll
             for (int c0 = 0; c0 < UPT; c0 += 16) {
@@ -151,8 +178,11 @@ __device__ void fwd_tile_tc(SmemTc1& sm, const GnnFwdArgs& a, long long row0, lo
 #pragma unroll
             for (int c = 0; c < UPT / 4; ++c) {
               const int off = (((UPT / 4) * uh + c) * kTP + m) * 4;
-              *reinterpret_cast<float4*>(sm.Alo + off) =
-                  make_float4(tc::lo_tf32(aj[4 * c]), tc::lo_tf32(aj[4 * c + 1]), tc::lo_tf32(aj[4 * c + 2]), tc::lo_tf32(aj[4 * c + 3]));
+              // tf32 remainders x - trunc_tf32(x) = trunc * (-1) + x (exact), two per instruction
+              const tc::f32x2 p01 = tc::pack2(aj[4 * c], aj[4 * c + 1]), p23 = tc::pack2(aj[4 * c + 2], aj[4 * c + 3]);
+              const tc::f32x2 l01 = tc::fma2(p01 & 0xFFFFE000FFFFE000ull, tc::splat2(-1.0f), p01);
+              const tc::f32x2 l23 = tc::fma2(p23 & 0xFFFFE000FFFFE000ull, tc::splat2(-1.0f), p23);
+              *reinterpret_cast<float4*>(sm.Alo + off) = make_float4(tc::lo2(l01), tc::hi2(l01), tc::lo2(l23), tc::hi2(l23));
             }
             tc::tmem_st_wait();
             tc::fence_async_smem();
@@ -178,7 +208,7 @@ __device__ void fwd_tile_tc(SmemTc1& sm, const GnnFwdArgs& a, long long row0, lo
         }
         __syncwarp();                                   // tcgen05.ld is .sync.aligned: reconverge after the spin loops
         tc::fence_after_sync();
-        float fp[3] = {0.f, 0.f, 0.f};
+        tc::f32x2 fpp[3] = {0ull, 0ull, 0ull};
         float* actp = nullptr;
         if (a.act != nullptr)
           actp = a.act + AL.seg_base((long long)(step * 4 + stage) * a.Na + i, seg_b)
@@ -192,17 +222,26 @@ __device__ void fwd_tile_tc(SmemTc1& sm, const GnnFwdArgs& a, long long row0, lo
           if (NJ == 3) tc::tmem_ld16(tlane + 2 * kH + UPT * uh + c0, p2);
           tc::tmem_ld_wait();
 #pragma unroll
-          for (int u = 0; u < 16; ++u) {
+          for (int u = 0; u < 16; u += 2) {
+            // layer-2 tanh jet and the last-layer dot, two units per FP32 instruction (packed)
+            using namespace tc;
             const int j = UPT * uh + c0 + u;
-            const float wv = sm.w3[j];
-            const float aa = tanh_f(p0[u] + sm.b2[j]);
-            p0[u] = aa;
-            fp[0] = fmaf(wv, aa, fp[0]);
+            const float2 w2 = *reinterpret_cast<const float2*>(&sm.w3[j]);
+            const float2 b2v = *reinterpret_cast<const float2*>(&sm.b2[j]);
+            const f32x2 wv = pack2(w2.x, w2.y);
+            const f32x2 aa = tanh2(add2(pack2(p0[u], p0[u + 1]), pack2(b2v.x, b2v.y)));
+            unpack2(aa, p0[u], p0[u + 1]);
+            fpp[0] = fma2(wv, aa, fpp[0]);
             if (NJ >= 2) {
-              const float sg = fmaf(-aa, aa, 1.0f);
-              const float a1 = sg * p1[u];
-              fp[1] = fmaf(wv, a1, fp[1]);
-              if (NJ == 3) fp[2] = fmaf(wv, fmaf(sg, p2[u], -2.0f * aa * a1 * p1[u]), fp[2]);
+              const f32x2 naa = mul2(aa, splat2(-1.0f));
+              const f32x2 sg = fma2(naa, aa, splat2(1.0f));
+              const f32x2 q1 = pack2(p1[u], p1[u + 1]);
+              const f32x2 a1 = mul2(sg, q1);
+              fpp[1] = fma2(wv, a1, fpp[1]);
+              if (NJ == 3) {
+                const f32x2 a2 = fma2(sg, pack2(p2[u], p2[u + 1]), mul2(mul2(mul2(naa, splat2(2.0f)), a1), q1));   // sg p2 - 2 a a1 p1
+                fpp[2] = fma2(wv, a2, fpp[2]);
+              }
             }
           }
 #ifdef OFDFT_ABL_NOACTSTORE    // timing ablation only (the backward then reads garbage)
@@ -221,7 +260,7 @@ __device__ void fwd_tile_tc(SmemTc1& sm, const GnnFwdArgs& a, long long row0, lo
           }
         }
 #pragma unroll
-        for (int jt = 0; jt < NJ; ++jt) sm.Fpart[(uh * 3 + jt) * kTP + m] = fp[jt];
+        for (int jt = 0; jt < NJ; ++jt) sm.Fpart[(uh * 3 + jt) * kTP + m] = tc::lo2(fpp[jt]) + tc::hi2(fpp[jt]);
         tc::fence_before_sync();
         __syncthreads();
       }
