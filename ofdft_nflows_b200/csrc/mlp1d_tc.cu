@@ -182,32 +182,43 @@ __global__ void __launch_bounds__(kGemmThreads, 1) mlp_layer_gemm_tc_kernel(cons
 #pragma unroll
         for (int q = 0; q < kCH; ++q) R.a[jt][q] = sm.A[it % kGemmRaw][jt][kCH * c + q][r];
     };
+    // operand jets and their tf32 remainders, two values per FP32 instruction (packed FFMA2 / FMUL2)
+    auto lo4 = [&](tc::f32x2 xy, tc::f32x2 zw, uint32_t col) {
+      using namespace tc;
+      const f32x2 m1 = splat2(-1.0f);
+      const f32x2 l0 = fma2(xy & 0xFFFFE000FFFFE000ull, m1, xy), l1 = fma2(zw & 0xFFFFE000FFFFE000ull, m1, zw);   // x - trunc_tf32(x)
+      tmem_st4(col, lo2(xy), hi2(xy), lo2(zw), hi2(zw));
+      tmem_st4(col + 16, lo2(l0), hi2(l0), lo2(l1), hi2(l1));
+    };
     auto store_tmem = [&](const Regs& R, int s) {
+      using namespace tc;
 #pragma unroll
       for (int q = 0; q < kCH; ++q) {
         const uint32_t base = tl + kColOp + 96 * s + 4 * (kCH * c + q);
         const float4 a = R.a[0][q];
-        tc::tmem_st4(base, a.x, a.y, a.z, a.w);
-        tc::tmem_st4(base + 16, tc::lo_tf32(a.x), tc::lo_tf32(a.y), tc::lo_tf32(a.z), tc::lo_tf32(a.w));
+        const f32x2 a01 = pack2(a.x, a.y), a23 = pack2(a.z, a.w);
+        lo4(a01, a23, base);
         if (MODE != 0) {
 #pragma unroll
           for (int jt = 1; jt < NJ; ++jt) {
             const float4 v = R.a[jt][q];
-            tc::tmem_st4(base + 32 * jt, v.x, v.y, v.z, v.w);
-            tc::tmem_st4(base + 32 * jt + 16, tc::lo_tf32(v.x), tc::lo_tf32(v.y), tc::lo_tf32(v.z), tc::lo_tf32(v.w));
+            lo4(pack2(v.x, v.y), pack2(v.z, v.w), base + 32 * jt);
           }
         } else if (NJ >= 2) {
           const float4 p1 = R.a[1][q];
-          const float4 sg = make_float4(fmaf(-a.x, a.x, 1.0f), fmaf(-a.y, a.y, 1.0f), fmaf(-a.z, a.z, 1.0f), fmaf(-a.w, a.w, 1.0f));
-          const float4 a1 = make_float4(sg.x * p1.x, sg.y * p1.y, sg.z * p1.z, sg.w * p1.w);
-          tc::tmem_st4(base + 32, a1.x, a1.y, a1.z, a1.w);
-          tc::tmem_st4(base + 48, tc::lo_tf32(a1.x), tc::lo_tf32(a1.y), tc::lo_tf32(a1.z), tc::lo_tf32(a1.w));
+          const f32x2 p01 = pack2(p1.x, p1.y), p23 = pack2(p1.z, p1.w);
+          const f32x2 one = splat2(1.0f), m1 = splat2(-1.0f);
+          const f32x2 n01 = mul2(a01, m1), n23 = mul2(a23, m1);
+          const f32x2 sg01 = fma2(n01, a01, one), sg23 = fma2(n23, a23, one);           // 1 - a^2
+          const f32x2 b01 = mul2(sg01, p01), b23 = mul2(sg23, p23);                     // a' = (1 - a^2) p'
+          lo4(b01, b23, base + 32);
           if (NJ == 3) {
             const float4 p2 = R.a[2][q];
-            const float4 a2 = make_float4(fmaf(sg.x, p2.x, -2.0f * a.x * a1.x * p1.x), fmaf(sg.y, p2.y, -2.0f * a.y * a1.y * p1.y),
-                                          fmaf(sg.z, p2.z, -2.0f * a.z * a1.z * p1.z), fmaf(sg.w, p2.w, -2.0f * a.w * a1.w * p1.w));
-            tc::tmem_st4(base + 64, a2.x, a2.y, a2.z, a2.w);
-            tc::tmem_st4(base + 80, tc::lo_tf32(a2.x), tc::lo_tf32(a2.y), tc::lo_tf32(a2.z), tc::lo_tf32(a2.w));
+            const f32x2 two = splat2(2.0f);
+            // a'' = (1 - a^2) p'' - 2 a a' p'
+            const f32x2 c01 = fma2(sg01, pack2(p2.x, p2.y), mul2(mul2(mul2(n01, two), b01), p01));
+            const f32x2 c23 = fma2(sg23, pack2(p2.z, p2.w), mul2(mul2(mul2(n23, two), b23), p23));
+            lo4(c01, c23, base + 64);
           }
         }
       }
