@@ -588,12 +588,16 @@ def main():
     # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture (same workload only)
     try:
         if args.workload == "h2o" and bs == 65536 and args.n_steps == 16 and not args.recompute and not args.full_jets:
-            prof = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_full_gnn_kernels.json")))
+            prof = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_full_gnn.json" if tensor_path else "r01_ncu_full_gnn_ffma_kernels.json")))
             for k in prof:
                 if ("gnn_bwd_tc_kernel" if tensor_path else "gnn_bwd_kernel") in k["kernel"]:
                     gb = lambda v: float(v.split()[0]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[v.split()[1]]
                     roofline["traffic"] = gb(k["dram__bytes_read.sum"]) + gb(k["dram__bytes_write.sum"])
-                    roofline["traffic_source"] = "profiles/r01_ncu_full_gnn_kernels.json (bytes per launch; 12.9 GB of it is the HBM activation checkpoint)"
+                    roofline["traffic_source"] = ("profiles/r02_ncu_full_gnn.json: dram__bytes_read + dram__bytes_write of one `ncu --set full` capture "
+                                                  "of this command (bytes per launch; 12.9 GB of it is the layer-2 activation checkpoint); "
+                                                  "algorithmic bytes without the checkpoint: state rows, stage checkpoint, tile partials")
+                    roofline["algorithmic_bytes_without_activation_checkpoint"] = float(
+                        B * 28 * 2 + 4 * args.n_steps * 6 * 4 * B + (2 * math.ceil(bs / 128)) * theta.numel() * 4)
     except Exception:
         pass
 
