@@ -579,6 +579,33 @@ __device__ void bwd_tile_tc(SmemTcB& sm, const GnnBwdArgs& a, long long row0, lo
         ysx[0] = ysx[1] = ysx[2] = 0.f; yss[0] = yss[1] = yss[2] = 0.f;
         pre(0);
       }
+      // x-only tiles (NJ == 1) have registers to spare: the four per-unit sums over the warp's trajectories are accumulated
+      // over the nuclei of the stage and reduced by ONE butterfly each per stage (per run of equal nucleus class for the
+      // first-layer pre-activation sum) instead of one per nucleus -- the butterflies are a third of such a tile's instructions
+#ifndef OFDFT_STAGE_ACC
+#define OFDFT_STAGE_ACC 1
+#endif
+      constexpr bool kStageAccR = NJ == 1 && (OFDFT_STAGE_ACC & 1);     // b2 / w3 sums (reverse epilogue)
+      constexpr bool kStageAcc = NJ == 1 && (OFDFT_STAGE_ACC & 2);      // first-layer sums
+      float b2acc[kStageAccR ? 32 : 1], w3acc[kStageAccR ? 32 : 1], pracc[kStageAcc ? 32 : 1], psacc[kStageAcc ? 32 : 1];
+      int ps_cls = -1;
+      if constexpr (kStageAccR) {
+#pragma unroll
+        for (int u = 0; u < 32; ++u) { b2acc[u] = 0.f; w3acc[u] = 0.f; }
+      }
+      if constexpr (kStageAcc) {
+#pragma unroll
+        for (int u = 0; u < 32; ++u) { pracc[u] = 0.f; psacc[u] = 0.f; }
+      }
+      auto flush_ps = [&]() {
+        if constexpr (kStageAcc) { if (ps_cls >= 0) {
+          const float ps = warp_vec32_sum(psacc, lane);
+          sm.S[(w * kMaxClasses + ps_cls) * 32 + lane] += ps;
+          G.g_wt = fmaf(tprime, ps, G.g_wt);
+#pragma unroll
+          for (int u = 0; u < 32; ++u) psacc[u] = 0.f;
+        } }
+      };
 #pragma unroll 1
       for (int i = 0; i < a.Na; ++i) {
         // ---- layer-2 jets (a2, p2', p2'') of (trajectory m, units 32 uh ..) from the HBM checkpoint ----
@@ -723,7 +750,12 @@ __device__ void bwd_tile_tc(SmemTcB& sm, const GnnBwdArgs& a, long long row0, lo
         tc::tmem_st_wait();
         tc::fence_before_sync();
         bar_arrive(kBarStaged0, kThreads + 32);          // -> MMA warp: B1hi(0 .. NJ-1)
-        G.g_w3 += warp_vec32_sum(g32, lane);
+        if constexpr (kStageAccR) {
+#pragma unroll
+          for (int u = 0; u < 32; ++u) { w3acc[u] += g32[u]; b2acc[u] += q0[u]; }
+        } else {
+          G.g_w3 += warp_vec32_sum(g32, lane);
+        }
 #pragma unroll
         for (int jt = 0; jt < NJ; ++jt) {
           // the bias gradient sum_traj Pbar2[0] needs q0, which is dead once jet 0 has been staged: its butterfly runs in the
@@ -802,7 +834,7 @@ __device__ void bwd_tile_tc(SmemTcB& sm, const GnnBwdArgs& a, long long row0, lo
           tc::fence_before_sync();
           bar_arrive(kBarStagedJet + jt, kThreads + 32);   // -> MMA warp: B1lo(jt), dW2(jt)
         }
-        if (NJ == 1) G.g_b2 += warp_vec32_sum(q0, lane);
+        if (NJ == 1 && !kStageAccR) G.g_b2 += warp_vec32_sum(q0, lane);
         dw_pending = true;
         // the earlier B1 batches were retired before their remainder buffer was reused: wait for the last one
         tc::mbar_wait(&sm.barB[NJ - 1], (phase >> (NJ - 1)) & 1u); phase ^= 1u << (NJ - 1);
@@ -873,11 +905,18 @@ __device__ void bwd_tile_tc(SmemTcB& sm, const GnnBwdArgs& a, long long row0, lo
             for (int u = 0; u < 16; ++u) sm.DW[(32 * uh + c0 + u) * kTP + m] += t[u] + t2[u];
           }
           }
-          const float ps = warp_vec32_sum(ps32, lane);
-          const float pr = warp_vec32_sum(pr32, lane);
-          sm.S[(w * kMaxClasses + sm.T.cls[i]) * 32 + lane] += ps;
-          G.g_wt = fmaf(tprime, ps, G.g_wt);
-          G.g_wr += pr;
+          if constexpr (kStageAcc) {
+            const int cls = sm.T.cls[i];
+            if (cls != ps_cls) { flush_ps(); ps_cls = cls; }
+#pragma unroll
+            for (int u = 0; u < 32; ++u) { psacc[u] += ps32[u]; pracc[u] += pr32[u]; }
+          } else {
+            const float ps = warp_vec32_sum(ps32, lane);
+            const float pr = warp_vec32_sum(pr32, lane);
+            sm.S[(w * kMaxClasses + sm.T.cls[i]) * 32 + lane] += ps;
+            G.g_wt = fmaf(tprime, ps, G.g_wt);
+            G.g_wr += pr;
+          }
         }
         tc::fence_before_sync();
         // the partner warp (same trajectories, other unit half) has published its Fpart / Rpart of this nucleus
@@ -885,6 +924,14 @@ __device__ void bwd_tile_tc(SmemTcB& sm, const GnnBwdArgs& a, long long row0, lo
         post(i);
         par ^= 1;
         if (i + 1 < a.Na) pre(i + 1);
+      }
+      if constexpr (kStageAccR) {
+        G.g_b2 += warp_vec32_sum(b2acc, lane);
+        G.g_w3 += warp_vec32_sum(w3acc, lane);
+      }
+      if constexpr (kStageAcc) {
+        flush_ps();
+        G.g_wr += warp_vec32_sum(pracc, lane);
       }
 #pragma unroll
       for (int c = 0; c < 3; ++c) {

@@ -202,7 +202,7 @@ class EnergyEstimator:
                                  norm_pairs=norm)
             w1.wait(); w2.wait()
             if timers is not None:
-                timers.append(("all_gather_wait", e0, mark()))
+                timers.append(("local_block_and_gather_wait", e0, mark()))
             for lo, hi in ((0, rank), (rank + 1, ws)):
                 if hi > lo:
                     # (local x) x (remote xp): energy + forces on the local x rows; (local xp) x (remote x): forces on xp
