@@ -408,6 +408,18 @@ def test_drop_in_neural_ode_score_autograd():
     # f.apply(params, t, states) == d/dt [x, logp]
     dy = model.apply(params, 0.25, dev(batch[:, :4])).cpu().numpy()
     assert np.abs(dy - fld.rhs(0.25, batch[:, :4], False)).max() < 2e-6 * max(1.0, np.abs(dy).max())
+    # gradient through neural_ode (rows [x, logp]: the two-jet instantiation of the adjoint kernels, LiH.py / rho_rev paths)
+    for path in (ops.PATH_DEFAULT, ops.PATH_FFMA):
+        th = dev(theta).requires_grad_(True)
+        y1, ck = ops.gnn_fwd(th.detach(), model.xyz_nuclei, model.z_one_hot, dev(batch[:, :4]), 200, 2, 2, 4, 0.0, 1.0, -1.0,
+                             want_ckpt=True, want_act=True, path=path)
+        ybar = np.concatenate([wx, wl], 1)
+        g, yb0 = ops.gnn_bwd(th.detach(), model.xyz_nuclei, model.z_one_hot, ck, dev(ybar), 200, 2, 2, 4, 0.0, 1.0, -1.0,
+                             want_ybar0=True, path=path)
+        _, st2 = O.odeint_rk4(lambda y, t: fld.rhs(t, y, False), batch[:, :4], 0.0, 1.0, 4, keep=True)
+        yb0_ref, t2 = O.rk4_adjoint(fld, st2, 0.0, 1.0, ybar, False)
+        assert rel(g.cpu().numpy(), t2) < G_TOL, (path, rel(g.cpu().numpy(), t2))
+        assert rel(yb0.cpu().numpy()[:, :4], yb0_ref[:, :4]) < G_TOL
 
 
 def test_device_prior_batch_generator_and_rho_rev():
