@@ -279,8 +279,8 @@ def strong_scaling_block(dev, rank: int, world: int, n_steps: int, global_bs: in
                         f"RK4 x{n_steps}, paired Hartree", "scaling": "strong", "n_gpus": world, "per_gpu_bs": bs,
             "ms_per_step": 1e3 * t_n, "trajectories_per_s": 2.0 * global_bs / t_n,
             "one_gpu_same_global_batch": {"ms_per_step": 1e3 * t_1, "trajectories_per_s": 2.0 * global_bs / t_1,
-                                          "note": "rank 0 alone; above the 64 GB activation-checkpoint cap the estimator "
-                                                  "re-integrates row chunks (one extra forward pass)"},
+                                          "note": "rank 0 alone; above the 64 GB activation-checkpoint cap the estimator runs "
+                                                  "the step over row chunks (forward -> functionals -> adjoint per chunk)"},
             "speedup_vs_one_gpu": t_1 / t_n, "collectives_per_step": "2 all-reduces (8 doubles, n_theta floats); no data-path exchange"}
 
 

@@ -105,6 +105,11 @@ class EnergyEstimator:
             # re-integrate and reverse the rows in chunks whose checkpoint fits -- one extra forward pass keeps the
             # backward on the tensor-core kernel, which is ~3x faster than the FP32 recompute kernel
             chunked = self.act_ckpt and not want_act and B > 0 and len(getattr(m, "features", (64, 64))) == 2
+            if chunked and self.hartree_mode == "paired":
+                # every term of the paired estimator is a mean over rows (i, i + bs): row chunks go through forward ->
+                # functionals -> adjoint independently, each with a checkpoint that fits -- no extra forward pass
+                sums, tbar, y1 = self._gnn_step_row_chunks(theta, batch, bs, Na, timers)
+                return self._reduce(sums, tbar, y1)
             y1, ckpt = ops.gnn_fwd(theta, m.xyz_nuclei, m.z_one_hot, batch, bs, ops.JETS_FULL, self.jets_b, self.n_steps,
                                    self.t0, self.t1, m.y0, want_ckpt=not chunked, want_act=want_act, path=self.path)
             e1 = mark()
@@ -133,6 +138,9 @@ class EnergyEstimator:
             e3 = mark()
             if timers is not None:
                 timers += [("mlp_fwd", e0, e1), ("functionals", e1, e2), ("mlp_bwd", e2, e3)]
+        return self._reduce(sums, tbar, y1)
+
+    def _reduce(self, sums, tbar, y1):
         if self._dist():
             import torch.distributed as dist
             ws = dist.get_world_size(self.group)
@@ -141,6 +149,40 @@ class EnergyEstimator:
             dist.all_reduce(tbar, group=self.group)
             sums /= ws
             tbar /= ws
+        return sums, tbar, y1
+
+    def _gnn_step_row_chunks(self, theta, batch, bs: int, Na: int, timers: Optional[list] = None):
+        """The whole step over row chunks [lo, hi) of BOTH halves (a trajectory and its Hartree partner stay together): the
+        per-term means and the parameter gradient are sums of the chunks' contributions weighted by their share of the rows."""
+        m = self.model
+        per_pair = max(1, ops.gnn_act_ckpt_bytes(256, 128, ops.JETS_FULL, self.jets_b, Na, self.n_steps) // 128)
+        rows = max(128, (self.act_ckpt_max_bytes // per_pair) // 128 * 128)
+        sums = torch.zeros(8, dtype=torch.float64, device=batch.device)
+        tbar = torch.zeros_like(theta)
+        y1 = torch.empty_like(batch)
+        for lo in range(0, bs, rows):
+            hi = min(bs, lo + rows)
+            n = hi - lo
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if timers is not None else None
+            if ev: ev[0].record()
+            sub = torch.cat([batch[lo:hi], batch[bs + lo:bs + hi]], 0)
+            y1c, ck = ops.gnn_fwd(theta, m.xyz_nuclei, m.z_one_hot, sub, n, ops.JETS_FULL, self.jets_b, self.n_steps,
+                                  self.t0, self.t1, m.y0, want_ckpt=True, want_act=True, path=self.path)
+            if ev: ev[1].record()
+            sc, ybar = ops.functionals_fwd_bwd(self.spec, y1c)
+            w = n / bs
+            sums += sc * w
+            ybar *= w
+            if ev: ev[2].record()
+            g, _ = ops.gnn_bwd(theta, m.xyz_nuclei, m.z_one_hot, ck, ybar, n, ops.JETS_FULL, self.jets_b, self.n_steps,
+                               self.t0, self.t1, m.y0, path=self.path)
+            tbar += g
+            if ev:
+                ev[3].record()
+                timers += [("gnn_fwd", ev[0], ev[1]), ("functionals", ev[1], ev[2]), ("gnn_bwd", ev[2], ev[3])]
+            y1[lo:hi] = y1c[:n]
+            y1[bs + lo:bs + hi] = y1c[n:]
+            del ck, y1c, ybar, sub
         return sums, tbar, y1
 
     def _gnn_bwd_chunked(self, theta: torch.Tensor, batch: torch.Tensor, ybar1: torch.Tensor, bs: int, Na: int) -> torch.Tensor:
