@@ -345,13 +345,14 @@ __global__ void __launch_bounds__(kTP * NU, 2) gnn_fwd_tc_kernel(const GnnFwdArg
 // tensor-core backward (discrete adjoint) -- requires the layer-2 activation checkpoint
 // =================================================================================================================
 // Per (tile, nucleus, RHS evaluation) and jet:
-//   B1 :  Abar1[jet] (128 traj x 64 k)  = Pbar2[jet] (TMEM A operand, tcgen05.st) . W2^T      3xTF32, 24 MMAs
-//   dW2:  D_dw[(hi|lo) k][j] += A1[jet]^T Pbar2[jet]  with K = trajectory: both operands staged "transposed"
-//         ([chunk of 4 traj][row][4], chunk stride padded by 16 B so the scalar stores are conflict free),
-//         A rows stacked [hi k | lo k] so two MMAs give all four hi/lo cross terms                     32 MMAs
-// The tensor core accumulates with truncation: a D_dw chain spanning the whole tile (~4600 MMAs) biases the gradient by
-// ~1e-4.  D_dw is therefore restarted every (nucleus, RHS evaluation) -- 96 MMAs -- and folded into round-to-nearest fp32
-// accumulators in shared memory (measured: dW2 error 2.8e-4 -> see DESIGN.md).
+//   B1 :  Abar1[jet] (128 traj x 64 k)  = Pbar2[jet] . W2^T as 3xTF32, A operand in tensor memory (the parked jet itself for
+//         the two "hi" passes, its tf32 remainder for the third)                                          24 MMAs (N = 64)
+//   dW2:  D_dw[(hi|lo) k][(hi|lo) j] += A1[jet]^T Pbar2[jet]  with K = trajectory: both operands staged "transposed"
+//         ([chunk of 4 traj][row][4], chunk stride padded by 16 B so the scalar stores are conflict free), A rows stacked
+//         [hi k | lo k], B rows stacked [hi j | lo j]: one M128.N128.K8 MMA per K step gives all four cross terms   16 MMAs
+// The tensor core accumulates with truncation: a D_dw chain spanning the whole tile (~2300 MMAs) biases the gradient by
+// ~1e-4.  D_dw is therefore restarted every RK4 stage (Na x 48 MMAs) and folded into round-to-nearest fp32 accumulators in
+// shared memory (see DESIGN.md for the measured errors).
 constexpr int kA1TChunk = kTP * 4 + 4;      // floats per trajectory-chunk of the stacked A1^T operand (128 rows)
 constexpr int kP2TChunk = 2 * kH * 4 + 4;   // floats per trajectory-chunk of the stacked [hi j | lo j] Pbar2^T operand (128 rows)
 // tensor-memory map (512 columns): B1 accumulators of the three jets | dW2 accumulator | Pbar2 of the three jets (the
@@ -724,10 +725,8 @@ __device__ void bwd_tile_tc(SmemTcB& sm, const GnnBwdArgs& a, long long row0, lo
 #pragma unroll
           for (int jt = 0; jt < NJ; ++jt) sm.Fpart[par][(uh * 3 + jt) * kTP + m] = fp[jt];
         }
-        // ---- per jet: B1 (TS mode: Pbar2 hi|lo in tensor memory) and the dW2 update (operands in shared memory) ----
-        // Two decoupled batches per jet so that only the shared-memory operands serialise:
-        //   issue order  B1(0) | dW2(0) B1(1) | dW2(1) B1(2) | dW2(2);   waits: dW2(jt-1) before restaging shared memory,
-        //   B1(last) before the layer-1 reverse; dW2(last) overlaps the reverse and the next evaluation's first phase.
+        // ---- per jet: B1 (A operand in tensor memory) and the dW2 update (operands in shared memory); issue order and
+        // waits: see bwd_mma_tile ----
         // Park the three cotangent jets in tensor memory (they are the unrounded "hi" operand of B1) and let the MMA warp
         // start the B1 passes that only need them; from here on a jet lives in registers only while it is being staged.
 #pragma unroll
