@@ -800,7 +800,7 @@ extern "C" int64_t ofdft_cnf_gnn_theta_size(int32_t n_types, int32_t n_layers) {
 }
 extern "C" size_t ofdft_cnf_gnn_bwd_scratch_bytes(int64_t B, int64_t n_a, int32_t n_types, int32_t n_layers) {
   if (B <= 0 || n_a < 0 || n_a > B) return kCounterBytes;
-  return kCounterBytes + (size_t)n_tiles_of(B, n_a) * (size_t)ofdft_cnf_gnn_theta_size(n_types, n_layers) * sizeof(float);
+  return kCounterBytes + kW2SplitBytes + (size_t)n_tiles_of(B, n_a) * (size_t)ofdft_cnf_gnn_theta_size(n_types, n_layers) * sizeof(float);
 }
 
 // path: OFDFT_PATH_DEFAULT (tcgen05 3xTF32 layer-2 GEMM, gnn_tc.cu) | OFDFT_PATH_FFMA (FP32-pipe kernel of this file)
@@ -884,11 +884,13 @@ extern "C" int ofdft_cnf_gnn_bwd(void* stream, const float* theta, const float* 
   const long long tiles = (n_a + kTP - 1) / kTP + (B - n_a + kTP - 1) / kTP;
   int sms = num_sms(); if (sms <= 0) sms = 148;
   const int grid = (int)(tiles < sms ? tiles : sms);
-  float* gpart = (float*)((char*)scratch + kCounterBytes);
+  float* w2split = (float*)((char*)scratch + kCounterBytes);
+  float* gpart = (float*)((char*)scratch + kCounterBytes + kW2SplitBytes);
   GnnBwdArgs a{theta, nuclei, onehot, ckpt, ybar1, ybar0, gpart, (int*)scratch, B, n_a, jets_a, jets_b, bar_stride,
-               Na, n_types, n_steps, t0, t1, y0sign, act_ckpt, pad_rows(n_a), pad_rows(B - n_a)};
-  // default with an activation checkpoint: tcgen05 3xTF32 GEMMs; OFDFT_PATH_FFMA or no checkpoint: FP32-pipe kernels
-  const bool tc_bwd = act_ckpt != nullptr && !(path & OFDFT_PATH_FFMA);
+               Na, n_types, n_steps, t0, t1, y0sign, n_layers == 2 ? act_ckpt : nullptr, pad_rows(n_a), pad_rows(B - n_a), w2split};
+  // default: tcgen05 3xTF32 GEMMs (without an activation checkpoint the layer-2 jets are recomputed on the tensor cores);
+  // OFDFT_PATH_FFMA: FP32-pipe kernels (checkpoint-reading or recomputing)
+  const bool tc_bwd = !(path & OFDFT_PATH_FFMA);
   if (n_layers != 2) {
     const int rc2 = launch_gnn_general_bwd(stream, a, n_layers);      // gnn_general.cu (no activation checkpoint)
     if (rc2) return rc2;

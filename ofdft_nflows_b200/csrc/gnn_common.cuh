@@ -18,6 +18,7 @@ struct GnnBwdArgs {
   long long B, n_a; int jets_a, jets_b; int bar_stride;
   int Na, n_types, n_steps; float t0, t1, y0;
   const float* act; long long act_rows_a, act_rows_b;
+  float* w2split;   // 2 x 4096 floats of caller scratch: W2 hi | lo in the forward GEMM orientation (tensor-core recompute mode)
 };
 
 // Layer-2 activation checkpoint (optional; trades 180 GB of HBM for the recompute GEMM of the backward pass):
@@ -96,11 +97,13 @@ __device__ __forceinline__ bool next_tile(int* counter, int* slot, long long n_t
 
 
 constexpr size_t kCounterBytes = 256;
+constexpr size_t kW2SplitBytes = 2 * kH * kH * sizeof(float);
 inline long long pad_rows(long long n) { return (n + kTP - 1) / kTP * kTP; }
 
 // tensor-core forward launcher (gnn_tc.cu); returns a cudaError_t / OFDFT_E* code
 int launch_gnn_fwd_tc(void* stream, GnnFwdArgs& a, void* scratch, size_t scratch_bytes);
-// tensor-core backward (needs a.act != nullptr); the caller has reset the tile counter and reduces gpart afterwards
+// tensor-core backward (a.act == nullptr: the layer-2 jets are recomputed on the tensor cores); the caller has reset the
+// tile counter and reduces gpart afterwards
 int launch_gnn_bwd_tc(void* stream, GnnBwdArgs& a, int grid);
 
 // general-depth kernels (gnn_general.cu): 1 or 3 hidden layers

@@ -382,6 +382,7 @@ struct SmemTcB {
   float red[8 * 32 * 4];
   float DW[kTP * kH];                     // fp32 (round-to-nearest) accumulators of the stacked dW2 tile, [col j][row]
   uint64_t barB[3], barD[3];              // per jet: B1 batch done / dW2 batch done (each completes once per evaluation)
+  uint64_t barR[3];                       // recompute mode: layer-2 GEMM of jet jt of the evaluation done
   unsigned int tmem_slot;
   int tile;
 };
@@ -394,7 +395,15 @@ constexpr int kBarPair = 1;          // 1..4: the two warps of a trajectory quar
 constexpr int kBarCompute = 5;       // the 256 compute threads
 constexpr int kBarStaged0 = 6;       // compute -> MMA warp: jet-0 operand of B1 is in tensor memory
 constexpr int kBarStagedJet = 7;     // 7..9: compute -> MMA warp: weight-gradient operands of jet jt (and the B1 operand of jt + 1)
+constexpr int kBarRecomp = 10;       // 10..12, recompute mode: compute -> MMA warp: layer-1 jet jt staged for the layer-2 GEMM
 constexpr int kBwdThreads = kThreads + 128;      // two compute warpgroups + the MMA-issue warpgroup
+// Recompute mode (no activation checkpoint): before the jets of an evaluation are staged the [A1T | P2T] operand region is
+// idle and holds, for the layer-2 forward GEMM, the tf32 remainders of the three layer-1 jets (K-major [k/4][row][4], 32 KB
+// each) and a copy of W2 in the forward orientation (hi, lo: [k/4][j][4], 16 KB each)
+constexpr int kRcLoFloats = kH * kTP;                 // one remainder buffer
+constexpr int kRcWOff = 3 * kRcLoFloats;              // float offset of W2 hi (lo follows)
+static_assert((kRcWOff + 2 * kH * kH) * 4 <= (int)(sizeof(float) * 32 * (kA1TChunk + kP2TChunk)), "recompute operands exceed the staging region");
+static_assert(offsetof(SmemTcB, P2T) == offsetof(SmemTcB, A1T) + sizeof(float) * 32 * kA1TChunk, "A1T and P2T must be contiguous");
 
 __device__ __forceinline__ void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
@@ -404,7 +413,7 @@ __device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.
 // as soon as all 256 compute threads have ARRIVED at the matching named barrier.  The compute warps never block on each
 // other for an MMA hand-off (they only wait on the completion mbarriers they depend on), so they drift apart and their
 // load / SFU / shared-memory phases overlap instead of running in lock-step.
-template <int NJ>
+template <int NJ, bool RC>
 __device__ void bwd_mma_tile(SmemTcB& sm, const GnnBwdArgs& a, uint32_t tmem) {
   const uint32_t idesc = tc::make_idesc_tf32(kTP, kH, 0, 0);
   const uint64_t dA1T = tc::make_desc(tc::smem_u32(sm.A1T), kA1TChunk * 4, 128);
@@ -435,6 +444,32 @@ __device__ void bwd_mma_tile(SmemTcB& sm, const GnnBwdArgs& a, uint32_t tmem) {
   for (int ev = 0; ev < n_eval; ++ev) {
 #pragma unroll 1
     for (int i = 0; i < a.Na; ++i) {
+      if (RC) {
+        // layer-2 forward GEMM of this evaluation: P2[jet] = A1[jet] . W2 as 3xTF32 (hi in tensor memory -- the columns the
+        // cotangent jets are parked in later --, remainder and W2 in the idle staging region); result in the B1 accumulators
+        // (one hand-off and one completion barrier per jet: the GEMM of jet jt runs under the staging of jet jt + 1)
+        const uint32_t base = tc::smem_u32(sm.A1T);
+        const uint64_t dWh = tc::make_desc(base + 4 * kRcWOff, kChunkBytesB, 128);
+        const uint64_t dWl = tc::make_desc(base + 4 * (kRcWOff + kH * kH), kChunkBytesB, 128);
+        constexpr uint64_t stepA = (2 * kChunkBytesA) >> 4, stepB = (2 * kChunkBytesB) >> 4;
+#pragma unroll 1
+        for (int jt = 0; jt < NJ; ++jt) {
+          bar_sync(kBarRecomp + jt, kThreads + 32);
+          tc::fence_after_sync();
+          if (tc::elect_one()) {
+            const uint32_t d = tmem + kColB1 + jt * kH, ahi = tmem + kColP + jt * kH;
+            const uint64_t dLo = tc::make_desc(base + 4 * jt * kRcLoFloats, kChunkBytesA, 128);
+#pragma unroll 1
+            for (int ks = 0; ks < 8; ++ks) tc::mma_tf32_ts(d, ahi + 8 * ks, dWh + ks * stepB, idesc, ks != 0);
+#pragma unroll 1
+            for (int ks = 0; ks < 8; ++ks) tc::mma_tf32_ts(d, ahi + 8 * ks, dWl + ks * stepB, idesc, true);
+#pragma unroll 1
+            for (int ks = 0; ks < 8; ++ks) tc::mma_tf32(d, dLo + ks * stepA, dWh + ks * stepB, idesc, true);
+            tc::commit(&sm.barR[jt]);
+          }
+          __syncwarp();
+        }
+      }
       bar_sync(kBarStaged0, kThreads + 32);
       tc::fence_after_sync();
       if (tc::elect_one()) issue_b1_hi(0);
@@ -470,7 +505,7 @@ struct TcBwdAccum {
   float g_b3;            // owner threads
 };
 
-template <int NJ>
+template <int NJ, bool RC>
 __device__ void bwd_tile_tc(SmemTcB& sm, const GnnBwdArgs& a, long long row0, long long seg_end, float b3, TcBwdAccum& G,
                             bool seg_b, long long seg_row0, uint32_t tmem, uint32_t& phase, bool& dw_pending) {
   const ActLayout AL(a.act_rows_a, a.act_rows_b, a.jets_a, a.jets_b);
@@ -611,7 +646,7 @@ __device__ void bwd_tile_tc(SmemTcB& sm, const GnnBwdArgs& a, long long row0, lo
       for (int i = 0; i < a.Na; ++i) {
         // ---- layer-2 jets (a2, p2', p2'') of (trajectory m, units 32 uh ..) from the HBM checkpoint ----
         float q0[32], q1[32], q2[32];
-        {
+        if constexpr (!RC) {
           const float* src = a.act + AL.seg_base((long long)(step * 4 + stage) * a.Na + i, seg_b)
                              + act_group_off(8 * uh, (row0 - seg_row0) + m, act_rows);
 #pragma unroll
@@ -669,6 +704,74 @@ __device__ void bwd_tile_tc(SmemTcB& sm, const GnnBwdArgs& a, long long row0, lo
             asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(q1r) : "f"(d1));
             unpack2(fma2(m2, pack2(q0r, q1r), one), av[u], av[u + 1]);
           }
+        }
+        if constexpr (RC) {
+          // ---- recompute mode: layer-2 jets (a2, p2', p2'') = tanh-jet of A1[jet] . W2 on the tensor cores ----
+          using namespace tc;
+          float* region = sm.A1T;
+          // the staging region is free once the previous evaluation's last weight-gradient batch has completed
+          if (dw_pending) { mbar_wait(&sm.barD[NJ - 1], (phase >> (3 + NJ - 1)) & 1u); phase ^= 1u << (3 + NJ - 1); dw_pending = false; __syncwarp(); }
+          // W2 (forward orientation, hi | lo) from the prepared global copy: 8192 floats, 32 per thread
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int o = (q * kThreads + (int)threadIdx.x) * 4;
+            *reinterpret_cast<float4*>(region + kRcWOff + o) = __ldg(reinterpret_cast<const float4*>(a.w2split + o));
+          }
+#pragma unroll
+          for (int jt = 0; jt < NJ; ++jt) {
+#pragma unroll
+            for (int c0 = 0; c0 < 32; c0 += 16) {
+              float hv[16];
+#pragma unroll
+              for (int u = 0; u < 16; u += 4) {
+                f32x2 p[2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                  const int uu = c0 + u + 2 * h;
+                  const f32x2 a2v = pack2(av[uu], av[uu + 1]);
+                  f32x2 ajp = a2v;
+                  if (jt > 0) {
+                    const float2 w2 = *reinterpret_cast<const float2*>(&sm.wr[32 * uh + uu]);
+                    const f32x2 wv = pack2(w2.x, w2.y);
+                    const f32x2 a1 = mul2(fma2(mul2(a2v, splat2(-1.0f)), a2v, splat2(1.0f)), wv);      // (1 - a^2) w
+                    ajp = jt == 1 ? a1 : mul2(mul2(mul2(a2v, splat2(-2.0f)), a1), wv);               // -2 a a' w
+                  }
+                  p[h] = ajp;
+                  unpack2(ajp, hv[u + 2 * h], hv[u + 2 * h + 1]);
+                }
+                const f32x2 l0 = fma2(p[0] & 0xFFFFE000FFFFE000ull, splat2(-1.0f), p[0]);
+                const f32x2 l1 = fma2(p[1] & 0xFFFFE000FFFFE000ull, splat2(-1.0f), p[1]);
+                const int chunk = 8 * uh + ((c0 + u) >> 2);
+                *reinterpret_cast<float4*>(region + jt * kRcLoFloats + (chunk * kTP + m) * 4) = make_float4(lo2(l0), hi2(l0), lo2(l1), hi2(l1));
+              }
+              tmem_st16(tlane + kColP + jt * kH + 32 * uh + c0, hv);
+            }
+            tmem_st_wait();
+            fence_async_smem();
+            fence_before_sync();
+            bar_arrive(kBarRecomp + jt, kThreads + 32);    // -> MMA warp: layer-2 GEMM of jet jt (runs under the next staging)
+          }
+#pragma unroll
+          for (int jt = 0; jt < NJ; ++jt) {
+            mbar_wait(&sm.barR[jt], (phase >> (6 + jt)) & 1u); phase ^= 1u << (6 + jt);
+            __syncwarp();
+            fence_after_sync();
+#pragma unroll
+            for (int c0 = 0; c0 < 32; c0 += 16) {
+              float t[16];
+              tmem_ld16(tlane + kColB1 + jt * kH + 32 * uh + c0, t);
+              tmem_ld_wait();
+#pragma unroll
+              for (int u = 0; u < 16; u += 2) {
+                if (jt == 0) {
+                  const float2 bb = *reinterpret_cast<const float2*>(&sm.b2[32 * uh + c0 + u]);
+                  unpack2(tanh2(add2(pack2(t[u], t[u + 1]), pack2(bb.x, bb.y))), q0[c0 + u], q0[c0 + u + 1]);
+                } else if (jt == 1) { q1[c0 + u] = t[u]; q1[c0 + u + 1] = t[u + 1]; }
+                else { q2[c0 + u] = t[u]; q2[c0 + u + 1] = t[u + 1]; }
+              }
+            }
+          }
+          fence_before_sync();
         }
         // ---- layer-2 tanh-jet: forward partials of f and reverse to the pre-activation cotangents (in place) ----
         float g32[32];
@@ -1001,6 +1104,7 @@ __device__ void flush_tile_grad_tc(SmemTcB& sm, TcBwdAccum& G, float* __restrict
   bar_sync(kBarCompute, kThreads);
 }
 
+template <bool RC>
 __global__ void __launch_bounds__(kBwdThreads, 1) gnn_bwd_tc_kernel(const GnnBwdArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   SmemTcB& sm = *reinterpret_cast<SmemTcB*>(smem_raw);
@@ -1024,6 +1128,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) gnn_bwd_tc_kernel(const GnnBwd
   for (int i = tid; i < kTP * kH; i += kBwdThreads) sm.DW[i] = 0.f;
   if (tid == 0) {
     for (int j = 0; j < 3; ++j) { tc::mbar_init(&sm.barB[j], 1); tc::mbar_init(&sm.barD[j], 1); }
+    for (int j = 0; j < 3; ++j) tc::mbar_init(&sm.barR[j], 1);
     tc::fence_mbar_init();
   }
   if (tid < 32) tc::tmem_alloc(&sm.tmem_slot, 512);
@@ -1041,7 +1146,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) gnn_bwd_tc_kernel(const GnnBwd
   static_assert(kThreads * 232 + 128 * 40 <= 168 * kBwdThreads, "setmaxnreg budget exceeds the registers allocated at launch");
   if (tid < kThreads) {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
-    uint32_t phase = 0;            // bits 0..2: parity of barB[jet], bits 3..5: parity of barD[jet]
+    uint32_t phase = 0;            // bits 0..2: parity of barB[jet], bits 3..5: parity of barD[jet], bits 6..8: barR[jet]
     const float b3 = a.theta[0];
     TcBwdAccum G;
     G.g_b2 = G.g_w3 = G.g_wt = G.g_wr = G.g_b3 = 0.f;
@@ -1052,9 +1157,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) gnn_bwd_tc_kernel(const GnnBwd
       if (tile < tiles_a) { row0 = tile * kTP; seg_end = a.n_a; nj = a.jets_a; seg_b = false; seg_row0 = 0; }
       else { row0 = a.n_a + (tile - tiles_a) * kTP; seg_end = a.B; nj = a.jets_b; seg_b = true; seg_row0 = a.n_a; }
       bool dw_pending = false;
-      if (nj == 3) bwd_tile_tc<3>(sm, a, row0, seg_end, b3, G, seg_b, seg_row0, tmem, phase, dw_pending);
-      else if (nj == 2) bwd_tile_tc<2>(sm, a, row0, seg_end, b3, G, seg_b, seg_row0, tmem, phase, dw_pending);
-      else bwd_tile_tc<1>(sm, a, row0, seg_end, b3, G, seg_b, seg_row0, tmem, phase, dw_pending);
+      if (nj == 3) bwd_tile_tc<3, RC>(sm, a, row0, seg_end, b3, G, seg_b, seg_row0, tmem, phase, dw_pending);
+      else if (nj == 2) bwd_tile_tc<2, RC>(sm, a, row0, seg_end, b3, G, seg_b, seg_row0, tmem, phase, dw_pending);
+      else bwd_tile_tc<1, RC>(sm, a, row0, seg_end, b3, G, seg_b, seg_row0, tmem, phase, dw_pending);
       bar_sync(kBarCompute, kThreads);
       flush_tile_grad_tc(sm, G, a.gpart + (size_t)tile * L.n, L, a.onehot, a.Na, a.n_types, tmem, dw_pending);
     }
@@ -1064,9 +1169,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) gnn_bwd_tc_kernel(const GnnBwd
     while (next_tile(a.counter, &sm.tile, tiles_a + tiles_b, tile)) {
       if (tid < kThreads + 32) {
         const int nj = tile < tiles_a ? a.jets_a : a.jets_b;
-        if (nj == 3) bwd_mma_tile<3>(sm, a, tmem);
-        else if (nj == 2) bwd_mma_tile<2>(sm, a, tmem);
-        else bwd_mma_tile<1>(sm, a, tmem);
+        if (nj == 3) bwd_mma_tile<3, RC>(sm, a, tmem);
+        else if (nj == 2) bwd_mma_tile<2, RC>(sm, a, tmem);
+        else bwd_mma_tile<1, RC>(sm, a, tmem);
       }
     }
   }
@@ -1075,11 +1180,30 @@ __global__ void __launch_bounds__(kBwdThreads, 1) gnn_bwd_tc_kernel(const GnnBwd
   if (tid < 32) tc::tmem_dealloc(tmem, 512);
 }
 
+// W2 in the forward GEMM orientation, split hi / lo: [k/4][j][4] (recompute mode: copied into shared memory per evaluation)
+__global__ void gnn_w2_split_kernel(const float* __restrict__ theta, float* __restrict__ out, int n_types) {
+  const GnnThetaLayout L(n_types);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= kH * kH) return;
+  const int k = i / kH, j = i % kH;
+  float hi, lo;
+  tc::split_tf32(theta[L.W2 + i], hi, lo);
+  const int off = ((k >> 2) * kH + j) * 4 + (k & 3);
+  out[off] = hi; out[kH * kH + off] = lo;
+}
+
 int launch_gnn_bwd_tc(void* stream, GnnBwdArgs& a, int grid) {
   cudaStream_t st = (cudaStream_t)stream;
-  cudaError_t e = cudaFuncSetAttribute(gnn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemTcB) + 1024);
+  const bool rc = a.act == nullptr;       // no activation checkpoint: recompute the layer-2 jets on the tensor cores
+  cudaError_t e = rc ? cudaFuncSetAttribute(gnn_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemTcB) + 1024)
+                     : cudaFuncSetAttribute(gnn_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemTcB) + 1024);
   if (e != cudaSuccess) return (int)e;
-  gnn_bwd_tc_kernel<<<grid, kBwdThreads, sizeof(SmemTcB) + 1024, st>>>(a);
+  if (rc) {
+    gnn_w2_split_kernel<<<(kH * kH + 255) / 256, 256, 0, st>>>(a.theta, a.w2split, a.n_types);
+    gnn_bwd_tc_kernel<true><<<grid, kBwdThreads, sizeof(SmemTcB) + 1024, st>>>(a);
+  } else {
+    gnn_bwd_tc_kernel<false><<<grid, kBwdThreads, sizeof(SmemTcB) + 1024, st>>>(a);
+  }
   return (int)cudaGetLastError();
 }
 

@@ -101,27 +101,25 @@ class EnergyEstimator:
                 self.act_ckpt_max_bytes = int(min(64 << 30, free // 2))
             act_bytes = ops.gnn_act_ckpt_bytes(B, bs, ops.JETS_FULL, self.jets_b, Na, self.n_steps)
             want_act = self.act_ckpt and act_bytes <= self.act_ckpt_max_bytes
-            # activation checkpoint above the cap (many nuclei x large batch): integrate once without checkpoints, then
-            # re-integrate and reverse the rows in chunks whose checkpoint fits -- one extra forward pass keeps the
-            # backward on the tensor-core kernel, which is ~3x faster than the FP32 recompute kernel
-            chunked = self.act_ckpt and not want_act and B > 0 and len(getattr(m, "features", (64, 64))) == 2
-            if chunked and self.hartree_mode == "paired":
-                # every term of the paired estimator is a mean over rows (i, i + bs): row chunks go through forward ->
-                # functionals -> adjoint independently, each with a checkpoint that fits -- no extra forward pass
+            # activation checkpoint above the cap (many nuclei x large batch):
+            #  * paired mode: every term is a mean over rows (i, i + bs), so row chunks go through forward -> functionals ->
+            #    adjoint independently, each with a checkpoint that fits (same speed as below the cap);
+            #  * all-pairs mode couples every row with every partner: one launch without the activation checkpoint, the
+            #    adjoint recomputes the layer-2 jets on the tensor cores (~13 % slower than with the checkpoint)
+            chunked = (self.act_ckpt and not want_act and B > 0 and len(getattr(m, "features", (64, 64))) == 2
+                       and self.hartree_mode == "paired")
+            if chunked:
                 sums, tbar, y1 = self._gnn_step_row_chunks(theta, batch, bs, Na, timers)
                 return self._reduce(sums, tbar, y1)
             y1, ckpt = ops.gnn_fwd(theta, m.xyz_nuclei, m.z_one_hot, batch, bs, ops.JETS_FULL, self.jets_b, self.n_steps,
-                                   self.t0, self.t1, m.y0, want_ckpt=not chunked, want_act=want_act, path=self.path)
+                                   self.t0, self.t1, m.y0, want_ckpt=True, want_act=want_act, path=self.path)
             e1 = mark()
             sums, ybar1 = ops.functionals_fwd_bwd(self.spec, y1)
             if self.hartree_mode == "allpairs":
                 self._allpairs_hartree(y1, ybar1, sums, timers)
             e2 = mark()
-            if chunked:
-                tbar = self._gnn_bwd_chunked(theta, batch, ybar1, bs, Na)
-            else:
-                tbar, _ = ops.gnn_bwd(theta, m.xyz_nuclei, m.z_one_hot, ckpt, ybar1, bs, ops.JETS_FULL, self.jets_b,
-                                      self.n_steps, self.t0, self.t1, m.y0, path=self.path)
+            tbar, _ = ops.gnn_bwd(theta, m.xyz_nuclei, m.z_one_hot, ckpt, ybar1, bs, ops.JETS_FULL, self.jets_b,
+                                  self.n_steps, self.t0, self.t1, m.y0, path=self.path)
             e3 = mark()
             if timers is not None:
                 timers += [("gnn_fwd", e0, e1), ("functionals", e1, e2), ("gnn_bwd", e2, e3)]
@@ -184,28 +182,6 @@ class EnergyEstimator:
             y1[bs + lo:bs + hi] = y1c[n:]
             del ck, y1c, ybar, sub
         return sums, tbar, y1
-
-    def _gnn_bwd_chunked(self, theta: torch.Tensor, batch: torch.Tensor, ybar1: torch.Tensor, bs: int, Na: int) -> torch.Tensor:
-        """theta_bar = sum over row chunks of [re-integrate the chunk with both checkpoints, reverse it]; the chunks never
-        straddle the two halves (their jets differ) and are sized so that one activation checkpoint fits the cap."""
-        m = self.model
-        tbar = torch.zeros_like(theta)
-        B = batch.shape[0]
-        for lo, hi, jets in ((0, bs, ops.JETS_FULL), (bs, B, self.jets_b)):
-            n = hi - lo
-            if n <= 0:
-                continue
-            per_row = max(1, ops.gnn_act_ckpt_bytes(128, 128, jets, jets, Na, self.n_steps) // 128)
-            rows = max(128, (self.act_ckpt_max_bytes // per_row) // 128 * 128)
-            for r0 in range(lo, hi, rows):
-                r1 = min(hi, r0 + rows)
-                _, ck = ops.gnn_fwd(theta, m.xyz_nuclei, m.z_one_hot, batch[r0:r1], r1 - r0, jets, jets, self.n_steps,
-                                    self.t0, self.t1, m.y0, want_ckpt=True, want_act=True)
-                g, _ = ops.gnn_bwd(theta, m.xyz_nuclei, m.z_one_hot, ck, ybar1[r0:r1], r1 - r0, jets, jets, self.n_steps,
-                                   self.t0, self.t1, m.y0)
-                tbar += g
-                del ck
-        return tbar
 
     def _allpairs_hartree(self, y1: torch.Tensor, ybar1: torch.Tensor, sums: torch.Tensor, timers: Optional[list] = None) -> None:
         """Adds the all-pairs Hartree energy of this rank's strips to ``sums`` and its forces to ``ybar1`` (in place).

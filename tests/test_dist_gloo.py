@@ -136,7 +136,7 @@ def test_chunked_backward_path_equals_single_launch_on_cpu_fakes():
     s1, g1, _ = est2.step_flat(torch.as_tensor(theta), torch.as_tensor(batch))
     assert np.allclose(s0.numpy(), s1.numpy(), rtol=1e-13, atol=1e-15)       # chunk means re-weighted: rounding-level differences
     assert np.linalg.norm(g1.numpy() - g0.numpy()) < 1e-12 * np.linalg.norm(g0.numpy())
-    # the all-pairs estimator couples every row with every partner: it keeps the re-integration path
+    # the all-pairs estimator couples every row with every partner: one launch without the activation checkpoint
     est3 = _make_estimator(mol, 4, "allpairs")
     s2, g2, _ = est3.step_flat(torch.as_tensor(theta), torch.as_tensor(batch))
     est4 = _make_estimator(mol, 4, "allpairs")

@@ -227,12 +227,12 @@ def test_chunked_backward_above_the_activation_checkpoint_cap():
     s1, g1, _ = small.step_flat(dev(theta), dev(batch))
     assert np.allclose(s0.cpu().numpy(), s1.cpu().numpy(), rtol=1e-6)        # float32 cotangent scaling / chunk re-weighting
     assert rel(g1.cpu().numpy(), g0.cpu().numpy()) < 2e-6
-    # all-pairs mode keeps the re-integration path (every row is coupled to every partner)
+    # all-pairs mode (every row is coupled to every partner): one launch, tensor-core recompute of the layer-2 jets
     fa = EnergyEstimator(model, spec, n_steps=4, hartree_mode="allpairs")
     sa = EnergyEstimator(model, spec, n_steps=4, hartree_mode="allpairs", act_ckpt_max_bytes=130 * per_row)
     s2, g2, _ = fa.step_flat(dev(theta), dev(batch))
     s3, g3, _ = sa.step_flat(dev(theta), dev(batch))
-    assert torch.equal(s2, s3) and rel(g3.cpu().numpy(), g2.cpu().numpy()) < 2e-6
+    assert torch.equal(s2, s3) and rel(g3.cpu().numpy(), g2.cpu().numpy()) < 5e-6
     ospec = O.EnergySpec(Ne=mol["Ne"], kin="tf-w", hart="hartree", nuc="hgh", x="lda", coords=mol["coords"], z=mol["z"])
     _, _, g_ref, _ = O.loss_and_grad(fld, ospec, batch, n_steps=4)
     for name, (a, b) in tensor_slices(nt).items():
