@@ -357,7 +357,8 @@ def main():
     ap.add_argument("--full-jets", action="store_true", help="carry logp/score on the second half too (reference dataflow)")
     ap.add_argument("--hartree", default="paired", choices=["paired", "allpairs"],
                     help="allpairs: O(bs^2) cross-half Hartree estimator (coordinates all-gathered over NCCL, tiled pair kernel)")
-    ap.add_argument("--recompute", action="store_true", help="recompute layer-2 activations in the backward pass (no HBM activation checkpoint)")
+    ap.add_argument("--recompute", action="store_true",
+                    help="no HBM activation checkpoint: the adjoint recomputes the layer-2 jets (tensor cores; with --ffma: FP32 pipe)")
     ap.add_argument("--ffma", action="store_true", help="FP32-pipe kernels (ops.PATH_FFMA) instead of the tcgen05 kernels")
     ap.add_argument("--no-extra-blocks", action="store_true",
                     help="skip the hartree_pairs block (N=1) and the strong / allpairs blocks (N>1) of the default run")
@@ -505,7 +506,7 @@ def main():
     kern_avg.setdefault("gnn_bwd", kern_avg.get("mlp_bwd", 0.0)); kern_avg.setdefault("gnn_fwd", kern_avg.get("mlp_fwd", 0.0))
     bwd_s = kern_avg["gnn_bwd"] * 1e-3
     fwd_s = kern_avg["gnn_fwd"] * 1e-3
-    tensor_path = (not is_1d) and (not args.recompute) and not args.ffma
+    tensor_path = (not is_1d) and not args.ffma
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -551,13 +552,15 @@ def main():
         # timed inside the step loop), else 1/2 of the profiling guide's 1.4 PFLOP/s fallback.
         mma = 2.0 * 128 * 64 * 8
         tiles_h, tiles_l = math.ceil(bs / 128), math.ceil(bs / 128)
-        per_h, per_l = (72 + 96), (24 + 32) if jets_b == 1 else (72 + 96)
+        rc = 72 if args.recompute else 0          # tensor-core recompute of the layer-2 jets: one more 3xTF32 GEMM per jet
+        per_h, per_l = (72 + 96 + rc), (24 + 32 + rc // 3) if jets_b == 1 else (72 + 96 + rc)
         bwd_tensor_flops = evals * na * mma * (tiles_h * per_h + tiles_l * per_l)
         fwd_tensor_flops = evals * na * mma * (tiles_h * 72 + tiles_l * (24 if jets_b == 1 else 72))
         tf32_peak = 0.5 * peaks.get("bf16_tflops_sustained", 1400.0)
         peak3 = tf32_peak / 3.0            # an fp32-accurate GEMM costs three TF32 passes
         roofline = {
-            "bound": "tensor", "kernel": "gnn_bwd_tc_kernel", "achieved": bwd_flops / bwd_s / 1e12, "peak": peak3,
+            "bound": "tensor", "kernel": "gnn_bwd_tc_kernel<recompute>" if args.recompute else "gnn_bwd_tc_kernel",
+            "achieved": bwd_flops / bwd_s / 1e12, "peak": peak3,
             "unit": "TFLOP/s (fp32-equivalent)", "frac": bwd_flops / bwd_s / 1e12 / peak3, "traffic": None,
             "peak_source": ("3xTF32 = 1/3 x 1/2 x bf16_tflops_sustained of MEASURED_PEAKS.json (kernel timed inside the step; of measured)"
                             if peaks else "1/3 x 1/2 x 1.4 PFLOP/s (B200_PROFILING.md fallback; of fallback)"),
@@ -572,6 +575,8 @@ def main():
                                 "ffma_peak": ffma_peak / 1e12, "frac_of_ffma_peak": bwd_flops / bwd_s / ffma_peak,
                                 "peak_source": "ofdft_microbench_ffma measured in this run"},
             "kernel_ms": kern_avg,
+            "backward_mode": ("layer-2 jets recomputed on the tensor cores (no activation checkpoint)" if args.recompute
+                              else "layer-2 activation checkpoint in HBM"),
             "fwd": {"kernel": "gnn_fwd_tc_kernel", "achieved": fwd_flops / fwd_s / 1e12, "frac": fwd_flops / fwd_s / 1e12 / peak3,
                     "executed_tensor_frac_of_dense_tf32": fwd_tensor_flops / fwd_s / 1e12 / tf32_peak,
                     "fp32_equivalent_frac_of_ffma_peak": fwd_flops / fwd_s / ffma_peak},

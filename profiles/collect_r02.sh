@@ -9,6 +9,7 @@ for wl in h2 lih c6h6 lih1d; do
   timeout 600 python bench.py --workload $wl --steps 10 --warmup 3 --no-cpu-baseline > $O/bench_$wl.json 2> $O/bench_$wl.err
 done
 timeout 600 python bench.py --steps 5 --warmup 3 --recompute --no-cpu-baseline > $O/bench_recompute.json 2> $O/bench_recompute.err
+timeout 600 python bench.py --steps 5 --warmup 3 --recompute --ffma --no-cpu-baseline > $O/bench_recompute_ffma.json 2> $O/bench_recompute_ffma.err
 timeout 600 python bench.py --steps 5 --warmup 3 --ffma --no-cpu-baseline > $O/bench_ffma.json 2> $O/bench_ffma.err
 # launch list (cold-cache, serialised: shares only) -- after the plain command above exited 0
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/ncu_launches.csv \
