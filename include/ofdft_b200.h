@@ -45,6 +45,9 @@ extern "C" {
 #define OFDFT_PATH_DEFAULT 0
 #define OFDFT_PATH_FFMA    1     /* integrator / adjoint sweep on the FP32 FFMA pipe                       */
 #define OFDFT_PATH_FFMA_DW 2     /* 1-D flow: weight-gradient GEMM on the FP32 pipe (bit-or with the above) */
+#define OFDFT_PATH_ACT_CKPT 4    /* 1-D flow, tensor-core path: `ckpt` is ofdft_cnf_mlp1d_act_ckpt_bytes() large; the forward
+                                    also keeps every evaluation's layer activations there and the adjoint reads them
+                                    instead of recomputing the hidden layers (pass the flag to both calls)          */
 
 /* jets carried per trajectory */
 #define OFDFT_JETS_X      1      /* x only                  (second-half rows: only xp is used, H20_...py:154-156) */
@@ -165,8 +168,11 @@ int ofdft_cnf_gnn_rhs(void* stream, const float* theta, const float* nuclei, con
  * instantiated for jets == OFDFT_JETS_FULL.  scratch (ofdft_cnf_mlp1d_scratch_bytes) holds 16-byte-aligned
  * (and transposed) copies of the hidden kernels and, for the backward pass, the per-stage activation /
  * cotangent jets of a 2048-row chunk that the weight-gradient GEMM contracts (~2 MB per row at H=512, RK4x16).
+ * ofdft_cnf_mlp1d_act_ckpt_bytes: size of `ckpt` under OFDFT_PATH_ACT_CKPT (stage states + ~2.4 MB per row of layer
+ * activations at 3 x 512, RK4x16); 0 when the shape does not support it (B above one 2048-row backward chunk).
  */
 size_t ofdft_cnf_mlp1d_ckpt_bytes(int64_t B, int32_t n_steps);
+size_t ofdft_cnf_mlp1d_act_ckpt_bytes(int64_t B, int32_t H, int32_t n_layers, int32_t n_steps);
 size_t ofdft_cnf_mlp1d_scratch_bytes(int64_t B, int32_t H, int32_t n_layers, int32_t n_steps);
 int ofdft_cnf_mlp1d_fwd(void* stream, const float* theta, const float* y_in, float* y_out, float* ckpt,
                         void* scratch, size_t scratch_bytes, int64_t B, int32_t jets, int32_t stride,

@@ -37,6 +37,7 @@ SIGNATURES = {
                                     f32, f32, f32, i32]),
     "ofdft_cnf_gnn_rhs": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, szt, i64, i32, i32, i32, i32, i32, f32, f32, i32]),
     "ofdft_cnf_mlp1d_ckpt_bytes": (szt, [i64, i32]),
+    "ofdft_cnf_mlp1d_act_ckpt_bytes": (szt, [i64, i32, i32, i32]),
     "ofdft_cnf_mlp1d_scratch_bytes": (szt, [i64, i32, i32, i32]),
     "ofdft_cnf_mlp1d_fwd": (C.c_int, [vp, vp, vp, vp, vp, vp, szt, i64, i32, i32, i32, i32, i32, f32, f32, f32, i32]),
     "ofdft_cnf_mlp1d_rhs": (C.c_int, [vp, vp, vp, vp, vp, szt, i64, i32, i32, i32, i32, f32, f32]),

@@ -69,16 +69,27 @@ def mlp_rhs(theta, y, f: Gen_CNFSimpleMLP, t: float, jets: int) -> torch.Tensor:
     return dy
 
 
+ACT_CKPT_MAX_BYTES = 16 << 30     # default cap of the 1-D activation checkpoint (~2.4 MB per row at 3 x 512, RK4 x 16)
+
+
 def mlp_fwd(theta, batch, f: Gen_CNFSimpleMLP, t0: float, t1: float, jets: int, n_steps: int, want_ckpt: bool = False,
-            path: int = ops.PATH_DEFAULT) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
-    """ofdft_cnf_mlp1d_fwd: rows [x | logp | s]."""
+            path: int = ops.PATH_DEFAULT, act_ckpt: bool = True) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """ofdft_cnf_mlp1d_fwd: rows [x | logp | s].  With ``want_ckpt`` the stage checkpoint the adjoint needs is returned; on
+    the tensor-core path with full jets it also holds every evaluation's layer activations (``act_ckpt``, when the shape
+    supports it and it fits ACT_CKPT_MAX_BYTES), which the adjoint then reads instead of recomputing the hidden layers --
+    mlp_bwd recognises the larger buffer by its size."""
     lib = _lib.load()
     theta, batch = ops._f32c(theta), ops._f32c(batch)
     B, stride = batch.shape
     y1 = torch.zeros_like(batch)
     ckpt = None
     if want_ckpt:
-        ckpt = torch.empty(lib.ofdft_cnf_mlp1d_ckpt_bytes(B, n_steps) // 4, dtype=torch.float32, device=batch.device)
+        n = lib.ofdft_cnf_mlp1d_ckpt_bytes(B, n_steps)
+        if act_ckpt and jets == ops.JETS_FULL and not (path & (ops.PATH_FFMA | ops.PATH_FFMA_DW)):
+            n_act = lib.ofdft_cnf_mlp1d_act_ckpt_bytes(B, f.H, f.n_layers, n_steps)
+            if 0 < n_act <= ACT_CKPT_MAX_BYTES:
+                n, path = n_act, path | ops.PATH_ACT_CKPT
+        ckpt = torch.empty(n // 4, dtype=torch.float32, device=batch.device)
     sb = lib.ofdft_cnf_mlp1d_scratch_bytes(B, f.H, f.n_layers, n_steps)
     scratch = torch.empty(sb, dtype=torch.uint8, device=batch.device)
     with ops._on(batch):
@@ -96,6 +107,10 @@ def mlp_bwd(theta, ckpt, ybar1, f: Gen_CNFSimpleMLP, t0: float, t1: float, jets:
     B, stride = ybar1.shape
     tbar = torch.empty_like(theta)
     ybar0 = torch.zeros_like(ybar1) if want_ybar0 else None
+    if B > 0 and ckpt.numel() * 4 > lib.ofdft_cnf_mlp1d_ckpt_bytes(B, n_steps):       # forward kept the layer activations
+        if ckpt.numel() * 4 != lib.ofdft_cnf_mlp1d_act_ckpt_bytes(B, f.H, f.n_layers, n_steps) or (path & (ops.PATH_FFMA | ops.PATH_FFMA_DW)):
+            raise ValueError("mlp_bwd: checkpoint size matches neither the stage nor the activation checkpoint of this shape/path")
+        path |= ops.PATH_ACT_CKPT
     sb = lib.ofdft_cnf_mlp1d_scratch_bytes(B, f.H, f.n_layers, n_steps)
     scratch = torch.empty(sb, dtype=torch.uint8, device=ybar1.device)
     with ops._on(ybar1):

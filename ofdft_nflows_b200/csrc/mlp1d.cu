@@ -15,6 +15,8 @@
 // atomics would be ~50x slower than the FFMA work.
 #include <cstdlib>
 
+#include <mutex>
+
 #include "common.cuh"
 #include "tc.cuh"
 #include "mlp1d_common.cuh"
@@ -658,126 +660,252 @@ __global__ void __launch_bounds__(256, 2) mlp_dw_gemm_tc_kernel(const float* __r
 }
 
 // ------------------------------------------------------------------------------------------------
-// 128 x 128 output tiles (H a multiple of 128): the 64 x 64 kernel above re-reads every HBM block for 8 column tiles and
-// is bound by that traffic (6.4 GB per layer at H = 512, B = 1024, RK4x16); this one halves it.  Per (block, jet):
-//   D[k 128][j 128] += A_hi . P_hi + A_lo . P_hi + A_hi . P_lo        (three M128 N128 K8 MMAs; the lo.lo term is dropped)
-// one HBM block per 48 KB stage, two stages, two CTAs per SM, 16 tiles x 16 splits; the TMEM chain is drained into fp32
-// registers every kDw2Flush stages.
+// 128 x 128 output tiles (H a multiple of 128), warp specialised.  With both operands in shared memory a (block, jet) slab of
+// 8 trajectories costs 16 KB of operand stores and 24 KB of MMA operand reads per 192 tensor-core clocks -- 208 B/clk
+// against the 128 B/clk of the shared-memory port -- so the activation operand goes through TENSOR MEMORY instead:
+//   warps 0..3 (A role, thread = unit k = TMEM lane): (a, p', p'') of 8 trajectories -> operand jets (a, a', a'') and their
+//              tf32 remainders -> tcgen05.st, per slot [jet][hi 8 | lo 8] = 48 columns;
+//   warps 4..7 (P role, thread = unit j): cotangent jets as stored -> (hi, lo) K-major operands in shared memory;
+//   warp 8   : D[k 128][j 128] += A_hi . P_hi + A_lo . P_hi + A_hi . P_lo per (block, jet)  (TS-mode M128 N128 K8; the
+//              lo.lo term is dropped), tcgen05.commit frees the slot.  Its warpgroup hands its registers to the staging
+//              warpgroups (setmaxnreg: 40 / 232), which hold 64 fp32 accumulators and the loads in flight.
+// The HBM loads run kDw3PF blocks ahead in registers (they are the latency of the loop: ~1 us each); four operand slots;
+// two accumulator sets of 128 columns alternate every kDw3Flush blocks and are drained into fp32 registers by all eight
+// staging warps because tensor-core accumulation truncates.  One CTA per SM: 16 tiles x 9 splits.
 // ------------------------------------------------------------------------------------------------
-constexpr int kDw2Flush = 32;     // 32 x 9 = 288 MMAs per chain (the chain length the 3-D backward kernel uses per stage)
-struct Dw2Stage {
-  float Ah[3][2 * 128 * 4], Al[3][2 * 128 * 4];   // [jet][chunk of 4 traj][row k 128][4]
-  float Ph[3][2 * 128 * 4], Pl[3][2 * 128 * 4];   // [jet][chunk][row j 128][4]
+constexpr int kDw3Slots = 4;
+constexpr int kDw3Flush = 32;     // blocks per TMEM accumulation chain: 32 x 9 = 288 MMAs
+constexpr int kDw3PF = 4;         // HBM blocks in flight per staging thread
+constexpr int kDw3Splits = 9;     // 16 tiles x 9 = 144 CTAs on 148 SMs
+constexpr int kDw3Threads = 12 * 32;   // two staging warpgroups + the MMA-issue warpgroup (one active warp)
+constexpr int kDw3ColA = 256;     // TMEM: accumulator sets at 0 and 128, operand ring from 256
+// SL = true: the operands are read straight from per-evaluation layer buffers ([jet][H/4][rows_pad][4], what the layer GEMMs
+// read and write anyway) instead of HBM blocks: block b = (evaluation b / n_tiles, rows 8 (b % n_tiles)..).  A thread's unit
+// owns eight 4-byte words 16 bytes apart there; loading them as such costs 8 L1 tag lookups per warp instruction (192 per
+// warp and block -- slower than the tensor core consumes them), so each lane quad loads the 4 units x 8 rows of its unit
+// group as float4 (4 units of one row) and transposes 4x4 in registers with four shuffles.
+struct DwSrc {
+  const float* a; const float* p;                 // layer buffers of evaluation 0: activations of layer - 1, cotangents of layer
+  size_t a_ev, p_ev;                              // strides between evaluations (floats)
+  long long rows_pad, rows; int n_tiles;
 };
-struct Dw2Smem {
-  Dw2Stage st[2];
-  uint64_t bar[2];
+// 4x4 transpose across the four lanes of a quad: lane i holds row i (x, y, z, w = columns 0..3) and ends with column i
+__device__ __forceinline__ float4 quad_transpose(float4 v, int i) {
+  const bool hi = (i & 2) != 0, odd = (i & 1) != 0;
+  // swap the off-diagonal 2x2 blocks between lanes i and i ^ 2
+  const float r0 = __shfl_xor_sync(0xffffffffu, hi ? v.x : v.z, 2), r1 = __shfl_xor_sync(0xffffffffu, hi ? v.y : v.w, 2);
+  if (hi) { v.x = r0; v.y = r1; } else { v.z = r0; v.w = r1; }
+  // swap the off-diagonal elements of every 2x2 block between lanes i and i ^ 1
+  const float q0 = __shfl_xor_sync(0xffffffffu, odd ? v.x : v.y, 1), q1 = __shfl_xor_sync(0xffffffffu, odd ? v.z : v.w, 1);
+  if (odd) { v.x = q0; v.z = q1; } else { v.y = q0; v.w = q1; }
+  return v;
+}
+
+struct Dw3Smem {
+  float Ph[kDw3Slots][3][2 * 128 * 4];            // [slot][jet][chunk of 4 traj][row j 128][4]
+  float Pl[kDw3Slots][3][2 * 128 * 4];
+  uint64_t full[kDw3Slots], empty[kDw3Slots], accf[2], acce[2];
   unsigned int tmem_slot;
 };
 
-__global__ void __launch_bounds__(256, 2) mlp_dw_gemm_tc128_kernel(const float* __restrict__ acts, const float* __restrict__ pbar,
-                                                                  float* __restrict__ part, int H, int L, int layer,
-                                                                  long long n_blocks, int splits) {
+template <bool SL>
+__global__ void __launch_bounds__(kDw3Threads, 1) mlp_dw_gemm_ts_kernel(const float* __restrict__ acts, const float* __restrict__ pbar,
+                                                                       float* __restrict__ part, int H, int L, int layer,
+                                                                       long long blk0, long long n_blocks, int splits, const DwSrc src,
+                                                                       int accumulate) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  Dw2Smem& sm = *reinterpret_cast<Dw2Smem*>(smem_raw);
+  Dw3Smem& sm = *reinterpret_cast<Dw3Smem*>(smem_raw);
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
   const int k0 = blockIdx.x * 128, j0 = blockIdx.y * 128, sp = blockIdx.z;
-  if (tid == 0) { tc::mbar_init(&sm.bar[0], 1); tc::mbar_init(&sm.bar[1], 1); tc::fence_mbar_init(); }
-  if (w == 0) tc::tmem_alloc(&sm.tmem_slot, 128);
+  if (tid == 0) {
+    for (int i = 0; i < kDw3Slots; ++i) { tc::mbar_init(&sm.full[i], 8); tc::mbar_init(&sm.empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&sm.accf[i], 1); tc::mbar_init(&sm.acce[i], 8); }
+    tc::fence_mbar_init();
+  }
+  if (w == 0) tc::tmem_alloc(&sm.tmem_slot, 512);
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem = sm.tmem_slot;
-  const uint32_t idesc = tc::make_idesc_tf32(128, 128, 0, 0);
   const long long per = (n_blocks + splits - 1) / splits;
-  const long long b_begin = sp * per, b_end = b_begin + per < n_blocks ? b_begin + per : n_blocks;
-  const long long n_it = b_end > b_begin ? b_end - b_begin : 0;
-  float acc[64];                                   // row 32 (w & 3) + lane, columns 64 (w >> 2) ..
-#pragma unroll
-  for (int i = 0; i < 64; ++i) acc[i] = 0.f;
-  uint32_t phase = 0, pending = 0;
-  int in_group = 0;
-  const int u = tid & 127, c = tid >> 7;           // unit row of the tile, trajectory chunk
-  for (long long it = 0; it < n_it; ++it) {
-    const int s = (int)(it & 1);
-    if (pending & (1u << s)) { tc::mbar_wait(&sm.bar[s], (phase >> s) & 1u); phase ^= 1u << s; pending &= ~(1u << s); }
-    Dw2Stage& S = sm.st[s];
-    const long long blk = b_begin + it;
-    {
-      const float* src = acts + act_blk(blk, layer - 1, H, L) + (size_t)(k0 + u) * kTT + 4 * c;
-      const float4 av = *reinterpret_cast<const float4*>(src);
-      const float4 p1 = *reinterpret_cast<const float4*>(src + (size_t)H * kTT);
-      const float4 p2 = *reinterpret_cast<const float4*>(src + (size_t)2 * H * kTT);
-      const float a0[4] = {av.x, av.y, av.z, av.w}, q1[4] = {p1.x, p1.y, p1.z, p1.w}, q2[4] = {p2.x, p2.y, p2.z, p2.w};
-      float j1[4], j2[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float sg = fmaf(-a0[e], a0[e], 1.0f);
-        j1[e] = sg * q1[e];
-        j2[e] = fmaf(sg, q2[e], -2.0f * a0[e] * j1[e] * q1[e]);
-      }
-      const int off = (c * 128 + u) * 4;
-      *reinterpret_cast<float4*>(&S.Ah[0][off]) = av;
-      *reinterpret_cast<float4*>(&S.Al[0][off]) = make_float4(tc::lo_tf32(a0[0]), tc::lo_tf32(a0[1]), tc::lo_tf32(a0[2]), tc::lo_tf32(a0[3]));
-      *reinterpret_cast<float4*>(&S.Ah[1][off]) = make_float4(j1[0], j1[1], j1[2], j1[3]);
-      *reinterpret_cast<float4*>(&S.Al[1][off]) = make_float4(tc::lo_tf32(j1[0]), tc::lo_tf32(j1[1]), tc::lo_tf32(j1[2]), tc::lo_tf32(j1[3]));
-      *reinterpret_cast<float4*>(&S.Ah[2][off]) = make_float4(j2[0], j2[1], j2[2], j2[3]);
-      *reinterpret_cast<float4*>(&S.Al[2][off]) = make_float4(tc::lo_tf32(j2[0]), tc::lo_tf32(j2[1]), tc::lo_tf32(j2[2]), tc::lo_tf32(j2[3]));
-      const float* psrc = pbar + pb_blk(blk, layer, H, L) + (size_t)(j0 + u) * kTT + 4 * c;
-#pragma unroll
-      for (int jt = 0; jt < 3; ++jt) {
-        const float4 v = *reinterpret_cast<const float4*>(psrc + (size_t)jt * H * kTT);
-        *reinterpret_cast<float4*>(&S.Ph[jt][off]) = v;
-        *reinterpret_cast<float4*>(&S.Pl[jt][off]) = make_float4(tc::lo_tf32(v.x), tc::lo_tf32(v.y), tc::lo_tf32(v.z), tc::lo_tf32(v.w));
-      }
-    }
-    tc::fence_async_smem();
-    __syncthreads();
-    if (w == 0) {
+  const long long b_begin = blk0 + sp * per, b_end = blk0 + (sp * per + per < n_blocks ? sp * per + per : n_blocks);
+  const int n_it = b_end > b_begin ? (int)(b_end - b_begin) : 0;
+
+  // 384 threads x 168 registers at launch; asking for more than was allocated would make setmaxnreg.inc wait forever
+  static_assert(256 * 232 + 128 * 40 <= 168 * kDw3Threads, "setmaxnreg budget exceeds the registers allocated at launch");
+  if (w >= 8) {
+    // ---------------- MMA issue warp (warps 9..11 only donate their registers) ----------------
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    const uint32_t idesc = tc::make_idesc_tf32(128, 128, 0, 0);
+    uint32_t ph_full = 0, ph_acce = 0;
+#pragma unroll 1
+    for (int it = 0; it < (w == 8 ? n_it : 0); ++it) {
+      const int s = it % kDw3Slots, set = (it / kDw3Flush) & 1;
+      const bool first = (it % kDw3Flush) == 0;
+      tc::mbar_wait(&sm.full[s], (ph_full >> s) & 1u); ph_full ^= 1u << s;
+      if (first && it >= 2 * kDw3Flush) { tc::mbar_wait(&sm.acce[set], (ph_acce >> set) & 1u); ph_acce ^= 1u << set; }
+      __syncwarp();
       tc::fence_after_sync();
       if (tc::elect_one()) {
+        const uint32_t d = tmem + 128 * set;
 #pragma unroll
         for (int jt = 0; jt < 3; ++jt) {
-          const uint64_t ah = tc::make_desc(tc::smem_u32(S.Ah[jt]), 128 * 16, 128), al = tc::make_desc(tc::smem_u32(S.Al[jt]), 128 * 16, 128);
-          const uint64_t ph = tc::make_desc(tc::smem_u32(S.Ph[jt]), 128 * 16, 128), pl = tc::make_desc(tc::smem_u32(S.Pl[jt]), 128 * 16, 128);
-          tc::mma_tf32(tmem, ah, ph, idesc, (in_group | jt) != 0);
-          tc::mma_tf32(tmem, al, ph, idesc, true);
-          tc::mma_tf32(tmem, ah, pl, idesc, true);
+          const uint32_t ahi = tmem + kDw3ColA + 48 * s + 16 * jt, alo = ahi + 8;
+          const uint64_t ph = tc::make_desc(tc::smem_u32(sm.Ph[s][jt]), 128 * 16, 128), pl = tc::make_desc(tc::smem_u32(sm.Pl[s][jt]), 128 * 16, 128);
+          tc::mma_tf32_ts(d, ahi, ph, idesc, !(first && jt == 0));
+          tc::mma_tf32_ts(d, alo, ph, idesc, true);
+          tc::mma_tf32_ts(d, ahi, pl, idesc, true);
         }
-        tc::commit(&sm.bar[s]);
+        tc::commit(&sm.empty[s]);
+        if ((it + 1) % kDw3Flush == 0 || it + 1 == n_it) tc::commit(&sm.accf[set]);
       }
       __syncwarp();
     }
-    pending |= 1u << s;
-    ++in_group;
-    if (in_group == kDw2Flush || it == n_it - 1) {
+  } else {
+    // ---------------- staging warps ----------------
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    const bool role_p = w >= 4;
+    const int u = tid & 127;                                   // unit row of the tile (A role: TMEM lane)
+    const uint32_t tl = tmem + ((uint32_t)(32 * (w & 3)) << 16);
+    float acc[64];                                             // row 32 (w & 3) + lane, columns 64 (w >> 2) ..
 #pragma unroll
-      for (int s2 = 0; s2 < 2; ++s2)
-        if (pending & (1u << s2)) { tc::mbar_wait(&sm.bar[s2], (phase >> s2) & 1u); phase ^= 1u << s2; pending &= ~(1u << s2); }
+    for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+    uint32_t ph_empty = 0, ph_accf = 0;
+    const size_t blk_stride = role_p ? (size_t)(L - 1) * 3 * H * kTT : (size_t)L * 3 * H * kTT;
+    const int unit = (role_p ? j0 : k0) + u;
+    // SL: lane i of the quad loads rows i and i + 4 of the quad's unit group
+    const float* src0 = SL ? (role_p ? src.p : src.a) + ((size_t)(unit >> 2) * src.rows_pad + (lane & 3)) * 4
+                           : (role_p ? pbar + pb_blk(b_begin, layer, H, L) : acts + act_blk(b_begin, layer - 1, H, L)) + (size_t)unit * kTT;
+    const size_t jet = SL ? (size_t)src.rows_pad * H : (size_t)H * kTT;
+    const size_t ev_stride = role_p ? src.p_ev : src.a_ev;
+    float4 pf[kDw3PF][3][2];
+    auto load_blk = [&](float4 (&R)[3][2], int it) {
+      if (SL) {
+        const long long b = b_begin + it;
+        const long long ev = b / src.n_tiles, row0 = (b - ev * src.n_tiles) * kTT;
+        const float* sp_ = src0 + (size_t)ev * ev_stride + (size_t)row0 * 4;
+        const long long r_lo = row0 + (lane & 3);             // rows beyond the batch contribute nothing
+#pragma unroll
+        for (int jt = 0; jt < 3; ++jt) {
+          R[jt][0] = r_lo < src.rows ? __ldg(reinterpret_cast<const float4*>(sp_ + jt * jet)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          R[jt][1] = r_lo + 4 < src.rows ? __ldg(reinterpret_cast<const float4*>(sp_ + jt * jet + 16)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        return;
+      }
+      const float* sp_ = src0 + (size_t)it * blk_stride;
+#pragma unroll
+      for (int jt = 0; jt < 3; ++jt) {
+        R[jt][0] = __ldg(reinterpret_cast<const float4*>(sp_ + jt * jet));
+        R[jt][1] = __ldg(reinterpret_cast<const float4*>(sp_ + jt * jet + 4));
+      }
+    };
+    auto drain = [&](int set) {
+      tc::mbar_wait(&sm.accf[set], (ph_accf >> set) & 1u); ph_accf ^= 1u << set;
       __syncwarp();
       tc::fence_after_sync();
 #pragma unroll
       for (int c0 = 0; c0 < 64; c0 += 16) {
         float t[16];
-        tc::tmem_ld16(tmem + ((uint32_t)(32 * (w & 3)) << 16) + 64 * (w >> 2) + c0, t);
+        tc::tmem_ld16(tl + 128 * set + 64 * (w >> 2) + c0, t);
         tc::tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 16; ++i) acc[c0 + i] += t[i];
       }
       tc::fence_before_sync();
-      __syncthreads();
-      in_group = 0;
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&sm.acce[set]);
+    };
+#pragma unroll
+    for (int q = 0; q < kDw3PF; ++q)
+      if (q < n_it) load_blk(pf[q], q);
+    static_assert(kDw3PF == kDw3Slots, "the unrolled staging loop indexes the prefetch registers and the operand slots together");
+    const tc::f32x2 one2 = tc::splat2(1.0f), m1 = tc::splat2(-1.0f), two2 = tc::splat2(2.0f);
+    auto lo2x = [&](tc::f32x2 x) { return tc::fma2(x & 0xFFFFE000FFFFE000ull, m1, x); };      // x - trunc_tf32(x), two lanes
+    // one block: registers R (this thread's unit, 8 rows x 3 jets) -> operand slot s; two values per FP32 instruction
+    auto stage = [&](float4 (&R)[3][2], int it, int s) {
+      using namespace tc;
+      if (SL) {
+#pragma unroll
+        for (int jt = 0; jt < 3; ++jt) { R[jt][0] = quad_transpose(R[jt][0], lane & 3); R[jt][1] = quad_transpose(R[jt][1], lane & 3); }
+      }
+      if (it >= kDw3Slots) { mbar_wait(&sm.empty[s], (ph_empty >> s) & 1u); ph_empty ^= 1u << s; }
+      if (!role_p) {
+        __syncwarp();
+        fence_after_sync();
+        float v0[16], v1[16], v2[16];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float4 A4 = R[0][e >> 1], P4 = R[1][e >> 1], Q4 = R[2][e >> 1];
+          const f32x2 av = (e & 1) ? pack2(A4.z, A4.w) : pack2(A4.x, A4.y);
+          const f32x2 p1 = (e & 1) ? pack2(P4.z, P4.w) : pack2(P4.x, P4.y);
+          const f32x2 p2 = (e & 1) ? pack2(Q4.z, Q4.w) : pack2(Q4.x, Q4.y);
+          const f32x2 na = mul2(av, m1);
+          const f32x2 sg = fma2(na, av, one2);                                  // 1 - a^2
+          const f32x2 j1 = mul2(sg, p1);                                        // a' = (1 - a^2) p'
+          const f32x2 j2 = fma2(sg, p2, mul2(mul2(mul2(na, two2), j1), p1));    // a'' = (1 - a^2) p'' - 2 a a' p'
+          const f32x2 l0 = lo2x(av), l1 = lo2x(j1), l2 = lo2x(j2);
+          unpack2(av, v0[2 * e], v0[2 * e + 1]); unpack2(l0, v0[8 + 2 * e], v0[9 + 2 * e]);
+          unpack2(j1, v1[2 * e], v1[2 * e + 1]); unpack2(l1, v1[8 + 2 * e], v1[9 + 2 * e]);
+          unpack2(j2, v2[2 * e], v2[2 * e + 1]); unpack2(l2, v2[8 + 2 * e], v2[9 + 2 * e]);
+        }
+        const uint32_t col = tl + kDw3ColA + 48 * s;
+        tmem_st16(col, v0);
+        tmem_st16(col + 16, v1);
+        tmem_st16(col + 32, v2);
+        tmem_st_wait();
+        fence_before_sync();
+      } else {
+#pragma unroll
+        for (int jt = 0; jt < 3; ++jt)
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const float4 v = R[jt][c];
+            const int off = (c * 128 + u) * 4;
+            const f32x2 lxy = lo2x(pack2(v.x, v.y)), lzw = lo2x(pack2(v.z, v.w));
+            *reinterpret_cast<float4*>(&sm.Ph[s][jt][off]) = v;
+            *reinterpret_cast<float4*>(&sm.Pl[s][jt][off]) = make_float4(lo2(lxy), hi2(lxy), lo2(lzw), hi2(lzw));
+          }
+        fence_async_smem();
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.full[s]);
+      // chain c = it / kDw3Flush is drained a few blocks into the next one, when its MMAs have long finished
+      if (it >= kDw3Flush && (it % kDw3Flush) == kDw3Slots - 1) drain(((it / kDw3Flush) - 1) & 1);
+    };
+#pragma unroll 1
+    for (int it0 = 0; it0 < n_it; it0 += kDw3PF) {
+#pragma unroll
+      for (int q = 0; q < kDw3PF; ++q) {                       // static register / slot indices: no rotation moves
+        const int it = it0 + q;
+        if (it < n_it) {
+          float4 R[3][2];
+#pragma unroll
+          for (int jt = 0; jt < 3; ++jt) { R[jt][0] = pf[q][jt][0]; R[jt][1] = pf[q][jt][1]; }
+          if (it + kDw3PF < n_it) load_blk(pf[q], it + kDw3PF);
+          stage(R, it, q);
+        }
+      }
     }
-  }
-  {
+    if (n_it > 0) {
+      const int last = (n_it - 1) / kDw3Flush;                 // chains not drained inside the loop: `last`, and last-1 if the
+      if (last >= 1 && (n_it - 1) % kDw3Flush < kDw3Slots - 1) drain((last - 1) & 1);   // loop ended before its drain point
+      drain(last & 1);
+    }
     const int r = 32 * (w & 3) + lane;
     float* out = part + ((size_t)sp * H + (k0 + r)) * H + j0 + 64 * (w >> 2);
 #pragma unroll
-    for (int i = 0; i < 64; i += 4) *reinterpret_cast<float4*>(out + i) = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
+    for (int i = 0; i < 64; i += 4) {
+      float4 o = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
+      if (accumulate) {                                        // a later chunk of evaluations (same CTA <-> same slots, launches ordered)
+        const float4 p = *reinterpret_cast<const float4*>(out + i);
+        o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+      }
+      *reinterpret_cast<float4*>(out + i) = o;
+    }
   }
   tc::fence_before_sync();
   __syncthreads();
-  if (w == 0) tc::tmem_dealloc(tmem, 128);
+  if (w == 0) tc::tmem_dealloc(tmem, 512);
 }
 
 // theta_bar[w(l) + i] (+)= sum_splits part[s][i]
@@ -803,6 +931,48 @@ __global__ void mlp_small_reduce_kernel(const float* __restrict__ gsmall, float*
   theta_bar[p] = (float)s;
 }
 
+// ---- weight-gradient GEMM overlapped with the adjoint sweep (activation-checkpoint path) ----------------------------------
+// The sweep is a dependent chain of launches that keeps (rows / 128) x (H / 64) SMs busy; the rest of the GPU contracts the
+// evaluations the sweep has already finished, on a second stream, in groups of kDwGroup evaluations.
+constexpr int kDwGroup = 4;
+struct SideStream { cudaStream_t s = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
+static SideStream* side_stream() {
+  static SideStream side[64];
+  static std::mutex mu;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lock(mu);
+  SideStream& ss = side[dev];
+  if (ss.s == nullptr) {
+    if (cudaStreamCreateWithFlags(&ss.s, cudaStreamNonBlocking) != cudaSuccess) { ss.s = nullptr; return nullptr; }
+    if (cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+  }
+  return &ss;
+}
+struct DwOverlapCtx {
+  cudaStream_t main; SideStream* side; float* part; const float* actS; const float* pbar;
+  int H, L, splits, launched; long long rows, n_tiles;
+};
+static int dw_overlap_launch(void* vctx, int ev_lo, int ev_hi) {
+  DwOverlapCtx& c = *static_cast<DwOverlapCtx*>(vctx);
+  cudaError_t e = cudaEventRecord(c.side->fork, c.main);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(c.side->s, c.side->fork, 0);
+  if (e != cudaSuccess) return (int)e;
+  const long long rows_pad = (c.rows + 127) / 128 * 128;
+  const size_t sbuf = al256(3 * (size_t)rows_pad * c.H * 4) / 4;
+  const dim3 gg(c.H / 128, c.H / 128, c.splits);
+  for (int l = 1; l < c.L; ++l) {
+    DwSrc src{c.actS + (size_t)(l - 1) * sbuf, c.pbar + (size_t)(l - 1) * sbuf, (size_t)c.L * sbuf, (size_t)(c.L - 1) * sbuf, rows_pad, c.rows,
+              (int)c.n_tiles};
+    mlp_dw_gemm_ts_kernel<true><<<gg, kDw3Threads, sizeof(Dw3Smem) + 1024, c.side->s>>>(
+        nullptr, nullptr, c.part + (size_t)(l - 1) * c.splits * c.H * c.H, c.H, c.L, l, (long long)ev_lo * c.n_tiles,
+        (long long)(ev_hi - ev_lo) * c.n_tiles, c.splits, src, c.launched);
+  }
+  c.launched = 1;
+  return (int)cudaGetLastError();
+}
+
 static int check_shape(int64_t B, int jets, int stride, int H, int L, int n_steps) {
   if (B < 0 || n_steps <= 0 || jets < 1 || jets > 3) return OFDFT_EINVAL;
   if (stride < (jets == 3 ? 3 : jets)) return OFDFT_EINVAL;
@@ -818,6 +988,11 @@ using namespace ofdft::mlp;
 
 extern "C" size_t ofdft_cnf_mlp1d_ckpt_bytes(int64_t B, int32_t n_steps) {
   return (size_t)n_steps * 4 * 2 * (size_t)B * sizeof(float);
+}
+extern "C" size_t ofdft_cnf_mlp1d_act_ckpt_bytes(int64_t B, int32_t H, int32_t n_layers, int32_t n_steps) {
+  if (B <= 0 || H < 64 || H > 512 || H % 64 || n_layers < 2 || n_layers > kMaxL || n_steps <= 0) return 0;
+  const ActLayout AL(B, H, n_layers, n_steps);
+  return AL.ok && H % 128 == 0 ? AL.total : 0;
 }
 extern "C" size_t ofdft_cnf_mlp1d_scratch_bytes(int64_t B, int32_t H, int32_t n_layers, int32_t n_steps) {
   if (B <= 0 || H <= 0 || n_layers < 2 || n_layers > kMaxL || n_steps <= 0) return 256;
@@ -836,6 +1011,11 @@ extern "C" int ofdft_cnf_mlp1d_fwd(void* stream, const float* theta, const float
   // default: per-layer tcgen05 3xTF32 GEMM launches (mlp1d_tc.cu); OFDFT_PATH_FFMA: the fused FP32 kernel of this file
   const bool fwd_tc = !(path & OFDFT_PATH_FFMA);
   if (scratch_bytes < (fwd_tc ? SL.fwd_end : SL.wtc)) return OFDFT_ESCRATCH;
+  const bool act = (path & OFDFT_PATH_ACT_CKPT) != 0;
+  const ActLayout AL(B, H, n_layers, n_steps);
+  if (act && H % 128) return OFDFT_EUNSUPPORTED;
+  if (act && (!fwd_tc || !ckpt || jets != 3 || (path & OFDFT_PATH_FFMA_DW))) return OFDFT_EINVAL;
+  if (act && !AL.ok) return OFDFT_EUNSUPPORTED;
   cudaStream_t st = (cudaStream_t)stream;
   float* Wc = (float*)((char*)scratch + SL.wc);
   float* WTc = (float*)((char*)scratch + SL.wtc);
@@ -851,7 +1031,7 @@ extern "C" int ofdft_cnf_mlp1d_fwd(void* stream, const float* theta, const float
     float* S1 = (float*)((char*)scratch + SL.fwd_s + sbuf);
     float* state = (float*)((char*)scratch + SL.fwd_state);
     return launch_mlp_fwd_tc(stream, theta, WTc, WTlo, y_in, y_out, ckpt, S0, S1, state, B, jets, stride, H, n_layers, n_steps, t0, t1,
-                             y0sign);
+                             y0sign, act ? ckpt + AL.s / 4 : nullptr);
   }
   const size_t smem = smem_bytes(H);
   e = cudaFuncSetAttribute(mlp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -918,6 +1098,11 @@ extern "C" int ofdft_cnf_mlp1d_bwd(void* stream, const float* theta, const float
   float* gsmall = (float*)(sc + SL.gsmall); float* part = (float*)(sc + SL.part);
   // default: adjoint sweep as per-layer tcgen05 GEMM launches (mlp1d_tc.cu); OFDFT_PATH_FFMA: fused FP32 sweep
   const bool bwd_tc = !(path & OFDFT_PATH_FFMA);
+  const bool act = (path & OFDFT_PATH_ACT_CKPT) != 0;
+  const ActLayout AL(B, H, L, n_steps);
+  if (act && H % 128) return OFDFT_EUNSUPPORTED;
+  if (act && (!bwd_tc || (path & OFDFT_PATH_FFMA_DW))) return OFDFT_EINVAL;
+  if (act && !AL.ok) return OFDFT_EUNSUPPORTED;
   float* WTlo = (float*)(sc + SL.wtlo); float* Wclo = (float*)(sc + SL.wclo);
   mlp_prep_kernel<<<256, 256, 0, st>>>(theta, Wc, WTc, H, L, bwd_tc ? WTlo : nullptr, bwd_tc ? Wclo : nullptr);
   cudaError_t e = cudaGetLastError();
@@ -940,6 +1125,21 @@ extern "C" int ofdft_cnf_mlp1d_bwd(void* stream, const float* theta, const float
     a.B = B; a.row_begin = r0; a.rows = rows; a.jets = 3; a.stride = stride; a.H = H; a.L = L; a.n_steps = n_steps;
     a.t0 = t0; a.t1 = t1; a.y0 = y0sign;
     int grid = (int)(n_tiles < sms ? n_tiles : sms);
+    // activation-checkpoint path: the weight-gradient GEMM runs beside the sweep on the SMs the sweep leaves idle
+    DwOverlapCtx ov{};
+    MlpDwHook hook{};
+    if (act) {
+      const int gemm_ctas = (int)((rows + 127) / 128) * (H / 64), tiles = (H / 128) * (H / 128);
+      int ov_splits = (sms - gemm_ctas) / tiles;
+      if (ov_splits > kDwSplits / (L - 1)) ov_splits = kDwSplits / (L - 1);
+      SideStream* side = ov_splits >= 1 ? side_stream() : nullptr;
+      if (side != nullptr) {
+        e = cudaFuncSetAttribute(mlp_dw_gemm_ts_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Dw3Smem) + 1024);
+        if (e != cudaSuccess) return (int)e;
+        ov = DwOverlapCtx{st, side, part, ckpt + AL.s / 4, a.pbar, H, L, ov_splits, 0, rows, n_tiles};
+        hook = MlpDwHook{kDwGroup, &ov, dw_overlap_launch};
+      }
+    }
     if (bwd_tc) {
       if (chunk_idx == 0) {
         const int rcp = launch_mlp_prep_tc(stream, theta, WTc, WTlo, (float*)(sc + SL.wbi), Wclo, H, L);
@@ -951,7 +1151,8 @@ extern "C" int ofdft_cnf_mlp1d_bwd(void* stream, const float* theta, const float
       for (int l = 0; l < L; ++l) S[l] = (float*)(sc + SL.bwd_s + (size_t)l * sb);
       const int rc2 = launch_mlp_bwd_sweep_tc(stream, theta, (float*)(sc + SL.wbi), Wclo, WTc, WTlo, ckpt, ybar1, ybar0, S, (float*)(sc + SL.bwd_pb),
                                               (float*)(sc + SL.bwd_pb + sb), (float*)(sc + SL.bwd_bst), (float*)(sc + SL.bwd_xpart),
-                                              gsmall, a.acts, a.pbar, B, r0, rows, stride, H, L, n_steps, t0, t1, y0sign);
+                                              gsmall, a.acts, a.pbar, B, r0, rows, stride, H, L, n_steps, t0, t1, y0sign,
+                                              act ? ckpt + AL.s / 4 : nullptr, hook.launch != nullptr ? &hook : nullptr);
       if (rc2) return rc2;
       grid = (int)n_tiles;                       // small-gradient slots: one per 8-row tile (<= 256 per chunk)
     } else {
@@ -965,14 +1166,31 @@ extern "C" int ofdft_cnf_mlp1d_bwd(void* stream, const float* theta, const float
     if (dw_tc) {
       e = cudaFuncSetAttribute(mlp_dw_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DwSmem) + 1024);
       if (e != cudaSuccess) return (int)e;
-      e = cudaFuncSetAttribute(mlp_dw_gemm_tc128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Dw2Smem) + 1024);
+      e = cudaFuncSetAttribute(mlp_dw_gemm_ts_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Dw3Smem) + 1024);
+      if (e != cudaSuccess) return (int)e;
+      e = cudaFuncSetAttribute(mlp_dw_gemm_ts_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Dw3Smem) + 1024);
       if (e != cudaSuccess) return (int)e;
     }
-    for (int l = 1; l < L; ++l) {
+    if (hook.launch != nullptr) {                 // every evaluation has been contracted beside the sweep: join and reduce
+      e = cudaEventRecord(ov.side->join, ov.side->s);
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(st, ov.side->join, 0);
+      if (e != cudaSuccess) return (int)e;
+      for (int l = 1; l < L; ++l)
+        mlp_dw_reduce_kernel<<<(H * H + 255) / 256, 256, 0, st>>>(part + (size_t)(l - 1) * ov.splits * H * H, theta_bar, TL.w(l), H * H,
+                                                                   ov.splits, chunk_idx > 0);
+    }
+    for (int l = 1; l < L && hook.launch == nullptr; ++l) {
       if (dw_tc && H % 128 == 0) {
-        dim3 gg(H / 128, H / 128, kDwSplits);
-        mlp_dw_gemm_tc128_kernel<<<gg, 256, sizeof(Dw2Smem) + 1024, st>>>(a.acts, a.pbar, part, H, L, l, n_blocks, kDwSplits);
-        mlp_dw_reduce_kernel<<<(H * H + 255) / 256, 256, 0, st>>>(part, theta_bar, TL.w(l), H * H, kDwSplits, chunk_idx > 0);
+        dim3 gg(H / 128, H / 128, kDw3Splits);
+        if (act) {      // operands straight from the per-evaluation layer buffers (activations: forward; cotangents: this sweep)
+          const size_t sbuf = al256(3 * (size_t)((rows + 127) / 128 * 128) * H * 4) / 4;
+          DwSrc src{ckpt + AL.s / 4 + (size_t)(l - 1) * sbuf, a.pbar + (size_t)(l - 1) * sbuf, (size_t)L * sbuf, (size_t)(L - 1) * sbuf,
+                    (rows + 127) / 128 * 128, rows, (int)n_tiles};
+          mlp_dw_gemm_ts_kernel<true><<<gg, kDw3Threads, sizeof(Dw3Smem) + 1024, st>>>(nullptr, nullptr, part, H, L, l, 0, n_blocks, kDw3Splits, src, 0);
+        } else {
+          mlp_dw_gemm_ts_kernel<false><<<gg, kDw3Threads, sizeof(Dw3Smem) + 1024, st>>>(a.acts, a.pbar, part, H, L, l, 0, n_blocks, kDw3Splits, DwSrc{}, 0);
+        }
+        mlp_dw_reduce_kernel<<<(H * H + 255) / 256, 256, 0, st>>>(part, theta_bar, TL.w(l), H * H, kDw3Splits, chunk_idx > 0);
       } else if (dw_tc) {
         dim3 gg(H / 64, H / 64, kDwTcSplits);
         mlp_dw_gemm_tc_kernel<<<gg, 256, sizeof(DwSmem) + 1024, st>>>(a.acts, a.pbar, part, H, L, l, n_blocks, kDwTcSplits);

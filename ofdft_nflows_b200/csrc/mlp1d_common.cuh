@@ -38,6 +38,19 @@ constexpr long long kChunkRows = 2048;     // backward row chunk (bounds the HBM
 constexpr int kDwSplits = 16;
 inline size_t al256(size_t v) { return (v + 255) & ~(size_t)255; }
 
+// Activation checkpoint of the tensor-core path (OFDFT_PATH_ACT_CKPT; one backward row chunk, i.e. B <= kChunkRows, H a
+// multiple of 128): appended to the stage checkpoint, per (evaluation, layer) buffers [jet][H/4][rows padded to 128][4] -- the
+// layout the layer GEMMs read and write, and the one the weight-gradient GEMM contracts in place (no HBM blocks).
+struct ActLayout {
+  size_t s, total; bool ok;
+  ActLayout(long long B, int H, int L, int n_steps) {
+    ok = B > 0 && B <= kChunkRows;
+    const size_t rows_pad = (size_t)((B + 127) / 128 * 128);
+    s = al256((size_t)n_steps * 4 * 2 * (size_t)B * 4);
+    total = s + (size_t)n_steps * 4 * L * al256(3 * rows_pad * H * 4);
+  }
+};
+
 struct ScratchLayout {
   size_t wc, wtc, wtlo, wclo, wbi, fwd_s, fwd_state, fwd_end, bwd_s, bwd_pb, bwd_bst, bwd_xpart, gsmall, part, acts, pbar, total;
   ScratchLayout(long long B, int H, int L, int n_steps) {
@@ -64,7 +77,11 @@ struct ScratchLayout {
     gsmall = o; o += al256((size_t)256 * ThetaLayout(H, L).n_small() * 4);
     part = o; o += al256((size_t)kDwSplits * H * H * 4);
     acts = o; o += al256((size_t)n_blocks * L * 3 * H * kTT * 4);
-    pbar = o; o += al256((size_t)n_blocks * (L - 1) * 3 * H * kTT * 4);
+    {   // HBM blocks, or (activation-checkpoint sweep) per-evaluation cotangent layer buffers padded to 128 rows
+      const size_t blocks = al256((size_t)n_blocks * (L - 1) * 3 * H * kTT * 4);
+      const size_t bufs = (size_t)n_steps * 4 * (L - 1) * al256(3 * rows_pad_c * H * 4);
+      pbar = o; o += blocks > bufs ? blocks : bufs;
+    }
     total = o;
   }
 };
@@ -76,7 +93,11 @@ struct ScratchLayout {
 int launch_mlp_prep_tc(void* stream, const float* theta, float* Wf, float* Wf_lo, float* Wb, float* Wb_lo, int H, int L);
 int launch_mlp_fwd_tc(void* stream, const float* theta, const float* WTc, const float* WTlo, const float* y_in, float* y_out, float* ckpt,
                       float* S0, float* S1, float* state, long long B, int jets, int stride, int H, int L, int n_steps,
-                      float t0, float t1, float y0sign);
+                      float t0, float t1, float y0sign, float* actS);
+
+// called by the sweep after the launches of evaluation `ev_lo` (evaluations run downwards) whenever ev_lo is a multiple of
+// `group`: the cotangents of evaluations [ev_lo, ev_hi) are complete on the sweep's stream
+struct MlpDwHook { int group; void* ctx; int (*launch)(void* ctx, int ev_lo, int ev_hi); };
 
 // tensor-core adjoint sweep of one row chunk (mlp1d_tc.cu): fills the HBM blocks the weight-gradient GEMM contracts and
 // the per-CTA small-gradient partials; returns a cudaError_t / OFDFT_E* code
@@ -84,7 +105,7 @@ int launch_mlp_bwd_sweep_tc(void* stream, const float* theta, const float* Wc, c
                             const float* WTlo, const float* ckpt, const float* ybar1, float* ybar0, float* const* S,
                             float* Pb0, float* Pb1, float* bst, float* xpart, float* gsmall, float* acts, float* pbar,
                             long long Bglob, long long r0, long long rows, int stride, int H, int L, int n_steps, float t0,
-                            float t1, float y0sign);
+                            float t1, float y0sign, const float* actS, const MlpDwHook* dw_hook);
 
 }  // namespace mlp
 }  // namespace ofdft

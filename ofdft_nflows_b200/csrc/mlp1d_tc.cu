@@ -41,7 +41,10 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
 }
 
 constexpr int kGemmKC = 16;                       // k per pipeline stage (4 chunks of 4)
-constexpr int kGemmGroup = 16;                    // stages per TMEM accumulation chain (256 k, 96 MMAs per jet); measured max
+#ifndef OFDFT_GEMM_GROUP
+#define OFDFT_GEMM_GROUP 16
+#endif
+constexpr int kGemmGroup = OFDFT_GEMM_GROUP;      // stages per TMEM accumulation chain (256 k, 96 MMAs per jet); measured max
                                                   // state error vs the float64 oracle (3x512): 6e-7 / 1.1e-6 / 1.7e-6 for 8 / 16 / 32
 constexpr int kGemmSlots = 3;                     // activation-operand ring in tensor memory
 constexpr int kGemmRaw = 4;                       // shared-memory ring fed by TMA bulk copies: raw activation jets + weight stage
@@ -330,11 +333,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) mlp_layer_gemm_tc_kernel(cons
               *reinterpret_cast<float4*>(d + jet_stride) = make_float4(q1[i], q1[i + 1], q1[i + 2], q1[i + 3]);
               *reinterpret_cast<float4*>(d + 2 * jet_stride) = make_float4(q2[i], q2[i + 1], q2[i + 2], q2[i + 3]);
             }
+            if (blk != nullptr) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              blk[(size_t)(i + e) * kTT] = q0[i + e];
-              blk[(size_t)(g.H + i + e) * kTT] = q1[i + e];
-              blk[(size_t)(2 * g.H + i + e) * kTT] = q2[i + e];
+              for (int e = 0; e < 4; ++e) {
+                blk[(size_t)(i + e) * kTT] = q0[i + e];
+                blk[(size_t)(g.H + i + e) * kTT] = q1[i + e];
+                blk[(size_t)(2 * g.H + i + e) * kTT] = q2[i + e];
+              }
             }
           }
         }
@@ -392,6 +397,7 @@ struct GlueArgs {
   const float* theta; const float* Slast; float* S0; float* state;
   const float* y_in; float* y_out; float* ckpt;
   long long B, rows_pad; int stride, H, L, n_steps, eval; float t0, t1, y0;
+  float* acts0; size_t act_tile_stride;           // activation checkpoint: HBM blocks of layer 0 of evaluation eval+1 (or null)
 };
 
 // Thread mapping of the row kernels: one CTA per tile of 8 trajectories, thread = (row t = tid & 7, unit-group slot
@@ -510,7 +516,8 @@ __global__ void __launch_bounds__(256) mlp_glue_tc_kernel(const GlueArgs g) {
   const int stage = ne & 3;
   const float cs = stage == 0 ? 0.f : (stage == 3 ? h : 0.5f * h);
   const float tp = g.y0 * (g.t0 + h * (float)(ne >> 2) + cs);
-  if (!valid) return;
+  if (!valid && g.acts0 == nullptr) return;
+  float* blk = g.acts0 != nullptr ? g.acts0 + (size_t)blockIdx.x * g.act_tile_stride + t : nullptr;
   for (int grp = gs; grp < H / 4; grp += 32) {
     const int k = 4 * grp;
     float* d0 = g.S0 + sbuf_off(grp, row, g.rows_pad);
@@ -519,7 +526,13 @@ __global__ void __launch_bounds__(256) mlp_glue_tc_kernel(const GlueArgs g) {
     for (int e = 0; e < 4; ++e) {
       wx[e] = g.theta[TL.w(0) + H + k + e];
       a[e] = tanh_f(fmaf(wx[e], xst, fmaf(tp, g.theta[TL.w(0) + k + e], g.theta[TL.b(0) + k + e])));
+      if (blk != nullptr) {                       // rows beyond B repeat row B-1 (finite; their cotangents are zero)
+        blk[(size_t)(k + e) * kTT] = a[e];
+        blk[(size_t)(H + k + e) * kTT] = wx[e];
+        blk[(size_t)(2 * H + k + e) * kTT] = 0.f;
+      }
     }
+    if (!valid) continue;
     *reinterpret_cast<float4*>(d0) = make_float4(a[0], a[1], a[2], a[3]);
     if (NJ >= 2) *reinterpret_cast<float4*>(d0 + jet_stride) = make_float4(wx[0], wx[1], wx[2], wx[3]);
     if (NJ == 3) *reinterpret_cast<float4*>(d0 + 2 * jet_stride) = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -529,30 +542,46 @@ __global__ void __launch_bounds__(256) mlp_glue_tc_kernel(const GlueArgs g) {
 template <int NJ>
 static int run_fwd_tc(cudaStream_t st, const float* theta, const float* WTc, const float* WTlo, const float* y_in, float* y_out, float* ckpt,
                       float* S0, float* S1, float* state, long long B, int stride, int H, int L, int n_steps, float t0, float t1,
-                      float y0sign) {
+                      float y0sign, float* actS) {
   const long long rows_pad = (B + 127) / 128 * 128;
   const ThetaLayout TL(H, L);
   cudaError_t e = cudaFuncSetAttribute(mlp_layer_gemm_tc_kernel<NJ, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)sizeof(GemmSmem) + 1024);
   if (e != cudaSuccess) return (int)e;
-  // rows beyond B of both buffers are read by the last tile: keep them finite
-  e = cudaMemsetAsync(S0, 0, 3 * (size_t)rows_pad * H * sizeof(float), st);
-  if (e != cudaSuccess) return (int)e;
-  e = cudaMemsetAsync(S1, 0, 3 * (size_t)rows_pad * H * sizeof(float), st);
-  if (e != cudaSuccess) return (int)e;
-  GlueArgs ga{theta, nullptr, S0, state, y_in, y_out, ckpt, B, rows_pad, stride, H, L, n_steps, -1, t0, t1, y0sign};
-  const int glue_grid = (int)((B + 7) / 8);
+  // activation checkpoint (NJ == 3): every evaluation keeps its own layer buffers (actS: [eval][layer]); the adjoint then
+  // skips the recomputation of the hidden layers and the weight-gradient GEMM contracts these buffers in place
+  const size_t sbuf = al256(3 * (size_t)rows_pad * H * sizeof(float)) / sizeof(float);
+  const long long n_tiles = (B + 7) / 8;
+  const size_t act_tile = (size_t)L * 3 * H * kTT;
+  auto sck = [&](int ev, int l) { return actS + ((size_t)ev * L + l) * sbuf; };
+  // rows beyond B of the layer buffers are read by the last tile: keep them finite
+  if (actS != nullptr) {
+    if (B % 128 != 0 && (e = cudaMemsetAsync(actS, 0, (size_t)4 * n_steps * L * sbuf * sizeof(float), st)) != cudaSuccess) return (int)e;
+  } else {
+    e = cudaMemsetAsync(S0, 0, 3 * (size_t)rows_pad * H * sizeof(float), st);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMemsetAsync(S1, 0, 3 * (size_t)rows_pad * H * sizeof(float), st);
+    if (e != cudaSuccess) return (int)e;
+  }
+  GlueArgs ga{theta, nullptr, S0, state, y_in, y_out, ckpt, B, rows_pad, stride, H, L, n_steps, -1, t0, t1, y0sign, nullptr, act_tile};
+  const int glue_grid = (int)n_tiles;
   const dim3 gemm_grid((unsigned)(rows_pad / 128), (unsigned)(H / 64));
   float* bufs[2] = {S0, S1};
   for (int ev = -1; ev < 4 * n_steps; ++ev) {
     // the last hidden layer of evaluation ev ended in bufs[(L-1) & 1]
     ga.eval = ev; ga.Slast = bufs[(L - 1) & 1];
+    const bool more = ev + 1 < 4 * n_steps;
+    if (actS != nullptr) {
+      ga.Slast = ev >= 0 ? sck(ev, L - 1) : nullptr;
+      ga.S0 = more ? sck(ev + 1, 0) : nullptr;
+    }
     if ((e = launch_pdl(mlp_glue_tc_kernel<NJ>, dim3(glue_grid), dim3(256), 0, st, ga)) != cudaSuccess) return (int)e;
-    if (ev + 1 == 4 * n_steps) break;
+    if (!more) break;
     for (int l = 1; l < L; ++l) {
       GemmArgs gg{};
       gg.Sin = bufs[(l - 1) & 1]; gg.Sout = bufs[l & 1]; gg.WT = WTc + (size_t)(l - 1) * H * H; gg.WTlo = WTlo + (size_t)(l - 1) * H * H;
       gg.bias = theta + TL.b(l); gg.B = B; gg.rows_pad = rows_pad; gg.H = H;
+      if (actS != nullptr) { gg.Sin = sck(ev + 1, l - 1); gg.Sout = sck(ev + 1, l); }
       if ((e = launch_pdl(mlp_layer_gemm_tc_kernel<NJ, 0>, gemm_grid, dim3(kGemmThreads), sizeof(GemmSmem) + 1024, st, gg)) != cudaSuccess) return (int)e;
     }
   }
@@ -579,7 +608,30 @@ struct SweepArgs {
   int e_done, e_next;      // tail: stage just finished (-1: initialise), stage to prepare (-1: none -> write ybar0)
   int e;                   // head: stage being reversed
   float t0, t1, y0;
+  int fused_tail;          // head: do the tail's row bookkeeping of stage e_done first (activation-checkpoint sweep)
 };
+
+// RK4 adjoint bookkeeping of the stage just finished (threads 0..7 of a tile: one row each)
+__device__ __forceinline__ void sweep_tail_rows(const SweepArgs& g, long long row, bool valid) {
+  float* st = g.bst + row * 8;
+  if (g.e_done < 0) {
+    const float* src = g.ybar1 + (g.r0 + (valid ? row : 0)) * g.stride;
+    st[0] = valid ? src[0] : 0.f; st[1] = valid ? src[1] : 0.f; st[2] = valid ? src[2] : 0.f;
+    st[3] = st[4] = st[5] = st[6] = st[7] = 0.f;
+  } else {
+    float ysx = 0.f;
+    for (int nt = 0; nt < g.n_xpart; ++nt) ysx += g.xpart[(size_t)nt * g.rows_pad + row];
+    const float yss = st[7];
+    float sumx = st[5] + ysx, sums = st[6] + yss;
+    st[3] = ysx; st[4] = yss;
+    if ((g.e_done & 3) == 0) { st[0] += sumx; st[2] += sums; sumx = 0.f; sums = 0.f; }
+    st[5] = sumx; st[6] = sums;
+  }
+  if (g.e_next < 0 && valid && g.ybar0 != nullptr) {
+    float* dst = g.ybar0 + (g.r0 + row) * g.stride;
+    dst[0] = st[0]; dst[1] = st[1]; dst[2] = st[2];
+  }
+}
 
 __global__ void __launch_bounds__(256) mlp_sweep_tail_kernel(const SweepArgs g) {
   pdl_trigger();
@@ -591,27 +643,8 @@ __global__ void __launch_bounds__(256) mlp_sweep_tail_kernel(const SweepArgs g) 
   const ThetaLayout TL(H, g.L);
   const size_t jet_stride = (size_t)g.rows_pad * H;
   const float h = (g.t1 - g.t0) / (float)g.n_steps;
-  if (tid < 8) {
-    float* st = g.bst + row * 8;
-    if (g.e_done < 0) {
-      const float* src = g.ybar1 + (g.r0 + (valid ? row : 0)) * g.stride;
-      st[0] = valid ? src[0] : 0.f; st[1] = valid ? src[1] : 0.f; st[2] = valid ? src[2] : 0.f;
-      st[3] = st[4] = st[5] = st[6] = st[7] = 0.f;
-    } else {
-      float ysx = 0.f;
-      for (int nt = 0; nt < g.n_xpart; ++nt) ysx += g.xpart[(size_t)nt * g.rows_pad + row];
-      const float yss = st[7];
-      float sumx = st[5] + ysx, sums = st[6] + yss;
-      st[3] = ysx; st[4] = yss;
-      if ((g.e_done & 3) == 0) { st[0] += sumx; st[2] += sums; sumx = 0.f; sums = 0.f; }
-      st[5] = sumx; st[6] = sums;
-    }
-    if (g.e_next < 0 && valid && g.ybar0 != nullptr) {
-      float* dst = g.ybar0 + (g.r0 + row) * g.stride;
-      dst[0] = st[0]; dst[1] = st[1]; dst[2] = st[2];
-    }
-  }
-  if (g.e_next < 0) return;
+  if (tid < 8) sweep_tail_rows(g, row, valid);
+  if (g.e_next < 0 || g.S0 == nullptr) return;
   // first layer of stage e_next: (a, p' = w_x, p'' = 0) -> layer buffer 0 and the HBM block of layer 0
   const int stage = g.e_next & 3;
   const float cs = stage == 0 ? 0.f : (stage == 3 ? h : 0.5f * h);
@@ -652,6 +685,10 @@ __global__ void __launch_bounds__(256) mlp_sweep_head_kernel(const SweepArgs g) 
   const size_t jet_stride = (size_t)g.rows_pad * H;
   const float h = (g.t1 - g.t0) / (float)g.n_steps;
   const int stage = g.e & 3;
+  if (g.fused_tail) {                              // uniform per launch
+    if (tid < 8) sweep_tail_rows(g, row, valid);
+    __syncthreads();
+  }
   const float* st = g.bst + row * 8;
   const float ca = (stage == 0 || stage == 3) ? h * (1.0f / 6.0f) : h * (1.0f / 3.0f);
   const float cp = stage == 3 ? 0.f : (stage == 2 ? h : 0.5f * h);
@@ -662,7 +699,7 @@ __global__ void __launch_bounds__(256) mlp_sweep_head_kernel(const SweepArgs g) 
   // dx = y0 h ; dlogp = -y0 h' ; ds = -y0 (h' s + h'')
   const float hb0 = valid ? g.y0 * kx : 0.f, hb1 = valid ? -g.y0 * (kl + sst * ks) : 0.f, hb2 = valid ? -g.y0 * ks : 0.f;
   float h1 = 0.f;
-  float* blk = g.pbar_last + (size_t)blockIdx.x * g.pb_tile_stride + t;
+  float* blk = g.pbar_last != nullptr ? g.pbar_last + (size_t)blockIdx.x * g.pb_tile_stride + t : nullptr;
   float* gsl = g.gsm + (size_t)blockIdx.x * TL.n_small();
   for (int grp = gs; grp < H / 4; grp += 32) {
     const int k = 4 * grp;
@@ -683,9 +720,11 @@ __global__ void __launch_bounds__(256) mlp_sweep_head_kernel(const SweepArgs g) 
       q2[e] = a2b * sg;
       q1[e] = sg * fmaf(-4.0f * av[e] * p1[e], a2b, a1b);
       q0[e] = sg * (ab - 2.0f * av[e] * p1[e] * a1b + a2b * fmaf(-2.0f * av[e], p2[e], -2.0f * fmaf(-3.0f * av[e], av[e], 1.0f) * p1[e] * p1[e]));
-      blk[(size_t)(k + e) * kTT] = q0[e];
-      blk[(size_t)(H + k + e) * kTT] = q1[e];
-      blk[(size_t)(2 * H + k + e) * kTT] = q2[e];
+      if (blk != nullptr) {
+        blk[(size_t)(k + e) * kTT] = q0[e];
+        blk[(size_t)(H + k + e) * kTT] = q1[e];
+        blk[(size_t)(2 * H + k + e) * kTT] = q2[e];
+      }
       // last-layer kernel and last hidden bias gradients: sums over the 8 rows of the tile, one writer per unit
       gwv[e] = tile_rows_sum(av[e] * hb0 + a1 * hb1 + a2 * hb2);
       gbv[e] = tile_rows_sum(q0[e]);
@@ -722,7 +761,7 @@ int launch_mlp_bwd_sweep_tc(void* stream, const float* theta, const float* Wc, c
                             const float* WTlo, const float* ckpt, const float* ybar1, float* ybar0, float* const* S,
                             float* Pb0, float* Pb1, float* bst, float* xpart, float* gsmall, float* acts, float* pbar,
                             long long Bglob, long long r0, long long rows, int stride, int H, int L, int n_steps, float t0,
-                            float t1, float y0sign) {
+                            float t1, float y0sign, const float* actS, const MlpDwHook* dw_hook) {
   cudaStream_t st = (cudaStream_t)stream;
   const long long rows_pad = (rows + 127) / 128 * 128;
   const long long n_tiles = (rows + 7) / 8;
@@ -732,7 +771,17 @@ int launch_mlp_bwd_sweep_tc(void* stream, const float* theta, const float* Wc, c
   if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_layer_gemm_tc_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GemmSmem) + 1024);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_layer_gemm_tc_kernel<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GemmSmem) + 1024);
   if (e != cudaSuccess) return (int)e;
-  for (int l = 0; l < L; ++l) if ((e = cudaMemsetAsync(S[l], 0, sbytes, st)) != cudaSuccess) return (int)e;
+  // activation checkpoint of the forward (single chunk: r0 == 0, rows == Bglob): every stage's layer buffers are read in
+  // place, the hidden layers are not recomputed, and the tail's bookkeeping rides in the head kernel
+  const size_t sbuf = al256(sbytes) / sizeof(float);
+  auto sck = [&](int ev, int l) { return const_cast<float*>(actS) + ((size_t)ev * L + l) * sbuf; };
+  // ... and the cotangent jets stay in per-evaluation layer buffers too (pbar: [eval][slot l-1 = cotangent of hidden layer l]),
+  // which the weight-gradient GEMM reads in place; rows beyond the batch must hold zeros (bias-gradient column sums)
+  auto pck = [&](int ev, int slot) { return pbar + ((size_t)ev * (L - 1) + slot) * sbuf; };
+  if (actS == nullptr)
+    for (int l = 0; l < L; ++l) if ((e = cudaMemsetAsync(S[l], 0, sbytes, st)) != cudaSuccess) return (int)e;
+  if (actS != nullptr && rows % 128 != 0 &&
+      (e = cudaMemsetAsync(pbar, 0, (size_t)4 * n_steps * (L - 1) * sbuf * sizeof(float), st)) != cudaSuccess) return (int)e;
   if ((e = cudaMemsetAsync(Pb0, 0, sbytes, st)) != cudaSuccess) return (int)e;
   if ((e = cudaMemsetAsync(Pb1, 0, sbytes, st)) != cudaSuccess) return (int)e;
   if ((e = cudaMemsetAsync(gsmall, 0, (size_t)256 * TL.n_small() * sizeof(float), st)) != cudaSuccess) return (int)e;
@@ -750,9 +799,11 @@ int launch_mlp_bwd_sweep_tc(void* stream, const float* theta, const float* Wc, c
     // finish stage ev+1 (or initialise), prepare stage ev
     sa.e_done = ev + 1 < n_evals ? ev + 1 : -1; sa.e_next = ev;
     sa.acts0 = ev >= 0 ? acts + (size_t)ev * n_tiles * act_tile : nullptr;                       // layer 0 slot of the tile block
-    if ((e = launch_pdl(mlp_sweep_tail_kernel, dim3(glue_grid), dim3(256), 0, st, sa)) != cudaSuccess) return (int)e;
+    sa.fused_tail = actS != nullptr && ev >= 0;
+    if (actS != nullptr) { sa.S0 = nullptr; sa.Slast = ev >= 0 ? sck(ev, L - 1) : nullptr; }
+    if (!sa.fused_tail && (e = launch_pdl(mlp_sweep_tail_kernel, dim3(glue_grid), dim3(256), 0, st, sa)) != cudaSuccess) return (int)e;
     if (ev < 0) break;
-    for (int l = 1; l < L; ++l) {
+    for (int l = 1; l < L && actS == nullptr; ++l) {
       GemmArgs gg{};
       gg.Sin = S[l - 1]; gg.Sout = S[l]; gg.WT = WTc + (size_t)(l - 1) * H * H; gg.WTlo = WTlo + (size_t)(l - 1) * H * H;
       gg.bias = theta + TL.b(l); gg.B = rows; gg.rows_pad = rows_pad; gg.H = H;
@@ -761,17 +812,19 @@ int launch_mlp_bwd_sweep_tc(void* stream, const float* theta, const float* Wc, c
     }
     sa.e = ev;
     sa.pbar_last = pbar + (size_t)ev * n_tiles * pb_tile + (size_t)(L - 2) * 3 * H * kTT;
+    if (actS != nullptr) { sa.pbar_last = nullptr; sa.Pb = pck(ev, L - 2); }
     if ((e = launch_pdl(mlp_sweep_head_kernel, dim3(glue_grid), dim3(256), 0, st, sa)) != cudaSuccess) return (int)e;
     const int stage = ev & 3;
     const float cs = stage == 0 ? 0.f : (stage == 3 ? hstep : 0.5f * hstep);
     float* pin = Pb0; float* pout = Pb1;
     for (int l = L - 1; l >= 1; --l) {
       GemmArgs gg{};
+      if (actS != nullptr) { pin = pck(ev, l - 1); pout = l >= 2 ? pck(ev, l - 2) : nullptr; }
       gg.Sin = pin; gg.Sout = pout; gg.WT = Wc + (size_t)(l - 1) * H * H; gg.WTlo = Wclo + (size_t)(l - 1) * H * H;
-      gg.B = rows; gg.rows_pad = rows_pad; gg.H = H; gg.Sprev = S[l - 1]; gg.gsm = gsmall; gg.n_small = TL.n_small();
+      gg.B = rows; gg.rows_pad = rows_pad; gg.H = H; gg.Sprev = actS != nullptr ? sck(ev, l - 1) : S[l - 1]; gg.gsm = gsmall; gg.n_small = TL.n_small();
       if (l >= 2) {
         gg.off_b = TL.c_b(l - 1);
-        gg.blk_out = pbar + (size_t)ev * n_tiles * pb_tile + (size_t)(l - 2) * 3 * H * kTT; gg.blk_tile_stride = pb_tile;
+        if (actS == nullptr) { gg.blk_out = pbar + (size_t)ev * n_tiles * pb_tile + (size_t)(l - 2) * 3 * H * kTT; gg.blk_tile_stride = pb_tile; }
         if ((e = launch_pdl(mlp_layer_gemm_tc_kernel<3, 1>, gemm_grid, dim3(kGemmThreads), sizeof(GemmSmem) + 1024, st, gg)) != cudaSuccess) return (int)e;
         float* t = pin; pin = pout; pout = t;
       } else {
@@ -779,6 +832,11 @@ int launch_mlp_bwd_sweep_tc(void* stream, const float* theta, const float* Wc, c
         gg.xs = ckpt + ((long long)ev * 2) * Bglob + r0; gg.tprime = y0sign * (t0 + hstep * (float)(ev >> 2) + cs); gg.xpart = xpart;
         if ((e = launch_pdl(mlp_layer_gemm_tc_kernel<3, 2>, gemm_grid, dim3(kGemmThreads), sizeof(GemmSmem) + 1024, st, gg)) != cudaSuccess) return (int)e;
       }
+    }
+    if (dw_hook != nullptr && ev % dw_hook->group == 0) {
+      const int hi = ev + dw_hook->group < n_evals ? ev + dw_hook->group : n_evals;
+      const int rc = dw_hook->launch(dw_hook->ctx, ev, hi);
+      if (rc) return rc;
     }
     // the head of the next stage writes Pb0 again; MODE 1 outputs alternate between the two buffers
   }
@@ -808,11 +866,12 @@ int launch_mlp_prep_tc(void* stream, const float* theta, float* Wf, float* Wf_lo
 
 int launch_mlp_fwd_tc(void* stream, const float* theta, const float* WTc, const float* WTlo, const float* y_in, float* y_out, float* ckpt,
                       float* S0, float* S1, float* state, long long B, int jets, int stride, int H, int L, int n_steps,
-                      float t0, float t1, float y0sign) {
+                      float t0, float t1, float y0sign, float* actS) {
   cudaStream_t st = (cudaStream_t)stream;
-  if (jets == 3) return run_fwd_tc<3>(st, theta, WTc, WTlo, y_in, y_out, ckpt, S0, S1, state, B, stride, H, L, n_steps, t0, t1, y0sign);
-  if (jets == 2) return run_fwd_tc<2>(st, theta, WTc, WTlo, y_in, y_out, ckpt, S0, S1, state, B, stride, H, L, n_steps, t0, t1, y0sign);
-  return run_fwd_tc<1>(st, theta, WTc, WTlo, y_in, y_out, ckpt, S0, S1, state, B, stride, H, L, n_steps, t0, t1, y0sign);
+  if (jets == 3) return run_fwd_tc<3>(st, theta, WTc, WTlo, y_in, y_out, ckpt, S0, S1, state, B, stride, H, L, n_steps, t0, t1, y0sign, actS);
+  if (actS != nullptr) return OFDFT_EINVAL;                    // the activation checkpoint belongs to the full-jet training path
+  if (jets == 2) return run_fwd_tc<2>(st, theta, WTc, WTlo, y_in, y_out, ckpt, S0, S1, state, B, stride, H, L, n_steps, t0, t1, y0sign, nullptr);
+  return run_fwd_tc<1>(st, theta, WTc, WTlo, y_in, y_out, ckpt, S0, S1, state, B, stride, H, L, n_steps, t0, t1, y0sign, nullptr);
 }
 
 }  // namespace mlp

@@ -126,7 +126,8 @@ class EnergyEstimator:
         else:
             from .cn_flows import mlp_fwd, mlp_bwd
             e0 = mark()
-            y1, ckpt = mlp_fwd(theta, batch, m, self.t0, self.t1, ops.JETS_FULL, self.n_steps, want_ckpt=True, path=self.path)
+            y1, ckpt = mlp_fwd(theta, batch, m, self.t0, self.t1, ops.JETS_FULL, self.n_steps, want_ckpt=True, path=self.path,
+                               act_ckpt=self.act_ckpt)
             e1 = mark()
             sums, ybar1 = ops.functionals_fwd_bwd(self.spec, y1)
             if self.hartree_mode == "allpairs":

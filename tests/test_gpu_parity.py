@@ -580,13 +580,15 @@ def test_mlp1d_forward_and_training_step_match_oracle(feat, bs):
     spec = ops.EnergySpec(Ne=2, d=1, kin="tfw_1d", hart="softc", nuc="attraction", x="", R=0.7, Z_alpha=3, Z_beta=1)
     e_ref, terms_ref, g_ref, _ = O.loss_and_grad(fld, ospec, batch, n_steps=n_steps)
     # tcgen05 kernels (default), the fused FP32 integrator / adjoint sweep and the FP32 weight-gradient GEMM
-    for path in (ops.PATH_DEFAULT, ops.PATH_FFMA, ops.PATH_FFMA | ops.PATH_FFMA_DW, ops.PATH_FFMA_DW):
-        sums, tbar, _ = EnergyEstimator(model, spec, n_steps=n_steps, path=path).step_flat(dev(theta), dev(batch))
+    # ... each tensor-core variant with the forward's activation checkpoint (default) and with the recomputing adjoint
+    for path, act in ((ops.PATH_DEFAULT, True), (ops.PATH_DEFAULT, False), (ops.PATH_FFMA, True),
+                      (ops.PATH_FFMA | ops.PATH_FFMA_DW, True), (ops.PATH_FFMA_DW, True), (ops.PATH_FFMA_DW, False)):
+        sums, tbar, _ = EnergyEstimator(model, spec, n_steps=n_steps, path=path, act_ckpt=act).step_flat(dev(theta), dev(batch))
         sums = sums.cpu().numpy(); g = tbar.cpu().numpy()
         for i in range(3):
-            assert abs(sums[i] - terms_ref[i]) <= E_TOL * abs(terms_ref[i]), (path, i, sums[i], terms_ref[i])
+            assert abs(sums[i] - terms_ref[i]) <= E_TOL * abs(terms_ref[i]), (path, act, i, sums[i], terms_ref[i])
         for name, (a, b) in _mlp_slices(feat).items():
-            assert rel(g[a:b], g_ref[a:b]) <= G_TOL, (path, name, rel(g[a:b], g_ref[a:b]))
+            assert rel(g[a:b], g_ref[a:b]) <= G_TOL, (path, act, name, rel(g[a:b], g_ref[a:b]))
     sums, tbar, _ = EnergyEstimator(model, spec, n_steps=n_steps).step_flat(dev(theta), dev(batch))
     # f.apply(params, t, states) (cn_flows.py:173-182) and the score-augmented right-hand side
     params = model.unravel(dev(theta))
