@@ -181,10 +181,20 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def _launches_1d(n: int, L: int, ffma: bool) -> int:
+def _launches_1d(n: int, L: int, ffma: bool, act: bool = False) -> int:
+    """Kernel launches of one 1-D step: n = RHS evaluations.  Tensor-core path: prep (2), glue (n + 1) and (L - 1) layer
+    GEMMs per evaluation forward; the adjoint adds head + tail kernels and the transposed GEMMs, plus either the recomputed
+    forward GEMMs and two weight-gradient launches per layer at the end, or -- with the forward's activation checkpoint --
+    (L - 1) weight-gradient launches per group of 4 evaluations on the second stream.  + 2 functionals, + reduces."""
     fwd = 2 + (n + 1) + n * (L - 1) if not ffma else 2
-    bwd = 2 + (n + 1) + n + 2 * n * (L - 1) if not ffma else 2
-    return fwd + 2 + bwd + 1 + 2 * (L - 1)
+    if ffma:
+        bwd = 2
+    elif act:
+        bwd = 2 + n + 1 + n * (L - 1)
+    else:
+        bwd = 2 + (n + 1) + n + 2 * n * (L - 1)
+    dw = ((n + 3) // 4 + 1) * (L - 1) if (act and not ffma) else 2 * (L - 1)
+    return fwd + 2 + bwd + 1 + dw
 
 
 def _timed(fn, reps: int, warm: int = 1) -> float:
@@ -522,11 +532,13 @@ def main():
         fwd_tensor_flops = evals * (L - 1) * gemm
         # weight gradients: 3 passes (hi.hi, lo.hi, hi.lo) over n_evals x B x 3 jets contraction rows (128 x 128 tiles)
         dw_flops = (L - 1) * 2.0 * Hm * Hm * (evals * math.ceil(B / 8) * 8 * 3) * 3
-        bwd_tensor_flops = 2.0 * evals * (L - 1) * gemm + dw_flops
+        act_1d = not args.recompute          # forward keeps the layer activations: the adjoint skips the recompute GEMMs
+        bwd_tensor_flops = (1.0 if act_1d else 2.0) * evals * (L - 1) * gemm + dw_flops
         tf32_peak = 0.5 * peaks.get("bf16_tflops_sustained", 1400.0)
         peak3 = tf32_peak / 3.0
         roofline = {
-            "bound": "tensor", "kernel": "mlp_layer_gemm_tc_kernel (+ mlp_dw_gemm_tc_kernel) launches of the adjoint",
+            "bound": "tensor", "kernel": "mlp_layer_gemm_tc_kernel launches of the adjoint + mlp_dw_gemm_ts_kernel" +
+                                         (" (on a second stream, beside the sweep)" if act_1d else ""),
             "achieved": bwd_flops / bwd_s / 1e12, "peak": peak3, "unit": "TFLOP/s", "achieved_is": "algorithmic fp32-equivalent flops / launch time",
             "frac": bwd_flops / bwd_s / 1e12 / peak3, "traffic": None,
             "peak_source": ("3xTF32 = 1/3 x 1/2 x bf16_tflops_sustained of MEASURED_PEAKS.json (kernel timed inside the step; of measured)"
@@ -536,7 +548,9 @@ def main():
             "executed_tensor_flops_per_launch": bwd_tensor_flops,
             "executed_tensor_frac_of_dense_tf32": bwd_tensor_flops / bwd_s / 1e12 / tf32_peak,
             "note": "3xTF32; one launch per hidden layer and RHS evaluation (a 128-row x 512-unit layer with three jets does "
-                    "not fit on chip); 64 of 148 SMs busy at bs=512 -- see DESIGN.md section 3c",
+                    "not fit on chip); the sweep keeps 64 of 148 SMs busy at bs=512, the weight-gradient GEMM the rest "
+                    "-- see DESIGN.md section 3c",
+            "activation_checkpoint": act_1d,
             "fp32_equivalent": {"algorithmic_flops_per_launch": bwd_flops, "achieved": bwd_flops / bwd_s / 1e12,
                                 "ffma_peak": ffma_peak / 1e12, "frac_of_ffma_peak": bwd_flops / bwd_s / ffma_peak,
                                 "peak_source": "ofdft_microbench_ffma measured in this run"},
@@ -647,7 +661,7 @@ def main():
             #   forward  tc: 2 weight preps + (n+1) glue + n (L-1) layer GEMMs          | ffma: prep + fused kernel
             #   adjoint  tc: 2 preps + (n+1) tail + n head + 2 n (L-1) layer GEMMs      | ffma: prep + fused sweep
             #   both: functionals x2, small-gradient reduce, (L-1) x (weight-gradient GEMM + reduce)
-            "gpu_launches": (5 if not is_1d else _launches_1d(4 * args.n_steps, len(MLP_FEAT), args.ffma)) * args.steps,
+            "gpu_launches": (5 if not is_1d else _launches_1d(4 * args.n_steps, len(MLP_FEAT), args.ffma, not args.recompute)) * args.steps,
             "roofline": roofline,
             "energy_terms_last_step": [float(v) for v in sums.cpu().numpy()[:6]],
             "hartree": ({"mode": "paired"} if args.hartree == "paired" else

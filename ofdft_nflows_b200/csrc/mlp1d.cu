@@ -715,7 +715,9 @@ __global__ void __launch_bounds__(kDw3Threads, 1) mlp_dw_gemm_ts_kernel(const fl
                                                                        int accumulate) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   Dw3Smem& sm = *reinterpret_cast<Dw3Smem*>(smem_raw);
-  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  // warp index through a shuffle: the compiler then knows it is warp-uniform and keeps the role branches (and the shuffles
+  // inside them) free of convergence barriers
+  const int tid = threadIdx.x, w = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
   const int k0 = blockIdx.x * 128, j0 = blockIdx.y * 128, sp = blockIdx.z;
   if (tid == 0) {
     for (int i = 0; i < kDw3Slots; ++i) { tc::mbar_init(&sm.full[i], 8); tc::mbar_init(&sm.empty[i], 1); }
@@ -878,6 +880,8 @@ __global__ void __launch_bounds__(kDw3Threads, 1) mlp_dw_gemm_ts_kernel(const fl
       for (int q = 0; q < kDw3PF; ++q) {                       // static register / slot indices: no rotation moves
         const int it = it0 + q;
         if (it < n_it) {
+          // the loop is bound by the latency of these loads: the next ones go out BEFORE this block is staged (4.8 -> 4.2 ms
+          // per step against issuing them afterwards; an additional L2 prefetch 8..32 blocks ahead changed nothing)
           float4 R[3][2];
 #pragma unroll
           for (int jt = 0; jt < 3; ++jt) { R[jt][0] = pf[q][jt][0]; R[jt][1] = pf[q][jt][1]; }
@@ -962,6 +966,9 @@ static int dw_overlap_launch(void* vctx, int ev_lo, int ev_hi) {
   const long long rows_pad = (c.rows + 127) / 128 * 128;
   const size_t sbuf = al256(3 * (size_t)rows_pad * c.H * 4) / 4;
   const dim3 gg(c.H / 128, c.H / 128, c.splits);
+#ifdef OFDFT_ABL_NODW       // timing ablation only (results invalid)
+  return 0;
+#endif
   for (int l = 1; l < c.L; ++l) {
     DwSrc src{c.actS + (size_t)(l - 1) * sbuf, c.pbar + (size_t)(l - 1) * sbuf, (size_t)c.L * sbuf, (size_t)(c.L - 1) * sbuf, rows_pad, c.rows,
               (int)c.n_tiles};
@@ -1132,6 +1139,9 @@ extern "C" int ofdft_cnf_mlp1d_bwd(void* stream, const float* theta, const float
       const int gemm_ctas = (int)((rows + 127) / 128) * (H / 64), tiles = (H / 128) * (H / 128);
       int ov_splits = (sms - gemm_ctas) / tiles;
       if (ov_splits > kDwSplits / (L - 1)) ov_splits = kDwSplits / (L - 1);
+#ifdef OFDFT_ABL_DWEND      // timing ablation: weight-gradient GEMM after the sweep instead of beside it
+      ov_splits = 0;
+#endif
       SideStream* side = ov_splits >= 1 ? side_stream() : nullptr;
       if (side != nullptr) {
         e = cudaFuncSetAttribute(mlp_dw_gemm_ts_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Dw3Smem) + 1024);

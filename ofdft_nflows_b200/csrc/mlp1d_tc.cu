@@ -41,20 +41,23 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
 }
 
 constexpr int kGemmKC = 16;                       // k per pipeline stage (4 chunks of 4)
-#ifndef OFDFT_GEMM_GROUP
-#define OFDFT_GEMM_GROUP 16
+#ifndef OFDFT_GEMM_SG
+#define OFDFT_GEMM_SG 2
 #endif
-constexpr int kGemmGroup = OFDFT_GEMM_GROUP;      // stages per TMEM accumulation chain (256 k, 96 MMAs per jet); measured max
+static_assert(512 / 16 <= 32, "one TMEM accumulation chain per launch assumes H <= 512");
+constexpr int kGemmGroup = 32;                    // stages per TMEM accumulation chain (256 k, 96 MMAs per jet); measured max
                                                   // state error vs the float64 oracle (3x512): 6e-7 / 1.1e-6 / 1.7e-6 for 8 / 16 / 32
 constexpr int kGemmSlots = 3;                     // activation-operand ring in tensor memory
 constexpr int kGemmRaw = 4;                       // shared-memory ring fed by TMA bulk copies: raw activation jets + weight stage
 constexpr int kLboB = 64 * 16;                    // chunk stride of the weight operand (bytes): 64 rows x 16 B, as TMA lays it
 constexpr int kColAcc = 0;                        // TMEM: accumulators 3 jets x 64 columns
 constexpr int kColOp = 192;                       // TMEM: operand ring, per slot [jet][hi 16 | lo 16] = 96 columns
-constexpr int kSW = 8;                            // staging warps: 4 row quadrants x (kSW/4) column groups; 8 warps do a stage in a
-                                                  // third fewer instructions than 16 (the per-warp waits/fences/arrivals halve)
-constexpr int kCT = 64 / (kSW / 4);               // output columns per staging thread (epilogue)
-constexpr int kCH = 4 / (kSW / 4);                // 4-wide k chunks per staging thread and stage
+constexpr int kSG = OFDFT_GEMM_SG;                // staging groups of 8 warps (4 row quadrants x 2 chunk halves): group g stages the
+                                                  // pipeline stages it = g (mod kSG), so kSG stages are in flight on the CUDA cores --
+                                                  // one group alone is latency-bound at ~950 clocks per stage against 576 of MMA
+constexpr int kSW = 8 * kSG;                      // staging warps
+constexpr int kCT = 64 / (kSW / 4);               // output columns per staging thread (epilogue: all staging warps)
+constexpr int kCH = 2;                            // 4-wide k chunks per staging thread and stage
 constexpr int kGemmThreads = (kSW + 2) * 32;      // staging warps + MMA warp + TMA warp
 
 // layer buffers: [jet: a, p', p''][unit / 4][row (padded to 128)][4 units] -- 32 consecutive rows x 4 units are 512
@@ -106,8 +109,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) mlp_layer_gemm_tc_kernel(cons
   const long long row0 = (long long)blockIdx.x * 128;
   const int j0 = blockIdx.y * 64;
   if (tid == 0) {
-    for (int i = 0; i < kGemmSlots; ++i) { tc::mbar_init(&sm.full[i], kSW); tc::mbar_init(&sm.empty[i], 1); }
-    for (int i = 0; i < kGemmRaw; ++i) { tc::mbar_init(&sm.rfull[i], 1); tc::mbar_init(&sm.rempty[i], kSW + 1); }
+    for (int i = 0; i < kGemmSlots; ++i) { tc::mbar_init(&sm.full[i], 8); tc::mbar_init(&sm.empty[i], 1); }
+    for (int i = 0; i < kGemmRaw; ++i) { tc::mbar_init(&sm.rfull[i], 1); tc::mbar_init(&sm.rempty[i], 8 + 1); }
     tc::mbar_init(&sm.accf, 1); tc::mbar_init(&sm.acce, kSW);
     tc::fence_mbar_init();
   }
@@ -159,12 +162,16 @@ __global__ void __launch_bounds__(kGemmThreads, 1) mlp_layer_gemm_tc_kernel(cons
       for (int it = 0; it < n_it; ++it) {
         const int s = it % kGemmRaw;
         if (it >= kGemmRaw) { tc::mbar_wait(&sm.rempty[s], (ph >> s) & 1u); ph ^= 1u << s; }
+#ifdef OFDFT_ABL_NOTMA_A      // timing ablation only (results invalid): the activation operand is not fetched
+        tc::mbar_arrive_expect_tx(&sm.rfull[s], (uint32_t)(2 * 4 * 1024));
+#else
         tc::mbar_arrive_expect_tx(&sm.rfull[s], (uint32_t)(NJ * 4 * 2048 + 2 * 4 * 1024));
 #pragma unroll
         for (int jt = 0; jt < NJ; ++jt)
 #pragma unroll
           for (int c = 0; c < 4; ++c)
             tc::bulk_g2s(&sm.A[s][jt][c][0], g.Sin + jt * jet_stride + sbuf_off(4 * it + c, row0, g.rows_pad), 2048, &sm.rfull[s]);
+#endif
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           const size_t off = ((size_t)(4 * it + c) * H + j0) * 4;
@@ -176,14 +183,15 @@ __global__ void __launch_bounds__(kGemmThreads, 1) mlp_layer_gemm_tc_kernel(cons
     __syncwarp();
   } else {
     // ---------------- staging warps ----------------
-    const int r = 32 * (w & 3) + lane, c = w >> 2;          // row (TMEM lane) and k chunk of this thread
+    // row (TMEM lane); staging: group grp handles stages it = grp (mod kSG), chunk half cs; epilogue: column group c
+    const int r = 32 * (w & 3) + lane, c = w >> 2, cs = (w >> 2) & 1, grp = w >> 3;
     const uint32_t tl = tmem + ((uint32_t)(32 * (w & 3)) << 16);
     struct Regs { float4 a[3][kCH]; };
     auto load_regs = [&](Regs& R, int it) {
 #pragma unroll
       for (int jt = 0; jt < NJ; ++jt)
 #pragma unroll
-        for (int q = 0; q < kCH; ++q) R.a[jt][q] = sm.A[it % kGemmRaw][jt][kCH * c + q][r];
+        for (int q = 0; q < kCH; ++q) R.a[jt][q] = sm.A[it % kGemmRaw][jt][kCH * cs + q][r];
     };
     // operand jets and their tf32 remainders, two values per FP32 instruction (packed FFMA2 / FMUL2)
     auto lo4 = [&](tc::f32x2 xy, tc::f32x2 zw, uint32_t col) {
@@ -197,7 +205,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) mlp_layer_gemm_tc_kernel(cons
       using namespace tc;
 #pragma unroll
       for (int q = 0; q < kCH; ++q) {
-        const uint32_t base = tl + kColOp + 96 * s + 4 * (kCH * c + q);
+        const uint32_t base = tl + kColOp + 96 * s + 4 * (kCH * cs + q);
         const float4 a = R.a[0][q];
         const f32x2 a01 = pack2(a.x, a.y), a23 = pack2(a.z, a.w);
         lo4(a01, a23, base);
@@ -232,7 +240,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) mlp_layer_gemm_tc_kernel(cons
     for (int jt = 0; jt < NJ; ++jt)
 #pragma unroll
       for (int i = 0; i < kCT; ++i) acc[jt][i] = 0.f;
-    uint32_t ph_empty = 0, ph_accf = 0;
+    uint32_t ph_accf = 0;
     auto drain = [&]() {
       tc::mbar_wait(&sm.accf, ph_accf); ph_accf ^= 1u;
       __syncwarp();
@@ -252,20 +260,21 @@ __global__ void __launch_bounds__(kGemmThreads, 1) mlp_layer_gemm_tc_kernel(cons
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&sm.acce);
     };
-    uint32_t ph_rfull = 0;
-    for (int it = 0; it < n_it; ++it) {
+    // one accumulation chain per launch (n_it <= kGemmGroup because H <= 512): no drain inside the loop
+    for (int it = grp; it < n_it; it += kSG) {
       const int s = it % kGemmSlots, rs = it % kGemmRaw;
-      tc::mbar_wait(&sm.rfull[rs], (ph_rfull >> rs) & 1u); ph_rfull ^= 1u << rs;          // TMA data of this stage has landed
+      tc::mbar_wait(&sm.rfull[rs], (uint32_t)(it / kGemmRaw) & 1u);                       // TMA data of this stage has landed
       Regs R;
       load_regs(R, it);
       // the TMEM slot of this stage is free once the MMAs of stage it-3 have completed
-      if (it >= kGemmSlots) { tc::mbar_wait(&sm.empty[s], (ph_empty >> s) & 1u); ph_empty ^= 1u << s; }
+      if (it >= kGemmSlots) tc::mbar_wait(&sm.empty[s], (uint32_t)(it / kGemmSlots - 1) & 1u);
+      __syncwarp();
+      tc::fence_after_sync();
       store_tmem(R, s);
       tc::tmem_st_wait();
       tc::fence_before_sync();
       __syncwarp();
       if (lane == 0) { tc::mbar_arrive(&sm.full[s]); tc::mbar_arrive(&sm.rempty[rs]); }
-      if ((it + 1) % kGemmGroup == 0 && it + 1 < n_it) drain();
     }
     drain();
     pdl_trigger();                                // the next kernel of the chain may be scheduled during this epilogue

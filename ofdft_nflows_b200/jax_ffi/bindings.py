@@ -33,13 +33,15 @@ for _name in FFI_TARGETS:
     jax.ffi.register_ffi_target(_name, jax.ffi.pycapsule(getattr(_xla, _name)), platform="CUDA")
 
 SIZE_HELPERS = ("ofdft_cnf_gnn_ckpt_bytes", "ofdft_cnf_gnn_act_ckpt_bytes", "ofdft_cnf_gnn_fwd_scratch_bytes",
-                "ofdft_cnf_gnn_bwd_scratch_bytes", "ofdft_cnf_mlp1d_ckpt_bytes", "ofdft_cnf_mlp1d_scratch_bytes",
+                "ofdft_cnf_gnn_bwd_scratch_bytes", "ofdft_cnf_mlp1d_ckpt_bytes", "ofdft_cnf_mlp1d_act_ckpt_bytes",
+                "ofdft_cnf_mlp1d_scratch_bytes",
                 "ofdft_functionals_scratch_bytes", "ofdft_hartree_allpairs_scratch_bytes")
 for _name in SIZE_HELPERS:
     getattr(_abi, _name).restype = ctypes.c_size_t
 _abi.ofdft_cnf_gnn_theta_size.restype = ctypes.c_int64
 _i64, _i32 = ctypes.c_int64, ctypes.c_int32
-PATH_DEFAULT = 0
+PATH_DEFAULT, PATH_FFMA, PATH_FFMA_DW, PATH_ACT_CKPT = 0, 1, 2, 4
+MLP1D_ACT_CKPT_MAX_BYTES = 16 << 30
 
 KIN = {"": 0, "tf": 1, "w": 2, "tf-w": 3, "tf1d": 4, "tfw_1d": 5}
 HART = {"": 0, "hartree": 1, "softc": 2, "hartree_mt": 3}
@@ -116,19 +118,29 @@ def gnn_rhs(theta, nuclei, onehot, y, t, *, bool_neg, jets, path=PATH_DEFAULT):
 
 
 # ---- 1-D tanh-MLP flow ------------------------------------------------------------------------------------------------------
-def make_mlp1d_flow(features, *, bool_neg, n_steps=16, t0=0.0, t1=1.0, path=PATH_DEFAULT):
+def make_mlp1d_flow(features, *, bool_neg, n_steps=16, t0=0.0, t1=1.0, path=PATH_DEFAULT, act_ckpt=True):
     """``flow(theta_flat, y0 (B,3)) -> y1`` for Gen_CNFSimpleMLP(1, features) (cn_flows.py:166-182), rows [x, logp, score];
-    the adjoint kernels carry all three channels, so ``neural_ode`` pads a zero score column (see below)."""
+    the adjoint kernels carry all three channels, so ``neural_ode`` pads a zero score column (see below).  ``act_ckpt``: the
+    residual also keeps the layer activations of every evaluation (OFDFT_PATH_ACT_CKPT) when the shape supports it."""
     H, L = int(features[0]), len(features)
     y0sign = -1.0 if bool_neg else 1.0
-    attrs = dict(jets=np.int32(3), H=np.int32(H), n_layers=np.int32(L), n_steps=np.int32(n_steps), t0=np.float32(t0),
-                 t1=np.float32(t1), y0sign=np.float32(y0sign), path=np.int32(path))
+    base = dict(jets=np.int32(3), H=np.int32(H), n_layers=np.int32(L), n_steps=np.int32(n_steps), t0=np.float32(t0),
+                t1=np.float32(t1), y0sign=np.float32(y0sign))
+
+    def act_bytes(B):
+        """Size of the activation checkpoint, or 0 when this batch / path does not use it (same rule on both sides of the vjp)."""
+        if not act_ckpt or (path & (PATH_FFMA | PATH_FFMA_DW)):
+            return 0
+        n = _abi.ofdft_cnf_mlp1d_act_ckpt_bytes(_i64(B), _i32(H), _i32(L), _i32(n_steps))
+        return n if 0 < n <= MLP1D_ACT_CKPT_MAX_BYTES else 0
 
     def call_fwd(theta, y0, want_ckpt):
         B = y0.shape[0]
-        ckpt_n = _abi.ofdft_cnf_mlp1d_ckpt_bytes(_i64(B), _i32(n_steps)) // 4 if want_ckpt else 1
+        n_act = act_bytes(B) if want_ckpt else 0
+        ckpt_n = (n_act or _abi.ofdft_cnf_mlp1d_ckpt_bytes(_i64(B), _i32(n_steps))) // 4 if want_ckpt else 1
         sb = _abi.ofdft_cnf_mlp1d_scratch_bytes(_i64(B), _i32(H), _i32(L), _i32(n_steps))
         out = (jax.ShapeDtypeStruct(y0.shape, jnp.float32), _f32(ckpt_n), _u8(sb))
+        attrs = dict(base, path=np.int32(path | (PATH_ACT_CKPT if n_act else 0)))
         y1, ckpt, _ = jax.ffi.ffi_call("OfdftMlp1dFwd", out)(theta, y0, **attrs)
         return y1, ckpt
 
@@ -145,6 +157,7 @@ def make_mlp1d_flow(features, *, bool_neg, n_steps=16, t0=0.0, t1=1.0, path=PATH
         B = ybar1.shape[0]
         sb = _abi.ofdft_cnf_mlp1d_scratch_bytes(_i64(B), _i32(H), _i32(L), _i32(n_steps))
         out = (jax.ShapeDtypeStruct(theta.shape, jnp.float32), jax.ShapeDtypeStruct(ybar1.shape, jnp.float32), _u8(sb))
+        attrs = dict(base, path=np.int32(path | (PATH_ACT_CKPT if act_bytes(B) else 0)))
         tbar, ybar0, _ = jax.ffi.ffi_call("OfdftMlp1dBwd", out)(theta, ckpt, ybar1, **attrs)
         return tbar, ybar0
 
