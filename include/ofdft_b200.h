@@ -280,6 +280,10 @@ int ofdft_microbench_sfu(void* stream, float* sink, int32_t iters, double* ops_o
  * `passes` = 1 (plain TF32) or 3 (3xTF32 error-compensated); M in {64, 128}.  Used by tests to pin the hand-written
  * descriptor / TMEM plumbing that the tensor-core integrator builds on. */
 int ofdft_tc_gemm_test(void* stream, const float* A, const float* W, float* D, int32_t M, int32_t passes);
+/* diagnostic: clocks for `reps` back-to-back tcgen05.mma (kind::tf32, M = 128, K = 8) of width N, A operand from shared
+ * memory (ts = 0) or tensor memory (ts = 1), accumulating round-robin into nacc (1..4) accumulators -- consecutive MMAs
+ * into the same accumulator are dependent; out = one int64 on the device. */
+int ofdft_tc_mma_rate(void* stream, long long* out, int32_t N, int32_t ts, int32_t reps, int32_t distinct_b, int32_t nacc);
 
 #ifdef __cplusplus
 }

@@ -57,6 +57,7 @@ SIGNATURES = {
     "ofdft_microbench_ffma": (C.c_int, [vp, vp, i32, C.POINTER(C.c_double)]),
     "ofdft_microbench_sfu": (C.c_int, [vp, vp, i32, C.POINTER(C.c_double)]),
     "ofdft_tc_gemm_test": (C.c_int, [vp, vp, vp, vp, i32, i32]),
+    "ofdft_tc_mma_rate": (C.c_int, [vp, vp, i32, i32, i32, i32, i32]),
 }
 
 

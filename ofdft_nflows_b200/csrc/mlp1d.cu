@@ -939,7 +939,9 @@ __global__ void mlp_small_reduce_kernel(const float* __restrict__ gsmall, float*
 // The sweep is a dependent chain of launches that keeps (rows / 128) x (H / 64) SMs busy; the rest of the GPU contracts the
 // evaluations the sweep has already finished, on a second stream, in groups of kDwGroup evaluations.
 constexpr int kDwGroup = 4;
-struct SideStream { cudaStream_t s = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
+// One library-owned stream and event pair per device, created on first use; `busy` serialises the host-side enqueueing of
+// calls that share them (the events are re-recorded per group of evaluations; waits already enqueued keep their meaning).
+struct SideStream { cudaStream_t s = nullptr; cudaEvent_t fork = nullptr, join = nullptr; std::mutex busy; };
 static SideStream* side_stream() {
   static SideStream side[64];
   static std::mutex mu;
@@ -1135,6 +1137,7 @@ extern "C" int ofdft_cnf_mlp1d_bwd(void* stream, const float* theta, const float
     // activation-checkpoint path: the weight-gradient GEMM runs beside the sweep on the SMs the sweep leaves idle
     DwOverlapCtx ov{};
     MlpDwHook hook{};
+    std::unique_lock<std::mutex> side_lock;
     if (act) {
       const int gemm_ctas = (int)((rows + 127) / 128) * (H / 64), tiles = (H / 128) * (H / 128);
       int ov_splits = (sms - gemm_ctas) / tiles;
@@ -1144,6 +1147,7 @@ extern "C" int ofdft_cnf_mlp1d_bwd(void* stream, const float* theta, const float
 #endif
       SideStream* side = ov_splits >= 1 ? side_stream() : nullptr;
       if (side != nullptr) {
+        side_lock = std::unique_lock<std::mutex>(side->busy);
         e = cudaFuncSetAttribute(mlp_dw_gemm_ts_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Dw3Smem) + 1024);
         if (e != cudaSuccess) return (int)e;
         ov = DwOverlapCtx{st, side, part, ckpt + AL.s / 4, a.pbar, H, L, ov_splits, 0, rows, n_tiles};

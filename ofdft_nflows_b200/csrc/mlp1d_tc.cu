@@ -22,6 +22,16 @@ namespace mlp {
 // serialization" attribute, calls pdl_wait() before it touches anything its predecessor wrote and pdl_trigger() once its
 // successor may start being scheduled -- so a kernel's prologue (TMEM allocation, barrier init, scheduling) overlaps the
 // tail of the one before it.  ~380 dependent launches per 1-D step make the fixed cost per launch matter.
+#ifdef OFDFT_GEMM_TRACE     // development only: %globaltimer stamps of CTA 0 of every kernel of the chain
+__device__ unsigned long long g_trace[1 << 16];
+__device__ unsigned int g_trace_n;
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define TRACE_BEGIN(kind) unsigned int tr_ = 0xffffffffu; if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == (kind == 0 ? 32 * kSW : 0)) { tr_ = atomicAdd(&g_trace_n, 1u) & 8191u; g_trace[tr_ * 8] = kind; g_trace[tr_ * 8 + 1] = gtime(); }
+#define TRACE(i) if (tr_ != 0xffffffffu) g_trace[tr_ * 8 + (i)] = gtime();
+#else
+#define TRACE_BEGIN(kind)
+#define TRACE(i)
+#endif
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
@@ -121,7 +131,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) mlp_layer_gemm_tc_kernel(cons
   const uint32_t tmem = sm.tmem_slot;
   const int n_it = H / kGemmKC;
   const size_t jet_stride = (size_t)g.rows_pad * H;
+  TRACE_BEGIN(0)
   pdl_wait();                                     // everything above overlapped the previous kernel's tail
+  TRACE(2)
 
   if (w == kSW) {
     // ---------------- MMA issue warp ----------------
@@ -131,6 +143,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) mlp_layer_gemm_tc_kernel(cons
       const int s = it % kGemmSlots;
       const bool first = (it % kGemmGroup) == 0;
       tc::mbar_wait(&sm.full[s], (ph_full >> s) & 1u); ph_full ^= 1u << s;
+      if (it == 0) { TRACE(3) }
       if (first && it > 0) { tc::mbar_wait(&sm.acce, ph_acce); ph_acce ^= 1u; }
       __syncwarp();
       tc::fence_after_sync();
@@ -153,6 +166,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) mlp_layer_gemm_tc_kernel(cons
       }
       __syncwarp();
     }
+    TRACE(4)
+#ifdef OFDFT_GEMM_TRACE
+    if (tr_ != 0xffffffffu) { tc::mbar_wait(&sm.accf, 0); TRACE(5) }
+#endif
   } else if (w == kSW + 1) {
     // ---------------- TMA warp: bulk copies global/L2 -> shared-memory ring ----------------
     // per stage: 3 jets x 4 unit groups x (128 rows x 16 B = 2 KB contiguous in the interleaved layer buffer) and
@@ -395,6 +412,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) mlp_layer_gemm_tc_kernel(cons
   }
   tc::fence_before_sync();
   __syncthreads();
+  TRACE(6)
   if (w == 0) tc::tmem_dealloc(tmem, 512);
 }
 
@@ -430,7 +448,9 @@ __global__ void __launch_bounds__(256) mlp_glue_tc_kernel(const GlueArgs g) {
   __shared__ float part[3][8][8];                 // [quantity][warp][row]
   __shared__ float bc[8][2];                      // per row: x and s of the next stage
   pdl_trigger();                                  // short kernel: let the next layer GEMM run its prologue underneath
+  TRACE_BEGIN(1)
   pdl_wait();
+  TRACE(2)
   const int tid = threadIdx.x, t = tid & 7, gs = tid >> 3, wp = tid >> 5;
   const long long row = (long long)blockIdx.x * 8 + t;
   const bool valid = row < g.B;
@@ -525,6 +545,7 @@ __global__ void __launch_bounds__(256) mlp_glue_tc_kernel(const GlueArgs g) {
   const int stage = ne & 3;
   const float cs = stage == 0 ? 0.f : (stage == 3 ? h : 0.5f * h);
   const float tp = g.y0 * (g.t0 + h * (float)(ne >> 2) + cs);
+  TRACE(6)
   if (!valid && g.acts0 == nullptr) return;
   float* blk = g.acts0 != nullptr ? g.acts0 + (size_t)blockIdx.x * g.act_tile_stride + t : nullptr;
   for (int grp = gs; grp < H / 4; grp += 32) {
@@ -885,3 +906,10 @@ int launch_mlp_fwd_tc(void* stream, const float* theta, const float* WTc, const 
 
 }  // namespace mlp
 }  // namespace ofdft
+
+#ifdef OFDFT_GEMM_TRACE
+extern "C" int ofdft_debug_trace_dump(unsigned long long* host, int n_words) {
+  cudaDeviceSynchronize();
+  return (int)cudaMemcpyFromSymbol(host, ofdft::mlp::g_trace, (size_t)n_words * 8);
+}
+#endif

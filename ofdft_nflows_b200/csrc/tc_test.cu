@@ -164,3 +164,69 @@ extern "C" int ofdft_tc_gemm_test(void* stream, const float* A, const float* W, 
   tc_gemm_test_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(A, W, D, M, passes == -3 ? 1 : (passes < 0 ? 0 : passes), passes == 0 ? 1 : 0, passes < 0 ? -passes : 0);
   return (int)cudaGetLastError();
 }
+
+// ------------------------------------------------------------------------------------------------
+// diagnostic: clocks per tcgen05.mma (kind::tf32, M = 128, K = 8) issued back to back, by N and by where the A operand
+// lives (shared memory descriptor / tensor memory).  out[0] = clocks for `reps` MMAs (issue + completion).
+// ------------------------------------------------------------------------------------------------
+namespace ofdft {
+__global__ void __launch_bounds__(128, 1) tc_mma_rate_kernel(long long* out, int N, int ts, int reps, int distinct_b, int nacc) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  float* A = reinterpret_cast<float*>(smem_raw);               // 128 x 8 tf32, K-major: 2 chunks x 128 rows x 16 B = 4 KB
+  float* B = A + 1024;                                         // up to 8 tiles of 256 x 8: 8 KB each
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(B + 8 * 2048);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(mbar + 1);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 1024 + 8 * 2048; i += 128) A[i] = 0.001f * (float)(i & 63);
+  if (tid == 0) { tc::mbar_init(mbar, 1); tc::fence_mbar_init(); }
+  if (warp == 0) tc::tmem_alloc(slot, 512);
+  tc::fence_async_smem();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = *slot;
+  {
+    float v[16];
+    for (int i = 0; i < 16; ++i) v[i] = 0.5f;
+    tc::tmem_st16(tmem + ((uint32_t)(32 * warp) << 16) + 448, v);     // A operand columns 448..463
+    tc::tmem_st_wait();
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  if (warp == 0 && tc::elect_one()) {      // elect.sync: the compiler keeps descriptors in uniform registers, as in the kernels
+    const uint32_t idesc = tc::make_idesc_tf32(128, N, 0, 0);
+    const uint64_t ad = tc::make_desc(tc::smem_u32(A), 128 * 16, 128);
+    const uint64_t bd0 = tc::make_desc(tc::smem_u32(B), N * 16, 128);
+    const uint64_t bd1 = tc::make_desc(tc::smem_u32(B + (distinct_b ? 2048 : 0)), N * 16, 128);
+    // nacc accumulators of N columns used round-robin: consecutive MMAs into the SAME accumulator depend on each other
+    const uint32_t stride = nacc > 1 ? (uint32_t)N : 0u;
+    const long long t0 = clock64();
+    for (int r = 0; r < reps; r += 12) {            // 12 back-to-back issues per loop trip, descriptors precomputed
+#pragma unroll
+      for (int q = 0; q < 12; ++q) {
+        const uint32_t d = tmem + stride * (uint32_t)(nacc == 2 ? (q & 1) : (nacc == 3 ? (q % 3) : (nacc == 4 ? (q & 3) : 0)));
+        if (ts) tc::mma_tf32_ts(d, tmem + 448 + 8 * (q & 1), (q & 1) ? bd1 : bd0, idesc, true);
+        else tc::mma_tf32(d, ad, (q & 1) ? bd1 : bd0, idesc, true);
+      }
+    }
+    tc::commit(mbar);
+    tc::mbar_wait(mbar, 0);
+    out[0] = clock64() - t0;
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, 512);
+}
+}  // namespace ofdft
+
+extern "C" int ofdft_tc_mma_rate(void* stream, long long* out, int32_t N, int32_t ts, int32_t reps, int32_t distinct_b,
+                                 int32_t nacc) {
+  using namespace ofdft;
+  if (!out || N < 8 || N > 256 || N % 8 || reps < 1 || nacc < 1 || nacc > 4 || nacc * N > 448) return OFDFT_EINVAL;
+  const size_t smem = sizeof(float) * (1024 + 8 * 2048) + 64 + 1024;
+  cudaError_t e = cudaFuncSetAttribute(tc_mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  tc_mma_rate_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(out, N, ts, reps, distinct_b, nacc);
+  return (int)cudaGetLastError();
+}
