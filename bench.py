@@ -193,7 +193,8 @@ def _launches_1d(n: int, L: int, ffma: bool, act: bool = False) -> int:
         bwd = 2 + n + 1 + n * (L - 1)
     else:
         bwd = 2 + (n + 1) + n + 2 * n * (L - 1)
-    dw = ((n + 3) // 4 + 1) * (L - 1) if (act and not ffma) else 2 * (L - 1)
+    # groups of 4 evaluations, the last 4 one by one; + one reduce per layer
+    dw = ((n - 4 + 3) // 4 + min(n, 4) + 1) * (L - 1) if (act and not ffma) else 2 * (L - 1)
     return fwd + 2 + bwd + 1 + dw
 
 

@@ -663,21 +663,26 @@ __global__ void __launch_bounds__(256, 2) mlp_dw_gemm_tc_kernel(const float* __r
 // 128 x 128 output tiles (H a multiple of 128), warp specialised.  With both operands in shared memory a (block, jet) slab of
 // 8 trajectories costs 16 KB of operand stores and 24 KB of MMA operand reads per 192 tensor-core clocks -- 208 B/clk
 // against the 128 B/clk of the shared-memory port -- so the activation operand goes through TENSOR MEMORY instead:
-//   warps 0..3 (A role, thread = unit k = TMEM lane): (a, p', p'') of 8 trajectories -> operand jets (a, a', a'') and their
-//              tf32 remainders -> tcgen05.st, per slot [jet][hi 8 | lo 8] = 48 columns;
-//   warps 4..7 (P role, thread = unit j): cotangent jets as stored -> (hi, lo) K-major operands in shared memory;
-//   warp 8   : D[k 128][j 128] += A_hi . P_hi + A_lo . P_hi + A_hi . P_lo per (block, jet)  (TS-mode M128 N128 K8; the
-//              lo.lo term is dropped), tcgen05.commit frees the slot.  Its warpgroup hands its registers to the staging
-//              warpgroups (setmaxnreg: 40 / 232), which hold 64 fp32 accumulators and the loads in flight.
-// The HBM loads run kDw3PF blocks ahead in registers (they are the latency of the loop: ~1 us each); four operand slots;
-// two accumulator sets of 128 columns alternate every kDw3Flush blocks and are drained into fp32 registers by all eight
-// staging warps because tensor-core accumulation truncates.  One CTA per SM: 16 tiles x 9 splits.
+//   warps 0..7  (A role, thread = unit k = TMEM lane; the two warps of a lane quadrant take the even / the odd blocks):
+//               (a, p', p'') of 8 trajectories -> operand jets (a, a', a'') and their tf32 remainders -> tcgen05.st, per
+//               slot [jet][hi 8 | lo 8] = 48 columns; they also keep the 64 fp32 accumulators per thread;
+//   warps 8..11 (P role): cotangent jets as stored -> (hi, lo) K-major operands in shared memory;
+//   warp 12    : D[k 128][j 128] += A_hi . P_hi + A_lo . P_hi + A_hi . P_lo per (block, jet)  (TS-mode M128 N128 K8; the
+//               lo.lo term is dropped), tcgen05.commit frees the slot.  setmaxnreg moves the register file to where it is
+//               needed: 176 (A) / 120 (P) / 40 (MMA warpgroup).
+// The HBM loads run 2 (A: 4 blocks of the stream) / 3 (P) blocks ahead in registers; four operand slots; two accumulator
+// sets of 128 columns alternate every kDw3Flush blocks and are drained into fp32 registers by the A warps because
+// tensor-core accumulation truncates.  Blocks whose cotangent jets p', p'' are exactly zero (rows whose logp / score the
+// loss does not use; flagged per (evaluation, 8-row tile) by the sweep's head kernel) are contracted over jet 0 only.
+// One CTA per SM: 16 tiles x 9 splits, or 16 x 5 beside the sweep.
 // ------------------------------------------------------------------------------------------------
-constexpr int kDw3Slots = 4;
+#ifndef OFDFT_DW_SLOTS
+#define OFDFT_DW_SLOTS 4
+#endif
+constexpr int kDw3Slots = OFDFT_DW_SLOTS;
 constexpr int kDw3Flush = 32;     // blocks per TMEM accumulation chain: 32 x 9 = 288 MMAs
-constexpr int kDw3PF = 4;         // HBM blocks in flight per staging thread
 constexpr int kDw3Splits = 9;     // 16 tiles x 9 = 144 CTAs on 148 SMs
-constexpr int kDw3Threads = 12 * 32;   // two staging warpgroups + the MMA-issue warpgroup (one active warp)
+constexpr int kDw3Threads = 16 * 32;   // two activation-operand warpgroups, the cotangent-operand warpgroup, the MMA-issue warpgroup
 constexpr int kDw3ColA = 256;     // TMEM: accumulator sets at 0 and 128, operand ring from 256
 // SL = true: the operands are read straight from per-evaluation layer buffers ([jet][H/4][rows_pad][4], what the layer GEMMs
 // read and write anyway) instead of HBM blocks: block b = (evaluation b / n_tiles, rows 8 (b % n_tiles)..).  A thread's unit
@@ -688,6 +693,8 @@ struct DwSrc {
   const float* a; const float* p;                 // layer buffers of evaluation 0: activations of layer - 1, cotangents of layer
   size_t a_ev, p_ev;                              // strides between evaluations (floats)
   long long rows_pad, rows; int n_tiles;
+  const unsigned char* live;                      // per block: 0 = the cotangent jets p', p'' of all 8 rows are exactly zero (rows
+                                                  // whose logp / score outputs the loss does not use): only jet 0 is contracted
 };
 // 4x4 transpose across the four lanes of a quad: lane i holds row i (x, y, z, w = columns 0..3) and ends with column i
 __device__ __forceinline__ float4 quad_transpose(float4 v, int i) {
@@ -701,12 +708,213 @@ __device__ __forceinline__ float4 quad_transpose(float4 v, int i) {
   return v;
 }
 
+constexpr int kDw3Sbo = 36;                       // floats between 8-unit core matrices of the cotangent operand (144 B)
+constexpr int kDw3Lbo = 16 * kDw3Sbo;             // floats between its 4-row chunks (128 units)
 struct Dw3Smem {
-  float Ph[kDw3Slots][3][2 * 128 * 4];            // [slot][jet][chunk of 4 traj][row j 128][4]
-  float Pl[kDw3Slots][3][2 * 128 * 4];
+  // cotangent operand, K-major: [slot][jet][chunk of 4 rows][group of 8 units j: 36 floats][unit: 4 rows].  The 8-unit core
+  // matrices are 144 B apart (SBO; 16 B of padding) so that the layer-buffer path can store a float4 = 4 units of one row
+  // as four scalar stores without bank conflicts (lane quad -> row within the chunk, 8 quads -> 8 unit groups)
+  float Ph[kDw3Slots][3][2 * kDw3Lbo];
+  float Pl[kDw3Slots][3][2 * kDw3Lbo];
   uint64_t full[kDw3Slots], empty[kDw3Slots], accf[2], acce[2];
   unsigned int tmem_slot;
+  int nj[kDw3Slots];                              // jets staged in the slot (staging warps -> MMA warp)
 };
+
+// staging loop of one warp.  ROLE_P = false: activation operand -> tensor memory; the two warps of a lane quadrant take the
+// even / the odd blocks (one warp alone is latency-bound at ~2400 clocks per block against 576 of MMA) and both keep 64
+// fp32 accumulators of the tile.  ROLE_P = true: cotangent operand -> shared memory, every block.
+template <bool SL, bool ROLE_P>
+__device__ __forceinline__ void dw3_staging(Dw3Smem& sm, const float* __restrict__ acts, const float* __restrict__ pbar,
+                                            float* __restrict__ part, int H, int L, int layer, long long b_begin, int n_it,
+                                            const DwSrc& src, int accumulate, uint32_t tmem, int w, int lane, int k0, int j0, int sp) {
+  constexpr int PF = ROLE_P ? 3 : 2;                           // blocks of this warp in flight (HBM loads in registers)
+  const int step = ROLE_P ? 1 : 2, it_first = ROLE_P ? 0 : (w >> 2);
+  const int u = 32 * (w & 3) + lane;                           // unit row of the tile (A role: TMEM lane)
+  const uint32_t tl = tmem + ((uint32_t)(32 * (w & 3)) << 16);
+  float acc[ROLE_P ? 1 : 64];                                  // A role: row 32 (w & 3) + lane, columns 64 (w >> 2) ..
+#pragma unroll
+  for (int i = 0; i < (ROLE_P ? 1 : 64); ++i) acc[i] = 0.f;
+  const size_t blk_stride = ROLE_P ? (size_t)(L - 1) * 3 * H * kTT : (size_t)L * 3 * H * kTT;
+  const int unit = (ROLE_P ? j0 : k0) + u;
+  // SL: lane i of the quad loads rows i and i + 4 of the quad's unit group
+  const float* src0 = SL ? (ROLE_P ? src.p : src.a) + ((size_t)(unit >> 2) * src.rows_pad + (lane & 3)) * 4
+                         : (ROLE_P ? pbar + pb_blk(b_begin, layer, H, L) : acts + act_blk(b_begin, layer - 1, H, L)) + (size_t)unit * kTT;
+  const size_t jet = SL ? (size_t)src.rows_pad * H : (size_t)H * kTT;
+  const size_t ev_stride = ROLE_P ? src.p_ev : src.a_ev;
+  float4 pf[PF][3][2];
+  int pfn[PF];                                                 // jets of the block in each prefetch slot (1 or 3)
+#pragma unroll
+  for (int q = 0; q < PF; ++q) pfn[q] = 3;
+  // (evaluation, tile) of the next block this warp loads: its blocks are loaded in order, one division up front
+  int ld_ev = 0, ld_tile = 0;
+  if (SL) { ld_ev = (int)((b_begin + it_first) / src.n_tiles); ld_tile = (int)(b_begin + it_first - (long long)ld_ev * src.n_tiles); }
+  auto load_blk = [&](float4 (&R)[3][2], int& nj, int it) {
+    nj = 3;
+    if (SL) {
+      const long long row0 = (long long)ld_tile * kTT;
+      const float* sp_ = src0 + (size_t)ld_ev * ev_stride + (size_t)row0 * 4;
+      const long long r_lo = row0 + (lane & 3);                // rows beyond the batch contribute nothing
+      if (src.live != nullptr) {                               // one byte for the whole CTA; the shuffle tells the compiler so
+        const int lv = __shfl_sync(0xffffffffu, (int)src.live[(size_t)ld_ev * src.n_tiles + ld_tile], 0);
+        if (lv == 0) nj = 1;
+      }
+      ld_tile += step;
+      while (ld_tile >= src.n_tiles) { ld_tile -= src.n_tiles; ++ld_ev; }
+#pragma unroll
+      for (int jt = 0; jt < 3; ++jt) {
+        if (jt >= nj) break;
+        R[jt][0] = r_lo < src.rows ? __ldg(reinterpret_cast<const float4*>(sp_ + jt * jet)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        R[jt][1] = r_lo + 4 < src.rows ? __ldg(reinterpret_cast<const float4*>(sp_ + jt * jet + 16)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      return;
+    }
+    const float* sp_ = src0 + (size_t)it * blk_stride;
+#pragma unroll
+    for (int jt = 0; jt < 3; ++jt) {
+      R[jt][0] = __ldg(reinterpret_cast<const float4*>(sp_ + jt * jet));
+      R[jt][1] = __ldg(reinterpret_cast<const float4*>(sp_ + jt * jet + 4));
+    }
+  };
+  // accumulation chain c (blocks 32 c .. 32 c + 31, accumulator set c & 1) -> fp32 registers
+  auto drain = [&](int c) {
+    const int set = c & 1;
+    tc::mbar_wait(&sm.accf[set], (uint32_t)(c >> 1) & 1u);
+    __syncwarp();
+    tc::fence_after_sync();
+#pragma unroll
+    for (int c0 = 0; c0 < (ROLE_P ? 0 : 64); c0 += 16) {
+      float t[16];
+      tc::tmem_ld16(tl + 128 * set + 64 * (w >> 2) + c0, t);
+      tc::tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) acc[c0 + i] += t[i];
+    }
+    tc::fence_before_sync();
+    __syncwarp();
+    if (lane == 0) tc::mbar_arrive(&sm.acce[set]);
+  };
+  int drained = 0;
+#pragma unroll
+  for (int q = 0; q < PF; ++q)
+    if (it_first + q * step < n_it) load_blk(pf[q], pfn[q], it_first + q * step);
+  const tc::f32x2 one2 = tc::splat2(1.0f), m1 = tc::splat2(-1.0f), two2 = tc::splat2(2.0f);
+  auto lo2x = [&](tc::f32x2 x) { return tc::fma2(x & 0xFFFFE000FFFFE000ull, m1, x); };      // x - trunc_tf32(x), two lanes
+  // one block: registers R (A role: this thread's unit, 8 rows x 3 jets after the transposition) -> operand slot s
+  auto stage = [&](float4 (&R)[3][2], int nj, int it) {
+    using namespace tc;
+    const int s = it % kDw3Slots;
+    if (SL && !ROLE_P) {                                       // tensor memory wants lane = unit: transpose the quad's 4 x 4 tiles
+#pragma unroll
+      for (int jt = 0; jt < 3; ++jt) {
+        if (jt >= nj) break;
+        R[jt][0] = quad_transpose(R[jt][0], lane & 3); R[jt][1] = quad_transpose(R[jt][1], lane & 3);
+      }
+    }
+    // use k = it / 4 of the slot: free once the MMAs of use k - 1 have completed
+    if (it >= kDw3Slots) mbar_wait(&sm.empty[s], (uint32_t)(it / kDw3Slots - 1) & 1u);
+    if (!ROLE_P) {
+      __syncwarp();
+      fence_after_sync();
+      const uint32_t col = tl + kDw3ColA + 48 * s;
+      if (nj == 1) {                                           // only the activations themselves are contracted
+        float v0[16];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float4 A4 = R[0][e >> 1];
+          const f32x2 av = (e & 1) ? pack2(A4.z, A4.w) : pack2(A4.x, A4.y);
+          unpack2(av, v0[2 * e], v0[2 * e + 1]); unpack2(lo2x(av), v0[8 + 2 * e], v0[9 + 2 * e]);
+        }
+        tmem_st16(col, v0);
+      } else {
+        float v0[16], v1[16], v2[16];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float4 A4 = R[0][e >> 1], P4 = R[1][e >> 1], Q4 = R[2][e >> 1];
+          const f32x2 av = (e & 1) ? pack2(A4.z, A4.w) : pack2(A4.x, A4.y);
+          const f32x2 p1 = (e & 1) ? pack2(P4.z, P4.w) : pack2(P4.x, P4.y);
+          const f32x2 p2 = (e & 1) ? pack2(Q4.z, Q4.w) : pack2(Q4.x, Q4.y);
+          const f32x2 na = mul2(av, m1);
+          const f32x2 sg = fma2(na, av, one2);                                  // 1 - a^2
+          const f32x2 j1 = mul2(sg, p1);                                        // a' = (1 - a^2) p'
+          const f32x2 j2 = fma2(sg, p2, mul2(mul2(mul2(na, two2), j1), p1));    // a'' = (1 - a^2) p'' - 2 a a' p'
+          const f32x2 l0 = lo2x(av), l1 = lo2x(j1), l2 = lo2x(j2);
+          unpack2(av, v0[2 * e], v0[2 * e + 1]); unpack2(l0, v0[8 + 2 * e], v0[9 + 2 * e]);
+          unpack2(j1, v1[2 * e], v1[2 * e + 1]); unpack2(l1, v1[8 + 2 * e], v1[9 + 2 * e]);
+          unpack2(j2, v2[2 * e], v2[2 * e + 1]); unpack2(l2, v2[8 + 2 * e], v2[9 + 2 * e]);
+        }
+        tmem_st16(col, v0);
+        tmem_st16(col + 16, v1);
+        tmem_st16(col + 32, v2);
+      }
+      tmem_st_wait();
+      fence_before_sync();
+    } else {
+      if (w == 8 && lane == 0) sm.nj[s] = nj;                  // read by the MMA warp after this slot's full barrier
+#pragma unroll
+      for (int jt = 0; jt < 3; ++jt) {
+        if (jt >= nj) break;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const float4 v = R[jt][c];
+          const f32x2 lxy = lo2x(pack2(v.x, v.y)), lzw = lo2x(pack2(v.z, v.w));
+          const float4 l = make_float4(lo2(lxy), hi2(lxy), lo2(lzw), hi2(lzw));
+          if (SL) {
+            // v = units 4 (u >> 2) .. + 3 at row 4 c + (lane & 3): element (unit n, row) sits at chunk c, group n / 8, n % 8, row % 4
+            const int n0 = u & ~3;
+            float* ph = &sm.Ph[s][jt][c * kDw3Lbo + (n0 >> 3) * kDw3Sbo + (n0 & 7) * 4 + (lane & 3)];
+            float* pl = &sm.Pl[s][jt][c * kDw3Lbo + (n0 >> 3) * kDw3Sbo + (n0 & 7) * 4 + (lane & 3)];
+            ph[0] = v.x; ph[4] = v.y; ph[8] = v.z; ph[12] = v.w;
+            pl[0] = l.x; pl[4] = l.y; pl[8] = l.z; pl[12] = l.w;
+          } else {
+            const int off = c * kDw3Lbo + (u >> 3) * kDw3Sbo + (u & 7) * 4;      // v = rows 4 c .. + 3 of unit u
+            *reinterpret_cast<float4*>(&sm.Ph[s][jt][off]) = v;
+            *reinterpret_cast<float4*>(&sm.Pl[s][jt][off]) = l;
+          }
+        }
+      }
+      fence_async_smem();
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&sm.full[s]);
+    // chain c is drained a few blocks into chain c + 1, when its MMAs have long finished
+    if (!ROLE_P) {
+      while (it >= 3 && drained < (it - 3) / kDw3Flush) { drain(drained); ++drained; }
+    }
+  };
+#pragma unroll 1
+  for (int it0 = it_first; it0 < n_it; it0 += PF * step) {
+#pragma unroll
+    for (int q = 0; q < PF; ++q) {                             // static register indices: no rotation moves
+      const int it = it0 + q * step;
+      if (it < n_it) {
+        // the loop is bound by the latency of these loads: the next ones go out BEFORE this block is staged (4.8 -> 4.2 ms
+        // per step against issuing them afterwards; an additional L2 prefetch 8..32 blocks ahead changed nothing)
+        float4 R[3][2];
+        const int nj = pfn[q];
+#pragma unroll
+        for (int jt = 0; jt < 3; ++jt) { R[jt][0] = pf[q][jt][0]; R[jt][1] = pf[q][jt][1]; }
+        if (it + PF * step < n_it) load_blk(pf[q], pfn[q], it + PF * step);
+        stage(R, nj, it);
+      }
+    }
+  }
+  if (!ROLE_P) {
+    const int n_chains = (n_it + kDw3Flush - 1) / kDw3Flush;
+    while (drained < n_chains) { drain(drained); ++drained; }
+    const int r = 32 * (w & 3) + lane;
+    float* out = part + ((size_t)sp * H + (k0 + r)) * H + j0 + 64 * (w >> 2);
+#pragma unroll
+    for (int i = 0; i < 64; i += 4) {
+      float4 o = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
+      if (accumulate) {                                        // a later chunk of evaluations (same CTA <-> same slots, launches ordered)
+        const float4 p = *reinterpret_cast<const float4*>(out + i);
+        o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+      }
+      *reinterpret_cast<float4*>(out + i) = o;
+    }
+  }
+}
 
 template <bool SL>
 __global__ void __launch_bounds__(kDw3Threads, 1) mlp_dw_gemm_ts_kernel(const float* __restrict__ acts, const float* __restrict__ pbar,
@@ -733,27 +941,32 @@ __global__ void __launch_bounds__(kDw3Threads, 1) mlp_dw_gemm_ts_kernel(const fl
   const long long b_begin = blk0 + sp * per, b_end = blk0 + (sp * per + per < n_blocks ? sp * per + per : n_blocks);
   const int n_it = b_end > b_begin ? (int)(b_end - b_begin) : 0;
 
-  // 384 threads x 168 registers at launch; asking for more than was allocated would make setmaxnreg.inc wait forever
-  static_assert(256 * 232 + 128 * 40 <= 168 * kDw3Threads, "setmaxnreg budget exceeds the registers allocated at launch");
-  if (w >= 8) {
-    // ---------------- MMA issue warp (warps 9..11 only donate their registers) ----------------
+  // warps 0..7: activation operand (two per lane quadrant, alternating blocks) + the fp32 accumulators; warps 8..11: cotangent
+  // operand; warp 12: MMA issue (13..15 only donate their registers).  512 threads x 128 registers at launch; asking for more
+  // than was allocated would make setmaxnreg.inc wait forever
+  static_assert(256 * 176 + 128 * 120 + 128 * 40 <= 128 * kDw3Threads, "setmaxnreg budget exceeds the registers allocated at launch");
+  if (w >= 12) {
+    // ---------------- MMA issue warp ----------------
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     const uint32_t idesc = tc::make_idesc_tf32(128, 128, 0, 0);
     uint32_t ph_full = 0, ph_acce = 0;
 #pragma unroll 1
-    for (int it = 0; it < (w == 8 ? n_it : 0); ++it) {
+    for (int it = 0; it < (w == 12 ? n_it : 0); ++it) {
       const int s = it % kDw3Slots, set = (it / kDw3Flush) & 1;
       const bool first = (it % kDw3Flush) == 0;
       tc::mbar_wait(&sm.full[s], (ph_full >> s) & 1u); ph_full ^= 1u << s;
       if (first && it >= 2 * kDw3Flush) { tc::mbar_wait(&sm.acce[set], (ph_acce >> set) & 1u); ph_acce ^= 1u << set; }
       __syncwarp();
       tc::fence_after_sync();
+      const int nj = *reinterpret_cast<volatile int*>(&sm.nj[s]);
       if (tc::elect_one()) {
         const uint32_t d = tmem + 128 * set;
 #pragma unroll
         for (int jt = 0; jt < 3; ++jt) {
+          if (jt >= nj) break;
           const uint32_t ahi = tmem + kDw3ColA + 48 * s + 16 * jt, alo = ahi + 8;
-          const uint64_t ph = tc::make_desc(tc::smem_u32(sm.Ph[s][jt]), 128 * 16, 128), pl = tc::make_desc(tc::smem_u32(sm.Pl[s][jt]), 128 * 16, 128);
+          const uint64_t ph = tc::make_desc(tc::smem_u32(sm.Ph[s][jt]), kDw3Lbo * 4, kDw3Sbo * 4);
+          const uint64_t pl = tc::make_desc(tc::smem_u32(sm.Pl[s][jt]), kDw3Lbo * 4, kDw3Sbo * 4);
           tc::mma_tf32_ts(d, ahi, ph, idesc, !(first && jt == 0));
           tc::mma_tf32_ts(d, alo, ph, idesc, true);
           tc::mma_tf32_ts(d, ahi, pl, idesc, true);
@@ -763,149 +976,12 @@ __global__ void __launch_bounds__(kDw3Threads, 1) mlp_dw_gemm_ts_kernel(const fl
       }
       __syncwarp();
     }
+  } else if (w >= 8) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 120;");
+    dw3_staging<SL, true>(sm, acts, pbar, part, H, L, layer, b_begin, n_it, src, accumulate, tmem, w, lane, k0, j0, sp);
   } else {
-    // ---------------- staging warps ----------------
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
-    const bool role_p = w >= 4;
-    const int u = tid & 127;                                   // unit row of the tile (A role: TMEM lane)
-    const uint32_t tl = tmem + ((uint32_t)(32 * (w & 3)) << 16);
-    float acc[64];                                             // row 32 (w & 3) + lane, columns 64 (w >> 2) ..
-#pragma unroll
-    for (int i = 0; i < 64; ++i) acc[i] = 0.f;
-    uint32_t ph_empty = 0, ph_accf = 0;
-    const size_t blk_stride = role_p ? (size_t)(L - 1) * 3 * H * kTT : (size_t)L * 3 * H * kTT;
-    const int unit = (role_p ? j0 : k0) + u;
-    // SL: lane i of the quad loads rows i and i + 4 of the quad's unit group
-    const float* src0 = SL ? (role_p ? src.p : src.a) + ((size_t)(unit >> 2) * src.rows_pad + (lane & 3)) * 4
-                           : (role_p ? pbar + pb_blk(b_begin, layer, H, L) : acts + act_blk(b_begin, layer - 1, H, L)) + (size_t)unit * kTT;
-    const size_t jet = SL ? (size_t)src.rows_pad * H : (size_t)H * kTT;
-    const size_t ev_stride = role_p ? src.p_ev : src.a_ev;
-    float4 pf[kDw3PF][3][2];
-    auto load_blk = [&](float4 (&R)[3][2], int it) {
-      if (SL) {
-        const long long b = b_begin + it;
-        const long long ev = b / src.n_tiles, row0 = (b - ev * src.n_tiles) * kTT;
-        const float* sp_ = src0 + (size_t)ev * ev_stride + (size_t)row0 * 4;
-        const long long r_lo = row0 + (lane & 3);             // rows beyond the batch contribute nothing
-#pragma unroll
-        for (int jt = 0; jt < 3; ++jt) {
-          R[jt][0] = r_lo < src.rows ? __ldg(reinterpret_cast<const float4*>(sp_ + jt * jet)) : make_float4(0.f, 0.f, 0.f, 0.f);
-          R[jt][1] = r_lo + 4 < src.rows ? __ldg(reinterpret_cast<const float4*>(sp_ + jt * jet + 16)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        return;
-      }
-      const float* sp_ = src0 + (size_t)it * blk_stride;
-#pragma unroll
-      for (int jt = 0; jt < 3; ++jt) {
-        R[jt][0] = __ldg(reinterpret_cast<const float4*>(sp_ + jt * jet));
-        R[jt][1] = __ldg(reinterpret_cast<const float4*>(sp_ + jt * jet + 4));
-      }
-    };
-    auto drain = [&](int set) {
-      tc::mbar_wait(&sm.accf[set], (ph_accf >> set) & 1u); ph_accf ^= 1u << set;
-      __syncwarp();
-      tc::fence_after_sync();
-#pragma unroll
-      for (int c0 = 0; c0 < 64; c0 += 16) {
-        float t[16];
-        tc::tmem_ld16(tl + 128 * set + 64 * (w >> 2) + c0, t);
-        tc::tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 16; ++i) acc[c0 + i] += t[i];
-      }
-      tc::fence_before_sync();
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&sm.acce[set]);
-    };
-#pragma unroll
-    for (int q = 0; q < kDw3PF; ++q)
-      if (q < n_it) load_blk(pf[q], q);
-    static_assert(kDw3PF == kDw3Slots, "the unrolled staging loop indexes the prefetch registers and the operand slots together");
-    const tc::f32x2 one2 = tc::splat2(1.0f), m1 = tc::splat2(-1.0f), two2 = tc::splat2(2.0f);
-    auto lo2x = [&](tc::f32x2 x) { return tc::fma2(x & 0xFFFFE000FFFFE000ull, m1, x); };      // x - trunc_tf32(x), two lanes
-    // one block: registers R (this thread's unit, 8 rows x 3 jets) -> operand slot s; two values per FP32 instruction
-    auto stage = [&](float4 (&R)[3][2], int it, int s) {
-      using namespace tc;
-      if (SL) {
-#pragma unroll
-        for (int jt = 0; jt < 3; ++jt) { R[jt][0] = quad_transpose(R[jt][0], lane & 3); R[jt][1] = quad_transpose(R[jt][1], lane & 3); }
-      }
-      if (it >= kDw3Slots) { mbar_wait(&sm.empty[s], (ph_empty >> s) & 1u); ph_empty ^= 1u << s; }
-      if (!role_p) {
-        __syncwarp();
-        fence_after_sync();
-        float v0[16], v1[16], v2[16];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float4 A4 = R[0][e >> 1], P4 = R[1][e >> 1], Q4 = R[2][e >> 1];
-          const f32x2 av = (e & 1) ? pack2(A4.z, A4.w) : pack2(A4.x, A4.y);
-          const f32x2 p1 = (e & 1) ? pack2(P4.z, P4.w) : pack2(P4.x, P4.y);
-          const f32x2 p2 = (e & 1) ? pack2(Q4.z, Q4.w) : pack2(Q4.x, Q4.y);
-          const f32x2 na = mul2(av, m1);
-          const f32x2 sg = fma2(na, av, one2);                                  // 1 - a^2
-          const f32x2 j1 = mul2(sg, p1);                                        // a' = (1 - a^2) p'
-          const f32x2 j2 = fma2(sg, p2, mul2(mul2(mul2(na, two2), j1), p1));    // a'' = (1 - a^2) p'' - 2 a a' p'
-          const f32x2 l0 = lo2x(av), l1 = lo2x(j1), l2 = lo2x(j2);
-          unpack2(av, v0[2 * e], v0[2 * e + 1]); unpack2(l0, v0[8 + 2 * e], v0[9 + 2 * e]);
-          unpack2(j1, v1[2 * e], v1[2 * e + 1]); unpack2(l1, v1[8 + 2 * e], v1[9 + 2 * e]);
-          unpack2(j2, v2[2 * e], v2[2 * e + 1]); unpack2(l2, v2[8 + 2 * e], v2[9 + 2 * e]);
-        }
-        const uint32_t col = tl + kDw3ColA + 48 * s;
-        tmem_st16(col, v0);
-        tmem_st16(col + 16, v1);
-        tmem_st16(col + 32, v2);
-        tmem_st_wait();
-        fence_before_sync();
-      } else {
-#pragma unroll
-        for (int jt = 0; jt < 3; ++jt)
-#pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            const float4 v = R[jt][c];
-            const int off = (c * 128 + u) * 4;
-            const f32x2 lxy = lo2x(pack2(v.x, v.y)), lzw = lo2x(pack2(v.z, v.w));
-            *reinterpret_cast<float4*>(&sm.Ph[s][jt][off]) = v;
-            *reinterpret_cast<float4*>(&sm.Pl[s][jt][off]) = make_float4(lo2(lxy), hi2(lxy), lo2(lzw), hi2(lzw));
-          }
-        fence_async_smem();
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sm.full[s]);
-      // chain c = it / kDw3Flush is drained a few blocks into the next one, when its MMAs have long finished
-      if (it >= kDw3Flush && (it % kDw3Flush) == kDw3Slots - 1) drain(((it / kDw3Flush) - 1) & 1);
-    };
-#pragma unroll 1
-    for (int it0 = 0; it0 < n_it; it0 += kDw3PF) {
-#pragma unroll
-      for (int q = 0; q < kDw3PF; ++q) {                       // static register / slot indices: no rotation moves
-        const int it = it0 + q;
-        if (it < n_it) {
-          // the loop is bound by the latency of these loads: the next ones go out BEFORE this block is staged (4.8 -> 4.2 ms
-          // per step against issuing them afterwards; an additional L2 prefetch 8..32 blocks ahead changed nothing)
-          float4 R[3][2];
-#pragma unroll
-          for (int jt = 0; jt < 3; ++jt) { R[jt][0] = pf[q][jt][0]; R[jt][1] = pf[q][jt][1]; }
-          if (it + kDw3PF < n_it) load_blk(pf[q], it + kDw3PF);
-          stage(R, it, q);
-        }
-      }
-    }
-    if (n_it > 0) {
-      const int last = (n_it - 1) / kDw3Flush;                 // chains not drained inside the loop: `last`, and last-1 if the
-      if (last >= 1 && (n_it - 1) % kDw3Flush < kDw3Slots - 1) drain((last - 1) & 1);   // loop ended before its drain point
-      drain(last & 1);
-    }
-    const int r = 32 * (w & 3) + lane;
-    float* out = part + ((size_t)sp * H + (k0 + r)) * H + j0 + 64 * (w >> 2);
-#pragma unroll
-    for (int i = 0; i < 64; i += 4) {
-      float4 o = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
-      if (accumulate) {                                        // a later chunk of evaluations (same CTA <-> same slots, launches ordered)
-        const float4 p = *reinterpret_cast<const float4*>(out + i);
-        o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
-      }
-      *reinterpret_cast<float4*>(out + i) = o;
-    }
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 176;");
+    dw3_staging<SL, false>(sm, acts, pbar, part, H, L, layer, b_begin, n_it, src, accumulate, tmem, w, lane, k0, j0, sp);
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -958,7 +1034,7 @@ static SideStream* side_stream() {
 }
 struct DwOverlapCtx {
   cudaStream_t main; SideStream* side; float* part; const float* actS; const float* pbar;
-  int H, L, splits, launched; long long rows, n_tiles;
+  int H, L, splits, launched; long long rows, n_tiles; const unsigned char* live;
 };
 static int dw_overlap_launch(void* vctx, int ev_lo, int ev_hi) {
   DwOverlapCtx& c = *static_cast<DwOverlapCtx*>(vctx);
@@ -973,7 +1049,7 @@ static int dw_overlap_launch(void* vctx, int ev_lo, int ev_hi) {
 #endif
   for (int l = 1; l < c.L; ++l) {
     DwSrc src{c.actS + (size_t)(l - 1) * sbuf, c.pbar + (size_t)(l - 1) * sbuf, (size_t)c.L * sbuf, (size_t)(c.L - 1) * sbuf, rows_pad, c.rows,
-              (int)c.n_tiles};
+              (int)c.n_tiles, c.live};
     mlp_dw_gemm_ts_kernel<true><<<gg, kDw3Threads, sizeof(Dw3Smem) + 1024, c.side->s>>>(
         nullptr, nullptr, c.part + (size_t)(l - 1) * c.splits * c.H * c.H, c.H, c.L, l, (long long)ev_lo * c.n_tiles,
         (long long)(ev_hi - ev_lo) * c.n_tiles, c.splits, src, c.launched);
@@ -1142,6 +1218,9 @@ extern "C" int ofdft_cnf_mlp1d_bwd(void* stream, const float* theta, const float
       const int gemm_ctas = (int)((rows + 127) / 128) * (H / 64), tiles = (H / 128) * (H / 128);
       int ov_splits = (sms - gemm_ctas) / tiles;
       if (ov_splits > kDwSplits / (L - 1)) ov_splits = kDwSplits / (L - 1);
+#ifdef OFDFT_DW_OV_SPLITS   // development: cap the SMs the overlapped weight-gradient GEMM takes
+      if (ov_splits > OFDFT_DW_OV_SPLITS) ov_splits = OFDFT_DW_OV_SPLITS;
+#endif
 #ifdef OFDFT_ABL_DWEND      // timing ablation: weight-gradient GEMM after the sweep instead of beside it
       ov_splits = 0;
 #endif
@@ -1150,7 +1229,7 @@ extern "C" int ofdft_cnf_mlp1d_bwd(void* stream, const float* theta, const float
         side_lock = std::unique_lock<std::mutex>(side->busy);
         e = cudaFuncSetAttribute(mlp_dw_gemm_ts_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Dw3Smem) + 1024);
         if (e != cudaSuccess) return (int)e;
-        ov = DwOverlapCtx{st, side, part, ckpt + AL.s / 4, a.pbar, H, L, ov_splits, 0, rows, n_tiles};
+        ov = DwOverlapCtx{st, side, part, ckpt + AL.s / 4, a.pbar, H, L, ov_splits, 0, rows, n_tiles, (const unsigned char*)(sc + SL.bwd_live)};
         hook = MlpDwHook{kDwGroup, &ov, dw_overlap_launch};
       }
     }
@@ -1166,7 +1245,8 @@ extern "C" int ofdft_cnf_mlp1d_bwd(void* stream, const float* theta, const float
       const int rc2 = launch_mlp_bwd_sweep_tc(stream, theta, (float*)(sc + SL.wbi), Wclo, WTc, WTlo, ckpt, ybar1, ybar0, S, (float*)(sc + SL.bwd_pb),
                                               (float*)(sc + SL.bwd_pb + sb), (float*)(sc + SL.bwd_bst), (float*)(sc + SL.bwd_xpart),
                                               gsmall, a.acts, a.pbar, B, r0, rows, stride, H, L, n_steps, t0, t1, y0sign,
-                                              act ? ckpt + AL.s / 4 : nullptr, hook.launch != nullptr ? &hook : nullptr);
+                                              act ? ckpt + AL.s / 4 : nullptr, hook.launch != nullptr ? &hook : nullptr,
+                                              act ? (unsigned char*)(sc + SL.bwd_live) : nullptr);
       if (rc2) return rc2;
       grid = (int)n_tiles;                       // small-gradient slots: one per 8-row tile (<= 256 per chunk)
     } else {
@@ -1199,7 +1279,7 @@ extern "C" int ofdft_cnf_mlp1d_bwd(void* stream, const float* theta, const float
         if (act) {      // operands straight from the per-evaluation layer buffers (activations: forward; cotangents: this sweep)
           const size_t sbuf = al256(3 * (size_t)((rows + 127) / 128 * 128) * H * 4) / 4;
           DwSrc src{ckpt + AL.s / 4 + (size_t)(l - 1) * sbuf, a.pbar + (size_t)(l - 1) * sbuf, (size_t)L * sbuf, (size_t)(L - 1) * sbuf,
-                    (rows + 127) / 128 * 128, rows, (int)n_tiles};
+                    (rows + 127) / 128 * 128, rows, (int)n_tiles, (const unsigned char*)(sc + SL.bwd_live)};
           mlp_dw_gemm_ts_kernel<true><<<gg, kDw3Threads, sizeof(Dw3Smem) + 1024, st>>>(nullptr, nullptr, part, H, L, l, 0, n_blocks, kDw3Splits, src, 0);
         } else {
           mlp_dw_gemm_ts_kernel<false><<<gg, kDw3Threads, sizeof(Dw3Smem) + 1024, st>>>(a.acts, a.pbar, part, H, L, l, 0, n_blocks, kDw3Splits, DwSrc{}, 0);

@@ -52,7 +52,7 @@ struct ActLayout {
 };
 
 struct ScratchLayout {
-  size_t wc, wtc, wtlo, wclo, wbi, fwd_s, fwd_state, fwd_end, bwd_s, bwd_pb, bwd_bst, bwd_xpart, gsmall, part, acts, pbar, total;
+  size_t wc, wtc, wtlo, wclo, wbi, fwd_s, fwd_state, fwd_end, bwd_s, bwd_pb, bwd_bst, bwd_xpart, bwd_live, gsmall, part, acts, pbar, total;
   ScratchLayout(long long B, int H, int L, int n_steps) {
     const long long rows = B < kChunkRows ? B : kChunkRows;
     const long long n_tiles = (rows + kTT - 1) / kTT;
@@ -74,6 +74,7 @@ struct ScratchLayout {
     bwd_pb = o; o += 2 * al256(3 * rows_pad_c * H * 4);
     bwd_bst = o; o += al256(rows_pad_c * 8 * 4);
     bwd_xpart = o; o += al256((size_t)(H / 64 > 0 ? H / 64 : 1) * rows_pad_c * 4);
+    bwd_live = o; o += al256((size_t)n_blocks);           // one byte per (evaluation, 8-row tile): are the cotangent jets p', p'' live?
     gsmall = o; o += al256((size_t)256 * ThetaLayout(H, L).n_small() * 4);
     part = o; o += al256((size_t)kDwSplits * H * H * 4);
     acts = o; o += al256((size_t)n_blocks * L * 3 * H * kTT * 4);
@@ -105,7 +106,7 @@ int launch_mlp_bwd_sweep_tc(void* stream, const float* theta, const float* Wc, c
                             const float* WTlo, const float* ckpt, const float* ybar1, float* ybar0, float* const* S,
                             float* Pb0, float* Pb1, float* bst, float* xpart, float* gsmall, float* acts, float* pbar,
                             long long Bglob, long long r0, long long rows, int stride, int H, int L, int n_steps, float t0,
-                            float t1, float y0sign, const float* actS, const MlpDwHook* dw_hook);
+                            float t1, float y0sign, const float* actS, const MlpDwHook* dw_hook, unsigned char* live);
 
 }  // namespace mlp
 }  // namespace ofdft

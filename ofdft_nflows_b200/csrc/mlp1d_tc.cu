@@ -639,6 +639,7 @@ struct SweepArgs {
   int e;                   // head: stage being reversed
   float t0, t1, y0;
   int fused_tail;          // head: do the tail's row bookkeeping of stage e_done first (activation-checkpoint sweep)
+  unsigned char* live;     // head: per (stage, 8-row tile) flag for the weight-gradient GEMM: any cotangent jet p', p'' nonzero?
 };
 
 // RK4 adjoint bookkeeping of the stage just finished (threads 0..7 of a tile: one row each)
@@ -728,6 +729,12 @@ __global__ void __launch_bounds__(256) mlp_sweep_head_kernel(const SweepArgs g) 
   const float sst = g.ckpt[((long long)g.e * 2 + 1) * g.Bglob + g.r0 + rowc];
   // dx = y0 h ; dlogp = -y0 h' ; ds = -y0 (h' s + h'')
   const float hb0 = valid ? g.y0 * kx : 0.f, hb1 = valid ? -g.y0 * (kl + sst * ks) : 0.f, hb2 = valid ? -g.y0 * ks : 0.f;
+  if (g.live != nullptr) {
+    // rows whose logp / score cotangents are zero (the second half of a batch: the loss only uses their positions) keep
+    // p'-bar = p''-bar = 0 exactly through every layer; a tile made of such rows is contracted over jet 0 only
+    const int any = __syncthreads_or((hb1 != 0.f) | (hb2 != 0.f));
+    if (tid == 0) g.live[(size_t)g.e * gridDim.x + blockIdx.x] = (unsigned char)(any != 0);
+  }
   float h1 = 0.f;
   float* blk = g.pbar_last != nullptr ? g.pbar_last + (size_t)blockIdx.x * g.pb_tile_stride + t : nullptr;
   float* gsl = g.gsm + (size_t)blockIdx.x * TL.n_small();
@@ -791,7 +798,7 @@ int launch_mlp_bwd_sweep_tc(void* stream, const float* theta, const float* Wc, c
                             const float* WTlo, const float* ckpt, const float* ybar1, float* ybar0, float* const* S,
                             float* Pb0, float* Pb1, float* bst, float* xpart, float* gsmall, float* acts, float* pbar,
                             long long Bglob, long long r0, long long rows, int stride, int H, int L, int n_steps, float t0,
-                            float t1, float y0sign, const float* actS, const MlpDwHook* dw_hook) {
+                            float t1, float y0sign, const float* actS, const MlpDwHook* dw_hook, unsigned char* live) {
   cudaStream_t st = (cudaStream_t)stream;
   const long long rows_pad = (rows + 127) / 128 * 128;
   const long long n_tiles = (rows + 7) / 8;
@@ -824,7 +831,8 @@ int launch_mlp_bwd_sweep_tc(void* stream, const float* theta, const float* Wc, c
   sa.theta = theta; sa.ckpt = ckpt; sa.ybar1 = ybar1; sa.ybar0 = ybar0; sa.S0 = S[0]; sa.Slast = S[L - 1]; sa.Pb = Pb0; sa.bst = bst;
   sa.xpart = xpart; sa.gsm = gsmall; sa.act_tile_stride = act_tile; sa.pb_tile_stride = pb_tile; sa.Bglob = Bglob; sa.r0 = r0;
   sa.rows = rows; sa.rows_pad = rows_pad; sa.stride = stride; sa.H = H; sa.L = L; sa.n_steps = n_steps; sa.n_xpart = H / 64;
-  sa.t0 = t0; sa.t1 = t1; sa.y0 = y0sign;
+  sa.t0 = t0; sa.t1 = t1; sa.y0 = y0sign; sa.live = live;
+  int dw_next_hi = n_evals;
   for (int ev = n_evals - 1; ev >= -1; --ev) {
     // finish stage ev+1 (or initialise), prepare stage ev
     sa.e_done = ev + 1 < n_evals ? ev + 1 : -1; sa.e_next = ev;
@@ -863,10 +871,12 @@ int launch_mlp_bwd_sweep_tc(void* stream, const float* theta, const float* Wc, c
         if ((e = launch_pdl(mlp_layer_gemm_tc_kernel<3, 2>, gemm_grid, dim3(kGemmThreads), sizeof(GemmSmem) + 1024, st, gg)) != cudaSuccess) return (int)e;
       }
     }
-    if (dw_hook != nullptr && ev % dw_hook->group == 0) {
-      const int hi = ev + dw_hook->group < n_evals ? ev + dw_hook->group : n_evals;
-      const int rc = dw_hook->launch(dw_hook->ctx, ev, hi);
+    // hand finished evaluations to the weight-gradient GEMM: in groups, and one by one at the end of the sweep (what is
+    // handed over last runs after the sweep, exposed)
+    if (dw_hook != nullptr && (ev % dw_hook->group == 0 || ev < dw_hook->group)) {
+      const int rc = dw_hook->launch(dw_hook->ctx, ev, dw_next_hi);
       if (rc) return rc;
+      dw_next_hi = ev;
     }
     // the head of the next stage writes Pb0 again; MODE 1 outputs alternate between the two buffers
   }
