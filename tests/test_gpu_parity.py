@@ -807,3 +807,31 @@ def test_full_size_roundtrip_self_convergence_and_determinism():
     gm = (parts[0][1] + parts[1][1]) / 2
     assert np.allclose(sm.cpu().numpy()[:6], a[:6], rtol=1e-9)
     assert rel(gm.cpu().numpy(), g16.cpu().numpy()) < 1e-5
+
+
+def test_tensor_core_diagnostics():
+    """The two diagnostic entry points of the ABI (they ship in the library, so the suite launches them): a 3xTF32 GEMM through
+    shared-memory and tensor-memory operands against float64, and the tcgen05.mma timing probe DESIGN.md quotes."""
+    from ofdft_nflows_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(5)
+    A = rng.standard_normal((128, 64)).astype(np.float32); W = rng.standard_normal((64, 64)).astype(np.float32)
+    ref = A.astype(np.float64) @ W.astype(np.float64)
+    st = torch.cuda.current_stream().cuda_stream
+    a_d, w_d = dev(A), dev(W)
+    for passes, tol in ((3, 5e-6), (-1, 5e-6), (1, 2e-3)):      # SS 3xTF32, TS 3xTF32, plain TF32
+        d = torch.full((128, 64), float("nan"), device="cuda")
+        _lib.check(lib.ofdft_tc_gemm_test(st, a_d.data_ptr(), w_d.data_ptr(), d.data_ptr(), 128, passes), "tc_gemm_test")
+        torch.cuda.synchronize()
+        err = np.abs(d.cpu().numpy() - ref).max() / np.abs(ref).max()
+        assert err <= tol, (passes, err)
+    out = torch.zeros(1, dtype=torch.int64, device="cuda")
+    clk = {}
+    for ts in (0, 1):
+        for N in (64, 128):
+            _lib.check(lib.ofdft_tc_mma_rate(st, out.data_ptr(), N, ts, 1200, 1, 1), "tc_mma_rate")
+            torch.cuda.synchronize()
+            clk[(ts, N)] = int(out.item()) / 1200
+    # more columns cost more, and an activation operand in tensor memory never costs more than one in shared memory
+    assert 16 < clk[(1, 64)] < clk[(1, 128)] < 200 and clk[(1, 64)] <= clk[(0, 64)] and clk[(1, 128)] <= clk[(0, 128)], clk
+    assert lib.ofdft_tc_mma_rate(st, out.data_ptr(), 100, 0, 10, 1, 1) == -1
