@@ -405,6 +405,14 @@ constexpr int kRcWOff = 3 * kRcLoFloats;              // float offset of W2 hi (
 static_assert((kRcWOff + 2 * kH * kH) * 4 <= (int)(sizeof(float) * 32 * (kA1TChunk + kP2TChunk)), "recompute operands exceed the staging region");
 static_assert(offsetof(SmemTcB, P2T) == offsetof(SmemTcB, A1T) + sizeof(float) * 32 * kA1TChunk, "A1T and P2T must be contiguous");
 
+#ifdef OFDFT_BWD_WAITPROF    // development only: clocks the compute threads spend in each tensor-core wait (thread 0 of every CTA)
+__device__ unsigned long long g_waitprof[8];
+#define WP_T0 const long long wp_t0_ = clock64();
+#define WP_ADD(i) if (threadIdx.x == 0) atomicAdd(&g_waitprof[i], (unsigned long long)(clock64() - wp_t0_));
+#else
+#define WP_T0
+#define WP_ADD(i)
+#endif
 __device__ __forceinline__ void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
@@ -865,8 +873,10 @@ __device__ void bwd_tile_tc(SmemTcB& sm, const GnnBwdArgs& a, long long row0, lo
           if (jt == 1) G.g_b2 += warp_vec32_sum(q0, lane);
           // the shared-memory operands and the remainder buffer are free once the previous dW2 batch has completed
           // (its commit also covers the B1lo pass issued in front of it)
+          { WP_T0
           if (jt > 0) { tc::mbar_wait(&sm.barD[jt - 1], (phase >> (3 + jt - 1)) & 1u); phase ^= 1u << (3 + jt - 1); __syncwarp(); }
           else if (dw_pending) { tc::mbar_wait(&sm.barD[NJ - 1], (phase >> (3 + NJ - 1)) & 1u); phase ^= 1u << (3 + NJ - 1); __syncwarp(); }
+          WP_ADD(jt == 0 ? 0 : 1) }
           float pj[32];
           if (jt == 0) {
 #pragma unroll
@@ -923,7 +933,9 @@ __device__ void bwd_tile_tc(SmemTcB& sm, const GnnBwdArgs& a, long long row0, lo
             }
           }
           // the remainder buffer is free once the previous jet's B1lo pass (issued behind its dW2 batch) has completed
+          { WP_T0
           if (jt > 0) { tc::mbar_wait(&sm.barB[jt - 1], (phase >> (jt - 1)) & 1u); phase ^= 1u << (jt - 1); __syncwarp(); }
+          WP_ADD(2) }
 #pragma unroll
           for (int c0 = 0; c0 < 32; c0 += 16) {
             float l16[16];
@@ -939,7 +951,9 @@ __device__ void bwd_tile_tc(SmemTcB& sm, const GnnBwdArgs& a, long long row0, lo
         if (NJ == 1 && !kStageAccR) G.g_b2 += warp_vec32_sum(q0, lane);
         dw_pending = true;
         // the earlier B1 batches were retired before their remainder buffer was reused: wait for the last one
+        { WP_T0
         tc::mbar_wait(&sm.barB[NJ - 1], (phase >> (NJ - 1)) & 1u); phase ^= 1u << (NJ - 1);
+        WP_ADD(3) }
         __syncwarp();
         tc::fence_after_sync();
         // ---- layer-1 reverse from D_b1 (cotangent jets of a1 for trajectory m, units k = 32 uh ..) ----
@@ -992,7 +1006,9 @@ __device__ void bwd_tile_tc(SmemTcB& sm, const GnnBwdArgs& a, long long row0, lo
           sm.Rpart[par][uh * kTP + m] = rp;
           // fold the dW2 tile into the fp32 accumulators (row m, columns 32 uh ..)
           if (kFlushPerEval || i == a.Na - 1) {
+            { WP_T0
             tc::mbar_wait(&sm.barD[NJ - 1], (phase >> (3 + NJ - 1)) & 1u); phase ^= 1u << (3 + NJ - 1);
+            WP_ADD(4) }
             dw_pending = false;
             __syncwarp();
             tc::fence_after_sync();
@@ -1225,3 +1241,12 @@ int launch_gnn_fwd_tc(void* stream, GnnFwdArgs& a, void* scratch, size_t scratch
 }
 
 }  // namespace ofdft
+
+#ifdef OFDFT_BWD_WAITPROF
+extern "C" int ofdft_debug_waitprof(unsigned long long* host, int reset) {
+  cudaDeviceSynchronize();
+  cudaError_t e = cudaMemcpyFromSymbol(host, ofdft::g_waitprof, sizeof(unsigned long long) * 8);
+  if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(ofdft::g_waitprof, z, sizeof(z)); }
+  return (int)e;
+}
+#endif
