@@ -1224,6 +1224,9 @@ extern "C" int ofdft_cnf_mlp1d_bwd(void* stream, const float* theta, const float
 #ifdef OFDFT_ABL_DWEND      // timing ablation: weight-gradient GEMM after the sweep instead of beside it
       ov_splits = 0;
 #endif
+      // the GEMM only hides behind the sweep if it keeps up with it: at 1024 rows it needs 64 of its CTAs (measured: 4 splits
+      // 4.15 ms, 3 splits 5.3 ms against 3.7 ms of sweep), and its work grows with the rows while the sweep's time does not
+      if ((long long)ov_splits * 1024 < 4 * rows) ov_splits = 0;
       SideStream* side = ov_splits >= 1 ? side_stream() : nullptr;
       if (side != nullptr) {
         side_lock = std::unique_lock<std::mutex>(side->busy);

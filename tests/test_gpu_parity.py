@@ -624,6 +624,28 @@ def test_mlp1d_multi_tile_multi_chunk_batch():
         assert torch.equal(tbar, tbar2)
 
 
+@pytest.mark.parametrize("bs", [500, 512, 700])
+def test_mlp1d_activation_checkpoint_matches_recompute_at_bench_width(bs):
+    """3 x 512 at batch sizes the oracle cannot afford: the adjoint that reads the forward's activation checkpoint (weight-gradient
+    GEMM beside the sweep at B = 1000 / 1024 rows, after it at B = 1400; B = 1000 and 1400 are ragged in the 128-row tiles)
+    against the recomputing adjoint, which the small-batch tests pin to the oracle."""
+    from ofdft_nflows_b200.cn_flows import Gen_CNFSimpleMLP
+    feat = (512, 512, 512)
+    theta, batch, _ = _mlp_problem(feat, bs, 31)
+    model = Gen_CNFSimpleMLP(1, feat, bool_neg=True)
+    spec = ops.EnergySpec(Ne=2, d=1, kin="tfw_1d", hart="softc", nuc="attraction", x="", R=0.7, Z_alpha=3, Z_beta=1)
+    out = {}
+    for act in (True, False):
+        est = EnergyEstimator(model, spec, n_steps=2, act_ckpt=act)
+        sums, tbar, _ = est.step_flat(dev(theta), dev(batch))
+        _, tbar2, _ = est.step_flat(dev(theta), dev(batch))
+        assert torch.equal(tbar, tbar2), act                  # bitwise reproducible, side stream or not
+        out[act] = (sums.cpu().numpy(), tbar.cpu().numpy().astype(np.float64))
+    assert np.array_equal(out[True][0], out[False][0])        # same forward
+    for name, (a, b) in _mlp_slices(feat).items():
+        assert rel(out[True][1][a:b], out[False][1][a:b]) <= 2e-5, (name, rel(out[True][1][a:b], out[False][1][a:b]))
+
+
 def test_rho_rev_1d_and_compute_integral():
     """LiH.py:104-111: density of the 1-D flow on a grid (reverse no-score flow + N(0,1) prior) and its trapezoid integral;
     compute_integral (H20_mol_ofdft_min_equiv_flows.py:35-39) over a weighted grid."""
