@@ -168,8 +168,10 @@ int ofdft_cnf_gnn_rhs(void* stream, const float* theta, const float* nuclei, con
  * instantiated for jets == OFDFT_JETS_FULL.  scratch (ofdft_cnf_mlp1d_scratch_bytes) holds 16-byte-aligned
  * (and transposed) copies of the hidden kernels and, for the backward pass, the per-stage activation /
  * cotangent jets of a 2048-row chunk that the weight-gradient GEMM contracts (~2 MB per row at H=512, RK4x16).
- * ofdft_cnf_mlp1d_act_ckpt_bytes: size of `ckpt` under OFDFT_PATH_ACT_CKPT (stage states + ~2.4 MB per row of layer
- * activations at 3 x 512, RK4x16); 0 when the shape does not support it (B above one 2048-row backward chunk).
+ * ofdft_cnf_mlp1d_act_ckpt_bytes: size of `ckpt` under OFDFT_PATH_ACT_CKPT (stage states + ~1.2 MB per row of layer
+ * activations at 3 x 512, RK4x16); 0 when the shape does not support it (B above one 2048-row backward chunk, or H not
+ * a multiple of 128).  With the flag the 1-D adjoint also forks its weight-gradient GEMM onto a library-owned stream
+ * and joins it before returning (stream order as seen by the caller is unchanged).
  */
 size_t ofdft_cnf_mlp1d_ckpt_bytes(int64_t B, int32_t n_steps);
 size_t ofdft_cnf_mlp1d_act_ckpt_bytes(int64_t B, int32_t H, int32_t n_layers, int32_t n_steps);
