@@ -47,6 +47,7 @@ struct SmemGen {
   NucTables T;
   float uA[kGT * kRow];
   float vP[kGT * kRow];
+  float wQ[kGT * kRow];            // adjoint: last-layer kernel gradient terms of the current (nucleus, evaluation)
   int tile;
 };
 
@@ -211,14 +212,22 @@ __global__ void __launch_bounds__(kGT) gnn_general_fwd_kernel(const GnnFwdArgs a
 // ----------------------------------------------------------------------------------------------------------------------
 // discrete adjoint
 // ----------------------------------------------------------------------------------------------------------------------
-// per-trajectory accumulators of the small gradients (column-summed over the tile at the end of the tile)
+// small-gradient accumulators of thread (j = tid & 63, row half = tid >> 6): column j, summed over the thread's 64 rows of
+// the tile.  Every (nucleus, evaluation) the 128 trajectories put their terms into shared-memory row buffers and each
+// thread adds up its column half -- per-trajectory 64-vectors accumulated in local memory (the first version) made the
+// adjoint L2-bound: 3 KB of read-modify-write per thread and evaluation.
 template <int L>
 struct SmallAcc {
-  float w3[kH];                    // d w3[j]
-  float bl[L][kH];                 // d b_l[j], l >= 1 (slot 0 unused)
-  float wt[kH], wr[kH];            // d W1[0][k], d W1[1][k]
-  float S[kMaxClasses][kH];        // per nucleus class: sum of first-layer pre-activation cotangents
-  float b3;
+  float w3;                        // d w3[j]
+  float bl[L];                     // d b_l[j], l >= 1 (slot 0 unused)
+  float wt, wr;                    // d W1[0][j], d W1[1][j]
+  float S[kMaxClasses];            // per nucleus class: sum of first-layer pre-activation cotangents
+  float b3;                        // per trajectory (thread = row)
+  __device__ void zero() {
+    w3 = 0.f; wt = 0.f; wr = 0.f; b3 = 0.f;
+    for (int l = 0; l < L; ++l) bl[l] = 0.f;
+    for (int c = 0; c < kMaxClasses; ++c) S[c] = 0.f;
+  }
 };
 
 // weight-gradient accumulators of thread (j = tid & 63, k-half = tid >> 6): dW_l[32 kh + kk][j]
@@ -292,6 +301,7 @@ __device__ void gen_bwd_tile(SmemGen& sm, const GnnBwdArgs& a, const GnnThetaLay
           if (!valid) { fb[0] = 0.f; fb[1] = 0.f; fb[2] = 0.f; }
         }
         G.b3 += fb[0];
+        __syncthreads();                                       // the previous evaluation's column sums have been read
         // last layer: f = b3 + w3 . a_{L-1}
         for (int j = 0; j < kH; ++j) {
           const float w = __ldg(a.theta + TL.w3 + j);
@@ -299,7 +309,7 @@ __device__ void gen_bwd_tile(SmemGen& sm, const GnnBwdArgs& a, const GnnThetaLay
           cot[0][j] = w * fb[0];
           if (NJ >= 2) { gw = fmaf(S.J[L - 1][1][j], fb[1], gw); cot[1][j] = w * fb[1]; }
           if (NJ == 3) { gw = fmaf(S.J[L - 1][2][j], fb[2], gw); cot[2][j] = w * fb[2]; }
-          G.w3[j] += gw;
+          sm.wQ[tid * kRow + j] = gw;
         }
         // hidden layers L-1 .. 1: reverse of the tanh jet, weight gradient, transposed mat-vec
         for (int l = L - 1; l >= 1; --l) {
@@ -322,19 +332,21 @@ __device__ void gen_bwd_tile(SmemGen& sm, const GnnBwdArgs& a, const GnnThetaLay
               cot[1][j] = sg * t1;
             }
             cot[0][j] = sg * pzb;
-            G.bl[l][j] += cot[0][j];
           }
           // dW_l[k][j] += sum over the tile's trajectories and jets of J[l-1][jet][k] * cot[jet][j]
           for (int jt = 0; jt < NJ; ++jt) {
             __syncthreads();
             for (int u = 0; u < kH; ++u) { sm.uA[tid * kRow + u] = S.J[l - 1][jt][u]; sm.vP[tid * kRow + u] = cot[jt][u]; }
             __syncthreads();
+            float bsum = 0.f;
             for (int t = 0; t < kGT; ++t) {
               const float v = sm.vP[t * kRow + jcol];
               const float* ua = sm.uA + t * kRow + 32 * kh;
 #pragma unroll
               for (int kk = 0; kk < 32; ++kk) D.v[l][kk] = fmaf(ua[kk], v, D.v[l][kk]);
+              if ((t >> 6) == kh) bsum += v;                   // jet 0 of the cotangent is the bias gradient of layer l
             }
+            if (jt == 0) G.bl[l] += bsum;
           }
           // cotangent jets of layer l-1: nxt[jet][k] = sum_j cot[jet][j] W_l[k][j]
           const float* __restrict__ W = a.theta + TL.W[l];
@@ -360,6 +372,7 @@ __device__ void gen_bwd_tile(SmemGen& sm, const GnnBwdArgs& a, const GnnThetaLay
         }
         // first layer reverse   [epilogue_b1 of gnn.cu]
         float rbar = 0.f;
+        if (L > 1) __syncthreads();                            // the weight-gradient pass above has read uA / vP
         for (int k = 0; k < kH; ++k) {
           const float aa = S.J[0][0][k];
           const float wv = __ldg(a.theta + TL.W[0] + kH + k);
@@ -375,9 +388,20 @@ __device__ void gen_bwd_tile(SmemGen& sm, const GnnBwdArgs& a, const GnnThetaLay
           }
           const float pb = sg * t;
           rbar = fmaf(pb, wv, rbar);
-          G.S[cls][k] += pb;
-          G.wt[k] = fmaf(tprime, pb, G.wt[k]);
-          G.wr[k] += fmaf(pb, r, sg * e);
+          sm.uA[tid * kRow + k] = pb;
+          sm.vP[tid * kRow + k] = fmaf(pb, r, sg * e);
+        }
+        // column sums of this (nucleus, evaluation) over the thread's half of the tile rows
+        __syncthreads();
+        {
+          float s_pb = 0.f, s_wr = 0.f, s_w3 = 0.f;
+          for (int t = 64 * kh; t < 64 * kh + 64; ++t) {
+            s_pb += sm.uA[t * kRow + jcol]; s_wr += sm.vP[t * kRow + jcol]; s_w3 += sm.wQ[t * kRow + jcol];
+          }
+          G.S[cls] += s_pb;
+          G.wt = fmaf(tprime, s_pb, G.wt);                     // t' is the same for every trajectory of the evaluation
+          G.wr += s_wr;
+          G.w3 += s_w3;
         }
         // explicit geometry   [post() of gnn.cu]
         {
@@ -422,18 +446,13 @@ __device__ void gen_bwd_tile(SmemGen& sm, const GnnBwdArgs& a, const GnnThetaLay
   }
 }
 
-// column sum over the tile's trajectories of one per-trajectory 64-vector: thread (j, k-half) sums its half of the rows
-__device__ __forceinline__ float tile_colsum(SmemGen& sm, const float* v) {
-  const int tid = threadIdx.x, jcol = tid & 63, kh = tid >> 6;
+// both row halves of column j (threads j and 64 + j) -> the column sum over the whole tile
+__device__ __forceinline__ float tile_halves_sum(SmemGen& sm, float v) {
+  const int tid = threadIdx.x, jcol = tid & 63;
   __syncthreads();
-  for (int u = 0; u < kH; ++u) sm.uA[tid * kRow + u] = v[u];
+  sm.vP[tid] = v;
   __syncthreads();
-  float s = 0.f;
-  for (int t = 64 * kh; t < 64 * kh + 64; ++t) s += sm.uA[t * kRow + jcol];
-  __syncthreads();
-  sm.vP[tid] = s;
-  __syncthreads();
-  return sm.vP[jcol] + sm.vP[64 + jcol];      // both halves now hold the full column sum of column jcol
+  return sm.vP[jcol] + sm.vP[64 + jcol];
 }
 
 template <int L>
@@ -443,14 +462,14 @@ __device__ void gen_flush_tile(SmemGen& sm, SmallAcc<L>& G, DwAcc<L>& D, float* 
   for (int l = 1; l < L; ++l)
     for (int kk = 0; kk < 32; ++kk) { out[TL.W[l] + (32 * kh + kk) * kH + jcol] = D.v[l][kk]; D.v[l][kk] = 0.f; }
   float s;
-  s = tile_colsum(sm, G.w3); if (kh == 0) out[TL.w3 + jcol] = s;
-  for (int l = 1; l < L; ++l) { s = tile_colsum(sm, G.bl[l]); if (kh == 0) out[TL.b[l] + jcol] = s; }
-  s = tile_colsum(sm, G.wt); if (kh == 0) out[TL.W[0] + jcol] = s;
-  s = tile_colsum(sm, G.wr); if (kh == 0) out[TL.W[0] + kH + jcol] = s;
+  s = tile_halves_sum(sm, G.w3); if (kh == 0) out[TL.w3 + jcol] = s;
+  for (int l = 1; l < L; ++l) { s = tile_halves_sum(sm, G.bl[l]); if (kh == 0) out[TL.b[l] + jcol] = s; }
+  s = tile_halves_sum(sm, G.wt); if (kh == 0) out[TL.W[0] + jcol] = s;
+  s = tile_halves_sum(sm, G.wr); if (kh == 0) out[TL.W[0] + kH + jcol] = s;
   float sb1 = 0.f, st[kMaxTypes];
   for (int t = 0; t < kMaxTypes; ++t) st[t] = 0.f;
   for (int c = 0; c < sm.T.n_cls; ++c) {
-    s = tile_colsum(sm, G.S[c]);
+    s = tile_halves_sum(sm, G.S[c]);
     sb1 += s;
     for (int t = 0; t < n_types; ++t) st[t] = fmaf(onehot[sm.T.rep[c] * n_types + t], s, st[t]);
   }
@@ -468,12 +487,7 @@ __device__ void gen_flush_tile(SmemGen& sm, SmallAcc<L>& G, DwAcc<L>& D, float* 
     out[TL.b3] = b;
   }
   __syncthreads();
-  for (int u = 0; u < kH; ++u) {
-    G.w3[u] = 0.f; G.wt[u] = 0.f; G.wr[u] = 0.f;
-    for (int l = 0; l < L; ++l) G.bl[l][u] = 0.f;
-    for (int c = 0; c < kMaxClasses; ++c) G.S[c][u] = 0.f;
-  }
-  G.b3 = 0.f;
+  G.zero();
 }
 
 template <int L>
@@ -485,12 +499,7 @@ __global__ void __launch_bounds__(kGT) gnn_general_bwd_kernel(const GnnBwdArgs a
   load_nuc_tables<kGT>(sm.T, a.theta, L2, a.nuclei, a.onehot, a.Na, a.n_types);
   SmallAcc<L> G;
   DwAcc<L> D;
-  for (int u = 0; u < kH; ++u) {
-    G.w3[u] = 0.f; G.wt[u] = 0.f; G.wr[u] = 0.f;
-    for (int l = 0; l < L; ++l) G.bl[l][u] = 0.f;
-    for (int c = 0; c < kMaxClasses; ++c) G.S[c][u] = 0.f;
-  }
-  G.b3 = 0.f;
+  G.zero();
   for (int l = 0; l < L; ++l)
     for (int kk = 0; kk < 32; ++kk) D.v[l][kk] = 0.f;
   const long long tiles_a = (a.n_a + kGT - 1) / kGT;
