@@ -48,6 +48,8 @@ extern "C" {
 #define OFDFT_PATH_ACT_CKPT 4    /* 1-D flow, tensor-core path: `ckpt` is ofdft_cnf_mlp1d_act_ckpt_bytes() large; the forward
                                     also keeps every evaluation's layer activations there and the adjoint reads them
                                     instead of recomputing the hidden layers (pass the flag to both calls)          */
+#define OFDFT_PATH_DEEP    8     /* 3-D flow, two hidden layers: run the depth-generic tensor-core kernels (the default of
+                                    three hidden layers) instead of the pipelined two-layer ones -- a cross-check      */
 
 /* jets carried per trajectory */
 #define OFDFT_JETS_X      1      /* x only                  (second-half rows: only xp is used, H20_...py:154-156) */

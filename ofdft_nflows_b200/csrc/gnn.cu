@@ -800,7 +800,7 @@ extern "C" int64_t ofdft_cnf_gnn_theta_size(int32_t n_types, int32_t n_layers) {
 }
 extern "C" size_t ofdft_cnf_gnn_bwd_scratch_bytes(int64_t B, int64_t n_a, int32_t n_types, int32_t n_layers) {
   if (B <= 0 || n_a < 0 || n_a > B) return kCounterBytes;
-  return kCounterBytes + kW2SplitBytes + (size_t)n_tiles_of(B, n_a) * (size_t)ofdft_cnf_gnn_theta_size(n_types, n_layers) * sizeof(float);
+  return kCounterBytes + kDeepWSplitBytes + (size_t)n_tiles_of(B, n_a) * (size_t)ofdft_cnf_gnn_theta_size(n_types, n_layers) * sizeof(float);
 }
 
 // path: OFDFT_PATH_DEFAULT (tcgen05 3xTF32 layer-2 GEMM, gnn_tc.cu) | OFDFT_PATH_FFMA (FP32-pipe kernel of this file)
@@ -808,6 +808,9 @@ static int launch_fwd(void* stream, GnnFwdArgs& a, void* scratch, size_t scratch
   if (!a.theta || !a.nuclei || !a.y_in || !a.y_out || !scratch) return OFDFT_EINVAL;
   if (a.n_types > 0 && !a.onehot) return OFDFT_EINVAL;
   if (scratch_bytes < kCounterBytes) return OFDFT_ESCRATCH;
+  // three hidden layers (or two with OFDFT_PATH_DEEP): depth-generic tensor-core kernels (gnn_deep_tc.cu)
+  if ((n_layers == 3 && !(path & OFDFT_PATH_FFMA)) || (n_layers == 2 && (path & OFDFT_PATH_DEEP)))
+    return launch_gnn_deep_fwd_tc(stream, a, scratch, scratch_bytes, n_layers);
   if (n_layers != 2) return launch_gnn_general_fwd(stream, a, scratch, scratch_bytes, n_layers);   // gnn_general.cu
   if (!(path & OFDFT_PATH_FFMA)) return launch_gnn_fwd_tc(stream, a, scratch, scratch_bytes);
   cudaStream_t st = (cudaStream_t)stream;
@@ -885,13 +888,17 @@ extern "C" int ofdft_cnf_gnn_bwd(void* stream, const float* theta, const float* 
   int sms = num_sms(); if (sms <= 0) sms = 148;
   const int grid = (int)(tiles < sms ? tiles : sms);
   float* w2split = (float*)((char*)scratch + kCounterBytes);
-  float* gpart = (float*)((char*)scratch + kCounterBytes + kW2SplitBytes);
+  float* gpart = (float*)((char*)scratch + kCounterBytes + kDeepWSplitBytes);
   GnnBwdArgs a{theta, nuclei, onehot, ckpt, ybar1, ybar0, gpart, (int*)scratch, B, n_a, jets_a, jets_b, bar_stride,
                Na, n_types, n_steps, t0, t1, y0sign, n_layers == 2 ? act_ckpt : nullptr, pad_rows(n_a), pad_rows(B - n_a), w2split};
   // default: tcgen05 3xTF32 GEMMs (without an activation checkpoint the layer-2 jets are recomputed on the tensor cores);
   // OFDFT_PATH_FFMA: FP32-pipe kernels (checkpoint-reading or recomputing)
   const bool tc_bwd = !(path & OFDFT_PATH_FFMA);
-  if (n_layers != 2) {
+  if ((n_layers == 3 && tc_bwd) || (n_layers == 2 && (path & OFDFT_PATH_DEEP))) {
+    a.act = nullptr;
+    const int rc2 = launch_gnn_deep_bwd_tc(stream, a, grid, n_layers);   // gnn_deep_tc.cu (no activation checkpoint)
+    if (rc2) return rc2;
+  } else if (n_layers != 2) {
     const int rc2 = launch_gnn_general_bwd(stream, a, n_layers);      // gnn_general.cu (no activation checkpoint)
     if (rc2) return rc2;
   } else if (tc_bwd) {

@@ -21,6 +21,22 @@ struct GnnBwdArgs {
   float* w2split;   // 2 x 4096 floats of caller scratch: W2 hi | lo in the forward GEMM orientation (tensor-core recompute mode)
 };
 
+// theta offsets for L hidden layers (key-sorted ravel_pytree order; L = 2 reproduces GnnThetaLayout)
+struct GnnThetaLayoutL {
+  int b3, w3, b[kMaxLayers], W[kMaxLayers], n;
+  __host__ __device__ GnnThetaLayoutL(int n_types, int L) {
+    const int I = 2 + n_types;
+    b3 = 0; w3 = 1;
+    b[0] = 1 + kH; W[0] = b[0] + kH;
+    int end = W[0] + I * kH;
+    for (int l = 1; l < kMaxLayers; ++l) {
+      b[l] = end; W[l] = end + kH;
+      if (l < L) end = W[l] + kH * kH;
+    }
+    n = end;
+  }
+};
+
 // Layer-2 activation checkpoint (optional; trades 180 GB of HBM for the recompute GEMM of the backward pass):
 // for every RHS evaluation e = (step*4+stage)*Na + nucleus and both row segments, the jets (a2, p2', p2'') as
 // [jet][group of 4 units][row][4 units]: a thread holding consecutive units of one trajectory moves them as float4, and
@@ -105,6 +121,11 @@ int launch_gnn_fwd_tc(void* stream, GnnFwdArgs& a, void* scratch, size_t scratch
 // tensor-core backward (a.act == nullptr: the layer-2 jets are recomputed on the tensor cores); the caller has reset the
 // tile counter and reduces gpart afterwards
 int launch_gnn_bwd_tc(void* stream, GnnBwdArgs& a, int grid);
+
+// tensor-core kernels for two or three hidden layers, no activation checkpoint (gnn_deep_tc.cu)
+constexpr size_t kDeepWSplitBytes = (size_t)(kMaxLayers - 1) * 4 * kH * kH * sizeof(float);
+int launch_gnn_deep_fwd_tc(void* stream, GnnFwdArgs& a, void* scratch, size_t scratch_bytes, int n_layers);
+int launch_gnn_deep_bwd_tc(void* stream, GnnBwdArgs& a, int grid, int n_layers);
 
 // general-depth kernels (gnn_general.cu): 1 or 3 hidden layers
 int gnn_general_theta_size(int n_types, int n_layers);

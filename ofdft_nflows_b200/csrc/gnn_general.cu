@@ -19,22 +19,6 @@ namespace ofdft {
 constexpr int kGT = kTP;               // trajectories = threads per tile
 constexpr int kRow = kH + 1;           // padded row of a shared-memory row buffer (thread-private rows: conflict free)
 
-// theta offsets for L hidden layers (key-sorted ravel_pytree order; L = 2 reproduces GnnThetaLayout)
-struct GnnThetaLayoutL {
-  int b3, w3, b[kMaxLayers], W[kMaxLayers], n;
-  __host__ __device__ GnnThetaLayoutL(int n_types, int L) {
-    const int I = 2 + n_types;
-    b3 = 0; w3 = 1;
-    b[0] = 1 + kH; W[0] = b[0] + kH;
-    int end = W[0] + I * kH;
-    for (int l = 1; l < kMaxLayers; ++l) {
-      b[l] = end; W[l] = end + kH;
-      if (l < L) end = W[l] + kH * kH;
-    }
-    n = end;
-  }
-};
-
 __device__ __forceinline__ float tanh_g(float x) {
 #ifdef OFDFT_HOST_SIM
   return tanhf(x);

@@ -18,6 +18,7 @@ JETS_X, JETS_XLOGP, JETS_FULL = 1, 2, 3
 # kernel-path selector of the integrator entry points (include/ofdft_b200.h): the default runs the GEMM-shaped phases on
 # the tcgen05 tensor cores; PATH_FFMA / PATH_FFMA_DW select the independently written FP32-pipe kernels
 PATH_DEFAULT, PATH_FFMA, PATH_FFMA_DW = 0, 1, 2
+PATH_DEEP = 8           # 3-D flow, (64, 64): depth-generic tensor-core kernels (the default of (64, 64, 64)) as a cross-check
 PATH_ACT_CKPT = 4       # 1-D flow: the checkpoint buffer also holds the layer activations (set by cn_flows.mlp_fwd / mlp_bwd)
 
 KIN = {"": 0, "none": 0, "tf": 1, "thomas_fermi": 1, "w": 2, "weizsacker": 2, "w1d": 2, "weizsacker1d": 2,
