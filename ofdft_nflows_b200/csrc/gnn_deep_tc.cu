@@ -247,7 +247,7 @@ __device__ void deep_fwd_tile(SmemDeepF& sm, const GnnFwdArgs& a, long long row0
           if (NJ == 3) deep_jet0<2>(J0, sm.wr + 32 * uh, J2);
           if (NJ >= 2) deep_jet0<1>(J0, sm.wr + 32 * uh, J1);
         }
-#pragma unroll
+#pragma unroll 1
         for (int l = 1; l < L; ++l) {
           const uint64_t dWh = tc::make_desc(tc::smem_u32(sm.Whi + (l - 1) * kH * kH), kDChunkB, 128);
           const uint64_t dWl = tc::make_desc(tc::smem_u32(sm.Wlo + (l - 1) * kH * kH), kDChunkB, 128);
@@ -536,7 +536,7 @@ __device__ void deep_bwd_tile(SmemDeepB& sm, const GnnBwdArgs& a, long long row0
           deep_first_layer(av, wr, sm.wt + 32 * uh, sm.T.cb + sm.T.cls[i] * kH + 32 * uh, r, tprime);
         }
         // ---------------- forward recompute: S(l) <- (a_l, P_l', P_l'') for l = 1 .. L-1 ----------------
-#pragma unroll
+#pragma unroll 1
         for (int l = 1; l < L; ++l) {
           load_W(l, 0);
 #pragma unroll
@@ -611,13 +611,15 @@ __device__ void deep_bwd_tile(SmemDeepB& sm, const GnnBwdArgs& a, long long row0
           G.g_w3 += warp_vec32_sum(g32, lane);
         }
         // ---------------- hidden layers L-1 .. 1 ----------------
-#pragma unroll
-        for (int l = L - 1; l >= 1; --l) {
+#pragma unroll 1
+        for (int l = L - 1; l >= 1; --l) {      // a real loop: one copy of the layer body keeps the code inside the instruction cache
           {
             float t[32];
 #pragma unroll
             for (int u = 0; u < 32; ++u) t[u] = q0[u];
-            G.g_b[l] += warp_vec32_sum(t, lane);
+            const float s = warp_vec32_sum(t, lane);
+#pragma unroll
+            for (int ll = 1; ll < L; ++ll) G.g_b[ll] += ll == l ? s : 0.f;
           }
           // Abar_{l-1}[jet] = Pbar_l[jet] . W_l^T  -> the (dead) state columns of layer l
           load_W(l, 1);

@@ -709,19 +709,14 @@ REF_STEP_3D = [("ref_step_h2_bs40", 32), ("ref_step_lih_bs32", 32), ("ref_step_h
                ("ref_step_h2o_L1_bs32", 32), ("ref_step_h2o_L3_bs32", 32)]
 
 
-@pytest.mark.parametrize("name,n_steps", REF_STEP_3D)
-def test_reference_source_fixtures_3d(name, n_steps):
-    """y(t1), every energy term and dE/dtheta as the REFERENCE'S OWN SOURCE computes them (unmodified functionals.py /
-    jax_ode.py / equiv_flows.py run under the jax stand-in, adaptive Dopri5 1e-7, float64): the driver-default functional
-    sets (dirac_b88_x_e + vwn_c_e / pw92_c_e), benzene, the --nn 1 / --nn 3 architectures and the benchmark's own
-    parameters at RK4 x16.  North-star tolerances: energy terms 1e-5, gradient 1e-4 per tensor."""
+def _check_ref_step_3d(name, n_steps, path=ops.PATH_DEFAULT, act_ckpt=True):
     g = np.load(os.path.join(GOLD, name + ".npz"))
     feats = tuple(int(v) for v in g["features"])
     kin, nuc, hart, x, c = (str(v) for v in g["names"])
     nt = g["onehot"].shape[1]
     model = Gen_EqvFlow(3, feats, g["coords"], g["onehot"], bool_neg=True)
     spec = ops.EnergySpec(Ne=float(g["Ne"]), d=3, kin=kin, hart=hart, nuc=nuc, x=x, c=c, coords=g["coords"], z=g["z"])
-    est = EnergyEstimator(model, spec, n_steps=n_steps)
+    est = EnergyEstimator(model, spec, n_steps=n_steps, path=path, act_ckpt=act_ckpt)
     sums, tbar, y1 = est.step_flat(dev(g["theta"]), dev(g["batch"]))
     sums = sums.cpu().numpy(); grad = tbar.cpu().numpy().astype(np.float64)
     ref_terms = g["terms"]
@@ -744,6 +739,47 @@ def test_reference_source_fixtures_3d(name, n_steps):
         rho = utils.rho_rev(model.unravel(dev(g["theta"])), dev(g["rev_x"]), Gen_EqvFlow(3, feats, g["coords"], g["onehot"], bool_neg=False),
                             utils.ProMolecularDensity(g["z"], g["coords"]), n_steps=n_steps)
         assert np.abs(rho.cpu().numpy().reshape(-1) / g["rev_rho"][:, 0] - 1.0).max() < 2e-5
+
+
+@pytest.mark.parametrize("name,n_steps", REF_STEP_3D)
+def test_reference_source_fixtures_3d(name, n_steps):
+    """y(t1), every energy term and dE/dtheta as the REFERENCE'S OWN SOURCE computes them (unmodified functionals.py /
+    jax_ode.py / equiv_flows.py run under the jax stand-in, adaptive Dopri5 1e-7, float64): the driver-default functional
+    sets (dirac_b88_x_e + vwn_c_e / pw92_c_e), benzene, the --nn 1 / --nn 3 architectures and the benchmark's own
+    parameters at RK4 x16.  North-star tolerances: energy terms 1e-5, gradient 1e-4 per tensor."""
+    _check_ref_step_3d(name, n_steps)
+
+
+@pytest.mark.parametrize("name,n_steps,path", [("ref_step_h2o_bench_bs512", 16, ops.PATH_DEEP), ("ref_step_c6h6_b88_pw92_bs24", 64, ops.PATH_DEEP),
+                                               ("ref_step_h2_bs40", 32, ops.PATH_DEEP), ("ref_step_h2o_L3_bs32", 32, ops.PATH_FFMA),
+                                               ("ref_step_h2o_L1_bs32", 32, ops.PATH_FFMA)])
+def test_reference_source_fixtures_3d_other_kernels(name, n_steps, path):
+    """The same reference-source fixtures through the kernels the default path does not take: the depth-generic tensor-core
+    kernels (gnn_deep_tc.cu, the default of (64, 64, 64)) on the (64, 64) fixtures, and the plain FP32 general-depth kernels
+    (gnn_general.cu) on the (64, 64, 64) / (64,) ones."""
+    _check_ref_step_3d(name, n_steps, path=path, act_ckpt=False)
+
+
+def test_three_layer_tensor_core_kernels_multi_tile_vs_fp32_kernels():
+    """(64, 64, 64): ragged multi-tile batch (both row segments, x-only second half), tensor-core kernels against the
+    independently written FP32 kernels; bitwise reproducible."""
+    Ne, atoms, z, coords = utils.coordinates("H2O")
+    oh = utils.jax_one_hot(z)
+    model = Gen_EqvFlow(3, (64, 64, 64), coords, oh, bool_neg=True)
+    g = torch.Generator().manual_seed(7)
+    theta = model.flat_theta(model.init(3)).to("cuda:0")
+    theta = theta + 0.05 * torch.randn(theta.numel(), generator=g).to("cuda:0")
+    batch = next(utils.batch_generator(99, 300, utils.ProMolecularDensity(z, coords)))
+    spec = ops.EnergySpec(Ne=Ne, d=3, kin="tf-w", hart="hartree", nuc="hgh", x="lda", coords=coords, z=z)
+    out = []
+    for path in (ops.PATH_DEFAULT, ops.PATH_DEFAULT, ops.PATH_FFMA):
+        sums, tbar, y1 = EnergyEstimator(model, spec, n_steps=16, path=path).step_flat(theta, dev(batch))
+        out.append((sums.cpu().numpy(), tbar.cpu().numpy().astype(np.float64), y1.cpu().numpy()))
+    assert np.array_equal(out[0][1], out[1][1]) and np.array_equal(out[0][2], out[1][2])
+    assert np.abs(out[0][2] - out[2][2]).max() < 2e-5 * max(1.0, np.abs(out[2][2]).max())
+    assert abs(out[0][0][5] - out[2][0][5]) <= E_TOL * abs(out[2][0][5])
+    for tname, (a, b) in gnn_slices(2 + oh.shape[1], (64, 64, 64)).items():
+        assert rel(out[0][1][a:b], out[2][1][a:b]) <= G_TOL, (tname, rel(out[0][1][a:b], out[2][1][a:b]))
 
 
 @pytest.mark.parametrize("name,n_steps", [("ref_step_lih1d_512x3_bs24", 16), ("ref_step_mlp1d_64x2_bs40", 16)])
