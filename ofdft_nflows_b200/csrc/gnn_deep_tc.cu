@@ -31,17 +31,17 @@ constexpr int kDTChunk = kTP * 4 + 4;       // floats per trajectory-chunk of a 
 constexpr int kDColDw = 384;                // weight-gradient accumulator (128 columns) / TS-mode "hi" operand (first 64)
 __host__ __device__ constexpr int dcol_state(int l) { return 192 * (l - 1); }
 constexpr int kDRegionFloats = 2 * 32 * kDTChunk;
-constexpr int kDWopOff = kH * kTP;          // float offset of the weight operand (hi | lo) inside the region; the remainder is at 0
+constexpr int kDWopOff = 2 * kH * kTP;      // float offset of the weight operand (hi | lo) inside the region; two remainder buffers in front
 static_assert(kDWopOff + 2 * kH * kH <= kDRegionFloats, "GEMM-phase operands exceed the staging region");
 
 struct SmemDeepF {
-  float Alo[kH * kTP];
+  float Alo[2 * kH * kTP];            // tf32 remainders of the jet being staged, two buffers
   float Whi[(kMaxLayers - 1) * kH * kH], Wlo[(kMaxLayers - 1) * kH * kH];   // [layer][k/4][j][k%4]
   float wr[kH], wt[kH], w3[kH], bl[(kMaxLayers - 1) * kH];
   NucTables T;
   float xs[3 * kTP];
   float Fpart[2 * 3 * kTP];
-  uint64_t bar;
+  uint64_t bar[3];
   unsigned int tmem_slot;
   int tile;
 };
@@ -49,21 +49,24 @@ struct SmemDeepF {
 struct SmemDeepB {
   float R[kDRegionFloats];
   float DWs[(kMaxLayers - 1) * kH * kH];    // [layer - 1][j][k]
+  float A0[kH * kTP];                       // first-layer activations of the current (nucleus, evaluation): [unit pair][trajectory][2]
   float wr[kH], wt[kH], w3[kH], bl[(kMaxLayers - 1) * kH];
   NucTables T;
   float S[8 * kMaxClasses * 32];            // per warp and nucleus class: sum over the warp's trajectories of pbar1[k = 32 uh + lane]
   float Fpart[2 * 3 * kTP];
   float Rpart[2 * kTP];
   float red[8 * 32 * (3 + kMaxLayers)];
-  uint64_t bar;
+  uint64_t bar[3];
   unsigned int tmem_slot;
   int tile;
 };
 static_assert(sizeof(SmemDeepB) + 1024 <= 227 * 1024, "backward tile state exceeds the 227 KB of shared memory per CTA");
 
-// wait for the single completion barrier (every commit is followed by exactly one wait of all threads); a wait that lasts
-// seconds is a protocol bug: trap instead of hanging the device
-__device__ __forceinline__ void deep_wait(uint64_t* bar, uint32_t& phase) {
+// wait for completion barrier b (0 / 1: GEMM of the jet staged in operand buffer b, 2: weight-gradient batch; bit b of `phase`
+// is its parity; every commit is followed by exactly one wait of all threads); a wait that lasts seconds is a protocol bug:
+// trap instead of hanging the device
+__device__ __forceinline__ void deep_wait(uint64_t* bars, uint32_t& phase, int b) {
+  uint64_t* bar = bars + b;
   uint32_t done = 0;
   const uint32_t addr = tc::smem_u32(bar);
   const long long t0 = clock64();
@@ -71,14 +74,32 @@ __device__ __forceinline__ void deep_wait(uint64_t* bar, uint32_t& phase) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
         : "=r"(done)
-        : "r"(addr), "r"(phase)
+        : "r"(addr), "r"((phase >> b) & 1u)
         : "memory");
     if (!done && clock64() - t0 > 8000000000ll) __trap();
   }
-  phase ^= 1u;
+  phase ^= 1u << b;
   __syncwarp();
   tc::fence_after_sync();
 }
+
+// The elementwise phases run on packed FP32 (FFMA2 / FMUL2 / FADD2: two hidden units per instruction, tc.cuh): they are
+// issue-bound at two warps per scheduler, and half the instructions is also half the code the instruction cache has to hold.
+// tf32 remainders x - trunc_tf32(x) = trunc * (-1) + x (exact) of two values
+__device__ __forceinline__ tc::f32x2 lo2pk(tc::f32x2 p) { return tc::fma2(p & 0xFFFFE000FFFFE000ull, tc::splat2(-1.0f), p); }
+// tanh of two values: 1 - 2 / (2^(2 x log2 e) + 1), one MUFU.EX2 + MUFU.RCP per value
+__device__ __forceinline__ tc::f32x2 deep_tanh2(tc::f32x2 x) {
+  using namespace tc;
+  float x0, x1, e0, e1, d0, d1, r0, r1;
+  unpack2(mul2(x, splat2(2.8853900817779268f)), x0, x1);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(x0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(x1));
+  unpack2(add2(pack2(e0, e1), splat2(1.0f)), d0, d1);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(d0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(d1));
+  return fma2(splat2(-2.0f), pack2(r0, r1), splat2(1.0f));
+}
+__device__ __forceinline__ tc::f32x2 ld2(const float* p) { const float2 v = *reinterpret_cast<const float2*>(p); return tc::pack2(v.x, v.y); }
 
 // 32 units (32 uh ..) of trajectory m as the A operand of a [128 x 64] . [64 x 64] GEMM: the unrounded values go to tensor
 // memory (the tensor core truncates them to tf32), the remainders x - trunc_tf32(x) to the K-major shared-memory buffer
@@ -93,8 +114,8 @@ __device__ __forceinline__ void deep_stage_A(const float (&x)[32], uint32_t tcol
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
     const int off = ((8 * uh + c) * kTP + m) * 4;
-    *reinterpret_cast<float4*>(Alo + off) =
-        make_float4(tc::lo_tf32(x[4 * c]), tc::lo_tf32(x[4 * c + 1]), tc::lo_tf32(x[4 * c + 2]), tc::lo_tf32(x[4 * c + 3]));
+    const tc::f32x2 l01 = lo2pk(tc::pack2(x[4 * c], x[4 * c + 1])), l23 = lo2pk(tc::pack2(x[4 * c + 2], x[4 * c + 3]));
+    *reinterpret_cast<float4*>(Alo + off) = make_float4(tc::lo2(l01), tc::hi2(l01), tc::lo2(l23), tc::hi2(l23));
   }
 }
 
@@ -124,41 +145,78 @@ __device__ __forceinline__ void deep_sync_issue_gemm(uint32_t d, uint32_t ahi, u
 
 // first layer for (trajectory, units 32 uh ..): a = tanh(w_r r + w_t t' + cb)
 __device__ __forceinline__ void deep_first_layer(float (&av)[32], const float* wr, const float* wt, const float* cbi, float r, float tprime) {
+  using namespace tc;
+  const f32x2 r2 = splat2(r), tp2 = splat2(tprime);
 #pragma unroll
-  for (int u = 0; u < 32; ++u) av[u] = tanh_f(fmaf(wr[u], r, fmaf(tprime, wt[u], cbi[u])));
+  for (int u = 0; u < 32; u += 2) unpack2(deep_tanh2(fma2(ld2(wr + u), r2, fma2(tp2, ld2(wt + u), ld2(cbi + u)))), av[u], av[u + 1]);
 }
 // jet jt of the first layer: a, a' = (1 - a^2) w_r, a'' = -2 a a' w_r
 template <int JT>
 __device__ __forceinline__ void deep_jet0(const float (&av)[32], const float* wr, float (&x)[32]) {
+  using namespace tc;
 #pragma unroll
-  for (int u = 0; u < 32; ++u) {
-    const float a = av[u];
-    if (JT == 0) x[u] = a;
-    else {
-      const float w = wr[u];
-      const float a1 = fmaf(-a, a, 1.0f) * w;
-      x[u] = JT == 1 ? a1 : -2.0f * a * a1 * w;
+  for (int u = 0; u < 32; u += 2) {
+    const f32x2 a = pack2(av[u], av[u + 1]);
+    f32x2 o = a;
+    if (JT > 0) {
+      const f32x2 w = ld2(wr + u);
+      const f32x2 a1 = mul2(fma2(mul2(a, splat2(-1.0f)), a, splat2(1.0f)), w);
+      o = JT == 1 ? a1 : mul2(mul2(mul2(a, splat2(-2.0f)), a1), w);
     }
+    unpack2(o, x[u], x[u + 1]);
+  }
+}
+// the adjoint keeps the first-layer activations in shared memory ([unit pair][trajectory][2]: a warp reads 256 contiguous
+// bytes) instead of 32 registers per thread: a0 points at (unit pair 16 uh, trajectory m)
+__device__ __forceinline__ void deep_first_layer_smem(float* a0, const float* wr, const float* wt, const float* cbi, float r, float tprime) {
+  using namespace tc;
+  const f32x2 r2 = splat2(r), tp2 = splat2(tprime);
+#pragma unroll
+  for (int u = 0; u < 32; u += 2) {
+    float x0, x1;
+    unpack2(deep_tanh2(fma2(ld2(wr + u), r2, fma2(tp2, ld2(wt + u), ld2(cbi + u)))), x0, x1);
+    *reinterpret_cast<float2*>(a0 + (u >> 1) * (2 * kTP)) = make_float2(x0, x1);
+  }
+}
+template <int JT>
+__device__ __forceinline__ void deep_jet0_smem(const float* a0, const float* wr, float (&x)[32]) {
+  using namespace tc;
+#pragma unroll
+  for (int u = 0; u < 32; u += 2) {
+    const f32x2 a = ld2(a0 + (u >> 1) * (2 * kTP));
+    f32x2 o = a;
+    if (JT > 0) {
+      const f32x2 w = ld2(wr + u);
+      const f32x2 a1 = mul2(fma2(mul2(a, splat2(-1.0f)), a, splat2(1.0f)), w);
+      o = JT == 1 ? a1 : mul2(mul2(mul2(a, splat2(-2.0f)), a1), w);
+    }
+    unpack2(o, x[u], x[u + 1]);
   }
 }
 // jet jt of hidden layer l >= 1 from its tensor-memory state (a, P', P''), units 32 uh .. of trajectory m
 template <int JT>
 __device__ __forceinline__ void deep_jet_state(uint32_t tstate, float (&x)[32]) {
+  using namespace tc;
 #pragma unroll
   for (int c0 = 0; c0 < 32; c0 += 16) {
     float a[16], p1[16], p2[16];
-    tc::tmem_ld16(tstate + c0, a);
-    if (JT >= 1) tc::tmem_ld16(tstate + kH + c0, p1);
-    if (JT == 2) tc::tmem_ld16(tstate + 2 * kH + c0, p2);
-    tc::tmem_ld_wait();
+    tmem_ld16(tstate + c0, a);
+    if (JT >= 1) tmem_ld16(tstate + kH + c0, p1);
+    if (JT == 2) tmem_ld16(tstate + 2 * kH + c0, p2);
+    tmem_ld_wait();
 #pragma unroll
-    for (int u = 0; u < 16; ++u) {
-      if (JT == 0) x[c0 + u] = a[u];
-      else {
-        const float sg = fmaf(-a[u], a[u], 1.0f);
-        const float a1 = sg * p1[u];
-        x[c0 + u] = JT == 1 ? a1 : fmaf(sg, p2[u], -2.0f * a[u] * a1 * p1[u]);
+    for (int u = 0; u < 16; u += 2) {
+      const f32x2 aa = pack2(a[u], a[u + 1]);
+      f32x2 o = aa;
+      if (JT > 0) {
+        const f32x2 naa = mul2(aa, splat2(-1.0f));
+        const f32x2 sg = fma2(naa, aa, splat2(1.0f));
+        const f32x2 q1 = pack2(p1[u], p1[u + 1]);
+        const f32x2 a1 = mul2(sg, q1);
+        o = a1;
+        if (JT == 2) o = fma2(sg, pack2(p2[u], p2[u + 1]), mul2(mul2(mul2(naa, splat2(2.0f)), a1), q1));   // sg p2 - 2 a a1 p1
       }
+      unpack2(o, x[c0 + u], x[c0 + u + 1]);
     }
   }
 }
@@ -166,7 +224,7 @@ __device__ __forceinline__ void deep_jet_state(uint32_t tstate, float (&x)[32]) 
 // =================================================================================================================
 // forward integrator
 // =================================================================================================================
-constexpr int kDFColAhi = 192;     // forward: accumulators of the three jets at columns 0..191, TS-mode operand behind them
+constexpr int kDFColAhi = 192;     // forward: accumulators of the three jets at columns 0..191, two TS-mode operand buffers behind them
 
 template <int NJ, int L>
 __device__ void deep_fwd_tile(SmemDeepF& sm, const GnnFwdArgs& a, long long row0, long long seg_end, float b3, uint32_t tmem,
@@ -190,7 +248,7 @@ __device__ void deep_fwd_tile(SmemDeepF& sm, const GnnFwdArgs& a, long long row0
   const float h = (a.t1 - a.t0) / (float)a.n_steps;
   const uint32_t idesc = tc::make_idesc_tf32(kTP, kH, 0, 0);
   const uint32_t tlane = tmem + ((uint32_t)(32 * (w & 3)) << 16);
-  const uint64_t dAlo = tc::make_desc(tc::smem_u32(sm.Alo), kDChunkA, 128);
+  const uint64_t dAlo[2] = {tc::make_desc(tc::smem_u32(sm.Alo), kDChunkA, 128), tc::make_desc(tc::smem_u32(sm.Alo + kH * kTP), kDChunkA, 128)};
 
   auto combine = [&](int i) {
     const float* nc = sm.T.nuc + i * 4;
@@ -252,12 +310,14 @@ __device__ void deep_fwd_tile(SmemDeepF& sm, const GnnFwdArgs& a, long long row0
           const uint64_t dWh = tc::make_desc(tc::smem_u32(sm.Whi + (l - 1) * kH * kH), kDChunkB, 128);
           const uint64_t dWl = tc::make_desc(tc::smem_u32(sm.Wlo + (l - 1) * kH * kH), kDChunkB, 128);
 #pragma unroll
-          for (int jt = 0; jt < NJ; ++jt) {
-            if (jt > 0) deep_wait(&sm.bar, phase);
-            deep_stage_A(jt == 0 ? J0 : (jt == 1 ? J1 : J2), tlane + kDFColAhi + 32 * uh, sm.Alo, uh, m);
-            deep_sync_issue_gemm(tmem + jt * kH, tmem + kDFColAhi, dAlo, dWh, dWl, idesc, &sm.bar);
+          for (int jt = 0; jt < NJ; ++jt) {      // the staging of jet jt + 1 runs under the MMAs of jet jt (two operand buffers)
+            const int buf = jt & 1;
+            if (jt >= 2) deep_wait(sm.bar, phase, buf);
+            deep_stage_A(jt == 0 ? J0 : (jt == 1 ? J1 : J2), tlane + kDFColAhi + kH * buf + 32 * uh, sm.Alo + buf * kH * kTP, uh, m);
+            deep_sync_issue_gemm(tmem + jt * kH, tmem + kDFColAhi + kH * buf, dAlo[buf], dWh, dWl, idesc, &sm.bar[buf]);
           }
-          deep_wait(&sm.bar, phase);
+#pragma unroll
+          for (int jt = (NJ >= 2 ? NJ - 2 : 0); jt < NJ; ++jt) deep_wait(sm.bar, phase, jt & 1);
           const float* bl = sm.bl + (l - 1) * kH + 32 * uh;
 #pragma unroll
           for (int c0 = 0; c0 < 32; c0 += 16) {
@@ -267,27 +327,32 @@ __device__ void deep_fwd_tile(SmemDeepF& sm, const GnnFwdArgs& a, long long row0
             if (NJ == 3) tc::tmem_ld16(tlane + 2 * kH + 32 * uh + c0, p2);
             tc::tmem_ld_wait();
 #pragma unroll
-            for (int u = 0; u < 16; ++u) {
-              const float aa = tanh_f(p0[u] + bl[c0 + u]);
-              J0[c0 + u] = aa;
+            for (int u = 0; u < 16; u += 2) {
+              using namespace tc;
+              const f32x2 aa = deep_tanh2(add2(pack2(p0[u], p0[u + 1]), ld2(bl + c0 + u)));
+              unpack2(aa, J0[c0 + u], J0[c0 + u + 1]);
               if (NJ >= 2) {
-                const float sg = fmaf(-aa, aa, 1.0f);
-                const float a1 = sg * p1[u];
-                J1[c0 + u] = a1;
-                if (NJ == 3) J2[c0 + u] = fmaf(sg, p2[u], -2.0f * aa * a1 * p1[u]);
+                const f32x2 naa = mul2(aa, splat2(-1.0f));
+                const f32x2 sg = fma2(naa, aa, splat2(1.0f));
+                const f32x2 q1 = pack2(p1[u], p1[u + 1]);
+                const f32x2 a1 = mul2(sg, q1);
+                unpack2(a1, J1[c0 + u], J1[c0 + u + 1]);
+                if (NJ == 3)
+                  unpack2(fma2(sg, pack2(p2[u], p2[u + 1]), mul2(mul2(mul2(naa, splat2(2.0f)), a1), q1)), J2[c0 + u], J2[c0 + u + 1]);
               }
             }
           }
         }
         {
-          float f0 = 0.f, f1 = 0.f, f2 = 0.f;
+          tc::f32x2 fpp[3] = {0ull, 0ull, 0ull};
 #pragma unroll
-          for (int u = 0; u < 32; ++u) {
-            const float wv = sm.w3[32 * uh + u];
-            f0 = fmaf(wv, J0[u], f0);
-            if (NJ >= 2) f1 = fmaf(wv, J1[u], f1);
-            if (NJ == 3) f2 = fmaf(wv, J2[u], f2);
+          for (int u = 0; u < 32; u += 2) {
+            const tc::f32x2 wv = ld2(sm.w3 + 32 * uh + u);
+            fpp[0] = tc::fma2(wv, tc::pack2(J0[u], J0[u + 1]), fpp[0]);
+            if (NJ >= 2) fpp[1] = tc::fma2(wv, tc::pack2(J1[u], J1[u + 1]), fpp[1]);
+            if (NJ == 3) fpp[2] = tc::fma2(wv, tc::pack2(J2[u], J2[u + 1]), fpp[2]);
           }
+          const float f0 = tc::lo2(fpp[0]) + tc::hi2(fpp[0]), f1 = tc::lo2(fpp[1]) + tc::hi2(fpp[1]), f2 = tc::lo2(fpp[2]) + tc::hi2(fpp[2]);
           sm.Fpart[(uh * 3 + 0) * kTP + m] = f0;
           if (NJ >= 2) sm.Fpart[(uh * 3 + 1) * kTP + m] = f1;
           if (NJ == 3) sm.Fpart[(uh * 3 + 2) * kTP + m] = f2;
@@ -342,8 +407,8 @@ __global__ void __launch_bounds__(kThreads, 1) gnn_deep_fwd_tc_kernel(const GnnF
     for (int l = 1; l < L; ++l) sm.bl[(l - 1) * kH + tid] = a.theta[TL.b[l] + tid];
   }
   load_nuc_tables<kThreads>(sm.T, a.theta, L2, a.nuclei, a.onehot, a.Na, a.n_types);
-  if (tid == 0) { tc::mbar_init(&sm.bar, 1); tc::fence_mbar_init(); }
-  if (tid < 32) tc::tmem_alloc(&sm.tmem_slot, 256);
+  if (tid == 0) { tc::mbar_init(&sm.bar[0], 1); tc::mbar_init(&sm.bar[1], 1); tc::mbar_init(&sm.bar[2], 1); tc::fence_mbar_init(); }
+  if (tid < 32) tc::tmem_alloc(&sm.tmem_slot, 512);
   tc::fence_async_smem();
   tc::fence_before_sync();
   __syncthreads();
@@ -364,7 +429,7 @@ __global__ void __launch_bounds__(kThreads, 1) gnn_deep_fwd_tc_kernel(const GnnF
   }
   tc::fence_before_sync();
   __syncthreads();
-  if (tid < 32) tc::tmem_dealloc(tmem, 256);
+  if (tid < 32) tc::tmem_dealloc(tmem, 512);
 }
 
 // =================================================================================================================
@@ -381,25 +446,29 @@ struct DeepAccum {
   }
 };
 
-// reverse of the tanh jet of a hidden layer l >= 1, in place: (c0, c1, c2) = cotangents of (a, a', a'') -> cotangents of the
-// pre-activation jets (P, P', P''); state = (a, P', P'')
+// reverse of the tanh jet of a hidden layer l >= 1 for two units, in place: (c0, c1, c2) = cotangents of (a, a', a'') ->
+// cotangents of the pre-activation jets (P, P', P''); state = (a, P', P'')
 template <int NJ>
-__device__ __forceinline__ void deep_tanh_jet_reverse(float aa, float p1, float p2, float& c0, float& c1, float& c2) {
-  const float sg = fmaf(-aa, aa, 1.0f);
-  float pzb = c0;
+__device__ __forceinline__ void deep_tanh_jet_reverse(tc::f32x2 aa, tc::f32x2 p1, tc::f32x2 p2, tc::f32x2& c0, tc::f32x2& c1, tc::f32x2& c2) {
+  using namespace tc;
+  const f32x2 one = splat2(1.0f), two = splat2(2.0f);
+  const f32x2 naa = mul2(aa, splat2(-1.0f));            // -a
+  const f32x2 sg = fma2(naa, aa, one);                  // 1 - a^2
+  f32x2 pzb = c0;
   if (NJ >= 2) {
-    const float a1b = c1;
-    pzb = fmaf(-2.0f * aa * p1, a1b, pzb);
-    float t1 = a1b;
+    const f32x2 nap1 = mul2(naa, p1);                   // -a p1
+    pzb = fma2(mul2(nap1, two), c1, pzb);               // - 2 a p1 c1
+    f32x2 t1 = c1;
     if (NJ == 3) {
-      const float a2b = c2;
-      c2 = a2b * sg;
-      t1 = fmaf(-4.0f * aa * p1, a2b, t1);
-      pzb = fmaf(a2b, fmaf(-2.0f * aa, p2, -2.0f * fmaf(-3.0f * aa, aa, 1.0f) * p1 * p1), pzb);
+      t1 = fma2(mul2(nap1, splat2(4.0f)), c2, t1);      // c1 - 4 a p1 c2
+      const f32x2 c3 = fma2(mul2(aa, splat2(-3.0f)), aa, one);                                   // 1 - 3 a^2
+      const f32x2 inner = fma2(mul2(naa, two), p2, mul2(mul2(c3, splat2(-2.0f)), mul2(p1, p1)));   // -2 a p2 - 2 (1 - 3 a^2) p1^2
+      pzb = fma2(c2, inner, pzb);
+      c2 = mul2(c2, sg);
     }
-    c1 = sg * t1;
+    c1 = mul2(sg, t1);
   }
-  c0 = sg * pzb;
+  c0 = mul2(sg, pzb);
 }
 
 template <int NJ, int L>
@@ -431,12 +500,13 @@ __device__ void deep_bwd_tile(SmemDeepB& sm, const GnnBwdArgs& a, long long row0
   float* const Wop = sm.R + kDWopOff;
   float* const AT = sm.R;
   float* const PT = sm.R + 32 * kDTChunk;
-  const uint64_t dAlo = tc::make_desc(tc::smem_u32(Alo), kDChunkA, 128);
+  const uint64_t dAlo[2] = {tc::make_desc(tc::smem_u32(Alo), kDChunkA, 128), tc::make_desc(tc::smem_u32(Alo + kH * kTP), kDChunkA, 128)};
   const uint64_t dWh = tc::make_desc(tc::smem_u32(Wop), kDChunkB, 128);
   const uint64_t dWl = tc::make_desc(tc::smem_u32(Wop + kH * kH), kDChunkB, 128);
   const uint64_t dAT = tc::make_desc(tc::smem_u32(AT), kDTChunk * 4, 128);
   const uint64_t dPT = tc::make_desc(tc::smem_u32(PT), kDTChunk * 4, 128);
   const float* const wr = sm.wr + 32 * uh;
+  float* const a0 = sm.A0 + (16 * uh * kTP + m) * 2;
 
   // cotangents of (f, f', f'') of nucleus i   [pre() of gnn.cu]
   auto pre = [&](int i) {
@@ -527,31 +597,32 @@ __device__ void deep_bwd_tile(SmemDeepB& sm, const GnnBwdArgs& a, long long row0
 #pragma unroll 1
       for (int i = 0; i < a.Na; ++i) {
         pre(i);
-        float av[32];
         float r;
         {
           const float* nc = sm.T.nuc + i * 4;
           const float d0 = xst[0] - nc[0], d1 = xst[1] - nc[1], d2 = xst[2] - nc[2];
           r = sqrtf(fmaf(d0, d0, fmaf(d1, d1, d2 * d2)));
-          deep_first_layer(av, wr, sm.wt + 32 * uh, sm.T.cb + sm.T.cls[i] * kH + 32 * uh, r, tprime);
+          deep_first_layer_smem(a0, wr, sm.wt + 32 * uh, sm.T.cb + sm.T.cls[i] * kH + 32 * uh, r, tprime);
         }
         // ---------------- forward recompute: S(l) <- (a_l, P_l', P_l'') for l = 1 .. L-1 ----------------
 #pragma unroll 1
         for (int l = 1; l < L; ++l) {
           load_W(l, 0);
 #pragma unroll
-          for (int jt = 0; jt < NJ; ++jt) {
-            if (jt > 0) deep_wait(&sm.bar, phase);
+          for (int jt = 0; jt < NJ; ++jt) {      // the staging of jet jt + 1 runs under the MMAs of jet jt (two operand buffers)
+            const int buf = jt & 1;
+            if (jt >= 2) deep_wait(sm.bar, phase, buf);
             float x[32];
-            if (l == 1) { if (jt == 0) deep_jet0<0>(av, wr, x); else if (jt == 1) deep_jet0<1>(av, wr, x); else deep_jet0<2>(av, wr, x); }
+            if (l == 1) { if (jt == 0) deep_jet0_smem<0>(a0, wr, x); else if (jt == 1) deep_jet0_smem<1>(a0, wr, x); else deep_jet0_smem<2>(a0, wr, x); }
             else {
               const uint32_t ts = tlane + dcol_state(l - 1) + 32 * uh;
               if (jt == 0) deep_jet_state<0>(ts, x); else if (jt == 1) deep_jet_state<1>(ts, x); else deep_jet_state<2>(ts, x);
             }
-            deep_stage_A(x, tlane + kDColDw + 32 * uh, Alo, uh, m);
-            deep_sync_issue_gemm(tmem + dcol_state(l) + jt * kH, tmem + kDColDw, dAlo, dWh, dWl, idesc, &sm.bar);
+            deep_stage_A(x, tlane + kDColDw + kH * buf + 32 * uh, Alo + buf * kH * kTP, uh, m);
+            deep_sync_issue_gemm(tmem + dcol_state(l) + jt * kH, tmem + kDColDw + kH * buf, dAlo[buf], dWh, dWl, idesc, &sm.bar[buf]);
           }
-          deep_wait(&sm.bar, phase);
+#pragma unroll
+          for (int jt = (NJ >= 2 ? NJ - 2 : 0); jt < NJ; ++jt) deep_wait(sm.bar, phase, jt & 1);
           // P -> a = tanh(P + b_l) in place (the derivative jets stay as they are)
           const float* bl = sm.bl + (l - 1) * kH + 32 * uh;
 #pragma unroll
@@ -560,7 +631,7 @@ __device__ void deep_bwd_tile(SmemDeepB& sm, const GnnBwdArgs& a, long long row0
             tc::tmem_ld16(tlane + dcol_state(l) + 32 * uh + c0, p0);
             tc::tmem_ld_wait();
 #pragma unroll
-            for (int u = 0; u < 16; ++u) p0[u] = tanh_f(p0[u] + bl[c0 + u]);
+            for (int u = 0; u < 16; u += 2) tc::unpack2(deep_tanh2(tc::add2(tc::pack2(p0[u], p0[u + 1]), ld2(bl + c0 + u))), p0[u], p0[u + 1]);
             tc::tmem_st16(tlane + dcol_state(l) + 32 * uh + c0, p0);
           }
           tc::tmem_st_wait();
@@ -568,7 +639,7 @@ __device__ void deep_bwd_tile(SmemDeepB& sm, const GnnBwdArgs& a, long long row0
         // ---------------- last layer and the reverse of the top hidden layer ----------------
         float q0[32], q1[32], q2[32];
         {
-          float f0 = 0.f, f1 = 0.f, f2 = 0.f;
+          tc::f32x2 fpp[3] = {0ull, 0ull, 0ull};
           float g32[32];
           const uint32_t ts = tlane + dcol_state(L - 1) + 32 * uh;
 #pragma unroll
@@ -579,32 +650,34 @@ __device__ void deep_bwd_tile(SmemDeepB& sm, const GnnBwdArgs& a, long long row0
             if (NJ == 3) tc::tmem_ld16(ts + 2 * kH + c0, s2);
             tc::tmem_ld_wait();
 #pragma unroll
-            for (int u = 0; u < 16; ++u) {
-              const float wv = sm.w3[32 * uh + c0 + u];
-              const float aa = s0[u];
-              const float sg = fmaf(-aa, aa, 1.0f);
-              f0 = fmaf(wv, aa, f0);
-              float gw = aa * fb0;
-              float c0v = wv * fb0, c1v = 0.f, c2v = 0.f, p1 = 0.f, p2 = 0.f;
+            for (int u = 0; u < 16; u += 2) {
+              using namespace tc;
+              const f32x2 wv = ld2(sm.w3 + 32 * uh + c0 + u);
+              const f32x2 aa = pack2(s0[u], s0[u + 1]);
+              const f32x2 sg = fma2(mul2(aa, splat2(-1.0f)), aa, splat2(1.0f));
+              fpp[0] = fma2(wv, aa, fpp[0]);
+              f32x2 gw = mul2(aa, splat2(fb0));
+              f32x2 c0v = mul2(wv, splat2(fb0)), c1v = 0ull, c2v = 0ull, p1 = 0ull, p2 = 0ull;
               if (NJ >= 2) {
-                p1 = s1[u];
-                const float a1 = sg * p1;
-                f1 = fmaf(wv, a1, f1);
-                gw = fmaf(a1, fb1, gw);
-                c1v = wv * fb1;
+                p1 = pack2(s1[u], s1[u + 1]);
+                const f32x2 a1 = mul2(sg, p1);
+                fpp[1] = fma2(wv, a1, fpp[1]);
+                gw = fma2(a1, splat2(fb1), gw);
+                c1v = mul2(wv, splat2(fb1));
                 if (NJ == 3) {
-                  p2 = s2[u];
-                  const float a2 = fmaf(sg, p2, -2.0f * aa * a1 * p1);
-                  f2 = fmaf(wv, a2, f2);
-                  gw = fmaf(a2, fb2, gw);
-                  c2v = wv * fb2;
+                  p2 = pack2(s2[u], s2[u + 1]);
+                  const f32x2 a2 = fma2(sg, p2, mul2(mul2(mul2(aa, splat2(-2.0f)), a1), p1));
+                  fpp[2] = fma2(wv, a2, fpp[2]);
+                  gw = fma2(a2, splat2(fb2), gw);
+                  c2v = mul2(wv, splat2(fb2));
                 }
               }
               deep_tanh_jet_reverse<NJ>(aa, p1, p2, c0v, c1v, c2v);
-              q0[c0 + u] = c0v; q1[c0 + u] = c1v; q2[c0 + u] = c2v;
-              g32[c0 + u] = gw;
+              unpack2(c0v, q0[c0 + u], q0[c0 + u + 1]); unpack2(c1v, q1[c0 + u], q1[c0 + u + 1]); unpack2(c2v, q2[c0 + u], q2[c0 + u + 1]);
+              unpack2(gw, g32[c0 + u], g32[c0 + u + 1]);
             }
           }
+          const float f0 = tc::lo2(fpp[0]) + tc::hi2(fpp[0]), f1 = tc::lo2(fpp[1]) + tc::hi2(fpp[1]), f2 = tc::lo2(fpp[2]) + tc::hi2(fpp[2]);
           sm.Fpart[(uh * 3 + 0) * kTP + m] = f0;
           if (NJ >= 2) sm.Fpart[(uh * 3 + 1) * kTP + m] = f1;
           if (NJ == 3) sm.Fpart[(uh * 3 + 2) * kTP + m] = f2;
@@ -625,17 +698,19 @@ __device__ void deep_bwd_tile(SmemDeepB& sm, const GnnBwdArgs& a, long long row0
           load_W(l, 1);
 #pragma unroll
           for (int jt = 0; jt < NJ; ++jt) {
-            if (jt > 0) deep_wait(&sm.bar, phase);
-            deep_stage_A(jt == 0 ? q0 : (jt == 1 ? q1 : q2), tlane + kDColDw + 32 * uh, Alo, uh, m);
-            deep_sync_issue_gemm(tmem + dcol_state(l) + jt * kH, tmem + kDColDw, dAlo, dWh, dWl, idesc, &sm.bar);
+            const int buf = jt & 1;
+            if (jt >= 2) deep_wait(sm.bar, phase, buf);
+            deep_stage_A(jt == 0 ? q0 : (jt == 1 ? q1 : q2), tlane + kDColDw + kH * buf + 32 * uh, Alo + buf * kH * kTP, uh, m);
+            deep_sync_issue_gemm(tmem + dcol_state(l) + jt * kH, tmem + kDColDw + kH * buf, dAlo[buf], dWh, dWl, idesc, &sm.bar[buf]);
           }
-          deep_wait(&sm.bar, phase);
+#pragma unroll
+          for (int jt = (NJ >= 2 ? NJ - 2 : 0); jt < NJ; ++jt) deep_wait(sm.bar, phase, jt & 1);
           // dW_l[k][j] += sum over trajectories and jets of A_{l-1}[jet][k] Pbar_l[jet][j]   (K = trajectory, stacked hi | lo rows)
 #pragma unroll
           for (int jt = 0; jt < NJ; ++jt) {
-            if (jt > 0) deep_wait(&sm.bar, phase);
+            if (jt > 0) deep_wait(sm.bar, phase, 2);
             float x[32];
-            if (l == 1) { if (jt == 0) deep_jet0<0>(av, wr, x); else if (jt == 1) deep_jet0<1>(av, wr, x); else deep_jet0<2>(av, wr, x); }
+            if (l == 1) { if (jt == 0) deep_jet0_smem<0>(a0, wr, x); else if (jt == 1) deep_jet0_smem<1>(a0, wr, x); else deep_jet0_smem<2>(a0, wr, x); }
             else {
               const uint32_t ts = tlane + dcol_state(l - 1) + 32 * uh;
               if (jt == 0) deep_jet_state<0>(ts, x); else if (jt == 1) deep_jet_state<1>(ts, x); else deep_jet_state<2>(ts, x);
@@ -643,11 +718,12 @@ __device__ void deep_bwd_tile(SmemDeepB& sm, const GnnBwdArgs& a, long long row0
             const float (&p)[32] = jt == 0 ? q0 : (jt == 1 ? q1 : q2);
             const int cbase = (m >> 2) * kDTChunk, csub = m & 3;
 #pragma unroll
-            for (int u = 0; u < 32; ++u) {
-              AT[cbase + (32 * uh + u) * 4 + csub] = x[u];
-              AT[cbase + (kH + 32 * uh + u) * 4 + csub] = tc::lo_tf32(x[u]);
-              PT[cbase + (32 * uh + u) * 4 + csub] = p[u];
-              PT[cbase + (kH + 32 * uh + u) * 4 + csub] = tc::lo_tf32(p[u]);
+            for (int u = 0; u < 32; u += 2) {
+              const tc::f32x2 xl = lo2pk(tc::pack2(x[u], x[u + 1])), pl = lo2pk(tc::pack2(p[u], p[u + 1]));
+              float* at = AT + cbase + (32 * uh + u) * 4 + csub;
+              float* pt = PT + cbase + (32 * uh + u) * 4 + csub;
+              at[0] = x[u]; at[4] = x[u + 1]; at[kH * 4] = tc::lo2(xl); at[kH * 4 + 4] = tc::hi2(xl);
+              pt[0] = p[u]; pt[4] = p[u + 1]; pt[kH * 4] = tc::lo2(pl); pt[kH * 4 + 4] = tc::hi2(pl);
             }
             tc::fence_async_smem();
             tc::fence_before_sync();
@@ -659,12 +735,79 @@ __device__ void deep_bwd_tile(SmemDeepB& sm, const GnnBwdArgs& a, long long row0
                 for (int ksx = 0; ksx < 16; ++ksx)
                   tc::mma_tf32(tmem + kDColDw, dAT + ksx * ((2 * kDTChunk * 4) >> 4), dPT + ksx * ((2 * kDTChunk * 4) >> 4), idesc_dw,
                                (jt | ksx) != 0);
-                tc::commit(&sm.bar);
+                tc::commit(&sm.bar[2]);
               }
               __syncwarp();
             }
           }
-          deep_wait(&sm.bar, phase);
+          if (l > 1) {
+            // reverse of the tanh jet of layer l-1: cotangent jets Abar_{l-1} (columns of layer l) and the state of layer l-1
+            const uint32_t tb = tlane + dcol_state(l) + 32 * uh, ts = tlane + dcol_state(l - 1) + 32 * uh;
+#pragma unroll
+            for (int c0 = 0; c0 < 32; c0 += 16) {
+              float b0[16], b1[16], b2[16], s0[16], s1[16], s2[16];
+              tc::tmem_ld16(tb + c0, b0); tc::tmem_ld16(ts + c0, s0);
+              if (NJ >= 2) { tc::tmem_ld16(tb + kH + c0, b1); tc::tmem_ld16(ts + kH + c0, s1); }
+              if (NJ == 3) { tc::tmem_ld16(tb + 2 * kH + c0, b2); tc::tmem_ld16(ts + 2 * kH + c0, s2); }
+              tc::tmem_ld_wait();
+#pragma unroll
+              for (int u = 0; u < 16; u += 2) {
+                using namespace tc;
+                f32x2 c0v = pack2(b0[u], b0[u + 1]), c1v = 0ull, c2v = 0ull, p1 = 0ull, p2 = 0ull;
+                if (NJ >= 2) { c1v = pack2(b1[u], b1[u + 1]); p1 = pack2(s1[u], s1[u + 1]); }
+                if (NJ == 3) { c2v = pack2(b2[u], b2[u + 1]); p2 = pack2(s2[u], s2[u + 1]); }
+                deep_tanh_jet_reverse<NJ>(pack2(s0[u], s0[u + 1]), p1, p2, c0v, c1v, c2v);
+                unpack2(c0v, q0[c0 + u], q0[c0 + u + 1]); unpack2(c1v, q1[c0 + u], q1[c0 + u + 1]); unpack2(c2v, q2[c0 + u], q2[c0 + u + 1]);
+              }
+            }
+          } else {
+            // first layer reverse   [epilogue_b1 of gnn.cu]
+            tc::f32x2 rp2 = 0ull;
+            float ps32[32], pr32[32];
+            const uint32_t tb = tlane + dcol_state(1) + 32 * uh;
+#pragma unroll
+            for (int c0 = 0; c0 < 32; c0 += 16) {
+              float b0[16], b1[16], b2[16];
+              tc::tmem_ld16(tb + c0, b0);
+              if (NJ >= 2) tc::tmem_ld16(tb + kH + c0, b1);
+              if (NJ == 3) tc::tmem_ld16(tb + 2 * kH + c0, b2);
+              tc::tmem_ld_wait();
+#pragma unroll
+              for (int u = 0; u < 16; u += 2) {
+                using namespace tc;
+                const f32x2 one = splat2(1.0f);
+                const f32x2 aa = ld2(a0 + ((c0 + u) >> 1) * (2 * kTP));
+                const f32x2 wv = ld2(wr + c0 + u);
+                const f32x2 aw = mul2(aa, wv);                                  // a w
+                const f32x2 sg = fma2(mul2(aa, splat2(-1.0f)), aa, one);        // 1 - a^2
+                f32x2 t = pack2(b0[u], b0[u + 1]);
+                f32x2 e = 0ull;
+                if (NJ >= 2) {
+                  const f32x2 c1 = pack2(b1[u], b1[u + 1]);
+                  t = fma2(mul2(aw, splat2(-2.0f)), c1, t);                     // - 2 a w b1
+                  e = c1;
+                  if (NJ == 3) {
+                    const f32x2 c2 = pack2(b2[u], b2[u + 1]);
+                    const f32x2 c3 = fma2(mul2(aa, splat2(-3.0f)), aa, one);    // 1 - 3 a^2
+                    t = fma2(mul2(mul2(mul2(wv, wv), splat2(-2.0f)), c3), c2, t);   // - 2 w^2 (1 - 3 a^2) b2
+                    e = fma2(mul2(aw, splat2(-4.0f)), c2, e);                   // b1 - 4 a w b2
+                  }
+                }
+                const f32x2 pb = mul2(sg, t);
+                rp2 = fma2(pb, wv, rp2);
+                unpack2(pb, ps32[c0 + u], ps32[c0 + u + 1]);
+                unpack2(fma2(pb, splat2(r), mul2(sg, e)), pr32[c0 + u], pr32[c0 + u + 1]);
+              }
+            }
+            sm.Rpart[uh * kTP + m] = tc::lo2(rp2) + tc::hi2(rp2);
+            const float ps = warp_vec32_sum(ps32, lane);
+            const float pr = warp_vec32_sum(pr32, lane);
+            sm.S[(w * kMaxClasses + sm.T.cls[i]) * 32 + lane] += ps;
+            G.g_wt = fmaf(tprime, ps, G.g_wt);
+            G.g_wr += pr;
+          }
+          // the last weight-gradient batch of the layer ran under the reverse epilogue above
+          deep_wait(sm.bar, phase, 2);
           // fold the stacked tile into the fp32 sums: dW_l[k][j] = D[k][j] + D[k][64 + j] + D[64 + k][j] (+ the lo.lo corner)
           {
             float v[32];
@@ -689,63 +832,6 @@ __device__ void deep_bwd_tile(SmemDeepB& sm, const GnnBwdArgs& a, long long row0
               for (int u = 0; u < 32; ++u) dws[(32 * uh + u) * kH] += v[u];
             }
           }
-          if (l > 1) {
-            // reverse of the tanh jet of layer l-1: cotangent jets Abar_{l-1} (columns of layer l) and the state of layer l-1
-            const uint32_t tb = tlane + dcol_state(l) + 32 * uh, ts = tlane + dcol_state(l - 1) + 32 * uh;
-#pragma unroll
-            for (int c0 = 0; c0 < 32; c0 += 16) {
-              float b0[16], b1[16], b2[16], s0[16], s1[16], s2[16];
-              tc::tmem_ld16(tb + c0, b0); tc::tmem_ld16(ts + c0, s0);
-              if (NJ >= 2) { tc::tmem_ld16(tb + kH + c0, b1); tc::tmem_ld16(ts + kH + c0, s1); }
-              if (NJ == 3) { tc::tmem_ld16(tb + 2 * kH + c0, b2); tc::tmem_ld16(ts + 2 * kH + c0, s2); }
-              tc::tmem_ld_wait();
-#pragma unroll
-              for (int u = 0; u < 16; ++u) {
-                float c0v = b0[u], c1v = NJ >= 2 ? b1[u] : 0.f, c2v = NJ == 3 ? b2[u] : 0.f;
-                deep_tanh_jet_reverse<NJ>(s0[u], NJ >= 2 ? s1[u] : 0.f, NJ == 3 ? s2[u] : 0.f, c0v, c1v, c2v);
-                q0[c0 + u] = c0v; q1[c0 + u] = c1v; q2[c0 + u] = c2v;
-              }
-            }
-          }
-        }
-        // ---------------- first layer reverse   [epilogue_b1 of gnn.cu] ----------------
-        {
-          float rp = 0.f;
-          float ps32[32], pr32[32];
-          const uint32_t tb = tlane + dcol_state(1) + 32 * uh;
-#pragma unroll
-          for (int c0 = 0; c0 < 32; c0 += 16) {
-            float b0[16], b1[16], b2[16];
-            tc::tmem_ld16(tb + c0, b0);
-            if (NJ >= 2) tc::tmem_ld16(tb + kH + c0, b1);
-            if (NJ == 3) tc::tmem_ld16(tb + 2 * kH + c0, b2);
-            tc::tmem_ld_wait();
-#pragma unroll
-            for (int u = 0; u < 16; ++u) {
-              const float aa = av[c0 + u];
-              const float wv = wr[c0 + u];
-              const float sg = fmaf(-aa, aa, 1.0f);
-              float t = b0[u], e = 0.f;
-              if (NJ >= 2) {
-                t = fmaf(-2.0f * aa * wv, b1[u], t);
-                e = b1[u];
-                if (NJ == 3) {
-                  t = fmaf(-2.0f * wv * wv * fmaf(-3.0f * aa, aa, 1.0f), b2[u], t);
-                  e = fmaf(-4.0f * aa * wv, b2[u], e);
-                }
-              }
-              const float pb = sg * t;
-              rp = fmaf(pb, wv, rp);
-              ps32[c0 + u] = pb;
-              pr32[c0 + u] = fmaf(pb, r, sg * e);
-            }
-          }
-          sm.Rpart[uh * kTP + m] = rp;
-          const float ps = warp_vec32_sum(ps32, lane);
-          const float pr = warp_vec32_sum(pr32, lane);
-          sm.S[(w * kMaxClasses + sm.T.cls[i]) * 32 + lane] += ps;
-          G.g_wt = fmaf(tprime, ps, G.g_wt);
-          G.g_wr += pr;
         }
         tc::fence_before_sync();
         __syncthreads();
@@ -830,7 +916,7 @@ __global__ void __launch_bounds__(kThreads, 1) gnn_deep_bwd_tc_kernel(const GnnB
   load_nuc_tables<kThreads>(sm.T, a.theta, L2, a.nuclei, a.onehot, a.Na, a.n_types);
   for (int i = tid; i < 8 * kMaxClasses * 32; i += kThreads) sm.S[i] = 0.f;
   for (int i = tid; i < (kMaxLayers - 1) * kH * kH; i += kThreads) sm.DWs[i] = 0.f;
-  if (tid == 0) { tc::mbar_init(&sm.bar, 1); tc::fence_mbar_init(); }
+  if (tid == 0) { tc::mbar_init(&sm.bar[0], 1); tc::mbar_init(&sm.bar[1], 1); tc::mbar_init(&sm.bar[2], 1); tc::fence_mbar_init(); }
   if (tid < 32) tc::tmem_alloc(&sm.tmem_slot, 512);
   tc::fence_async_smem();
   tc::fence_before_sync();
