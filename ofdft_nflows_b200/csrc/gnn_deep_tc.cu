@@ -31,8 +31,8 @@ constexpr int kDTChunk = kTP * 4 + 4;       // floats per trajectory-chunk of a 
 constexpr int kDColDw = 384;                // weight-gradient accumulator (128 columns) / TS-mode "hi" operand (first 64)
 __host__ __device__ constexpr int dcol_state(int l) { return 192 * (l - 1); }
 constexpr int kDRegionFloats = 2 * 32 * kDTChunk;
-constexpr int kDWopOff = 2 * kH * kTP;      // float offset of the weight operand (hi | lo) inside the region; two remainder buffers in front
-static_assert(kDWopOff + 2 * kH * kH <= kDRegionFloats, "GEMM-phase operands exceed the staging region");
+constexpr int kDWopOff = 2 * kH * kTP;      // float offset of the two weight operand buffers (hi | lo each) inside the region; two remainder buffers in front
+static_assert(kDWopOff + 2 * 2 * kH * kH <= kDRegionFloats, "GEMM-phase operands exceed the staging region");
 
 struct SmemDeepF {
   float Alo[2 * kH * kTP];            // tf32 remainders of the jet being staged, two buffers
@@ -124,6 +124,7 @@ __device__ __forceinline__ void deep_sync_issue_gemm(uint32_t d, uint32_t ahi, u
                                                      uint64_t* bar) {
   tc::tmem_st_wait();
   tc::tmem_ld_wait();
+  asm volatile("cp.async.wait_all;" ::: "memory");     // weight operand copies of this thread (backward kernel)
   tc::fence_async_smem();
   tc::fence_before_sync();
   __syncthreads();
@@ -501,8 +502,9 @@ __device__ void deep_bwd_tile(SmemDeepB& sm, const GnnBwdArgs& a, long long row0
   float* const AT = sm.R;
   float* const PT = sm.R + 32 * kDTChunk;
   const uint64_t dAlo[2] = {tc::make_desc(tc::smem_u32(Alo), kDChunkA, 128), tc::make_desc(tc::smem_u32(Alo + kH * kTP), kDChunkA, 128)};
-  const uint64_t dWh = tc::make_desc(tc::smem_u32(Wop), kDChunkB, 128);
-  const uint64_t dWl = tc::make_desc(tc::smem_u32(Wop + kH * kH), kDChunkB, 128);
+  const uint64_t dWh[2] = {tc::make_desc(tc::smem_u32(Wop), kDChunkB, 128), tc::make_desc(tc::smem_u32(Wop + 2 * kH * kH), kDChunkB, 128)};
+  const uint64_t dWl[2] = {tc::make_desc(tc::smem_u32(Wop + kH * kH), kDChunkB, 128), tc::make_desc(tc::smem_u32(Wop + 3 * kH * kH), kDChunkB, 128)};
+  int wb = 0;                 // weight operand buffer of the current GEMM phase (the next phase's operand is copied into the other one)
   const uint64_t dAT = tc::make_desc(tc::smem_u32(AT), kDTChunk * 4, 128);
   const uint64_t dPT = tc::make_desc(tc::smem_u32(PT), kDTChunk * 4, 128);
   const float* const wr = sm.wr + 32 * uh;
@@ -565,11 +567,15 @@ __device__ void deep_bwd_tile(SmemDeepB& sm, const GnnBwdArgs& a, long long row0
     ysx[2] += fmaf(rbar, u2, db2);
   };
   // hi | lo weight operand of hidden layer l (orient 0: forward, B[n = j][k]; 1: transposed, B[n = k][j]) -> staging region
-  auto load_W = [&](int l, int orient) {
-    const float4* src = reinterpret_cast<const float4*>(a.w2split + (size_t)((l - 1) * 4 + 2 * orient) * kH * kH);
+  // (asynchronous copies: cp.async, completed by the wait in front of the next MMA hand-off)
+  auto load_W = [&](int l, int orient, int buf) {
+    const float4* src = reinterpret_cast<const float4*>(a.w2split + (size_t)((l - 1) * 4 + 2 * orient) * kH * kH) + tid;
+    const uint32_t dst = tc::smem_u32(Wop + buf * 2 * kH * kH) + tid * 16;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) reinterpret_cast<float4*>(Wop)[q * kThreads + tid] = __ldg(src + q * kThreads + tid);
+    for (int q = 0; q < 8; ++q)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + q * kThreads * 16), "l"(src + q * kThreads) : "memory");
   };
+  load_W(1, 0, wb);           // forward operand of the first hidden layer for the first nucleus
 
   for (int step = a.n_steps - 1; step >= 0; --step) {
     sumx[0] = sumx[1] = sumx[2] = 0.f; sums[0] = sums[1] = sums[2] = 0.f;
@@ -607,7 +613,8 @@ __device__ void deep_bwd_tile(SmemDeepB& sm, const GnnBwdArgs& a, long long row0
         // ---------------- forward recompute: S(l) <- (a_l, P_l', P_l'') for l = 1 .. L-1 ----------------
 #pragma unroll 1
         for (int l = 1; l < L; ++l) {
-          load_W(l, 0);
+          // the next GEMM phase's weight operand (forward of layer l + 1, or transposed of the top layer) into the other buffer
+          if (l + 1 < L) load_W(l + 1, 0, wb ^ 1); else load_W(L - 1, 1, wb ^ 1);
 #pragma unroll
           for (int jt = 0; jt < NJ; ++jt) {      // the staging of jet jt + 1 runs under the MMAs of jet jt (two operand buffers)
             const int buf = jt & 1;
@@ -619,8 +626,9 @@ __device__ void deep_bwd_tile(SmemDeepB& sm, const GnnBwdArgs& a, long long row0
               if (jt == 0) deep_jet_state<0>(ts, x); else if (jt == 1) deep_jet_state<1>(ts, x); else deep_jet_state<2>(ts, x);
             }
             deep_stage_A(x, tlane + kDColDw + kH * buf + 32 * uh, Alo + buf * kH * kTP, uh, m);
-            deep_sync_issue_gemm(tmem + dcol_state(l) + jt * kH, tmem + kDColDw + kH * buf, dAlo[buf], dWh, dWl, idesc, &sm.bar[buf]);
+            deep_sync_issue_gemm(tmem + dcol_state(l) + jt * kH, tmem + kDColDw + kH * buf, dAlo[buf], dWh[wb], dWl[wb], idesc, &sm.bar[buf]);
           }
+          wb ^= 1;
 #pragma unroll
           for (int jt = (NJ >= 2 ? NJ - 2 : 0); jt < NJ; ++jt) deep_wait(sm.bar, phase, jt & 1);
           // P -> a = tanh(P + b_l) in place (the derivative jets stay as they are)
@@ -686,22 +694,24 @@ __device__ void deep_bwd_tile(SmemDeepB& sm, const GnnBwdArgs& a, long long row0
         // ---------------- hidden layers L-1 .. 1 ----------------
 #pragma unroll 1
         for (int l = L - 1; l >= 1; --l) {      // a real loop: one copy of the layer body keeps the code inside the instruction cache
+          // Abar_{l-1}[jet] = Pbar_l[jet] . W_l^T  -> the (dead) state columns of layer l; the top layer's transposed operand was
+          // copied under the forward GEMM, the others come in here (the weight-gradient operands overwrite the whole region)
+          if (l < L - 1) load_W(l, 1, wb);
+#pragma unroll
+          for (int jt = 0; jt < NJ; ++jt) {
+            const int buf = jt & 1;
+            if (jt >= 2) deep_wait(sm.bar, phase, buf);
+            deep_stage_A(jt == 0 ? q0 : (jt == 1 ? q1 : q2), tlane + kDColDw + kH * buf + 32 * uh, Alo + buf * kH * kTP, uh, m);
+            deep_sync_issue_gemm(tmem + dcol_state(l) + jt * kH, tmem + kDColDw + kH * buf, dAlo[buf], dWh[wb], dWl[wb], idesc, &sm.bar[buf]);
+          }
           {
+            // bias gradient of layer l (the butterfly runs under the MMAs)
             float t[32];
 #pragma unroll
             for (int u = 0; u < 32; ++u) t[u] = q0[u];
             const float s = warp_vec32_sum(t, lane);
 #pragma unroll
             for (int ll = 1; ll < L; ++ll) G.g_b[ll] += ll == l ? s : 0.f;
-          }
-          // Abar_{l-1}[jet] = Pbar_l[jet] . W_l^T  -> the (dead) state columns of layer l
-          load_W(l, 1);
-#pragma unroll
-          for (int jt = 0; jt < NJ; ++jt) {
-            const int buf = jt & 1;
-            if (jt >= 2) deep_wait(sm.bar, phase, buf);
-            deep_stage_A(jt == 0 ? q0 : (jt == 1 ? q1 : q2), tlane + kDColDw + kH * buf + 32 * uh, Alo + buf * kH * kTP, uh, m);
-            deep_sync_issue_gemm(tmem + dcol_state(l) + jt * kH, tmem + kDColDw + kH * buf, dAlo[buf], dWh, dWl, idesc, &sm.bar[buf]);
           }
 #pragma unroll
           for (int jt = (NJ >= 2 ? NJ - 2 : 0); jt < NJ; ++jt) deep_wait(sm.bar, phase, jt & 1);
@@ -833,6 +843,7 @@ __device__ void deep_bwd_tile(SmemDeepB& sm, const GnnBwdArgs& a, long long row0
             }
           }
         }
+        load_W(1, 0, wb);       // forward operand of the first hidden layer for the next nucleus (the region is free again)
         tc::fence_before_sync();
         __syncthreads();
         post(i);
@@ -846,6 +857,7 @@ __device__ void deep_bwd_tile(SmemDeepB& sm, const GnnBwdArgs& a, long long row0
 #pragma unroll
     for (int c = 0; c < 3; ++c) { xb[c] += sumx[c]; sb[c] += sums[c]; }
   }
+  asm volatile("cp.async.wait_all;" ::: "memory");     // the operand copy issued for a next nucleus that does not exist
   if (owner && valid && a.ybar0 != nullptr) {
     float* dst = a.ybar0 + row * a.bar_stride;
     dst[0] = xb[0]; dst[1] = xb[1]; dst[2] = xb[2];
