@@ -38,13 +38,13 @@ WORKLOADS = {
 MLP_FEAT = (512, 512, 512)
 
 
-def algorithmic_flops_per_traj_eval(na: int, jets: int) -> float:
-    """Mat-mul-only 2-jet count per (trajectory, RHS evaluation): Na * [2*J*H^2 + 2*J*H + 2*H]
-    (J = jets carried: 3 = x/logp/score, 1 = x only)."""
-    return na * (2.0 * jets * H * H + 2.0 * jets * H + 2.0 * H)
+def algorithmic_flops_per_traj_eval(na: int, jets: int, nn: int = 2) -> float:
+    """Mat-mul-only 2-jet count per (trajectory, RHS evaluation): Na * [(nn-1)*2*J*H^2 + 2*J*H + 2*H]
+    (J = jets carried: 3 = x/logp/score, 1 = x only; nn hidden layers, 2 in every config of BASELINE.json)."""
+    return na * ((nn - 1) * 2.0 * jets * H * H + 2.0 * jets * H + 2.0 * H)
 
 
-def make_problem(workload: str, bs: int, seed_offset: int = 0):
+def make_problem(workload: str, bs: int, seed_offset: int = 0, nn: int = 2):
     """Synthetic inputs of the named config: promolecular base samples + prior logp/score, LeCun-normal hidden
     layers (zero biases) and a non-zero last layer 0.5*N(0,1/64) (the reference's zero-init
     last layer would make the field trivial).  Uses only the package's own host-side input producers."""
@@ -70,7 +70,12 @@ def make_problem(workload: str, bs: int, seed_offset: int = 0):
     # keep the summed field benign for many-nucleus molecules (the displacement scales with Na)
     w3 = 0.5 * min(1.0, 3.0 / len(z)) * rng.standard_normal((H, 1)) / math.sqrt(H)
     # flat theta, ravel_pytree key order: last_layer.{bias,kernel}, layers_0.{bias,kernel}, layers_1.{bias,kernel}
-    theta = np.concatenate([np.zeros(1), w3.ravel(), np.zeros(H), w1.ravel(), np.zeros(H), w2.ravel()]).astype(np.float32)
+    parts = [np.zeros(1), w3.ravel(), np.zeros(H), w1.ravel()]
+    if nn >= 2:
+        parts += [np.zeros(H), w2.ravel()]
+    for _ in range(nn - 2):                                     # --nn 3 (OFDFT_NF.py:320-326): one more LeCun-normal hidden layer
+        parts += [np.zeros(H), (rng.standard_normal((H, H)) / math.sqrt(H)).ravel()]
+    theta = np.concatenate(parts).astype(np.float32)
     batch = next(U.batch_generator(1234 + seed_offset, bs, U.ProMolecularDensity(z, coords)))
     return mol, nuc, theta, batch
 
@@ -370,6 +375,8 @@ def main():
                     help="allpairs: O(bs^2) cross-half Hartree estimator (coordinates all-gathered over NCCL, tiled pair kernel)")
     ap.add_argument("--recompute", action="store_true",
                     help="no HBM activation checkpoint: the adjoint recomputes the layer-2 jets (tensor cores; with --ffma: FP32 pipe)")
+    ap.add_argument("--nn", type=int, default=2, choices=[1, 2, 3],
+                    help="hidden layers of the GNN radial MLP (OFDFT_NF.py --nn: (64,) / (64,64) / (64,64,64)); BASELINE.json's configs use 2")
     ap.add_argument("--ffma", action="store_true", help="FP32-pipe kernels (ops.PATH_FFMA) instead of the tcgen05 kernels")
     ap.add_argument("--no-extra-blocks", action="store_true",
                     help="skip the hartree_pairs block (N=1) and the strong / allpairs blocks (N>1) of the default run")
@@ -434,7 +441,7 @@ def main():
         return
     molname, bs_default, nuc = WORKLOADS[args.workload]
     bs = args.bs or bs_default
-    mol, nuc, theta_np, batch_np = make_problem(args.workload, bs, seed_offset=rank)
+    mol, nuc, theta_np, batch_np = make_problem(args.workload, bs, seed_offset=rank, nn=args.nn)
     B = 2 * bs
     na = mol["coords"].shape[0]
     is_1d = args.workload == "lih1d"
@@ -443,7 +450,7 @@ def main():
         model = Gen_CNFSimpleMLP(1, MLP_FEAT, bool_neg=True, device=dev)
         spec = ops.EnergySpec(Ne=2, d=1, kin="tfw_1d", hart="softc", nuc="attraction", x="", R=0.7, Z_alpha=3, Z_beta=1)
     else:
-        model = Gen_EqvFlow(3, (H, H), mol["coords"], mol["onehot"], bool_neg=True, device=dev)
+        model = Gen_EqvFlow(3, (H,) * args.nn, mol["coords"], mol["onehot"], bool_neg=True, device=dev)
         spec = ops.EnergySpec(Ne=mol["Ne"], d=3, kin="tf-w", hart="hartree", nuc=nuc, x="lda", coords=mol["coords"], z=mol["z"])
     path = (ops.PATH_FFMA | ops.PATH_FFMA_DW) if args.ffma else ops.PATH_DEFAULT
     est = EnergyEstimator(model, spec, n_steps=args.n_steps, skip_unused_jets=not args.full_jets, act_ckpt=not args.recompute,
@@ -523,12 +530,12 @@ def main():
         Hm, L = MLP_FEAT[0], len(MLP_FEAT)
         fwd_flops = B * evals * ((L - 1) * 3 * 2.0 * Hm * Hm + 3 * 2.0 * Hm + 2 * 2.0 * Hm)    # 3.151 MFLOP
     else:
-        fwd_flops = bs * evals * (algorithmic_flops_per_traj_eval(na, 3) + algorithmic_flops_per_traj_eval(na, jets_b))
+        fwd_flops = bs * evals * (algorithmic_flops_per_traj_eval(na, 3, args.nn) + algorithmic_flops_per_traj_eval(na, jets_b, args.nn))
     bwd_flops = 2.0 * fwd_flops
     kern_avg.setdefault("gnn_bwd", kern_avg.get("mlp_bwd", 0.0)); kern_avg.setdefault("gnn_fwd", kern_avg.get("mlp_fwd", 0.0))
     bwd_s = kern_avg["gnn_bwd"] * 1e-3
     fwd_s = kern_avg["gnn_fwd"] * 1e-3
-    tensor_path = (not is_1d) and not args.ffma
+    tensor_path = (not is_1d) and not args.ffma and args.nn != 1      # one hidden layer has no GEMM: plain FP32 kernels
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -580,12 +587,19 @@ def main():
         tiles_h, tiles_l = math.ceil(bs / 128), math.ceil(bs / 128)
         rc = 72 if args.recompute else 0          # tensor-core recompute of the layer-2 jets: one more 3xTF32 GEMM per jet
         per_h, per_l = (72 + 96 + rc), (24 + 32 + rc // 3) if jets_b == 1 else (72 + 96 + rc)
+        fwd_h, fwd_l = 72, (24 if jets_b == 1 else 72)
+        if args.nn == 3:
+            # gnn_deep_tc.cu, per hidden GEMM layer and jet: 24 forward-recompute + 24 transposed MMAs and a 16-MMA N = 128
+            # weight-gradient batch (2 units each); forward kernel: 24 per layer and jet
+            per_h, per_l = 2 * 3 * (48 + 32), 2 * jets_b * (48 + 32)
+            fwd_h, fwd_l = 2 * 72, 2 * 24 * jets_b
         bwd_tensor_flops = evals * na * mma * (tiles_h * per_h + tiles_l * per_l)
-        fwd_tensor_flops = evals * na * mma * (tiles_h * 72 + tiles_l * (24 if jets_b == 1 else 72))
+        fwd_tensor_flops = evals * na * mma * (tiles_h * fwd_h + tiles_l * fwd_l)
         tf32_peak = 0.5 * peaks.get("bf16_tflops_sustained", 1400.0)
         peak3 = tf32_peak / 3.0            # an fp32-accurate GEMM costs three TF32 passes
         roofline = {
-            "bound": "tensor", "kernel": "gnn_bwd_tc_kernel<recompute>" if args.recompute else "gnn_bwd_tc_kernel",
+            "bound": "tensor", "kernel": ("gnn_deep_bwd_tc_kernel<3>" if args.nn == 3 else
+                                          "gnn_bwd_tc_kernel<recompute>" if args.recompute else "gnn_bwd_tc_kernel"),
             "achieved": bwd_flops / bwd_s / 1e12, "peak": peak3,
             "unit": "TFLOP/s", "achieved_is": "algorithmic fp32-equivalent flops / launch time", "frac": bwd_flops / bwd_s / 1e12 / peak3, "traffic": None,
             "peak_source": ("3xTF32 = 1/3 x 1/2 x bf16_tflops_sustained of MEASURED_PEAKS.json (kernel timed inside the step; of measured)"
@@ -601,9 +615,9 @@ def main():
                                 "ffma_peak": ffma_peak / 1e12, "frac_of_ffma_peak": bwd_flops / bwd_s / ffma_peak,
                                 "peak_source": "ofdft_microbench_ffma measured in this run"},
             "kernel_ms": kern_avg,
-            "backward_mode": ("layer-2 jets recomputed on the tensor cores (no activation checkpoint)" if args.recompute
+            "backward_mode": ("hidden-layer jets recomputed on the tensor cores (no activation checkpoint)" if args.recompute or args.nn == 3
                               else "layer-2 activation checkpoint in HBM"),
-            "fwd": {"kernel": "gnn_fwd_tc_kernel", "achieved": fwd_flops / fwd_s / 1e12, "frac": fwd_flops / fwd_s / 1e12 / peak3,
+            "fwd": {"kernel": "gnn_deep_fwd_tc_kernel<3>" if args.nn == 3 else "gnn_fwd_tc_kernel", "achieved": fwd_flops / fwd_s / 1e12, "frac": fwd_flops / fwd_s / 1e12 / peak3,
                     "executed_tensor_frac_of_dense_tf32": fwd_tensor_flops / fwd_s / 1e12 / tf32_peak,
                     "fp32_equivalent_frac_of_ffma_peak": fwd_flops / fwd_s / ffma_peak},
             "step": {"algorithmic_flops": 3.0 * fwd_flops, "frac_of_ffma_peak": 3.0 * fwd_flops / (total_s / args.steps) / ffma_peak},
@@ -611,21 +625,23 @@ def main():
     else:
         achieved = bwd_flops / bwd_s / 1e12
         roofline = {
-            "bound": "fp32", "kernel": "mlp_bwd_sweep_kernel + mlp_dw_gemm_kernel" if is_1d else "gnn_bwd_kernel",
+            "bound": "fp32", "kernel": ("mlp_bwd_sweep_kernel + mlp_dw_gemm_kernel" if is_1d else
+                                        "gnn_bwd_kernel" if args.nn == 2 else f"gnn_general_bwd_kernel<{args.nn}>"),
             "achieved": achieved, "peak": ffma_peak / 1e12, "unit": "TFLOP/s",
             "frac": achieved / (ffma_peak / 1e12), "traffic": None,
             "peak_source": "ofdft_microbench_ffma measured in this run (FP32 FFMA pipe; MEASURED_PEAKS.json holds HBM/bf16 only)",
             "algorithmic_flops_per_launch": bwd_flops, "executed_over_algorithmic": 1.5 if args.recompute else 1.0,
             "backward_mode": "recompute" if args.recompute else "layer-2 activation checkpoint in HBM",
             "kernel_ms": kern_avg,
-            "fwd": {"kernel": "mlp_fwd_kernel" if is_1d else "gnn_fwd_kernel", "achieved": fwd_flops / fwd_s / 1e12,
+            "fwd": {"kernel": "mlp_fwd_kernel" if is_1d else ("gnn_fwd_kernel" if args.nn == 2 else f"gnn_general_fwd_kernel<{args.nn}>"),
+                    "achieved": fwd_flops / fwd_s / 1e12,
                     "frac": fwd_flops / fwd_s / ffma_peak},
             "step": {"algorithmic_flops": 3.0 * fwd_flops, "frac": 3.0 * fwd_flops / (total_s / args.steps) / ffma_peak},
         }
 
     # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture (same workload only)
     try:
-        if args.workload == "h2o" and bs == 65536 and args.n_steps == 16 and not args.recompute and not args.full_jets:
+        if args.workload == "h2o" and bs == 65536 and args.n_steps == 16 and not args.recompute and not args.full_jets and args.nn == 2:
             prof = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_full_gnn.json" if tensor_path else "r01_ncu_full_gnn_ffma_kernels.json")))
             for k in prof:
                 if ("gnn_bwd_tc_kernel" if tensor_path else "gnn_bwd_kernel") in k["kernel"]:
@@ -643,7 +659,7 @@ def main():
     # the strong-scaling (configs[3]) and all-pairs (configs[4]) blocks (N > 1) -------------------------------------------
     extra = {}
     default_run = (args.workload == "h2o" and not args.bs and args.hartree == "paired" and not args.no_extra_blocks
-                   and not args.recompute and not args.ffma)
+                   and not args.recompute and not args.ffma and args.nn == 2)
     if default_run:
         del batch, flush
         torch.cuda.empty_cache()
@@ -661,7 +677,7 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": (f"LiH 1-D tanh-MLP flow {MLP_FEAT}, TF1D+W / attraction / soft-Coulomb, bs={bs} per GPU "
                                     f"({B} trajectories), RK4 x{args.n_steps}") if is_1d else
-                                   (f"{molname} 3-D equivariant flow (64,64), TF+W / {nuc} / paired Hartree / LDA, "
+                                   (f"{molname} 3-D equivariant flow ({','.join(['64'] * args.nn)}), TF+W / {nuc} / paired Hartree / LDA, "
                                     f"bs={bs} per GPU ({B} trajectories), RK4 x{args.n_steps}"),
                        "second_half_jets": "x only (denp/scorep are unused by the reference loss)" if not args.full_jets
                        else "full (reference dataflow)",

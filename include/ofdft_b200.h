@@ -109,8 +109,9 @@ const char* ofdft_b200_strerror(int code);
 /* ---- 3-D equivariant GNN flow: fused fixed-step (RK4) integrator -------------------------------
  * Replaces neural_ode / neural_ode_score (ofdft_normflows/jax_ode.py:9-49, 51-110) evaluated on
  * Gen_EqvFlow (ofdft_normflows/equiv_flows.py:108-127) with features = (64,) * n_layers, n_layers in {1, 2, 3}
- * (OFDFT_NF.py:320-326; every other driver hard-codes (64, 64)).  n_layers = 2 runs on the tcgen05 tile kernels,
- * 1 and 3 on a plain FP32 kernel pair (no activation checkpoint: act_ckpt is ignored there).
+ * (OFDFT_NF.py:320-326; every other driver hard-codes (64, 64)).  n_layers = 2 runs on the pipelined tcgen05 tile kernels,
+ * n_layers = 3 on the depth-generic tcgen05 kernels (layer states in tensor memory, no activation checkpoint: act_ckpt is
+ * ignored), n_layers = 1 (no hidden GEMM) on a plain FP32 kernel pair; OFDFT_PATH_FFMA selects FP32-pipe kernels for 2 and 3.
  *   theta   : ofdft_cnf_gnn_theta_size(n_types, n_layers) floats (4289 + 64*(2+n_types) for two layers)
  *   nuclei  : (Na,3)     onehot : (Na,n_types)
  *   y_in    : (B, in_stride)  rows [x | logp | s]; columns beyond what the row's jets need are ignored
