@@ -6,8 +6,10 @@
 // the same tiles (128 trajectories per CTA, thread (warp w, lane l) = trajectory m = 32 (w & 3) + l -- the TMEM lane its warp
 // may access -- and unit half uh = w >> 2), the same operand layouts and the same error-compensated 3xTF32 GEMMs
 //     x.w ~= x_hi.w_hi + x_hi.w_lo + x_lo.w_hi         (fp32 accumulation in tensor memory)
-// but one straight-line phase sequence per (RK4 stage, nucleus) with CTA-wide barriers: every hand-off to the tensor core is
-// `stage operands -> __syncthreads -> one elected lane issues the MMAs + tcgen05.commit -> all threads wait on ONE mbarrier`.
+// but one phase sequence per (RK4 stage, nucleus) that every thread walks through: each hand-off to the tensor core is
+// `stage operands -> __syncthreads -> one elected lane issues the MMAs + tcgen05.commit`, each completion one mbarrier that
+// all threads wait on exactly once (two barriers for the two operand buffers of a GEMM -- the staging of jet jt + 1 runs under
+// the MMAs of jet jt --, one for the weight-gradient batches; the last batch of a layer runs under the next reverse epilogue).
 //
 // Tensor memory (512 columns) is the layer-state store of the adjoint.  S(l) = 192 (l - 1) .. + 191 holds hidden layer l >= 1:
 // the forward GEMM leaves the pre-activation jets (P, P', P'') there, the epilogue overwrites P by a = tanh(P + b_l) IN PLACE
@@ -15,11 +17,13 @@
 // l has been reversed its columns are dead and receive the cotangent jets Abar_{l-1} = Pbar_l . W_l^T.  Columns 384..511 are
 // the stacked [hi k | lo k] x [hi j | lo j] weight-gradient accumulator (one chain per (nucleus, evaluation, layer): 48 MMAs,
 // folded into round-to-nearest fp32 sums in shared memory -- the tensor core accumulates with truncation); outside the
-// weight-gradient GEMM its first 64 columns carry the unrounded "hi" A operand of the TS-mode passes.
+// weight-gradient GEMM they carry the two unrounded "hi" A-operand buffers of the TS-mode passes.
 //
 // Shared memory: one 129 KB operand region -- [A^T | Pbar^T] stacked K = trajectory operands of the weight gradient, or, in the
-// GEMM phases, the tf32 remainder of the A operand + the hi | lo weight operand of the layer, copied per use from a prepared
-// global buffer (forward / transposed orientation: 4 x 16 KB per layer) -- plus 16 KB of fp32 weight-gradient sums per layer.
+// GEMM phases, two tf32-remainder buffers of the A operand + two hi | lo weight-operand buffers, filled by cp.async one GEMM
+// phase ahead from a prepared global buffer (forward / transposed orientation: 4 x 16 KB per layer) --, 16 KB of fp32
+// weight-gradient sums per layer and the first-layer activations of the current (nucleus, evaluation).  The layer loops are
+// real loops (one copy of the layer body): unrolled, the code did not fit the instruction cache.
 #include "gnn_common.cuh"
 #include "tc.cuh"
 

@@ -2,7 +2,9 @@
 // (`--nn 1|3` of OFDFT_NF.py:320-326 selects features (64,) / (64,64,64); equiv_flows.py:36-62 builds the stack).
 //
 // The (64, 64) network -- what every other driver of the reference hard-codes -- has the tensor-core tile kernels of
-// gnn_tc.cu.  This file covers the other two depths with one plain FP32 kernel pair: thread = trajectory, the layer jets
+// gnn_tc.cu, (64, 64, 64) those of gnn_deep_tc.cu.  This file covers one hidden layer (no GEMM in that network) and, under
+// OFDFT_PATH_FFMA, three with one plain FP32 kernel pair -- the second, independently written implementation the parity
+// tests compare the tensor-core kernels of depth 3 with: thread = trajectory, the layer jets
 // (a, a', a'') of one (trajectory, nucleus, RHS evaluation) live in the thread's local memory, weights are read through
 // the read-only path with warp-uniform addresses, and the only cross-thread step is the weight-gradient update
 //     dW_l[k][j] += sum over the tile's 128 trajectories and the jets of A_{l-1}[k] Pbar_l[j]

@@ -135,17 +135,17 @@ def test_golden_vectors_reference_semantics(path):
     assert np.abs(y1.cpu().numpy()[:bs, :3] - g["y1"][:bs, :3]).max() < 1e-4
 
 
-def _synthetic_field(Na, nt, seed):
+def _synthetic_field(Na, nt, seed, feats=(64, 64)):
     """Random geometry with ``Na`` nuclei of ``nt`` species (not a reference molecule: exercises the kernel limits)."""
     rng = np.random.default_rng(seed)
     coords = 2.5 * rng.standard_normal((Na, 3))
     onehot = np.zeros((Na, nt)); onehot[np.arange(Na), rng.integers(0, nt, Na)] = 1.0
-    p = O.init_params(rng, 2 + nt, (64, 64), 1, last_scale=0.5 * min(1.0, 3.0 / Na))
+    p = O.init_params(rng, 2 + nt, feats, 1, last_scale=0.5 * min(1.0, 3.0 / Na))
     for w, b in p.hidden:
         b[:] = 0.1 * rng.standard_normal(b.shape)
     p.last[1][:] = 0.05
     theta = O.flatten_params(p).astype(np.float32).astype(np.float64)
-    fld = O.GNNField(O.unflatten_params(theta, 2 + nt, (64, 64)), coords, onehot, bool_neg=True)
+    fld = O.GNNField(O.unflatten_params(theta, 2 + nt, feats), coords, onehot, bool_neg=True)
     return coords, onehot, theta, fld
 
 
@@ -183,6 +183,43 @@ def test_edge_shapes_forward_and_adjoint_match_oracle(Na, nt, B, n_a, n_steps):
         yb0 = yb0.cpu().numpy()
         assert rel(yb0[:n_a], ybar0_ref[:n_a]) <= G_TOL if n_a else True
         assert rel(yb0[n_a:, :3], ybar0_ref[n_a:, :3]) <= G_TOL if n_a < B else True
+
+
+@pytest.mark.parametrize("n_layers,path", [(3, ops.PATH_DEFAULT), (3, ops.PATH_FFMA), (1, ops.PATH_DEFAULT), (2, ops.PATH_DEEP)])
+@pytest.mark.parametrize("Na,nt,B,n_a,n_steps,jets_a", [(1, 1, 1, 1, 1, 3), (3, 2, 130, 129, 2, 3), (16, 4, 257, 0, 1, 3), (74, 3, 70, 40, 1, 3),
+                                                        (4, 2, 200, 77, 2, 2)])
+def test_edge_shapes_other_depths_match_oracle(n_layers, path, Na, nt, B, n_a, n_steps, jets_a):
+    """The edge shapes above for the --nn 1 / --nn 3 networks (OFDFT_NF.py:320-326) on both kernel families of depth 3 (tensor
+    cores: gnn_deep_tc.cu; FP32: gnn_general.cu) and, as a cross-check, the depth-generic tensor-core kernels on (64, 64):
+    forward states, one RHS evaluation and the discrete adjoint against the float64 oracle with the same scheme; one case
+    carries (x, logp) only in its first segment (neural_ode, jax_ode.py:9-49)."""
+    feats = (64,) * n_layers
+    coords, onehot, theta, fld = _synthetic_field(Na, nt, 23 + Na + B, feats)
+    rng = np.random.default_rng(6)
+    y0 = np.concatenate([coords[rng.integers(0, Na, B)] + rng.standard_normal((B, 3)), rng.standard_normal((B, 4))], 1)
+    y0 = y0.astype(np.float32).astype(np.float64)
+    ybar1 = rng.standard_normal((B, 7))
+    ybar1[n_a:, 3:] = 0.0                      # rows of the x-only segment have no logp / score cotangent
+    if jets_a == 2:
+        ybar1[:, 4:] = 0.0                     # no score channel anywhere
+    score = jets_a == 3
+    nc = 7 if score else 4
+    fn = lambda y, t: fld.rhs(t, y, score)
+    ref, stages = O.odeint_rk4(fn, y0[:, :nc], 0.0, 1.0, n_steps, keep=True)
+    ybar0_ref, g_ref = O.rk4_adjoint(fld, stages, 0.0, 1.0, ybar1[:, :nc], score)
+    th, nuc, oh = dev(theta), dev(coords), dev(onehot)
+    y1, ck = ops.gnn_fwd(th, nuc, oh, dev(y0), n_a, jets_a, 1, n_steps, 0.0, 1.0, -1.0, want_ckpt=True, path=path)
+    y1 = y1.cpu().numpy()
+    assert np.abs(y1[:n_a, :nc] - ref[:n_a]).max(initial=0.0) < 5e-6 * max(1.0, np.abs(ref).max())
+    assert np.abs(y1[n_a:, :3] - ref[n_a:, :3]).max(initial=0.0) < 5e-6 * max(1.0, np.abs(ref).max())
+    g, yb0 = ops.gnn_bwd(th, nuc, oh, ck, dev(ybar1), n_a, jets_a, 1, n_steps, 0.0, 1.0, -1.0, want_ybar0=True, path=path)
+    assert rel(g.cpu().numpy(), g_ref) <= G_TOL, rel(g.cpu().numpy(), g_ref)
+    yb0 = yb0.cpu().numpy()
+    assert rel(yb0[:n_a, :nc], ybar0_ref[:n_a]) <= G_TOL if n_a else True
+    assert rel(yb0[n_a:, :3], ybar0_ref[n_a:, :3]) <= G_TOL if n_a < B else True
+    dy = ops.gnn_rhs(th, nuc, oh, dev(y0), jets_a, 0.37, -1.0, path=path).cpu().numpy()
+    dref = fld.rhs(0.37, y0[:, :nc], score)
+    assert np.abs(dy[:, :nc] - dref).max() < 2e-5 * max(1.0, np.abs(dref).max())
 
 
 def test_error_behaviour_of_the_c_abi():
