@@ -85,7 +85,8 @@ def measure_traffic(args, kernel_label: str):
     (two steps) in a child process under ncu and reads the second launch.  Returns None when ncu is not usable."""
     import csv, io, re, shutil, subprocess
     ncu = shutil.which("ncu") or ("/usr/local/cuda/bin/ncu" if os.path.exists("/usr/local/cuda/bin/ncu") else None)
-    if ncu is None:
+    # not when this process is itself being profiled (ncu exports its injection settings to the processes it launches)
+    if ncu is None or any(k in os.environ for k in ("NV_NSIGHT_INJECTION_PORT_BASE", "NV_TPS_LAUNCH_TOKEN", "CUDA_INJECTION64_PATH")):
         return None
     name = re.split(r"[<\s+]", kernel_label.strip())[0]        # "gnn_bwd_tc_kernel<recompute>" -> gnn_bwd_tc_kernel
     child = [sys.executable, os.path.abspath(__file__), "--traffic-child", "--workload", args.workload, "--n-steps", str(args.n_steps),
