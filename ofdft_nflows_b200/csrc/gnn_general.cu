@@ -29,6 +29,11 @@ __device__ __forceinline__ float tanh_g(float x) {
 #endif
 }
 
+struct SmemGenF {                    // forward: the tables only (5 KB: the CTAs per SM are not limited by shared memory)
+  NucTables T;
+  int tile;
+};
+
 struct SmemGen {
   NucTables T;
   float uA[kGT * kRow];
@@ -96,6 +101,23 @@ __device__ void mlp_forward(const float* __restrict__ theta, const GnnThetaLayou
   }
 }
 
+// one hidden layer: f = b3 + w3 . tanh-jet(first layer) unit by unit -- nothing is stored (the layer arrays of mlp_forward live
+// in local memory, and with no GEMM to feed that traffic is all the kernel would do)
+template <int NJ>
+__device__ void mlp_forward_1(const float* __restrict__ theta, const GnnThetaLayoutL& TL, const float* __restrict__ cbi, float r,
+                              float tprime, float (&f)[3]) {
+  f[0] = __ldg(theta + TL.b3); f[1] = 0.f; f[2] = 0.f;
+#pragma unroll 8
+  for (int k = 0; k < kH; ++k) {          // unrolled: eight independent tanh chains in flight per thread
+    const float wt = __ldg(theta + TL.W[0] + k), wr = __ldg(theta + TL.W[0] + kH + k), w = __ldg(theta + TL.w3 + k);
+    const float a = tanh_g(fmaf(wr, r, fmaf(tprime, wt, cbi[k])));
+    const float a1 = fmaf(-a, a, 1.0f) * wr;
+    f[0] = fmaf(w, a, f[0]);
+    if (NJ >= 2) f[1] = fmaf(w, a1, f[1]);
+    if (NJ == 3) f[2] = fmaf(w, -2.0f * a * a1 * wr, f[2]);
+  }
+}
+
 // explicit (geometry) part of one nucleus' contribution to d/dt (x, logp, s)   [same formulas as combine() in gnn.cu]
 template <int NJ>
 __device__ __forceinline__ void combine_nucleus(const float (&f)[3], const float* nc, const float (&xst)[3], const float (&sst)[3],
@@ -116,7 +138,7 @@ __device__ __forceinline__ void combine_nucleus(const float (&f)[3], const float
 }
 
 template <int L, int NJ>
-__device__ void gen_fwd_tile(SmemGen& sm, const GnnFwdArgs& a, const GnnThetaLayoutL& TL, long long row0, long long seg_end) {
+__device__ void gen_fwd_tile(SmemGenF& sm, const GnnFwdArgs& a, const GnnThetaLayoutL& TL, long long row0, long long seg_end) {
   const int tid = threadIdx.x;
   const long long row = row0 + tid;
   const bool valid = row < seg_end;
@@ -130,7 +152,6 @@ __device__ void gen_fwd_tile(SmemGen& sm, const GnnFwdArgs& a, const GnnThetaLay
   }
   const int n_steps = a.rhs_only ? 1 : a.n_steps;
   const float h = (a.t1 - a.t0) / (float)a.n_steps;
-  LayerJets<L> S;
   for (int step = 0; step < n_steps; ++step) {
     for (int stage = 0; stage < (a.rhs_only ? 1 : 4); ++stage) {
       const float cs = stage == 0 ? 0.f : (stage == 3 ? h : 0.5f * h);
@@ -154,7 +175,12 @@ __device__ void gen_fwd_tile(SmemGen& sm, const GnnFwdArgs& a, const GnnThetaLay
         const float d0 = xst[0] - nc[0], d1 = xst[1] - nc[1], d2 = xst[2] - nc[2];
         const float r = sqrtf(fmaf(d0, d0, fmaf(d1, d1, d2 * d2)));
         float f[3];
-        mlp_forward<L, NJ>(a.theta, TL, sm.T.cb + sm.T.cls[i] * kH, r, tprime, S, f);
+        if constexpr (L == 1) {
+          mlp_forward_1<NJ>(a.theta, TL, sm.T.cb + sm.T.cls[i] * kH, r, tprime, f);
+        } else {
+          LayerJets<L> S;
+          mlp_forward<L, NJ>(a.theta, TL, sm.T.cb + sm.T.cls[i] * kH, r, tprime, S, f);
+        }
         combine_nucleus<NJ>(f, nc, xst, sst, g, dv, ds);
       }
       const float wgt = (stage == 0 || stage == 3) ? 1.0f : 2.0f;
@@ -178,7 +204,7 @@ __device__ void gen_fwd_tile(SmemGen& sm, const GnnFwdArgs& a, const GnnThetaLay
 template <int L>
 __global__ void __launch_bounds__(kGT) gnn_general_fwd_kernel(const GnnFwdArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  SmemGen& sm = *reinterpret_cast<SmemGen*>(smem_raw);
+  SmemGenF& sm = *reinterpret_cast<SmemGenF*>(smem_raw);
   const GnnThetaLayoutL TL(a.n_types, L);
   const GnnThetaLayout L2(a.n_types);       // b1 / W1 offsets do not depend on the depth
   load_nuc_tables<kGT>(sm.T, a.theta, L2, a.nuclei, a.onehot, a.Na, a.n_types);
@@ -237,8 +263,6 @@ __device__ void gen_bwd_tile(SmemGen& sm, const GnnBwdArgs& a, const GnnThetaLay
   }
   const float h = (a.t1 - a.t0) / (float)a.n_steps;
   float prevx[3] = {0, 0, 0}, prevs[3] = {0, 0, 0};
-  LayerJets<L> S;
-  float cot[3][kH], nxt[3][kH];
   for (int step = a.n_steps - 1; step >= 0; --step) {
     float sumx[3] = {0, 0, 0}, sums[3] = {0, 0, 0};
     for (int stage = 3; stage >= 0; --stage) {
@@ -264,7 +288,6 @@ __device__ void gen_bwd_tile(SmemGen& sm, const GnnBwdArgs& a, const GnnThetaLay
         const float r = sqrtf(fmaf(d0, d0, fmaf(d1, d1, d2 * d2)));
         const float rinv = 1.0f / r;
         float f[3];
-        mlp_forward<L, NJ>(a.theta, TL, sm.T.cb + cls * kH, r, tprime, S, f);
         // cotangents of (f, f', f'')   [pre() of gnn.cu]
         float fb[3] = {0.f, 0.f, 0.f};
         float q = 0.f, gam = 0.f;
@@ -288,94 +311,134 @@ __device__ void gen_bwd_tile(SmemGen& sm, const GnnBwdArgs& a, const GnnThetaLay
         }
         G.b3 += fb[0];
         __syncthreads();                                       // the previous evaluation's column sums have been read
-        // last layer: f = b3 + w3 . a_{L-1}
-        for (int j = 0; j < kH; ++j) {
-          const float w = __ldg(a.theta + TL.w3 + j);
-          float gw = S.J[L - 1][0][j] * fb[0];
-          cot[0][j] = w * fb[0];
-          if (NJ >= 2) { gw = fmaf(S.J[L - 1][1][j], fb[1], gw); cot[1][j] = w * fb[1]; }
-          if (NJ == 3) { gw = fmaf(S.J[L - 1][2][j], fb[2], gw); cot[2][j] = w * fb[2]; }
-          sm.wQ[tid * kRow + j] = gw;
-        }
-        // hidden layers L-1 .. 1: reverse of the tanh jet, weight gradient, transposed mat-vec
-        for (int l = L - 1; l >= 1; --l) {
-          for (int j = 0; j < kH; ++j) {
-            const float aa = S.J[l][0][j];
-            const float sg = fmaf(-aa, aa, 1.0f);
-            float pzb = cot[0][j];
-            if (NJ >= 2) {
-              const float p1 = S.Pd[l][0][j];
-              const float a1b = cot[1][j];
-              pzb = fmaf(-2.0f * aa * p1, a1b, pzb);
-              float t1 = a1b;
-              if (NJ == 3) {
-                const float p2 = S.Pd[l][1][j];
-                const float a2b = cot[2][j];
-                cot[2][j] = a2b * sg;
-                t1 = fmaf(-4.0f * aa * p1, a2b, t1);
-                pzb = fmaf(a2b, fmaf(-2.0f * aa, p2, -2.0f * fmaf(-3.0f * aa, aa, 1.0f) * p1 * p1), pzb);
-              }
-              cot[1][j] = sg * t1;
-            }
-            cot[0][j] = sg * pzb;
-          }
-          // dW_l[k][j] += sum over the tile's trajectories and jets of J[l-1][jet][k] * cot[jet][j]
-          for (int jt = 0; jt < NJ; ++jt) {
-            __syncthreads();
-            for (int u = 0; u < kH; ++u) { sm.uA[tid * kRow + u] = S.J[l - 1][jt][u]; sm.vP[tid * kRow + u] = cot[jt][u]; }
-            __syncthreads();
-            float bsum = 0.f;
-            for (int t = 0; t < kGT; ++t) {
-              const float v = sm.vP[t * kRow + jcol];
-              const float* ua = sm.uA + t * kRow + 32 * kh;
-#pragma unroll
-              for (int kk = 0; kk < 32; ++kk) D.v[l][kk] = fmaf(ua[kk], v, D.v[l][kk]);
-              if ((t >> 6) == kh) bsum += v;                   // jet 0 of the cotangent is the bias gradient of layer l
-            }
-            if (jt == 0) G.bl[l] += bsum;
-          }
-          // cotangent jets of layer l-1: nxt[jet][k] = sum_j cot[jet][j] W_l[k][j]
-          const float* __restrict__ W = a.theta + TL.W[l];
-          for (int k0 = 0; k0 < kH; k0 += 8) {
-            float acc[3][8];
-#pragma unroll
-            for (int qq = 0; qq < 8; ++qq) { acc[0][qq] = 0.f; acc[1][qq] = 0.f; acc[2][qq] = 0.f; }
-            for (int j = 0; j < kH; ++j) {
-              const float c0 = cot[0][j], c1 = NJ >= 2 ? cot[1][j] : 0.f, c2 = NJ == 3 ? cot[2][j] : 0.f;
-#pragma unroll
-              for (int qq = 0; qq < 8; ++qq) {
-                const float w = __ldg(W + (k0 + qq) * kH + j);
-                acc[0][qq] = fmaf(c0, w, acc[0][qq]);
-                if (NJ >= 2) acc[1][qq] = fmaf(c1, w, acc[1][qq]);
-                if (NJ == 3) acc[2][qq] = fmaf(c2, w, acc[2][qq]);
-              }
-            }
-#pragma unroll
-            for (int qq = 0; qq < 8; ++qq) { nxt[0][k0 + qq] = acc[0][qq]; nxt[1][k0 + qq] = acc[1][qq]; nxt[2][k0 + qq] = acc[2][qq]; }
-          }
-          for (int jt = 0; jt < NJ; ++jt)
-            for (int k = 0; k < kH; ++k) cot[jt][k] = nxt[jt][k];
-        }
-        // first layer reverse   [epilogue_b1 of gnn.cu]
         float rbar = 0.f;
-        if (L > 1) __syncthreads();                            // the weight-gradient pass above has read uA / vP
-        for (int k = 0; k < kH; ++k) {
-          const float aa = S.J[0][0][k];
-          const float wv = __ldg(a.theta + TL.W[0] + kH + k);
-          const float sg = fmaf(-aa, aa, 1.0f);
-          float t = cot[0][k], e = 0.f;
-          if (NJ >= 2) {
-            t = fmaf(-2.0f * aa * wv, cot[1][k], t);
-            e = cot[1][k];
-            if (NJ == 3) {
-              t = fmaf(-2.0f * wv * wv * fmaf(-3.0f * aa, aa, 1.0f), cot[2][k], t);
-              e = fmaf(-4.0f * aa * wv, cot[2][k], e);
+        if constexpr (L == 1) {
+          // one hidden layer: forward jet, last-layer gradient term and first-layer reverse unit by unit, nothing stored per thread
+          const float* cbi = sm.T.cb + cls * kH;
+          f[0] = __ldg(a.theta + TL.b3); f[1] = 0.f; f[2] = 0.f;
+#pragma unroll 8
+          for (int k = 0; k < kH; ++k) {
+            const float wt = __ldg(a.theta + TL.W[0] + k), wv = __ldg(a.theta + TL.W[0] + kH + k), w = __ldg(a.theta + TL.w3 + k);
+            const float aa = tanh_g(fmaf(wv, r, fmaf(tprime, wt, cbi[k])));
+            const float sg = fmaf(-aa, aa, 1.0f);
+            const float a1 = sg * wv;
+            const float a2 = -2.0f * aa * a1 * wv;
+            f[0] = fmaf(w, aa, f[0]);
+            float gw = aa * fb[0];
+            float t = w * fb[0], e = 0.f;
+            if (NJ >= 2) {
+              f[1] = fmaf(w, a1, f[1]);
+              gw = fmaf(a1, fb[1], gw);
+              const float c1 = w * fb[1];
+              t = fmaf(-2.0f * aa * wv, c1, t);
+              e = c1;
+              if (NJ == 3) {
+                f[2] = fmaf(w, a2, f[2]);
+                gw = fmaf(a2, fb[2], gw);
+                const float c2 = w * fb[2];
+                t = fmaf(-2.0f * wv * wv * fmaf(-3.0f * aa, aa, 1.0f), c2, t);
+                e = fmaf(-4.0f * aa * wv, c2, e);
+              }
             }
+            const float pb = sg * t;
+            rbar = fmaf(pb, wv, rbar);
+            sm.wQ[tid * kRow + k] = gw;
+            sm.uA[tid * kRow + k] = pb;
+            sm.vP[tid * kRow + k] = fmaf(pb, r, sg * e);
           }
-          const float pb = sg * t;
-          rbar = fmaf(pb, wv, rbar);
-          sm.uA[tid * kRow + k] = pb;
-          sm.vP[tid * kRow + k] = fmaf(pb, r, sg * e);
+        } else {
+          LayerJets<L> S;
+          float cot[3][kH], nxt[3][kH];
+          mlp_forward<L, NJ>(a.theta, TL, sm.T.cb + cls * kH, r, tprime, S, f);
+          // last layer: f = b3 + w3 . a_{L-1}
+          for (int j = 0; j < kH; ++j) {
+            const float w = __ldg(a.theta + TL.w3 + j);
+            float gw = S.J[L - 1][0][j] * fb[0];
+            cot[0][j] = w * fb[0];
+            if (NJ >= 2) { gw = fmaf(S.J[L - 1][1][j], fb[1], gw); cot[1][j] = w * fb[1]; }
+            if (NJ == 3) { gw = fmaf(S.J[L - 1][2][j], fb[2], gw); cot[2][j] = w * fb[2]; }
+            sm.wQ[tid * kRow + j] = gw;
+          }
+          // hidden layers L-1 .. 1: reverse of the tanh jet, weight gradient, transposed mat-vec
+          for (int l = L - 1; l >= 1; --l) {
+            for (int j = 0; j < kH; ++j) {
+              const float aa = S.J[l][0][j];
+              const float sg = fmaf(-aa, aa, 1.0f);
+              float pzb = cot[0][j];
+              if (NJ >= 2) {
+                const float p1 = S.Pd[l][0][j];
+                const float a1b = cot[1][j];
+                pzb = fmaf(-2.0f * aa * p1, a1b, pzb);
+                float t1 = a1b;
+                if (NJ == 3) {
+                  const float p2 = S.Pd[l][1][j];
+                  const float a2b = cot[2][j];
+                  cot[2][j] = a2b * sg;
+                  t1 = fmaf(-4.0f * aa * p1, a2b, t1);
+                  pzb = fmaf(a2b, fmaf(-2.0f * aa, p2, -2.0f * fmaf(-3.0f * aa, aa, 1.0f) * p1 * p1), pzb);
+                }
+                cot[1][j] = sg * t1;
+              }
+              cot[0][j] = sg * pzb;
+            }
+            // dW_l[k][j] += sum over the tile's trajectories and jets of J[l-1][jet][k] * cot[jet][j]
+            for (int jt = 0; jt < NJ; ++jt) {
+              __syncthreads();
+              for (int u = 0; u < kH; ++u) { sm.uA[tid * kRow + u] = S.J[l - 1][jt][u]; sm.vP[tid * kRow + u] = cot[jt][u]; }
+              __syncthreads();
+              float bsum = 0.f;
+              for (int t = 0; t < kGT; ++t) {
+                const float v = sm.vP[t * kRow + jcol];
+                const float* ua = sm.uA + t * kRow + 32 * kh;
+#pragma unroll
+                for (int kk = 0; kk < 32; ++kk) D.v[l][kk] = fmaf(ua[kk], v, D.v[l][kk]);
+                if ((t >> 6) == kh) bsum += v;                   // jet 0 of the cotangent is the bias gradient of layer l
+              }
+              if (jt == 0) G.bl[l] += bsum;
+            }
+            // cotangent jets of layer l-1: nxt[jet][k] = sum_j cot[jet][j] W_l[k][j]
+            const float* __restrict__ W = a.theta + TL.W[l];
+            for (int k0 = 0; k0 < kH; k0 += 8) {
+              float acc[3][8];
+#pragma unroll
+              for (int qq = 0; qq < 8; ++qq) { acc[0][qq] = 0.f; acc[1][qq] = 0.f; acc[2][qq] = 0.f; }
+              for (int j = 0; j < kH; ++j) {
+                const float c0 = cot[0][j], c1 = NJ >= 2 ? cot[1][j] : 0.f, c2 = NJ == 3 ? cot[2][j] : 0.f;
+#pragma unroll
+                for (int qq = 0; qq < 8; ++qq) {
+                  const float w = __ldg(W + (k0 + qq) * kH + j);
+                  acc[0][qq] = fmaf(c0, w, acc[0][qq]);
+                  if (NJ >= 2) acc[1][qq] = fmaf(c1, w, acc[1][qq]);
+                  if (NJ == 3) acc[2][qq] = fmaf(c2, w, acc[2][qq]);
+                }
+              }
+#pragma unroll
+              for (int qq = 0; qq < 8; ++qq) { nxt[0][k0 + qq] = acc[0][qq]; nxt[1][k0 + qq] = acc[1][qq]; nxt[2][k0 + qq] = acc[2][qq]; }
+            }
+            for (int jt = 0; jt < NJ; ++jt)
+              for (int k = 0; k < kH; ++k) cot[jt][k] = nxt[jt][k];
+          }
+          // first layer reverse   [epilogue_b1 of gnn.cu]
+          rbar = 0.f;
+          if (L > 1) __syncthreads();                            // the weight-gradient pass above has read uA / vP
+          for (int k = 0; k < kH; ++k) {
+            const float aa = S.J[0][0][k];
+            const float wv = __ldg(a.theta + TL.W[0] + kH + k);
+            const float sg = fmaf(-aa, aa, 1.0f);
+            float t = cot[0][k], e = 0.f;
+            if (NJ >= 2) {
+              t = fmaf(-2.0f * aa * wv, cot[1][k], t);
+              e = cot[1][k];
+              if (NJ == 3) {
+                t = fmaf(-2.0f * wv * wv * fmaf(-3.0f * aa, aa, 1.0f), cot[2][k], t);
+                e = fmaf(-4.0f * aa * wv, cot[2][k], e);
+              }
+            }
+            const float pb = sg * t;
+            rbar = fmaf(pb, wv, rbar);
+            sm.uA[tid * kRow + k] = pb;
+            sm.vP[tid * kRow + k] = fmaf(pb, r, sg * e);
+          }
         }
         // column sums of this (nucleus, evaluation) over the thread's half of the tile rows
         __syncthreads();
@@ -514,11 +577,11 @@ int launch_gnn_general_fwd(void* stream, GnnFwdArgs& a, void* scratch, size_t sc
   const long long tiles = (a.n_a + kGT - 1) / kGT + (a.B - a.n_a + kGT - 1) / kGT;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int grid = (int)(tiles < 4LL * sms ? tiles : 4LL * sms);
+  const int grid = (int)(tiles < 8LL * sms ? tiles : 8LL * sms);
   auto kern = n_layers == 1 ? gnn_general_fwd_kernel<1> : gnn_general_fwd_kernel<3>;
-  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemGen));
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemGenF));
   if (e != cudaSuccess) return (int)e;
-  kern<<<grid, kGT, sizeof(SmemGen), st>>>(a);
+  kern<<<grid, kGT, sizeof(SmemGenF), st>>>(a);
   return (int)cudaGetLastError();
 }
 
