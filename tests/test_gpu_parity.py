@@ -904,6 +904,41 @@ def test_full_size_roundtrip_self_convergence_and_determinism():
     assert rel(gm.cpu().numpy(), g16.cpu().numpy()) < 1e-5
 
 
+def test_full_size_three_layer_network_properties():
+    """BASELINE.json's headline batch (H2O, bs = 65 536) with the --nn 3 network on the depth-generic tensor-core kernels:
+    zero-initialised last layer => identity flow and a gradient in the last layer only (bit-exact), rev o fwd = id, N vs 2N
+    self-convergence of the energy terms and the gradient, run-to-run bitwise determinism, sharding invariance."""
+    Ne, z, coords, oh, theta2, batch = _full_problem()
+    rng = np.random.default_rng(99)
+    theta = np.concatenate([theta2, np.zeros(64), (rng.standard_normal((64, 64)) / 8).ravel()]).astype(np.float32)
+    feats = (64, 64, 64)
+    model = Gen_EqvFlow(3, feats, coords, oh, bool_neg=True)
+    spec = ops.EnergySpec(Ne=Ne, d=3, kin="tf-w", hart="hartree", nuc="hgh", x="lda", coords=coords, z=z)
+    th, nuc, ohd, y = dev(theta), dev(coords), dev(oh), dev(batch)
+    B = y.shape[0]
+    theta0 = theta.copy(); theta0[:65] = 0.0
+    sums0, tbar0, y10 = EnergyEstimator(model, spec, n_steps=16, skip_unused_jets=False).step_flat(dev(theta0), y)
+    assert torch.equal(y10, y)
+    g0 = tbar0.cpu().numpy()
+    assert np.abs(g0[65:]).max() == 0.0 and np.abs(g0[:65]).max() > 0.0
+    y1 = ops.gnn_fwd(th, nuc, ohd, y[:, :4].contiguous(), B, 2, 2, 16, 0.0, 1.0, -1.0)[0]
+    y0 = ops.gnn_fwd(th, nuc, ohd, y1, B, 2, 2, 16, -1.0, 0.0, 1.0)[0]
+    assert (y0[:, :3] - y[:, :3]).abs().max().item() < 2e-5
+    assert ((y1[:, 3] - y[:, 3]) + (y0[:, 3] - y1[:, 3])).abs().max().item() < 2e-5
+    s16, g16, _ = EnergyEstimator(model, spec, n_steps=16).step_flat(th, y)
+    s32, g32, _ = EnergyEstimator(model, spec, n_steps=32).step_flat(th, y)
+    s16b, g16b, _ = EnergyEstimator(model, spec, n_steps=16).step_flat(th, y)
+    assert torch.equal(s16, s16b) and torch.equal(g16, g16b)
+    a, b = s16.cpu().numpy(), s32.cpu().numpy()
+    assert np.all(np.abs(a[:4] - b[:4]) <= E_TOL * np.abs(b[:4]))
+    assert rel(g16.cpu().numpy(), g32.cpu().numpy()) <= G_TOL
+    from ofdft_nflows_b200.estimator import shard_batch
+    est = EnergyEstimator(model, spec, n_steps=16)
+    parts = [est.step_flat(th, shard_batch(y, r, 2).contiguous()) for r in range(2)]
+    assert np.allclose(((parts[0][0] + parts[1][0]) / 2).cpu().numpy()[:6], a[:6], rtol=1e-9)
+    assert rel(((parts[0][1] + parts[1][1]) / 2).cpu().numpy(), g16.cpu().numpy()) < 1e-5
+
+
 def test_tensor_core_diagnostics():
     """The two diagnostic entry points of the ABI (they ship in the library, so the suite launches them): a 3xTF32 GEMM through
     shared-memory and tensor-memory operands against float64, and the tcgen05.mma timing probe DESIGN.md quotes."""
