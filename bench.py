@@ -102,7 +102,7 @@ def measure_traffic(args, kernel_label: str):
     for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
         env.pop(k, None)
     try:
-        out = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=env).stdout
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=150, env=env).stdout
         rows = [r for r in csv.reader(io.StringIO(out[out.index('"ID"'):]))]
         hdr = rows[0]
         tot, kern = 0.0, None
@@ -748,7 +748,9 @@ def main():
             #   forward  tc: 2 weight preps + (n+1) glue + n (L-1) layer GEMMs          | ffma: prep + fused kernel
             #   adjoint  tc: 2 preps + (n+1) tail + n head + 2 n (L-1) layer GEMMs      | ffma: prep + fused sweep
             #   both: functionals x2, small-gradient reduce, (L-1) x (weight-gradient GEMM + reduce)
-            "gpu_launches": (5 if not is_1d else _launches_1d(4 * args.n_steps, len(MLP_FEAT), args.ffma, not args.recompute)) * args.steps,
+            # (--nn 3 and the tensor-core recompute mode add the weight-split kernel in front of the backward)
+            "gpu_launches": ((5 + (1 if (tensor_path and (args.nn == 3 or args.recompute)) else 0)) if not is_1d
+                             else _launches_1d(4 * args.n_steps, len(MLP_FEAT), args.ffma, not args.recompute)) * args.steps,
             "roofline": roofline,
             "energy_terms_last_step": [float(v) for v in sums.cpu().numpy()[:6]],
             "hartree": ({"mode": "paired"} if args.hartree == "paired" else
