@@ -56,6 +56,21 @@ def test_size_helpers():
     assert lib.ofdft_hartree_allpairs_scratch_bytes(1000, 777) > 0
 
 
+def test_path_selectors_of_the_python_mirror_match_the_header():
+    """ops.PATH_* / JETS_* are the OFDFT_PATH_* / OFDFT_JETS_* values of include/ofdft_b200.h (the kernel path is an argument of
+    the ABI, not an environment variable); the bwd scratch holds the prepared weight operands of the depth-generic kernels."""
+    from ofdft_nflows_b200 import ops
+    src = open(HEADER).read()
+    defs = {k: int(v) for k, v in re.findall(r"#define\s+(OFDFT_(?:PATH|JETS)_\w+)\s+(\d+)", src)}
+    assert defs["OFDFT_PATH_DEFAULT"] == ops.PATH_DEFAULT and defs["OFDFT_PATH_FFMA"] == ops.PATH_FFMA
+    assert defs["OFDFT_PATH_FFMA_DW"] == ops.PATH_FFMA_DW and defs["OFDFT_PATH_ACT_CKPT"] == ops.PATH_ACT_CKPT
+    assert defs["OFDFT_PATH_DEEP"] == ops.PATH_DEEP == 8
+    assert (defs["OFDFT_JETS_X"], defs["OFDFT_JETS_XLOGP"], defs["OFDFT_JETS_FULL"]) == (ops.JETS_X, ops.JETS_XLOGP, ops.JETS_FULL)
+    lib = _lib.load()
+    n3 = lib.ofdft_cnf_gnn_theta_size(3, 3)
+    assert lib.ofdft_cnf_gnn_bwd_scratch_bytes(256, 128, 3, 3) >= 2 * n3 * 4 + 2 * 4 * 64 * 64 * 4     # 2 tiles + [layer][4][64 x 64]
+
+
 def test_argument_validation_without_device():
     lib = _lib.load()
     # null pointers / bad sizes are rejected before any CUDA call
