@@ -89,7 +89,7 @@ def gnn_fwd(theta, nuclei, onehot, y_in, n_a: int, jets_a: int, jets_b: int, n_s
     if want_ckpt:
         ckpt = torch.empty(lib.ofdft_cnf_gnn_ckpt_bytes(B, n_steps) // 4, dtype=torch.float32, device=y_in.device)
     act = None
-    if want_ckpt and want_act and L == 2:
+    if want_ckpt and want_act and L == 2 and not (int(path) & PATH_DEEP):      # the depth-generic kernels keep no activation checkpoint
         nb = lib.ofdft_cnf_gnn_act_ckpt_bytes(B, n_a, jets_a, jets_b, Na, n_steps)
         act = torch.empty(nb // 4, dtype=torch.float32, device=y_in.device)
     sb = lib.ofdft_cnf_gnn_fwd_scratch_bytes()
