@@ -321,9 +321,53 @@ __device__ void deep_fwd_tile(SmemDeepF& sm, const GnnFwdArgs& a, long long row0
             deep_stage_A(jt == 0 ? J0 : (jt == 1 ? J1 : J2), tlane + kDFColAhi + kH * buf + 32 * uh, sm.Alo + buf * kH * kTP, uh, m);
             deep_sync_issue_gemm(tmem + jt * kH, tmem + kDFColAhi + kH * buf, dAlo[buf], dWh, dWl, idesc, &sm.bar[buf]);
           }
+          const float* bl = sm.bl + (l - 1) * kH + 32 * uh;
+          if constexpr (NJ == 3) {
+            // jet 0 has completed (its barrier was waited for in front of the staging of jet 2): the tanh of the layer runs
+            // under the MMAs of jets 1 and 2, the derivative jets follow as their accumulators complete
+#pragma unroll
+            for (int c0 = 0; c0 < 32; c0 += 16) {
+              float p0[16];
+              tc::tmem_ld16(tlane + 32 * uh + c0, p0);
+              tc::tmem_ld_wait();
+#pragma unroll
+              for (int u = 0; u < 16; u += 2)
+                tc::unpack2(deep_tanh2(tc::add2(tc::pack2(p0[u], p0[u + 1]), ld2(bl + c0 + u))), J0[c0 + u], J0[c0 + u + 1]);
+            }
+            deep_wait(sm.bar, phase, 1);
+#pragma unroll
+            for (int c0 = 0; c0 < 32; c0 += 16) {
+              float p1[16];
+              tc::tmem_ld16(tlane + kH + 32 * uh + c0, p1);
+              tc::tmem_ld_wait();
+#pragma unroll
+              for (int u = 0; u < 16; u += 2) {
+                using namespace tc;
+                const f32x2 aa = pack2(J0[c0 + u], J0[c0 + u + 1]);
+                unpack2(mul2(fma2(mul2(aa, splat2(-1.0f)), aa, splat2(1.0f)), pack2(p1[u], p1[u + 1])), J1[c0 + u], J1[c0 + u + 1]);
+              }
+            }
+            deep_wait(sm.bar, phase, 0);
+#pragma unroll
+            for (int c0 = 0; c0 < 32; c0 += 16) {
+              float p1[16], p2[16];
+              tc::tmem_ld16(tlane + kH + 32 * uh + c0, p1);
+              tc::tmem_ld16(tlane + 2 * kH + 32 * uh + c0, p2);
+              tc::tmem_ld_wait();
+#pragma unroll
+              for (int u = 0; u < 16; u += 2) {
+                using namespace tc;
+                const f32x2 aa = pack2(J0[c0 + u], J0[c0 + u + 1]);
+                const f32x2 naa = mul2(aa, splat2(-1.0f));
+                const f32x2 sg = fma2(naa, aa, splat2(1.0f));
+                const f32x2 a1 = pack2(J1[c0 + u], J1[c0 + u + 1]);
+                // sg p2 - 2 a a1 p1
+                unpack2(fma2(sg, pack2(p2[u], p2[u + 1]), mul2(mul2(mul2(naa, splat2(2.0f)), a1), pack2(p1[u], p1[u + 1]))), J2[c0 + u], J2[c0 + u + 1]);
+              }
+            }
+          } else {
 #pragma unroll
           for (int jt = (NJ >= 2 ? NJ - 2 : 0); jt < NJ; ++jt) deep_wait(sm.bar, phase, jt & 1);
-          const float* bl = sm.bl + (l - 1) * kH + 32 * uh;
 #pragma unroll
           for (int c0 = 0; c0 < 32; c0 += 16) {
             float p0[16], p1[16], p2[16];
@@ -346,6 +390,7 @@ __device__ void deep_fwd_tile(SmemDeepF& sm, const GnnFwdArgs& a, long long row0
                   unpack2(fma2(sg, pack2(p2[u], p2[u + 1]), mul2(mul2(mul2(naa, splat2(2.0f)), a1), q1)), J2[c0 + u], J2[c0 + u + 1]);
               }
             }
+          }
           }
         }
         {
@@ -633,8 +678,11 @@ __device__ void deep_bwd_tile(SmemDeepB& sm, const GnnBwdArgs& a, long long row0
             deep_sync_issue_gemm(tmem + dcol_state(l) + jt * kH, tmem + kDColDw + kH * buf, dAlo[buf], dWh[wb], dWl[wb], idesc, &sm.bar[buf]);
           }
           wb ^= 1;
+          // three jets: jet 0 has completed (waited for in front of the staging of jet 2), its tanh runs under the MMAs of jets 1, 2
+          if (NJ < 3) {
 #pragma unroll
-          for (int jt = (NJ >= 2 ? NJ - 2 : 0); jt < NJ; ++jt) deep_wait(sm.bar, phase, jt & 1);
+            for (int jt = (NJ >= 2 ? NJ - 2 : 0); jt < NJ; ++jt) deep_wait(sm.bar, phase, jt & 1);
+          }
           // P -> a = tanh(P + b_l) in place (the derivative jets stay as they are)
           const float* bl = sm.bl + (l - 1) * kH + 32 * uh;
 #pragma unroll
@@ -647,6 +695,7 @@ __device__ void deep_bwd_tile(SmemDeepB& sm, const GnnBwdArgs& a, long long row0
             tc::tmem_st16(tlane + dcol_state(l) + 32 * uh + c0, p0);
           }
           tc::tmem_st_wait();
+          if (NJ == 3) { deep_wait(sm.bar, phase, 1); deep_wait(sm.bar, phase, 0); }
         }
         // ---------------- last layer and the reverse of the top hidden layer ----------------
         float q0[32], q1[32], q2[32];
