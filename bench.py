@@ -692,7 +692,7 @@ def main():
     # counters, one pass, the second launch of the kernel); outside the timed region, never a timing.  Where ncu or the
     # counters are unavailable the figure falls back to the committed `ncu --set full` capture of the default workload.
     measured = None
-    if rank == 0 and world == 1 and not args.no_traffic_probe:
+    if rank == 0 and world == 1 and not args.no_traffic_probe and not is_1d:     # (1-D: the roofline is a chain of launches, not one kernel)
         measured = measure_traffic(args, roofline["kernel"])
     if measured is not None:
         roofline["traffic"] = measured["bytes"]
