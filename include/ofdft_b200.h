@@ -147,8 +147,8 @@ int ofdft_cnf_gnn_fwd(void* stream, const float* theta, const float* nuclei, con
  *   ybar1     : (B, bar_stride) cotangent of y(t1), rows [xbar | logpbar | sbar]
  *   theta_bar : n_theta floats, OVERWRITTEN with d<ybar1, y(t1)>/d theta
  *   ybar0     : NULL or (B, bar_stride) cotangent of y(t0)
- *   scratch   : ofdft_cnf_gnn_bwd_scratch_bytes(B, n_a, n_types, n_layers) bytes (one partial gradient per 128-row tile,
- *               reduced in fixed order: theta_bar is bitwise reproducible)
+ *   scratch   : ofdft_cnf_gnn_bwd_scratch_bytes(B, n_a, n_types, n_layers) bytes (tile counter, 128 KB of prepared hi / lo weight
+ *               operands, one partial gradient per 128-row tile reduced in fixed order: theta_bar is bitwise reproducible)
  */
 size_t ofdft_cnf_gnn_bwd_scratch_bytes(int64_t B, int64_t n_a, int32_t n_types, int32_t n_layers);
 int ofdft_cnf_gnn_bwd(void* stream, const float* theta, const float* nuclei, const float* onehot,

@@ -18,7 +18,9 @@ struct GnnBwdArgs {
   long long B, n_a; int jets_a, jets_b; int bar_stride;
   int Na, n_types, n_steps; float t0, t1, y0;
   const float* act; long long act_rows_a, act_rows_b;
-  float* w2split;   // 2 x 4096 floats of caller scratch: W2 hi | lo in the forward GEMM orientation (tensor-core recompute mode)
+  float* w2split;   // kDeepWSplitBytes of caller scratch for prepared weight operands: W2 hi | lo in the forward GEMM orientation
+                    // (tensor-core recompute mode of gnn_tc.cu: the first 2 x 4096 floats) or [layer][fwd hi | fwd lo | transposed hi |
+                    // transposed lo] (gnn_deep_tc.cu)
 };
 
 // theta offsets for L hidden layers (key-sorted ravel_pytree order; L = 2 reproduces GnnThetaLayout)
