@@ -70,17 +70,20 @@ static_assert(sizeof(SmemDeepB) + 1024 <= 227 * 1024, "backward tile state excee
 // is its parity; every commit is followed by exactly one wait of all threads); a wait that lasts seconds is a protocol bug:
 // trap instead of hanging the device
 __device__ __forceinline__ void deep_wait(uint64_t* bars, uint32_t& phase, int b) {
-  uint64_t* bar = bars + b;
-  uint32_t done = 0;
-  const uint32_t addr = tc::smem_u32(bar);
-  const long long t0 = clock64();
-  while (!done) {
+  const uint32_t addr = tc::smem_u32(bars + b), par = (phase >> b) & 1u;
+  auto probe = [&]() {
+    uint32_t done;
     asm volatile(
         "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
         : "=r"(done)
-        : "r"(addr), "r"((phase >> b) & 1u)
+        : "r"(addr), "r"(par)
         : "memory");
-    if (!done && clock64() - t0 > 8000000000ll) __trap();
+    return done != 0;
+  };
+  if (!probe()) {                                   // the clock is only read when the batch has not completed yet
+    const long long t0 = clock64();
+    while (!probe())
+      if (clock64() - t0 > 8000000000ll) __trap();
   }
   phase ^= 1u << b;
   __syncwarp();
